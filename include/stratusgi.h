@@ -1,0 +1,228 @@
+/*
+ * stratusgi.h — C-ABI of the B200-native VPL global-illumination pass.
+ *
+ * This is the drop-in boundary for the three private RendererBackend methods of
+ * StratusGFX that make up its real-time GI hot path (reference paths relative to
+ * the StratusGFX tree):
+ *
+ *   PerformVirtualPointLightCullingStage1_      Source/Engine/StratusRendererBackend.cpp:1578-1612
+ *   PerformVirtualPointLightCullingStage2_      Source/Engine/StratusRendererBackend.cpp:1666-1731 (+ dormant 1733-1783)
+ *   ComputeVirtualPointLightGlobalIllumination_ Source/Engine/StratusRendererBackend.cpp:1816-1952
+ *
+ * Everything is `extern "C"`, plain pointers and sizes, status returned as int
+ * (0 = OK).  No C++ exception crosses the boundary and there is NO CPU fallback:
+ * if no CUDA device is usable every entry point returns SGI_ERR_CUDA.
+ *
+ * Threading: one thread per handle, stream-ordered, non-reentrant — the same
+ * contract as the reference, which calls these passes from the single thread
+ * that owns the GL context (StratusRendererBackend.cpp:810, :1955).
+ *
+ * Memory formats ("planes") are the reference's G-buffer formats
+ * (StratusRendererBackend.cpp:384-424, 511-585, 2413-2421) with 3-component
+ * texels padded to 4 components — the same padding CUDA-GL interop forces
+ * (cudaGraphicsGLRegisterImage accepts only 1/2/4-component formats):
+ *
+ *   depth, prevDepth            float32          [rows][W]   GL window depth in [0,1]
+ *   normal, prevNormal          unorm8 x4 (rgb_) [rows][W]   n*0.5+0.5
+ *   albedo                      unorm8 x4 (rgb_) [rows][W]
+ *   baseReflectivity            unorm8 x2 (r_)   [rows][W]
+ *   roughnessMetallicAmbient    unorm8 x4 (rgb_) [rows][W]
+ *   ssao                        binary16         [rows][W]
+ *   velocity                    binary16 x2      [rows][W]
+ *   id, prevId                  float32          [rows][W]
+ *   screen (lightingColorBuffer) binary16 x4 (rgb_) [rows][W]
+ *   GI targets                  binary16 x4      [rows][W]   (RGB16F padded, RGBA16F as is)
+ *   history                     binary16         [rows][W]
+ *   shadowCubeMaps[a]           unorm16          [layers][6][res][res]   face order +X,-X,+Y,-Y,+Z,-Z
+ *   diffuseCubeMaps[a]          unorm8 x4 (rgb_) [layers][6][res][res]
+ *   infiniteLightShadowMap      float32          [cascades][csm][csm]    depth in [0,1]
+ *
+ * Row bands: a handle may own only rows [y_offset, y_offset+rows) of a
+ * full_height-row frame (multi-GPU split).  Every per-pixel
+ * plane handed to that handle then holds exactly `rows` rows.
+ */
+#ifndef STRATUSGI_H
+#define STRATUSGI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- limits: Source/Engine/StratusGpuCommon.h:15-17, :34-36 ------------------------------ */
+#define SGI_MAX_TOTAL_SHADOW_ATLASES        14
+#define SGI_MAX_TOTAL_SHADOWS_PER_ATLAS     320
+#define SGI_MAX_TOTAL_SHADOW_MAPS           (SGI_MAX_TOTAL_SHADOW_ATLASES * SGI_MAX_TOTAL_SHADOWS_PER_ATLAS)
+#define SGI_MAX_TOTAL_VPLS_BEFORE_CULLING   10000
+#define SGI_MAX_TOTAL_VPLS_PER_FRAME        SGI_MAX_TOTAL_SHADOW_MAPS   /* 4480 */
+#define SGI_MAX_VPLS_PER_TILE               12
+#define SGI_TILE_DIVISOR                    5   /* tileXDivisor/tileYDivisor, StratusRendererBackend.h:346-347 */
+#define SGI_NUM_CASCADES                    4
+
+/* ---- wire formats (std430, tightly packed) ------------------------------------------------ */
+/* GpuVplData, Source/Engine/StratusGpuCommon.h:217-232; GLSL twin vpl_common.glsl:48-56 */
+typedef struct SgiVplData {
+    float position[4];
+    float color[4];
+    float specularPosition[4];
+    float radius;
+    float farPlane;
+    float intensity;
+    float _pad;
+} SgiVplData;
+
+/* GpuVplStage1PerTileOutputs, StratusGpuCommon.h:192-195 */
+typedef struct SgiVplStage1PerTileOutputs {
+    float averageLocalPosition[4];
+    float averageLocalNormal[4];
+} SgiVplStage1PerTileOutputs;
+
+/* GpuVplStage2PerTileOutputs, StratusGpuCommon.h:203-209 */
+typedef struct SgiVplStage2PerTileOutputs {
+    int32_t numVisible;
+    int32_t indices[SGI_MAX_VPLS_PER_TILE];
+} SgiVplStage2PerTileOutputs;
+
+/* GpuAtlasEntry, StratusGpuCommon.h:276-279 */
+typedef struct SgiAtlasEntry {
+    int32_t index;   /* which atlas (0..13) */
+    int32_t layer;   /* cube layer inside that atlas */
+} SgiAtlasEntry;
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+    SGI_OK              = 0,
+    SGI_ERR_INVALID_ARG = 1,
+    SGI_ERR_CUDA        = 2,   /* CUDA runtime/driver error, or no device: there is no CPU path */
+    SGI_ERR_NOT_BOUND   = 3,   /* a buffer the stage needs was never bound */
+    SGI_ERR_UNSUPPORTED = 4
+};
+
+enum { SGI_GATHER_STOCHASTIC = 0, SGI_GATHER_TILE_LIST = 1 };
+
+/* which library-owned plane sgi_get_plane returns */
+enum {
+    SGI_PLANE_GI_COLOR       = 0,  /* vplGIFbo attachment 0: albedo + 1e-5            half4 */
+    SGI_PLANE_GI_RESERVOIR   = 1,  /* vplGIFbo attachment 1: (radiance, sum weights)  half4 */
+    SGI_PLANE_DENOISE_RES_A  = 2,  /* vplGIDenoisedFbo1 attachment 2 (reservoir)      half4 */
+    SGI_PLANE_DENOISE_RES_B  = 3,  /* vplGIDenoisedFbo2 attachment 2                  half4 */
+    SGI_PLANE_GI_ILLUM       = 4,  /* this frame's `giColor` after the final pass     half4 */
+    SGI_PLANE_HISTORY        = 5,  /* this frame's `newHistoryDepth`                  half  */
+    SGI_PLANE_PREV_GI_ILLUM  = 6,  /* vplGIDenoisedPrevFrameFbo attachment 1          half4 */
+    SGI_PLANE_PREV_HISTORY   = 7,  /* vplGIDenoisedPrevFrameFbo attachment 3          half  */
+    SGI_PLANE_COMBINED       = 8   /* `combinedColor` of the final pass               half4 */
+};
+
+/* ---- create-time parameters (mirrors UpdateWindowDimensions_/InitializeVplData_,
+ *      StratusRendererBackend.cpp:297-310, 436-445, 510-589) -------------------------------- */
+typedef struct SgiCreateParams {
+    int32_t width;               /* frame width  (multiple of 5 for the tile stages)                */
+    int32_t full_height;         /* frame height                                                    */
+    int32_t y_offset;            /* first frame row owned by this handle (0 for a whole frame)      */
+    int32_t rows;                /* rows owned (== full_height for a whole frame); multiple of 5    */
+    int32_t cube_res;            /* vplShadowCubeMapX/Y, reference 32 (StratusRendererBackend.h:349) */
+    int32_t csm_res;             /* cascadeResolutionXY                                             */
+    int32_t denoise_iters;       /* maxIterations, reference 4 (StratusRendererBackend.cpp:1914)    */
+    int32_t device;              /* CUDA device ordinal                                             */
+    void*   stream;              /* cudaStream_t to run on; NULL = library creates its own          */
+} SgiCreateParams;
+
+/* ---- every uniform the five shaders read ------------------------------ */
+typedef struct SgiFrameParams {
+    float   invProjectionView[16];      /* column-major, as glm stores it                           */
+    float   prevInvProjectionView[16];  /* bound by the reference, unused by the live shader text   */
+    float   viewPosition[3];
+    float   time;                       /* `time` uniform: milliseconds as float (BE:1823-1824)     */
+    double  deltaSeconds;               /* framesPerSecond = float(1.0/deltaSeconds) (BE:1908)      */
+    float   minGiOcclusionFactor;       /* RendererSettings default 0.95                             */
+    float   minRoughness;               /* 0.08                                                      */
+    int32_t usePerceptualRoughness;     /* 1                                                         */
+    float   fogDensity;
+    float   fogColor[3];
+    float   infiniteLightDirection[3];
+    float   infiniteLightColor[3];      /* GetLuminance() = colour * intensity                       */
+    float   cascadeProjViews[SGI_NUM_CASCADES][16];   /* projectionViewSample, column-major          */
+    float   cascadePlanes[3][4];
+    int32_t totalNumLights;             /* N handed to the cull (<= 10000)                           */
+    int32_t gatherMode;                 /* SGI_GATHER_*                                              */
+} SgiFrameParams;
+
+/* ---- caller-owned device buffers (the SSBOs and textures the reference binds) -------------- */
+typedef struct SgiBuffers {
+    /* current-frame G-buffer, state_.currentFrame.* (BE:384-424) */
+    const void* depth;
+    const void* normal;
+    const void* albedo;
+    const void* baseReflectivity;
+    const void* roughnessMetallicAmbient;
+    const void* velocity;
+    const void* id;
+    /* previous-frame G-buffer, state_.previousFrame.{normals,id,depth} */
+    const void* prevNormal;
+    const void* prevId;
+    const void* prevDepth;
+    /* ssaoOcclusionBlurredTexture (BE:501) and lightingColorBuffer (BE:462) */
+    const void* ssao;
+    const void* screen;
+    /* where `combinedColor` goes (the blit into lightingFbo, BE:1946); may alias `screen` */
+    void*       lightingOut;
+    /* VPL SSBOs, state_.vpls.* (StratusRendererBackend.h:352-357) */
+    const SgiVplData*            vplData;               /* [N]            in  */
+    SgiVplData*                  vplUpdatedData;        /* [4480]         out */
+    int32_t*                     vplVisibleIndices;     /* [N+1]          out: [0]=V, [1..V]=indices */
+    SgiAtlasEntry*               shadowDiffuseIndices;  /* [4480]         out (built on device)      */
+    SgiVplStage1PerTileOutputs*  vplStage1Results;      /* [tiles]        out */
+    SgiVplStage2PerTileOutputs*  vplVisiblePerTile;     /* [tiles]        out */
+    /* shadow-map cache assignment per *input* VPL.  The reference builds
+     * shadowDiffuseIndices on the CPU from a blocking read-back of the visible
+     * list (BE:1609-1610, 1675-1701); here the table is indexed by original VPL
+     * index and compacted on the device by the cull, so no fence is needed. */
+    const SgiAtlasEntry*         atlasEntryByVpl;       /* [N]            in  */
+    /* vplSmapCache_.buffers[0..13] (BE:2413-2421) */
+    const void* shadowCubeMaps[SGI_MAX_TOTAL_SHADOW_ATLASES];
+    const void* diffuseCubeMaps[SGI_MAX_TOTAL_SHADOW_ATLASES];
+    /* frame_->csc.fbo depth attachment (BE:348-352) */
+    const void* infiniteLightShadowMap;
+} SgiBuffers;
+
+typedef struct SgiHandle_* SgiHandle;
+
+/* create / destroy / resize — UpdateWindowDimensions_ (BE:436) and InitializeVplData_ (BE:297) */
+int  sgi_create(const SgiCreateParams* params, SgiHandle* out);
+int  sgi_destroy(SgiHandle h);
+int  sgi_resize(SgiHandle h, int32_t width, int32_t full_height, int32_t y_offset, int32_t rows);
+
+/* hand over raw device pointers (the "BindBase/BindTexture" calls, BE:1599-1601, 1840-1861, 1888-1900) */
+int  sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers);
+/* GL-interop hand-over (GLuint names).  Returns SGI_ERR_UNSUPPORTED when the
+ * library was built without GL headers (this image has none). */
+int  sgi_register_gl(SgiHandle h, const uint32_t* gl_names, int32_t count);
+
+/* stage entry points; all stream-ordered, none blocks the host */
+int  sgi_cull(SgiHandle h, const SgiFrameParams* fp);          /* viscull_vpls.cs (a1)               */
+int  sgi_color(SgiHandle h, const SgiFrameParams* fp);         /* vpl_light_color.cs (a2)            */
+int  sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp);    /* ..._stage1.cs + ..._stage2.cs (a3,a4) */
+int  sgi_gather(SgiHandle h, const SgiFrameParams* fp);        /* vpl_pbr_gi.fs (a5)                  */
+int  sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass);  /* one vpl_pbr_gi_denoise.fs pass */
+int  sgi_denoise(SgiHandle h, const SgiFrameParams* fp);       /* all passes + blit + history swap (a6) */
+/* all of the above on one stream: cull, colour, tile lists, gather, denoise */
+int  sgi_frame(SgiHandle h, const SgiFrameParams* fp);
+
+/* the blocking variant of the visible count (what BE:1675-1678 maps the buffer for) */
+int  sgi_visible_count(SgiHandle h, int32_t* out_count);
+/* library-owned planes (device pointers valid until resize/destroy) */
+int  sgi_get_plane(SgiHandle h, int32_t which, void** out_ptr, int64_t* out_bytes);
+/* clear temporal state (history/prev GI), as after FrameBuffer re-creation (BE:569-585) */
+int  sgi_reset_history(SgiHandle h);
+int  sgi_synchronize(SgiHandle h);
+void* sgi_stream(SgiHandle h);
+/* number of kernel launches issued through this handle since creation */
+int64_t sgi_launch_count(SgiHandle h);
+const char* sgi_last_error(SgiHandle h);
+const char* sgi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRATUSGI_H */

@@ -1,0 +1,187 @@
+"""Python front end of the CPU oracle (oracle/oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  It loads oracle/liboracle.so (own maths layer) or, with variant="glm",
+oracle/_ref/liboracle_glm.so (same source compiled against the reference's vendored glm).
+
+`OracleFrame` mirrors the pass sequencing of the reference backend
+(StratusRendererBackend.cpp:1578-1952): cull -> colour -> [tile lists] -> gather -> denoise passes
+with the Fbo1/Fbo2 ping-pong and the previous-frame swap.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from stratusgfx_b200._abi import (AtlasEntry, FrameParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+                                   TILE_DIVISOR)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REFERENCE_ROOT = "/root/reference"
+_FLAGS = ["-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared"]
+
+
+def build(force=False):
+    """Compile the oracle; also the glm-backed cross-check when the reference tree is present."""
+    src = os.path.join(_HERE, "oracle.cpp")
+    deps = [src, os.path.join(_HERE, "vm.h"), os.path.join(_HERE, "..", "include", "stratusgi.h")]
+    newest = max(os.path.getmtime(d) for d in deps)
+    out = os.path.join(_HERE, "liboracle.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+        subprocess.check_call(["g++"] + _FLAGS + ["-o", out, src])
+    if os.path.isdir(os.path.join(_REFERENCE_ROOT, "glm")):
+        ref_dir = os.path.join(_HERE, "_ref")
+        os.makedirs(ref_dir, exist_ok=True)
+        out_glm = os.path.join(ref_dir, "liboracle_glm.so")
+        if force or not os.path.exists(out_glm) or os.path.getmtime(out_glm) < newest:
+            subprocess.check_call(["g++"] + _FLAGS + ["-DORACLE_USE_GLM", "-I" + _REFERENCE_ROOT, "-o", out_glm, src])
+    return out
+
+
+class OrcDims(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cube_res", C.c_int32), ("csm_res", C.c_int32)]
+
+
+class OrcDenoisePass(C.Structure):
+    _fields_ = [("multiplier", C.c_int32), ("mergeReservoirs", C.c_int32), ("final_", C.c_int32), ("numVisible", C.c_int32)] + \
+               [(n, C.c_void_p) for n in ("screenH4", "velocityH2", "normal4", "ids", "depth", "prevNormal4", "prevIds", "prevDepth",
+                                          "indirectIlluminationH4", "indirectShadowsH4", "prevIndirectIlluminationH4", "historyDepthH",
+                                          "combinedOutH4", "giOutH4", "reservoirOutH4", "historyOutH")]
+
+
+_libs = {}
+
+
+def has_variant(variant):
+    path = os.path.join(_HERE, "liboracle.so") if variant == "own" else os.path.join(_HERE, "_ref", "liboracle_glm.so")
+    return os.path.exists(path)
+
+
+def lib(variant="own"):
+    if variant not in _libs:
+        if variant == "own":
+            path = os.path.join(_HERE, "liboracle.so")
+            if not os.path.exists(path):
+                build()
+        else:
+            path = os.path.join(_HERE, "_ref", "liboracle_glm.so")
+        L = C.CDLL(path)
+        L.orc_f2h.restype = C.c_uint16
+        L.orc_f2h.argtypes = [C.c_float]
+        L.orc_h2f.restype = C.c_float
+        L.orc_h2f.argtypes = [C.c_uint16]
+        L.orc_hash3.restype = C.c_uint32
+        L.orc_hash3.argtypes = [C.c_float] * 3
+        L.orc_random3.restype = C.c_float
+        L.orc_random3.argtypes = [C.c_float] * 3
+        for name, n in (("orc_cull", 8), ("orc_color", 7), ("orc_stage1", 5), ("orc_gather", 15)):
+            getattr(L, name).argtypes = [C.c_void_p] * n
+        L.orc_stage2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.orc_denoise_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _libs[variant] = L
+    return _libs[variant]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _atlas_ptrs(arr):
+    """arr: [A, 320, 6, R, R(,4)] contiguous -> (c_void_p * 14) of per-atlas base pointers."""
+    tab = (C.c_void_p * MAX_TOTAL_SHADOW_ATLASES)()
+    stride = arr[0].nbytes
+    for a in range(arr.shape[0]):
+        tab[a] = arr.ctypes.data + a * stride
+    return tab
+
+
+class OracleFrame:
+    """Whole-frame CPU pipeline over numpy buffers, keeping temporal state between frames."""
+
+    def __init__(self, width, height, cube_res=32, csm_res=1024, denoise_iters=4, variant="own"):
+        self.L = lib(variant)
+        self.W, self.H = width, height
+        self.dims = OrcDims(width, height, cube_res, csm_res)
+        self.denoise_iters = denoise_iters
+        self.tiles = (width // TILE_DIVISOR) * (height // TILE_DIVISOR)
+        z4 = lambda: np.zeros((height, width, 4), np.float16)
+        self.prev_gi = z4()                                   # vplGIDenoisedPrevFrameFbo attachment 1
+        self.prev_history = np.zeros((height, width), np.float16)   # attachment 3
+
+    # ---- a1 ----
+    def cull(self, fp, vpl_data, atlas_by_vpl, csm):
+        n = fp.totalNumLights
+        self.updated = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 16), np.float32)
+        self.visible = np.zeros(max(n, 0) + 1, np.int32)
+        self.entries = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 2), np.int32)
+        self.L.orc_cull(C.addressof(fp), C.addressof(self.dims), _p(vpl_data), _p(atlas_by_vpl), _p(csm),
+                        _p(self.updated), _p(self.visible), _p(self.entries))
+        return int(self.visible[0])
+
+    # ---- a2 ----
+    def color(self, fp, shadow_atlas, diffuse_atlas):
+        self._sh_ptrs = _atlas_ptrs(shadow_atlas)
+        self._df_ptrs = _atlas_ptrs(diffuse_atlas)
+        self._keep = (shadow_atlas, diffuse_atlas)
+        self.L.orc_color(C.addressof(fp), C.addressof(self.dims), _p(self.updated), _p(self.visible), _p(self.entries),
+                         C.addressof(self._sh_ptrs), C.addressof(self._df_ptrs))
+
+    # ---- a3 + a4 ----
+    def tile_lists(self, fp, gb, vpl_data):
+        self.stage1 = np.zeros((self.tiles, 8), np.float32)
+        self.stage2 = np.zeros((self.tiles, 13), np.int32)
+        self.L.orc_stage1(C.addressof(fp), C.addressof(self.dims), _p(gb.depth), _p(gb.normal), _p(self.stage1))
+        v = int(self.visible[0])
+        idx = np.ascontiguousarray(self.visible[1:1 + v])
+        self.L.orc_stage2(C.addressof(self.dims), _p(self.stage1), _p(vpl_data), v, _p(idx), _p(self.stage2))
+
+    # ---- a5 ----
+    def gather(self, fp, gb):
+        H, W = self.H, self.W
+        self.gi_color = np.zeros((H, W, 4), np.float16)
+        self.gi_reservoir = np.zeros((H, W, 4), np.float16)
+        self.sample_stats = np.zeros(3, np.int64)
+        self.L.orc_gather(C.addressof(fp), C.addressof(self.dims), _p(gb.depth), _p(gb.normal), _p(gb.albedo), _p(gb.baseReflectivity),
+                          _p(gb.roughnessMetallicAmbient), _p(gb.ssao), _p(self.updated), _p(self.visible), _p(self.entries),
+                          C.addressof(self._sh_ptrs), _p(self.gi_color), _p(self.gi_reservoir), _p(self.sample_stats))
+
+    # ---- a6: the host loop of BE:1879-1952 ----
+    def denoise(self, fp, gb, prev_gb, keep_passes=False):
+        H, W = self.H, self.W
+        mk4 = lambda: np.zeros((H, W, 4), np.float16)
+        fbos = [dict(combined=mk4(), gi=mk4(), reservoir=mk4(), history=np.zeros((H, W), np.float16)) for _ in range(2)]
+        illum, shadows = self.gi_color, self.gi_reservoir
+        self.pass_reservoirs = []
+        iters = self.denoise_iters
+        last = None
+        for i in range(iters):
+            fbo = fbos[i % 2]
+            ps = OrcDenoisePass()
+            ps.multiplier = (1 << i) - 1
+            ps.mergeReservoirs = 1 if i < 1 else 0
+            ps.final_ = 1 if i + 1 == iters else 0
+            ps.numVisible = int(self.visible[0])
+            ps.screenH4, ps.velocityH2, ps.normal4, ps.ids, ps.depth = _p(gb.screen), _p(gb.velocity), _p(gb.normal), _p(gb.id), _p(gb.depth)
+            ps.prevNormal4, ps.prevIds, ps.prevDepth = _p(prev_gb.normal), _p(prev_gb.id), _p(prev_gb.depth)
+            ps.indirectIlluminationH4, ps.indirectShadowsH4 = _p(illum), _p(shadows)
+            ps.prevIndirectIlluminationH4, ps.historyDepthH = _p(self.prev_gi), _p(self.prev_history)
+            ps.combinedOutH4, ps.giOutH4, ps.reservoirOutH4, ps.historyOutH = _p(fbo["combined"]), _p(fbo["gi"]), _p(fbo["reservoir"]), _p(fbo["history"])
+            self.L.orc_denoise_pass(C.addressof(fp), C.addressof(self.dims), C.addressof(ps))
+            illum, shadows = fbo["gi"], fbo["reservoir"]
+            if keep_passes:
+                self.pass_reservoirs.append(fbo["reservoir"].copy())
+            last = fbo
+        self.combined = last["combined"]        # blitted into lightingFbo (BE:1946)
+        self.gi_illum = last["gi"]
+        self.history = last["history"]
+        # swap with the previous-frame FBO (BE:1949-1951)
+        self.prev_gi, self.prev_history = last["gi"].copy(), last["history"].copy()
+
+    def frame(self, fp, gb, prev_gb, vpl_data, atlas_by_vpl, csm, shadow_atlas, diffuse_atlas, tile_lists=True, keep_passes=False):
+        self.cull(fp, vpl_data, atlas_by_vpl, csm)
+        self.color(fp, shadow_atlas, diffuse_atlas)
+        if tile_lists:
+            self.tile_lists(fp, gb, vpl_data)
+        self.gather(fp, gb)
+        self.denoise(fp, gb, prev_gb, keep_passes=keep_passes)
