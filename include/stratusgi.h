@@ -213,6 +213,8 @@ int  sgi_frame(SgiHandle h, const SgiFrameParams* fp);
 int  sgi_visible_count(SgiHandle h, int32_t* out_count);
 /* library-owned planes (device pointers valid until resize/destroy) */
 int  sgi_get_plane(SgiHandle h, int32_t which, void** out_ptr, int64_t* out_bytes);
+/* blocking device->host copy of a library-owned plane (tests, debugging) */
+int  sgi_download_plane(SgiHandle h, int32_t which, void* host_dst, int64_t bytes);
 /* clear temporal state (history/prev GI), as after FrameBuffer re-creation (BE:569-585) */
 int  sgi_reset_history(SgiHandle h);
 int  sgi_synchronize(SgiHandle h);

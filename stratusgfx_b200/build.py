@@ -1,0 +1,58 @@
+"""In-tree native build of the product library (nvcc, sm_100a only) and the scene generator.
+
+    python -m stratusgfx_b200.build [--force]
+
+Outputs (git-ignored, but they travel to the GPU box with the repo snapshot):
+    stratusgfx_b200/csrc/libstratusgi.so     CUDA kernels + C-ABI of include/stratusgi.h
+    stratusgfx_b200/scene/libsgi_scene.so    host-only procedural input generator
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB = os.path.join(CSRC, "libstratusgi.so")
+CU_SOURCES = ["sgi_abi.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu"]
+HEADERS = ["sgi_internal.h", "sgi_math.cuh", os.path.join("..", "..", "include", "stratusgi.h")]
+
+# -fmad=false: the integer outputs of this path hinge on float comparisons, so no mul+add may be
+# contracted behind the source's back (see csrc/sgi_math.cuh).  IEEE sqrt/div are nvcc defaults.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def build_native(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest(deps):
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objs = []
+    for s in srcs:
+        o = s[:-3] + ".o"
+        if force or not os.path.exists(o) or os.path.getmtime(o) < _newest([s] + deps[len(srcs):]):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed for " + s)
+        objs.append(o)
+    subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB
+
+
+def build_all(force=False, verbose=False):
+    from .scene import build as build_scene
+    build_scene(force)
+    return build_native(force, verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,316 @@
+// sgi_abi.cu — the C-ABI of include/stratusgi.h over the CUDA stages.
+//
+// Host-side sequencing mirrors the three reference methods
+//   PerformVirtualPointLightCullingStage1_      (StratusRendererBackend.cpp:1578-1612)
+//   PerformVirtualPointLightCullingStage2_      (:1666-1731, dormant tile stages :1733-1783)
+//   ComputeVirtualPointLightGlobalIllumination_ (:1816-1952)
+// with the fence + map round trip (:1609-1610, :1675-1701) removed: everything is enqueued on
+// one stream and nothing blocks the host.  There is no CPU fallback anywhere in this library.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "sgi_internal.h"
+
+using namespace sgi;
+
+#define SGI_CUDA(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            char _b[512];                                                                         \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (h)->lastError = _b;                                                                  \
+            return SGI_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+static thread_local std::string g_createError;
+
+static int fail(SgiHandle h, int code, const char* msg) { h->lastError = msg; return code; }
+
+static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h->cp.rows; }
+
+static void freePlanes(SgiHandle h) {
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1], &h->history[0], &h->history[1]};
+    for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+}
+
+static int allocPlanes(SgiHandle h) {
+    const size_t n = pixels(h);
+    void** half4s[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1]};
+    for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
+    for (int i = 0; i < 2; ++i) SGI_CUDA(h, cudaMalloc(&h->history[i], n * 2));
+    // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the
+    // previous-frame FBO is never cleared and starts at zero
+    for (int i = 0; i < 2; ++i) {
+        SGI_CUDA(h, cudaMemsetAsync(h->giIllum[i], 0, n * 8, h->stream));
+        SGI_CUDA(h, cudaMemsetAsync(h->history[i], 0, n * 2, h->stream));
+    }
+    h->cur = 0;
+    return SGI_OK;
+}
+
+static int checkDims(int width, int full_height, int y_offset, int rows) {
+    if (width <= 0 || full_height <= 0 || rows <= 0 || y_offset < 0 || y_offset + rows > full_height) return SGI_ERR_INVALID_ARG;
+    return SGI_OK;
+}
+
+static BandDims bandDims(const SgiHandle h) {
+    BandDims bd;
+    bd.W = h->cp.width; bd.fullH = h->cp.full_height; bd.yOffset = h->cp.y_offset; bd.rows = h->cp.rows;
+    bd.cubeRes = h->cp.cube_res; bd.csmRes = h->cp.csm_res;
+    return bd;
+}
+
+static AtlasTable atlasTable(const SgiHandle h) {
+    AtlasTable t;
+    for (int i = 0; i < SGI_MAX_TOTAL_SHADOW_ATLASES; ++i) {
+        t.shadow[i] = (const unsigned short*)h->buf.shadowCubeMaps[i];
+        t.diffuse[i] = (const uchar4*)h->buf.diffuseCubeMaps[i];
+    }
+    return t;
+}
+
+extern "C" {
+
+const char* sgi_version(void) { return "stratusgi-b200 0.1 (sm_100a)"; }
+
+int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
+    if (!params || !out) return SGI_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (checkDims(params->width, params->full_height, params->y_offset, params->rows) != SGI_OK) return SGI_ERR_INVALID_ARG;
+    if (params->cube_res <= 0 || params->csm_res <= 0 || params->denoise_iters < 1 || params->denoise_iters > 16) return SGI_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || params->device < 0 || params->device >= ndev) {
+        cudaGetLastError();
+        return SGI_ERR_CUDA;     // no usable CUDA device: there is deliberately no CPU path
+    }
+    SgiHandle h = new (std::nothrow) SgiHandle_();
+    if (!h) return SGI_ERR_INVALID_ARG;
+    h->cp = *params;
+    std::memset(&h->buf, 0, sizeof(h->buf));
+    auto bail = [&](int code) { sgi_destroy(h); return code; };
+    if (cudaSetDevice(params->device) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (params->stream) { h->stream = (cudaStream_t)params->stream; h->ownStream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        h->ownStream = true;
+    }
+    if (cudaMalloc(&h->cullBallots, 512 * sizeof(uint32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMalloc(&h->cullTicket, sizeof(unsigned int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
+    *out = h;
+    return SGI_OK;
+}
+
+int sgi_destroy(SgiHandle h) {
+    if (!h) return SGI_ERR_INVALID_ARG;
+    cudaSetDevice(h->cp.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    freePlanes(h);
+    if (h->cullBallots) cudaFree(h->cullBallots);
+    if (h->cullTicket) cudaFree(h->cullTicket);
+    if (h->pinnedCount) cudaFreeHost(h->pinnedCount);
+    if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SGI_OK;
+}
+
+int sgi_resize(SgiHandle h, int32_t width, int32_t full_height, int32_t y_offset, int32_t rows) {
+    if (!h) return SGI_ERR_INVALID_ARG;
+    if (checkDims(width, full_height, y_offset, rows) != SGI_OK) return fail(h, SGI_ERR_INVALID_ARG, "sgi_resize: bad dimensions");
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    freePlanes(h);
+    h->cp.width = width; h->cp.full_height = full_height; h->cp.y_offset = y_offset; h->cp.rows = rows;
+    h->bound = false;                       // per-pixel planes of the old size are no longer valid
+    return allocPlanes(h);
+}
+
+int sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers) {
+    if (!h || !buffers) return SGI_ERR_INVALID_ARG;
+    h->buf = *buffers;
+    h->bound = true;
+    return SGI_OK;
+}
+
+int sgi_register_gl(SgiHandle h, const uint32_t*, int32_t) {
+    if (!h) return SGI_ERR_INVALID_ARG;
+    return fail(h, SGI_ERR_UNSUPPORTED, "sgi_register_gl: library built without OpenGL headers (none in this image); use sgi_bind_device_buffers");
+}
+
+#define NEED(h, field)                                                                             \
+    do { if (!(h)->bound || (h)->buf.field == nullptr) return fail(h, SGI_ERR_NOT_BOUND, "buffer not bound: " #field); } while (0)
+
+static int postLaunch(SgiHandle h, int n) {
+    h->launches += n;
+    SGI_CUDA(h, cudaGetLastError());
+    return SGI_OK;
+}
+
+int sgi_cull(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    if (fp->totalNumLights < 0 || fp->totalNumLights > SGI_MAX_TOTAL_VPLS_BEFORE_CULLING) return fail(h, SGI_ERR_INVALID_ARG, "sgi_cull: totalNumLights out of range");
+    NEED(h, vplData); NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, infiniteLightShadowMap);
+    if (h->buf.atlasEntryByVpl && !h->buf.shadowDiffuseIndices) return fail(h, SGI_ERR_NOT_BOUND, "buffer not bound: shadowDiffuseIndices");
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const int n = launchCull(h->stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
+                             h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket);
+    return postLaunch(h, n);
+}
+
+int sgi_color(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, shadowDiffuseIndices); NEED(h, shadowCubeMaps[0]); NEED(h, diffuseCubeMaps[0]);
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const int n = launchColor(h->stream, fc, bandDims(h), h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, atlasTable(h));
+    return postLaunch(h, n);
+}
+
+int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    NEED(h, depth); NEED(h, normal); NEED(h, vplData); NEED(h, vplVisibleIndices); NEED(h, vplStage1Results); NEED(h, vplVisiblePerTile);
+    if (h->cp.width % SGI_TILE_DIVISOR || h->cp.rows % SGI_TILE_DIVISOR || h->cp.y_offset % SGI_TILE_DIVISOR)
+        return fail(h, SGI_ERR_INVALID_ARG, "sgi_tile_lists: width, rows and y_offset must be multiples of 5");
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const BandDims bd = bandDims(h);
+    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results);
+    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile);
+    return postLaunch(h, n);
+}
+
+int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    if (fp->gatherMode != SGI_GATHER_STOCHASTIC) return fail(h, SGI_ERR_UNSUPPORTED, "sgi_gather: only SGI_GATHER_STOCHASTIC (the reference's live path) is implemented");
+    NEED(h, depth); NEED(h, normal); NEED(h, albedo); NEED(h, baseReflectivity); NEED(h, roughnessMetallicAmbient); NEED(h, ssao);
+    NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, shadowDiffuseIndices); NEED(h, shadowCubeMaps[0]);
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const int n = launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
+                               (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
+                               (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
+                               atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir);
+    return postLaunch(h, n);
+}
+
+int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    const int iters = h->cp.denoise_iters;
+    if (pass < 0 || pass >= iters) return fail(h, SGI_ERR_INVALID_ARG, "sgi_denoise_pass: pass out of range");
+    NEED(h, depth); NEED(h, normal); NEED(h, vplVisibleIndices);
+    const bool merge = pass < 1;                 // maxReservoirMergingPasses = 1 (BE:1913)
+    const bool final_ = (pass + 1 == iters);     // BE:1929-1931
+    if (final_) { NEED(h, screen); NEED(h, velocity); NEED(h, id); NEED(h, prevNormal); NEED(h, prevId); NEED(h, prevDepth); }
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    DenoiseIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.screen = (const uint2*)h->buf.screen; io.velocity = (const uint32_t*)h->buf.velocity; io.normal = (const uint32_t*)h->buf.normal;
+    io.ids = (const float*)h->buf.id; io.depth = (const float*)h->buf.depth;
+    io.prevNormal = (const uint32_t*)h->buf.prevNormal; io.prevIds = (const float*)h->buf.prevId; io.prevDepth = (const float*)h->buf.prevDepth;
+    io.illum = (const uint2*)h->giColor;
+    void* fbo[2] = {h->resA, h->resB};           // buffers[bufferIndex % 2] (BE:1921)
+    io.shadowsIn = (const uint2*)(pass == 0 ? h->giReservoir : fbo[(pass - 1) % 2]);
+    io.reservoirOut = (uint2*)fbo[pass % 2];
+    io.prevGi = (const uint2*)h->giIllum[h->cur ^ 1];
+    io.historyIn = (const unsigned short*)h->history[h->cur ^ 1];
+    io.numVisible = h->buf.vplVisibleIndices;
+    io.combinedOut = (uint2*)(h->buf.lightingOut ? h->buf.lightingOut : h->combined);
+    io.giOut = (uint2*)h->giIllum[h->cur];
+    io.historyOut = (unsigned short*)h->history[h->cur];
+    io.multiplier = (1 << pass) - 1;             // std::pow(2, i) - 1 (BE:1920)
+    const int n = launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
+    if (final_) h->cur ^= 1;                     // swap with the previous-frame FBO (BE:1949-1951)
+    return postLaunch(h, n);
+}
+
+int sgi_denoise(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    for (int pass = 0; pass < h->cp.denoise_iters; ++pass) {
+        const int rc = sgi_denoise_pass(h, fp, pass);
+        if (rc != SGI_OK) return rc;
+    }
+    return SGI_OK;
+}
+
+int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
+    if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    int rc;
+    if (fp->totalNumLights == 0) return SGI_OK;      // `if (perVPLDistToViewer.size() == 0) return;` (BE:1582, 1675, 1817)
+    if ((rc = sgi_cull(h, fp)) != SGI_OK) return rc;
+    if ((rc = sgi_color(h, fp)) != SGI_OK) return rc;
+    if (h->buf.vplStage1Results && h->buf.vplVisiblePerTile) { if ((rc = sgi_tile_lists(h, fp)) != SGI_OK) return rc; }
+    if ((rc = sgi_gather(h, fp)) != SGI_OK) return rc;
+    return sgi_denoise(h, fp);
+}
+
+int sgi_visible_count(SgiHandle h, int32_t* out_count) {
+    if (!h || !out_count) return SGI_ERR_INVALID_ARG;
+    NEED(h, vplVisibleIndices);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA(h, cudaMemcpyAsync(h->pinnedCount, h->buf.vplVisibleIndices, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    *out_count = *h->pinnedCount;
+    return SGI_OK;
+}
+
+int sgi_get_plane(SgiHandle h, int32_t which, void** out_ptr, int64_t* out_bytes) {
+    if (!h || !out_ptr) return SGI_ERR_INVALID_ARG;
+    const int64_t n = (int64_t)pixels(h);
+    void* p = nullptr; int64_t bytes = n * 8;
+    const int prev = h->cur ^ 1;    // after a completed frame `cur` was swapped, so "this frame's" output sits in prev
+    switch (which) {
+        case SGI_PLANE_GI_COLOR: p = h->giColor; break;
+        case SGI_PLANE_GI_RESERVOIR: p = h->giReservoir; break;
+        case SGI_PLANE_DENOISE_RES_A: p = h->resA; break;
+        case SGI_PLANE_DENOISE_RES_B: p = h->resB; break;
+        case SGI_PLANE_GI_ILLUM: case SGI_PLANE_PREV_GI_ILLUM: p = h->giIllum[prev]; break;
+        case SGI_PLANE_HISTORY: case SGI_PLANE_PREV_HISTORY: p = h->history[prev]; bytes = n * 2; break;
+        case SGI_PLANE_COMBINED: p = h->buf.lightingOut ? h->buf.lightingOut : h->combined; break;
+        default: return fail(h, SGI_ERR_INVALID_ARG, "sgi_get_plane: unknown plane");
+    }
+    *out_ptr = p;
+    if (out_bytes) *out_bytes = bytes;
+    return SGI_OK;
+}
+
+int sgi_download_plane(SgiHandle h, int32_t which, void* host_dst, int64_t bytes) {
+    if (!h || !host_dst) return SGI_ERR_INVALID_ARG;
+    void* p = nullptr; int64_t n = 0;
+    const int rc = sgi_get_plane(h, which, &p, &n);
+    if (rc != SGI_OK) return rc;
+    if (bytes > n) return fail(h, SGI_ERR_INVALID_ARG, "sgi_download_plane: more bytes requested than the plane holds");
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA(h, cudaMemcpyAsync(host_dst, p, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SGI_OK;
+}
+
+int sgi_reset_history(SgiHandle h) {
+    if (!h) return SGI_ERR_INVALID_ARG;
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const size_t n = pixels(h);
+    for (int i = 0; i < 2; ++i) {
+        SGI_CUDA(h, cudaMemsetAsync(h->giIllum[i], 0, n * 8, h->stream));
+        SGI_CUDA(h, cudaMemsetAsync(h->history[i], 0, n * 2, h->stream));
+    }
+    return SGI_OK;
+}
+
+int sgi_synchronize(SgiHandle h) {
+    if (!h) return SGI_ERR_INVALID_ARG;
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SGI_OK;
+}
+
+void* sgi_stream(SgiHandle h) { return h ? (void*)h->stream : nullptr; }
+int64_t sgi_launch_count(SgiHandle h) { return h ? h->launches : 0; }
+const char* sgi_last_error(SgiHandle h) { return h ? h->lastError.c_str() : "null handle"; }
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""Host-side mirror of the reference's GI pass interface over the C-ABI (include/stratusgi.h).
+
+`VplGiPass` exposes the three RendererBackend methods the CUDA path replaces, under their
+reference names (Source/Engine/StratusRendererBackend.h:666-669):
+
+    PerformVirtualPointLightCullingStage1   -> sgi_cull
+    PerformVirtualPointLightCullingStage2   -> sgi_color (+ sgi_tile_lists, dormant in the reference)
+    ComputeVirtualPointLightGlobalIllumination -> sgi_gather + sgi_denoise
+
+PyTorch is used only for device memory (torch.cuda tensors own the buffers that are handed
+over as raw pointers) and streams.  There is no CPU fallback: a missing library or a missing
+GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import Buffers, CreateParams, FrameParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME, TILE_DIVISOR
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
+_lib = None
+
+
+class StratusGiError(RuntimeError):
+    pass
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libstratusgi.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise StratusGiError(f"{_LIB_PATH} is missing: run `python -m stratusgfx_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(_LIB_PATH)
+    H = C.c_void_p
+    L.sgi_create.argtypes = [C.POINTER(CreateParams), C.POINTER(H)]
+    L.sgi_destroy.argtypes = [H]
+    L.sgi_resize.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.sgi_bind_device_buffers.argtypes = [H, C.POINTER(Buffers)]
+    L.sgi_register_gl.argtypes = [H, C.c_void_p, C.c_int32]
+    for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
+        getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
+    L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
+    L.sgi_visible_count.argtypes = [H, C.POINTER(C.c_int32)]
+    L.sgi_get_plane.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.sgi_download_plane.argtypes = [H, C.c_int32, C.c_void_p, C.c_int64]
+    L.sgi_reset_history.argtypes = [H]
+    L.sgi_synchronize.argtypes = [H]
+    L.sgi_stream.argtypes = [H]
+    L.sgi_stream.restype = C.c_void_p
+    L.sgi_launch_count.argtypes = [H]
+    L.sgi_launch_count.restype = C.c_int64
+    L.sgi_last_error.argtypes = [H]
+    L.sgi_last_error.restype = C.c_char_p
+    L.sgi_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+_PER_PIXEL = ("depth", "normal", "albedo", "baseReflectivity", "roughnessMetallicAmbient", "velocity", "id",
+              "prevNormal", "prevId", "prevDepth", "ssao", "screen")
+
+
+class VplGiPass:
+    """One GI pass instance for a frame (or a row band of it) on one GPU."""
+
+    def __init__(self, width, full_height, y_offset=0, rows=None, cube_res=32, csm_res=1024, denoise_iters=4, device=0,
+                 use_torch_stream=False):
+        import torch
+        if not torch.cuda.is_available():
+            raise StratusGiError("no CUDA device: the GI pass has no CPU path")
+        self.torch = torch
+        self.L = load_library()
+        self.device = torch.device("cuda", device)
+        rows = full_height - y_offset if rows is None else rows
+        self.width, self.full_height, self.y_offset, self.rows = width, full_height, y_offset, rows
+        self.cube_res, self.csm_res, self.denoise_iters = cube_res, csm_res, denoise_iters
+        cp = CreateParams(width, full_height, y_offset, rows, cube_res, csm_res, denoise_iters, device,
+                          torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None)
+        self._h = C.c_void_p()
+        rc = self.L.sgi_create(C.byref(cp), C.byref(self._h))
+        if rc != _abi.SGI_OK:
+            raise StratusGiError(f"sgi_create failed with status {rc}")
+        self.t = {}            # name -> torch tensor keeping the device memory alive
+        self.buffers = Buffers()
+        tiles = (width // TILE_DIVISOR) * (rows // TILE_DIVISOR)
+        dev = self.device
+        # outputs the caller owns in the reference (state_.vpls.*, StratusRendererBackend.h:352-357)
+        self.t["vplUpdatedData"] = torch.zeros((MAX_TOTAL_VPLS_PER_FRAME, 16), dtype=torch.float32, device=dev)
+        self.t["shadowDiffuseIndices"] = torch.zeros((MAX_TOTAL_VPLS_PER_FRAME, 2), dtype=torch.int32, device=dev)
+        self.t["vplStage1Results"] = torch.zeros((max(tiles, 1), 8), dtype=torch.float32, device=dev)
+        self.t["vplVisiblePerTile"] = torch.zeros((max(tiles, 1), 13), dtype=torch.int32, device=dev)
+        self.t["lightingOut"] = torch.zeros((rows, width, 4), dtype=torch.float16, device=dev)
+        self.tiles = tiles
+
+    # ---- buffer hand-over --------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != _abi.SGI_OK:
+            raise StratusGiError(f"status {rc}: {self.L.sgi_last_error(self._h).decode()}")
+
+    def _up(self, a):
+        torch = self.torch
+        if isinstance(a, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        return a.to(self.device).contiguous()
+
+    def set_gbuffer(self, gb, prev_gb):
+        """gb / prev_gb: scene.GBuffer of the band's rows (numpy) or dicts of cuda tensors."""
+        get = (lambda o, k: getattr(o, k)) if not isinstance(gb, dict) else (lambda o, k: o[k])
+        for k in ("depth", "normal", "albedo", "baseReflectivity", "roughnessMetallicAmbient", "velocity", "id", "ssao", "screen"):
+            self.t[k] = self._up(get(gb, k))
+        self.t["prevNormal"] = self._up(get(prev_gb, "normal"))
+        self.t["prevId"] = self._up(get(prev_gb, "id"))
+        self.t["prevDepth"] = self._up(get(prev_gb, "depth"))
+
+    def set_vpls(self, vpl_data, atlas_by_vpl):
+        self.t["vplData"] = self._up(vpl_data)
+        self.t["atlasEntryByVpl"] = self._up(atlas_by_vpl)
+        n = int(self.t["vplData"].shape[0])
+        self.t["vplVisibleIndices"] = self.torch.zeros(n + 1, dtype=self.torch.int32, device=self.device)
+
+    def set_atlases(self, shadow_atlas, diffuse_atlas):
+        """[A,320,6,R,R] uint16 and [A,320,6,R,R,4] uint8, contiguous concatenation of the atlases."""
+        torch = self.torch
+        if isinstance(shadow_atlas, np.ndarray):
+            shadow_atlas = torch.from_numpy(shadow_atlas.view(np.int16))     # torch has no uint16 arithmetic; bytes are what matter
+        self.t["shadowAtlas"] = shadow_atlas.to(self.device).contiguous()
+        self.t["diffuseAtlas"] = self._up(diffuse_atlas)
+
+    def set_csm(self, csm):
+        self.t["infiniteLightShadowMap"] = self._up(csm)
+
+    def bind(self):
+        b = Buffers()
+        for k in _PER_PIXEL + ("lightingOut", "vplData", "vplUpdatedData", "vplVisibleIndices", "shadowDiffuseIndices",
+                               "vplStage1Results", "vplVisiblePerTile", "atlasEntryByVpl", "infiniteLightShadowMap"):
+            if k in self.t:
+                setattr(b, k, self.t[k].data_ptr())
+        if "shadowAtlas" in self.t:
+            sa, da = self.t["shadowAtlas"], self.t["diffuseAtlas"]
+            for a in range(min(sa.shape[0], MAX_TOTAL_SHADOW_ATLASES)):
+                b.shadowCubeMaps[a] = sa[a].data_ptr()
+                b.diffuseCubeMaps[a] = da[a].data_ptr()
+        self.buffers = b
+        self.torch.cuda.synchronize(self.device)     # uploads/fills ran on torch's stream; the pass runs on its own
+        self._check(self.L.sgi_bind_device_buffers(self._h, C.byref(b)))
+
+    # ---- the reference's pass interface --------------------------------------------------------------
+    def PerformVirtualPointLightCullingStage1(self, fp):
+        """viscull_vpls.cs; fills vplUpdatedData / vplVisibleIndices / shadowDiffuseIndices (BE:1578)."""
+        self._check(self.L.sgi_cull(self._h, C.byref(fp)))
+
+    def PerformVirtualPointLightCullingStage2(self, fp, tile_lists=True):
+        """vpl_light_color.cs, then the (reference-dormant) per-tile list stages (BE:1666)."""
+        self._check(self.L.sgi_color(self._h, C.byref(fp)))
+        if tile_lists:
+            self._check(self.L.sgi_tile_lists(self._h, C.byref(fp)))
+
+    def ComputeVirtualPointLightGlobalIllumination(self, fp):
+        """vpl_pbr_gi.fs + the vpl_pbr_gi_denoise.fs passes, blit and history swap (BE:1816)."""
+        self._check(self.L.sgi_gather(self._h, C.byref(fp)))
+        self._check(self.L.sgi_denoise(self._h, C.byref(fp)))
+
+    # ---- finer-grained entry points --------------------------------------------------------------------
+    def cull(self, fp): self._check(self.L.sgi_cull(self._h, C.byref(fp)))
+    def color(self, fp): self._check(self.L.sgi_color(self._h, C.byref(fp)))
+    def tile_lists(self, fp): self._check(self.L.sgi_tile_lists(self._h, C.byref(fp)))
+    def gather(self, fp): self._check(self.L.sgi_gather(self._h, C.byref(fp)))
+    def denoise_pass(self, fp, i): self._check(self.L.sgi_denoise_pass(self._h, C.byref(fp), i))
+    def denoise(self, fp): self._check(self.L.sgi_denoise(self._h, C.byref(fp)))
+    def frame(self, fp): self._check(self.L.sgi_frame(self._h, C.byref(fp)))
+    def synchronize(self): self._check(self.L.sgi_synchronize(self._h))
+    def reset_history(self): self._check(self.L.sgi_reset_history(self._h))
+
+    def visible_count(self):
+        n = C.c_int32()
+        self._check(self.L.sgi_visible_count(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count(self):
+        return int(self.L.sgi_launch_count(self._h))
+
+    def stream_ptr(self):
+        return self.L.sgi_stream(self._h)
+
+    def plane(self, which):
+        """Blocking download of a library-owned plane as a numpy array."""
+        if which in (_abi.PLANE_HISTORY, _abi.PLANE_PREV_HISTORY):
+            out = np.empty((self.rows, self.width), np.float16)
+        else:
+            out = np.empty((self.rows, self.width, 4), np.float16)
+        self._check(self.L.sgi_download_plane(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def output(self, name):
+        """Blocking download of a caller-owned output buffer as numpy."""
+        self.synchronize()
+        return self.t[name].cpu().numpy()
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.L.sgi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
