@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — VPL GI + denoise throughput of the CUDA path (and, with --impl reference, of the CPU
+restatement of the reference's shaders) on BASELINE.json's metric.
+
+A "step" is one frame of the hot path over one batch of synthetic input:
+    cull + colour + tile lists (stage1+stage2) + stochastic gather + à-trous/temporal denoise.
+Metric: Gpixel·VPL/s = W·H·N_vpl / t_frame / 1e9, ms_per_step = ms/frame.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4] [--impl ours|reference]
+
+N > 1 is launched by torchrun, one rank per GPU; the frame is split into horizontal row bands
+(SURVEY.md §8e): every step rank 0 broadcasts the VPL table and the frame's refreshed cube maps
+over NCCL, each rank runs its band (+ a 30-row apron so the à-trous passes need no halo exchange),
+and the lit bands are gathered to rank 0 — strong scaling of one frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "vpl_gi_denoise_throughput"
+UNIT = "Gpixel*VPL/s"
+APRON = 30            # >= 4+8+16 rows of à-trous reach (28), rounded to the 5-pixel tile grid
+CPU_SAMPLE_ROWS = 270  # bounded CPU sample: one 1/8-frame band of a 4K frame
+
+
+def workload_text(s):
+    kind = "Cornell box" if s.kind == 0 else "Sponza-scale hall"
+    return f"{s.workload}: {s.width}x{s.height} {kind}, {s.num_vpls} VPLs, cube shadow maps 32^2x6, {s.denoise_iters} denoise passes, tile lists on"
+
+
+# ---- clocks during the timed region (B200_PROFILING.md) -----------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- algorithmic bytes per stage, for the roofline -----------------------------------------------
+def algorithmic_bytes(P, T, N, V, iters):
+    return {
+        "cull": 64 * N + 64 * V + 4 * (V + 1),
+        "color": (64 + 32 + 8) * V,
+        "stage1": (4 + 3) * P + 32 * T,
+        "stage2": (32 + 52) * T + 20 * V,
+        "gather": 30 * P,
+        "denoise_pass": 23 * P,          # non-final pass
+        "denoise_final": 76 * P,
+        "frame": (4 + 3) * P + 32 * T + (32 + 52) * T + 30 * P + 23 * (iters - 1) * P + 76 * P,
+    }
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU arm: the oracle on a bounded band sample -------------------------------------------------------------------
+def cpu_sample_run(scene, steps, warmup):
+    """Times the CPU restatement (oracle/, kind "port") on rows [y0, y0+rows) of the workload's frame, all host threads."""
+    from oracle.oracle_py import OracleFrame, lib
+    H = scene.height
+    rows = min(CPU_SAMPLE_ROWS, H)
+    y0 = ((H - rows) // 2) // 5 * 5
+    fp = scene.frame_params(0)
+    gb, pgb = scene.gbuffer(0, y0, rows), scene.gbuffer(-1, y0, rows)
+    vd, at = scene.vpls()
+    sh, df = scene.cubemaps()
+    csm = scene.csm(0)
+    o = OracleFrame(scene.width, rows, scene.cube_res, scene.csm_res, scene.denoise_iters, y_offset=y0, full_height=H)
+    cores = int(lib().orc_num_threads())
+    times = []
+    for i in range(warmup + steps):
+        fp.time = 1000.0 + 16.0 * i
+        t = time.perf_counter()
+        o.frame(fp, gb, pgb, vd, at, csm, sh, df)
+        times.append(time.perf_counter() - t)
+    t_step = float(np.mean(times[warmup:]))
+    value = scene.width * rows * scene.num_vpls / t_step / 1e9
+    return dict(value=value, unit=UNIT, cores=cores, kind="port",
+                sample=f"rows {y0}..{y0 + rows} of {scene.width}x{H} ({rows}/{H} of the frame), whole VPL set, {steps} step(s) after {warmup} warm-up, mean",
+                ms_per_step=t_step * 1e3, V=int(o.visible[0]))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from stratusgfx_b200.scene import Scene
+    scene = Scene(args.workload)
+    r = cpu_sample_run(scene, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_text(scene), "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from stratusgfx_b200.gipass import VplGiPass
+    from stratusgfx_b200.scene import Scene
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scene = Scene(args.workload)
+    W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
+    if H % (5 * world):
+        raise SystemExit(f"height {H} does not split into {world} bands of whole 5-pixel tiles")
+    band = H // world
+    b0, b1 = rank * band, (rank + 1) * band
+    y0, y1 = (max(0, b0 - APRON), min(H, b1 + APRON)) if world > 1 else (0, H)
+    rows = y1 - y0
+
+    fp = scene.frame_params(0)
+    gb, pgb = scene.gbuffer(0, y0, rows), scene.gbuffer(-1, y0, rows)
+    vd, at = scene.vpls()
+    sh, df = scene.cubemaps()
+    csm = scene.csm(0)
+
+    gp = VplGiPass(W, H, y0, rows, scene.cube_res, scene.csm_res, iters, device=local_rank, use_torch_stream=True)
+    gp.set_gbuffer(gb, pgb)
+    gp.set_vpls(vd, at)
+    gp.set_atlases(sh, df)
+    gp.set_csm(csm)
+    gp.bind()
+
+    # per-step NCCL traffic of the band split: VPL table + atlas entries + the <= 5 cube maps refreshed this frame
+    refreshed = [int(at[i, 0]) * 320 + int(at[i, 1]) for i in range(min(5, N))]
+    if world > 1:
+        sa = gp.t["shadowAtlas"].view(-1, 6, scene.cube_res, scene.cube_res)
+        maps_buf = torch.stack([sa[s] for s in refreshed]).contiguous()
+        full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
+        gather_list = [full_out[r * band:(r + 1) * band] for r in range(world)] if rank == 0 else None
+
+    def step(i):
+        fp.time = 1000.0 + 16.0 * i
+        if world > 1:
+            dist.broadcast(gp.t["vplData"], 0)
+            dist.broadcast(gp.t["atlasEntryByVpl"], 0)
+            dist.broadcast(maps_buf, 0)
+            for j, s in enumerate(refreshed):
+                sa[s].copy_(maps_buf[j])
+        gp.frame(fp)
+        if world > 1:
+            dist.gather(gp.t["lightingOut"][b0 - y0:b1 - y0], gather_list, dst=0)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    fence()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = gp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    fence()
+    ms_total = e0.elapsed_time(e1)
+    launches = gp.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = W * H * N / (ms_step * 1e-3) / 1e9
+    V = gp.visible_count()
+
+    # ---- per-stage device times (CUDA events on the launching stream), for the roofline ----
+    stages = {}
+    order = [("cull", lambda: gp.cull(fp)), ("color", lambda: gp.color(fp)), ("tile_lists", lambda: gp.tile_lists(fp)), ("gather", lambda: gp.gather(fp))]
+    order += [(f"denoise_pass{i}", (lambda i=i: gp.denoise_pass(fp, i))) for i in range(iters)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(order) + 1)] for _ in range(args.steps)]
+    fence()
+    for k in range(args.steps):
+        fp.time = 1000.0 + 16.0 * (args.warmup + args.steps + k)
+        evs[k][0].record()
+        for j, (_, fn) in enumerate(order):
+            fn()
+            evs[k][j + 1].record()
+    fence()
+    for j, (name, _) in enumerate(order):
+        stages[name] = float(np.mean([evs[k][j].elapsed_time(evs[k][j + 1]) for k in range(args.steps)]))
+
+    # ---- end to end through the public host-buffer API: H2D of the frame's inputs, the pass, D2H of the lit image ----
+    slots = refreshed
+    R = scene.cube_res
+    gp.stage_host_inputs(gb, pgb, vd, at, csm,
+                         refreshed_maps=(slots, sh.reshape(-1, 6, R, R)[slots], df.reshape(-1, 6, R, R, 4)[slots]))
+    for i in range(2):
+        gp.frame_host(fp)
+    fence()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        fp.time = 1000.0 + 16.0 * i
+        gp.frame_host(fp)
+    fence()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d, d2h = gp.h2d_bytes, gp.d2h_bytes
+    if world > 1:
+        t = torch.tensor([float(h2d), float(d2h)], device=dev)
+        dist.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
+
+    if rank == 0:
+        P, T = W * rows, (W // 5) * (rows // 5)
+        ab = algorithmic_bytes(P, T, N, V, iters)
+        peak, peak_src = load_peaks()
+        per_stage = {}
+        for name, ms in stages.items():
+            key = {"tile_lists": None, "cull": "cull", "color": "color", "gather": "gather"}.get(name, "denoise_final" if name == f"denoise_pass{iters - 1}" else "denoise_pass")
+            b = ab["stage1"] + ab["stage2"] if name == "tile_lists" else ab[key]
+            per_stage[name] = {"ms": round(ms, 5), "algorithmic_bytes": int(b), "gbs": round(b / (ms * 1e-3) / 1e9, 2), "hbm_frac": round(b / (ms * 1e-3) / 1e9 / peak, 4)}
+        dom = max(stages, key=stages.get)
+        d = per_stage[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s", "frac": d["hbm_frac"], "traffic": None,
+                    "peak_source": peak_src, "share_of_step": round(stages[dom] / sum(stages.values()), 4),
+                    "frame_algorithmic_bytes": int(ab["frame"]), "frame_hbm_frac": round(ab["frame"] / (sum(stages.values()) * 1e-3) / 1e9 / peak, 4)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
+                           "parallelism": "single GPU" if world == 1 else f"{world} row bands of {band} rows + {APRON}-row apron, NCCL broadcast of VPL table and 5 cube maps, NCCL gather of lit bands",
+                           "visible_vpls": V, "storage": "f16/unorm8 planes"},
+                "clocks": clocks,
+                "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches),
+                "roofline": roofline,
+                "stages": per_stage}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_sample_run(scene, 1, 1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    gp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c4", choices=["tiny", "c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        if world != max(args.gpus, 1) and world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,9 +13,10 @@
 //
 // Each function follows one shader entry point; citations are relative to the
 // StratusGFX tree.  GL fixed-function semantics (texel addressing, cube-face
-// selection, hardware PCF, 16F stores) follow SURVEY.md Appendix A.  Whole frames
-// only (no row bands): the band logic of the product is checked against rows of
-// the whole-frame result.
+// selection, hardware PCF, 16F stores) follow SURVEY.md Appendix A.  Parity tests run
+// it on whole frames (the product's band logic is checked against rows of the
+// whole-frame result); OrcDims::y_offset/full_height exist so the CPU-baseline timing
+// can take a bounded row-band sample of a 4K/8K frame with the right coordinates.
 //
 // Build: g++ -O2 -std=c++17 -fopenmp -ffp-contract=off  (no FMA contraction, no fast-math)
 #include <cstdint>
@@ -294,9 +295,12 @@ inline float bilinMix(const Bilin& k, float t00, float t10, float t01, float t11
 extern "C" {
 
 typedef struct OrcDims {
-    int32_t width, height;     // whole frame
+    int32_t width, height;     // rows held by the per-pixel planes (== the whole frame unless y_offset/full_height say otherwise)
     int32_t cube_res, csm_res;
+    int32_t y_offset;          // first frame row of the planes; used for the bounded CPU-baseline samples of large frames
+    int32_t full_height;       // 0 = height
 } OrcDims;
+static inline int orcFullH(const OrcDims* dm) { return dm->full_height > 0 ? dm->full_height : dm->height; }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
 uint16_t orc_f2h(float f) { return f2h(f); }
@@ -371,6 +375,7 @@ int orc_stage1(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
                SgiVplStage1PerTileOutputs* out) {
     const int W = dm->width, H = dm->height;
     const int tilesX = W / SGI_TILE_DIVISOR, tilesY = H / SGI_TILE_DIVISOR;
+    const int fullTilesY = orcFullH(dm) / SGI_TILE_DIVISOR, yOff = dm->y_offset;
     const mat4 invPV = loadMat(fp->invProjectionView);
     const float localWorkGroupSize = 25.0f;
     #pragma omp parallel for schedule(static)
@@ -378,7 +383,7 @@ int orc_stage1(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
         vec3 averageLocalPosition(0.0f), averageLocalNormal(0.0f);
         for (int i = 0; i < 25; ++i) {                // gl_LocalInvocationIndex = ly*5 + lx
             const int px = tx * 5 + (i % 5), py = ty * 5 + (i / 5);
-            const vec2 texCoords = (vec2((float)px, (float)py) + vec2(0.5f)) / vec2((float)(tilesX * 5), (float)(tilesY * 5));
+            const vec2 texCoords = (vec2((float)px, (float)(py + yOff)) + vec2(0.5f)) / vec2((float)(tilesX * 5), (float)(fullTilesY * 5));
             const float depth = gDepth[(size_t)py * W + px];
             const vec3 fragPos = worldPositionFromDepth(texCoords, depth, invPV);
             const vec3 normal = decodeNormal(gNormal4 + ((size_t)py * W + px) * 4);
@@ -452,6 +457,7 @@ int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
                const SgiVplData* lightData, const int32_t* numVisible, const SgiAtlasEntry* shadowIndices,
                const void* const* shadowCubeMaps, uint16_t* colorOutH4, uint16_t* reservoirOutH4, int64_t* sampleStats) {
     const int W = dm->width, H = dm->height, cubeRes = dm->cube_res;
+    const int fullH = orcFullH(dm), yOff = dm->y_offset;
     const mat4 invPV = loadMat(fp->invProjectionView);
     const vec3 viewPosition(fp->viewPosition[0], fp->viewPosition[1], fp->viewPosition[2]);
     const float time = fp->time;
@@ -461,8 +467,8 @@ int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
     #pragma omp parallel for schedule(dynamic, 4) reduction(+ : itersTotal, shadedTotal, fetchTotal)
     for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
         const size_t p = (size_t)y * W + x;
-        const vec2 pixelCoords((float)x + 0.5f, (float)y + 0.5f);                     // gl_FragCoord.xy
-        const vec2 texCoords(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);   // fsTexCoords (Appendix A1)
+        const vec2 pixelCoords((float)x + 0.5f, (float)(y + yOff) + 0.5f);            // gl_FragCoord.xy
+        const vec2 texCoords(((float)x + 0.5f) / (float)W, ((float)(y + yOff) + 0.5f) / (float)fullH);   // fsTexCoords (Appendix A1)
         const float depth = gDepth[p];
         const vec3 fragPos = worldPositionFromDepth(texCoords, depth, invPV);
         const vec3 viewDir = normalize(viewPosition - fragPos);
@@ -546,6 +552,7 @@ typedef struct OrcDenoisePass {
 
 int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoisePass* ps) {
     const int W = dm->width, H = dm->height;
+    const int fullH = orcFullH(dm), yOff = dm->y_offset;
     const float time = fp->time;
     const float framesPerSecond = (float)(1.0 / fp->deltaSeconds);
     const int multiplier = ps->multiplier;
@@ -554,7 +561,7 @@ int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoi
     #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
         const size_t p = (size_t)y * W + x;
-        const vec2 fsTexCoords(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+        const vec2 fsTexCoords(((float)x + 0.5f) / (float)W, ((float)(y + yOff) + 0.5f) / (float)fullH);
         const vec3 screenColor(h2f(ps->screenH4[p * 4]), h2f(ps->screenH4[p * 4 + 1]), h2f(ps->screenH4[p * 4 + 2]));
         const vec2 velocityVal(h2f(ps->velocityH2[p * 2]), h2f(ps->velocityH2[p * 2 + 1]));
         const vec2 prevTexCoords = fsTexCoords - velocityVal;
@@ -566,7 +573,7 @@ int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoi
         vec4 reservoirFiltered(0.0f);
         if (ps->mergeReservoirs) {
             // computeMergedReservoir (:192-273) with minmaxNearest = 0: the centre texel only
-            vec3 seed((float)x + 0.5f, (float)y + 0.5f, time);
+            vec3 seed((float)x + 0.5f, (float)(y + yOff) + 0.5f, time);
             vec4 centerReservoir(0.0f);
             const float depthCutoff = 0.1f * centerDepth;
             float runningSum = 0.0f;
@@ -616,7 +623,8 @@ int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoi
         if (ps->final_) {
             float accumMultiplier = 1.0f;
             const vec3 currGi = shadowFactor;
-            const Bilin k = bilinSetup(prevTexCoords.x, prevTexCoords.y, W, H);
+            Bilin k = bilinSetup(prevTexCoords.x, prevTexCoords.y, W, fullH);
+            k.j0 = clampi(k.j0 - yOff, 0, H - 1); k.j1 = clampi(k.j1 - yOff, 0, H - 1);
             const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
             const float prevCenterDepth = bilinMix(k, ps->prevDepth[q00], ps->prevDepth[q10], ps->prevDepth[q01], ps->prevDepth[q11]);
             vec3 pn;
@@ -629,7 +637,8 @@ int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoi
                                      h2f(ps->prevIndirectIlluminationH4[q01 * 4 + c]), h2f(ps->prevIndirectIlluminationH4[q11 * 4 + c]));
             const float currId = ps->ids[p];
             // prevIds is NEAREST (BE:418)
-            const int ni = clampi((int)floor(prevTexCoords.x * (float)W), 0, W - 1), nj = clampi((int)floor(prevTexCoords.y * (float)H), 0, H - 1);
+            const int ni = clampi((int)floor(prevTexCoords.x * (float)W), 0, W - 1);
+            const int nj = clampi(clampi((int)floor(prevTexCoords.y * (float)fullH), 0, fullH - 1) - yOff, 0, H - 1);
             const float prevId = ps->prevIds[(size_t)nj * W + ni];
             const float wn = max(0.0f, dot(centerNormal, prevCenterNormal));
             const float wz = exp(-abs(centerDepth - prevCenterDepth));

@@ -40,7 +40,8 @@ def build(force=False):
 
 
 class OrcDims(C.Structure):
-    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cube_res", C.c_int32), ("csm_res", C.c_int32)]
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("cube_res", C.c_int32), ("csm_res", C.c_int32),
+                ("y_offset", C.c_int32), ("full_height", C.c_int32)]
 
 
 class OrcDenoisePass(C.Structure):
@@ -99,10 +100,10 @@ def _atlas_ptrs(arr):
 class OracleFrame:
     """Whole-frame CPU pipeline over numpy buffers, keeping temporal state between frames."""
 
-    def __init__(self, width, height, cube_res=32, csm_res=1024, denoise_iters=4, variant="own"):
+    def __init__(self, width, height, cube_res=32, csm_res=1024, denoise_iters=4, variant="own", y_offset=0, full_height=0):
         self.L = lib(variant)
         self.W, self.H = width, height
-        self.dims = OrcDims(width, height, cube_res, csm_res)
+        self.dims = OrcDims(width, height, cube_res, csm_res, y_offset, full_height)
         self.denoise_iters = denoise_iters
         self.tiles = (width // TILE_DIVISOR) * (height // TILE_DIVISOR)
         z4 = lambda: np.zeros((height, width, 4), np.float16)

@@ -204,6 +204,57 @@ class VplGiPass:
         self.synchronize()
         return self.t[name].cpu().numpy()
 
+    # ---- host-buffer entry point (what a caller without device-resident buffers uses) -----------------
+    def stage_host_inputs(self, gb, prev_gb, vpl_data, atlas_by_vpl, csm, refreshed_maps=None):
+        """Register one frame's HOST inputs (numpy).  They are kept in pinned memory; `frame_host`
+        copies them to the device every call.  `refreshed_maps` = (slot indices, depth [k,6,R,R] uint16,
+        diffuse [k,6,R,R,4] uint8): the <= 5 cube maps re-rendered this frame (StratusRendererBackend.h:378)."""
+        torch = self.torch
+        get = (lambda o, k: getattr(o, k)) if not isinstance(gb, dict) else (lambda o, k: o[k])
+        host = {}
+        for k in ("depth", "normal", "albedo", "baseReflectivity", "roughnessMetallicAmbient", "velocity", "id", "ssao", "screen"):
+            host[k] = torch.from_numpy(np.ascontiguousarray(get(gb, k))).pin_memory()
+        host["prevNormal"] = torch.from_numpy(np.ascontiguousarray(get(prev_gb, "normal"))).pin_memory()
+        host["prevId"] = torch.from_numpy(np.ascontiguousarray(get(prev_gb, "id"))).pin_memory()
+        host["prevDepth"] = torch.from_numpy(np.ascontiguousarray(get(prev_gb, "depth"))).pin_memory()
+        host["vplData"] = torch.from_numpy(np.ascontiguousarray(vpl_data)).pin_memory()
+        host["atlasEntryByVpl"] = torch.from_numpy(np.ascontiguousarray(atlas_by_vpl)).pin_memory()
+        host["infiniteLightShadowMap"] = torch.from_numpy(np.ascontiguousarray(csm)).pin_memory()
+        self._host = host
+        self._host_maps = None
+        if refreshed_maps is not None:
+            slots, dep, dif = refreshed_maps
+            self._host_maps = (list(slots), torch.from_numpy(np.ascontiguousarray(dep).view(np.int16)).pin_memory(),
+                               torch.from_numpy(np.ascontiguousarray(dif)).pin_memory())
+        for k, v in host.items():
+            if k not in self.t or self.t[k].shape != v.shape:
+                self.t[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+        if "vplVisibleIndices" not in self.t or self.t["vplVisibleIndices"].numel() != host["vplData"].shape[0] + 1:
+            self.t["vplVisibleIndices"] = torch.zeros(host["vplData"].shape[0] + 1, dtype=torch.int32, device=self.device)
+        self._host_out = torch.empty((self.rows, self.width, 4), dtype=torch.float16).pin_memory()
+        self.bind()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+        if self._host_maps:
+            self.h2d_bytes += self._host_maps[1].numel() * 2 + self._host_maps[2].numel()
+        self.d2h_bytes = self._host_out.numel() * 2
+
+    def frame_host(self, fp):
+        """One frame from HOST buffers: H2D of every per-frame input, the whole pass, D2H of the lit image.
+        Requires use_torch_stream=True so copies and kernels share one stream.  Returns the pinned result."""
+        with self.torch.cuda.device(self.device):
+            for k, v in self._host.items():
+                self.t[k].copy_(v, non_blocking=True)
+            if self._host_maps:
+                slots, dep, dif = self._host_maps
+                sa = self.t["shadowAtlas"].view(-1, 6, self.cube_res, self.cube_res)
+                da = self.t["diffuseAtlas"].view(-1, 6, self.cube_res, self.cube_res, 4)
+                for j, s in enumerate(slots):
+                    sa[s].copy_(dep[j], non_blocking=True)
+                    da[s].copy_(dif[j], non_blocking=True)
+            self.frame(fp)
+            self._host_out.copy_(self.t["lightingOut"], non_blocking=True)
+        return self._host_out
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self.L.sgi_destroy(self._h)

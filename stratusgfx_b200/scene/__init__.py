@@ -44,6 +44,7 @@ def _load():
         _lib.sgs_vpls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.sgs_cubemaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.sgs_csm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.sgs_sun_visibility.argtypes = [C.c_void_p, C.c_void_p]
         _lib.sgs_float_to_half.restype = C.c_uint16
         _lib.sgs_float_to_half.argtypes = [C.c_float]
     return _lib
@@ -142,6 +143,12 @@ class Scene:
         diffuse = np.zeros((A, MAX_TOTAL_SHADOWS_PER_ATLAS, 6, R, R, 4), np.uint8)
         _load().sgs_cubemaps(self._h, 0, self.num_vpls, _ptr(depth), _ptr(diffuse))
         return depth, diffuse
+
+    def sun_visibility(self):
+        """Ray-traced (exact geometry) sun visibility per VPL, uint8 [N]."""
+        out = np.zeros(self.num_vpls, np.uint8)
+        _load().sgs_sun_visibility(self._h, _ptr(out))
+        return out
 
     def csm(self, frame=0):
         out = np.empty((4, self.csm_res, self.csm_res), np.float32)

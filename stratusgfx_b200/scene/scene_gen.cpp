@@ -514,6 +514,17 @@ int sgs_csm(void* p, int frame, float* depth) {
     return 0;
 }
 
+// Exact (ray-traced) sun visibility of every VPL position: an independent check of the CSM chain.
+int sgs_sun_visibility(void* p, uint8_t* out) {
+    Scene& s = *(Scene*)p;
+    for (int k = 0; k < s.N; ++k) {
+        const SgiVplData& v = s.vpls[k];
+        Hit h = trace(s, V3{v.position[0], v.position[1], v.position[2]}, s.sunDir * -1.0);
+        out[k] = (h.box <= 0) ? 1 : 0;
+    }
+    return 0;
+}
+
 uint16_t sgs_float_to_half(float f) { return f2h(f); }
 
 }  // extern "C"

@@ -1,0 +1,256 @@
+"""What pins the CPU oracle, given that the reference holds no golden vectors for this path
+(SURVEY.md §4, §8c): the self-checks 1-7 of SURVEY.md §8(c), RNG known answers from an
+independent pure-Python restatement (tests/golden/), and a bit-for-bit comparison of the
+oracle's own maths layer against the reference's vendored glm (oracle/_ref build)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from stratusgfx_b200._abi import FrameParams, MAX_TOTAL_VPLS_PER_FRAME
+from tests.parity_util import SceneData, run_oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+f32 = np.float32
+
+
+# ---- (7) RNG known answers ------------------------------------------------------------------------
+def test_rng_known_answers(built):
+    from oracle.oracle_py import lib
+    L = lib()
+    for c in json.load(open(os.path.join(GOLDEN, "rng_kat.json"))):
+        assert L.orc_hash3(c["x"], c["y"], c["time"]) == c["hash"]
+        r = L.orc_random3(c["x"], c["y"], c["time"])
+        assert np.float32(r).view(np.uint32) == c["random_bits"]
+        assert 0.0 <= r < 1.0
+
+
+def test_half_conversion_matches_numpy(built):
+    from oracle.oracle_py import lib
+    L = lib()
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.standard_normal(2000).astype(f32) * 10.0 ** rng.integers(-8, 5, 2000),
+                           np.array([0.0, 65504.0, 65519.9, 65520.0, 1e-8, 6e-8, 2.0 ** -24, 2.0 ** -25, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11], f32)])
+    for v in vals:
+        assert L.orc_f2h(float(v)) == int(np.float16(v).view(np.uint16)), v
+    for h in rng.integers(0, 0x7c00, 500):
+        assert L.orc_h2f(int(h)) == float(np.uint16(h).view(np.float16))
+
+
+# ---- glm cross-check --------------------------------------------------------------------------------
+def test_own_maths_layer_is_bit_identical_to_reference_glm(tiny, tiny_oracle):
+    from oracle import oracle_py
+    if not oracle_py.has_variant("glm"):
+        pytest.skip("oracle/_ref/liboracle_glm.so not built (needs the reference tree's glm headers)")
+    from oracle.oracle_py import OracleFrame
+    s = tiny.scene
+    o = OracleFrame(tiny.W, tiny.H, s.cube_res, s.csm_res, s.denoise_iters, variant="glm")
+    assert o.L.orc_uses_glm() == 1
+    for f in range(2):
+        o.frame(tiny.fp[f], tiny.gb[f], tiny.gb[f - 1], tiny.vpl_data, tiny.atlas_by_vpl, tiny.csm[f], tiny.shadow_atlas, tiny.diffuse_atlas, keep_passes=True)
+        ref = tiny_oracle[f]
+        assert np.array_equal(o.visible, ref["visible"])
+        assert np.array_equal(o.updated.view(np.uint32), ref["updated"].view(np.uint32))
+        assert np.array_equal(o.stage1.view(np.uint32), ref["stage1"].view(np.uint32))
+        assert np.array_equal(o.stage2, ref["stage2"])
+        for name in ("gi_color", "gi_reservoir", "combined", "gi_illum", "history"):
+            assert np.array_equal(getattr(o, name).view(np.uint16), ref[name].view(np.uint16)), name
+        for a, b in zip(o.pass_reservoirs, ref["pass_reservoirs"]):
+            assert np.array_equal(a.view(np.uint16), b.view(np.uint16))
+
+
+# ---- (2) cull: ordered compaction is the serial loop ---------------------------------------------------
+def test_cull_is_ordered_compaction(tiny, tiny_oracle):
+    o = tiny_oracle[0]
+    V = int(o["visible"][0])
+    idx = o["visible"][1:V + 1]
+    assert 0 < V <= tiny.N
+    assert np.all(np.diff(idx) > 0)                              # ascending original index = serial order
+    assert np.array_equal(o["entries"][:V], tiny.atlas_by_vpl[idx])
+    # position/radius fields are copied verbatim (colour/specularPosition are rewritten by a2)
+    assert np.array_equal(o["updated"][:V, 0:4], tiny.vpl_data[idx, 0:4])
+    assert np.array_equal(o["updated"][:V, 12:16], tiny.vpl_data[idx, 12:16])
+
+
+def test_cull_agrees_with_ray_traced_sun_visibility(built):
+    d = SceneData("c1")
+    o = run_oracle(d, keep_passes=False)[0]
+    V = int(o["visible"][0])
+    vis = np.zeros(d.N, bool); vis[o["visible"][1:V + 1]] = True
+    truth = d.scene.sun_visibility().astype(bool)
+    # the CSM test is a 3x3 PCF neighbourhood at 1024^2, so it may keep a few VPLs the exact ray test rejects
+    assert (vis == truth).mean() >= 0.9
+    assert vis[truth].mean() >= 0.95
+
+
+# ---- (1) stage 2 == brute force "stable sort, take 12" -------------------------------------------------
+def test_stage2_equals_bruteforce_stable_sort(tiny, tiny_oracle):
+    o = tiny_oracle[0]
+    V = int(o["visible"][0]); idx = o["visible"][1:V + 1]
+    L = tiny.vpl_data
+    for t in range(0, o["stage1"].shape[0], 7):
+        p = o["stage1"][t, 0:3].astype(f32); n = o["stage1"][t, 4:7].astype(f32)
+        d = (L[idx, 0:3].astype(f32) - p[None, :]).astype(f32)
+        nd = (n[None, :] * d).astype(f32); side = ((nd[:, 0] + nd[:, 1]).astype(f32) + nd[:, 2]).astype(f32)
+        dd = (d * d).astype(f32); l2 = ((dd[:, 0] + dd[:, 1]).astype(f32) + dd[:, 2]).astype(f32)
+        ratio = (np.sqrt(l2).astype(f32) / L[idx, 12].astype(f32)).astype(f32)
+        ok = ~(side < 0) & ~(ratio > 1.0)
+        cand = np.nonzero(ok)[0]
+        order = cand[np.argsort(ratio[cand], kind="stable")][:12]
+        cnt = int(o["stage2"][t, 0])
+        assert cnt == len(order)
+        assert np.array_equal(o["stage2"][t, 1:1 + cnt], idx[order])
+
+
+# ---- (3) pass 0 == rgb / a ------------------------------------------------------------------------------
+def test_denoise_pass0_is_rgb_over_a(tiny_oracle):
+    o = tiny_oracle[0]
+    res = o["gi_reservoir"].astype(f32)
+    want = (res[..., :3] / np.maximum(f32(1e-5), res[..., 3:4])).astype(f32).astype(np.float16)
+    got = o["pass_reservoirs"][0]
+    assert np.array_equal(got[..., :3].view(np.uint16), want.view(np.uint16))
+    assert np.all(got[..., 3] == 1.0)
+
+
+# ---- (4) uniform guides -> box mean ------------------------------------------------------------------------
+def _denoise_pass(L, W, H, multiplier, reservoir, normal, depth, final=0, merge=0):
+    from oracle.oracle_py import OrcDenoisePass, OrcDims, _p
+    fp = FrameParams(); fp.time = 1000.0; fp.deltaSeconds = 1 / 60.0
+    dims = OrcDims(W, H, 32, 1024, 0, 0)
+    z4 = lambda: np.zeros((H, W, 4), np.float16)
+    outs = dict(combined=z4(), gi=z4(), reservoir=z4(), history=np.zeros((H, W), np.float16))
+    keep = dict(screen=z4(), vel=np.zeros((H, W, 2), np.float16), ids=np.zeros((H, W), f32), illum=z4(), prevgi=z4(), hist=np.zeros((H, W), np.float16))
+    ps = OrcDenoisePass()
+    ps.multiplier, ps.mergeReservoirs, ps.final_, ps.numVisible = multiplier, merge, final, 8
+    ps.screenH4, ps.velocityH2, ps.normal4, ps.ids, ps.depth = _p(keep["screen"]), _p(keep["vel"]), _p(normal), _p(keep["ids"]), _p(depth)
+    ps.prevNormal4, ps.prevIds, ps.prevDepth = _p(normal), _p(keep["ids"]), _p(depth)
+    ps.indirectIlluminationH4, ps.indirectShadowsH4 = _p(keep["illum"]), _p(reservoir)
+    ps.prevIndirectIlluminationH4, ps.historyDepthH = _p(keep["prevgi"]), _p(keep["hist"])
+    ps.combinedOutH4, ps.giOutH4, ps.reservoirOutH4, ps.historyOutH = _p(outs["combined"]), _p(outs["gi"]), _p(outs["reservoir"]), _p(outs["history"])
+    L.orc_denoise_pass(C.addressof(fp), C.addressof(dims), C.addressof(ps))
+    return outs
+
+
+@pytest.mark.parametrize("multiplier", [1, 3, 7])
+def test_atrous_on_uniform_guides_is_a_box_mean(built, multiplier):
+    from oracle.oracle_py import lib
+    W, H = 48, 40
+    rng = np.random.default_rng(multiplier)
+    reservoir = np.ones((H, W, 4), np.float16)
+    reservoir[..., :3] = rng.random((H, W, 3)).astype(np.float16)
+    normal = np.zeros((H, W, 4), np.uint8); normal[...] = (128, 128, 255, 255)
+    depth = np.full((H, W), 0.75, f32)
+    out = _denoise_pass(lib(), W, H, multiplier, reservoir, normal, depth)["reservoir"].astype(np.float64)
+    src = reservoir[..., :3].astype(np.float64)
+    step = 1 + multiplier
+    acc = np.zeros_like(src)
+    for dx in range(-2, 3):
+        xs = np.clip(np.arange(W) + dx * step, 0, W - 1)
+        for dy in range(-2, 3):
+            ys = np.clip(np.arange(H) + dy * step, 0, H - 1)
+            acc += src[ys][:, xs]
+    want = acc / 25.0
+    # every weight is exactly 1 here (identical normals: dot -> 1 within 1 ulp, ^128 keeps it within 2e-5)
+    assert np.max(np.abs(out[..., :3] - want)) < 1.5e-3      # half output: 2^-11 relative on values < 1, plus the ^128 slack
+    assert np.all(out[..., 3] == 1.0)
+
+
+# ---- (5) temporal accumulation on a static camera ----------------------------------------------------------
+def test_static_camera_history_counts_frames_and_gi_is_running_mean(built):
+    d = SceneData("tiny", frames=4)
+    outs = run_oracle(d)
+    prev = None
+    for t, o in enumerate(outs, start=1):
+        assert np.all(o["history"] == np.float16(min(t, 60))), t          # history = min(t, 1/dt)
+        curr = o["pass_reservoirs"][-1][..., :3].astype(f32)
+        if prev is None:
+            want = curr
+        else:
+            want = prev + f32(1.0 / t) * (curr - prev)                     # mix(prev, curr, 1/history)
+        got = o["gi_illum"][..., :3].astype(f32)
+        assert np.allclose(got, want, rtol=2e-3, atol=1e-6)
+        prev = got
+
+
+# ---- (6) energy: one unshadowed VPL over a plane vs closed-form (float64) -------------------------------------
+def test_gather_single_light_matches_closed_form(built):
+    from oracle.oracle_py import OracleFrame, _atlas_ptrs
+    W, H = 20, 10
+    s = SceneData("tiny").scene          # only for a valid camera / params
+    fp = s.frame_params(0)
+    fp.minGiOcclusionFactor = 0.95
+    cam = np.array(list(fp.viewPosition), np.float64)
+    invPV = np.array(list(fp.invProjectionView), np.float64).reshape(4, 4).T     # column-major -> matrix
+    depth = np.full((H, W), 0.9, f32)
+    normal = np.zeros((H, W, 4), np.uint8); normal[...] = (128, 128, 0, 255)      # ~ -z, facing the camera
+    albedo = np.zeros((H, W, 4), np.uint8); albedo[...] = (200, 120, 60, 0)
+    refl = np.zeros((H, W, 2), np.uint8); refl[..., 0] = 128
+    rma = np.zeros((H, W, 4), np.uint8); rma[..., 0] = 204
+    ssao = np.ones((H, W), np.float16)
+    o = OracleFrame(W, H, 32, 1024, 4)
+    # two identical lights: index = int((V-1)*rand) is always 0 for V = 2 (the last VPL is never drawn)
+    light_pos = cam + np.array([3.0, 4.0, 1.0])
+    o.updated = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 16), f32)
+    for k in range(2):
+        o.updated[k, 0:3] = light_pos; o.updated[k, 3] = 1
+        o.updated[k, 4:7] = (7.0, 5.0, 3.0); o.updated[k, 7] = 1
+        o.updated[k, 8:11] = light_pos + np.array([0.5, -0.25, 0.125]); o.updated[k, 11] = 1
+        o.updated[k, 12:15] = (500.0, 500.0, 0.02)
+    o.visible = np.array([2, 0, 1], np.int32)
+    o.entries = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 2), np.int32)
+    shadow = np.full((1, 320, 6, 32, 32), 65535, np.uint16)                      # nothing occludes
+    o._sh_ptrs = _atlas_ptrs(shadow)
+
+    class GB: pass
+    gb = GB(); gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao = depth, normal, albedo, refl, rma, ssao
+    o.gather(fp, gb)
+    res = o.gi_reservoir.astype(np.float64)
+    got = res[..., :3] / res[..., 3:4]                                           # mean contribution per sample
+
+    # closed form in float64 for every pixel
+    xs, ys = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    ndc = np.stack([xs / W * 2 - 1, ys / H * 2 - 1, np.full_like(xs, float(f32(0.9)) * 2 - 1), np.ones_like(xs)], -1)
+    wp = ndc @ invPV.T
+    P = wp[..., :3] / wp[..., 3:4]
+    n = np.array([128, 128, 0]) / 255.0 * 2 - 1; n /= np.linalg.norm(n)
+    base = np.maximum(np.array([200, 120, 60]) / 255.0, 0.01)
+    rough = max(0.5, 204 / 255.0); rr = max(0.08, rough * rough)
+    Vv = cam - P; dist = np.linalg.norm(Vv, axis=-1, keepdims=True); Vd = Vv / dist
+
+    def atten(Ld):
+        ld = np.linalg.norm(Ld, axis=-1)
+        ratio = np.minimum(ld / 500.0, 1.0)
+        return 1.0 / ((10 + np.exp(-3 * ratio) * (1 - 10)) * 500.0 + ld * ld)
+
+    def dots(Ld):
+        Lh = Ld / np.linalg.norm(Ld, axis=-1, keepdims=True); Hh = Vd + Lh; Hh /= np.linalg.norm(Hh, axis=-1, keepdims=True)
+        sat = lambda v: np.clip(v, 0, 1)
+        return sat((Vd * n).sum(-1)), sat((Lh * n).sum(-1)), sat((Hh * n).sum(-1)), sat((Lh * Hh).sum(-1))
+
+    Ls = light_pos + np.array([0.5, -0.25, 0.125]) - P
+    Ld = light_pos - P
+    NdV, NdL, NdH, LdH = dots(Ls)
+    r2 = rr * rr
+    f = (NdH * r2 - NdH) * NdH + 1
+    ndf = r2 / np.maximum(np.pi * f * f, 1e-5)
+    vis = 0.5 / np.maximum(NdL * np.sqrt((NdV - r2 * NdV) * NdV + r2) + NdV * np.sqrt((NdL - r2 * NdL) * NdL + r2), 1e-5)
+    f0 = 0.16 * (128 / 255.0) ** 2 * (1.0 / (base + 1e-5))
+    fr = (1 - LdH) ** 5
+    spec = (ndf * vis)[..., None] * (fr[..., None] + f0 * (1 - fr[..., None])) * NdL[..., None] * atten(Ls)[..., None]
+    _, NdL2, _, _ = dots(Ld)
+    diff = (base / (base + 1e-5)) / np.pi * NdL2[..., None] * atten(Ld)[..., None]
+    want = (spec + diff) * np.array([7.0, 5.0, 3.0])
+    assert np.all(NdL2 > 0.05)                                                    # the light really faces the plane
+    assert np.allclose(got, want, rtol=3e-3, atol=1e-7)                           # half output: ~1e-3 relative
+
+
+def test_gather_outputs_are_bounded_and_weights_at_least_one(tiny_oracle):
+    o = tiny_oracle[0]
+    res = o["gi_reservoir"].astype(f32)
+    assert np.all(np.isfinite(res)) and np.all(res[..., :3] >= 0) and np.all(res[..., :3] <= 65504)
+    assert np.all(res[..., 3] >= 1.0)
+    it, shaded, fetch = o["sample_stats"]
+    P = res.shape[0] * res.shape[1]
+    assert P <= shaded <= 6 * P and shaded <= it <= 11 * P                          # 1..6 samples, <= 5 re-draws
