@@ -171,6 +171,10 @@ def run_ours(args, rank, world, local_rank):
     sh, df = scene.cubemaps()
     csm = scene.csm(0)
 
+    side = torch.cuda.Stream(device=dev)     # everything (kernels, copies, NCCL, events) runs on this one stream
+    torch.cuda.synchronize(dev)
+    ctx = torch.cuda.stream(side)
+    ctx.__enter__()
     gp = VplGiPass(W, H, y0, rows, scene.cube_res, scene.csm_res, iters, device=local_rank, use_torch_stream=True)
     gp.set_gbuffer(gb, pgb)
     gp.set_vpls(vd, at)
@@ -269,6 +273,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t)
         h2d, d2h = int(t[0].item()), int(t[1].item())
 
+    ctx.__exit__(None, None, None)
     if rank == 0:
         P, T = W * rows, (W // 5) * (rows // 5)
         ab = algorithmic_bytes(P, T, N, V, iters)

@@ -82,8 +82,12 @@ class VplGiPass:
         rows = full_height - y_offset if rows is None else rows
         self.width, self.full_height, self.y_offset, self.rows = width, full_height, y_offset, rows
         self.cube_res, self.csm_res, self.denoise_iters = cube_res, csm_res, denoise_iters
-        cp = CreateParams(width, full_height, y_offset, rows, cube_res, csm_res, denoise_iters, device,
-                          torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None)
+        stream = None
+        if use_torch_stream:
+            # run on torch's current stream.  Its default stream has handle 0, which the ABI reads as
+            # "create your own", so name the legacy default stream explicitly (cudaStreamLegacy == 0x1).
+            stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        cp = CreateParams(width, full_height, y_offset, rows, cube_res, csm_res, denoise_iters, device, stream)
         self._h = C.c_void_p()
         rc = self.L.sgi_create(C.byref(cp), C.byref(self._h))
         if rc != _abi.SGI_OK:
