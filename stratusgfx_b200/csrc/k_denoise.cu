@@ -14,6 +14,13 @@
 // Non-final passes write only the reservoir attachment: the other three attachments of the
 // reference's FBO are dead until the final pass (combined/gi are overwritten, history is passed
 // through unchanged, and `indirectIllumination` is the unchanged albedo plane of the gather).
+//
+// Arithmetic tiers.  The reference evaluates the 25 tap weights through the texture units, a
+// normalize, pow(x,128) and exp per tap; here the decoded normal and the depth of every pixel are
+// stored once per frame in a float4 "guide" plane (bit-identical to normalize(rgb*2-1)), x^128 is
+// seven squarings, exp is ex2.approx, and the weighted sum uses FMA.  That is radiance arithmetic
+// (tolerance 1e-3 relative / 60 dB PSNR); the one decision in this shader — the history reset
+// `similarity < 0.99` — stays in exact IEEE arithmetic in glm order.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -43,6 +50,14 @@ SGI_DEV float bilinMix(const Bilin& k, float t00, float t10, float t01, float t1
     return r;
 }
 
+__global__ void __launch_bounds__(256)
+prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* __restrict__ depth, float4* __restrict__ guide) {
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    const f3 nn = decodeNormal(__ldg(normal + p));
+    guide[p] = make_float4(nn.x, nn.y, nn.z, __ldg(depth + p));
+}
+
 template <bool MERGE, bool FINAL>
 __global__ void __launch_bounds__(kDnX * kDnY)
 denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
@@ -53,15 +68,16 @@ denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * W + x;
 
-    const f3 centerNormal = decodeNormal(__ldg(io.normal + p));
-    const float centerDepth = __ldg(io.depth + p);
+    const float4 gc = __ldg(io.guide + p);
+    const f3 centerNormal = mk3(gc.x, gc.y, gc.z);
+    const float centerDepth = gc.w;
 
-    f4 reservoirFiltered = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f, aw = 0.0f;
     if (MERGE) {
         // computeMergedReservoir with minmaxNearest = 0 (:259-264): the centre texel only
         const float depthCutoff = fmul(0.1f, centerDepth);
         float runningSum = 0.0f;
-        f4 centerReservoir = mk4(0.0f, 0.0f, 0.0f, 0.0f);
+        float cw = 0.0f;
         const float probabilisticWeight = fdiv(1.0f, (float)__ldg(io.numVisible));
         const bool normalReject = dot(centerNormal, centerNormal) < 0.906f;
         const bool depthReject = fabsf(fsub(centerDepth, centerDepth)) > depthCutoff;
@@ -69,42 +85,39 @@ denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_
             const f4 currReservoir = loadHalf4(io.shadowsIn, p);
             const float randUpdate = random3(fadd((float)x, 0.5f), fadd((float)y, 0.5f), fc.time);
             const float probability = fmul(currReservoir.w, probabilisticWeight);
-            centerReservoir.w = fadd(centerReservoir.w, probability);
-            if (randUpdate < fdiv(probability, centerReservoir.w)) {
-                centerReservoir.x = fadd(centerReservoir.x, currReservoir.x);
-                centerReservoir.y = fadd(centerReservoir.y, currReservoir.y);
-                centerReservoir.z = fadd(centerReservoir.z, currReservoir.z);
+            cw = fadd(cw, probability);
+            if (randUpdate < fdiv(probability, cw)) {
+                ax = currReservoir.x; ay = currReservoir.y; az = currReservoir.z;
                 runningSum = fadd(runningSum, currReservoir.w);
             }
         }
-        centerReservoir.w = runningSum;
-        reservoirFiltered = centerReservoir;
+        aw = runningSum;
     } else {
         const int step = 1 + io.multiplier;
+        int tys[5];
+        #pragma unroll
+        for (int k = 0; k < 5; ++k) tys[k] = iclamp(ly + (k - 2) * step, 0, rows - 1) * W;   // band-local clamp == CLAMP_TO_EDGE on a whole frame
         #pragma unroll
         for (int dx = -2; dx <= 2; ++dx) {
             const int tx = iclamp(x + dx * step, 0, W - 1);
             #pragma unroll
             for (int dy = -2; dy <= 2; ++dy) {
-                const int ty = iclamp(ly + dy * step, 0, rows - 1);   // band-local clamp == CLAMP_TO_EDGE on a whole frame
-                const size_t q = (size_t)ty * W + tx;
-                const f4 reservoir = loadHalf4(io.shadowsIn, q);
-                float filtered;
-                if (dx == 0 && dy == 0) filtered = 1.0f;
-                else {
-                    const float currDepth = __ldg(io.depth + q);
-                    const float wz = fdiv(expf(-fabsf(fsub(centerDepth, currDepth))), 1.0f);
-                    const f3 currNormal = decodeNormal(__ldg(io.normal + q));
-                    float wn = vmax(0.0f, dot(centerNormal, currNormal));
-                    wn = powf(wn, 128.0f);
-                    filtered = fmul(fmul(wn, wz), 1.0f);
+                const size_t q = (size_t)(tys[dy + 2] + tx);
+                const f4 r = loadHalf4(io.shadowsIn, q);
+                float w = 1.0f;
+                if (dx != 0 || dy != 0) {
+                    const float4 g = __ldg(io.guide + q);
+                    float wn = __fmaf_rn(gc.z, g.z, __fmaf_rn(gc.y, g.y, __fmul_rn(gc.x, g.x)));
+                    wn = fmaxf(wn, 0.0f);
+                    wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn;   // ^128
+                    w = wn * __expf(-fabsf(gc.w - g.w));
                 }
-                reservoirFiltered = reservoirFiltered + filtered * reservoir;
+                ax = __fmaf_rn(w, r.x, ax); ay = __fmaf_rn(w, r.y, ay); az = __fmaf_rn(w, r.z, az); aw = __fmaf_rn(w, r.w, aw);
             }
         }
     }
-    const float denom = vmax(PREVENT_DIV_BY_ZERO, reservoirFiltered.w);
-    const f3 shadowFactor = mk3(reservoirFiltered.x, reservoirFiltered.y, reservoirFiltered.z) / denom;
+    const float denom = vmax(PREVENT_DIV_BY_ZERO, aw);
+    const f3 shadowFactor = mk3(ax, ay, az) / denom;
     storeHalf4(io.reservoirOut, p, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
 
     if (FINAL) {
@@ -136,6 +149,7 @@ denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_
         const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);
         const float prevId = __ldg(io.prevIds + (size_t)nj * W + ni);
 
+        // the history-reset decision: exact IEEE arithmetic (expf(-0) == 1 exactly on a static camera)
         const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
         const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
         const float wid = currId != prevId ? 0.0f : 1.0f;
@@ -152,6 +166,12 @@ denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_
 }
 
 }  // namespace
+
+int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide) {
+    const size_t n = (size_t)bd.W * bd.rows;
+    prepareGuideKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, normal, depth, guide);
+    return 1;
+}
 
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_) {
     dim3 block(kDnX, kDnY);

@@ -11,9 +11,21 @@
 //   singleScatteringBRDF_Specular :102-115, NDF_GGX :51-55, Visibility_G_SmithGGX :59-64, Fr_Fresnel_Schlick :73-76)
 //   applyFog                             fog.glsl:37-41
 //
-// One thread per pixel.  Which VPL a pixel draws is a pure integer function of (x+0.5, y+0.5, time)
-// and the re-draw decision is IEEE-exact arithmetic in glm's evaluation order, so the light choice
-// is identical to the CPU transcription; only exp/pow differ (by ulps).
+// One thread per pixel.  Two arithmetic tiers:
+//
+//   DECISIONS (which VPL is drawn, re-draw or keep, sample budget, cube texel, shadowed or lit) are
+//   evaluated so that they come out exactly as the IEEE / glm-order evaluation of the shader text
+//   would: the light index is pure integer hashing of (x+0.5, y+0.5, time); every float comparison is
+//   first tried with a cheap FMA estimate and a conservative margin (1e-5 relative, >50x the rounding
+//   error of either evaluation) and falls back to the exact operation chain only when the estimate
+//   is inside that margin.  Both routes give the same answer by construction.
+//
+//   RADIANCE (attenuation, GGX, Fresnel, Lambert, accumulation) uses FMA, rsqrt/rcp/ex2 approximations
+//   and (1-u)^5 by multiplication.  It differs from the CPU transcription by a few float ulps, far
+//   inside the 1e-3 relative / 60 dB PSNR bar once stored as binary16.
+//
+// The kernel also writes the frame's "guide" plane (decoded normal + depth, float4) that the
+// denoiser passes read instead of re-decoding 25 normals per pixel per pass.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -23,69 +35,86 @@ namespace {
 constexpr float PI_F = 3.14159265359f;
 constexpr float PREVENT_DIV_BY_ZERO = 0.00001f;
 constexpr float HALF_FLOAT_MAX = 65504.0f;
+constexpr float kMargin = 1e-5f;
 constexpr int kGatherThreadsX = 32, kGatherThreadsY = 8;
 
-SGI_DEV float vplDiffuseAttenuation(f3 lightDir, float lightRadius) {
-    const float lightDist = length(lightDir);
-    const float ratio = vmin(fdiv(lightDist, lightRadius), 1.0f);
-    const float minDist = fmul(mix(10.0f, 1.0f, expf(fmul(-3.0f, ratio))), lightRadius);
-    return fdiv(1.0f, fadd(minDist, fmul(fmul(1.0f, lightDist), lightDist)));
+SGI_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SGI_DEV float rcpFast(float x) { return __fdividef(1.0f, x); }
+SGI_DEV float sqrtFast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SGI_DEV float dotFast(f3 a, f3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
+SGI_DEV float satFast(float x) { return __saturatef(x); }
+
+// ---- exact fallbacks (rarely executed) ----------------------------------------------------------------------
+__device__ __noinline__ bool exactRedraw(f3 normal, f3 lightMinusFrag, float lightRadius) {
+    const float distance = length(lightMinusFrag);
+    const float sideCheck = dot(normal, normalize(lightMinusFrag));
+    return sideCheck < 0.0f || distance > lightRadius;
+}
+__device__ __noinline__ int exactCubeTexel(f3 fragDir, int res) { return cubeTexel(fragDir, res); }
+__device__ __noinline__ bool exactShadowed(f3 fragDir, float lightNormalDot, float texelDepth, float farPlane) {
+    const float currentDepth = length(fragDir);
+    const float bias = fmul(currentDepth, vmax(0.1f, fmul(saturate(lightNormalDot), 0.03f)));
+    return fsub(currentDepth, bias) > fmul(texelDepth, farPlane);
 }
 
-SGI_DEV float NDF_GGX(float NdotH, float roughness) {
-    const float r2 = fmul(roughness, roughness);
-    const float f = fadd(fmul(fsub(fmul(NdotH, r2), NdotH), NdotH), 1.0f);
-    return fdiv(r2, vmax(fmul(fmul(PI_F, f), f), PREVENT_DIV_BY_ZERO));
-}
-
-SGI_DEV float Visibility_G_SmithGGX(float NdotV, float NdotL, float roughness) {
-    const float a2 = fmul(roughness, roughness);
-    const float ggxv = fmul(NdotL, fsqrt(fadd(fmul(fsub(NdotV, fmul(a2, NdotV)), NdotV), a2)));
-    const float ggxl = fmul(NdotV, fsqrt(fadd(fmul(fsub(NdotL, fmul(a2, NdotL)), NdotL), a2)));
-    return fdiv(0.5f, vmax(fadd(ggxv, ggxl), PREVENT_DIV_BY_ZERO));
-}
-
-struct Dots { float NdotV, NdotL, NdotH, LdotH; };
-SGI_DEV Dots BRDF_DotProducts(f3 V, f3 lightDir, f3 N) {
-    const f3 L = normalize(lightDir), H = normalize(V + L);
-    Dots d;
-    d.NdotV = saturate(dot(N, V)); d.NdotL = saturate(dot(N, L));
-    d.NdotH = saturate(dot(N, H)); d.LdotH = saturate(dot(L, H));
-    return d;
+// cube texel with exact semantics: estimate s*res, t*res; only a coordinate within 1e-4 of a texel edge
+// (or a near-tie between major axes) needs the exact division chain
+SGI_DEV int cubeTexelDecided(f3 d, int res) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face; float sc, tc, ma;
+    if (ax >= ay && ax >= az) { ma = ax; if (d.x >= 0.0f) { face = 0; sc = -d.z; tc = -d.y; } else { face = 1; sc = d.z; tc = -d.y; } }
+    else if (ay >= az)        { ma = ay; if (d.y >= 0.0f) { face = 2; sc = d.x; tc = d.z; } else { face = 3; sc = d.x; tc = -d.z; } }
+    else                      { ma = az; if (d.z >= 0.0f) { face = 4; sc = d.x; tc = -d.y; } else { face = 5; sc = -d.x; tc = -d.y; } }
+    // the face choice above uses exact comparisons of the inputs, so it is already the exact one
+    const float inv = rcpFast(ma), fres = (float)res;
+    const float se = fma_(sc * inv, 0.5f, 0.5f) * fres, te = fma_(tc * inv, 0.5f, 0.5f) * fres;
+    const float sf = floorf(se), tf = floorf(te);
+    const float eps = 1e-4f;
+    const bool sure = (se - sf > eps) && (sf + 1.0f - se > eps) && (te - tf > eps) && (tf + 1.0f - te > eps);
+    if (!sure) return exactCubeTexel(d, res);
+    const int i = iclamp((int)sf, 0, res - 1), j = iclamp((int)tf, 0, res - 1);
+    return (face * res + j) * res + i;
 }
 
 struct PixelConsts {   // per-pixel values that do not depend on the light
-    f3 fragPos, baseColor, normal, viewDir, diffuseColor, f0base;
-    float distToCamera, roughness, remappedRoughness, metallic, ambientOcclusion, ambient, fogF;
+    f3 fragPos, normal, viewDir, diffuseOverPi, f0;
+    float NdotV, ggxvTerm, r2, fogAo;
 };
 
-// calculateVirtualPointLighting2 with the constant arguments of the call site (vpl_pbr_gi.fs:195-197)
-SGI_DEV f3 calculateVirtualPointLighting2(const FrameConsts& fc, const PixelConsts& px, f3 specularLightPos, f3 diffuseLightPos, f3 lightColor,
-                                          float lightRadius) {
-    const f3 specularLightDir = specularLightPos - px.fragPos;
-    const f3 diffuseLightDir = diffuseLightPos - px.fragPos;
-    const float adjustedShadowFactor = fsub(1.0f, 0.0f);
-    const float specularAttenuationFactor = vplDiffuseAttenuation(specularLightDir, lightRadius);
-    const float diffuseAttenuationFactor = vplDiffuseAttenuation(diffuseLightDir, lightRadius);
-
-    Dots d = BRDF_DotProducts(px.viewDir, specularLightDir, px.normal);
-    const float NDF = NDF_GGX(d.NdotH, px.remappedRoughness);
-    const float fr = powf(fsub(1.0f, d.LdotH), 5.0f);
-    const f3 Fresnel = fr + px.f0base * fsub(1.0f, fr);
-    const float Visibility = Visibility_G_SmithGGX(d.NdotV, d.NdotL, px.remappedRoughness);
-    const f3 Fr = (fmul(NDF, Visibility) * Fresnel) * d.NdotL;
-
-    d = BRDF_DotProducts(px.viewDir, diffuseLightDir, px.normal);
-    const f3 Fd = (px.diffuseColor * fdiv(1.0f, PI_F)) * d.NdotL;
-
-    const f3 brdfSpecular = specularAttenuationFactor * Fr;
-    const f3 brdfDiffuse = diffuseAttenuationFactor * Fd;
-    const f3 brdf = brdfSpecular + brdfDiffuse;
-    const f3 ambient = ((brdf * px.ambient) * lightColor) * 0.0f;      // ambientIntensity = 0
-    const f3 finalBrightness = brdf * lightColor;
-    const f3 fc3 = mk3(fc.fogColor[0], fc.fogColor[1], fc.fogColor[2]) * 0.0f;   // fogIntensity = 0
-    const f3 fogged = finalBrightness * px.fogF + fc3 * fsub(1.0f, px.fogF);
-    return ambient + adjustedShadowFactor * fogged;
+// radiance tier: ambientOcclusion * calculateVirtualPointLighting2(...) with the constant arguments of the
+// call site (vpl_pbr_gi.fs:195-197: shadowFactor 0, ambientIntensity 0, fogIntensity 0)
+SGI_DEV f3 shadeFast(const PixelConsts& px, f3 specularLightPos, f3 diffuseLightPos, f3 lightColor, float lightRadius, float invRadius) {
+    const f3 Ls = mk3(specularLightPos.x - px.fragPos.x, specularLightPos.y - px.fragPos.y, specularLightPos.z - px.fragPos.z);
+    const f3 Ld = mk3(diffuseLightPos.x - px.fragPos.x, diffuseLightPos.y - px.fragPos.y, diffuseLightPos.z - px.fragPos.z);
+    const float ds2 = dotFast(Ls, Ls), dd2 = dotFast(Ld, Ld);
+    const float is = rsqrtf(ds2), id = rsqrtf(dd2);
+    // vplDiffuseAttenuation for both directions (pbr.glsl:260-267): 1 / (mix(10,1,exp(-3*ratio))*radius + dist^2)
+    const float rs = fminf(ds2 * is * invRadius, 1.0f), rd = fminf(dd2 * id * invRadius, 1.0f);
+    const float es = __expf(-3.0f * rs), ed = __expf(-3.0f * rd);
+    const float attS = rcpFast(fma_(fma_(es, -9.0f, 10.0f), lightRadius, ds2));
+    const float attD = rcpFast(fma_(fma_(ed, -9.0f, 10.0f), lightRadius, dd2));
+    // specular lobe
+    const f3 L = mk3(Ls.x * is, Ls.y * is, Ls.z * is);
+    f3 H = mk3(px.viewDir.x + L.x, px.viewDir.y + L.y, px.viewDir.z + L.z);
+    const float ih = rsqrtf(dotFast(H, H));
+    const float NdotL = satFast(dotFast(px.normal, L));
+    const float NdotH = satFast(dotFast(px.normal, H) * ih);
+    const float LdotH = satFast(dotFast(L, H) * ih);
+    const float f = fma_(fma_(NdotH, px.r2, -NdotH), NdotH, 1.0f);
+    const float ndfDen = fmaxf(PI_F * f * f, PREVENT_DIV_BY_ZERO);
+    const float ggxl = px.NdotV * sqrtFast(fma_(fma_(-px.r2, NdotL, NdotL), NdotL, px.r2));
+    const float visDen = fmaxf(fma_(NdotL, px.ggxvTerm, ggxl), PREVENT_DIV_BY_ZERO);
+    const float ndfVis = (px.r2 * 0.5f) * rcpFast(ndfDen * visDen);
+    const float x1 = 1.0f - LdotH, x2 = x1 * x1, fr = x2 * x2 * x1;
+    const float sw = ndfVis * NdotL * attS, omf = 1.0f - fr;
+    // diffuse lobe
+    const float NdotL2 = satFast(dotFast(px.normal, Ld) * id);
+    const float dw = NdotL2 * attD;
+    f3 brdf;
+    brdf.x = fma_(sw, fma_(px.f0.x, omf, fr), dw * px.diffuseOverPi.x);
+    brdf.y = fma_(sw, fma_(px.f0.y, omf, fr), dw * px.diffuseOverPi.y);
+    brdf.z = fma_(sw, fma_(px.f0.z, omf, fr), dw * px.diffuseOverPi.z);
+    return mk3(brdf.x * lightColor.x * px.fogAo, brdf.y * lightColor.y * px.fogAo, brdf.z * lightColor.z * px.fogAo);
 }
 
 __global__ void __launch_bounds__(kGatherThreadsX * kGatherThreadsY)
@@ -93,7 +122,7 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
              const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
-             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut) {
+             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut) {
     const int x = blockIdx.x * kGatherThreadsX + threadIdx.x;
     const int ly = blockIdx.y * kGatherThreadsY + threadIdx.y;
     if (x >= bd.W || ly >= bd.rows) return;
@@ -102,94 +131,113 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     const int cubeRes = bd.cubeRes;
     const int texelsPerLayer = 6 * cubeRes * cubeRes;
 
+    // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
     const m4 invPV = loadMat(fc.invPV);
     const f3 viewPosition = mk3(fc.viewPos[0], fc.viewPos[1], fc.viewPos[2]);
     const float pcx = fadd((float)x, 0.5f), pcy = fadd((float)y, 0.5f);          // gl_FragCoord.xy
     const float u = fdiv(pcx, (float)bd.W), v = fdiv(pcy, (float)bd.fullH);       // fsTexCoords
-
+    const float depth = __ldg(gDepth + p);
     PixelConsts px;
-    px.fragPos = worldPositionFromDepth(u, v, __ldg(gDepth + p), invPV);
+    px.fragPos = worldPositionFromDepth(u, v, depth, invPV);
     const f3 toView = viewPosition - px.fragPos;
-    px.viewDir = normalize(toView);
-    px.distToCamera = length(toView);
-    const uint32_t alb = __ldg(gAlbedo + p);
-    px.baseColor = mk3(vmax(unorm8(alb & 0xffu), 0.01f), vmax(unorm8((alb >> 8) & 0xffu), 0.01f), vmax(unorm8((alb >> 16) & 0xffu), 0.01f));
+    const float distToCamera = length(toView);
     px.normal = decodeNormal(__ldg(gNormal + p));
+    guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
+    const uint32_t alb = __ldg(gAlbedo + p);
+    const f3 baseColor = mk3(vmax(unorm8(alb & 0xffu), 0.01f), vmax(unorm8((alb >> 8) & 0xffu), 0.01f), vmax(unorm8((alb >> 16) & 0xffu), 0.01f));
     const uint32_t rma = __ldg(gRma + p);
-    px.roughness = vmax(0.5f, unorm8(rma & 0xffu));
-    px.metallic = unorm8((rma >> 8) & 0xffu);
-    px.ambientOcclusion = vclamp(h2f(__ldg(ssao + p)), 0.35f, 1.0f);
-    px.ambient = unorm8((rma >> 16) & 0xffu);
-    const f3 baseReflectivity = mk3(unorm8((uint32_t)__ldg(gRefl + p) & 0xffu));
-    const float roughnessWeight = fsub(1.0f, px.roughness);
+    const float roughness = vmax(0.5f, unorm8(rma & 0xffu));
+    const float roughnessWeight = fsub(1.0f, roughness);
+    const float distRatioToCamera = vmin(fsub(1.0f, fdiv(distToCamera, 1000.0f)), 1.0f);
+    const int maxSamplesPerPixel = (int)mix(2.0f, 10.0f, roughnessWeight);
+    const int sampleCount = max(1, (int)fmul((float)maxSamplesPerPixel, distRatioToCamera));
+    const bool shadowsOn = distToCamera < 500.0f;
 
-    // BRDF_Base (pbr2.glsl:146-168): light-independent, hoisted out of the sample loop
+    // ---- per-pixel set-up: radiance tier (BRDF_Base pbr2.glsl:146-168 and everything light-independent) ----
     {
-        float rr = px.roughness;
-        if (fc.usePerceptualRoughness) rr = fmul(rr, rr);
-        px.remappedRoughness = vmax(vmax(0.0f, fc.minRoughness), rr);
-        const f3 diffuseDivisor = px.baseColor;
-        const f3 specularMultiplier = 1.0f / (px.baseColor + PREVENT_DIV_BY_ZERO);
-        f3 diffuseColor = fsub(1.0f, px.metallic) * px.baseColor;
-        px.diffuseColor = diffuseColor / (diffuseDivisor + PREVENT_DIV_BY_ZERO);
-        f3 f0 = ((0.16f * baseReflectivity) * baseReflectivity) * fsub(1.0f, px.metallic) + px.baseColor * px.metallic;
-        px.f0base = f0 * specularMultiplier;
-        px.fogF = expf(fmul(-fc.fogDensity, px.distToCamera));
+        const float metallic = unorm8((rma >> 8) & 0xffu);
+        const float ambientOcclusion = vclamp(h2f(__ldg(ssao + p)), 0.35f, 1.0f);
+        const float refl = unorm8((uint32_t)__ldg(gRefl + p) & 0xffu);
+        float rr = roughness;
+        if (fc.usePerceptualRoughness) rr = rr * rr;
+        rr = fmaxf(fmaxf(0.0f, fc.minRoughness), rr);
+        px.r2 = rr * rr;
+        const float iv = rsqrtf(dotFast(toView, toView));
+        px.viewDir = mk3(toView.x * iv, toView.y * iv, toView.z * iv);
+        px.NdotV = satFast(dotFast(px.normal, px.viewDir));
+        px.ggxvTerm = sqrtFast(fma_(fma_(-px.r2, px.NdotV, px.NdotV), px.NdotV, px.r2));
+        const float om = 1.0f - metallic, f0s = 0.16f * refl * refl * om;
+        const f3 inv = mk3(rcpFast(baseColor.x + PREVENT_DIV_BY_ZERO), rcpFast(baseColor.y + PREVENT_DIV_BY_ZERO), rcpFast(baseColor.z + PREVENT_DIV_BY_ZERO));
+        // diffuseColor / (diffuseDivisor + eps) / PI   and   f0 * specularMultiplier
+        px.diffuseOverPi = mk3(om * baseColor.x * inv.x * (1.0f / PI_F), om * baseColor.y * inv.y * (1.0f / PI_F), om * baseColor.z * inv.z * (1.0f / PI_F));
+        px.f0 = mk3(fma_(baseColor.x, metallic, f0s) * inv.x, fma_(baseColor.y, metallic, f0s) * inv.y, fma_(baseColor.z, metallic, f0s) * inv.z);
+        px.fogAo = __expf(-fc.fogDensity * distToCamera) * ambientOcclusion;
     }
 
     f3 vplColor = mk3(0.0f);
     float seedZ = fc.time;
     float validSamples = 0.0f;
-    const float distRatioToCamera = vmin(fsub(1.0f, fdiv(px.distToCamera, 1000.0f)), 1.0f);
-    const int maxSamplesPerPixel = (int)mix(2.0f, 10.0f, roughnessWeight);
-    const int sampleCount = max(1, (int)fmul((float)maxSamplesPerPixel, distRatioToCamera));
     const int V = __ldg(numVisible);
-    const int maxRandomIndex = V - 1;
+    const float maxRandomIndexF = (float)(V - 1);
     const float minGi = fc.minGiOcclusionFactor;
 
     // V <= 0: undefined in the reference (stale lights); defined here as "no light"
     for (int i = 0, resamples = 0; V > 0 && i < sampleCount; ++i) {
         const float rnd = random3(pcx, pcy, seedZ);
         seedZ = fadd(seedZ, 10000.0f);
-        const int lightIndex = (int)fmul((float)maxRandomIndex, rnd);
+        const int lightIndex = (int)fmul(maxRandomIndexF, rnd);
         const float4* L = reinterpret_cast<const float4*>(lightData + lightIndex);
         const float4 lp = __ldg(L);
         const float4 rfi = __ldg(L + 3);                    // radius, farPlane, intensity, pad
         const f3 lightPosition = mk3(lp.x, lp.y, lp.z);
-        const f3 lightMinusFrag = lightPosition - px.fragPos;
+        const f3 lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
         const float lightRadius = rfi.x;
-        const float distance = length(lightMinusFrag);
+        const float d2 = dotFast(lightMinusFrag, lightMinusFrag);
         if (resamples < 5) {
-            const float sideCheck = dot(px.normal, normalize(lightMinusFrag));
-            if (sideCheck < 0.0f || distance > lightRadius) { ++resamples; --i; continue; }
+            // if (dot(normal, normalize(l)) < 0 || length(l) > radius) re-draw      (vpl_pbr_gi.fs:164-171)
+            const float s = dotFast(px.normal, lightMinusFrag);      // same sign as the normalised dot product
+            const float r2 = lightRadius * lightRadius;
+            const bool sideSure = s * s > (kMargin * kMargin) * d2;
+            const bool farSure = d2 > r2 * (1.0f + 4.0f * kMargin), nearSure = d2 < r2 * (1.0f - 4.0f * kMargin);
+            bool redraw;
+            if (sideSure && (farSure || nearSure)) redraw = (s < 0.0f) || farSure;
+            else redraw = exactRedraw(px.normal, lightMinusFrag, lightRadius);
+            if (redraw) { ++resamples; --i; continue; }
         }
         const float4 lc = __ldg(L + 1);
         const float4 sp = __ldg(L + 2);
-        const float distanceRatio = vclamp(fdiv(fmul(2.0f, distance), lightRadius), 0.0f, 1.0f);
+        const float invRadius = rcpFast(lightRadius);
+        const float distance = d2 * rsqrtf(d2);
+        const float distanceRatio = satFast(2.0f * distance * invRadius);
         float shadowFactor = 0.0f;
-        if (px.distToCamera < 500.0f) {
-            // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1
+        if (shadowsOn) {
+            // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1: texel choice and the lit/shadowed verdict are decisions
             const SgiAtlasEntry entry = shadowIndices[lightIndex];
             const f3 fragDir = px.fragPos - lightPosition;
-            const float currentDepth = length(fragDir);
-            const float lightNormalDot = dot(lightPosition - px.fragPos, px.normal);
-            const float bias = fmul(currentDepth, vmax(0.1f, fmul(saturate(lightNormalDot), 0.03f)));
-            const unsigned short texel = __ldg(atlases.shadow[entry.index] + (size_t)entry.layer * texelsPerLayer + cubeTexel(fragDir, cubeRes));
-            const float depth = fmul(fdiv((float)texel, 65535.0f), rfi.y);
-            if (fsub(currentDepth, bias) > depth) shadowFactor = 1.0f;
+            const unsigned short texel = __ldg(atlases.shadow[entry.index] + (size_t)entry.layer * texelsPerLayer + cubeTexelDecided(fragDir, cubeRes));
+            const float texelDepth = unorm16(texel);
+            const float lightNormalDot = dotFast(lightMinusFrag, px.normal);
+            const float biasFactor = fmaxf(0.1f, satFast(lightNormalDot) * 0.03f);
+            const float lhs = distance * (1.0f - biasFactor), rhs = texelDepth * rfi.y;
+            const float gap = lhs - rhs;
+            // lightNormalDot only matters through saturate(.)*0.03 vs 0.1, i.e. when it exceeds 3.33: never borderline for the verdict's margin
+            bool shadowed;
+            if (fabsf(gap) > 8.0f * kMargin * fmaxf(lhs, rhs)) shadowed = gap > 0.0f;
+            else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), texelDepth, rfi.y);
+            shadowFactor = shadowed ? 1.0f : 0.0f;
         }
-        shadowFactor = vmin(shadowFactor, mix(minGi, 1.0f, distanceRatio));
+        shadowFactor = fminf(shadowFactor, fma_(distanceRatio, 1.0f - minGi, minGi));
         float reweightingFactor = 1.0f;
-        if (shadowFactor > 0.0f) reweightingFactor = fadd(fmul(fsub(1.0f, distanceRatio), minGi), distanceRatio);
-        validSamples = fadd(validSamples, reweightingFactor);
-        const f3 tmpColor = px.ambientOcclusion * calculateVirtualPointLighting2(fc, px, mk3(sp.x, sp.y, sp.z), lightPosition, mk3(lc.x, lc.y, lc.z), lightRadius);
-        vplColor = vplColor + fsub(1.0f, shadowFactor) * tmpColor;
+        if (shadowFactor > 0.0f) reweightingFactor = fma_(1.0f - distanceRatio, minGi, distanceRatio);
+        validSamples += reweightingFactor;
+        const f3 tmpColor = shadeFast(px, mk3(sp.x, sp.y, sp.z), lightPosition, mk3(lc.x, lc.y, lc.z), lightRadius, invRadius);
+        const float lit = 1.0f - shadowFactor;
+        vplColor = mk3(fma_(lit, tmpColor.x, vplColor.x), fma_(lit, tmpColor.y, vplColor.y), fma_(lit, tmpColor.z, vplColor.z));
     }
-    validSamples = vmax(validSamples, 1.0f);
-    const f3 color = px.baseColor + PREVENT_DIV_BY_ZERO;
-    const f3 bounded = vmin(vplColor, HALF_FLOAT_MAX);
+    validSamples = fmaxf(validSamples, 1.0f);
+    const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
     storeHalf4(colorOut, p, color.x, color.y, color.z, 1.0f);
-    storeHalf4(reservoirOut, p, bounded.x, bounded.y, bounded.z, validSamples);
+    storeHalf4(reservoirOut, p, fminf(vplColor.x, HALF_FLOAT_MAX), fminf(vplColor.y, HALF_FLOAT_MAX), fminf(vplColor.z, HALF_FLOAT_MAX), validSamples);
 }
 
 }  // namespace
@@ -197,10 +245,10 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut) {
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut) {
     dim3 block(kGatherThreadsX, kGatherThreadsY);
     dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
-    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut);
+    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut);
     return 1;
 }
 

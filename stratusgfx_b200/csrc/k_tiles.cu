@@ -88,6 +88,17 @@ stage2Kernel(int numTiles, const SgiVplStage1PerTileOutputs* __restrict__ stage1
         for (int j = 0; j < n; ++j) {
             const StagedVpl L = sVpl[j];
             const f3 lightMinusFrag = mk3(L.x, L.y, L.z) - fragPos;
+            {
+                // Cheap conservative pre-test (FMA estimates, 4e-5 relative margin = >100x the rounding error of
+                // either evaluation): a light that is surely farther than min(1, current 12th-best ratio) or surely
+                // behind the tile cannot change the list, so the exact chain below is skipped for it.
+                const float d2e = __fmaf_rn(lightMinusFrag.z, lightMinusFrag.z, __fmaf_rn(lightMinusFrag.y, lightMinusFrag.y, lightMinusFrag.x * lightMinusFrag.x));
+                const float w = fminf(dist[SGI_MAX_VPLS_PER_TILE - 1], 1.0f);
+                const float t = L.radius * w;
+                if (d2e > t * t * (1.0f + 4e-5f)) continue;
+                const float se = __fmaf_rn(normal.z, lightMinusFrag.z, __fmaf_rn(normal.y, lightMinusFrag.y, normal.x * lightMinusFrag.x));
+                if (se < 0.0f && se * se > 1e-10f * d2e) continue;
+            }
             const float sideCheck = dot(normal, lightMinusFrag);
             if (sideCheck < 0.0f) continue;
             const float ratio = fdiv(length(lightMinusFrag), L.radius);

@@ -31,7 +31,7 @@ static int fail(SgiHandle h, int code, const char* msg) { h->lastError = msg; re
 static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h->cp.rows; }
 
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1], &h->history[0], &h->history[1]};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1], &h->history[0], &h->history[1], &h->guide};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
 }
 
@@ -40,6 +40,8 @@ static int allocPlanes(SgiHandle h) {
     void** half4s[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1]};
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
     for (int i = 0; i < 2; ++i) SGI_CUDA(h, cudaMalloc(&h->history[i], n * 2));
+    SGI_CUDA(h, cudaMalloc(&h->guide, n * 16));
+    h->guideValid = false;
     // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the
     // previous-frame FBO is never cleared and starts at zero
     for (int i = 0; i < 2; ++i) {
@@ -133,6 +135,7 @@ int sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers) {
     if (!h || !buffers) return SGI_ERR_INVALID_ARG;
     h->buf = *buffers;
     h->bound = true;
+    h->guideValid = false;
     return SGI_OK;
 }
 
@@ -194,7 +197,8 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     const int n = launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
-                               atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir);
+                               atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide);
+    h->guideValid = true;
     return postLaunch(h, n);
 }
 
@@ -224,8 +228,14 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
     io.giOut = (uint2*)h->giIllum[h->cur];
     io.historyOut = (unsigned short*)h->history[h->cur];
     io.multiplier = (1 << pass) - 1;             // std::pow(2, i) - 1 (BE:1920)
-    const int n = launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
-    if (final_) h->cur ^= 1;                     // swap with the previous-frame FBO (BE:1949-1951)
+    io.guide = (const float4*)h->guide;
+    int n = 0;
+    if (!h->guideValid) {                        // denoise called without this library's gather in the same frame
+        n += launchPrepareGuide(h->stream, bandDims(h), (const uint32_t*)h->buf.normal, (const float*)h->buf.depth, (float4*)h->guide);
+        h->guideValid = true;
+    }
+    n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
+    if (final_) { h->cur ^= 1; h->guideValid = false; }   // swap with the previous-frame FBO (BE:1949-1951)
     return postLaunch(h, n);
 }
 

@@ -49,6 +49,7 @@ struct DenoiseIO {
     const uint32_t* prevNormal;
     const float* prevIds;
     const float* prevDepth;
+    const float4* guide;          // library-owned: (decoded normal, depth) of every pixel of this frame
     const uint2* illum;           // half4: the demodulation plane (vplGIFbo attachment 0)
     const uint2* shadowsIn;       // half4: reservoir input of this pass
     const uint2* prevGi;          // half4
@@ -80,6 +81,8 @@ struct SgiHandle_ {
     void* giIllum[2] = {nullptr, nullptr};    // half4, [cur] / [cur^1] = previous frame
     void* history[2] = {nullptr, nullptr};    // half
     int cur = 0;
+    void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
+    bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
     // scratch for the cull
     uint32_t* cullBallots = nullptr;
     unsigned int* cullTicket = nullptr;
@@ -102,7 +105,8 @@ int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerT
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut);
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut);
+int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
 
 }  // namespace sgi

@@ -99,7 +99,19 @@ SGI_DEV f3 worldPositionFromDepth(float u, float v, float depth, const m4& invPr
     return mk3(fdiv(wp.x, wp.w), fdiv(wp.y, wp.w), fdiv(wp.z, wp.w));
 }
 
-SGI_DEV float unorm8(uint32_t b) { return fdiv((float)b, 255.0f); }
+// b / 255.0f and u / 65535.0f, bit-identical to the IEEE division for every 8-/16-bit input, in three
+// instructions: q = x*r, one FMA residual, one FMA correction (r = fl(1/D)).  Verified exhaustively with
+// exact rational arithmetic in tests/test_device_math_identities.py.
+SGI_DEV float unorm8(uint32_t b) {
+    const float x = (float)b, r = 1.0f / 255.0f;
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, x), r, q);
+}
+SGI_DEV float unorm16(uint32_t u) {
+    const float x = (float)u, r = 1.0f / 65535.0f;
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-q, 65535.0f, x), r, q);
+}
 
 // normalize(texel.rgb * 2.0 - vec3(1.0)) from a packed rgba8 texel (common.glsl:216-220)
 SGI_DEV f3 decodeNormal(uint32_t rgba) {
