@@ -135,15 +135,25 @@ denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_
         Bilin k = bilinSetup(pu, pv, W, bd.fullH);
         k.j0 = iclamp(k.j0 - bd.yOffset, 0, rows - 1); k.j1 = iclamp(k.j1 - bd.yOffset, 0, rows - 1);
         const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
-        const float prevCenterDepth = bilinMix(k, __ldg(io.prevDepth + q00), __ldg(io.prevDepth + q10), __ldg(io.prevDepth + q01), __ldg(io.prevDepth + q11));
-        const uint32_t n00 = __ldg(io.prevNormal + q00), n10 = __ldg(io.prevNormal + q10), n01 = __ldg(io.prevNormal + q01), n11 = __ldg(io.prevNormal + q11);
-        f3 pn;
-        pn.x = bilinMix(k, unorm8(n00 & 0xffu), unorm8(n10 & 0xffu), unorm8(n01 & 0xffu), unorm8(n11 & 0xffu));
-        pn.y = bilinMix(k, unorm8((n00 >> 8) & 0xffu), unorm8((n10 >> 8) & 0xffu), unorm8((n01 >> 8) & 0xffu), unorm8((n11 >> 8) & 0xffu));
-        pn.z = bilinMix(k, unorm8((n00 >> 16) & 0xffu), unorm8((n10 >> 16) & 0xffu), unorm8((n01 >> 16) & 0xffu), unorm8((n11 >> 16) & 0xffu));
+        float prevCenterDepth; f3 pn, prevGi;
+        if (k.a == 0.0f && k.b == 0.0f) {
+            // the reprojected tap sits on a texel centre (always, on a static camera): the bilinear blend
+            // (1*1)*t00 + 0*t10 + 0*t01 + 0*t11 is t00 exactly, so three of the four fetches are skipped
+            prevCenterDepth = __ldg(io.prevDepth + q00);
+            const uint32_t n00 = __ldg(io.prevNormal + q00);
+            pn = mk3(unorm8(n00 & 0xffu), unorm8((n00 >> 8) & 0xffu), unorm8((n00 >> 16) & 0xffu));
+            const f4 g00 = loadHalf4(io.prevGi, q00);
+            prevGi = mk3(g00.x, g00.y, g00.z);
+        } else {
+            prevCenterDepth = bilinMix(k, __ldg(io.prevDepth + q00), __ldg(io.prevDepth + q10), __ldg(io.prevDepth + q01), __ldg(io.prevDepth + q11));
+            const uint32_t n00 = __ldg(io.prevNormal + q00), n10 = __ldg(io.prevNormal + q10), n01 = __ldg(io.prevNormal + q01), n11 = __ldg(io.prevNormal + q11);
+            pn.x = bilinMix(k, unorm8(n00 & 0xffu), unorm8(n10 & 0xffu), unorm8(n01 & 0xffu), unorm8(n11 & 0xffu));
+            pn.y = bilinMix(k, unorm8((n00 >> 8) & 0xffu), unorm8((n10 >> 8) & 0xffu), unorm8((n01 >> 8) & 0xffu), unorm8((n11 >> 8) & 0xffu));
+            pn.z = bilinMix(k, unorm8((n00 >> 16) & 0xffu), unorm8((n10 >> 16) & 0xffu), unorm8((n01 >> 16) & 0xffu), unorm8((n11 >> 16) & 0xffu));
+            const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
+            prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
+        }
         const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
-        const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
-        const f3 prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
         const float currId = __ldg(io.ids + p);
         const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
         const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);

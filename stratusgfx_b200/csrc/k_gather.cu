@@ -117,7 +117,7 @@ SGI_DEV f3 shadeFast(const PixelConsts& px, f3 specularLightPos, f3 diffuseLight
     return mk3(brdf.x * lightColor.x * px.fogAo, brdf.y * lightColor.y * px.fogAo, brdf.z * lightColor.z * px.fogAo);
 }
 
-__global__ void __launch_bounds__(kGatherThreadsX * kGatherThreadsY)
+__global__ void __launch_bounds__(kGatherThreadsX * kGatherThreadsY, 4)
 gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,

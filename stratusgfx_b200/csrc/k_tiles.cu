@@ -50,12 +50,13 @@ stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     o[1] = make_float4(sumN.x, sumN.y, sumN.z, 1.0f);
 }
 
-struct StagedVpl { float x, y, z, radius; };
+struct StagedVpl { float x, y, z, r2m; };   // position and radius^2 * (1 + margin), the pre-test threshold at ratio 1
 
 __global__ void __launch_bounds__(kTileThreads)
 stage2Kernel(int numTiles, const SgiVplStage1PerTileOutputs* __restrict__ stage1, const SgiVplData* __restrict__ lightData,
              const int32_t* __restrict__ visible, SgiVplStage2PerTileOutputs* __restrict__ out) {
     __shared__ StagedVpl sVpl[kStage2Chunk];
+    __shared__ float sRadius[kStage2Chunk];
     __shared__ int sIdx[kStage2Chunk];
     const int tile = blockIdx.x * kTileThreads + threadIdx.x;
     const bool active = tile < numTiles;
@@ -72,6 +73,7 @@ stage2Kernel(int numTiles, const SgiVplStage1PerTileOutputs* __restrict__ stage1
     #pragma unroll
     for (int i = 0; i < SGI_MAX_VPLS_PER_TILE; ++i) { dist[i] = FLOAT_MAX_; idx[i] = i; }
     int count = 0;
+    float w2 = 1.0f;          // min(1, current 12th-best ratio)^2: only lights with ratio below it can change the list
 
     for (int base = 0; base < numVisible; base += kStage2Chunk) {
         const int n = min(kStage2Chunk, numVisible - base);
@@ -80,28 +82,27 @@ stage2Kernel(int numTiles, const SgiVplStage1PerTileOutputs* __restrict__ stage1
             const int lightIndex = __ldg(visible + 1 + base + j);
             const float4 p = __ldg(reinterpret_cast<const float4*>(lightData + lightIndex));
             const float r = __ldg(&lightData[lightIndex].radius);
-            sVpl[j].x = p.x; sVpl[j].y = p.y; sVpl[j].z = p.z; sVpl[j].radius = r;
+            sVpl[j].x = p.x; sVpl[j].y = p.y; sVpl[j].z = p.z; sVpl[j].r2m = r * r * (1.0f + 4e-5f);
+            sRadius[j] = r;
             sIdx[j] = lightIndex;
         }
         __syncthreads();
         if (!active) continue;
+        #pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const StagedVpl L = sVpl[j];
             const f3 lightMinusFrag = mk3(L.x, L.y, L.z) - fragPos;
-            {
-                // Cheap conservative pre-test (FMA estimates, 4e-5 relative margin = >100x the rounding error of
-                // either evaluation): a light that is surely farther than min(1, current 12th-best ratio) or surely
-                // behind the tile cannot change the list, so the exact chain below is skipped for it.
-                const float d2e = __fmaf_rn(lightMinusFrag.z, lightMinusFrag.z, __fmaf_rn(lightMinusFrag.y, lightMinusFrag.y, lightMinusFrag.x * lightMinusFrag.x));
-                const float w = fminf(dist[SGI_MAX_VPLS_PER_TILE - 1], 1.0f);
-                const float t = L.radius * w;
-                if (d2e > t * t * (1.0f + 4e-5f)) continue;
-                const float se = __fmaf_rn(normal.z, lightMinusFrag.z, __fmaf_rn(normal.y, lightMinusFrag.y, normal.x * lightMinusFrag.x));
-                if (se < 0.0f && se * se > 1e-10f * d2e) continue;
-            }
+            // Cheap conservative pre-test (FMA estimate, 4e-5 relative margin = >100x the rounding error of either
+            // evaluation): a light that is surely farther than min(1, current 12th-best ratio) cannot change the list.
+            const float d2e = __fmaf_rn(lightMinusFrag.z, lightMinusFrag.z, __fmaf_rn(lightMinusFrag.y, lightMinusFrag.y, lightMinusFrag.x * lightMinusFrag.x));
+            if (d2e > L.r2m * w2) continue;
+            // ... nor can one that is surely behind the tile
+            const float se = __fmaf_rn(normal.z, lightMinusFrag.z, __fmaf_rn(normal.y, lightMinusFrag.y, normal.x * lightMinusFrag.x));
+            if (se < 0.0f && se * se > 1e-10f * d2e) continue;
+            // exact evaluation in the shader's operation order (stage2.cs:86-94)
             const float sideCheck = dot(normal, lightMinusFrag);
             if (sideCheck < 0.0f) continue;
-            const float ratio = fdiv(length(lightMinusFrag), L.radius);
+            const float ratio = fdiv(length(lightMinusFrag), sRadius[j]);
             if (ratio > 1.0f) continue;
             if (!(ratio < dist[SGI_MAX_VPLS_PER_TILE - 1])) continue;   // sorted list: no slot can take it
             // insert before the first strictly larger entry, shifting the rest down (stage2.cs:100-122)
@@ -115,6 +116,8 @@ stage2Kernel(int numTiles, const SgiVplStage1PerTileOutputs* __restrict__ stage1
                 inserted = take;
             }
             if (count < SGI_MAX_VPLS_PER_TILE) ++count;
+            const float w = fminf(dist[SGI_MAX_VPLS_PER_TILE - 1], 1.0f);
+            w2 = w * w;
         }
     }
     if (!active) return;
