@@ -29,7 +29,6 @@ import numpy as np
 
 METRIC = "vpl_gi_denoise_throughput"
 UNIT = "Gpixel*VPL/s"
-APRON = 30            # >= 4+8+16 rows of à-trous reach (28), rounded to the 5-pixel tile grid
 CPU_SAMPLE_ROWS = 270  # bounded CPU sample: one 1/8-frame band of a 4K frame
 
 
@@ -149,6 +148,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    from stratusgfx_b200.bands import APRON, broadcast_frame_inputs, gather_bands, plan_bands
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
 
@@ -158,12 +158,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     scene = Scene(args.workload)
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
-    if H % (5 * world):
-        raise SystemExit(f"height {H} does not split into {world} bands of whole 5-pixel tiles")
-    band = H // world
-    b0, b1 = rank * band, (rank + 1) * band
-    y0, y1 = (max(0, b0 - APRON), min(H, b1 + APRON)) if world > 1 else (0, H)
-    rows = y1 - y0
+    bands = plan_bands(H, world)
+    me = bands[rank]
+    band, y0, rows = me.b1 - me.b0, me.y0, me.rows
 
     fp = scene.frame_params(0)
     gb, pgb = scene.gbuffer(0, y0, rows), scene.gbuffer(-1, y0, rows)
@@ -188,19 +185,16 @@ def run_ours(args, rank, world, local_rank):
         sa = gp.t["shadowAtlas"].view(-1, 6, scene.cube_res, scene.cube_res)
         maps_buf = torch.stack([sa[s] for s in refreshed]).contiguous()
         full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
-        gather_list = [full_out[r * band:(r + 1) * band] for r in range(world)] if rank == 0 else None
 
     def step(i):
         fp.time = 1000.0 + 16.0 * i
         if world > 1:
-            dist.broadcast(gp.t["vplData"], 0)
-            dist.broadcast(gp.t["atlasEntryByVpl"], 0)
-            dist.broadcast(maps_buf, 0)
+            broadcast_frame_inputs(dist, [gp.t["vplData"], gp.t["atlasEntryByVpl"], maps_buf])
             for j, s in enumerate(refreshed):
                 sa[s].copy_(maps_buf[j])
         gp.frame(fp)
         if world > 1:
-            dist.gather(gp.t["lightingOut"][b0 - y0:b1 - y0], gather_list, dst=0)
+            gather_bands(dist, gp.t["lightingOut"][me.owned], full_out, bands, rank)
 
     def fence():
         if world > 1:

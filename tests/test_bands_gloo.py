@@ -1,0 +1,78 @@
+"""The N>1 host path on CPU: world_size-2 gloo processes run the row-band plan of stratusgfx_b200/bands.py
+(broadcast of the per-frame VPL tables, per-band processing with an apron, gather of the lit bands).
+The per-band processor here is the CPU oracle in band mode — the GPU box runs the same plumbing with
+the CUDA pass and NCCL (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from stratusgfx_b200.bands import APRON, plan_bands
+
+
+def test_band_plan_covers_the_frame_on_the_tile_grid():
+    for H, world in ((2160, 1), (2160, 2), (2160, 4), (2160, 8), (4320, 8), (1080, 8), (360, 2)):
+        bands = plan_bands(H, world)
+        assert [b.b0 for b in bands] == [r * H // world for r in range(world)]
+        assert bands[-1].b1 == H and bands[0].y0 == 0 and bands[-1].y1 == H
+        for b in bands:
+            assert b.b0 % 5 == 0 and b.b1 % 5 == 0 and b.y0 % 5 == 0 and b.rows % 5 == 0
+            assert b.y0 <= b.b0 < b.b1 <= b.y1
+            if world > 1:
+                assert b.b0 - b.y0 in (0, APRON) and b.y1 - b.b1 in (0, APRON)
+            assert b.owned == slice(b.b0 - b.y0, b.b1 - b.y0)
+    with pytest.raises(ValueError):
+        plan_bands(1080, 16)        # 67.5 rows per band
+    assert APRON >= 4 + 8 + 16      # reach of the three à-trous passes (BE:1920: multiplier 1, 3, 7 -> 2*(m+1))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, workload, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "4"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle_py import OracleFrame
+    from stratusgfx_b200.bands import broadcast_frame_inputs, gather_bands
+    from stratusgfx_b200.scene import Scene
+    scene = Scene(workload)
+    W, H = scene.width, scene.height
+    bands = plan_bands(H, world)
+    me = bands[rank]
+    fp = scene.frame_params(0)
+    gb, pgb = scene.gbuffer(0, me.y0, me.rows), scene.gbuffer(-1, me.y0, me.rows)
+    sh, df = scene.cubemaps()
+    csm = scene.csm(0)
+    # only rank 0 "knows" this frame's VPL tables; the others receive them
+    vd, at = scene.vpls()
+    t_vd, t_at = torch.from_numpy(vd.copy()), torch.from_numpy(at.copy())
+    if rank != 0:
+        t_vd.zero_(); t_at.zero_()
+    broadcast_frame_inputs(dist, [t_vd, t_at])
+    assert np.array_equal(t_vd.numpy(), vd) and np.array_equal(t_at.numpy(), at)
+    o = OracleFrame(W, me.rows, scene.cube_res, scene.csm_res, scene.denoise_iters, y_offset=me.y0, full_height=H)
+    o.frame(fp, gb, pgb, t_vd.numpy(), t_at.numpy(), csm, sh, df)
+    band_out = torch.from_numpy(np.ascontiguousarray(o.combined[me.owned]))
+    full = torch.zeros((H, W, 4), dtype=torch.float16) if rank == 0 else None
+    gather_bands(dist, band_out, full, bands, rank)
+    if rank == 0:
+        np.save(out_path, full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_bands_reproduce_the_whole_frame(built, tmp_path):
+    import torch.multiprocessing as mp
+    from tests.parity_util import SceneData, run_oracle
+    workload = "c1"
+    out_path = str(tmp_path / "assembled.npy")
+    mp.spawn(_worker, args=(2, _free_port(), workload, out_path), nprocs=2, join=True)
+    assembled = np.load(out_path)
+    whole = run_oracle(SceneData(workload), keep_passes=False)[0]["combined"]
+    # apron rows make every owned row see exactly the taps it would see in the whole frame
+    assert np.array_equal(assembled.view(np.uint16), whole.view(np.uint16))
