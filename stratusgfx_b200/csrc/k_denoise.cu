@@ -17,10 +17,19 @@
 //
 // Arithmetic tiers.  The reference evaluates the 25 tap weights through the texture units, a
 // normalize, pow(x,128) and exp per tap; here the decoded normal and the depth of every pixel are
-// stored once per frame in a float4 "guide" plane (bit-identical to normalize(rgb*2-1)), x^128 is
-// seven squarings, exp is ex2.approx, and the weighted sum uses FMA.  That is radiance arithmetic
-// (tolerance 1e-3 relative / 60 dB PSNR); the one decision in this shader — the history reset
-// `similarity < 0.99` — stays in exact IEEE arithmetic in glm order.
+// stored once per frame in a float4 "guide" plane (bit-identical to normalize(rgb*2-1)) and a weight
+// is  ex2(128*lg2(max(0,n.n')) - |z-z'|*log2(e))  with FMA and the MUFU approximations.  That is
+// radiance arithmetic (tolerance 1e-3 relative / 60 dB PSNR); the one decision in this shader — the
+// history reset `similarity < 0.99` — stays in exact IEEE arithmetic in glm order.
+//
+// Work mapping of the à-trous passes.  With tap spacing s, pixel (x,y) only ever reads rows
+// y + dy*s.  A thread therefore owns kLat outputs on ONE lattice column: rows (g*kLat + k)*s + r,
+// k = 0..kLat-1.  Those outputs share tap rows (output k, tap dy <-> lattice row k+dy), so the thread
+// loads (kLat+4)*5 taps for kLat*25 weights: 2.5x fewer L1 requests and half->float conversions than
+// one-pixel-per-thread, which is what bounds this stencil on a B200 (L1/tex + issue, not HBM).  Lanes
+// of a warp are consecutive in x, so every request is fully coalesced.  Each output accumulates its
+// taps in the same order (dy ascending, dx ascending) wherever it sits in a band, so a row band with an
+// apron reproduces the whole-frame bytes.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -58,120 +67,168 @@ prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* _
     guide[p] = make_float4(nn.x, nn.y, nn.z, __ldg(depth + p));
 }
 
-template <bool MERGE, bool FINAL>
-__global__ void __launch_bounds__(kDnX * kDnY)
-denoiseKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
-    const int x = blockIdx.x * kDnX + threadIdx.x;
-    const int ly = blockIdx.y * kDnY + threadIdx.y;
-    if (x >= bd.W || ly >= bd.rows) return;
+// ---- final-pass epilogue: temporal accumulation + re-modulation (vpl_pbr_gi_denoise.fs:337-434) ------------
+SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 centerNormal, f3 shadowFactor) {
     const int W = bd.W, rows = bd.rows;
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * W + x;
+    const float centerDepth = __ldg(io.depth + p);
+    const float u = fdiv(fadd((float)x, 0.5f), (float)W), v = fdiv(fadd((float)y, 0.5f), (float)bd.fullH);
+    const f4 screenColor = loadHalf4(io.screen, p);
+    const f4 gi4 = loadHalf4(io.illum, p);
+    const f3 gi = mk3(gi4.x, gi4.y, gi4.z);
+    const uint32_t vel = __ldg(io.velocity + p);
+    const float pu = fsub(u, h2f((unsigned short)(vel & 0xffffu))), pv = fsub(v, h2f((unsigned short)(vel >> 16)));
+    float historyAccum = h2f(__ldg(io.historyIn + p));
+    float accumMultiplier = 1.0f;
+    const f3 currGi = shadowFactor;
 
+    // reprojected reads; rows are band-local (previous-frame planes hold the same rows)
+    Bilin k = bilinSetup(pu, pv, W, bd.fullH);
+    k.j0 = iclamp(k.j0 - bd.yOffset, 0, rows - 1); k.j1 = iclamp(k.j1 - bd.yOffset, 0, rows - 1);
+    const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
+    float prevCenterDepth; f3 pn, prevGi;
+    if (k.a == 0.0f && k.b == 0.0f) {
+        // the reprojected tap sits on a texel centre (always, on a static camera): the bilinear blend
+        // (1*1)*t00 + 0*t10 + 0*t01 + 0*t11 is t00 exactly, so three of the four fetches are skipped
+        prevCenterDepth = __ldg(io.prevDepth + q00);
+        const uint32_t n00 = __ldg(io.prevNormal + q00);
+        pn = mk3(unorm8(n00 & 0xffu), unorm8((n00 >> 8) & 0xffu), unorm8((n00 >> 16) & 0xffu));
+        const f4 g00 = loadHalf4(io.prevGi, q00);
+        prevGi = mk3(g00.x, g00.y, g00.z);
+    } else {
+        prevCenterDepth = bilinMix(k, __ldg(io.prevDepth + q00), __ldg(io.prevDepth + q10), __ldg(io.prevDepth + q01), __ldg(io.prevDepth + q11));
+        const uint32_t n00 = __ldg(io.prevNormal + q00), n10 = __ldg(io.prevNormal + q10), n01 = __ldg(io.prevNormal + q01), n11 = __ldg(io.prevNormal + q11);
+        pn.x = bilinMix(k, unorm8(n00 & 0xffu), unorm8(n10 & 0xffu), unorm8(n01 & 0xffu), unorm8(n11 & 0xffu));
+        pn.y = bilinMix(k, unorm8((n00 >> 8) & 0xffu), unorm8((n10 >> 8) & 0xffu), unorm8((n01 >> 8) & 0xffu), unorm8((n11 >> 8) & 0xffu));
+        pn.z = bilinMix(k, unorm8((n00 >> 16) & 0xffu), unorm8((n10 >> 16) & 0xffu), unorm8((n01 >> 16) & 0xffu), unorm8((n11 >> 16) & 0xffu));
+        const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
+        prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
+    }
+    const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
+    const float currId = __ldg(io.ids + p);
+    const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
+    const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);
+    const float prevId = __ldg(io.prevIds + (size_t)nj * W + ni);
+
+    // the history-reset decision: exact IEEE arithmetic (expf(-0) == 1 exactly on a static camera)
+    const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
+    const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
+    const float wid = currId != prevId ? 0.0f : 1.0f;
+    const float similarity = fmul(fmul(wn, wz), wid);
+    if (similarity < 0.99f) accumMultiplier = 0.0f;
+    historyAccum = vmin(fadd(1.0f, fmul(historyAccum, accumMultiplier)), fc.framesPerSecond);
+    const float maxAccumulationFactor = fdiv(1.0f, historyAccum);
+    const f3 illumAvg = mix(prevGi, currGi, maxAccumulationFactor);
+    const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
+    storeHalf4(io.combinedOut, p, combined.x, combined.y, combined.z, 1.0f);
+    storeHalf4(io.giOut, p, illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
+    io.historyOut[p] = f2h(historyAccum);
+}
+
+// ---- pass 0: mergeReservoirs, the centre texel only (computeMergedReservoir with minmaxNearest = 0, :259-264) ----
+template <bool FINAL>
+__global__ void __launch_bounds__(kDnX * kDnY)
+mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
+    const int x = blockIdx.x * kDnX + threadIdx.x;
+    const int ly = blockIdx.y * kDnY + threadIdx.y;
+    if (x >= bd.W || ly >= bd.rows) return;
+    const int y = ly + bd.yOffset;
+    const size_t p = (size_t)ly * bd.W + x;
     const float4 gc = __ldg(io.guide + p);
     const f3 centerNormal = mk3(gc.x, gc.y, gc.z);
     const float centerDepth = gc.w;
-
-    float ax = 0.0f, ay = 0.0f, az = 0.0f, aw = 0.0f;
-    if (MERGE) {
-        // computeMergedReservoir with minmaxNearest = 0 (:259-264): the centre texel only
-        const float depthCutoff = fmul(0.1f, centerDepth);
-        float runningSum = 0.0f;
-        float cw = 0.0f;
-        const float probabilisticWeight = fdiv(1.0f, (float)__ldg(io.numVisible));
-        const bool normalReject = dot(centerNormal, centerNormal) < 0.906f;
-        const bool depthReject = fabsf(fsub(centerDepth, centerDepth)) > depthCutoff;
-        if (!normalReject && !depthReject) {
-            const f4 currReservoir = loadHalf4(io.shadowsIn, p);
-            const float randUpdate = random3(fadd((float)x, 0.5f), fadd((float)y, 0.5f), fc.time);
-            const float probability = fmul(currReservoir.w, probabilisticWeight);
-            cw = fadd(cw, probability);
-            if (randUpdate < fdiv(probability, cw)) {
-                ax = currReservoir.x; ay = currReservoir.y; az = currReservoir.z;
-                runningSum = fadd(runningSum, currReservoir.w);
-            }
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    const float depthCutoff = fmul(0.1f, centerDepth);
+    float runningSum = 0.0f;
+    float cw = 0.0f;
+    const float probabilisticWeight = fdiv(1.0f, (float)__ldg(io.numVisible));
+    const bool normalReject = dot(centerNormal, centerNormal) < 0.906f;
+    const bool depthReject = fabsf(fsub(centerDepth, centerDepth)) > depthCutoff;
+    if (!normalReject && !depthReject) {
+        const f4 currReservoir = loadHalf4(io.shadowsIn, p);
+        const float randUpdate = random3(fadd((float)x, 0.5f), fadd((float)y, 0.5f), fc.time);
+        const float probability = fmul(currReservoir.w, probabilisticWeight);
+        cw = fadd(cw, probability);
+        if (randUpdate < fdiv(probability, cw)) {
+            ax = currReservoir.x; ay = currReservoir.y; az = currReservoir.z;
+            runningSum = fadd(runningSum, currReservoir.w);
         }
-        aw = runningSum;
-    } else {
-        const int step = 1 + io.multiplier;
-        int tys[5];
+    }
+    const float denom = vmax(PREVENT_DIV_BY_ZERO, runningSum);
+    const f3 shadowFactor = mk3(ax, ay, az) / denom;
+    storeHalf4(io.reservoirOut, p, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+    if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, shadowFactor);
+}
+
+// ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
+constexpr int kLat = 4;                       // outputs per thread, consecutive on the tap lattice of its column
+constexpr float kLog2e = 1.4426950408889634f;
+
+SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <bool FINAL>
+__global__ void __launch_bounds__(kDnX * kDnY)
+atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
+    const int W = bd.W, rows = bd.rows;
+    const int x = blockIdx.x * kDnX + threadIdx.x;
+    if (x >= W) return;
+    const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
+    const int t = blockIdx.y * kDnY + threadIdx.y;           // lattice column-of-rows id: residue r, group g
+    const int g = t / s, r = t - g * s;
+    const int m0 = g * kLat;                                 // lattice index of output 0: row (m0 + k)*s + r
+    if (m0 * s + r >= rows) return;
+
+    float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
+    float acc[kLat][4];
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) {
+        const int ly = min((m0 + k) * s + r, rows - 1);
+        cen[k] = __ldg(io.guide + (size_t)ly * W + x);
+        cen[k].w *= kLog2e;
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+    }
+    int txs[5];
+    #pragma unroll
+    for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
+
+    #pragma unroll
+    for (int c = 0; c < kLat + 4; ++c) {
+        // band-local clamp == CLAMP_TO_EDGE on a whole frame
+        const size_t rowBase = (size_t)iclamp((m0 + c - 2) * s + r, 0, rows - 1) * W;
+        const float4* __restrict__ rowG = io.guide + rowBase;
+        const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
         #pragma unroll
-        for (int k = 0; k < 5; ++k) tys[k] = iclamp(ly + (k - 2) * step, 0, rows - 1) * W;   // band-local clamp == CLAMP_TO_EDGE on a whole frame
-        #pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) {
-            const int tx = iclamp(x + dx * step, 0, W - 1);
+        for (int d = 0; d < 5; ++d) {
+            const float4 gq = __ldg(rowG + txs[d]);
+            const uint2 rv = __ldg(rowS + txs[d]);
+            // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly
+            const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
+            const float tq = gq.w * kLog2e;
             #pragma unroll
-            for (int dy = -2; dy <= 2; ++dy) {
-                const size_t q = (size_t)(tys[dy + 2] + tx);
-                const f4 r = loadHalf4(io.shadowsIn, q);
-                float w = 1.0f;
-                if (dx != 0 || dy != 0) {
-                    const float4 g = __ldg(io.guide + q);
-                    float wn = __fmaf_rn(gc.z, g.z, __fmaf_rn(gc.y, g.y, __fmul_rn(gc.x, g.x)));
-                    wn = fmaxf(wn, 0.0f);
-                    wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn; wn = wn * wn;   // ^128
-                    w = wn * __expf(-fabsf(gc.w - g.w));
+            for (int k = 0; k < kLat; ++k) {
+                const int dy = c - 2 - k;
+                if (dy < -2 || dy > 2) continue;
+                float w = 1.0f;                              // centre tap (:156)
+                if (dy != 0 || d != 2) {
+                    // max(0, n.n')^128 * exp(-|z - z'|)   (sigmaN = 128, sigmaZ = 1, :93-98, :169-173)
+                    const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
+                    w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
                 }
-                ax = __fmaf_rn(w, r.x, ax); ay = __fmaf_rn(w, r.y, ay); az = __fmaf_rn(w, r.z, az); aw = __fmaf_rn(w, r.w, aw);
+                acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
+                acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
             }
         }
     }
-    const float denom = vmax(PREVENT_DIV_BY_ZERO, aw);
-    const f3 shadowFactor = mk3(ax, ay, az) / denom;
-    storeHalf4(io.reservoirOut, p, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
-
-    if (FINAL) {
-        const float u = fdiv(fadd((float)x, 0.5f), (float)W), v = fdiv(fadd((float)y, 0.5f), (float)bd.fullH);
-        const f4 screenColor = loadHalf4(io.screen, p);
-        const f4 gi4 = loadHalf4(io.illum, p);
-        const f3 gi = mk3(gi4.x, gi4.y, gi4.z);
-        const uint32_t vel = __ldg(io.velocity + p);
-        const float pu = fsub(u, h2f((unsigned short)(vel & 0xffffu))), pv = fsub(v, h2f((unsigned short)(vel >> 16)));
-        float historyAccum = h2f(__ldg(io.historyIn + p));
-        float accumMultiplier = 1.0f;
-        const f3 currGi = shadowFactor;
-
-        // reprojected reads; rows are band-local (previous-frame planes hold the same rows)
-        Bilin k = bilinSetup(pu, pv, W, bd.fullH);
-        k.j0 = iclamp(k.j0 - bd.yOffset, 0, rows - 1); k.j1 = iclamp(k.j1 - bd.yOffset, 0, rows - 1);
-        const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
-        float prevCenterDepth; f3 pn, prevGi;
-        if (k.a == 0.0f && k.b == 0.0f) {
-            // the reprojected tap sits on a texel centre (always, on a static camera): the bilinear blend
-            // (1*1)*t00 + 0*t10 + 0*t01 + 0*t11 is t00 exactly, so three of the four fetches are skipped
-            prevCenterDepth = __ldg(io.prevDepth + q00);
-            const uint32_t n00 = __ldg(io.prevNormal + q00);
-            pn = mk3(unorm8(n00 & 0xffu), unorm8((n00 >> 8) & 0xffu), unorm8((n00 >> 16) & 0xffu));
-            const f4 g00 = loadHalf4(io.prevGi, q00);
-            prevGi = mk3(g00.x, g00.y, g00.z);
-        } else {
-            prevCenterDepth = bilinMix(k, __ldg(io.prevDepth + q00), __ldg(io.prevDepth + q10), __ldg(io.prevDepth + q01), __ldg(io.prevDepth + q11));
-            const uint32_t n00 = __ldg(io.prevNormal + q00), n10 = __ldg(io.prevNormal + q10), n01 = __ldg(io.prevNormal + q01), n11 = __ldg(io.prevNormal + q11);
-            pn.x = bilinMix(k, unorm8(n00 & 0xffu), unorm8(n10 & 0xffu), unorm8(n01 & 0xffu), unorm8(n11 & 0xffu));
-            pn.y = bilinMix(k, unorm8((n00 >> 8) & 0xffu), unorm8((n10 >> 8) & 0xffu), unorm8((n01 >> 8) & 0xffu), unorm8((n11 >> 8) & 0xffu));
-            pn.z = bilinMix(k, unorm8((n00 >> 16) & 0xffu), unorm8((n10 >> 16) & 0xffu), unorm8((n01 >> 16) & 0xffu), unorm8((n11 >> 16) & 0xffu));
-            const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
-            prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
-        }
-        const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
-        const float currId = __ldg(io.ids + p);
-        const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
-        const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);
-        const float prevId = __ldg(io.prevIds + (size_t)nj * W + ni);
-
-        // the history-reset decision: exact IEEE arithmetic (expf(-0) == 1 exactly on a static camera)
-        const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
-        const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
-        const float wid = currId != prevId ? 0.0f : 1.0f;
-        const float similarity = fmul(fmul(wn, wz), wid);
-        if (similarity < 0.99f) accumMultiplier = 0.0f;
-        historyAccum = vmin(fadd(1.0f, fmul(historyAccum, accumMultiplier)), fc.framesPerSecond);
-        const float maxAccumulationFactor = fdiv(1.0f, historyAccum);
-        const f3 illumAvg = mix(prevGi, currGi, maxAccumulationFactor);
-        const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
-        storeHalf4(io.combinedOut, p, combined.x, combined.y, combined.z, 1.0f);
-        storeHalf4(io.giOut, p, illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
-        io.historyOut[p] = f2h(historyAccum);
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) {
+        const int ly = (m0 + k) * s + r;
+        if (ly >= rows) break;
+        const float denom = vmax(PREVENT_DIV_BY_ZERO, acc[k][3]);
+        const f3 shadowFactor = mk3(acc[k][0], acc[k][1], acc[k][2]) / denom;
+        storeHalf4(io.reservoirOut, (size_t)ly * W + x, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+        if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), shadowFactor);
     }
 }
 
@@ -185,11 +242,18 @@ int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* 
 
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_) {
     dim3 block(kDnX, kDnY);
-    dim3 grid((bd.W + kDnX - 1) / kDnX, (bd.rows + kDnY - 1) / kDnY);
-    if (merge && final_) denoiseKernel<true, true><<<grid, block, 0, stream>>>(fc, bd, io);
-    else if (merge) denoiseKernel<true, false><<<grid, block, 0, stream>>>(fc, bd, io);
-    else if (final_) denoiseKernel<false, true><<<grid, block, 0, stream>>>(fc, bd, io);
-    else denoiseKernel<false, false><<<grid, block, 0, stream>>>(fc, bd, io);
+    if (merge) {
+        dim3 grid((bd.W + kDnX - 1) / kDnX, (bd.rows + kDnY - 1) / kDnY);
+        if (final_) mergeKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
+        else mergeKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
+    } else {
+        // thread rows enumerate (group, residue) pairs of the tap lattice: ceil(rows / (s*kLat)) groups of s residues
+        const int s = 1 + io.multiplier;
+        const int threadRows = ((bd.rows + s * kLat - 1) / (s * kLat)) * s;
+        dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
+        if (final_) atrousKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
+        else atrousKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
+    }
     return 1;
 }
 
