@@ -32,6 +32,7 @@
 // apron reproduces the whole-frame bytes.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
+#include "sgi_merge.cuh"
 
 namespace sgi {
 namespace {
@@ -138,25 +139,8 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
     const float4 gc = __ldg(io.guide + p);
     const f3 centerNormal = mk3(gc.x, gc.y, gc.z);
     const float centerDepth = gc.w;
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    const float depthCutoff = fmul(0.1f, centerDepth);
-    float runningSum = 0.0f;
-    float cw = 0.0f;
-    const float probabilisticWeight = fdiv(1.0f, (float)__ldg(io.numVisible));
-    const bool normalReject = dot(centerNormal, centerNormal) < 0.906f;
-    const bool depthReject = fabsf(fsub(centerDepth, centerDepth)) > depthCutoff;
-    if (!normalReject && !depthReject) {
-        const f4 currReservoir = loadHalf4(io.shadowsIn, p);
-        const float randUpdate = random3(fadd((float)x, 0.5f), fadd((float)y, 0.5f), fc.time);
-        const float probability = fmul(currReservoir.w, probabilisticWeight);
-        cw = fadd(cw, probability);
-        if (randUpdate < fdiv(probability, cw)) {
-            ax = currReservoir.x; ay = currReservoir.y; az = currReservoir.z;
-            runningSum = fadd(runningSum, currReservoir.w);
-        }
-    }
-    const float denom = vmax(PREVENT_DIV_BY_ZERO, runningSum);
-    const f3 shadowFactor = mk3(ax, ay, az) / denom;
+    const f3 shadowFactor = mergeCentreTexel(centerNormal, centerDepth, loadHalf4(io.shadowsIn, p), fadd((float)x, 0.5f), fadd((float)y, 0.5f),
+                                             fc.time, __ldg(io.numVisible));
     storeHalf4(io.reservoirOut, p, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
     if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, shadowFactor);
 }
@@ -169,7 +153,7 @@ SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 template <bool FINAL>
-__global__ void __launch_bounds__(kDnX * kDnY)
+__global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;

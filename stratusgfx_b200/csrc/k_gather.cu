@@ -25,7 +25,8 @@
 //   inside the 1e-3 relative / 60 dB PSNR bar once stored as binary16.
 //
 // The kernel also writes the frame's "guide" plane (decoded normal + depth, float4) that the
-// denoiser passes read instead of re-decoding 25 normals per pixel per pass.
+// denoiser passes read instead of re-decoding 25 normals per pixel per pass, and (when asked) the
+// output of denoise pass 0, which is a per-pixel function of the reservoir it has just computed.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -61,10 +62,14 @@ __device__ __noinline__ bool exactShadowed(f3 fragDir, float lightNormalDot, flo
 // (or a near-tie between major axes) needs the exact division chain
 SGI_DEV int cubeTexelDecided(f3 d, int res) {
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int face; float sc, tc, ma;
-    if (ax >= ay && ax >= az) { ma = ax; if (d.x >= 0.0f) { face = 0; sc = -d.z; tc = -d.y; } else { face = 1; sc = d.z; tc = -d.y; } }
-    else if (ay >= az)        { ma = ay; if (d.y >= 0.0f) { face = 2; sc = d.x; tc = d.z; } else { face = 3; sc = d.x; tc = -d.z; } }
-    else                      { ma = az; if (d.z >= 0.0f) { face = 4; sc = d.x; tc = -d.y; } else { face = 5; sc = -d.x; tc = -d.y; } }
+    // major axis and (sc, tc) of GL 4.6 table 8.19 as selects (no divergent branches)
+    const bool xMajor = ax >= ay && ax >= az, yMajor = !xMajor && ay >= az;
+    const float ma = xMajor ? ax : (yMajor ? ay : az);
+    const float dm = xMajor ? d.x : (yMajor ? d.y : d.z);           // signed major component
+    const bool pos = dm >= 0.0f;
+    const int face = (xMajor ? 0 : (yMajor ? 2 : 4)) + (pos ? 0 : 1);
+    const float sc = xMajor ? (pos ? -d.z : d.z) : (yMajor ? d.x : (pos ? d.x : -d.x));
+    const float tc = yMajor ? (pos ? d.z : -d.z) : -d.y;
     // the face choice above uses exact comparisons of the inputs, so it is already the exact one
     const float inv = rcpFast(ma), fres = (float)res;
     const float se = fma_(sc * inv, 0.5f, 0.5f) * fres, te = fma_(tc * inv, 0.5f, 0.5f) * fres;
@@ -122,7 +127,7 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
              const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
-             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut) {
+             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut) {
     const int x = blockIdx.x * kGatherThreadsX + threadIdx.x;
     const int ly = blockIdx.y * kGatherThreadsY + threadIdx.y;
     if (x >= bd.W || ly >= bd.rows) return;
@@ -181,19 +186,24 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     const float maxRandomIndexF = (float)(V - 1);
     const float minGi = fc.minGiOcclusionFactor;
 
-    // V <= 0: undefined in the reference (stale lights); defined here as "no light"
+    // V <= 0: undefined in the reference (stale lights); defined here as "no light".
+    // The shader's single loop re-draws with `--i; continue;` (vpl_pbr_gi.fs:164-171).  Here the re-draws of one sample run in
+    // an inner loop (the same sequence of draws per pixel), so that the lanes of a warp reach the expensive shading part
+    // together: it then executes max-over-lanes(sampleCount) times per warp instead of max-over-lanes(samples + re-draws).
     for (int i = 0, resamples = 0; V > 0 && i < sampleCount; ++i) {
-        const float rnd = random3(pcx, pcy, seedZ);
-        seedZ = fadd(seedZ, 10000.0f);
-        const int lightIndex = (int)fmul(maxRandomIndexF, rnd);
-        const float4* L = reinterpret_cast<const float4*>(lightData + lightIndex);
-        const float4 lp = __ldg(L);
-        const float4 rfi = __ldg(L + 3);                    // radius, farPlane, intensity, pad
-        const f3 lightPosition = mk3(lp.x, lp.y, lp.z);
-        const f3 lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
-        const float lightRadius = rfi.x;
-        const float d2 = dotFast(lightMinusFrag, lightMinusFrag);
-        if (resamples < 5) {
+        const float4* L; float4 lp, rfi; f3 lightPosition, lightMinusFrag; float lightRadius, d2; int lightIndex;
+        while (true) {
+            const float rnd = random3(pcx, pcy, seedZ);
+            seedZ = fadd(seedZ, 10000.0f);
+            lightIndex = (int)fmul(maxRandomIndexF, rnd);
+            L = reinterpret_cast<const float4*>(lightData + lightIndex);
+            lp = __ldg(L);
+            rfi = __ldg(L + 3);                                 // radius, farPlane, intensity, pad
+            lightPosition = mk3(lp.x, lp.y, lp.z);
+            lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
+            lightRadius = rfi.x;
+            d2 = dotFast(lightMinusFrag, lightMinusFrag);
+            if (resamples >= 5) break;
             // if (dot(normal, normalize(l)) < 0 || length(l) > radius) re-draw      (vpl_pbr_gi.fs:164-171)
             const float s = dotFast(px.normal, lightMinusFrag);      // same sign as the normalised dot product
             const float r2 = lightRadius * lightRadius;
@@ -202,7 +212,8 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
             bool redraw;
             if (sideSure && (farSure || nearSure)) redraw = (s < 0.0f) || farSure;
             else redraw = exactRedraw(px.normal, lightMinusFrag, lightRadius);
-            if (redraw) { ++resamples; --i; continue; }
+            if (!redraw) break;
+            ++resamples;
         }
         const float4 lc = __ldg(L + 1);
         const float4 sp = __ldg(L + 2);
@@ -237,7 +248,20 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     validSamples = fmaxf(validSamples, 1.0f);
     const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
     storeHalf4(colorOut, p, color.x, color.y, color.z, 1.0f);
-    storeHalf4(reservoirOut, p, fminf(vplColor.x, HALF_FLOAT_MAX), fminf(vplColor.y, HALF_FLOAT_MAX), fminf(vplColor.z, HALF_FLOAT_MAX), validSamples);
+    const unsigned short hr = f2h(fminf(vplColor.x, HALF_FLOAT_MAX)), hg = f2h(fminf(vplColor.y, HALF_FLOAT_MAX)), hb = f2h(fminf(vplColor.z, HALF_FLOAT_MAX)),
+                         ha = f2h(validSamples);
+    uint2 packed;
+    packed.x = (uint32_t)hr | ((uint32_t)hg << 16);
+    packed.y = (uint32_t)hb | ((uint32_t)ha << 16);
+    reservoirOut[p] = packed;
+    if (mergedOut != nullptr) {
+        // Denoise pass 0 on the binary16 reservoir just stored.  mergeCentreTexel (sgi_merge.cuh) reduces to rgb / max(1e-5, a)
+        // here: the normal is unit length, |z - z| = 0, and with a >= 1 and 1 <= V <= 4480 the single candidate's acceptance
+        // ratio probability / cw is x / x = 1 exactly, which every draw in [0,1) passes.  V <= 0 leaves the reservoir empty.
+        const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha));
+        const f3 m = V > 0 ? mk3(h2f(hr), h2f(hg), h2f(hb)) / denom : mk3(0.0f);
+        storeHalf4(mergedOut, p, m.x, m.y, m.z, 1.0f);
+    }
 }
 
 }  // namespace
@@ -245,10 +269,10 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut) {
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut) {
     dim3 block(kGatherThreadsX, kGatherThreadsY);
     dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
-    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut);
+    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut, mergedOut);
     return 1;
 }
 

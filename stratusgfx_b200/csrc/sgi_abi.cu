@@ -136,6 +136,7 @@ int sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers) {
     h->buf = *buffers;
     h->bound = true;
     h->guideValid = false;
+    h->pass0Fused = false;
     return SGI_OK;
 }
 
@@ -197,8 +198,13 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     const int n = launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
-                               atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide);
+                               atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
+                               h->cp.denoise_iters > 1 ? (uint2*)h->resA : nullptr);
     h->guideValid = true;
+    // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it
+    // into vplGIDenoisedFbo1's reservoir attachment already, valid for a pass-0 call with the same `time`
+    h->pass0Fused = h->cp.denoise_iters > 1;
+    h->pass0Time = fp->time;
     return postLaunch(h, n);
 }
 
@@ -230,6 +236,11 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
     io.multiplier = (1 << pass) - 1;             // std::pow(2, i) - 1 (BE:1920)
     io.guide = (const float4*)h->guide;
     int n = 0;
+    if (pass == 0 && !final_ && h->pass0Fused && std::memcmp(&h->pass0Time, &fp->time, sizeof(float)) == 0) {
+        h->pass0Fused = false;                   // resA already holds this pass's output (written by sgi_gather)
+        return SGI_OK;
+    }
+    if (pass == 0) h->pass0Fused = false;
     if (!h->guideValid) {                        // denoise called without this library's gather in the same frame
         n += launchPrepareGuide(h->stream, bandDims(h), (const uint32_t*)h->buf.normal, (const float*)h->buf.depth, (float4*)h->guide);
         h->guideValid = true;

@@ -83,6 +83,8 @@ struct SgiHandle_ {
     int cur = 0;
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
     bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
+    bool pass0Fused = false;        // the gather of this frame already wrote denoise pass 0 into resA, for `pass0Time`
+    float pass0Time = 0.0f;
     // scratch for the cull
     uint32_t* cullBallots = nullptr;
     unsigned int* cullTicket = nullptr;
@@ -105,7 +107,7 @@ int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerT
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut);
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
 

@@ -78,6 +78,25 @@ def test_fused_frame_call_equals_staged_calls(tiny):
     gp.close()
 
 
+def test_host_pipeline_equals_device_resident_frames(built):
+    """The pipelined host-buffer API (hostpipe.py: rotating device slots, previous-frame planes kept on the device,
+    copies on side streams) must produce the bytes of the plain device-resident path, frame after frame."""
+    import torch
+    from stratusgfx_b200.hostpipe import HostFramePipeline, pin_frame
+    d = SceneData("tiny", frames=5, yaw_deg_per_frame=0.25)
+    staged = run_cuda_staged(d)
+    gp = make_pass(d)
+    pipe = HostFramePipeline(gp)
+    first_prev = {k: torch.from_numpy(getattr(d.gb[-1], k)).pin_memory() for k in ("normal", "id", "depth")}
+    for f in range(5):
+        host = pin_frame(torch, d.gb[f], d.vpl_data, d.atlas_by_vpl, d.csm[f])
+        tk = pipe.submit(d.fp[f], host, None, first_prev if f == 0 else None)
+        out = pipe.result(tk).numpy()
+        assert np.array_equal(out.view(np.uint16), staged[f]["combined"].view(np.uint16)), f
+    assert pipe.h2d_bytes > 0 and pipe.d2h_bytes == d.W * d.H * 8
+    gp.close()
+
+
 def test_reference_method_names_drive_the_same_path(tiny):
     staged = run_cuda_staged(tiny, frames=1)
     gp = make_pass(tiny)
