@@ -148,7 +148,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from stratusgfx_b200.bands import APRON, broadcast_frame_inputs, gather_bands, plan_bands
+    from stratusgfx_b200.bands import APRON, broadcast_frame_inputs, connect_bands, gather_bands, halo_rows, plan_bands
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
 
@@ -158,7 +158,9 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     scene = Scene(args.workload)
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
-    bands = plan_bands(H, world)
+    p2p = world > 1 and args.bands == "p2p"
+    halo = halo_rows(iters)
+    bands = plan_bands(H, world, halo if p2p else APRON)
     me = bands[rank]
     band, y0, rows = me.b1 - me.b0, me.y0, me.rows
 
@@ -179,22 +181,36 @@ def run_ours(args, rank, world, local_rank):
     gp.set_csm(csm)
     gp.bind()
 
-    # per-step NCCL traffic of the band split: VPL table + atlas entries + the <= 5 cube maps refreshed this frame
+    # per-step NCCL traffic of the band split: VPL table + atlas entries + the <= 5 cube maps refreshed this frame, packed
+    # into ONE byte buffer (one broadcast; NCCL has no 16-bit integer type) that the pass reads in place
     refreshed = [int(at[i, 0]) * 320 + int(at[i, 1]) for i in range(min(5, N))]
     if world > 1:
-        sa = gp.t["shadowAtlas"].view(-1, 6, scene.cube_res, scene.cube_res)
-        maps_buf = torch.stack([sa[s] for s in refreshed]).contiguous()
-        full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
+        R = scene.cube_res
+        nb_v, nb_a, nb_m = N * 64, N * 8, len(refreshed) * 6 * R * R * 2
+        packed = torch.empty(nb_v + nb_a + nb_m, dtype=torch.uint8, device=dev)
+        v_view = packed[:nb_v].view(torch.float32).view(N, 16)
+        a_view = packed[nb_v:nb_v + nb_a].view(torch.int32).view(N, 2)
+        maps_buf = packed[nb_v + nb_a:].view(torch.int16).view(len(refreshed), 6, R, R)
+        v_view.copy_(gp.t["vplData"]); a_view.copy_(gp.t["atlasEntryByVpl"])
+        gp.t["vplData"], gp.t["atlasEntryByVpl"] = v_view, a_view
+        sa = gp.t["shadowAtlas"].view(-1, 6, R, R)
+        maps_buf.copy_(torch.stack([sa[s] for s in refreshed]))
+        gp.bind()
+        if p2p:
+            connect_bands(dist, gp, me, world)           # band_setup + CUDA IPC attach of the neighbours and of rank 0's frame image
+        else:
+            full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
 
     def step(i):
         fp.time = 1000.0 + 16.0 * i
         if world > 1:
-            broadcast_frame_inputs(dist, [gp.t["vplData"], gp.t["atlasEntryByVpl"], maps_buf])
+            broadcast_frame_inputs(dist, [packed])
             for j, s in enumerate(refreshed):
                 sa[s].copy_(maps_buf[j])
         gp.frame(fp)
-        if world > 1:
+        if world > 1 and not p2p:
             gather_bands(dist, gp.t["lightingOut"][me.owned], full_out, bands, rank)
+        # p2p: every band's final pass stored its rows into rank 0's frame image and rank 0's stream has waited for all of them
 
     def fence():
         if world > 1:
@@ -226,6 +242,7 @@ def run_ours(args, rank, world, local_rank):
     ms_step = ms_total / args.steps
     value = W * H * N / (ms_step * 1e-3) / 1e9
     V = gp.visible_count()
+    band_timeouts = gp.band_timeouts() if p2p else 0
 
     # ---- per-stage device times (CUDA events on the launching stream), for the roofline ----
     stages = {}
@@ -295,8 +312,10 @@ def run_ours(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
-                           "parallelism": "single GPU" if world == 1 else f"{world} row bands of {band} rows + {APRON}-row apron, NCCL broadcast of VPL table and 5 cube maps, NCCL gather of lit bands",
-                           "visible_vpls": V, "storage": "f16/unorm8 planes"},
+                           "parallelism": "single GPU" if world == 1 else (
+                               f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of VPL table + 5 cube maps, lit rows stored into rank 0's frame image by the final pass" if p2p else
+                               f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
+                           "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts},
                 "clocks": clocks,
                 "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass"},
@@ -323,6 +342,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["tiny", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bands", default="p2p", choices=["p2p", "apron"], help="multi-GPU halo strategy (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -188,6 +188,37 @@ typedef struct SgiBuffers {
 
 typedef struct SgiHandle_* SgiHandle;
 
+/* ---- multi-GPU row bands with peer-to-peer halos (no reference counterpart — the
+ *      reference is single-GPU) ------------------------------------------------------------------
+ * A band handle HOLDS frame rows [y_offset, y_offset+rows) of every per-pixel plane but COMPUTES only
+ * [compute_y0, compute_y0+compute_rows).  The held rows outside the computed range are halo: the caller
+ * supplies the G-buffer there (it is an input), while the denoiser's reservoir / GI / history halo rows
+ * are written by the neighbouring band's kernels directly into this handle's memory through NVLink peer
+ * stores, followed by a release flag; the consumer pass waits on the flag in stream order.  The final
+ * pass of every band also stores its lit rows into the root band's frame image (the "gather").
+ * Handles may live in one process (peer access) or one process per GPU (CUDA IPC). */
+#define SGI_HALO_ROWS 20   /* >= 16 = reach of the widest reference à-trous pass (2*(multiplier+1), BE:1920), on the 5-row tile grid */
+enum { SGI_PEER_UP = 0 /* band rank-1 */, SGI_PEER_DOWN = 1 /* band rank+1 */, SGI_PEER_ROOT = 2 /* owner of the frame image */ };
+
+typedef struct SgiBandParams {
+    int32_t compute_y0;        /* first frame row this handle computes (>= y_offset, multiple of 5)        */
+    int32_t compute_rows;      /* rows it computes (multiple of 5)                                          */
+    int32_t rank;              /* band index, 0 = top                                                        */
+    int32_t world;             /* number of bands                                                            */
+    int32_t owns_frame_image;  /* 1: allocate the full_height x width half4 frame images bands store into    */
+} SgiBandParams;
+
+typedef struct SgiPeerInfo {   /* plain data; exchanged between band processes (e.g. all_gather) */
+    uint8_t  mem_handle[64];   /* cudaIpcMemHandle_t of the handle's shared slab                             */
+    uint64_t local_base;       /* slab address in the exporting process (used when pid matches)              */
+    int64_t  off_res[2];       /* vplGIDenoisedFbo1/2 reservoir attachments                                  */
+    int64_t  off_gi[2];        /* GI ping-pong                                                               */
+    int64_t  off_hist[2];      /* history ping-pong                                                          */
+    int64_t  off_flags;        /* int32[SGI_BAND_FLAGS]                                                      */
+    int64_t  off_image[2];     /* frame images (owner only, else -1), alternating by frame parity            */
+    int32_t  y_offset, rows, compute_y0, compute_rows, rank, device, pid, _pad;
+} SgiPeerInfo;
+
 /* create / destroy / resize — UpdateWindowDimensions_ (BE:436) and InitializeVplData_ (BE:297) */
 int  sgi_create(const SgiCreateParams* params, SgiHandle* out);
 int  sgi_destroy(SgiHandle h);
@@ -208,6 +239,17 @@ int  sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass);  /* 
 int  sgi_denoise(SgiHandle h, const SgiFrameParams* fp);       /* all passes + blit + history swap (a6) */
 /* all of the above on one stream: cull, colour, tile lists, gather, denoise */
 int  sgi_frame(SgiHandle h, const SgiFrameParams* fp);
+
+/* row bands with peer-to-peer halos: set up (re-allocates the shared planes), export, attach neighbours / root.
+ * After sgi_band_setup every stage entry point computes only the band's rows, pushes its boundary rows to the
+ * attached neighbours and orders itself against them with device-side flags; sgi_frame_image returns the assembled
+ * image of the last completed frame on the owner (stream-ordered: the owner's stream has already waited for all bands). */
+int  sgi_band_setup(SgiHandle h, const SgiBandParams* bp);
+int  sgi_band_export(SgiHandle h, SgiPeerInfo* out);
+int  sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer);
+int  sgi_frame_image(SgiHandle h, void** out_ptr, int64_t* out_bytes);
+/* nonzero when a peer wait timed out since creation (a neighbour died or never signalled) */
+int  sgi_band_timeouts(SgiHandle h, int32_t* out_count);
 
 /* the blocking variant of the visible count (what BE:1675-1678 maps the buffer for) */
 int  sgi_visible_count(SgiHandle h, int32_t* out_count);

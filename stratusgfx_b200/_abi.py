@@ -71,8 +71,25 @@ class Buffers(C.Structure):
                 ("infiniteLightShadowMap", C.c_void_p)]
 
 
+HALO_ROWS = 20
+PEER_UP, PEER_DOWN, PEER_ROOT = 0, 1, 2
+
+
+class BandParams(C.Structure):
+    _fields_ = [("compute_y0", C.c_int32), ("compute_rows", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("owns_frame_image", C.c_int32)]
+
+
+class PeerInfo(C.Structure):
+    _fields_ = [("mem_handle", C.c_uint8 * 64), ("local_base", C.c_uint64), ("off_res", C.c_int64 * 2), ("off_gi", C.c_int64 * 2),
+                ("off_hist", C.c_int64 * 2), ("off_flags", C.c_int64), ("off_image", C.c_int64 * 2),
+                ("y_offset", C.c_int32), ("rows", C.c_int32), ("compute_y0", C.c_int32), ("compute_rows", C.c_int32),
+                ("rank", C.c_int32), ("device", C.c_int32), ("pid", C.c_int32), ("_pad", C.c_int32)]
+
+
 ABI_SYMBOLS = [
     "sgi_create", "sgi_destroy", "sgi_resize", "sgi_bind_device_buffers", "sgi_register_gl",
+    "sgi_band_setup", "sgi_band_export", "sgi_band_attach", "sgi_frame_image", "sgi_band_timeouts",
     "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
     "sgi_visible_count", "sgi_get_plane", "sgi_download_plane", "sgi_reset_history", "sgi_synchronize", "sgi_stream",
     "sgi_launch_count", "sgi_last_error", "sgi_version",

@@ -6,16 +6,21 @@ One process per GPU (torch.distributed; NCCL on the GPU box, gloo in the CPU tes
   1. rank 0 broadcasts what the CPU side of the renderer produced for this frame: the VPL table,
      the per-VPL atlas entries and the <= 5 cube shadow maps re-rendered this frame
      (StratusRendererBackend.h:378) — < 0.5 MB in total;
-  2. every rank runs the whole pass on its band plus an apron of APRON rows on each inner edge, so the
-     three à-trous passes (reach 4 + 8 + 16 = 28 rows) need no halo exchange; apron rows are
-     recomputed redundantly and discarded;
-  3. the lit bands are gathered to rank 0.
+  2. every rank runs the whole pass on its band.  Two ways to feed the à-trous passes at the band edges:
+       peer-to-peer (default): the band holds halo_rows() extra rows per inner edge; the neighbours' kernels store
+         their boundary rows of every pass straight into them over NVLink (csrc/sgi_band.cu), ordered by epoch flags;
+         the final pass also stores the lit rows into rank 0's frame image, so there is no separate gather;
+       apron (comparison): the band holds APRON = 30 extra rows and recomputes them redundantly (reach 4 + 8 + 16 = 28),
+         no exchange, then
+  3. (apron mode only) the lit bands are gathered to rank 0 with NCCL.
 
 Band heights and aprons are multiples of the 5-pixel tile so per-tile lists never straddle a band.
 """
+import ctypes as C
 from dataclasses import dataclass
 
-APRON = 30   # >= 28 rows of à-trous reach, rounded up to the 5-pixel tile grid
+APRON = 30   # >= 28 rows of à-trous reach, rounded up to the 5-pixel tile grid (redundant-compute mode)
+HALO = 20    # >= 16 rows = reach of one à-trous pass (peer-to-peer mode, SGI_HALO_ROWS)
 TILE = 5
 
 
@@ -37,18 +42,52 @@ class Band:
         return slice(self.b0 - self.y0, self.b1 - self.y0)
 
 
+def halo_rows(denoise_iters):
+    """Rows a band must hold beyond its own for ONE à-trous pass of the widest spacing: 2*(multiplier+1) with
+    multiplier = 2^i - 1 (StratusRendererBackend.cpp:1920), rounded up to the tile grid.  4 iterations -> 16 -> 20."""
+    reach = 2 * (1 << max(denoise_iters - 1, 0)) if denoise_iters > 1 else 0
+    return (reach + TILE - 1) // TILE * TILE
+
+
 def plan_bands(height, world, apron=APRON):
+    """Bands for `world` GPUs.  `apron` = extra rows held on each inner edge: APRON for the redundant-compute mode
+    (every à-trous pass recomputed locally), halo_rows(iters) for the peer-to-peer mode (neighbours fill them)."""
     if height % (TILE * world):
         raise ValueError(f"height {height} does not split into {world} bands of whole {TILE}-pixel tiles")
     if apron % TILE:
         raise ValueError("apron must be a multiple of the tile size")
     h = height // world
+    if world > 1 and apron > h:
+        raise ValueError(f"bands of {h} rows are thinner than the {apron}-row halo")
     out = []
     for r in range(world):
         b0, b1 = r * h, (r + 1) * h
         y0, y1 = (max(0, b0 - apron), min(height, b1 + apron)) if world > 1 else (0, height)
         out.append(Band(r, b0, b1, y0, y1))
     return out
+
+
+def connect_bands(dist, gp, band, world, root=0):
+    """Peer-to-peer mode: band_setup on this rank's pass, all-gather the peer descriptors (plain bytes), attach the
+    neighbours and the frame-image owner.  Works with NCCL (GPU box) and gloo (tests) alike: only host bytes travel."""
+    import torch
+    from ._abi import PEER_DOWN, PEER_ROOT, PEER_UP, PeerInfo
+    gp.band_setup(band.b0, band.b1 - band.b0, band.rank, world, owns_frame_image=(band.rank == root))
+    mine = gp.band_export()
+    raw = bytes(mine)
+    infos = [None] * world
+    if world > 1:
+        dist.all_gather_object(infos, raw)
+    else:
+        infos[0] = raw
+    infos = [PeerInfo.from_buffer_copy(b) for b in infos]
+    if band.rank > 0:
+        gp.band_attach(PEER_UP, infos[band.rank - 1])
+    if band.rank + 1 < world:
+        gp.band_attach(PEER_DOWN, infos[band.rank + 1])
+    if band.rank != root:
+        gp.band_attach(PEER_ROOT, infos[root])
+    return infos
 
 
 def broadcast_frame_inputs(dist, tensors, src=0):

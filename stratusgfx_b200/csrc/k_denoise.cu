@@ -122,9 +122,15 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
     const float maxAccumulationFactor = fdiv(1.0f, historyAccum);
     const f3 illumAvg = mix(prevGi, currGi, maxAccumulationFactor);
     const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
-    storeHalf4(io.combinedOut, p, combined.x, combined.y, combined.z, 1.0f);
-    storeHalf4(io.giOut, p, illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
-    io.historyOut[p] = f2h(historyAccum);
+    const uint2 cv = packHalf4(combined.x, combined.y, combined.z, 1.0f), gv = packHalf4(illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
+    const unsigned short hv = f2h(historyAccum);
+    io.combinedOut[p] = cv;
+    io.giOut[p] = gv;
+    io.historyOut[p] = hv;
+    // row bands: this frame's GI/history boundary rows go to the neighbours' halos (reprojection may land there next
+    // frame), and the lit pixel goes straight into the root band's frame image — the "gather", overlapped with the pass
+    pushGiHistory(io.links, y, x, W, gv, hv);
+    if (io.links.image != nullptr) io.links.image[(size_t)y * W + x] = cv;
 }
 
 // ---- pass 0: mergeReservoirs, the centre texel only (computeMergedReservoir with minmaxNearest = 0, :259-264) ----
@@ -132,8 +138,8 @@ template <bool FINAL>
 __global__ void __launch_bounds__(kDnX * kDnY)
 mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
     const int x = blockIdx.x * kDnX + threadIdx.x;
-    const int ly = blockIdx.y * kDnY + threadIdx.y;
-    if (x >= bd.W || ly >= bd.rows) return;
+    const int ly = bd.c0 + blockIdx.y * kDnY + threadIdx.y;          // computed rows only
+    if (x >= bd.W || ly >= bd.c0 + bd.crows) return;
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * bd.W + x;
     const float4 gc = __ldg(io.guide + p);
@@ -141,7 +147,9 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
     const float centerDepth = gc.w;
     const f3 shadowFactor = mergeCentreTexel(centerNormal, centerDepth, loadHalf4(io.shadowsIn, p), fadd((float)x, 0.5f), fadd((float)y, 0.5f),
                                              fc.time, __ldg(io.numVisible));
-    storeHalf4(io.reservoirOut, p, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+    const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+    io.reservoirOut[p] = rv;
+    pushRes(io.links, y, x, bd.W, rv);
     if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, shadowFactor);
 }
 
@@ -161,14 +169,15 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
     const int t = blockIdx.y * kDnY + threadIdx.y;           // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
-    const int m0 = g * kLat;                                 // lattice index of output 0: row (m0 + k)*s + r
-    if (m0 * s + r >= rows) return;
+    const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
+    const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
+    if (c0 + m0 * s + r >= cEnd) return;
 
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
     float acc[kLat][4];
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
-        const int ly = min((m0 + k) * s + r, rows - 1);
+        const int ly = min(c0 + (m0 + k) * s + r, rows - 1);
         cen[k] = __ldg(io.guide + (size_t)ly * W + x);
         cen[k].w *= kLog2e;
         acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
@@ -180,7 +189,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     #pragma unroll
     for (int c = 0; c < kLat + 4; ++c) {
         // band-local clamp == CLAMP_TO_EDGE on a whole frame
-        const size_t rowBase = (size_t)iclamp((m0 + c - 2) * s + r, 0, rows - 1) * W;
+        const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
         const float4* __restrict__ rowG = io.guide + rowBase;
         const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
         #pragma unroll
@@ -207,16 +216,30 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     }
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
-        const int ly = (m0 + k) * s + r;
-        if (ly >= rows) break;
+        const int ly = c0 + (m0 + k) * s + r;
+        if (ly >= cEnd) break;
         const float denom = vmax(PREVENT_DIV_BY_ZERO, acc[k][3]);
         const f3 shadowFactor = mk3(acc[k][0], acc[k][1], acc[k][2]) / denom;
-        storeHalf4(io.reservoirOut, (size_t)ly * W + x, shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+        const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+        io.reservoirOut[(size_t)ly * W + x] = rv;
+        pushRes(io.links, ly + bd.yOffset, x, W, rv);
         if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), shadowFactor);
     }
 }
 
 }  // namespace
+
+// CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
+// (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+bool preloadDenoiseKernels() {
+    cudaFuncAttributes a; bool ok = true;
+    ok = ok && cudaFuncGetAttributes(&a, prepareGuideKernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, mergeKernel<false>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, mergeKernel<true>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true>) == cudaSuccess;
+    return ok;
+}
 
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide) {
     const size_t n = (size_t)bd.W * bd.rows;
@@ -227,13 +250,13 @@ int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* 
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_) {
     dim3 block(kDnX, kDnY);
     if (merge) {
-        dim3 grid((bd.W + kDnX - 1) / kDnX, (bd.rows + kDnY - 1) / kDnY);
+        dim3 grid((bd.W + kDnX - 1) / kDnX, (bd.crows + kDnY - 1) / kDnY);
         if (final_) mergeKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
         else mergeKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
     } else {
         // thread rows enumerate (group, residue) pairs of the tap lattice: ceil(rows / (s*kLat)) groups of s residues
         const int s = 1 + io.multiplier;
-        const int threadRows = ((bd.rows + s * kLat - 1) / (s * kLat)) * s;
+        const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
         if (final_) atrousKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
         else atrousKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);

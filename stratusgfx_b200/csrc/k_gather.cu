@@ -127,7 +127,8 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
              const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
-             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut) {
+             uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
+             const __grid_constant__ BandLinks links) {
     const int x = blockIdx.x * kGatherThreadsX + threadIdx.x;
     const int ly = blockIdx.y * kGatherThreadsY + threadIdx.y;
     if (x >= bd.W || ly >= bd.rows) return;
@@ -137,17 +138,18 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     const int texelsPerLayer = 6 * cubeRes * cubeRes;
 
     // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
+    const float depth = __ldg(gDepth + p);
+    PixelConsts px;
+    px.normal = decodeNormal(__ldg(gNormal + p));
+    guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
+    if (ly < bd.c0 || ly >= bd.c0 + bd.crows) return;      // halo row of a band: only the guide plane is needed here
     const m4 invPV = loadMat(fc.invPV);
     const f3 viewPosition = mk3(fc.viewPos[0], fc.viewPos[1], fc.viewPos[2]);
     const float pcx = fadd((float)x, 0.5f), pcy = fadd((float)y, 0.5f);          // gl_FragCoord.xy
     const float u = fdiv(pcx, (float)bd.W), v = fdiv(pcy, (float)bd.fullH);       // fsTexCoords
-    const float depth = __ldg(gDepth + p);
-    PixelConsts px;
     px.fragPos = worldPositionFromDepth(u, v, depth, invPV);
     const f3 toView = viewPosition - px.fragPos;
     const float distToCamera = length(toView);
-    px.normal = decodeNormal(__ldg(gNormal + p));
-    guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
     const uint32_t alb = __ldg(gAlbedo + p);
     const f3 baseColor = mk3(vmax(unorm8(alb & 0xffu), 0.01f), vmax(unorm8((alb >> 8) & 0xffu), 0.01f), vmax(unorm8((alb >> 16) & 0xffu), 0.01f));
     const uint32_t rma = __ldg(gRma + p);
@@ -260,19 +262,29 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
         // ratio probability / cw is x / x = 1 exactly, which every draw in [0,1) passes.  V <= 0 leaves the reservoir empty.
         const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha));
         const f3 m = V > 0 ? mk3(h2f(hr), h2f(hg), h2f(hb)) / denom : mk3(0.0f);
-        storeHalf4(mergedOut, p, m.x, m.y, m.z, 1.0f);
+        const uint2 mv = packHalf4(m.x, m.y, m.z, 1.0f);
+        mergedOut[p] = mv;
+        pushRes(links, y, x, bd.W, mv);
     }
 }
 
 }  // namespace
 
+// CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
+// (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+bool preloadGatherKernels() {
+    cudaFuncAttributes a; bool ok = true;
+    ok = ok && cudaFuncGetAttributes(&a, gatherKernel) == cudaSuccess;
+    return ok;
+}
+
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut) {
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links) {
     dim3 block(kGatherThreadsX, kGatherThreadsY);
     dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
-    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut, mergedOut);
+    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut, mergedOut, links);
     return 1;
 }
 

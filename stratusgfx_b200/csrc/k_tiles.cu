@@ -23,10 +23,12 @@ constexpr int kTileThreads = 128;
 __global__ void __launch_bounds__(kTileThreads)
 stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
              SgiVplStage1PerTileOutputs* __restrict__ out) {
-    const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesYLocal = bd.rows / SGI_TILE_DIVISOR;
-    const int tile = blockIdx.x * kTileThreads + threadIdx.x;
-    if (tile >= tilesX * tilesYLocal) return;
-    const int tx = tile % tilesX, ty = tile / tilesX;
+    // tiles of the band's computed rows only; outputs stay indexed by held tile row
+    const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesYCompute = bd.crows / SGI_TILE_DIVISOR;
+    const int t = blockIdx.x * kTileThreads + threadIdx.x;
+    if (t >= tilesX * tilesYCompute) return;
+    const int tx = t % tilesX, ty = t / tilesX + bd.c0 / SGI_TILE_DIVISOR;
+    const int tile = ty * tilesX + tx;
     const m4 invPV = loadMat(fc.invPV);
     // viewportWidthHeight = gl_NumWorkGroups.xy * gl_WorkGroupSize.xy (stage1.cs:54)
     const float vw = (float)(tilesX * SGI_TILE_DIVISOR), vh = (float)((bd.fullH / SGI_TILE_DIVISOR) * SGI_TILE_DIVISOR);
@@ -74,7 +76,7 @@ SGI_DEV float warpMin(float v) {
 //   thread level: FMA estimate against the tile's own 12th-best ratio, then the exact chain in the shader's operation order.
 // Margins (1e-4 relative at CTA level, 4e-5 at thread level) are >100x the rounding error of either evaluation.
 __global__ void __launch_bounds__(kS2Threads)
-stage2Kernel(int tilesX, int tilesY, const SgiVplStage1PerTileOutputs* __restrict__ stage1, const SgiVplData* __restrict__ lightData,
+stage2Kernel(int tilesX, int tileY0, int tilesY, const SgiVplStage1PerTileOutputs* __restrict__ stage1, const SgiVplData* __restrict__ lightData,
              const int32_t* __restrict__ visible, SgiVplStage2PerTileOutputs* __restrict__ out) {
     __shared__ StagedVpl sVpl[kS2Chunk];
     __shared__ float sRadius[kS2Chunk];
@@ -82,8 +84,8 @@ stage2Kernel(int tilesX, int tilesY, const SgiVplStage1PerTileOutputs* __restric
     __shared__ int sCnt[kS2Threads / 32];
     __shared__ float sRed[kS2Threads / 32][6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = blockIdx.x * kS2X + (tid % kS2X), ty = blockIdx.y * kS2Y + (tid / kS2X);
-    const bool active = tx < tilesX && ty < tilesY;
+    const int tx = blockIdx.x * kS2X + (tid % kS2X), ty = tileY0 + blockIdx.y * kS2Y + (tid / kS2X);   // computed tile rows [tileY0, tileY0 + tilesY)
+    const bool active = tx < tilesX && ty < tileY0 + tilesY;
     const int tile = ty * tilesX + tx;
     const int numVisible = __ldg(visible);            // slot 0 = count, list starts at slot 1
     f3 fragPos = mk3(0.0f), normal = mk3(0.0f);
@@ -192,9 +194,18 @@ stage2Kernel(int tilesX, int tilesY, const SgiVplStage1PerTileOutputs* __restric
 
 }  // namespace
 
+// CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
+// (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+bool preloadTileKernels() {
+    cudaFuncAttributes a; bool ok = true;
+    ok = ok && cudaFuncGetAttributes(&a, stage1Kernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, stage2Kernel) == cudaSuccess;
+    return ok;
+}
+
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  SgiVplStage1PerTileOutputs* out) {
-    const int tiles = (bd.W / SGI_TILE_DIVISOR) * (bd.rows / SGI_TILE_DIVISOR);
+    const int tiles = (bd.W / SGI_TILE_DIVISOR) * (bd.crows / SGI_TILE_DIVISOR);
     if (tiles <= 0) return 0;
     stage1Kernel<<<(tiles + kTileThreads - 1) / kTileThreads, kTileThreads, 0, stream>>>(fc, bd, depth, normal, out);
     return 1;
@@ -202,10 +213,10 @@ int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
 
 int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightData,
                  const int32_t* visible, SgiVplStage2PerTileOutputs* out) {
-    const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.rows / SGI_TILE_DIVISOR;
+    const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.crows / SGI_TILE_DIVISOR;
     if (tilesX <= 0 || tilesY <= 0) return 0;
     dim3 grid((tilesX + kS2X - 1) / kS2X, (tilesY + kS2Y - 1) / kS2Y);
-    stage2Kernel<<<grid, kS2Threads, 0, stream>>>(tilesX, tilesY, stage1, lightData, visible, out);
+    stage2Kernel<<<grid, kS2Threads, 0, stream>>>(tilesX, bd.c0 / SGI_TILE_DIVISOR, tilesY, stage1, lightData, visible, out);
     return 1;
 }
 

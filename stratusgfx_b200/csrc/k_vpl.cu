@@ -172,6 +172,15 @@ colorKernel(const __grid_constant__ FrameConsts fc, int cubeRes, SgiVplData* __r
 
 }  // namespace
 
+// CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
+// (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+bool preloadVplKernels() {
+    cudaFuncAttributes a; bool ok = true;
+    ok = ok && cudaFuncGetAttributes(&a, cullKernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, colorKernel) == cudaSuccess;
+    return ok;
+}
+
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc) {
     for (int i = 0; i < 16; ++i) fc->invPV[i] = fp->invProjectionView[i];
     for (int i = 0; i < 3; ++i) {

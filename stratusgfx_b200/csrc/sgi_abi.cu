@@ -31,25 +31,51 @@ static int fail(SgiHandle h, int code, const char* msg) { h->lastError = msg; re
 static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h->cp.rows; }
 
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1], &h->history[0], &h->history[1], &h->guide};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+    h->resA = h->resB = nullptr;
+    h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
+    h->frameImage[0] = h->frameImage[1] = nullptr;
+    h->flags = nullptr;
 }
 
+// Planes that another band may store into (reservoir ping-pong, GI/history ping-pong, flags, frame images) live in ONE
+// cudaMalloc slab, so a single CUDA IPC handle (or one peer-access base pointer) exposes them all (sgi_band.cu).
 static int allocPlanes(SgiHandle h) {
     const size_t n = pixels(h);
-    void** half4s[] = {&h->giColor, &h->giReservoir, &h->resA, &h->resB, &h->combined, &h->giIllum[0], &h->giIllum[1]};
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~size_t(255); return (int64_t)o; };
+    h->offRes[0] = take(n * 8); h->offRes[1] = take(n * 8);
+    h->offGi[0] = take(n * 8); h->offGi[1] = take(n * 8);
+    h->offHist[0] = take(n * 2); h->offHist[1] = take(n * 2);
+    h->offFlags = take(sgi::kBandFlags * sizeof(int32_t));
+    h->offImage[0] = h->offImage[1] = -1;
+    if (h->banded && h->band.owns_frame_image) {
+        const size_t img = (size_t)h->cp.width * (size_t)h->cp.full_height * 8;
+        h->offImage[0] = take(img); h->offImage[1] = take(img);
+    }
+    SGI_CUDA(h, cudaMalloc(&h->slab, off));
+    h->slabBytes = off;
+    char* base = (char*)h->slab;
+    h->resA = base + h->offRes[0]; h->resB = base + h->offRes[1];
+    for (int i = 0; i < 2; ++i) { h->giIllum[i] = base + h->offGi[i]; h->history[i] = base + h->offHist[i]; }
+    h->flags = (int32_t*)(base + h->offFlags);
+    for (int i = 0; i < 2; ++i) h->frameImage[i] = h->offImage[i] >= 0 ? base + h->offImage[i] : nullptr;
+    void** half4s[] = {&h->giColor, &h->giReservoir, &h->combined};
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
-    for (int i = 0; i < 2; ++i) SGI_CUDA(h, cudaMalloc(&h->history[i], n * 2));
     SGI_CUDA(h, cudaMalloc(&h->guide, n * 16));
     h->guideValid = false;
-    // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the
-    // previous-frame FBO is never cleared and starts at zero
-    for (int i = 0; i < 2; ++i) {
-        SGI_CUDA(h, cudaMemsetAsync(h->giIllum[i], 0, n * 8, h->stream));
-        SGI_CUDA(h, cudaMemsetAsync(h->history[i], 0, n * 2, h->stream));
-    }
+    // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the previous-frame FBO is
+    // never cleared and starts at zero.  Reservoir halo rows start at zero too.
+    SGI_CUDA(h, cudaMemsetAsync(h->slab, 0, off, h->stream));
     h->cur = 0;
+    h->frameNo = 0;
     return SGI_OK;
+}
+
+int sgiAllocPlanesForBand(SgiHandle h) {     // sgi_band_setup (sgi_band.cu): the slab layout depends on the band parameters
+    freePlanes(h);
+    return allocPlanes(h);
 }
 
 static int checkDims(int width, int full_height, int y_offset, int rows) {
@@ -61,6 +87,8 @@ static BandDims bandDims(const SgiHandle h) {
     BandDims bd;
     bd.W = h->cp.width; bd.fullH = h->cp.full_height; bd.yOffset = h->cp.y_offset; bd.rows = h->cp.rows;
     bd.cubeRes = h->cp.cube_res; bd.csmRes = h->cp.csm_res;
+    bd.c0 = h->banded ? h->band.compute_y0 - h->cp.y_offset : 0;
+    bd.crows = h->banded ? h->band.compute_rows : h->cp.rows;
     return bd;
 }
 
@@ -102,6 +130,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (cudaMalloc(&h->cullTicket, sizeof(unsigned int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (!(preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels())) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
     *out = h;
     return SGI_OK;
@@ -111,6 +140,7 @@ int sgi_destroy(SgiHandle h) {
     if (!h) return SGI_ERR_INVALID_ARG;
     cudaSetDevice(h->cp.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    sgi::detachPeers(h);
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
     if (h->cullTicket) cudaFree(h->cullTicket);
@@ -125,7 +155,9 @@ int sgi_resize(SgiHandle h, int32_t width, int32_t full_height, int32_t y_offset
     if (checkDims(width, full_height, y_offset, rows) != SGI_OK) return fail(h, SGI_ERR_INVALID_ARG, "sgi_resize: bad dimensions");
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    sgi::detachPeers(h);
     freePlanes(h);
+    h->banded = false;                      // a resized handle is a plain whole-range handle again; call sgi_band_setup to re-band
     h->cp.width = width; h->cp.full_height = full_height; h->cp.y_offset = y_offset; h->cp.rows = rows;
     h->bound = false;                       // per-pixel planes of the old size are no longer valid
     return allocPlanes(h);
@@ -195,11 +227,22 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, shadowDiffuseIndices); NEED(h, shadowCubeMaps[0]);
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
-    const int n = launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
+    int n = 0;
+    const bool fuse = h->cp.denoise_iters > 1;
+    BandLinks links = sgi::noLinks();
+    if (h->banded) {
+        // a new band frame starts here.  Neighbours must be done with the previous frame (their final pass read the halo rows
+        // this gather is about to overwrite) before the boundary rows of pass 0 are pushed into their memory.
+        ++h->frameNo;
+        if (h->frameNo > 1) n += sgi::waitNeighbours(h, sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters));
+        if (fuse) links = sgi::bandLinks(h, 0, false);
+    }
+    n += launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
-                               h->cp.denoise_iters > 1 ? (uint2*)h->resA : nullptr);
+                               fuse ? (uint2*)h->resA : nullptr, links);
+    if (h->banded && fuse) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it
     // into vplGIDenoisedFbo1's reservoir attachment already, valid for a pass-0 call with the same `time`
@@ -236,6 +279,7 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
     io.multiplier = (1 << pass) - 1;             // std::pow(2, i) - 1 (BE:1920)
     io.guide = (const float4*)h->guide;
     int n = 0;
+    if (h->banded && h->frameNo == 0) return fail(h, SGI_ERR_INVALID_ARG, "sgi_denoise_pass: a band handle needs sgi_gather first in every frame");
     if (pass == 0 && !final_ && h->pass0Fused && std::memcmp(&h->pass0Time, &fp->time, sizeof(float)) == 0) {
         h->pass0Fused = false;                   // resA already holds this pass's output (written by sgi_gather)
         return SGI_OK;
@@ -245,7 +289,16 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         n += launchPrepareGuide(h->stream, bandDims(h), (const uint32_t*)h->buf.normal, (const float*)h->buf.depth, (float4*)h->guide);
         h->guideValid = true;
     }
+    if (h->banded) {
+        // pass p reads the neighbours' pass p-1 rows from this handle's halo: wait (in stream order) for their flags
+        if (pass >= 1) n += sgi::waitNeighbours(h, sgi::bandEpoch(h->frameNo, pass));
+        io.links = sgi::bandLinks(h, pass % 2, final_);
+    }
     n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
+    if (h->banded) {
+        n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
+        if (final_ && h->band.owns_frame_image) n += sgi::waitAllBands(h);     // the assembled frame image is complete from here on
+    }
     if (final_) { h->cur ^= 1; h->guideValid = false; }   // swap with the previous-frame FBO (BE:1949-1951)
     return postLaunch(h, n);
 }

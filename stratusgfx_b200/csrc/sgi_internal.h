@@ -15,6 +15,21 @@ struct BandDims {
     int rows;         // rows held by the planes
     int cubeRes;
     int csmRes;
+    int c0;           // first held row this handle computes (band-local index; 0 for a whole frame)
+    int crows;        // rows computed (== rows unless the handle is a band with halo rows)
+};
+
+// where a band's kernels also store their boundary rows: the neighbour's halo rows (NVLink peer memory)
+struct PushTarget {
+    uint2* res;                // neighbour's reservoir plane written by this pass (half4), or nullptr
+    uint2* gi;                 // neighbour's GI plane of this frame (half4; final pass)
+    unsigned short* hist;      // neighbour's history plane of this frame (half; final pass)
+    int yOffset;               // neighbour's first held frame row
+    int firstRow, lastRow;     // frame rows [firstRow, lastRow) of mine that the neighbour holds as halo
+};
+struct BandLinks {
+    PushTarget up, down;
+    uint2* image;              // root's frame image (half4 [fullH][W]) or nullptr
 };
 
 // uniforms in device-friendly form; passed by value as a __grid_constant__ kernel parameter
@@ -40,6 +55,22 @@ struct AtlasTable {
     const uchar4* diffuse[SGI_MAX_TOTAL_SHADOW_ATLASES];
 };
 
+#ifdef __CUDACC__
+// store a band's boundary pixel into the neighbours' halo rows (plain st.global on peer-mapped pointers: NVLink writes)
+__device__ __forceinline__ void pushRes(const BandLinks& L, int y, int x, int W, uint2 v) {
+    if (L.up.res != nullptr && y >= L.up.firstRow && y < L.up.lastRow) L.up.res[(size_t)(y - L.up.yOffset) * W + x] = v;
+    if (L.down.res != nullptr && y >= L.down.firstRow && y < L.down.lastRow) L.down.res[(size_t)(y - L.down.yOffset) * W + x] = v;
+}
+__device__ __forceinline__ void pushGiHistory(const BandLinks& L, int y, int x, int W, uint2 gi, unsigned short hist) {
+    if (L.up.gi != nullptr && y >= L.up.firstRow && y < L.up.lastRow) {
+        const size_t q = (size_t)(y - L.up.yOffset) * W + x; L.up.gi[q] = gi; L.up.hist[q] = hist;
+    }
+    if (L.down.gi != nullptr && y >= L.down.firstRow && y < L.down.lastRow) {
+        const size_t q = (size_t)(y - L.down.yOffset) * W + x; L.down.gi[q] = gi; L.down.hist[q] = hist;
+    }
+}
+#endif
+
 struct DenoiseIO {
     const uint2* screen;          // half4
     const uint32_t* velocity;     // half2
@@ -55,6 +86,7 @@ struct DenoiseIO {
     const uint2* prevGi;          // half4
     const unsigned short* historyIn;   // half
     const int32_t* numVisible;    // vplVisibleIndices (count in slot 0)
+    BandLinks links;              // peer destinations (all null for a whole-frame handle)
     uint2* reservoirOut;          // half4
     uint2* combinedOut;           // half4 (final pass)
     uint2* giOut;                 // half4 (final pass)
@@ -85,6 +117,16 @@ struct SgiHandle_ {
     bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
     bool pass0Fused = false;        // the gather of this frame already wrote denoise pass 0 into resA, for `pass0Time`
     float pass0Time = 0.0f;
+    // one cudaMalloc slab holds the planes other bands may write into (resA, resB, giIllum, history, flags, frame images)
+    void* slab = nullptr;
+    size_t slabBytes = 0;
+    int64_t offRes[2] = {0, 0}, offGi[2] = {0, 0}, offHist[2] = {0, 0}, offFlags = 0, offImage[2] = {-1, -1};
+    int32_t* flags = nullptr;       // [SGI_BAND_FLAGS] inside the slab
+    void* frameImage[2] = {nullptr, nullptr};
+    bool banded = false;
+    SgiBandParams band{};
+    struct Peer { bool attached = false; bool ipc = false; char* base = nullptr; SgiPeerInfo info{}; } peer[3];
+    int64_t frameNo = 0;            // frames started through sgi_gather since creation (band epochs)
     // scratch for the cull
     uint32_t* cullBallots = nullptr;
     unsigned int* cullTicket = nullptr;
@@ -94,12 +136,25 @@ struct SgiHandle_ {
 namespace sgi {
 
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
+bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels(); bool preloadDenoiseKernels(); bool preloadBandKernels();
 
 // each launcher enqueues its kernels on `stream` and returns the number of launches made
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
                const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket);
 int launchColor(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, SgiVplData* updated, const int32_t* visible,
                 const SgiAtlasEntry* entries, const AtlasTable& atlases);
+// ---- row bands (sgi_band.cu) ----
+BandLinks noLinks();
+BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_);      // peer destinations of the pass writing reservoir resIndex
+inline int bandEpoch(int64_t frameNo, int stage) { return (int)(uint32_t)(frameNo * 32 + stage); }   // stage k: output of pass k-1 pushed
+int waitNeighbours(SgiHandle_* h, int epoch);
+int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
+int waitAllBands(SgiHandle_* h);
+void detachPeers(SgiHandle_* h);
+constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [8+r] band r's image rows landed
+int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
+int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int epoch, int32_t* timeouts);
+int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  SgiVplStage1PerTileOutputs* out);
 int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightData,
@@ -107,7 +162,7 @@ int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerT
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut);
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
 

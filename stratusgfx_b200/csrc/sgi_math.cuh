@@ -140,11 +140,12 @@ SGI_DEV f4 loadHalf4(const uint2* plane, size_t i) {
     return mk4(h2f((unsigned short)(v.x & 0xffffu)), h2f((unsigned short)(v.x >> 16)),
                h2f((unsigned short)(v.y & 0xffffu)), h2f((unsigned short)(v.y >> 16)));
 }
-SGI_DEV void storeHalf4(uint2* plane, size_t i, float r, float g, float b, float a) {
+SGI_DEV uint2 packHalf4(float r, float g, float b, float a) {
     uint2 v;
     v.x = (uint32_t)f2h(r) | ((uint32_t)f2h(g) << 16);
     v.y = (uint32_t)f2h(b) | ((uint32_t)f2h(a) << 16);
-    plane[i] = v;
+    return v;
 }
+SGI_DEV void storeHalf4(uint2* plane, size_t i, float r, float g, float b, float a) { plane[i] = packHalf4(r, g, b, a); }
 
 }  // namespace sgi

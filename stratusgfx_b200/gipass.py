@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import Buffers, CreateParams, FrameParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME, TILE_DIVISOR
+from ._abi import (BandParams, Buffers, CreateParams, FrameParams, PeerInfo, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+                   TILE_DIVISOR)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
 _lib = None
@@ -48,6 +49,11 @@ def load_library():
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
+    L.sgi_band_setup.argtypes = [H, C.POINTER(BandParams)]
+    L.sgi_band_export.argtypes = [H, C.POINTER(PeerInfo)]
+    L.sgi_band_attach.argtypes = [H, C.c_int32, C.POINTER(PeerInfo)]
+    L.sgi_frame_image.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.sgi_band_timeouts.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_visible_count.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_get_plane.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.sgi_download_plane.argtypes = [H, C.c_int32, C.c_void_p, C.c_int64]
@@ -66,6 +72,14 @@ def load_library():
 
 _PER_PIXEL = ("depth", "normal", "albedo", "baseReflectivity", "roughnessMetallicAmbient", "velocity", "id",
               "prevNormal", "prevId", "prevDepth", "ssao", "screen")
+
+
+class _DeviceView:
+    """A torch tensor over library-owned device memory (no copy, no ownership) via __cuda_array_interface__."""
+
+    def __init__(self, torch, ptr, shape, device):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f2", "data": (int(ptr), False), "version": 3, "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)
 
 
 class VplGiPass:
@@ -182,6 +196,31 @@ class VplGiPass:
     def frame(self, fp): self._check(self.L.sgi_frame(self._h, C.byref(fp)))
     def synchronize(self): self._check(self.L.sgi_synchronize(self._h))
     def reset_history(self): self._check(self.L.sgi_reset_history(self._h))
+
+    # ---- row bands with peer-to-peer halos (include/stratusgi.h "multi-GPU row bands") -------------------------
+    def band_setup(self, compute_y0, compute_rows, rank, world, owns_frame_image=False):
+        bp = BandParams(compute_y0, compute_rows, rank, world, 1 if owns_frame_image else 0)
+        self._check(self.L.sgi_band_setup(self._h, C.byref(bp)))
+        self.band = bp
+
+    def band_export(self):
+        info = PeerInfo()
+        self._check(self.L.sgi_band_export(self._h, C.byref(info)))
+        return info
+
+    def band_attach(self, which, info):
+        self._check(self.L.sgi_band_attach(self._h, which, C.byref(info)))
+
+    def band_timeouts(self):
+        n = C.c_int32()
+        self._check(self.L.sgi_band_timeouts(self._h, C.byref(n)))
+        return n.value
+
+    def frame_image(self):
+        """Owner band only: the assembled frame image of the last frame as a torch view (half [H, W, 4]) of library memory."""
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._check(self.L.sgi_frame_image(self._h, C.byref(ptr), C.byref(nbytes)))
+        return _DeviceView(self.torch, ptr.value, (self.full_height, self.width, 4), self.device).tensor
 
     def visible_count(self):
         n = C.c_int32()

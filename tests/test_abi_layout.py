@@ -31,6 +31,9 @@ def test_ctypes_layout_matches_header(tmp_path):
         "SgiBuffers": (_abi.Buffers, ["depth", "prevNormal", "ssao", "lightingOut", "vplData", "atlasEntryByVpl", "shadowCubeMaps",
                                       "diffuseCubeMaps", "infiniteLightShadowMap"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),
+        "SgiBandParams": (_abi.BandParams, ["compute_y0", "compute_rows", "rank", "world", "owns_frame_image"]),
+        "SgiPeerInfo": (_abi.PeerInfo, ["mem_handle", "local_base", "off_res", "off_gi", "off_hist", "off_flags", "off_image",
+                                        "y_offset", "rows", "compute_y0", "compute_rows", "rank", "device", "pid"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, (_, fields) in probes.items():

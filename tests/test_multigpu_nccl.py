@@ -14,6 +14,69 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames):
+    """One process per band; peer descriptors travel as bytes (all_gather_object), memory is attached with CUDA IPC."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    device = 0 if share_gpu else rank
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    if share_gpu:
+        dist.init_process_group("gloo", rank=rank, world_size=world)          # both ranks on one GPU: NCCL refuses that, gloo carries the bytes
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from stratusgfx_b200.bands import connect_bands, halo_rows, plan_bands
+    from stratusgfx_b200.gipass import VplGiPass
+    from stratusgfx_b200.scene import Scene
+    scene = Scene(workload, yaw_deg_per_frame=0.25)
+    W, H = scene.width, scene.height
+    bands = plan_bands(H, world, halo_rows(scene.denoise_iters))
+    me = bands[rank]
+    vd, at = scene.vpls()
+    sh, df = scene.cubemaps()
+    gp = VplGiPass(W, H, me.y0, me.rows, scene.cube_res, scene.csm_res, scene.denoise_iters, device=device)
+    gp.set_vpls(vd, at)
+    gp.set_atlases(sh, df)
+    connect_bands(dist, gp, me, world)
+    for f in range(frames):
+        gp.set_gbuffer(scene.gbuffer(f, me.y0, me.rows), scene.gbuffer(f - 1, me.y0, me.rows))
+        gp.set_csm(scene.csm(f))
+        gp.bind()
+        gp.frame(scene.frame_params(f))
+        gp.synchronize()
+        dist.barrier()                      # every band's final pass has completed: the assembled image is final
+        if rank == 0:
+            np.save(out_path % f, gp.frame_image().cpu().numpy())
+    assert gp.band_timeouts() == 0
+    dist.barrier()
+    gp.close()
+    dist.destroy_process_group()
+
+
+def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3):
+    import torch.multiprocessing as mp
+    from tests.parity_util import SceneData, run_cuda_staged
+    out_path = str(tmp_path / "p2p_frame%d.npy")
+    mp.spawn(_p2p_worker, args=(world, _free_port(), workload, out_path, share_gpu, frames), nprocs=world, join=True)
+    single = run_cuda_staged(SceneData(workload, frames=frames, yaw_deg_per_frame=0.25))
+    for f in range(frames):
+        assert np.array_equal(np.load(out_path % f).view(np.uint16), single[f]["combined"].view(np.uint16)), f
+
+
+def test_p2p_bands_over_cuda_ipc_two_processes_on_one_gpu(built, tmp_path):
+    """The cross-process path (CUDA IPC mapping of the neighbour's slab, epoch flags) exercised on a single GPU."""
+    _check_p2p(tmp_path, 2, share_gpu=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_p2p_bands_over_nvlink_equal_single_gpu_frames(built, tmp_path, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _check_p2p(tmp_path, world, share_gpu=False, workload="c2", frames=2)
+
+
 def _worker(rank, world, port, workload, out_path):
     import torch
     import torch.distributed as dist

@@ -127,6 +127,64 @@ def test_row_bands_with_apron_reproduce_the_whole_frame(built):
         gp.close()
 
 
+def _run_p2p_bands_in_one_process(d, world, frames):
+    """`world` band handles on one GPU in one process, linked through sgi_band_attach (same-process peer pointers)."""
+    from stratusgfx_b200.bands import halo_rows, plan_bands
+    from stratusgfx_b200._abi import PEER_DOWN, PEER_ROOT, PEER_UP
+    bands = plan_bands(d.H, world, halo_rows(d.scene.denoise_iters))
+    gps = [make_pass(d, b.y0, b.rows) for b in bands]
+    for gp, b in zip(gps, bands):
+        gp.band_setup(b.b0, b.b1 - b.b0, b.rank, world, owns_frame_image=(b.rank == 0))
+    infos = [gp.band_export() for gp in gps]
+    for gp, b in zip(gps, bands):
+        if b.rank > 0: gp.band_attach(PEER_UP, infos[b.rank - 1])
+        if b.rank + 1 < world: gp.band_attach(PEER_DOWN, infos[b.rank + 1])
+        if b.rank != 0: gp.band_attach(PEER_ROOT, infos[0])
+    images = []
+    for f in range(frames):
+        for gp, b in zip(gps, bands):
+            gp.set_gbuffer(band_of(d.gb[f], b.y0, b.rows), band_of(d.gb[f - 1], b.y0, b.rows)); gp.set_csm(d.csm[f]); gp.bind()
+        order = gps if f % 2 == 0 else gps[::-1]          # the enqueue order of the bands must not matter
+        for gp in order:
+            gp.frame(d.fp[f])
+        for gp in gps:
+            gp.synchronize()
+        images.append(gps[0].frame_image().cpu().numpy())
+    timeouts = [gp.band_timeouts() for gp in gps]
+    tiles = [gp.output("vplVisiblePerTile") for gp in gps]
+    for gp in gps:
+        gp.close()
+    return bands, images, timeouts, tiles
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_p2p_row_bands_reproduce_the_whole_frame(built, world):
+    """Peer-to-peer halo mode (csrc/sgi_band.cu): each band computes only its own rows; the neighbours' kernels store the
+    boundary rows of every denoise pass (and of the GI/history planes) into its halo, the final pass stores the lit rows
+    into band 0's frame image.  Three frames of a moving camera: the assembled image must equal the whole-frame bytes."""
+    d = SceneData("c1", frames=3, yaw_deg_per_frame=0.25)
+    whole = run_cuda_staged(d)
+    bands, images, timeouts, tiles = _run_p2p_bands_in_one_process(d, world, 3)
+    assert timeouts == [0] * world
+    for f in range(3):
+        assert np.array_equal(images[f].view(np.uint16), whole[f]["combined"].view(np.uint16)), f
+    tx = d.W // 5
+    for b, t in zip(bands, tiles):          # tile lists of the band's own tile rows
+        r0, r1 = (b.b0 - b.y0) // 5, (b.b1 - b.y0) // 5
+        assert np.array_equal(t[r0 * tx:r1 * tx], whole[2]["stage2"][b.b0 // 5 * tx:b.b1 // 5 * tx])
+
+
+def test_p2p_row_bands_five_iterations_need_a_wider_halo(built):
+    from stratusgfx_b200.bands import halo_rows
+    assert halo_rows(4) == 20 and halo_rows(5) == 35 and halo_rows(1) == 0
+    d = SceneData("c1", frames=1)
+    d.scene.denoise_iters = 5               # make_pass / run_cuda_staged read the iteration count from the scene
+    whole = run_cuda_staged(d)
+    bands, images, timeouts, _ = _run_p2p_bands_in_one_process(d, 2, 1)
+    assert timeouts == [0, 0]
+    assert np.array_equal(images[0].view(np.uint16), whole[0]["combined"].view(np.uint16))
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------
 def test_single_vpl_and_two_vpls(built):
     for n in (1, 2):
