@@ -148,7 +148,8 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from stratusgfx_b200.bands import APRON, broadcast_frame_inputs, connect_bands, gather_bands, halo_rows, plan_bands
+    from stratusgfx_b200.bands import (APRON, balance_cuts, bands_from_cuts, broadcast_frame_inputs, connect_bands, gather_bands, halo_rows,
+                                       plan_bands)
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
 
@@ -160,15 +161,43 @@ def run_ours(args, rank, world, local_rank):
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
     p2p = world > 1 and args.bands == "p2p"
     halo = halo_rows(iters)
-    bands = plan_bands(H, world, halo if p2p else APRON)
+    apron = halo if p2p else APRON
+    bands = plan_bands(H, world, apron)
+    vd, at = scene.vpls()
+    sh, df = scene.cubemaps()
+    csm = scene.csm(0)
+    balance_log = []
+    if world > 1 and args.balance > 0:
+        # measured load balancing, before the timed region: every rank times the row-dependent stages (tile lists, gather,
+        # denoise) on its own rows with a plain handle, the times are all-gathered and the cuts moved to equalise them
+        for it in range(args.balance):
+            b = bands[rank]
+            cal = VplGiPass(W, H, b.b0, b.b1 - b.b0, scene.cube_res, scene.csm_res, iters, device=local_rank)
+            cal.set_gbuffer(scene.gbuffer(0, b.b0, b.b1 - b.b0), scene.gbuffer(-1, b.b0, b.b1 - b.b0))
+            cal.set_vpls(vd, at); cal.set_atlases(sh, df); cal.set_csm(csm); cal.bind()
+            cfp = scene.frame_params(0)
+            cs = torch.cuda.ExternalStream(cal.stream_ptr(), device=dev)
+            evs = []
+            for k in range(6):
+                cal.cull(cfp); cal.color(cfp)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cs)
+                cal.tile_lists(cfp); cal.gather(cfp); cal.denoise(cfp)
+                e1.record(cs)
+                evs.append((e0, e1))
+            cal.synchronize()
+            t_mine = float(np.median([a.elapsed_time(bb) for a, bb in evs[2:]]))
+            cal.close()
+            times = [None] * world
+            dist.all_gather_object(times, t_mine)
+            cuts = balance_cuts(bands, times, H, apron)
+            balance_log.append({"rows": [b.b1 - b.b0 for b in bands], "ms": [round(t, 4) for t in times]})
+            bands = bands_from_cuts(cuts, H, apron)
     me = bands[rank]
     band, y0, rows = me.b1 - me.b0, me.y0, me.rows
 
     fp = scene.frame_params(0)
     gb, pgb = scene.gbuffer(0, y0, rows), scene.gbuffer(-1, y0, rows)
-    vd, at = scene.vpls()
-    sh, df = scene.cubemaps()
-    csm = scene.csm(0)
 
     side = torch.cuda.Stream(device=dev)     # everything (kernels, copies, NCCL, events) runs on this one stream
     torch.cuda.synchronize(dev)
@@ -315,7 +344,8 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "single GPU" if world == 1 else (
                                f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of VPL table + 5 cube maps, lit rows stored into rank 0's frame image by the final pass" if p2p else
                                f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
-                           "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts},
+                           "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
+                           "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log},
                 "clocks": clocks,
                 "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass"},
@@ -342,6 +372,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["tiny", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--balance", type=int, default=2, help="measured band-balancing rounds before the timed region (N > 1)")
     ap.add_argument("--bands", default="p2p", choices=["p2p", "apron"], help="multi-GPU halo strategy (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

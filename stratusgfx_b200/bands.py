@@ -67,6 +67,51 @@ def plan_bands(height, world, apron=APRON):
     return out
 
 
+def bands_from_cuts(cuts, height, apron):
+    """Bands owning rows [cuts[r], cuts[r+1]) plus `apron` held rows on each inner edge."""
+    world = len(cuts) - 1
+    if cuts[0] != 0 or cuts[-1] != height or any(c % TILE for c in cuts) or any(b <= a for a, b in zip(cuts, cuts[1:])):
+        raise ValueError(f"bad band cuts {cuts}")
+    if world > 1 and min(b - a for a, b in zip(cuts, cuts[1:])) < apron:
+        raise ValueError("a band is thinner than the halo")
+    out = []
+    for r in range(world):
+        b0, b1 = cuts[r], cuts[r + 1]
+        y0, y1 = (max(0, b0 - apron), min(height, b1 + apron)) if world > 1 else (0, height)
+        out.append(Band(r, b0, b1, y0, y1))
+    return out
+
+
+def balance_cuts(bands, times, height, min_rows):
+    """Load balancing from measurements: band r took times[r] for its rows, so its rows cost times[r]/rows each
+    (piecewise-constant density); move the cuts so every band gets the same share of the total, on the tile grid,
+    never thinner than `min_rows`.  A VPL gather is content dependent (1-6 samples per pixel, re-draws, shadow tests),
+    so equal-height bands are not equal work."""
+    world = len(bands)
+    if world == 1:
+        return [0, height]
+    min_rows = max(TILE, (min_rows + TILE - 1) // TILE * TILE)
+    dens = []
+    for b, t in zip(bands, times):
+        dens += [float(t) / (b.b1 - b.b0)] * (b.b1 - b.b0)
+    cum = [0.0]
+    for d in dens:
+        cum.append(cum[-1] + d)
+    total = cum[-1]
+    cuts = [0]
+    y = 0
+    for r in range(1, world):
+        target = total * r / world
+        while y < height and cum[y] < target:
+            y += 1
+        c = int(round(y / TILE)) * TILE
+        c = max(c, cuts[-1] + min_rows)                     # not thinner than the halo
+        c = min(c, height - (world - r) * min_rows)         # and leave room for the bands below
+        cuts.append(c)
+    cuts.append(height)
+    return cuts
+
+
 def connect_bands(dist, gp, band, world, root=0):
     """Peer-to-peer mode: band_setup on this rank's pass, all-gather the peer descriptors (plain bytes), attach the
     neighbours and the frame-image owner.  Works with NCCL (GPU box) and gloo (tests) alike: only host bytes travel."""

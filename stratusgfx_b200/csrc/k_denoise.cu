@@ -165,13 +165,16 @@ __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
-    if (x >= W) return;
     const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
     const int t = blockIdx.y * kDnY + threadIdx.y;           // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
     const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
     const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
-    if (c0 + m0 * s + r >= cEnd) return;
+    const bool live = x < W && c0 + m0 * s + r < cEnd;
+    // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
+    // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
+    bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
+    if (!live) return;
 
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
     float acc[kLat][4];

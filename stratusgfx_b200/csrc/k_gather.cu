@@ -131,8 +131,12 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
              const __grid_constant__ BandLinks links) {
     const int x = blockIdx.x * kGatherThreadsX + threadIdx.x;
     const int ly = blockIdx.y * kGatherThreadsY + threadIdx.y;
-    if (x >= bd.W || ly >= bd.rows) return;
     const int y = ly + bd.yOffset;
+    // row bands: the CTAs that will store pass-0 rows into a neighbour's halo first wait until that neighbour has finished
+    // the previous frame (its final pass read those halo rows)
+    bandWaitCta(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
+                links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
+    if (x >= bd.W || ly >= bd.rows) return;
     const size_t p = (size_t)ly * bd.W + x;
     const int cubeRes = bd.cubeRes;
     const int texelsPerLayer = 6 * cubeRes * cubeRes;

@@ -17,7 +17,7 @@ namespace sgi {
 
 namespace {
 
-constexpr int kCullThreads = 256;
+constexpr int kCullThreads = 1024;         // 32 warps = 32 VPLs = one ballot word per CTA
 
 // hardware PCF of a sampler2DArrayShadow (LINEAR, compare LEQUAL): SURVEY.md Appendix A4
 SGI_DEV float shadowArrayPcf(const float* __restrict__ csm, int res, float u, float v, int layer, float ref) {
@@ -38,8 +38,11 @@ SGI_DEV float shadowArrayPcf(const float* __restrict__ csm, int res, float u, fl
     return r;
 }
 
-// pbr.glsl:158-227 with useDepthBias = false and normal = infiniteLightDirection (viscull_vpls.cs:68)
-SGI_DEV float calculateInfiniteShadowValue(const FrameConsts& fc, const float* __restrict__ csm, int csmRes, f3 lightPos, f3 cascadeBlends) {
+// pbr.glsl:158-227 with useDepthBias = false and normal = infiniteLightDirection (viscull_vpls.cs:68), one WARP per VPL:
+// lane l < 18 evaluates ONE of the 18 PCF taps (lanes 0-8: the 3x3 taps of the first cascade, 9-17: of the second), so the
+// 72 dependent-latency texel fetches of a VPL are in flight together; the taps are then summed in the shader's order
+// (y outer, x inner, sequential adds) so the result is bit-identical to the serial loop.
+SGI_DEV float calculateInfiniteShadowValueWarp(const FrameConsts& fc, const float* __restrict__ csm, int csmRes, f3 lightPos, f3 cascadeBlends, int lane) {
     const f3 sun = mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]);
     const f3 normal = sun;
     const f3 off = (normal * fsub(1.0f, saturate(dot(normal, sun)))) * 1.0f;
@@ -48,38 +51,59 @@ SGI_DEV float calculateInfiniteShadowValue(const FrameConsts& fc, const float* _
     const bool beyondCascade3 = cascadeBlends.z >= 0.0f;
     const int index1 = beyondCascade2 ? 2 : 0;
     const int index2 = beyondCascade3 ? 3 : 1;
-    f3 cc[2];
-    #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int idx = k == 0 ? index1 : index2;
-        const m4 M = loadMat(fc.cascadeProjViews[idx]);
-        const f4 coords = mul(M, position);
-        cc[k] = (mk3(coords.x, coords.y, coords.z) / coords.w) * 0.5f + 0.5f;
-    }
-    const float depth1 = cc[0].z;
-    const float depth2 = beyondCascade3 ? saturate(cc[1].z) : cc[1].z;
+    const bool second = lane >= 9;
+    const int idx = second ? index2 : index1;
+    const m4 M = loadMat(fc.cascadeProjViews[idx]);
+    const f4 coords = mul(M, position);
+    const f3 cc = (mk3(coords.x, coords.y, coords.z) / coords.w) * 0.5f + 0.5f;
+    const float depth = (second && beyondCascade3) ? saturate(cc.z) : cc.z;
     const float weight = beyondCascade2 ? fsub(saturate(cascadeBlends.y), saturate(cascadeBlends.z)) : fsub(1.0f, saturate(cascadeBlends.x));
     const float wh = fdiv(1.0f, (float)csmRes);
+    const int t = second ? lane - 9 : lane;                 // tap index: (iy+1)*3 + (ix+1)
+    float tap = 0.0f;
+    if (lane < 18) {
+        const float ox = fmul((float)(t % 3 - 1), wh), oy = fmul((float)(t / 3 - 1), wh);
+        tap = shadowArrayPcf(csm, csmRes, fadd(cc.x, ox), fadd(cc.y, oy), idx, depth);
+    }
     float light1 = 0.0f, light2 = 0.0f;
     #pragma unroll
-    for (int iy = -1; iy <= 1; ++iy) {
-        #pragma unroll
-        for (int ix = -1; ix <= 1; ++ix) {
-            const float ox = fmul((float)ix, wh), oy = fmul((float)iy, wh);
-            light1 = fadd(light1, shadowArrayPcf(csm, csmRes, fadd(cc[0].x, ox), fadd(cc[0].y, oy), index1, depth1));
-            light2 = fadd(light2, shadowArrayPcf(csm, csmRes, fadd(cc[1].x, ox), fadd(cc[1].y, oy), index2, depth2));
-        }
+    for (int k = 0; k < 9; ++k) {
+        light1 = fadd(light1, __shfl_sync(0xffffffffu, tap, k));
+        light2 = fadd(light2, __shfl_sync(0xffffffffu, tap, 9 + k));
     }
     return fmul(mix(light2, light1, weight), fdiv(1.0f, 9.0f));
 }
 
+// vpl_light_color.cs:41-76 for one visible VPL
+SGI_DEV void colorOneVpl(const FrameConsts& fc, int cubeRes, int texel, SgiVplData* __restrict__ lightData, int index,
+                         const SgiAtlasEntry* __restrict__ diffuseIndices, const AtlasTable& atlases) {
+    const float colorMultiplier = 50000.0f;
+    const f3 sun = mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]);
+    const f3 sunColor = mk3(fc.sunColor[0], fc.sunColor[1], fc.sunColor[2]);
+    const float4 pos = reinterpret_cast<const float4*>(lightData + index)[0];
+    const float4 rfi = reinterpret_cast<const float4*>(lightData + index)[3];   // radius, farPlane, intensity, pad
+    const SgiAtlasEntry entry = diffuseIndices[index];
+    const size_t t = (size_t)entry.layer * 6 * cubeRes * cubeRes + texel;
+    const uchar4 d = __ldg(atlases.diffuse[entry.index] + t);
+    const f3 color = mk3(unorm8(d.x), unorm8(d.y), unorm8(d.z)) * sunColor;
+    const float depth = fdiv((float)__ldg(atlases.shadow[entry.index] + t), 65535.0f);
+    const float magnitude = fmul(rfi.x, depth);
+    const f3 specularPos = mk3(pos.x, pos.y, pos.z) - (fmul(1.1f, magnitude) * sun);
+    const f3 c = ((color / 1.0f) * rfi.z) * colorMultiplier;
+    reinterpret_cast<float4*>(lightData + index)[1] = make_float4(c.x, c.y, c.z, 1.0f);
+    reinterpret_cast<float4*>(lightData + index)[2] = make_float4(specularPos.x, specularPos.y, specularPos.z, 1.0f);
+}
+
+// `colorToo`: the last CTA also colours the compacted VPLs (what the separate colorKernel launch would do), for sgi_frame
 __global__ void __launch_bounds__(kCullThreads)
-cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, const SgiVplData* __restrict__ lightData,
+cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, int cubeRes, const SgiVplData* __restrict__ lightData,
            const SgiAtlasEntry* __restrict__ atlasByVpl, const float* __restrict__ csm, SgiVplData* __restrict__ updated,
            int32_t* __restrict__ visible, SgiAtlasEntry* __restrict__ entries, uint32_t* __restrict__ ballots,
-           unsigned int* __restrict__ ticket) {
+           unsigned int* __restrict__ ticket, const __grid_constant__ AtlasTable atlases, int colorToo) {
     const int N = fc.totalNumLights;
-    const int index = blockIdx.x * kCullThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int index = blockIdx.x * 32 + warp;                  // one warp per VPL
+    __shared__ int sVis[32];
     bool vis = false;
     if (index < N) {
         const float4 p = __ldg(reinterpret_cast<const float4*>(lightData + index));
@@ -89,11 +113,15 @@ cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, const SgiVplData*
         blends.x = dot(mk4(fc.cascadePlanes[0][0], fc.cascadePlanes[0][1], fc.cascadePlanes[0][2], fc.cascadePlanes[0][3]), lp4);
         blends.y = dot(mk4(fc.cascadePlanes[1][0], fc.cascadePlanes[1][1], fc.cascadePlanes[1][2], fc.cascadePlanes[1][3]), lp4);
         blends.z = dot(mk4(fc.cascadePlanes[2][0], fc.cascadePlanes[2][1], fc.cascadePlanes[2][2], fc.cascadePlanes[2][3]), lp4);
-        const float shadowFactor = fsub(1.0f, calculateInfiniteShadowValue(fc, csm, csmRes, lightPos, blends));
+        const float shadowFactor = fsub(1.0f, calculateInfiniteShadowValueWarp(fc, csm, csmRes, lightPos, blends, lane));
         vis = shadowFactor < 1.0f;
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, vis);
-    if ((threadIdx.x & 31) == 0) ballots[index >> 5] = bal;
+    if (lane == 0) sVis[warp] = vis ? 1 : 0;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, sVis[lane] != 0);
+        if (lane == 0) ballots[blockIdx.x] = bal;              // bit w of word b <-> VPL 32*b + w
+    }
 
     // ---- last CTA to arrive does the ordered compaction for the whole list ----
     __shared__ bool isLast;
@@ -110,18 +138,18 @@ cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, const SgiVplData*
     __shared__ int prefix[(SGI_MAX_TOTAL_VPLS_BEFORE_CULLING + 31) / 32 + 1];
     __shared__ int warpSums[kCullThreads / 32];
     const int numWords = (N + 31) >> 5;
-    // exclusive scan of popcounts over <= 313 words: 256 threads, at most 2 words per thread
+    // exclusive scan of popcounts over <= 313 words
     int carry = 0;
     for (int base = 0; base < numWords; base += kCullThreads) {
         const int w = base + threadIdx.x;
         const int c = w < numWords ? __popc(__ldcg(ballots + w)) : 0;
         int incl = c;
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
-        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warpSums[warp] = incl;
         __syncthreads();
         int warpBase = 0;
-        for (int k = 0; k < (threadIdx.x >> 5); ++k) warpBase += warpSums[k];
+        for (int k = 0; k < warp; ++k) warpBase += warpSums[k];
         if (w < numWords) prefix[w] = carry + warpBase + incl - c;
         int total = 0;
         for (int k = 0; k < kCullThreads / 32; ++k) total += warpSums[k];
@@ -140,34 +168,25 @@ cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, const SgiVplData*
         visible[k + 1] = i;
         if (atlasByVpl != nullptr) entries[k] = atlasByVpl[i];
     }
+    const int V = total > SGI_MAX_TOTAL_VPLS_PER_FRAME ? SGI_MAX_TOTAL_VPLS_PER_FRAME : total;
     if (threadIdx.x == 0) {
-        visible[0] = total > SGI_MAX_TOTAL_VPLS_PER_FRAME ? SGI_MAX_TOTAL_VPLS_PER_FRAME : total;
+        visible[0] = V;
         *ticket = 0u;   // re-arm for the next frame
+    }
+    if (colorToo) {
+        __syncthreads();                                         // the compacted table was written by this CTA
+        const int texel = cubeTexel(-mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]), cubeRes);
+        for (int k = threadIdx.x; k < V; k += kCullThreads) colorOneVpl(fc, cubeRes, texel, updated, k, entries, atlases);
     }
 }
 
 __global__ void __launch_bounds__(256)
 colorKernel(const __grid_constant__ FrameConsts fc, int cubeRes, SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
             const SgiAtlasEntry* __restrict__ diffuseIndices, const __grid_constant__ AtlasTable atlases) {
-    const float colorMultiplier = 50000.0f;
     const int visibleVpls = __ldg(numVisible);
-    const f3 sun = mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]);
-    const f3 sunColor = mk3(fc.sunColor[0], fc.sunColor[1], fc.sunColor[2]);
-    const int texel = cubeTexel(-sun, cubeRes);
-    for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < visibleVpls; index += gridDim.x * blockDim.x) {
-        const float4 pos = reinterpret_cast<const float4*>(lightData + index)[0];
-        const float4 rfi = reinterpret_cast<const float4*>(lightData + index)[3];   // radius, farPlane, intensity, pad
-        const SgiAtlasEntry entry = diffuseIndices[index];
-        const size_t t = (size_t)entry.layer * 6 * cubeRes * cubeRes + texel;
-        const uchar4 d = __ldg(atlases.diffuse[entry.index] + t);
-        const f3 color = mk3(unorm8(d.x), unorm8(d.y), unorm8(d.z)) * sunColor;
-        const float depth = fdiv((float)__ldg(atlases.shadow[entry.index] + t), 65535.0f);
-        const float magnitude = fmul(rfi.x, depth);
-        const f3 specularPos = mk3(pos.x, pos.y, pos.z) - (fmul(1.1f, magnitude) * sun);
-        const f3 c = ((color / 1.0f) * rfi.z) * colorMultiplier;
-        reinterpret_cast<float4*>(lightData + index)[1] = make_float4(c.x, c.y, c.z, 1.0f);
-        reinterpret_cast<float4*>(lightData + index)[2] = make_float4(specularPos.x, specularPos.y, specularPos.z, 1.0f);
-    }
+    const int texel = cubeTexel(-mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]), cubeRes);
+    for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < visibleVpls; index += gridDim.x * blockDim.x)
+        colorOneVpl(fc, cubeRes, texel, lightData, index, diffuseIndices, atlases);
 }
 
 }  // namespace
@@ -199,10 +218,14 @@ void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc) {
 }
 
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
-               const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket) {
+               const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket,
+               const AtlasTable* colorAtlases) {
     const int N = fc.totalNumLights;
-    const int blocks = N > 0 ? (N + kCullThreads - 1) / kCullThreads : 1;
-    cullKernel<<<blocks, kCullThreads, 0, stream>>>(fc, bd.csmRes, lightData, atlasByVpl, csm, updated, visible, entries, ballots, ticket);
+    const int blocks = N > 0 ? (N + 31) / 32 : 1;
+    AtlasTable none;
+    for (int i = 0; i < SGI_MAX_TOTAL_SHADOW_ATLASES; ++i) { none.shadow[i] = nullptr; none.diffuse[i] = nullptr; }
+    cullKernel<<<blocks, kCullThreads, 0, stream>>>(fc, bd.csmRes, bd.cubeRes, lightData, atlasByVpl, csm, updated, visible, entries, ballots, ticket,
+                                                    colorAtlases ? *colorAtlases : none, colorAtlases ? 1 : 0);
     return 1;
 }
 

@@ -30,8 +30,10 @@ static int fail(SgiHandle h, int code, const char* msg) { h->lastError = msg; re
 
 static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h->cp.rows; }
 
+static BandDims bandDims(const SgiHandle h);
+
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab, (void**)&h->patchScratch};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
     h->resA = h->resB = nullptr;
     h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
@@ -64,6 +66,7 @@ static int allocPlanes(SgiHandle h) {
     void** half4s[] = {&h->giColor, &h->giReservoir, &h->combined};
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
     SGI_CUDA(h, cudaMalloc(&h->guide, n * 16));
+    SGI_CUDA(h, cudaMalloc((void**)&h->patchScratch, (size_t)patchScratchInts(bandDims(h)) * sizeof(int)));
     h->guideValid = false;
     // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the previous-frame FBO is
     // never cleared and starts at zero.  Reservoir halo rows start at zero too.
@@ -186,17 +189,22 @@ static int postLaunch(SgiHandle h, int n) {
     return SGI_OK;
 }
 
-int sgi_cull(SgiHandle h, const SgiFrameParams* fp) {
+static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
     if (fp->totalNumLights < 0 || fp->totalNumLights > SGI_MAX_TOTAL_VPLS_BEFORE_CULLING) return fail(h, SGI_ERR_INVALID_ARG, "sgi_cull: totalNumLights out of range");
     NEED(h, vplData); NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, infiniteLightShadowMap);
     if (h->buf.atlasEntryByVpl && !h->buf.shadowDiffuseIndices) return fail(h, SGI_ERR_NOT_BOUND, "buffer not bound: shadowDiffuseIndices");
+    if (colorToo) { NEED(h, shadowDiffuseIndices); NEED(h, atlasEntryByVpl); NEED(h, shadowCubeMaps[0]); NEED(h, diffuseCubeMaps[0]); }
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const AtlasTable atl = atlasTable(h);
     const int n = launchCull(h->stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
-                             h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket);
+                             h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket,
+                             colorToo ? &atl : nullptr);
     return postLaunch(h, n);
 }
+
+int sgi_cull(SgiHandle h, const SgiFrameParams* fp) { return cullImpl(h, fp, false); }
 
 int sgi_color(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
@@ -209,14 +217,15 @@ int sgi_color(SgiHandle h, const SgiFrameParams* fp) {
 
 int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
-    NEED(h, depth); NEED(h, normal); NEED(h, vplData); NEED(h, vplVisibleIndices); NEED(h, vplStage1Results); NEED(h, vplVisiblePerTile);
+    NEED(h, depth); NEED(h, normal); NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, vplStage1Results); NEED(h, vplVisiblePerTile);
     if (h->cp.width % SGI_TILE_DIVISOR || h->cp.rows % SGI_TILE_DIVISOR || h->cp.y_offset % SGI_TILE_DIVISOR)
         return fail(h, SGI_ERR_INVALID_ARG, "sgi_tile_lists: width, rows and y_offset must be multiples of 5");
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     const BandDims bd = bandDims(h);
-    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results);
-    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile);
+    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch);
+    // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
+    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->patchScratch);
     return postLaunch(h, n);
 }
 
@@ -234,8 +243,9 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
         // a new band frame starts here.  Neighbours must be done with the previous frame (their final pass read the halo rows
         // this gather is about to overwrite) before the boundary rows of pass 0 are pushed into their memory.
         ++h->frameNo;
-        if (h->frameNo > 1) n += sgi::waitNeighbours(h, sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters));
-        if (fuse) links = sgi::bandLinks(h, 0, false);
+        const int prevDone = h->frameNo > 1 ? sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters) : 0;
+        if (fuse) links = sgi::bandLinks(h, 0, false, prevDone);         // the CTAs that push wait inside the kernel
+        else if (prevDone) n += sgi::waitNeighbours(h, prevDone);
     }
     n += launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
@@ -291,8 +301,8 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
     }
     if (h->banded) {
         // pass p reads the neighbours' pass p-1 rows from this handle's halo: wait (in stream order) for their flags
-        if (pass >= 1) n += sgi::waitNeighbours(h, sgi::bandEpoch(h->frameNo, pass));
-        io.links = sgi::bandLinks(h, pass % 2, final_);
+        // (inside the kernel, by the CTAs whose taps reach the halo; interior CTAs start at once)
+        io.links = sgi::bandLinks(h, pass % 2, final_, pass >= 1 ? sgi::bandEpoch(h->frameNo, pass) : 0);
     }
     n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
     if (h->banded) {
@@ -316,8 +326,14 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
     int rc;
     if (fp->totalNumLights == 0) return SGI_OK;      // `if (perVPLDistToViewer.size() == 0) return;` (BE:1582, 1675, 1817)
-    if ((rc = sgi_cull(h, fp)) != SGI_OK) return rc;
-    if ((rc = sgi_color(h, fp)) != SGI_OK) return rc;
+    // cull + colour in one launch when the atlas assignment is available on the device (the cull's last CTA colours
+    // the compacted table); otherwise the two reference dispatches separately
+    if (h->bound && h->buf.atlasEntryByVpl && h->buf.shadowDiffuseIndices && h->buf.diffuseCubeMaps[0] && h->buf.shadowCubeMaps[0]) {
+        if ((rc = cullImpl(h, fp, true)) != SGI_OK) return rc;
+    } else {
+        if ((rc = sgi_cull(h, fp)) != SGI_OK) return rc;
+        if ((rc = sgi_color(h, fp)) != SGI_OK) return rc;
+    }
     if (h->buf.vplStage1Results && h->buf.vplVisiblePerTile) { if ((rc = sgi_tile_lists(h, fp)) != SGI_OK) return rc; }
     if ((rc = sgi_gather(h, fp)) != SGI_OK) return rc;
     return sgi_denoise(h, fp);

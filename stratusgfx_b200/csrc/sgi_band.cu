@@ -24,25 +24,6 @@
 namespace sgi {
 namespace {
 
-__device__ __forceinline__ int ldAcquireSys(const int32_t* p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stReleaseSys(int32_t* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-constexpr long long kSpinLimitCycles = 4000000000LL;      // ~2 s at 1.9 GHz
-
-__device__ bool spinUntil(const int32_t* flag, int epoch, long long t0) {
-    while ((int)(ldAcquireSys(flag) - epoch) < 0) {           // wrap-safe "flag >= epoch"
-        __nanosleep(100);
-        if (clock64() - t0 > kSpinLimitCycles) return false;
-    }
-    return true;
-}
-
 __global__ void waitFlagsKernel(const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts) {
     const long long t0 = clock64();
     bool ok = true;
@@ -105,7 +86,7 @@ static int32_t* peerFlags(SgiHandle_* h, int which) {
 
 // Where the pass that writes reservoir `resIndex` also stores its boundary rows.  `cur` parity is the same on every band
 // (all bands run the same number of final passes), so the neighbour's GI/history of this frame is its plane [cur].
-BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_) {
+BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
     BandLinks L = noLinks();
     const int myC0 = h->band.compute_y0, myC1 = h->band.compute_y0 + h->band.compute_rows;
     for (int which = 0; which < 2; ++which) {
@@ -122,6 +103,12 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_) {
         t.firstRow = lo > myC0 ? lo : myC0;
         t.lastRow = hi < myC1 ? hi : myC1;
         if (t.firstRow >= t.lastRow) { t.res = nullptr; t.gi = nullptr; t.hist = nullptr; }
+    }
+    if (waitEpoch != 0) {          // my flags[0] is written by the band above, flags[1] by the band below
+        L.waitUp = h->peer[SGI_PEER_UP].attached ? h->flags + 0 : nullptr;
+        L.waitDown = h->peer[SGI_PEER_DOWN].attached ? h->flags + 1 : nullptr;
+        L.waitEpoch = waitEpoch;
+        L.timeouts = h->flags + 2;
     }
     if (final_) {
         const int parity = (int)(h->frameNo & 1);

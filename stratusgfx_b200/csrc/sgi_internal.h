@@ -30,6 +30,12 @@ struct PushTarget {
 struct BandLinks {
     PushTarget up, down;
     uint2* image;              // root's frame image (half4 [fullH][W]) or nullptr
+    // in-kernel wait: CTAs that touch a halo (read it, or overwrite the neighbour's) spin until the neighbour's epoch
+    // flag in THIS handle's slab reaches waitEpoch; all other CTAs of the launch start immediately
+    const int32_t* waitUp;     // this handle's flags[0] (written by the band above) or nullptr
+    const int32_t* waitDown;   // this handle's flags[1] (written by the band below) or nullptr
+    int waitEpoch;
+    int32_t* timeouts;
 };
 
 // uniforms in device-friendly form; passed by value as a __grid_constant__ kernel parameter
@@ -56,6 +62,39 @@ struct AtlasTable {
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ int ldAcquireSys(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stReleaseSys(int32_t* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr long long kSpinLimitCycles = 4000000000LL;      // ~2 s at 1.9 GHz: a dead neighbour must not hang the GPU
+__device__ __forceinline__ bool spinUntil(const int32_t* flag, int epoch, long long t0) {
+    while ((int)(ldAcquireSys(flag) - epoch) < 0) {           // wrap-safe "flag >= epoch"
+        __nanosleep(100);
+        if (clock64() - t0 > kSpinLimitCycles) return false;
+    }
+    return true;
+}
+// Called by EVERY thread of a CTA.  If some thread needs a halo, thread 0 spins on the neighbour's flag and the CTA
+// proceeds after a barrier (acquire + bar.sync orders the CTA's later loads/stores after the neighbour's release).
+__device__ __forceinline__ void bandWaitCta(const BandLinks& L, bool needUp, bool needDown) {
+    if (L.waitUp == nullptr && L.waitDown == nullptr) return;          // uniform across the launch
+    const int up = __syncthreads_or(needUp && L.waitUp != nullptr);
+    const int down = __syncthreads_or(needDown && L.waitDown != nullptr);
+    if (up | down) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const long long t0 = clock64();
+            bool ok = true;
+            if (up) ok = spinUntil(L.waitUp, L.waitEpoch, t0) && ok;
+            if (down) ok = spinUntil(L.waitDown, L.waitEpoch, t0) && ok;
+            if (!ok) atomicAdd(L.timeouts, 1);
+        }
+        __syncthreads();
+    }
+}
 // store a band's boundary pixel into the neighbours' halo rows (plain st.global on peer-mapped pointers: NVLink writes)
 __device__ __forceinline__ void pushRes(const BandLinks& L, int y, int x, int W, uint2 v) {
     if (L.up.res != nullptr && y >= L.up.firstRow && y < L.up.lastRow) L.up.res[(size_t)(y - L.up.yOffset) * W + x] = v;
@@ -113,6 +152,7 @@ struct SgiHandle_ {
     void* giIllum[2] = {nullptr, nullptr};    // half4, [cur] / [cur^1] = previous frame
     void* history[2] = {nullptr, nullptr};    // half
     int cur = 0;
+    int* patchScratch = nullptr;    // stage-1 -> stage-2 patch size classes (k_tiles.cu)
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
     bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
     bool pass0Fused = false;        // the gather of this frame already wrote denoise pass 0 into resA, for `pass0Time`
@@ -140,12 +180,13 @@ bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels()
 
 // each launcher enqueues its kernels on `stream` and returns the number of launches made
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
-               const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket);
+               const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket,
+               const AtlasTable* colorAtlases /* non-null: the cull's last CTA also runs the colouring stage */);
 int launchColor(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, SgiVplData* updated, const int32_t* visible,
                 const SgiAtlasEntry* entries, const AtlasTable& atlases);
 // ---- row bands (sgi_band.cu) ----
 BandLinks noLinks();
-BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_);      // peer destinations of the pass writing reservoir resIndex
+BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch);   // peer destinations of the pass writing reservoir resIndex; waitEpoch 0 = no wait
 inline int bandEpoch(int64_t frameNo, int stage) { return (int)(uint32_t)(frameNo * 32 + stage); }   // stage k: output of pass k-1 pushed
 int waitNeighbours(SgiHandle_* h, int epoch);
 int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
@@ -155,10 +196,11 @@ constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
 int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int epoch, int32_t* timeouts);
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);
+int patchScratchInts(const BandDims& bd);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
-                 SgiVplStage1PerTileOutputs* out);
-int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightData,
-                 const int32_t* visible, SgiVplStage2PerTileOutputs* out);
+                 SgiVplStage1PerTileOutputs* out, int* patchScratch);
+int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightTable,
+                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, const int* patchScratch);
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,

@@ -15,6 +15,9 @@ for g in 2 4 8; do
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus $g --steps 20 --warmup 5 > $out/bench_$g.json 2> $out/bench_$g.err
     echo "bench $g exit $?"; tail -2 $out/bench_$g.err
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus $g --steps 20 --warmup 5 --bands apron > $out/bench_apron_$g.json 2> $out/bench_apron_$g.err
+    echo "bench apron $g exit $?"
   fi
 done
 python - <<PY
