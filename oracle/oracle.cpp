@@ -452,10 +452,11 @@ int orc_stage2(const OrcDims* dm, const SgiVplStage1PerTileOutputs* stage1Data, 
 // a5: vpl_pbr_gi.fs:81-207.  Outputs: color (attachment 0, RGB16F) and reservoir (attachment 1, RGBA16F),
 // both as half4 planes.  `sampleStats`, if given, receives [0] = executed loop iterations (S·P),
 // [1] = shaded samples, [2] = cube-shadow fetches.
-int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth, const uint8_t* gNormal4, const uint8_t* gAlbedo4,
+static int gatherImpl(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth, const uint8_t* gNormal4, const uint8_t* gAlbedo4,
                const uint8_t* gBaseReflectivity2, const uint8_t* gRoughnessMetallicAmbient4, const uint16_t* ssaoH,
                const SgiVplData* lightData, const int32_t* numVisible, const SgiAtlasEntry* shadowIndices,
-               const void* const* shadowCubeMaps, uint16_t* colorOutH4, uint16_t* reservoirOutH4, int64_t* sampleStats) {
+               const void* const* shadowCubeMaps, uint16_t* colorOutH4, uint16_t* reservoirOutH4, int64_t* sampleStats,
+               const SgiVplStage2PerTileOutputs* tileLists, const int32_t* visibleList) {
     const int W = dm->width, H = dm->height, cubeRes = dm->cube_res;
     const int fullH = orcFullH(dm), yOff = dm->y_offset;
     const mat4 invPV = loadMat(fp->invProjectionView);
@@ -493,6 +494,46 @@ int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
         samplesMax = max(1, (int)((float)samplesMax * distRatioToCamera));
         const int sampleCount = samplesMax;
         const int maxRandomIndex = V - 1;
+        if (tileLists != nullptr) {
+            // SGI_GATHER_TILE_LIST (include/stratusgi.h): the dormant tile lookup of vpl_pbr_gi.fs:86-97 composed with the live
+            // per-light body (:153-198).  Every VPL of the pixel's tile list in list order; a VPL behind the pixel or out of
+            // range is skipped.  The list holds indices into the ORIGINAL table (stage2.cs:81-82); the coloured, compacted
+            // table is indexed by position in the visible list, so the index is mapped back through that list.
+            const int tilesX = W / SGI_TILE_DIVISOR;
+            const SgiVplStage2PerTileOutputs& tl = tileLists[(size_t)(y / SGI_TILE_DIVISOR) * tilesX + x / SGI_TILE_DIVISOR];
+            const int count = tl.numVisible < SGI_MAX_VPLS_PER_TILE ? tl.numVisible : SGI_MAX_VPLS_PER_TILE;
+            for (int l = 0; l < count; ++l) {
+                int lightIndex = -1;
+                for (int k = 0; k < V; ++k) if (visibleList[1 + k] == tl.indices[l]) { lightIndex = k; break; }
+                if (lightIndex < 0) continue;
+                ++itersTotal;
+                const SgiAtlasEntry entry = shadowIndices[lightIndex];
+                const vec3 lightPosition(lightData[lightIndex].position[0], lightData[lightIndex].position[1], lightData[lightIndex].position[2]);
+                const vec3 specularLightPosition(lightData[lightIndex].specularPosition[0], lightData[lightIndex].specularPosition[1], lightData[lightIndex].specularPosition[2]);
+                const vec3 lightMinusFrag = lightPosition - fragPos;
+                const float lightRadius = lightData[lightIndex].radius;
+                const float distance = length(lightMinusFrag);
+                const float sideCheck = dot(normal, normalize(lightMinusFrag));
+                if (sideCheck < 0.0f || distance > lightRadius) continue;
+                const float distanceRatio = clamp((2.0f * distance) / lightRadius, 0.0f, 1.0f);
+                const float distAttenuation = distanceRatio;
+                const vec3 lightColor(lightData[lightIndex].color[0], lightData[lightIndex].color[1], lightData[lightIndex].color[2]);
+                float shadowFactor = 0.0f;
+                if (distToCamera < 500.0f) {
+                    ++fetchTotal;
+                    shadowFactor = calculateShadowValue1Sample(shadowCubeMaps, entry, cubeRes, lightData[lightIndex].farPlane, fragPos, lightPosition,
+                                                               dot(lightPosition - fragPos, normal), 0.1f);
+                }
+                shadowFactor = min(shadowFactor, mix(minGiOcclusionFactor, 1.0f, distanceRatio));
+                float reweightingFactor = 1.0f;
+                if (shadowFactor > 0.0f) reweightingFactor = (1.0f - distAttenuation) * minGiOcclusionFactor + distAttenuation;
+                validSamples += reweightingFactor;
+                ++shadedTotal;
+                const vec3 tmpColor = ambientOcclusion * calculateVirtualPointLighting2(*fp, fragPos, baseColor, normal, viewDir, specularLightPosition,
+                    lightPosition, lightColor, distToCamera, lightRadius, roughness, metallic, ambient, 0.0f, baseReflectivity);
+                vplColor = vplColor + (1.0f - shadowFactor) * tmpColor;
+            }
+        } else
         // V <= 0: the reference would read stale lights (undefined); defined here as "no light".
         for (int i = 0, resamples = 0, count = 0; V > 0 && i < sampleCount; i += 1, count += 1) {
             ++itersTotal;
@@ -535,6 +576,24 @@ int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth,
     }
     if (sampleStats) { sampleStats[0] = itersTotal; sampleStats[1] = shadedTotal; sampleStats[2] = fetchTotal; }
     return 0;
+}
+
+int orc_gather(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth, const uint8_t* gNormal4, const uint8_t* gAlbedo4,
+               const uint8_t* gBaseReflectivity2, const uint8_t* gRoughnessMetallicAmbient4, const uint16_t* ssaoH,
+               const SgiVplData* lightData, const int32_t* numVisible, const SgiAtlasEntry* shadowIndices,
+               const void* const* shadowCubeMaps, uint16_t* colorOutH4, uint16_t* reservoirOutH4, int64_t* sampleStats) {
+    return gatherImpl(fp, dm, gDepth, gNormal4, gAlbedo4, gBaseReflectivity2, gRoughnessMetallicAmbient4, ssaoH, lightData, numVisible, shadowIndices,
+                      shadowCubeMaps, colorOutH4, reservoirOutH4, sampleStats, nullptr, nullptr);
+}
+
+// tile-list mode of the gather: `numVisible` is the whole visible list ([0] = count), `tileLists` the stage-2 output
+int orc_gather_tiles(const SgiFrameParams* fp, const OrcDims* dm, const float* gDepth, const uint8_t* gNormal4, const uint8_t* gAlbedo4,
+                     const uint8_t* gBaseReflectivity2, const uint8_t* gRoughnessMetallicAmbient4, const uint16_t* ssaoH,
+                     const SgiVplData* lightData, const int32_t* numVisible, const SgiAtlasEntry* shadowIndices,
+                     const void* const* shadowCubeMaps, uint16_t* colorOutH4, uint16_t* reservoirOutH4, int64_t* sampleStats,
+                     const SgiVplStage2PerTileOutputs* tileLists) {
+    return gatherImpl(fp, dm, gDepth, gNormal4, gAlbedo4, gBaseReflectivity2, gRoughnessMetallicAmbient4, ssaoH, lightData, numVisible, shadowIndices,
+                      shadowCubeMaps, colorOutH4, reservoirOutH4, sampleStats, tileLists, numVisible);
 }
 
 // a6: one pass of vpl_pbr_gi_denoise.fs:275-435.

@@ -78,6 +78,7 @@ def lib(variant="own"):
         L.orc_random3.argtypes = [C.c_float] * 3
         for name, n in (("orc_cull", 8), ("orc_color", 7), ("orc_stage1", 5), ("orc_gather", 15)):
             getattr(L, name).argtypes = [C.c_void_p] * n
+        L.orc_gather_tiles.argtypes = [C.c_void_p] * 16
         L.orc_stage2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_denoise_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[variant] = L
@@ -138,11 +139,16 @@ class OracleFrame:
         self.L.orc_stage2(C.addressof(self.dims), _p(self.stage1), _p(vpl_data), v, _p(idx), _p(self.stage2))
 
     # ---- a5 ----
-    def gather(self, fp, gb):
+    def gather(self, fp, gb, tile_mode=False):
         H, W = self.H, self.W
         self.gi_color = np.zeros((H, W, 4), np.float16)
         self.gi_reservoir = np.zeros((H, W, 4), np.float16)
         self.sample_stats = np.zeros(3, np.int64)
+        if tile_mode:          # SGI_GATHER_TILE_LIST: needs tile_lists() first
+            self.L.orc_gather_tiles(C.addressof(fp), C.addressof(self.dims), _p(gb.depth), _p(gb.normal), _p(gb.albedo), _p(gb.baseReflectivity),
+                                    _p(gb.roughnessMetallicAmbient), _p(gb.ssao), _p(self.updated), _p(self.visible), _p(self.entries),
+                                    C.addressof(self._sh_ptrs), _p(self.gi_color), _p(self.gi_reservoir), _p(self.sample_stats), _p(self.stage2))
+            return
         self.L.orc_gather(C.addressof(fp), C.addressof(self.dims), _p(gb.depth), _p(gb.normal), _p(gb.albedo), _p(gb.baseReflectivity),
                           _p(gb.roughnessMetallicAmbient), _p(gb.ssao), _p(self.updated), _p(self.visible), _p(self.entries),
                           C.addressof(self._sh_ptrs), _p(self.gi_color), _p(self.gi_reservoir), _p(self.sample_stats))
@@ -184,5 +190,5 @@ class OracleFrame:
         self.color(fp, shadow_atlas, diffuse_atlas)
         if tile_lists:
             self.tile_lists(fp, gb, vpl_data)
-        self.gather(fp, gb)
+        self.gather(fp, gb, tile_mode=(fp.gatherMode == 1))
         self.denoise(fp, gb, prev_gb, keep_passes=keep_passes)

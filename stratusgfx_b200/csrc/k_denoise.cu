@@ -89,11 +89,14 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
     k.j0 = iclamp(k.j0 - bd.yOffset, 0, rows - 1); k.j1 = iclamp(k.j1 - bd.yOffset, 0, rows - 1);
     const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
     float prevCenterDepth; f3 pn, prevGi;
-    if (k.a == 0.0f && k.b == 0.0f) {
+    uint32_t prevNormalBits = 0;
+    const bool onTexel = k.a == 0.0f && k.b == 0.0f;
+    if (onTexel) {
         // the reprojected tap sits on a texel centre (always, on a static camera): the bilinear blend
         // (1*1)*t00 + 0*t10 + 0*t01 + 0*t11 is t00 exactly, so three of the four fetches are skipped
         prevCenterDepth = __ldg(io.prevDepth + q00);
         const uint32_t n00 = __ldg(io.prevNormal + q00);
+        prevNormalBits = n00;
         pn = mk3(unorm8(n00 & 0xffu), unorm8((n00 >> 8) & 0xffu), unorm8((n00 >> 16) & 0xffu));
         const f4 g00 = loadHalf4(io.prevGi, q00);
         prevGi = mk3(g00.x, g00.y, g00.z);
@@ -106,20 +109,25 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
         const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
         prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
     }
-    const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
     const float currId = __ldg(io.ids + p);
     const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
     const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);
     const float prevId = __ldg(io.prevIds + (size_t)nj * W + ni);
 
-    // the history-reset decision: exact IEEE arithmetic (expf(-0) == 1 exactly on a static camera)
-    const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
-    const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
-    const float wid = currId != prevId ? 0.0f : 1.0f;
-    const float similarity = fmul(fmul(wn, wz), wid);
-    if (similarity < 0.99f) accumMultiplier = 0.0f;
+    // the history-reset decision `similarity < 0.99` (:410-418), exact.  Shortcut: when the reprojected tap is the same texel with
+    // the same normal bits, depth and id as the current pixel (every pixel of a static camera), prevCenterNormal is bit-identical
+    // to centerNormal, so wn = fl(n.n) = 1 +- 3e-7, wz = exp(-0) = 1, wid = 1 and the test cannot fire.
+    const bool sameTexel = onTexel && prevNormalBits == __ldg(io.normal + p) && prevCenterDepth == centerDepth && currId == prevId;
+    if (!sameTexel) {
+        const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
+        const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
+        const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
+        const float wid = currId != prevId ? 0.0f : 1.0f;
+        const float similarity = fmul(fmul(wn, wz), wid);
+        if (similarity < 0.99f) accumMultiplier = 0.0f;
+    }
     historyAccum = vmin(fadd(1.0f, fmul(historyAccum, accumMultiplier)), fc.framesPerSecond);
-    const float maxAccumulationFactor = fdiv(1.0f, historyAccum);
+    const float maxAccumulationFactor = __fdividef(1.0f, historyAccum);      // radiance tier (the stored history itself is exact)
     const f3 illumAvg = mix(prevGi, currGi, maxAccumulationFactor);
     const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
     const uint2 cv = packHalf4(combined.x, combined.y, combined.z, 1.0f), gv = packHalf4(illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
@@ -157,6 +165,7 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 constexpr int kLat = 4;                       // outputs per thread, consecutive on the tap lattice of its column
 constexpr float kLog2e = 1.4426950408889634f;
 
+SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -176,6 +185,17 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
     if (!live) return;
 
+    if (FINAL) {
+        // the temporal epilogue reads ten more planes per output, first touched in this kernel: ask L2 for them now so the
+        // DRAM latency overlaps the filter loop (the reprojected previous-frame taps sit at or near the same pixel)
+        #pragma unroll
+        for (int k = 0; k < kLat; ++k) {
+            const size_t p = (size_t)min(c0 + (m0 + k) * s + r, cEnd - 1) * W + x;
+            prefetchL2(io.screen + p); prefetchL2(io.illum + p); prefetchL2(io.velocity + p); prefetchL2(io.historyIn + p);
+            prefetchL2(io.ids + p); prefetchL2(io.depth + p); prefetchL2(io.prevDepth + p); prefetchL2(io.prevNormal + p);
+            prefetchL2(io.prevGi + p); prefetchL2(io.prevIds + p);
+        }
+    }
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
     float acc[kLat][4];
     #pragma unroll
@@ -221,8 +241,8 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
         if (ly >= cEnd) break;
-        const float denom = vmax(PREVENT_DIV_BY_ZERO, acc[k][3]);
-        const f3 shadowFactor = mk3(acc[k][0], acc[k][1], acc[k][2]) / denom;
+        const float invDenom = __fdividef(1.0f, vmax(PREVENT_DIV_BY_ZERO, acc[k][3]));      // radiance tier (see header)
+        const f3 shadowFactor = mk3(acc[k][0] * invDenom, acc[k][1] * invDenom, acc[k][2] * invDenom);
         const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
         io.reservoirOut[(size_t)ly * W + x] = rv;
         pushRes(io.links, ly + bd.yOffset, x, W, rv);

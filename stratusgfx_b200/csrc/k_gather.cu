@@ -122,15 +122,92 @@ SGI_DEV f3 shadeFast(const PixelConsts& px, f3 specularLightPos, f3 diffuseLight
     return mk3(brdf.x * lightColor.x * px.fogAo, brdf.y * lightColor.y * px.fogAo, brdf.z * lightColor.z * px.fogAo);
 }
 
-__global__ void __launch_bounds__(kGatherThreadsX * kGatherThreadsY, 4)
+
+// decision: `if (dot(normal, normalize(l)) < 0 || length(l) > radius)` (vpl_pbr_gi.fs:164-166), exact by the two-tier rule
+SGI_DEV bool behindOrOutOfRange(f3 normal, f3 lightMinusFrag, float d2, float lightRadius) {
+    const float s = dotFast(normal, lightMinusFrag);      // same sign as the normalised dot product
+    const float r2 = lightRadius * lightRadius;
+    const bool sideSure = s * s > (kMargin * kMargin) * d2;
+    const bool farSure = d2 > r2 * (1.0f + 4.0f * kMargin), nearSure = d2 < r2 * (1.0f - 4.0f * kMargin);
+    if (sideSure && (farSure || nearSure)) return (s < 0.0f) || farSure;
+    return exactRedraw(normal, lightMinusFrag, lightRadius);
+}
+
+// one accepted light: shadow test, occlusion floor, re-weighting and shading (vpl_pbr_gi.fs:173-198)
+SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 lightMinusFrag, float d2, float lightRadius, float farPlane,
+                                f3 lightColor, f3 specularPosition, SgiAtlasEntry entry, bool shadowsOn, float minGi, int cubeRes,
+                                int texelsPerLayer, const AtlasTable& atlases, f3& vplColor, float& validSamples) {
+    const float invRadius = rcpFast(lightRadius);
+    const float distance = d2 * rsqrtf(d2);
+    const float distanceRatio = satFast(2.0f * distance * invRadius);
+    float shadowFactor = 0.0f;
+    if (shadowsOn) {
+        // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1: texel choice and the lit/shadowed verdict are decisions
+        const f3 fragDir = px.fragPos - lightPosition;
+        const unsigned short texel = __ldg(atlases.shadow[entry.index] + (size_t)entry.layer * texelsPerLayer + cubeTexelDecided(fragDir, cubeRes));
+        const float texelDepth = unorm16(texel);
+        const float lightNormalDot = dotFast(lightMinusFrag, px.normal);
+        const float biasFactor = fmaxf(0.1f, satFast(lightNormalDot) * 0.03f);
+        const float lhs = distance * (1.0f - biasFactor), rhs = texelDepth * farPlane;
+        const float gap = lhs - rhs;
+        // lightNormalDot only matters through saturate(.)*0.03 vs 0.1, i.e. when it exceeds 3.33: never borderline for the verdict's margin
+        bool shadowed;
+        if (fabsf(gap) > 8.0f * kMargin * fmaxf(lhs, rhs)) shadowed = gap > 0.0f;
+        else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), texelDepth, farPlane);
+        shadowFactor = shadowed ? 1.0f : 0.0f;
+    }
+    shadowFactor = fminf(shadowFactor, fma_(distanceRatio, 1.0f - minGi, minGi));
+    float reweightingFactor = 1.0f;
+    if (shadowFactor > 0.0f) reweightingFactor = fma_(1.0f - distanceRatio, minGi, distanceRatio);
+    validSamples += reweightingFactor;
+    const f3 tmpColor = shadeFast(px, specularPosition, lightPosition, lightColor, lightRadius, invRadius);
+    const float lit = 1.0f - shadowFactor;
+    vplColor = mk3(fma_(lit, tmpColor.x, vplColor.x), fma_(lit, tmpColor.y, vplColor.y), fma_(lit, tmpColor.z, vplColor.z));
+}
+
+// tile-list mode: the <= 12 VPLs of a tile as the kernel stages them in shared memory
+struct StagedLight { float4 posRadius, colorFar, specEntry; };       // specEntry.w = bits of (atlas index << 16 | layer)
+constexpr int kTileCtaX = 8, kTileCtaY = 2;                          // tiles per CTA in tile-list mode: 40 x 10 pixels, one thread per pixel
+
+template <int MODE>      // SGI_GATHER_STOCHASTIC (the reference's live shader) or SGI_GATHER_TILE_LIST
+__global__ void __launch_bounds__(MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY * 25 : kGatherThreadsX * kGatherThreadsY, MODE == SGI_GATHER_TILE_LIST ? 2 : 4)
 gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
              const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
              uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
-             const __grid_constant__ BandLinks links) {
-    const int x = blockIdx.x * kGatherThreadsX + threadIdx.x;
-    const int ly = blockIdx.y * kGatherThreadsY + threadIdx.y;
+             const __grid_constant__ BandLinks links, const SgiVplStage2PerTileOutputs* __restrict__ tileLists, const unsigned short* __restrict__ tilePos) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ly = blockIdx.y * blockDim.y + threadIdx.y;
+    // ---- tile-list mode: stage this CTA's 8x2 tiles' VPL lists through shared memory ----
+    __shared__ StagedLight sLight[MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY * SGI_MAX_VPLS_PER_TILE : 1];
+    __shared__ int sCount[MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY : 1];
+    if (MODE == SGI_GATHER_TILE_LIST) {
+        const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.rows / SGI_TILE_DIVISOR;
+        const int t = threadIdx.y * blockDim.x + threadIdx.x;
+        if (t < kTileCtaX * kTileCtaY * SGI_MAX_VPLS_PER_TILE) {
+            const int lt = t / SGI_MAX_VPLS_PER_TILE, l = t % SGI_MAX_VPLS_PER_TILE;
+            const int tx = blockIdx.x * kTileCtaX + lt % kTileCtaX, ty = blockIdx.y * kTileCtaY + lt / kTileCtaX;
+            int count = 0;
+            if (tx < tilesX && ty < tilesY) {
+                const int tile = ty * tilesX + tx;
+                count = min(__ldg(&tileLists[tile].numVisible), SGI_MAX_VPLS_PER_TILE);
+                if (l < count) {
+                    const int k = min((int)__ldg(tilePos + (size_t)tile * SGI_MAX_VPLS_PER_TILE + l), SGI_MAX_TOTAL_VPLS_PER_FRAME - 1);   // position in the compacted (coloured) table
+                    const float4* L = reinterpret_cast<const float4*>(lightData + k);
+                    const float4 lp = __ldg(L), lc = __ldg(L + 1), sp = __ldg(L + 2), rfi = __ldg(L + 3);
+                    const SgiAtlasEntry e = shadowIndices[k];
+                    StagedLight sl;
+                    sl.posRadius = make_float4(lp.x, lp.y, lp.z, rfi.x);
+                    sl.colorFar = make_float4(lc.x, lc.y, lc.z, rfi.y);
+                    sl.specEntry = make_float4(sp.x, sp.y, sp.z, __int_as_float((e.index << 16) | (e.layer & 0xffff)));
+                    sLight[t] = sl;
+                }
+            }
+            if (l == 0) sCount[lt] = count;
+        }
+        __syncthreads();
+    }
     const int y = ly + bd.yOffset;
     // row bands: the CTAs that will store pass-0 rows into a neighbour's halo first wait until that neighbour has finished
     // the previous frame (its final pass read those halo rows)
@@ -192,64 +269,54 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     const float maxRandomIndexF = (float)(V - 1);
     const float minGi = fc.minGiOcclusionFactor;
 
-    // V <= 0: undefined in the reference (stale lights); defined here as "no light".
-    // The shader's single loop re-draws with `--i; continue;` (vpl_pbr_gi.fs:164-171).  Here the re-draws of one sample run in
-    // an inner loop (the same sequence of draws per pixel), so that the lanes of a warp reach the expensive shading part
-    // together: it then executes max-over-lanes(sampleCount) times per warp instead of max-over-lanes(samples + re-draws).
-    for (int i = 0, resamples = 0; V > 0 && i < sampleCount; ++i) {
-        const float4* L; float4 lp, rfi; f3 lightPosition, lightMinusFrag; float lightRadius, d2; int lightIndex;
-        while (true) {
-            const float rnd = random3(pcx, pcy, seedZ);
-            seedZ = fadd(seedZ, 10000.0f);
-            lightIndex = (int)fmul(maxRandomIndexF, rnd);
-            L = reinterpret_cast<const float4*>(lightData + lightIndex);
-            lp = __ldg(L);
-            rfi = __ldg(L + 3);                                 // radius, farPlane, intensity, pad
-            lightPosition = mk3(lp.x, lp.y, lp.z);
-            lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
-            lightRadius = rfi.x;
-            d2 = dotFast(lightMinusFrag, lightMinusFrag);
-            if (resamples >= 5) break;
-            // if (dot(normal, normalize(l)) < 0 || length(l) > radius) re-draw      (vpl_pbr_gi.fs:164-171)
-            const float s = dotFast(px.normal, lightMinusFrag);      // same sign as the normalised dot product
-            const float r2 = lightRadius * lightRadius;
-            const bool sideSure = s * s > (kMargin * kMargin) * d2;
-            const bool farSure = d2 > r2 * (1.0f + 4.0f * kMargin), nearSure = d2 < r2 * (1.0f - 4.0f * kMargin);
-            bool redraw;
-            if (sideSure && (farSure || nearSure)) redraw = (s < 0.0f) || farSure;
-            else redraw = exactRedraw(px.normal, lightMinusFrag, lightRadius);
-            if (!redraw) break;
-            ++resamples;
+    if (MODE == SGI_GATHER_STOCHASTIC) {
+        // V <= 0: undefined in the reference (stale lights); defined here as "no light".
+        // The shader's single loop re-draws with `--i; continue;` (vpl_pbr_gi.fs:164-171).  Here the re-draws of one sample run in
+        // an inner loop (the same sequence of draws per pixel), so that the lanes of a warp reach the expensive shading part
+        // together: it then executes max-over-lanes(sampleCount) times per warp instead of max-over-lanes(samples + re-draws).
+        const uint32_t seedXY = __float_as_uint(pcx) ^ hash1(__float_as_uint(pcy));     // the draw-invariant part of hash(uvec3)
+        for (int i = 0, resamples = 0; V > 0 && i < sampleCount; ++i) {
+            const float4* L; float4 lp, rfi; f3 lightPosition, lightMinusFrag; float lightRadius, d2; int lightIndex;
+            while (true) {
+                const float rnd = floatConstruct(hash1(seedXY ^ hash1(__float_as_uint(seedZ))));     // random(vec3(gl_FragCoord.xy, time)), common.glsl:210-214
+                seedZ = fadd(seedZ, 10000.0f);
+                lightIndex = (int)fmul(maxRandomIndexF, rnd);
+                L = reinterpret_cast<const float4*>(lightData + lightIndex);
+                lp = __ldg(L);
+                rfi = __ldg(L + 3);                                 // radius, farPlane, intensity, pad
+                lightPosition = mk3(lp.x, lp.y, lp.z);
+                lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
+                lightRadius = rfi.x;
+                d2 = dotFast(lightMinusFrag, lightMinusFrag);
+                if (resamples >= 5) break;
+                if (!behindOrOutOfRange(px.normal, lightMinusFrag, d2, lightRadius)) break;
+                ++resamples;
+            }
+            const float4 lc = __ldg(L + 1);
+            const float4 sp = __ldg(L + 2);
+            SgiAtlasEntry entry; entry.index = 0; entry.layer = 0;
+            if (shadowsOn) entry = shadowIndices[lightIndex];
+            shadeAcceptedLight(px, lightPosition, lightMinusFrag, d2, lightRadius, rfi.y, mk3(lc.x, lc.y, lc.z), mk3(sp.x, sp.y, sp.z), entry, shadowsOn, minGi,
+                               cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
         }
-        const float4 lc = __ldg(L + 1);
-        const float4 sp = __ldg(L + 2);
-        const float invRadius = rcpFast(lightRadius);
-        const float distance = d2 * rsqrtf(d2);
-        const float distanceRatio = satFast(2.0f * distance * invRadius);
-        float shadowFactor = 0.0f;
-        if (shadowsOn) {
-            // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1: texel choice and the lit/shadowed verdict are decisions
-            const SgiAtlasEntry entry = shadowIndices[lightIndex];
-            const f3 fragDir = px.fragPos - lightPosition;
-            const unsigned short texel = __ldg(atlases.shadow[entry.index] + (size_t)entry.layer * texelsPerLayer + cubeTexelDecided(fragDir, cubeRes));
-            const float texelDepth = unorm16(texel);
-            const float lightNormalDot = dotFast(lightMinusFrag, px.normal);
-            const float biasFactor = fmaxf(0.1f, satFast(lightNormalDot) * 0.03f);
-            const float lhs = distance * (1.0f - biasFactor), rhs = texelDepth * rfi.y;
-            const float gap = lhs - rhs;
-            // lightNormalDot only matters through saturate(.)*0.03 vs 0.1, i.e. when it exceeds 3.33: never borderline for the verdict's margin
-            bool shadowed;
-            if (fabsf(gap) > 8.0f * kMargin * fmaxf(lhs, rhs)) shadowed = gap > 0.0f;
-            else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), texelDepth, rfi.y);
-            shadowFactor = shadowed ? 1.0f : 0.0f;
+    } else {
+        // Tile-list mode (no live reference counterpart: the tile lookup of vpl_pbr_gi.fs:86-97 is commented out): every VPL of
+        // the pixel's 5x5 tile list, in list order, through the same per-light body; a VPL behind the pixel or out of range is
+        // skipped (the stochastic shader would re-draw).  Deterministic: no random numbers.
+        const int lt = ((int)threadIdx.y / SGI_TILE_DIVISOR) * kTileCtaX + (int)threadIdx.x / SGI_TILE_DIVISOR;
+        const int count = sCount[lt];
+        for (int l = 0; l < count; ++l) {
+            const StagedLight sl = sLight[lt * SGI_MAX_VPLS_PER_TILE + l];
+            const f3 lightPosition = mk3(sl.posRadius.x, sl.posRadius.y, sl.posRadius.z);
+            const f3 lightMinusFrag = lightPosition - px.fragPos;
+            const float lightRadius = sl.posRadius.w;
+            const float d2 = dotFast(lightMinusFrag, lightMinusFrag);
+            if (behindOrOutOfRange(px.normal, lightMinusFrag, d2, lightRadius)) continue;
+            const int eb = __float_as_int(sl.specEntry.w);
+            SgiAtlasEntry entry; entry.index = eb >> 16; entry.layer = eb & 0xffff;
+            shadeAcceptedLight(px, lightPosition, lightMinusFrag, d2, lightRadius, sl.colorFar.w, mk3(sl.colorFar.x, sl.colorFar.y, sl.colorFar.z),
+                               mk3(sl.specEntry.x, sl.specEntry.y, sl.specEntry.z), entry, shadowsOn, minGi, cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
         }
-        shadowFactor = fminf(shadowFactor, fma_(distanceRatio, 1.0f - minGi, minGi));
-        float reweightingFactor = 1.0f;
-        if (shadowFactor > 0.0f) reweightingFactor = fma_(1.0f - distanceRatio, minGi, distanceRatio);
-        validSamples += reweightingFactor;
-        const f3 tmpColor = shadeFast(px, mk3(sp.x, sp.y, sp.z), lightPosition, mk3(lc.x, lc.y, lc.z), lightRadius, invRadius);
-        const float lit = 1.0f - shadowFactor;
-        vplColor = mk3(fma_(lit, tmpColor.x, vplColor.x), fma_(lit, tmpColor.y, vplColor.y), fma_(lit, tmpColor.z, vplColor.z));
     }
     validSamples = fmaxf(validSamples, 1.0f);
     const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
@@ -278,17 +345,27 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 // (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
 bool preloadGatherKernels() {
     cudaFuncAttributes a; bool ok = true;
-    ok = ok && cudaFuncGetAttributes(&a, gatherKernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_STOCHASTIC>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_TILE_LIST>) == cudaSuccess;
     return ok;
 }
 
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links) {
-    dim3 block(kGatherThreadsX, kGatherThreadsY);
-    dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
-    gatherKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases, colorOut, reservoirOut, guideOut, mergedOut, links);
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
+                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos) {
+    if (tileLists != nullptr) {
+        dim3 block(kTileCtaX * SGI_TILE_DIVISOR, kTileCtaY * SGI_TILE_DIVISOR);
+        dim3 grid((bd.W + block.x - 1) / block.x, (bd.rows + block.y - 1) / block.y);
+        gatherKernel<SGI_GATHER_TILE_LIST><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+                                                                       colorOut, reservoirOut, guideOut, mergedOut, links, tileLists, tilePos);
+    } else {
+        dim3 block(kGatherThreadsX, kGatherThreadsY);
+        dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
+        gatherKernel<SGI_GATHER_STOCHASTIC><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, nullptr, nullptr);
+    }
     return 1;
 }
 

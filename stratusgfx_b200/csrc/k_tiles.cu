@@ -109,8 +109,8 @@ stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 // the colouring stage), which saves the indirection through the index list.
 __global__ void __launch_bounds__(kS2Threads)
 stage2Kernel(int tilesX, int tileY0, int tilesY, int patchesX, const SgiVplStage1PerTileOutputs* __restrict__ stage1, const SgiVplData* __restrict__ lightTable,
-             const int32_t* __restrict__ visible, SgiVplStage2PerTileOutputs* __restrict__ out, const int* __restrict__ classCount,
-             const int* __restrict__ classList, int maxPatches) {
+             const int32_t* __restrict__ visible, SgiVplStage2PerTileOutputs* __restrict__ out, unsigned short* __restrict__ tilePos,
+             const int* __restrict__ classCount, const int* __restrict__ classList, int maxPatches) {
     __shared__ unsigned short sOrder[SGI_MAX_TOTAL_VPLS_PER_FRAME];
     __shared__ int sBinCount[kS2Bins], sBinStart[kS2Bins + 1], sBinFill[kS2Bins];
     __shared__ float sRed[kS2Threads / 32][6];
@@ -254,6 +254,9 @@ stage2Kernel(int tilesX, int tileY0, int tilesY, int patchesX, const SgiVplStage
     o[0] = count;
     #pragma unroll
     for (int i = 0; i < SGI_MAX_VPLS_PER_TILE; ++i) if (i < count) o[1 + i] = __ldg(visible + 1 + pos[i]);
+    // the same list as positions in the compacted table, for the tile-list gather (library-owned side output)
+    #pragma unroll
+    for (int i = 0; i < SGI_MAX_VPLS_PER_TILE; ++i) if (i < count) tilePos[(size_t)tile * SGI_MAX_VPLS_PER_TILE + i] = (unsigned short)pos[i];
 }
 
 }  // namespace
@@ -286,11 +289,11 @@ int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
 }
 
 int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightTable,
-                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, const int* patchScratch) {
+                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, const int* patchScratch) {
     const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.crows / SGI_TILE_DIVISOR;
     if (tilesX <= 0 || tilesY <= 0) return 0;
     const int patchesX = (tilesX + kS2X - 1) / kS2X, patchesY = (tilesY + kS2Y - 1) / kS2Y;
-    stage2Kernel<<<patchesX * patchesY, kS2Threads, 0, stream>>>(tilesX, bd.c0 / SGI_TILE_DIVISOR, tilesY, patchesX, stage1, lightTable, visible, out,
+    stage2Kernel<<<patchesX * patchesY, kS2Threads, 0, stream>>>(tilesX, bd.c0 / SGI_TILE_DIVISOR, tilesY, patchesX, stage1, lightTable, visible, out, tilePos,
                                                                  patchScratch, patchScratch + kPatchClasses, maxPatchesOf(bd));
     return 1;
 }

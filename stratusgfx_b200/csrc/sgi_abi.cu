@@ -33,7 +33,7 @@ static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h
 static BandDims bandDims(const SgiHandle h);
 
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab, (void**)&h->patchScratch};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab, (void**)&h->patchScratch, (void**)&h->tilePos};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
     h->resA = h->resB = nullptr;
     h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
@@ -67,7 +67,12 @@ static int allocPlanes(SgiHandle h) {
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
     SGI_CUDA(h, cudaMalloc(&h->guide, n * 16));
     SGI_CUDA(h, cudaMalloc((void**)&h->patchScratch, (size_t)patchScratchInts(bandDims(h)) * sizeof(int)));
+    {
+        const size_t tiles = (size_t)(h->cp.width / SGI_TILE_DIVISOR) * (size_t)(h->cp.rows / SGI_TILE_DIVISOR);
+        SGI_CUDA(h, cudaMalloc((void**)&h->tilePos, (tiles > 0 ? tiles : 1) * SGI_MAX_VPLS_PER_TILE * sizeof(unsigned short)));
+    }
     h->guideValid = false;
+    h->tileListsValid = false;
     // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the previous-frame FBO is
     // never cleared and starts at zero.  Reservoir halo rows start at zero too.
     SGI_CUDA(h, cudaMemsetAsync(h->slab, 0, off, h->stream));
@@ -172,6 +177,7 @@ int sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers) {
     h->bound = true;
     h->guideValid = false;
     h->pass0Fused = false;
+    h->tileListsValid = false;
     return SGI_OK;
 }
 
@@ -225,13 +231,19 @@ int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
     const BandDims bd = bandDims(h);
     int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch);
     // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
-    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->patchScratch);
+    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
+    h->tileListsValid = true;
     return postLaunch(h, n);
 }
 
 int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
-    if (fp->gatherMode != SGI_GATHER_STOCHASTIC) return fail(h, SGI_ERR_UNSUPPORTED, "sgi_gather: only SGI_GATHER_STOCHASTIC (the reference's live path) is implemented");
+    if (fp->gatherMode != SGI_GATHER_STOCHASTIC && fp->gatherMode != SGI_GATHER_TILE_LIST) return fail(h, SGI_ERR_INVALID_ARG, "sgi_gather: unknown gatherMode");
+    const bool tileMode = fp->gatherMode == SGI_GATHER_TILE_LIST;
+    if (tileMode) {
+        NEED(h, vplVisiblePerTile);
+        if (!h->tileListsValid) return fail(h, SGI_ERR_NOT_BOUND, "sgi_gather: SGI_GATHER_TILE_LIST needs sgi_tile_lists first (since the last bind)");
+    }
     NEED(h, depth); NEED(h, normal); NEED(h, albedo); NEED(h, baseReflectivity); NEED(h, roughnessMetallicAmbient); NEED(h, ssao);
     NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, shadowDiffuseIndices); NEED(h, shadowCubeMaps[0]);
     FrameConsts fc; fillFrameConsts(fp, &fc);
@@ -251,7 +263,7 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
-                               fuse ? (uint2*)h->resA : nullptr, links);
+                               fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos);
     if (h->banded && fuse) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it

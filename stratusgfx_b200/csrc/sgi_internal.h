@@ -153,6 +153,8 @@ struct SgiHandle_ {
     void* history[2] = {nullptr, nullptr};    // half
     int cur = 0;
     int* patchScratch = nullptr;    // stage-1 -> stage-2 patch size classes (k_tiles.cu)
+    unsigned short* tilePos = nullptr;   // [tiles][12] per-tile lists as positions in the compacted VPL table (tile-list gather)
+    bool tileListsValid = false;    // sgi_tile_lists ran since the last bind
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
     bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
     bool pass0Fused = false;        // the gather of this frame already wrote denoise pass 0 into resA, for `pass0Time`
@@ -200,11 +202,12 @@ int patchScratchInts(const BandDims& bd);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  SgiVplStage1PerTileOutputs* out, int* patchScratch);
 int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightTable,
-                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, const int* patchScratch);
+                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, const int* patchScratch);
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
-                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links);
+                 uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
+                 const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
 

@@ -66,6 +66,28 @@ def test_denoise_iteration_count_is_a_parameter(tiny, iters):
     _assert_parity(run_cuda_staged(tiny, frames=1, denoise_iters=iters), run_oracle(tiny, frames=1, denoise_iters=iters))
 
 
+def test_tile_list_gather_mode(built):
+    """SGI_GATHER_TILE_LIST: every VPL of the pixel's 5x5-tile list instead of random draws (the tile lookup that is
+    commented out at vpl_pbr_gi.fs:86-97, composed with the live per-light body); deterministic, lists staged through
+    shared memory.  Checked against the oracle's restatement of the same composition, through the denoiser."""
+    for wl, frames in (("tiny", 2), ("c1", 1)):
+        d = SceneData(wl, frames=frames)
+        for fp in d.fp:
+            fp.gatherMode = _abi.GATHER_TILE_LIST
+        cu, orc = run_cuda_staged(d), run_oracle(d)
+        _assert_parity(cu, orc)
+        assert orc[0]["sample_stats"][1] > 0                      # lights were shaded
+        w = cu[0]["gi_reservoir"][..., 3].astype(np.float32)
+        assert w.min() >= 1.0 and w.max() <= 12.0                  # at most 12 VPLs per tile, weights re-scaled into [minGi, 1] each
+    # the mode needs the tile lists of this frame
+    gp = make_pass(d)
+    gp.set_gbuffer(d.gb[0], d.gb[-1]); gp.bind()
+    gp.cull(d.fp[0]); gp.color(d.fp[0])
+    with pytest.raises(Exception, match="sgi_tile_lists"):
+        gp.gather(d.fp[0])
+    gp.close()
+
+
 def test_fused_frame_call_equals_staged_calls(tiny):
     staged = run_cuda_staged(tiny)
     gp = make_pass(tiny)
