@@ -142,9 +142,20 @@ def broadcast_frame_inputs(dist, tensors, src=0):
 
 
 def gather_bands(dist, band_tensor, full_tensor, bands, rank, dst=0):
-    """Step 3: gather each rank's owned rows into `full_tensor` ([H, ...]) on rank `dst`."""
+    """Step 3: gather each rank's owned rows into `full_tensor` ([H, ...]) on rank `dst`.  Bands of equal height use one
+    collective gather; balanced (unequal) bands are received row range by row range (point-to-point)."""
+    if len({b.b1 - b.b0 for b in bands}) == 1:
+        if rank == dst:
+            views = [full_tensor[b.b0:b.b1] for b in bands]
+            dist.gather(band_tensor, views, dst=dst)
+        else:
+            dist.gather(band_tensor, None, dst=dst)
+        return
     if rank == dst:
-        views = [full_tensor[b.b0:b.b1] for b in bands]
-        dist.gather(band_tensor, views, dst=dst)
+        me = bands[dst]
+        full_tensor[me.b0:me.b1].copy_(band_tensor)
+        reqs = [dist.irecv(full_tensor[b.b0:b.b1], src=b.rank) for b in bands if b.rank != dst]
+        for r in reqs:
+            r.wait()
     else:
-        dist.gather(band_tensor, None, dst=dst)
+        dist.send(band_tensor.contiguous(), dst)

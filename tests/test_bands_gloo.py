@@ -31,18 +31,18 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, workload, out_path):
+def _worker(rank, world, port, workload, out_path, cuts=None):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     os.environ["OMP_NUM_THREADS"] = "4"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle.oracle_py import OracleFrame
-    from stratusgfx_b200.bands import broadcast_frame_inputs, gather_bands
+    from stratusgfx_b200.bands import bands_from_cuts, broadcast_frame_inputs, gather_bands
     from stratusgfx_b200.scene import Scene
     scene = Scene(workload)
     W, H = scene.width, scene.height
-    bands = plan_bands(H, world)
+    bands = plan_bands(H, world) if cuts is None else bands_from_cuts(list(cuts), H, APRON)
     me = bands[rank]
     fp = scene.frame_params(0)
     gb, pgb = scene.gbuffer(0, me.y0, me.rows), scene.gbuffer(-1, me.y0, me.rows)
@@ -66,12 +66,14 @@ def _worker(rank, world, port, workload, out_path):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_bands_reproduce_the_whole_frame(built, tmp_path):
+@pytest.mark.parametrize("cuts", [None, (0, 205, 360)], ids=["equal", "balanced"])
+def test_two_rank_gloo_bands_reproduce_the_whole_frame(built, tmp_path, cuts):
+    """Equal bands (one collective gather) and measured-balance bands of unequal height (point-to-point gather)."""
     import torch.multiprocessing as mp
     from tests.parity_util import SceneData, run_oracle
     workload = "c1"
     out_path = str(tmp_path / "assembled.npy")
-    mp.spawn(_worker, args=(2, _free_port(), workload, out_path), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), workload, out_path, cuts), nprocs=2, join=True)
     assembled = np.load(out_path)
     whole = run_oracle(SceneData(workload), keep_passes=False)[0]["combined"]
     # apron rows make every owned row see exactly the taps it would see in the whole frame
