@@ -69,11 +69,11 @@ prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* _
 }
 
 // ---- final-pass epilogue: temporal accumulation + re-modulation (vpl_pbr_gi_denoise.fs:337-434) ------------
-SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 centerNormal, f3 shadowFactor) {
+// `centerDepth` comes from the guide plane (a bit copy of the depth texel), so the depth plane is not read again here
+SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 centerNormal, float centerDepth, f3 shadowFactor) {
     const int W = bd.W, rows = bd.rows;
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * W + x;
-    const float centerDepth = __ldg(io.depth + p);
     const float u = fdiv(fadd((float)x, 0.5f), (float)W), v = fdiv(fadd((float)y, 0.5f), (float)bd.fullH);
     const f4 screenColor = loadHalf4(io.screen, p);
     const f4 gi4 = loadHalf4(io.illum, p);
@@ -158,7 +158,7 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
     const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
     io.reservoirOut[p] = rv;
     pushRes(io.links, y, x, bd.W, rv);
-    if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, shadowFactor);
+    if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, centerDepth, shadowFactor);
 }
 
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
@@ -192,7 +192,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
         for (int k = 0; k < kLat; ++k) {
             const size_t p = (size_t)min(c0 + (m0 + k) * s + r, cEnd - 1) * W + x;
             prefetchL2(io.screen + p); prefetchL2(io.illum + p); prefetchL2(io.velocity + p); prefetchL2(io.historyIn + p);
-            prefetchL2(io.ids + p); prefetchL2(io.depth + p); prefetchL2(io.prevDepth + p); prefetchL2(io.prevNormal + p);
+            prefetchL2(io.ids + p); prefetchL2(io.normal + p); prefetchL2(io.prevDepth + p); prefetchL2(io.prevNormal + p);
             prefetchL2(io.prevGi + p); prefetchL2(io.prevIds + p);
         }
     }
@@ -246,7 +246,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
         const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
         io.reservoirOut[(size_t)ly * W + x] = rv;
         pushRes(io.links, ly + bd.yOffset, x, W, rv);
-        if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), shadowFactor);
+        if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), __ldg(&io.guide[(size_t)ly * W + x].w), shadowFactor);
     }
 }
 

@@ -11,7 +11,16 @@
 //   singleScatteringBRDF_Specular :102-115, NDF_GGX :51-55, Visibility_G_SmithGGX :59-64, Fr_Fresnel_Schlick :73-76)
 //   applyFog                             fog.glsl:37-41
 //
-// One thread per pixel.  Two arithmetic tiers:
+// One thread per pixel.  The stochastic mode (the reference's live shader) runs as a PERSISTENT kernel:
+// one or two CTAs per SM stage the frame's compacted VPL table (48 B per VPL: position+radius,
+// colour+farPlane, specular position+atlas entry) in shared memory once, then their warps stride
+// over 32-pixel row segments.  A pixel's draws are a fixed sequence (draw k hashes (x, y, time+10000k)),
+// so the kernel first runs the accept/re-draw decisions for the whole sequence (phase 1: one hash,
+// one 16 B shared-memory read and the side/range test per draw, every lane busy until its own
+// sample budget is met) and then shades the accepted VPLs in order (phase 2).  The shader's single
+// loop does the same work in the same order; splitting it keeps the lanes of a warp together in the
+// expensive part and replaces scattered L1 reads (32 tag look-ups per request) by shared-memory reads.
+// Two arithmetic tiers:
 //
 //   DECISIONS (which VPL is drawn, re-draw or keep, sample budget, cube texel, shadowed or lit) are
 //   evaluated so that they come out exactly as the IEEE / glm-order evaluation of the shader text
@@ -27,6 +36,7 @@
 // The kernel also writes the frame's "guide" plane (decoded normal + depth, float4) that the
 // denoiser passes read instead of re-decoding 25 normals per pixel per pass, and (when asked) the
 // output of denoise pass 0, which is a per-pixel function of the reservoir it has just computed.
+#include <cstdlib>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -167,6 +177,8 @@ SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 ligh
 
 // tile-list mode: the <= 12 VPLs of a tile as the kernel stages them in shared memory
 struct StagedLight { float4 posRadius, colorFar, specEntry; };       // specEntry.w = bits of (atlas index << 16 | layer)
+constexpr int kTableBytesPerVpl = 48;                                // three float4 per staged VPL
+constexpr int kTableBytesTwoCtas = 110 * 1024;                       // two CTAs per SM while 2 x (table + 1 KB reserve) <= 227 KB
 constexpr int kTileCtaX = 8, kTileCtaY = 2;                          // tiles per CTA in tile-list mode: 40 x 10 pixels, one thread per pixel
 
 template <int MODE>      // SGI_GATHER_STOCHASTIC (the reference's live shader) or SGI_GATHER_TILE_LIST
@@ -339,6 +351,181 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     }
 }
 
+
+// ---- stochastic mode, persistent two-phase kernel ------------------------------------------------------------------
+constexpr int kMaxSamples = 6;                // int(mix(2, 10, 1 - max(roughness, 0.5))) <= 6 (vpl_pbr_gi.fs:138-143)
+constexpr int kMaxResamples = 5;              // vpl_pbr_gi.fs:164-171
+constexpr int kMaxDraws = kMaxSamples + kMaxResamples;
+static_assert(kMaxDraws <= kGatherMaxDraws, "FrameConsts::hashZ is too short");
+
+SGI_DEV void bandWaitWarp(const BandLinks& L, bool needUp, bool needDown) {
+    if (L.waitUp == nullptr && L.waitDown == nullptr) return;          // uniform across the launch
+    const bool up = __any_sync(0xffffffffu, needUp && L.waitUp != nullptr);
+    const bool down = __any_sync(0xffffffffu, needDown && L.waitDown != nullptr);
+    if (up || down) {
+        if ((threadIdx.x & 31) == 0) {
+            const long long t0 = clock64();
+            bool ok = true;
+            if (up) ok = spinUntil(L.waitUp, L.waitEpoch, t0) && ok;
+            if (down) ok = spinUntil(L.waitDown, L.waitEpoch, t0) && ok;
+            if (!ok) atomicAdd(L.timeouts, 1);
+        }
+        __syncwarp();
+    }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
+                       const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
+                       const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
+                       const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
+                       uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
+                       const __grid_constant__ BandLinks links, int tableCap) {
+    extern __shared__ float4 sTab[];
+    float4* __restrict__ sPos = sTab;                       // (position, radius)
+    float4* __restrict__ sCol = sTab + tableCap;            // (colour, farPlane)
+    float4* __restrict__ sSpec = sTab + 2 * tableCap;       // (specular position, atlas index << 16 | layer)
+    const int V = __ldg(numVisible);
+    const int staged = min(max(V, 0), tableCap);
+    for (int i = threadIdx.x; i < staged; i += THREADS) {
+        const float4* L = reinterpret_cast<const float4*>(lightData + i);
+        const float4 lp = __ldg(L), lc = __ldg(L + 1), sp = __ldg(L + 2), rfi = __ldg(L + 3);
+        const SgiAtlasEntry e = shadowIndices[i];
+        sPos[i] = make_float4(lp.x, lp.y, lp.z, rfi.x);
+        sCol[i] = make_float4(lc.x, lc.y, lc.z, rfi.y);
+        sSpec[i] = make_float4(sp.x, sp.y, sp.z, __int_as_float((e.index << 16) | (e.layer & 0xffff)));
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int unitsX = (bd.W + 31) >> 5;
+    const int units = unitsX * bd.rows;
+    const int warpStride = gridDim.x * (THREADS / 32);
+    const int cubeRes = bd.cubeRes;
+    const int texelsPerLayer = 6 * cubeRes * cubeRes;
+    const m4 invPV = loadMat(fc.invPV);
+    const f3 viewPosition = mk3(fc.viewPos[0], fc.viewPos[1], fc.viewPos[2]);
+    const float maxRandomIndexF = (float)(V - 1);
+    const float minGi = fc.minGiOcclusionFactor;
+    const int lastStaged = max(staged - 1, 0);
+
+    for (int unit = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); unit < units; unit += warpStride) {
+        const int ly = unit / unitsX;
+        const int x = (unit - ly * unitsX) * 32 + lane;
+        const int y = ly + bd.yOffset;
+        // row bands: a warp that will store pass-0 rows into a neighbour's halo first waits until that neighbour has finished
+        // the previous frame (its final pass read those halo rows)
+        bandWaitWarp(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
+                     links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
+        if (x >= bd.W) continue;
+        const size_t p = (size_t)ly * bd.W + x;
+
+        // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
+        const float depth = __ldg(gDepth + p);
+        PixelConsts px;
+        px.normal = decodeNormal(__ldg(gNormal + p));
+        guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
+        if (ly < bd.c0 || ly >= bd.c0 + bd.crows) continue;      // halo row of a band: only the guide plane is needed here
+        const float pcx = fadd((float)x, 0.5f), pcy = fadd((float)y, 0.5f);          // gl_FragCoord.xy
+        const float u = fdiv(pcx, (float)bd.W), v = fdiv(pcy, (float)bd.fullH);       // fsTexCoords
+        px.fragPos = worldPositionFromDepth(u, v, depth, invPV);
+        const f3 toView = viewPosition - px.fragPos;
+        const float distToCamera = length(toView);
+        const uint32_t alb = __ldg(gAlbedo + p);
+        const f3 baseColor = mk3(vmax(unorm8(alb & 0xffu), 0.01f), vmax(unorm8((alb >> 8) & 0xffu), 0.01f), vmax(unorm8((alb >> 16) & 0xffu), 0.01f));
+        const uint32_t rma = __ldg(gRma + p);
+        const float roughness = vmax(0.5f, unorm8(rma & 0xffu));
+        const float roughnessWeight = fsub(1.0f, roughness);
+        const float distRatioToCamera = vmin(fsub(1.0f, fdiv(distToCamera, 1000.0f)), 1.0f);
+        const int maxSamplesPerPixel = (int)mix(2.0f, 10.0f, roughnessWeight);
+        // V <= 0: undefined in the reference (stale lights); defined here as "no light"
+        const int sampleCount = V > 0 ? min(max(1, (int)fmul((float)maxSamplesPerPixel, distRatioToCamera)), kMaxSamples) : 0;
+        const bool shadowsOn = distToCamera < 500.0f;
+
+        // ---- phase 1: the accept / re-draw decisions of the pixel's draw sequence (vpl_pbr_gi.fs:148-171) ----
+        // draw k: rand = random(vec3(gl_FragCoord.xy, time + 10000 k)); the hash of the third component is the same for every
+        // pixel and comes precomputed in fc.hashZ (common.glsl:199-214).  `--i; continue;` re-draws without consuming a sample,
+        // at most 5 times per pixel; after that every draw is accepted.
+        const uint32_t seedXY = __float_as_uint(pcx) ^ hash1(__float_as_uint(pcy));
+        uint32_t q0 = 0u, q1 = 0u, q2 = 0u;          // accepted VPL positions, six 16-bit slots in sample order
+        int accepted = 0, resamples = 0;
+        #pragma unroll
+        for (int k = 0; k < kMaxDraws; ++k) {
+            if (accepted >= sampleCount) break;
+            const float rnd = floatConstruct(hash1(seedXY ^ fc.hashZ[k]));
+            const int lightIndex = min((int)fmul(maxRandomIndexF, rnd), lastStaged);
+            bool reject = false;
+            if (resamples < kMaxResamples) {
+                const float4 pr = sPos[lightIndex];
+                const f3 lightMinusFrag = mk3(pr.x, pr.y, pr.z) - px.fragPos;        // exact (single rounding per component)
+                reject = behindOrOutOfRange(px.normal, lightMinusFrag, dotFast(lightMinusFrag, lightMinusFrag), pr.w);
+            }
+            if (reject) ++resamples;
+            else {
+                const uint32_t sv = (uint32_t)lightIndex << ((accepted & 1) * 16);
+                if (accepted < 2) q0 |= sv; else if (accepted < 4) q1 |= sv; else q2 |= sv;
+                ++accepted;
+            }
+        }
+
+        // ---- per-pixel set-up: radiance tier (BRDF_Base pbr2.glsl:146-168 and everything light-independent) ----
+        {
+            const float metallic = unorm8((rma >> 8) & 0xffu);
+            const float ambientOcclusion = vclamp(h2f(__ldg(ssao + p)), 0.35f, 1.0f);
+            const float refl = unorm8((uint32_t)__ldg(gRefl + p) & 0xffu);
+            float rr = roughness;
+            if (fc.usePerceptualRoughness) rr = rr * rr;
+            rr = fmaxf(fmaxf(0.0f, fc.minRoughness), rr);
+            px.r2 = rr * rr;
+            const float iv = rsqrtf(dotFast(toView, toView));
+            px.viewDir = mk3(toView.x * iv, toView.y * iv, toView.z * iv);
+            px.NdotV = satFast(dotFast(px.normal, px.viewDir));
+            px.ggxvTerm = sqrtFast(fma_(fma_(-px.r2, px.NdotV, px.NdotV), px.NdotV, px.r2));
+            const float om = 1.0f - metallic, f0s = 0.16f * refl * refl * om;
+            const f3 inv = mk3(rcpFast(baseColor.x + PREVENT_DIV_BY_ZERO), rcpFast(baseColor.y + PREVENT_DIV_BY_ZERO), rcpFast(baseColor.z + PREVENT_DIV_BY_ZERO));
+            // diffuseColor / (diffuseDivisor + eps) / PI   and   f0 * specularMultiplier
+            px.diffuseOverPi = mk3(om * baseColor.x * inv.x * (1.0f / PI_F), om * baseColor.y * inv.y * (1.0f / PI_F), om * baseColor.z * inv.z * (1.0f / PI_F));
+            px.f0 = mk3(fma_(baseColor.x, metallic, f0s) * inv.x, fma_(baseColor.y, metallic, f0s) * inv.y, fma_(baseColor.z, metallic, f0s) * inv.z);
+            px.fogAo = __expf(-fc.fogDensity * distToCamera) * ambientOcclusion;
+        }
+
+        // ---- phase 2: shade the accepted VPLs in sample order (vpl_pbr_gi.fs:173-198) ----
+        f3 vplColor = mk3(0.0f);
+        float validSamples = 0.0f;
+        for (int s = 0; s < accepted; ++s) {
+            const uint32_t qw = s < 2 ? q0 : (s < 4 ? q1 : q2);
+            const int lightIndex = (int)((qw >> ((s & 1) * 16)) & 0xffffu);
+            const float4 pr = sPos[lightIndex], cf = sCol[lightIndex], se = sSpec[lightIndex];
+            const f3 lightPosition = mk3(pr.x, pr.y, pr.z);
+            const f3 lightMinusFrag = lightPosition - px.fragPos;
+            const int eb = __float_as_int(se.w);
+            SgiAtlasEntry entry; entry.index = eb >> 16; entry.layer = eb & 0xffff;
+            shadeAcceptedLight(px, lightPosition, lightMinusFrag, dotFast(lightMinusFrag, lightMinusFrag), pr.w, cf.w, mk3(cf.x, cf.y, cf.z), mk3(se.x, se.y, se.z),
+                               entry, shadowsOn, minGi, cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
+        }
+        validSamples = fmaxf(validSamples, 1.0f);
+        const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
+        storeHalf4(colorOut, p, color.x, color.y, color.z, 1.0f);
+        const unsigned short hr = f2h(fminf(vplColor.x, HALF_FLOAT_MAX)), hg = f2h(fminf(vplColor.y, HALF_FLOAT_MAX)), hb = f2h(fminf(vplColor.z, HALF_FLOAT_MAX)),
+                             ha = f2h(validSamples);
+        uint2 packed;
+        packed.x = (uint32_t)hr | ((uint32_t)hg << 16);
+        packed.y = (uint32_t)hb | ((uint32_t)ha << 16);
+        reservoirOut[p] = packed;
+        if (mergedOut != nullptr) {
+            // Denoise pass 0 on the binary16 reservoir just stored.  mergeCentreTexel (sgi_merge.cuh) reduces to rgb / max(1e-5, a)
+            // here: the normal is unit length, |z - z| = 0, and with a >= 1 and 1 <= V <= 4480 the single candidate's acceptance
+            // ratio probability / cw is x / x = 1 exactly, which every draw in [0,1) passes.  V <= 0 leaves the reservoir empty.
+            const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha));
+            const f3 m = V > 0 ? mk3(h2f(hr), h2f(hg), h2f(hb)) / denom : mk3(0.0f);
+            const uint2 mv = packHalf4(m.x, m.y, m.z, 1.0f);
+            mergedOut[p] = mv;
+            pushRes(links, y, x, bd.W, mv);
+        }
+    }
+}
+
 }  // namespace
 
 // CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
@@ -347,7 +534,29 @@ bool preloadGatherKernels() {
     cudaFuncAttributes a; bool ok = true;
     ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_STOCHASTIC>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_TILE_LIST>) == cudaSuccess;
+    // the persistent kernel keeps the VPL table in dynamic shared memory: up to 4480 x 48 B = 210 KB of the SM's 227 KB
+    ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytesTwoCtas) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SGI_MAX_TOTAL_VPLS_PER_FRAME * kTableBytesPerVpl) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, gatherStochasticKernel<512>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, gatherStochasticKernel<1024>) == cudaSuccess;
     return ok;
+}
+
+static int smCount() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+
+// SGI_GATHER_LEGACY=1 selects the one-CTA-per-32x8-pixels kernel with global-memory VPL reads (kept for A/B timing)
+static bool legacyGather() {
+    static const bool v = [] { const char* e = getenv("SGI_GATHER_LEGACY"); return e && e[0] == '1'; }();
+    return v;
 }
 
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
@@ -360,6 +569,20 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
         dim3 grid((bd.W + block.x - 1) / block.x, (bd.rows + block.y - 1) / block.y);
         gatherKernel<SGI_GATHER_TILE_LIST><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, tileLists, tilePos);
+    } else if (!legacyGather()) {
+        // persistent: every SM holds the table once (two 512-thread CTAs while two copies fit, else one 1024-thread CTA)
+        const int cap = max(1, min(fc.totalNumLights, SGI_MAX_TOTAL_VPLS_PER_FRAME));
+        const int bytes = cap * kTableBytesPerVpl;
+        const int units = ((bd.W + 31) / 32) * bd.rows;
+        if (bytes <= kTableBytesTwoCtas) {
+            const int grid = max(1, min(2 * smCount(), (units + 15) / 16));
+            gatherStochasticKernel<512><<<grid, 512, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+                                                                      colorOut, reservoirOut, guideOut, mergedOut, links, cap);
+        } else {
+            const int grid = max(1, min(smCount(), (units + 31) / 32));
+            gatherStochasticKernel<1024><<<grid, 1024, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, cap);
+        }
     } else {
         dim3 block(kGatherThreadsX, kGatherThreadsY);
         dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);

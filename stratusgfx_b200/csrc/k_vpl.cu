@@ -10,6 +10,7 @@
 // No host round trip: the atlas entry of each survivor is compacted on the device too.
 //
 // a2 replaces vpl_light_color.cs:41-76.
+#include <cstring>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -215,6 +216,15 @@ void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc) {
     for (int c = 0; c < 4; ++c) for (int i = 0; i < 16; ++i) fc->cascadeProjViews[c][i] = fp->cascadeProjViews[c][i];
     for (int c = 0; c < 3; ++c) for (int i = 0; i < 4; ++i) fc->cascadePlanes[c][i] = fp->cascadePlanes[c][i];
     fc->totalNumLights = fp->totalNumLights;
+    // seed.z of the gather's draw sequence: time, then `seed.z += 10000.0` in binary32 per draw (vpl_pbr_gi.fs:150)
+    volatile float seedZ = fp->time;
+    for (int k = 0; k < kGatherMaxDraws; ++k) {
+        const float z = seedZ;
+        uint32_t bits; std::memcpy(&bits, &z, sizeof(bits));
+        bits += (bits << 10u); bits ^= (bits >> 6u); bits += (bits << 3u); bits ^= (bits >> 11u); bits += (bits << 15u);     // hash(uint), common.glsl:183-190
+        fc->hashZ[k] = bits;
+        seedZ = z + 10000.0f;
+    }
 }
 
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,

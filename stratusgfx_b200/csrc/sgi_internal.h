@@ -38,6 +38,8 @@ struct BandLinks {
     int32_t* timeouts;
 };
 
+constexpr int kGatherMaxDraws = 12;   // draws of one pixel's VPL sequence: <= 6 samples + 5 re-draws (vpl_pbr_gi.fs:138-171)
+
 // uniforms in device-friendly form; passed by value as a __grid_constant__ kernel parameter
 struct FrameConsts {
     float invPV[16];
@@ -54,6 +56,9 @@ struct FrameConsts {
     float cascadeProjViews[4][16];
     float cascadePlanes[3][4];
     int   totalNumLights;
+    // hash(floatBitsToUint(time + 10000 k)) of the gather's k-th draw: the part of random(vec3(gl_FragCoord.xy, seed.z))
+    // that is the same for every pixel (common.glsl:199-214, vpl_pbr_gi.fs:149-150)
+    uint32_t hashZ[kGatherMaxDraws];
 };
 
 struct AtlasTable {
