@@ -19,7 +19,7 @@ HEADERS = ["sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", os.path.join("..",
 # -fmad=false: the integer outputs of this path hinge on float comparisons, so no mul+add may be
 # contracted behind the source's back (see csrc/sgi_math.cuh).  IEEE sqrt/div are nvcc defaults.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("SGI_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _newest(paths):

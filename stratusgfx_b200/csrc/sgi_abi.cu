@@ -135,6 +135,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
         h->ownStream = true;
     }
     if (cudaMalloc(&h->cullBallots, 512 * sizeof(uint32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMalloc((void**)&h->posRadius, SGI_MAX_TOTAL_VPLS_PER_FRAME * sizeof(float4)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc(&h->cullTicket, sizeof(unsigned int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
@@ -151,6 +152,7 @@ int sgi_destroy(SgiHandle h) {
     sgi::detachPeers(h);
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
+    if (h->posRadius) cudaFree(h->posRadius);
     if (h->cullTicket) cudaFree(h->cullTicket);
     if (h->pinnedCount) cudaFreeHost(h->pinnedCount);
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
@@ -229,9 +231,10 @@ int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     const BandDims bd = bandDims(h);
-    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch);
+    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch,
+                         h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->posRadius);
     // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
-    n += launchStage2(h->stream, bd, h->buf.vplStage1Results, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
+    n += launchStage2(h->stream, fc, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
     h->tileListsValid = true;
     return postLaunch(h, n);
 }

@@ -158,6 +158,7 @@ struct SgiHandle_ {
     void* history[2] = {nullptr, nullptr};    // half
     int cur = 0;
     int* patchScratch = nullptr;    // stage-1 -> stage-2 patch size classes (k_tiles.cu)
+    float4* posRadius = nullptr;         // [SGI_MAX_TOTAL_VPLS_PER_FRAME] (position, radius) of the compacted VPLs, packed by stage 1 for stage 2
     unsigned short* tilePos = nullptr;   // [tiles][12] per-tile lists as positions in the compacted VPL table (tile-list gather)
     bool tileListsValid = false;    // sgi_tile_lists ran since the last bind
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
@@ -205,9 +206,9 @@ int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);
 int patchScratchInts(const BandDims& bd);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
-                 SgiVplStage1PerTileOutputs* out, int* patchScratch);
-int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const SgiVplData* lightTable,
-                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, const int* patchScratch);
+                 SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius);
+int launchStage2(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
+                 const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, int* patchScratch);
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
