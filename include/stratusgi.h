@@ -195,7 +195,7 @@ typedef struct SgiHandle_* SgiHandle;
  * supplies the G-buffer there (it is an input), while the denoiser's reservoir / GI / history halo rows
  * are written by the neighbouring band's kernels directly into this handle's memory through NVLink peer
  * stores, followed by a release flag; the consumer pass waits on the flag in stream order.  The final
- * pass of every band also stores its lit rows into the root band's frame image (the "gather").
+ * lit rows of every band end up in the root band's frame image (the "gather").
  * Handles may live in one process (peer access) or one process per GPU (CUDA IPC). */
 #define SGI_HALO_ROWS 20   /* >= 16 = reach of the widest reference à-trous pass (2*(multiplier+1), BE:1920), on the 5-row tile grid */
 enum { SGI_PEER_UP = 0 /* band rank-1 */, SGI_PEER_DOWN = 1 /* band rank+1 */, SGI_PEER_ROOT = 2 /* owner of the frame image */ };
@@ -242,8 +242,11 @@ int  sgi_frame(SgiHandle h, const SgiFrameParams* fp);
 
 /* row bands with peer-to-peer halos: set up (re-allocates the shared planes), export, attach neighbours / root.
  * After sgi_band_setup every stage entry point computes only the band's rows, pushes its boundary rows to the
- * attached neighbours and orders itself against them with device-side flags; sgi_frame_image returns the assembled
- * image of the last completed frame on the owner (stream-ordered: the owner's stream has already waited for all bands). */
+ * attached neighbours and orders itself against them with device-side flags.  A band's lit rows travel to the owner's
+ * frame image after its final pass (copy engine, overlapping the next frame; two images alternate by frame parity), and
+ * the owner's stream waits for them one frame late.  sgi_frame_image makes the owner's stream wait for every band's rows
+ * of the last frame started on the handle and returns that image (stream-ordered; every band must have been given the
+ * frame, and sgi_synchronize on a band also drains its transfer). */
 int  sgi_band_setup(SgiHandle h, const SgiBandParams* bp);
 int  sgi_band_export(SgiHandle h, SgiPeerInfo* out);
 int  sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer);

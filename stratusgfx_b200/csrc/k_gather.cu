@@ -356,6 +356,7 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 constexpr int kMaxSamples = 6;                // int(mix(2, 10, 1 - max(roughness, 0.5))) <= 6 (vpl_pbr_gi.fs:138-143)
 constexpr int kMaxResamples = 5;              // vpl_pbr_gi.fs:164-171
 constexpr int kMaxDraws = kMaxSamples + kMaxResamples;
+constexpr int kUnitChunk = 2;                 // 32-pixel row segments a warp takes per fetch from the work counter
 static_assert(kMaxDraws <= kGatherMaxDraws, "FrameConsts::hashZ is too short");
 
 SGI_DEV void bandWaitWarp(const BandLinks& L, bool needUp, bool needDown) {
@@ -381,7 +382,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
                        const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
                        const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
                        uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
-                       const __grid_constant__ BandLinks links, int tableCap) {
+                       const __grid_constant__ BandLinks links, int tableCap, int* __restrict__ unitCounters, int counterSel) {
     extern __shared__ float4 sTab[];
     float4* __restrict__ sPos = sTab;                       // (position, radius)
     float4* __restrict__ sCol = sTab + tableCap;            // (colour, farPlane)
@@ -401,7 +402,6 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     const int lane = threadIdx.x & 31;
     const int unitsX = (bd.W + 31) >> 5;
     const int units = unitsX * bd.rows;
-    const int warpStride = gridDim.x * (THREADS / 32);
     const int cubeRes = bd.cubeRes;
     const int texelsPerLayer = 6 * cubeRes * cubeRes;
     const m4 invPV = loadMat(fc.invPV);
@@ -410,9 +410,23 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     const float minGi = fc.minGiOcclusionFactor;
     const int lastStaged = max(staged - 1, 0);
 
-    for (int unit = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); unit < units; unit += warpStride) {
-        const int ly = unit / unitsX;
-        const int x = (unit - ly * unitsX) * 32 + lane;
+    // Warps fetch 32-pixel row segments from a global counter, kUnitChunk at a time, so the kernel finishes on time even when not
+    // all of its CTAs are resident from the start (sgi_frame runs the tile-list stages next to it on a side stream).  Counter
+    // [frame & 1] serves this launch; the other one is re-armed for the next launch on this stream.
+    int* __restrict__ counter = unitCounters + (counterSel & 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) unitCounters[(counterSel & 1) ^ 1] = 0;
+    int unit = 0, unitEnd = 0;
+    while (true) {
+        if (unit >= unitEnd) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(counter, kUnitChunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= units) break;
+            unit = base; unitEnd = min(base + kUnitChunk, units);
+        }
+        const int thisUnit = unit++;
+        const int ly = thisUnit / unitsX;
+        const int x = (thisUnit - ly * unitsX) * 32 + lane;
         const int y = ly + bd.yOffset;
         // row bands: a warp that will store pass-0 rows into a neighbour's halo first waits until that neighbour has finished
         // the previous frame (its final pass read those halo rows)
@@ -563,7 +577,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
-                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos) {
+                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int counterSel) {
     if (tileLists != nullptr) {
         dim3 block(kTileCtaX * SGI_TILE_DIVISOR, kTileCtaY * SGI_TILE_DIVISOR);
         dim3 grid((bd.W + block.x - 1) / block.x, (bd.rows + block.y - 1) / block.y);
@@ -577,11 +591,11 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
         if (bytes <= kTableBytesTwoCtas) {
             const int grid = max(1, min(2 * smCount(), (units + 15) / 16));
             gatherStochasticKernel<512><<<grid, 512, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                      colorOut, reservoirOut, guideOut, mergedOut, links, cap);
+                                                                      colorOut, reservoirOut, guideOut, mergedOut, links, cap, unitCounters, counterSel);
         } else {
             const int grid = max(1, min(smCount(), (units + 31) / 32));
             gatherStochasticKernel<1024><<<grid, 1024, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, cap);
+                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, cap, unitCounters, counterSel);
         }
     } else {
         dim3 block(kGatherThreadsX, kGatherThreadsY);

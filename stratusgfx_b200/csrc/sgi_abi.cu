@@ -7,6 +7,7 @@
 // with the fence + map round trip (:1609-1610, :1675-1701) removed: everything is enqueued on
 // one stream and nothing blocks the host.  There is no CPU fallback anywhere in this library.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "sgi_internal.h"
@@ -134,9 +135,23 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
         if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
         h->ownStream = true;
     }
+    {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return bail(SGI_ERR_CUDA);      // lo = least priority
+        const char* e = getenv("SGI_TILE_STREAM_PRIO");          // "equal": same priority as a default stream (A/B timing)
+        if (e && e[0] == 'e') lo = 0;
+        if (cudaStreamCreateWithPriority(&h->tileStream, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evFinal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evCopyDone, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    }
     if (cudaMalloc(&h->cullBallots, 512 * sizeof(uint32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->posRadius, SGI_MAX_TOTAL_VPLS_PER_FRAME * sizeof(float4)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc(&h->cullTicket, sizeof(unsigned int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMalloc((void**)&h->gatherCounters, 2 * sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMemsetAsync(h->gatherCounters, 0, 2 * sizeof(int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (!(preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels())) return bail(SGI_ERR_CUDA);
@@ -149,11 +164,18 @@ int sgi_destroy(SgiHandle h) {
     if (!h) return SGI_ERR_INVALID_ARG;
     cudaSetDevice(h->cp.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->tileStream) { cudaStreamSynchronize(h->tileStream); cudaStreamDestroy(h->tileStream); }
+    if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
+    if (h->evFinal) cudaEventDestroy(h->evFinal);
+    if (h->evCopyDone) cudaEventDestroy(h->evCopyDone);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     sgi::detachPeers(h);
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
     if (h->posRadius) cudaFree(h->posRadius);
     if (h->cullTicket) cudaFree(h->cullTicket);
+    if (h->gatherCounters) cudaFree(h->gatherCounters);
     if (h->pinnedCount) cudaFreeHost(h->pinnedCount);
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -223,7 +245,7 @@ int sgi_color(SgiHandle h, const SgiFrameParams* fp) {
     return postLaunch(h, n);
 }
 
-int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
+static int tileListsOn(SgiHandle h, const SgiFrameParams* fp, cudaStream_t stream) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
     NEED(h, depth); NEED(h, normal); NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, vplStage1Results); NEED(h, vplVisiblePerTile);
     if (h->cp.width % SGI_TILE_DIVISOR || h->cp.rows % SGI_TILE_DIVISOR || h->cp.y_offset % SGI_TILE_DIVISOR)
@@ -231,13 +253,15 @@ int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) {
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     const BandDims bd = bandDims(h);
-    int n = launchStage1(h->stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch,
+    int n = launchStage1(stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch,
                          h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->posRadius);
     // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
-    n += launchStage2(h->stream, fc, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
+    n += launchStage2(stream, fc, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
     h->tileListsValid = true;
     return postLaunch(h, n);
 }
+
+int sgi_tile_lists(SgiHandle h, const SgiFrameParams* fp) { return h ? tileListsOn(h, fp, h->stream) : SGI_ERR_INVALID_ARG; }
 
 int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
@@ -266,7 +290,8 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
-                               fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos);
+                               fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
+                               h->gatherCounters, (int)(h->gatherLaunches++ & 1));
     if (h->banded && fuse) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it
@@ -319,10 +344,32 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         // (inside the kernel, by the CTAs whose taps reach the halo; interior CTAs start at once)
         io.links = sgi::bandLinks(h, pass % 2, final_, pass >= 1 ? sgi::bandEpoch(h->frameNo, pass) : 0);
     }
+    const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && !sgi::imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached &&
+                         h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
+    if (copyOut && h->copyPending) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evCopyDone, 0));   // the previous frame's rows have left `combined`
     n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
     if (h->banded) {
         n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
-        if (final_ && h->band.owns_frame_image) n += sgi::waitAllBands(h);     // the assembled frame image is complete from here on
+        if (copyOut) {
+            // the band's lit rows -> the owner's frame image of this parity, by the copy engine, then this band's flag in the
+            // owner's slab; both on the copy stream, so the next frame starts at once on the main stream
+            const SgiHandle_::Peer& root = h->peer[SGI_PEER_ROOT];
+            const size_t rowBytes = (size_t)h->cp.width * 8;
+            const char* src = (const char*)io.combinedOut + (size_t)(h->band.compute_y0 - h->cp.y_offset) * rowBytes;
+            char* dst = root.base + root.info.off_image[(int)(h->frameNo & 1)] + (size_t)h->band.compute_y0 * rowBytes;
+            SGI_CUDA(h, cudaEventRecord(h->evFinal, h->stream));
+            SGI_CUDA(h, cudaStreamWaitEvent(h->copyStream, h->evFinal, 0));
+            SGI_CUDA(h, cudaMemcpyAsync(dst, src, (size_t)h->band.compute_rows * rowBytes, cudaMemcpyDeviceToDevice, h->copyStream));
+            n += sgi::launchSignal(h->copyStream, nullptr, nullptr, 0, (int32_t*)(root.base + root.info.off_flags) + 8 + h->band.rank, (int)(uint32_t)h->frameNo);
+            SGI_CUDA(h, cudaEventRecord(h->evCopyDone, h->copyStream));
+            h->copyPending = true;
+        }
+        // the owner waits for the PREVIOUS frame's rows here (they travelled during this frame); sgi_frame_image waits for
+        // the current frame's
+        if (final_ && h->band.owns_frame_image && h->frameNo > 1 && h->imageWaitedFrame < h->frameNo - 1) {
+            n += sgi::waitAllBands(h, h->frameNo - 1);
+            h->imageWaitedFrame = h->frameNo - 1;
+        }
     }
     if (final_) { h->cur ^= 1; h->guideValid = false; }   // swap with the previous-frame FBO (BE:1949-1951)
     return postLaunch(h, n);
@@ -349,9 +396,25 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         if ((rc = sgi_cull(h, fp)) != SGI_OK) return rc;
         if ((rc = sgi_color(h, fp)) != SGI_OK) return rc;
     }
-    if (h->buf.vplStage1Results && h->buf.vplVisiblePerTile) { if ((rc = sgi_tile_lists(h, fp)) != SGI_OK) return rc; }
+    const bool lists = h->buf.vplStage1Results && h->buf.vplVisiblePerTile;
+    // The stochastic gather (the reference's live shader) and the denoiser do not read the per-tile lists, so the two tile
+    // stages run on a low-priority side stream next to them: forked here, joined at the end of the frame.  Their long,
+    // thinly populated tail (a few loose patches) then overlaps with the gather instead of idling the SMs.  The tile-list
+    // gather consumes the lists, so that mode stays serial.  SGI_SERIAL_TILE_LISTS=1 keeps everything on one stream.
+    static const bool serialLists = [] { const char* e = getenv("SGI_SERIAL_TILE_LISTS"); return e && e[0] == '1'; }();
+    const bool fork = lists && fp->gatherMode == SGI_GATHER_STOCHASTIC && !serialLists;
+    if (lists && !fork) { if ((rc = sgi_tile_lists(h, fp)) != SGI_OK) return rc; }
+    if (fork) {
+        SGI_CUDA(h, cudaSetDevice(h->cp.device));
+        SGI_CUDA(h, cudaEventRecord(h->evFork, h->stream));
+        SGI_CUDA(h, cudaStreamWaitEvent(h->tileStream, h->evFork, 0));
+        if ((rc = tileListsOn(h, fp, h->tileStream)) != SGI_OK) return rc;
+        SGI_CUDA(h, cudaEventRecord(h->evJoin, h->tileStream));
+    }
     if ((rc = sgi_gather(h, fp)) != SGI_OK) return rc;
-    return sgi_denoise(h, fp);
+    rc = sgi_denoise(h, fp);
+    if (fork) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+    return rc;
 }
 
 int sgi_visible_count(SgiHandle h, int32_t* out_count) {
@@ -411,6 +474,8 @@ int sgi_synchronize(SgiHandle h) {
     if (!h) return SGI_ERR_INVALID_ARG;
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->tileStream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->copyStream));
     return SGI_OK;
 }
 

@@ -17,6 +17,7 @@
 // which applies pass 0 itself); stage denoise_iters = the band's frame is complete.  Write-after-read hazards are
 // covered by the same flags: a band's pass p+2 overwrites the halo rows its neighbour's pass p+1 read, and it has
 // waited for the neighbour's pass p+1 flag by then; the next frame's gather waits for the neighbours' frame-complete flag.
+#include <cstdlib>
 #include <cstring>
 #include <unistd.h>
 #include "sgi_internal.h"
@@ -113,7 +114,7 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
     if (final_) {
         const int parity = (int)(h->frameNo & 1);
         if (h->band.owns_frame_image) L.image = (uint2*)h->frameImage[parity];
-        else if (h->peer[SGI_PEER_ROOT].attached && h->peer[SGI_PEER_ROOT].info.off_image[parity] >= 0)
+        else if (imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached && h->peer[SGI_PEER_ROOT].info.off_image[parity] >= 0)
             L.image = (uint2*)(h->peer[SGI_PEER_ROOT].base + h->peer[SGI_PEER_ROOT].info.off_image[parity]);
     }
     return L;
@@ -134,13 +135,21 @@ int signalNeighbours(SgiHandle_* h, int epoch, bool final_) {
     int32_t* c = nullptr;
     if (final_) {
         if (h->band.owns_frame_image) c = h->flags + 8 + h->band.rank;
-        else if (int32_t* root = peerFlags(h, SGI_PEER_ROOT)) c = root + 8 + h->band.rank;
+        else if (imagePushByKernel()) { if (int32_t* root = peerFlags(h, SGI_PEER_ROOT)) c = root + 8 + h->band.rank; }
     }
     return launchSignal(h->stream, a, b, epoch, c, (int)(uint32_t)h->frameNo);
 }
 
-int waitAllBands(SgiHandle_* h) {
-    return launchWaitAllBands(h->stream, h->flags + 8, h->band.world, (int)(uint32_t)h->frameNo, h->flags + 2);
+int waitAllBands(SgiHandle_* h, int64_t frameNo) {
+    return launchWaitAllBands(h->stream, h->flags + 8, h->band.world, (int)(uint32_t)frameNo, h->flags + 2);
+}
+
+// SGI_IMAGE_PUSH=kernel: the final pass of every band stores its lit rows into the owner's frame image itself (NVLink peer
+// stores); default: a copy-engine transfer after the final pass (sgi_abi.cu), which keeps 7/8 of the frame's bytes converging
+// on one GPU out of the final pass's critical path
+bool imagePushByKernel() {
+    static const bool v = [] { const char* e = getenv("SGI_IMAGE_PUSH"); return e && e[0] == 'k'; }();
+    return v;
 }
 
 void detachPeers(SgiHandle_* h) {
@@ -186,7 +195,10 @@ int sgi_band_setup(SgiHandle h, const SgiBandParams* bp) {
     }
     SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
     SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
+    SGI_CUDA_B(h, cudaStreamSynchronize(h->copyStream));
     detachPeers(h);
+    h->copyPending = false;
+    h->imageWaitedFrame = h->frameNo;       // the new slab's flags start at zero: nothing earlier to wait for
     h->banded = true;
     h->band = *bp;
     return sgiAllocPlanesForBand(h);
@@ -247,7 +259,15 @@ int sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer) {
 int sgi_frame_image(SgiHandle h, void** out_ptr, int64_t* out_bytes) {
     if (!h || !out_ptr) return SGI_ERR_INVALID_ARG;
     if (!h->banded || !h->band.owns_frame_image) { h->lastError = "sgi_frame_image: this handle does not own the frame image"; return SGI_ERR_INVALID_ARG; }
-    *out_ptr = h->frameImage[(int)(h->frameNo & 1)];       // the image of the last frame started on this handle
+    // the owner's stream waits here for every band's rows of the last frame started on this handle (the wait at the end of
+    // a frame is for the frame before it, so that the transfers overlap the next frame)
+    if (h->frameNo > 0 && h->imageWaitedFrame < h->frameNo) {
+        SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
+        h->launches += sgi::waitAllBands(h, h->frameNo);
+        h->imageWaitedFrame = h->frameNo;
+        SGI_CUDA_B(h, cudaGetLastError());
+    }
+    *out_ptr = h->frameImage[(int)(h->frameNo & 1)];
     if (out_bytes) *out_bytes = (int64_t)h->cp.width * h->cp.full_height * 8;
     return SGI_OK;
 }

@@ -148,6 +148,16 @@ struct SgiHandle_ {
     bool ownStream = false;
     int64_t launches = 0;
     std::string lastError;
+    // sgi_frame runs the tile-list stages on this low-priority side stream next to the stochastic gather + denoiser (which do
+    // not read the lists): forked after the cull, joined at the end of the frame
+    cudaStream_t tileStream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // row bands: a non-owner band sends its lit rows to the owner's frame image with a copy-engine transfer on this stream
+    // after its final pass (the transfer overlaps the next frame), then raises its flag in the owner's slab
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evFinal = nullptr, evCopyDone = nullptr;
+    bool copyPending = false;
+    int64_t imageWaitedFrame = 0;   // owner: last frame whose image the stream has waited for
     // library-owned planes
     void* giColor = nullptr;        // half4
     void* giReservoir = nullptr;    // half4
@@ -176,6 +186,8 @@ struct SgiHandle_ {
     struct Peer { bool attached = false; bool ipc = false; char* base = nullptr; SgiPeerInfo info{}; } peer[3];
     int64_t frameNo = 0;            // frames started through sgi_gather since creation (band epochs)
     // scratch for the cull
+    int* gatherCounters = nullptr;  // two work counters of the persistent gather, used alternately (k_gather.cu)
+    int64_t gatherLaunches = 0;
     uint32_t* cullBallots = nullptr;
     unsigned int* cullTicket = nullptr;
     int32_t* pinnedCount = nullptr;
@@ -198,7 +210,8 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch);   
 inline int bandEpoch(int64_t frameNo, int stage) { return (int)(uint32_t)(frameNo * 32 + stage); }   // stage k: output of pass k-1 pushed
 int waitNeighbours(SgiHandle_* h, int epoch);
 int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
-int waitAllBands(SgiHandle_* h);
+int waitAllBands(SgiHandle_* h, int64_t frameNo);
+bool imagePushByKernel();
 void detachPeers(SgiHandle_* h);
 constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [8+r] band r's image rows landed
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
@@ -213,7 +226,8 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
-                 const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos);
+                 const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos,
+                 int* unitCounters /* two ints: work counters of the persistent gather */, int counterSel);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
 

@@ -220,7 +220,13 @@ class VplGiPass:
         """Owner band only: the assembled frame image of the last frame as a torch view (half [H, W, 4]) of library memory."""
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self._check(self.L.sgi_frame_image(self._h, C.byref(ptr), C.byref(nbytes)))
+        self.synchronize()          # the view is read on torch's stream: the pass's stream has now waited for every band's rows
         return _DeviceView(self.torch, ptr.value, (self.full_height, self.width, 4), self.device).tensor
+
+    def frame_image_wait(self):
+        """Owner band only: make the pass's stream wait for every band's rows of the last frame (no host synchronisation)."""
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._check(self.L.sgi_frame_image(self._h, C.byref(ptr), C.byref(nbytes)))
 
     def visible_count(self):
         n = C.c_int32()
