@@ -184,7 +184,36 @@ typedef struct SgiBuffers {
     const void* diffuseCubeMaps[SGI_MAX_TOTAL_SHADOW_ATLASES];
     /* frame_->csc.fbo depth attachment (BE:348-352) */
     const void* infiniteLightShadowMap;
+    /* optional: device int32 holding the number of valid entries of vplData (written by sgi_vpl_prepass).  When bound,
+     * the cull uses min(totalNumLights, *vplCountDevice), so the host passes an upper bound and never reads N back. */
+    const int32_t* vplCountDevice;
 } SgiBuffers;
+
+/* ---- VPL pre-pass: the CPU loop of UpdatePointLights_ (BE:1359-1392) and InitVplFrameData_
+ *      (BE:1281-1292) on the device ----------------------------------------------------------------------------------------
+ * What the engine keeps per VirtualPointLight (position, radius, far plane, intensity: Source/Engine/StratusLight.h) plus
+ * the slot its cube maps occupy in the shadow-map cache. */
+typedef struct SgiLightRecord {
+    float   position[3];
+    float   radius;
+    float   farPlane;
+    float   intensity;
+    int32_t atlasIndex;        /* GpuAtlasEntry of the light's cube maps (StratusGpuCommon.h:276-279) */
+    int32_t atlasLayer;
+} SgiLightRecord;
+
+#define SGI_MAX_PREPASS_LIGHTS 262144
+
+typedef struct SgiPrepassParams {
+    float   viewPosition[3];           /* c.GetPosition() (BE:1360)                                                   */
+    int32_t numLights;                 /* virtual point lights of the frame, <= SGI_MAX_PREPASS_LIGHTS                */
+    float   frustumPlanes[6][4];       /* frame_->viewFrustumPlanes, IsSphereInFrustum (StratusMath.h:401-412)        */
+    const SgiLightRecord* lights;      /* device [numLights]                                                          */
+    SgiVplData*    vplDataOut;         /* device [min(numLights, 10000)]: the table InitVplFrameData_ uploads         */
+    SgiAtlasEntry* atlasEntryOut;      /* device, same length, or NULL: atlasEntryByVpl for the cull                  */
+    int32_t*       orderOut;           /* device, same length, or NULL: index into `lights` of output i               */
+    int32_t*       countOut;           /* device int32: N = min(lights in the frustum, 10000)                         */
+} SgiPrepassParams;
 
 typedef struct SgiHandle_* SgiHandle;
 
@@ -229,6 +258,12 @@ int  sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers);
 /* GL-interop hand-over (GLuint names).  Returns SGI_ERR_UNSUPPORTED when the
  * library was built without GL headers (this image has none). */
 int  sgi_register_gl(SgiHandle h, const uint32_t* gl_names, int32_t count);
+
+/* VPL pre-pass: lights whose sphere touches the view frustum, ordered by distance to the viewer (equal distances keep
+ * their input order, as std::multiset insertion does), the nearest 10000 written as the cull's input table.  Stream-ordered;
+ * bind countOut as SgiBuffers.vplCountDevice and pass totalNumLights = min(numLights, 10000) to run a frame without
+ * reading N back. */
+int  sgi_vpl_prepass(SgiHandle h, const SgiPrepassParams* pp);
 
 /* stage entry points; all stream-ordered, none blocks the host */
 int  sgi_cull(SgiHandle h, const SgiFrameParams* fp);          /* viscull_vpls.cs (a1)               */

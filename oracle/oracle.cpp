@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cmath>
+#include <set>
 #include <vector>
 #include <omp.h>
 #include "vm.h"
@@ -342,6 +343,41 @@ int orc_cull(const SgiFrameParams* fp, const OrcDims* dm, const SgiVplData* ligh
     }
     vplVisibleIndex[0] = count > SGI_MAX_TOTAL_VPLS_PER_FRAME ? SGI_MAX_TOTAL_VPLS_PER_FRAME : count;
     return 0;
+}
+
+// f1: the virtual-point-light branch of UpdatePointLights_ (StratusRendererBackend.cpp:1359-1392)
+// and InitVplFrameData_ (:1281-1292).  The reference inserts VplDistKey_(light, distance) into a std::multiset ordered by the
+// distance alone (StratusRendererBackend.h:602-623) and copies its first MAX_TOTAL_VPLS_BEFORE_CULLING entries.
+int orc_vpl_prepass(const SgiLightRecord* lights, int n, const float* viewPosition, const float* frustumPlanes /* [6][4] */,
+                    SgiVplData* vplDataOut, SgiAtlasEntry* atlasEntryOut, int32_t* orderOut) {
+    struct Key { int light; double distance; };
+    struct Less { bool operator()(const Key& l, const Key& r) const { return l.distance < r.distance; } };
+    std::multiset<Key, Less> perVPLDistToViewerSet;
+    const vec3 c(viewPosition[0], viewPosition[1], viewPosition[2]);
+    for (int i = 0; i < n; ++i) {
+        const vec3 position(lights[i].position[0], lights[i].position[1], lights[i].position[2]);
+        const double distance = length(position - c);                        // glm::distance(p0, p1) = length(p1 - p0)
+        bool inFrustum = true;                                               // IsSphereInFrustum, StratusMath.h:401-412
+        for (int k = 0; k < 6; ++k) {
+            const vec4 g(frustumPlanes[4 * k], frustumPlanes[4 * k + 1], frustumPlanes[4 * k + 2], frustumPlanes[4 * k + 3]);
+            const float d = dot(g, vec4(position, 1.0f));
+            if (d < -lights[i].radius) { inFrustum = false; break; }
+        }
+        if (inFrustum) perVPLDistToViewerSet.insert(Key{i, distance});
+    }
+    int count = 0;
+    for (const Key& entry : perVPLDistToViewerSet) {
+        const SgiLightRecord& L = lights[entry.light];
+        SgiVplData data;
+        std::memset(&data, 0, sizeof(data));
+        data.position[0] = L.position[0]; data.position[1] = L.position[1]; data.position[2] = L.position[2]; data.position[3] = 1.0f;
+        data.farPlane = L.farPlane; data.radius = L.radius; data.intensity = L.intensity;
+        vplDataOut[count] = data;
+        if (atlasEntryOut) { atlasEntryOut[count].index = L.atlasIndex; atlasEntryOut[count].layer = L.atlasLayer; }
+        if (orderOut) orderOut[count] = entry.light;
+        if (++count >= SGI_MAX_TOTAL_VPLS_BEFORE_CULLING) break;              // `if (size() >= capacity()) break;` (:1387)
+    }
+    return count;
 }
 
 // a2: vpl_light_color.cs:41-76

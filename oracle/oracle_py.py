@@ -81,6 +81,7 @@ def lib(variant="own"):
         L.orc_gather_tiles.argtypes = [C.c_void_p] * 16
         L.orc_stage2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_denoise_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_vpl_prepass.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _libs[variant] = L
     return _libs[variant]
 
@@ -96,6 +97,21 @@ def _atlas_ptrs(arr):
     for a in range(arr.shape[0]):
         tab[a] = arr.ctypes.data + a * stride
     return tab
+
+
+def vpl_prepass(lights, view_position, frustum_planes, variant="own"):
+    """UpdatePointLights_ (virtual point lights) + InitVplFrameData_ on the CPU (orc_vpl_prepass).
+    lights: numpy array of stratusgfx_b200.prepass.LIGHT_DTYPE.  Returns (vplData [N,16] f32, atlas [N,2] i32, order [N] i32)."""
+    n = int(lights.shape[0])
+    cap = max(1, min(n, 10000))
+    vd = np.zeros((cap, 16), np.float32)
+    at = np.zeros((cap, 2), np.int32)
+    order = np.zeros(cap, np.int32)
+    vp = np.ascontiguousarray(view_position, np.float32)
+    fr = np.ascontiguousarray(frustum_planes, np.float32).reshape(6, 4)
+    lights = np.ascontiguousarray(lights)
+    count = lib(variant).orc_vpl_prepass(_p(lights), n, _p(vp), _p(fr), _p(vd), _p(at), _p(order))
+    return vd[:count], at[:count], order[:count]
 
 
 class OracleFrame:

@@ -68,7 +68,21 @@ class Buffers(C.Structure):
                 ("atlasEntryByVpl", C.c_void_p),
                 ("shadowCubeMaps", C.c_void_p * MAX_TOTAL_SHADOW_ATLASES),
                 ("diffuseCubeMaps", C.c_void_p * MAX_TOTAL_SHADOW_ATLASES),
-                ("infiniteLightShadowMap", C.c_void_p)]
+                ("infiniteLightShadowMap", C.c_void_p), ("vplCountDevice", C.c_void_p)]
+
+
+MAX_PREPASS_LIGHTS = 262144
+
+
+class LightRecord(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("radius", C.c_float), ("farPlane", C.c_float), ("intensity", C.c_float),
+                ("atlasIndex", C.c_int32), ("atlasLayer", C.c_int32)]
+
+
+class PrepassParams(C.Structure):
+    _fields_ = [("viewPosition", C.c_float * 3), ("numLights", C.c_int32), ("frustumPlanes", (C.c_float * 4) * 6),
+                ("lights", C.c_void_p), ("vplDataOut", C.c_void_p), ("atlasEntryOut", C.c_void_p), ("orderOut", C.c_void_p),
+                ("countOut", C.c_void_p)]
 
 
 HALO_ROWS = 20
@@ -90,7 +104,7 @@ class PeerInfo(C.Structure):
 ABI_SYMBOLS = [
     "sgi_create", "sgi_destroy", "sgi_resize", "sgi_bind_device_buffers", "sgi_register_gl",
     "sgi_band_setup", "sgi_band_export", "sgi_band_attach", "sgi_frame_image", "sgi_band_timeouts",
-    "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
+    "sgi_vpl_prepass", "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
     "sgi_visible_count", "sgi_get_plane", "sgi_download_plane", "sgi_reset_history", "sgi_synchronize", "sgi_stream",
     "sgi_launch_count", "sgi_last_error", "sgi_version",
 ]

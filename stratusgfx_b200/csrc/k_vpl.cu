@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(kCullThreads)
 cullKernel(const __grid_constant__ FrameConsts fc, int csmRes, int cubeRes, const SgiVplData* __restrict__ lightData,
            const SgiAtlasEntry* __restrict__ atlasByVpl, const float* __restrict__ csm, SgiVplData* __restrict__ updated,
            int32_t* __restrict__ visible, SgiAtlasEntry* __restrict__ entries, uint32_t* __restrict__ ballots,
-           unsigned int* __restrict__ ticket, const __grid_constant__ AtlasTable atlases, int colorToo) {
-    const int N = fc.totalNumLights;
+           unsigned int* __restrict__ ticket, const __grid_constant__ AtlasTable atlases, int colorToo, const int32_t* __restrict__ countDevice) {
+    // the host's N may be an upper bound when the table was built on the device (sgi_vpl_prepass)
+    const int N = countDevice != nullptr ? max(0, min(fc.totalNumLights, __ldg(countDevice))) : fc.totalNumLights;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int index = blockIdx.x * 32 + warp;                  // one warp per VPL
     __shared__ int sVis[32];
@@ -229,13 +230,13 @@ void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc) {
 
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
                const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket,
-               const AtlasTable* colorAtlases) {
+               const AtlasTable* colorAtlases, const int32_t* countDevice) {
     const int N = fc.totalNumLights;
     const int blocks = N > 0 ? (N + 31) / 32 : 1;
     AtlasTable none;
     for (int i = 0; i < SGI_MAX_TOTAL_SHADOW_ATLASES; ++i) { none.shadow[i] = nullptr; none.diffuse[i] = nullptr; }
     cullKernel<<<blocks, kCullThreads, 0, stream>>>(fc, bd.csmRes, bd.cubeRes, lightData, atlasByVpl, csm, updated, visible, entries, ballots, ticket,
-                                                    colorAtlases ? *colorAtlases : none, colorAtlases ? 1 : 0);
+                                                    colorAtlases ? *colorAtlases : none, colorAtlases ? 1 : 0, countDevice);
     return 1;
 }
 

@@ -154,7 +154,8 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (cudaMemsetAsync(h->gatherCounters, 0, 2 * sizeof(int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
-    if (!(preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels())) return bail(SGI_ERR_CUDA);
+    if (cudaMalloc((void**)&h->prepassInside, sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels())) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
     *out = h;
     return SGI_OK;
@@ -176,6 +177,8 @@ int sgi_destroy(SgiHandle h) {
     if (h->posRadius) cudaFree(h->posRadius);
     if (h->cullTicket) cudaFree(h->cullTicket);
     if (h->gatherCounters) cudaFree(h->gatherCounters);
+    if (h->prepassKeys) cudaFree(h->prepassKeys);
+    if (h->prepassInside) cudaFree(h->prepassInside);
     if (h->pinnedCount) cudaFreeHost(h->pinnedCount);
     if (h->ownStream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -230,8 +233,24 @@ static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo) {
     const AtlasTable atl = atlasTable(h);
     const int n = launchCull(h->stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
                              h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket,
-                             colorToo ? &atl : nullptr);
+                             colorToo ? &atl : nullptr, h->buf.vplCountDevice);
     return postLaunch(h, n);
+}
+
+int sgi_vpl_prepass(SgiHandle h, const SgiPrepassParams* pp) {
+    if (!h || !pp) return SGI_ERR_INVALID_ARG;
+    if (pp->numLights < 0 || pp->numLights > SGI_MAX_PREPASS_LIGHTS) return fail(h, SGI_ERR_INVALID_ARG, "sgi_vpl_prepass: numLights out of range");
+    if (!pp->countOut || (pp->numLights > 0 && (!pp->lights || !pp->vplDataOut))) return fail(h, SGI_ERR_NOT_BOUND, "sgi_vpl_prepass: lights, vplDataOut and countOut are required");
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    if (pp->numLights > h->prepassCap) {                      // grow the key scratch (stream-ordered with respect to its last use)
+        SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->prepassKeys) cudaFree(h->prepassKeys);
+        h->prepassKeys = nullptr; h->prepassCap = 0;
+        const int cap = ((pp->numLights + 4095) / 4096) * 4096;
+        SGI_CUDA(h, cudaMalloc((void**)&h->prepassKeys, (size_t)cap * sizeof(unsigned long long)));
+        h->prepassCap = cap;
+    }
+    return postLaunch(h, launchPrepass(h->stream, *pp, h->prepassKeys, h->prepassInside));
 }
 
 int sgi_cull(SgiHandle h, const SgiFrameParams* fp) { return cullImpl(h, fp, false); }

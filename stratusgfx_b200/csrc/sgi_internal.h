@@ -186,6 +186,9 @@ struct SgiHandle_ {
     struct Peer { bool attached = false; bool ipc = false; char* base = nullptr; SgiPeerInfo info{}; } peer[3];
     int64_t frameNo = 0;            // frames started through sgi_gather since creation (band epochs)
     // scratch for the cull
+    unsigned long long* prepassKeys = nullptr;   // [prepassCap] sort keys of the VPL pre-pass (k_prepass.cu), grown on demand
+    int prepassCap = 0;
+    int* prepassInside = nullptr;   // lights inside the frustum (before the 10000 cap)
     int* gatherCounters = nullptr;  // two work counters of the persistent gather, used alternately (k_gather.cu)
     int64_t gatherLaunches = 0;
     uint32_t* cullBallots = nullptr;
@@ -196,12 +199,14 @@ struct SgiHandle_ {
 namespace sgi {
 
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
+bool preloadPrepassKernels(); int launchPrepass(cudaStream_t stream, const SgiPrepassParams& pp, unsigned long long* keys, int* inside);
 bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels(); bool preloadDenoiseKernels(); bool preloadBandKernels();
 
 // each launcher enqueues its kernels on `stream` and returns the number of launches made
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
                const float* csm, SgiVplData* updated, int32_t* visible, SgiAtlasEntry* entries, uint32_t* ballots, unsigned int* ticket,
-               const AtlasTable* colorAtlases /* non-null: the cull's last CTA also runs the colouring stage */);
+               const AtlasTable* colorAtlases /* non-null: the cull's last CTA also runs the colouring stage */,
+               const int32_t* countDevice /* non-null: N = min(totalNumLights, *countDevice) */);
 int launchColor(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, SgiVplData* updated, const int32_t* visible,
                 const SgiAtlasEntry* entries, const AtlasTable& atlases);
 // ---- row bands (sgi_band.cu) ----

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import (BandParams, Buffers, CreateParams, FrameParams, PeerInfo, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+from ._abi import (BandParams, Buffers, CreateParams, FrameParams, PeerInfo, PrepassParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
                    TILE_DIVISOR)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
@@ -46,6 +46,7 @@ def load_library():
     L.sgi_resize.argtypes = [H, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.sgi_bind_device_buffers.argtypes = [H, C.POINTER(Buffers)]
     L.sgi_register_gl.argtypes = [H, C.c_void_p, C.c_int32]
+    L.sgi_vpl_prepass.argtypes = [H, C.POINTER(PrepassParams)]
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
@@ -158,7 +159,7 @@ class VplGiPass:
     def bind(self):
         b = Buffers()
         for k in _PER_PIXEL + ("lightingOut", "vplData", "vplUpdatedData", "vplVisibleIndices", "shadowDiffuseIndices",
-                               "vplStage1Results", "vplVisiblePerTile", "atlasEntryByVpl", "infiniteLightShadowMap"):
+                               "vplStage1Results", "vplVisiblePerTile", "atlasEntryByVpl", "infiniteLightShadowMap", "vplCountDevice"):
             if k in self.t:
                 setattr(b, k, self.t[k].data_ptr())
         if "shadowAtlas" in self.t:
@@ -169,6 +170,39 @@ class VplGiPass:
         self.buffers = b
         self.torch.cuda.synchronize(self.device)     # uploads/fills ran on torch's stream; the pass runs on its own
         self._check(self.L.sgi_bind_device_buffers(self._h, C.byref(b)))
+
+    # ---- the step before the cull: UpdatePointLights_ for virtual point lights (BE:1359-1392) + InitVplFrameData_ ----
+    def set_lights(self, records):
+        """records: numpy array of prepass.LIGHT_DTYPE (every virtual point light of the scene).  Allocates the cull's
+        input table for min(len, 10000) VPLs; vpl_prepass() fills it on the device."""
+        torch = self.torch
+        n = int(records.shape[0])
+        cap = max(1, min(n, _abi.MAX_TOTAL_VPLS_BEFORE_CULLING))
+        self.num_lights = n
+        self.t["lightRecords"] = torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).reshape(n, 32)).to(self.device)
+        self.t["vplData"] = torch.zeros((cap, 16), dtype=torch.float32, device=self.device)
+        self.t["atlasEntryByVpl"] = torch.zeros((cap, 2), dtype=torch.int32, device=self.device)
+        self.t["vplVisibleIndices"] = torch.zeros(cap + 1, dtype=torch.int32, device=self.device)
+        self.t["prepassOrder"] = torch.zeros(cap, dtype=torch.int32, device=self.device)
+        self.t["vplCountDevice"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return cap            # the upper bound to pass as FrameParams.totalNumLights
+
+    def vpl_prepass(self, view_position, frustum_planes):
+        """Frustum test, distance order and the 10000 cap on the device (stream-ordered, no read-back)."""
+        pp = PrepassParams()
+        for i in range(3):
+            pp.viewPosition[i] = float(view_position[i])
+        fr = np.asarray(frustum_planes, np.float32).reshape(6, 4)
+        for k in range(6):
+            for i in range(4):
+                pp.frustumPlanes[k][i] = float(fr[k, i])
+        pp.numLights = self.num_lights
+        pp.lights = self.t["lightRecords"].data_ptr()
+        pp.vplDataOut = self.t["vplData"].data_ptr()
+        pp.atlasEntryOut = self.t["atlasEntryByVpl"].data_ptr()
+        pp.orderOut = self.t["prepassOrder"].data_ptr()
+        pp.countOut = self.t["vplCountDevice"].data_ptr()
+        self._check(self.L.sgi_vpl_prepass(self._h, C.byref(pp)))
 
     # ---- the reference's pass interface --------------------------------------------------------------
     def PerformVirtualPointLightCullingStage1(self, fp):

@@ -29,7 +29,10 @@ def test_ctypes_layout_matches_header(tmp_path):
         "SgiFrameParams": (_abi.FrameParams, ["viewPosition", "time", "deltaSeconds", "minGiOcclusionFactor", "fogColor",
                                               "infiniteLightDirection", "cascadeProjViews", "cascadePlanes", "totalNumLights", "gatherMode"]),
         "SgiBuffers": (_abi.Buffers, ["depth", "prevNormal", "ssao", "lightingOut", "vplData", "atlasEntryByVpl", "shadowCubeMaps",
-                                      "diffuseCubeMaps", "infiniteLightShadowMap"]),
+                                      "diffuseCubeMaps", "infiniteLightShadowMap", "vplCountDevice"]),
+        "SgiLightRecord": (_abi.LightRecord, ["position", "radius", "farPlane", "intensity", "atlasIndex", "atlasLayer"]),
+        "SgiPrepassParams": (_abi.PrepassParams, ["viewPosition", "numLights", "frustumPlanes", "lights", "vplDataOut", "atlasEntryOut",
+                                                  "orderOut", "countOut"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),
         "SgiBandParams": (_abi.BandParams, ["compute_y0", "compute_rows", "rank", "world", "owns_frame_image"]),
         "SgiPeerInfo": (_abi.PeerInfo, ["mem_handle", "local_base", "off_res", "off_gi", "off_hist", "off_flags", "off_image",

@@ -254,3 +254,54 @@ def test_gather_outputs_are_bounded_and_weights_at_least_one(tiny_oracle):
     it, shaded, fetch = o["sample_stats"]
     P = res.shape[0] * res.shape[1]
     assert P <= shaded <= 6 * P and shaded <= it <= 11 * P                          # 1..6 samples, <= 5 re-draws
+
+
+# ---- self-check 8 (widening row f1): the VPL pre-pass restatement against an independent numpy formulation ------------
+def _random_lights(n, seed, dup=True):
+    from stratusgfx_b200.prepass import LIGHT_DTYPE
+    rng = np.random.default_rng(seed)
+    rec = np.zeros(n, LIGHT_DTYPE)
+    rec["position"] = rng.uniform(-300, 300, (n, 3)).astype(np.float32)
+    rec["radius"] = rng.choice(np.array([5, 50, 500], np.float32), n)
+    rec["farPlane"] = rec["radius"]
+    rec["intensity"] = rng.uniform(0.01, 0.05, n).astype(np.float32)
+    rec["atlasIndex"] = rng.integers(0, 14, n)
+    rec["atlasLayer"] = rng.integers(0, 320, n)
+    if dup and n >= 8:       # equal distances: exact duplicates and mirror images about the viewer's x
+        rec["position"][n // 2] = rec["position"][1]
+        rec["position"][n // 3] = rec["position"][2]
+    return rec
+
+
+def _prepass_numpy(rec, view, planes):
+    """multiset ordered by distance == stable sort by distance; IsSphereInFrustum plane by plane (glm dot order (x+y)+(z+w))."""
+    p = rec["position"].astype(np.float32)
+    d = p - np.asarray(view, np.float32)
+    t = d * d
+    dist = np.sqrt((t[:, 0] + t[:, 1]) + t[:, 2]).astype(np.float32)
+    inside = np.ones(len(rec), bool)
+    for g in np.asarray(planes, np.float32).reshape(6, 4):
+        s = (g[0] * p[:, 0] + g[1] * p[:, 1]) + (g[2] * p[:, 2] + g[3] * np.float32(1.0))
+        inside &= ~(s < -rec["radius"])
+    idx = np.nonzero(inside)[0]
+    order = idx[np.argsort(dist[idx].astype(np.float64), kind="stable")]
+    return order[:10000].astype(np.int32)
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (257, 3), (30000, 4)])
+def test_vpl_prepass_equals_stable_sort_restatement(n, seed):
+    from oracle import oracle_py as O
+    from stratusgfx_b200.prepass import frustum_planes
+    from stratusgfx_b200.scene import Scene
+    fp = Scene("tiny").frame_params(0)
+    planes = frustum_planes(list(fp.invProjectionView))
+    view = list(fp.viewPosition)
+    rec = _random_lights(n, seed)
+    vd, at, order = O.vpl_prepass(rec, view, planes)
+    want = _prepass_numpy(rec, view, planes)
+    assert np.array_equal(order, want)
+    assert len(order) <= 10000 and (n < 30000 or len(order) == 10000)      # the 10000 cap bites in the large case
+    if len(order):
+        assert np.array_equal(vd[:, 0:3], rec["position"][order]) and np.all(vd[:, 3] == 1.0) and np.all(vd[:, 4:12] == 0.0)
+        assert np.array_equal(vd[:, 12], rec["radius"][order]) and np.array_equal(vd[:, 13], rec["farPlane"][order])
+        assert np.array_equal(at[:, 0], rec["atlasIndex"][order]) and np.array_equal(at[:, 1], rec["atlasLayer"][order])

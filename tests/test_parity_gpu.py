@@ -295,3 +295,68 @@ def test_c4_4k_2048vpl_properties_and_parity(built):
     # gather is deterministic: a second run gives the same bytes
     cu2 = run_cuda_staged(d)[0]
     assert np.array_equal(cu2["combined"].view(np.uint16), cu["combined"].view(np.uint16))
+
+
+# ---- widening row f1: the VPL pre-pass (UpdatePointLights_ + InitVplFrameData_, BE:1359-1392, :1281-1292) ---------------
+def _prepass_inputs(n, seed):
+    from stratusgfx_b200.prepass import frustum_planes
+    from stratusgfx_b200.scene import Scene
+    from tests.test_oracle_selfchecks import _random_lights
+    fp = Scene("tiny").frame_params(0)
+    return _random_lights(n, seed), list(fp.viewPosition), frustum_planes(list(fp.invProjectionView))
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (257, 3), (2048, 5), (30000, 4)])
+def test_vpl_prepass_is_bit_exact(tiny, n, seed):
+    """Frustum decisions, distance order (ties keep input order) and the 10000 cap: the device table must equal the CPU
+    restatement of the reference's multiset loop byte for byte."""
+    from oracle import oracle_py as O
+    rec, view, planes = _prepass_inputs(n, seed)
+    vd, at, order = O.vpl_prepass(rec, view, planes)
+    gp = make_pass(tiny)
+    gp.set_lights(rec)
+    gp.vpl_prepass(view, planes)
+    gp.synchronize()
+    count = int(gp.t["vplCountDevice"].cpu().numpy()[0])
+    assert count == len(order)
+    assert n < 30000 or count == 10000
+    if count:
+        assert np.array_equal(gp.t["prepassOrder"].cpu().numpy()[:count], order)
+        assert np.array_equal(gp.t["vplData"].cpu().numpy()[:count].view(np.uint32), vd.view(np.uint32))
+        assert np.array_equal(gp.t["atlasEntryByVpl"].cpu().numpy()[:count], at)
+    gp.close()
+
+
+def test_frame_from_device_built_vpl_table_equals_host_built(built):
+    """The whole chain without a read-back: pre-pass -> cull (N clamped on the device by vplCountDevice) -> colour -> tile
+    lists -> gather -> denoise must give the bytes of the same frame fed with the CPU-built table and its exact N."""
+    from oracle import oracle_py as O
+    from stratusgfx_b200.prepass import frustum_planes, light_records
+    d = SceneData("c1", frames=1)
+    fp = d.fp[0]
+    rec = light_records(d.vpl_data, d.atlas_by_vpl)
+    # shrink the radii so that the frustum test actually rejects some of the lights behind the camera plane
+    rec["radius"] = 2.0
+    planes = frustum_planes(list(fp.invProjectionView))
+    view = list(fp.viewPosition)
+    vd, at, order = O.vpl_prepass(rec, view, planes)
+    # host-built reference run: exact N, the oracle's table (radius restored to what the gather expects is irrelevant: both runs share it)
+    ref = make_pass(d)
+    ref.set_vpls(vd, at); ref.set_gbuffer(d.gb[0], d.gb[-1]); ref.bind()
+    fp_ref = fp.copy(); fp_ref.totalNumLights = len(order)
+    ref.frame(fp_ref)
+    want = ref.output("lightingOut").view(np.uint16).copy()
+    want_vis = ref.output("vplVisibleIndices")[:len(order) + 1].copy()
+    ref.close()
+    gp = make_pass(d)
+    upper = gp.set_lights(rec)
+    gp.set_gbuffer(d.gb[0], d.gb[-1]); gp.bind()
+    gp.vpl_prepass(view, planes)
+    fp_dev = fp.copy(); fp_dev.totalNumLights = upper            # an upper bound: the cull reads the real N on the device
+    gp.frame(fp_dev)
+    got = gp.output("lightingOut").view(np.uint16)
+    got_vis = gp.output("vplVisibleIndices")
+    assert 0 < len(order) <= upper
+    assert np.array_equal(got_vis[:want_vis[0] + 1], want_vis[:want_vis[0] + 1])
+    assert np.array_equal(got, want)
+    gp.close()
