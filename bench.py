@@ -301,8 +301,10 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(args.warmup + i)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps     # host time to enqueue one step (no synchronisation inside)
     finish()                                  # the last frame's image is assembled (and the look-ahead broadcast drained) inside the timed region
     e1.record()
     fence()
@@ -404,7 +406,8 @@ def run_ours(args, rank, world, local_rank):
                                f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of VPL table + 5 cube maps per frame ({'issued one frame ahead' if prefetch else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
                                f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
                            "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
-                           "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log},
+                           "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log,
+                           "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
                 "clocks": clocks,
                 "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass"},

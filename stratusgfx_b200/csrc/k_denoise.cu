@@ -39,6 +39,7 @@ namespace {
 
 constexpr float PREVENT_DIV_BY_ZERO = 0.00001f;
 constexpr int kDnX = 32, kDnY = 8;
+constexpr int kLat = 4;                       // à-trous: outputs per thread, consecutive on the tap lattice of its column
 
 struct Bilin { int i0, i1, j0, j1; float a, b; };
 SGI_DEV Bilin bilinSetup(float u, float v, int W, int H) {
@@ -162,12 +163,31 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 }
 
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
-constexpr int kLat = 4;                       // outputs per thread, consecutive on the tap lattice of its column
 constexpr float kLog2e = 1.4426950408889634f;
 
 SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Rows a CTA row `by` of the à-trous grid can output (band-local, a superset for spacings > kDnY): thread rows kDnY*by .. +kDnY-1
+// are lattice groups g = t / s, each kLat*s rows tall.  Host and device use the same formula to decide which CTAs push rows to
+// a neighbour (the producers of the in-kernel signal).
+__host__ __device__ inline void atrousSlab(int by, int s, int c0, int cEnd, int* lo, int* hi) {
+    const int gLo = (by * kDnY) / s, gHi = (by * kDnY + kDnY - 1) / s;
+    *lo = c0 + gLo * kLat * s;
+    const int h = c0 + (gHi + 1) * kLat * s;
+    *hi = h < cEnd ? h : cEnd;
+}
+__host__ __device__ inline bool slabPushes(const BandLinks& L, int lo, int hi, int yOffset) {      // band-local rows [lo, hi)
+    const int a = lo + yOffset, b = hi + yOffset;
+    return (L.up.res != nullptr && a < L.up.lastRow && b > L.up.firstRow) || (L.down.res != nullptr && a < L.down.lastRow && b > L.down.firstRow);
+}
+// CTA rows in launch order when the kernel signals its neighbours itself: the first, the last and the second-last row of the grid
+// (the ones that hold the band's boundary rows) before the interior
+__device__ __forceinline__ int boundaryFirst(int p, int n) {
+    if (n <= 3) return p;
+    return p == 0 ? 0 : (p == 1 ? n - 1 : (p == 2 ? n - 2 : p - 2));
+}
 
 template <bool FINAL>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
@@ -175,7 +195,8 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
     const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
-    const int t = blockIdx.y * kDnY + threadIdx.y;           // lattice column-of-rows id: residue r, group g
+    const int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
+    const int t = by * kDnY + threadIdx.y;                   // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
     const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
     const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
@@ -183,7 +204,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
     // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
     bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
-    if (!live) return;
+    if (live) {
 
     if (FINAL) {
         // the temporal epilogue reads ten more planes per output, first touched in this kernel: ask L2 for them now so the
@@ -248,6 +269,15 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
         pushRes(io.links, ly + bd.yOffset, x, W, rv);
         if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), __ldg(&io.guide[(size_t)ly * W + x].w), shadowFactor);
     }
+    }   // live
+    if (io.links.doneCounter != nullptr) {                   // (uniform per CTA) a producer CTA counts itself once all its threads have stored
+        int lo, hi;
+        atrousSlab(by, s, c0, cEnd, &lo, &hi);
+        if (lo < hi && slabPushes(io.links, lo, hi, bd.yOffset)) {
+            __syncthreads();
+            if (threadIdx.x == 0 && threadIdx.y == 0) producerDone(io.links);
+        }
+    }
 }
 
 }  // namespace
@@ -270,9 +300,12 @@ int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* 
     return 1;
 }
 
-int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_) {
+int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& ioIn, bool merge, bool final_, bool* signalled) {
     dim3 block(kDnX, kDnY);
+    if (signalled) *signalled = false;
+    DenoiseIO io = ioIn;
     if (merge) {
+        io.links.doneCounter = nullptr;          // the centre-only merge pass keeps the host-launched signal
         dim3 grid((bd.W + kDnX - 1) / kDnX, (bd.crows + kDnY - 1) / kDnY);
         if (final_) mergeKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
         else mergeKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
@@ -281,6 +314,17 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int s = 1 + io.multiplier;
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
+        if (io.links.doneCounter != nullptr) {   // producers of the in-kernel signal: the CTA rows whose slab holds rows pushed to a neighbour
+            int producerRows = 0;
+            for (int by = 0; by < (int)grid.y; ++by) {
+                int lo, hi;
+                atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+                if (lo < hi && slabPushes(io.links, lo, hi, bd.yOffset)) ++producerRows;
+            }
+            io.links.producers = producerRows * (int)grid.x;
+            if (io.links.producers == 0) io.links.doneCounter = nullptr;
+            else if (signalled) *signalled = true;
+        }
         if (final_) atrousKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
         else atrousKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
     }

@@ -413,6 +413,12 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     // Warps fetch 32-pixel row segments from a global counter, kUnitChunk at a time, so the kernel finishes on time even when not
     // all of its CTAs are resident from the start (sgi_frame runs the tile-list stages next to it on a side stream).  Counter
     // [frame & 1] serves this launch; the other one is re-armed for the next launch on this stream.
+    int topLo = 0, nTop = 0, botLo = 0, nBot = 0;               // band-local row ranges pushed to the upper / lower neighbour
+    if (links.doneCounter != nullptr) {
+        if (links.up.res != nullptr) { topLo = links.up.firstRow - bd.yOffset; nTop = links.up.lastRow - links.up.firstRow; }
+        if (links.down.res != nullptr) { botLo = links.down.firstRow - bd.yOffset; nBot = links.down.lastRow - links.down.firstRow; }
+        if (nTop > 0 && nBot > 0 && topLo + nTop > botLo) { nTop = 0; nBot = 0; }      // overlapping ranges (a very thin band): plain order
+    }
     int* __restrict__ counter = unitCounters + (counterSel & 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) unitCounters[(counterSel & 1) ^ 1] = 0;
     int unit = 0, unitEnd = 0;
@@ -425,9 +431,18 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             unit = base; unitEnd = min(base + kUnitChunk, units);
         }
         const int thisUnit = unit++;
-        const int ly = thisUnit / unitsX;
+        // row order: the rows whose pass-0 output goes to a neighbour's halo first (top range, bottom range), then the rest
+        int ly = thisUnit / unitsX;
         const int x = (thisUnit - ly * unitsX) * 32 + lane;
+        if (ly < nTop) ly = topLo + ly;
+        else if (ly < nTop + nBot) ly = botLo + (ly - nTop);
+        else {
+            ly -= nTop + nBot;
+            if (nTop > 0 && ly >= topLo) ly += nTop;
+            if (nBot > 0 && ly >= botLo) ly += nBot;
+        }
         const int y = ly + bd.yOffset;
+        do {
         // row bands: a warp that will store pass-0 rows into a neighbour's halo first waits until that neighbour has finished
         // the previous frame (its final pass read those halo rows)
         bandWaitWarp(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
@@ -537,6 +552,11 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             mergedOut[p] = mv;
             pushRes(links, y, x, bd.W, mv);
         }
+        } while (false);                                           // (`continue` above leaves the pixel, not the segment)
+        if (links.doneCounter != nullptr && pushesRow(links, y)) { // warp-uniform: this segment stored rows into a neighbour's halo
+            __syncwarp();
+            if (lane == 0) producerDone(links);
+        }
     }
 }
 
@@ -577,31 +597,47 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
-                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int counterSel) {
+                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int counterSel, bool* signalled) {
+    if (signalled) *signalled = false;
+    BandLinks plain = links;                 // the kernels without the in-kernel signal
+    plain.doneCounter = nullptr;
     if (tileLists != nullptr) {
         dim3 block(kTileCtaX * SGI_TILE_DIVISOR, kTileCtaY * SGI_TILE_DIVISOR);
         dim3 grid((bd.W + block.x - 1) / block.x, (bd.rows + block.y - 1) / block.y);
         gatherKernel<SGI_GATHER_TILE_LIST><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                       colorOut, reservoirOut, guideOut, mergedOut, links, tileLists, tilePos);
+                                                                       colorOut, reservoirOut, guideOut, mergedOut, plain, tileLists, tilePos);
     } else if (!legacyGather()) {
         // persistent: every SM holds the table once (two 512-thread CTAs while two copies fit, else one 1024-thread CTA)
         const int cap = max(1, min(fc.totalNumLights, SGI_MAX_TOTAL_VPLS_PER_FRAME));
         const int bytes = cap * kTableBytesPerVpl;
         const int units = ((bd.W + 31) / 32) * bd.rows;
+        // producers of the in-kernel signal: the 32-pixel segments of the rows pushed to a neighbour (pass 0 is pushed only when fused)
+        BandLinks armed = links;
+        if (armed.doneCounter != nullptr) {
+            int rows = 0;
+            if (mergedOut != nullptr) for (int y = bd.yOffset + bd.c0; y < bd.yOffset + bd.c0 + bd.crows; ++y) {
+                const bool up = armed.up.res != nullptr && y >= armed.up.firstRow && y < armed.up.lastRow;
+                const bool down = armed.down.res != nullptr && y >= armed.down.firstRow && y < armed.down.lastRow;
+                rows += (up || down) ? 1 : 0;
+            }
+            armed.producers = rows * ((bd.W + 31) / 32);
+            if (armed.producers == 0) armed.doneCounter = nullptr;
+            else if (signalled) *signalled = true;
+        }
         if (bytes <= kTableBytesTwoCtas) {
             const int grid = max(1, min(2 * smCount(), (units + 15) / 16));
             gatherStochasticKernel<512><<<grid, 512, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                      colorOut, reservoirOut, guideOut, mergedOut, links, cap, unitCounters, counterSel);
+                                                                      colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
         } else {
             const int grid = max(1, min(smCount(), (units + 31) / 32));
             gatherStochasticKernel<1024><<<grid, 1024, bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, cap, unitCounters, counterSel);
+                                                                        colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
         }
     } else {
         dim3 block(kGatherThreadsX, kGatherThreadsY);
         dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
         gatherKernel<SGI_GATHER_STOCHASTIC><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                        colorOut, reservoirOut, guideOut, mergedOut, links, nullptr, nullptr);
+                                                                        colorOut, reservoirOut, guideOut, mergedOut, plain, nullptr, nullptr);
     }
     return 1;
 }

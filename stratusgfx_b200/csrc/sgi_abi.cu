@@ -39,7 +39,7 @@ static void freePlanes(SgiHandle h) {
     h->resA = h->resB = nullptr;
     h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
     h->frameImage[0] = h->frameImage[1] = nullptr;
-    h->flags = nullptr;
+    h->flags = nullptr; h->bandDone = nullptr;
 }
 
 // Planes that another band may store into (reservoir ping-pong, GI/history ping-pong, flags, frame images) live in ONE
@@ -63,6 +63,7 @@ static int allocPlanes(SgiHandle h) {
     h->resA = base + h->offRes[0]; h->resB = base + h->offRes[1];
     for (int i = 0; i < 2; ++i) { h->giIllum[i] = base + h->offGi[i]; h->history[i] = base + h->offHist[i]; }
     h->flags = (int32_t*)(base + h->offFlags);
+    h->bandDone = h->flags + 4;             // producer counter of the in-kernel signal (flags[4]; the slab's flags start at zero)
     for (int i = 0; i < 2; ++i) h->frameImage[i] = h->offImage[i] >= 0 ? base + h->offImage[i] : nullptr;
     void** half4s[] = {&h->giColor, &h->giReservoir, &h->combined};
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
@@ -79,6 +80,8 @@ static int allocPlanes(SgiHandle h) {
     SGI_CUDA(h, cudaMemsetAsync(h->slab, 0, off, h->stream));
     h->cur = 0;
     h->frameNo = 0;
+    h->imageWaitedFrame = 0;
+    h->copyPending = false;
     return SGI_OK;
 }
 
@@ -302,16 +305,19 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
         // this gather is about to overwrite) before the boundary rows of pass 0 are pushed into their memory.
         ++h->frameNo;
         const int prevDone = h->frameNo > 1 ? sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters) : 0;
-        if (fuse) links = sgi::bandLinks(h, 0, false, prevDone);         // the CTAs that push wait inside the kernel
-        else if (prevDone) n += sgi::waitNeighbours(h, prevDone);
+        if (fuse) {
+            links = sgi::bandLinks(h, 0, false, prevDone);               // the CTAs that push wait inside the kernel
+            sgi::armInKernelSignal(h, &links, sgi::bandEpoch(h->frameNo, 1));
+        } else if (prevDone) n += sgi::waitNeighbours(h, prevDone);
     }
+    bool signalled = false;
     n += launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
                                fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
-                               h->gatherCounters, (int)(h->gatherLaunches++ & 1));
-    if (h->banded && fuse) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
+                               h->gatherCounters, (int)(h->gatherLaunches++ & 1), &signalled);
+    if (h->banded && fuse && !signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it
     // into vplGIDenoisedFbo1's reservoir attachment already, valid for a pass-0 call with the same `time`
@@ -362,13 +368,18 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         // pass p reads the neighbours' pass p-1 rows from this handle's halo: wait (in stream order) for their flags
         // (inside the kernel, by the CTAs whose taps reach the halo; interior CTAs start at once)
         io.links = sgi::bandLinks(h, pass % 2, final_, pass >= 1 ? sgi::bandEpoch(h->frameNo, pass) : 0);
+        // (with SGI_IMAGE_PUSH=kernel the final pass's flag also tells the owner that the image rows landed: host-launched signal)
+        if (!(final_ && sgi::imagePushByKernel())) sgi::armInKernelSignal(h, &io.links, sgi::bandEpoch(h->frameNo, pass + 1));
     }
+    bool signalled = false;
     const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && !sgi::imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached &&
                          h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
     if (copyOut && h->copyPending) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evCopyDone, 0));   // the previous frame's rows have left `combined`
-    n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_);
+    n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_, &signalled);
     if (h->banded) {
-        n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
+        // the pass's boundary CTAs released the neighbours' flags themselves; otherwise a one-thread kernel does it after the pass
+        if (!signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
+        else if (final_) n += sgi::signalOwnerRowsDone(h);
         if (copyOut) {
             // the band's lit rows -> the owner's frame image of this parity, by the copy engine, then this band's flag in the
             // owner's slab; both on the copy stream, so the next frame starts at once on the main stream

@@ -140,6 +140,22 @@ int signalNeighbours(SgiHandle_* h, int epoch, bool final_) {
     return launchSignal(h->stream, a, b, epoch, c, (int)(uint32_t)h->frameNo);
 }
 
+void armInKernelSignal(SgiHandle_* h, BandLinks* L, int epoch) {
+    static const bool off = [] { const char* e = getenv("SGI_BAND_SIGNAL"); return e && e[0] == 'k'; }();      // SGI_BAND_SIGNAL=kernel: always the signal kernel
+    int32_t* up = peerFlags(h, SGI_PEER_UP);
+    int32_t* down = peerFlags(h, SGI_PEER_DOWN);
+    if (off || h->bandDone == nullptr || (up == nullptr && down == nullptr)) return;
+    L->doneCounter = h->bandDone;
+    L->sigUp = up ? up + 1 : nullptr;
+    L->sigDown = down ? down + 0 : nullptr;
+    L->sigEpoch = epoch;
+}
+
+int signalOwnerRowsDone(SgiHandle_* h) {
+    if (!h->band.owns_frame_image) return 0;
+    return launchSignal(h->stream, nullptr, nullptr, 0, h->flags + 8 + h->band.rank, (int)(uint32_t)h->frameNo);
+}
+
 int waitAllBands(SgiHandle_* h, int64_t frameNo) {
     return launchWaitAllBands(h->stream, h->flags + 8, h->band.world, (int)(uint32_t)frameNo, h->flags + 2);
 }
@@ -197,8 +213,6 @@ int sgi_band_setup(SgiHandle h, const SgiBandParams* bp) {
     SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
     SGI_CUDA_B(h, cudaStreamSynchronize(h->copyStream));
     detachPeers(h);
-    h->copyPending = false;
-    h->imageWaitedFrame = h->frameNo;       // the new slab's flags start at zero: nothing earlier to wait for
     h->banded = true;
     h->band = *bp;
     return sgiAllocPlanesForBand(h);

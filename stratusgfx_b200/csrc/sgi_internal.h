@@ -36,6 +36,15 @@ struct BandLinks {
     const int32_t* waitDown;   // this handle's flags[1] (written by the band below) or nullptr
     int waitEpoch;
     int32_t* timeouts;
+    // in-kernel signal: the CTAs (gather: 32-pixel row segments) that store rows into a neighbour's halo are scheduled first and
+    // counted; the last of them releases the neighbours' flags, so the neighbours see this pass's boundary rows a pass-time
+    // before they need them and ranks no longer wait for each other stage by stage.  doneCounter == nullptr: the host
+    // launches the one-thread signal kernel after the pass instead.
+    int32_t* doneCounter;      // this handle's counter (device, zero between launches)
+    int producers;             // how many producer CTAs / segments this launch has
+    int32_t* sigUp;            // the upper neighbour's flag word for me (its flags[1]) or nullptr
+    int32_t* sigDown;          // the lower neighbour's flag word for me (its flags[0]) or nullptr
+    int sigEpoch;
 };
 
 constexpr int kGatherMaxDraws = 12;   // draws of one pixel's VPL sequence: <= 6 samples + 5 re-draws (vpl_pbr_gi.fs:138-171)
@@ -99,6 +108,21 @@ __device__ __forceinline__ void bandWaitCta(const BandLinks& L, bool needUp, boo
         }
         __syncthreads();
     }
+}
+// the last producer releases the neighbours' flags.  Called by ONE thread after a barrier that orders the CTA's (warp's) stores
+// before it: fence.sys makes them visible system-wide before the count, and the thread that sees the full count fences again
+// (acquire of the other producers' fenced stores) before the release stores.
+__device__ __forceinline__ void producerDone(const BandLinks& L) {
+    __threadfence_system();
+    if (atomicAdd(L.doneCounter, 1) == L.producers - 1) {
+        __threadfence_system();
+        *L.doneCounter = 0;                                   // re-armed for the next launch on this stream
+        if (L.sigUp != nullptr) stReleaseSys(L.sigUp, L.sigEpoch);
+        if (L.sigDown != nullptr) stReleaseSys(L.sigDown, L.sigEpoch);
+    }
+}
+__device__ __forceinline__ bool pushesRow(const BandLinks& L, int y) {      // frame row y is stored into a neighbour's halo
+    return (L.up.res != nullptr && y >= L.up.firstRow && y < L.up.lastRow) || (L.down.res != nullptr && y >= L.down.firstRow && y < L.down.lastRow);
 }
 // store a band's boundary pixel into the neighbours' halo rows (plain st.global on peer-mapped pointers: NVLink writes)
 __device__ __forceinline__ void pushRes(const BandLinks& L, int y, int x, int W, uint2 v) {
@@ -180,6 +204,7 @@ struct SgiHandle_ {
     size_t slabBytes = 0;
     int64_t offRes[2] = {0, 0}, offGi[2] = {0, 0}, offHist[2] = {0, 0}, offFlags = 0, offImage[2] = {-1, -1};
     int32_t* flags = nullptr;       // [SGI_BAND_FLAGS] inside the slab
+    int32_t* bandDone = nullptr;    // producer counter of the in-kernel signal (BandLinks::doneCounter)
     void* frameImage[2] = {nullptr, nullptr};
     bool banded = false;
     SgiBandParams band{};
@@ -211,14 +236,16 @@ int launchColor(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, 
                 const SgiAtlasEntry* entries, const AtlasTable& atlases);
 // ---- row bands (sgi_band.cu) ----
 BandLinks noLinks();
-BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch);   // peer destinations of the pass writing reservoir resIndex; waitEpoch 0 = no wait
+BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch);
+void armInKernelSignal(SgiHandle_* h, BandLinks* L, int epoch);     // fills doneCounter / sigUp / sigDown / sigEpoch (producers is set by the launcher)
+int signalOwnerRowsDone(SgiHandle_* h);                             // owner band: its own rows of the frame image are complete   // peer destinations of the pass writing reservoir resIndex; waitEpoch 0 = no wait
 inline int bandEpoch(int64_t frameNo, int stage) { return (int)(uint32_t)(frameNo * 32 + stage); }   // stage k: output of pass k-1 pushed
 int waitNeighbours(SgiHandle_* h, int epoch);
 int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
 int waitAllBands(SgiHandle_* h, int64_t frameNo);
 bool imagePushByKernel();
 void detachPeers(SgiHandle_* h);
-constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [8+r] band r's image rows landed
+constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [4] producer counter of the in-kernel signal, [8+r] band r's image rows landed
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
 int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int epoch, int32_t* timeouts);
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);
@@ -232,8 +259,10 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
                  const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos,
-                 int* unitCounters /* two ints: work counters of the persistent gather */, int counterSel);
+                 int* unitCounters /* two ints: work counters of the persistent gather */, int counterSel,
+                 bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
-int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_);
+int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
+                      bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 
 }  // namespace sgi
