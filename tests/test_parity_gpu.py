@@ -360,3 +360,60 @@ def test_frame_from_device_built_vpl_table_equals_host_built(built):
     assert np.array_equal(got_vis[:want_vis[0] + 1], want_vis[:want_vis[0] + 1])
     assert np.array_equal(got, want)
     gp.close()
+
+
+# ---- BASELINE.json configs[4]: one 7680x4320 view with 4096 VPLs (the largest size of the path) -------------------------
+def test_c5_8k_4096vpl_band_parity_and_whole_view_properties(built):
+    """The 8K view is too slow for the CPU oracle as a whole, so: (1) a 270-row band of it runs as a plain band handle and
+    must match the oracle on the same band stage by stage (integer lists bit-exact, radiance within the bar); (2) the whole
+    view runs once through sgi_frame and is checked through size-independent properties — ordered compaction, list
+    bounds, history, determinism — and its gather output on the band's rows must be the band handle's bytes (the gather
+    is per pixel, so a band and the whole view agree exactly)."""
+    from oracle.oracle_py import OracleFrame
+    from stratusgfx_b200.gipass import VplGiPass
+    from stratusgfx_b200.scene import Scene
+    s = Scene("c5")
+    W, H, N = s.width, s.height, s.num_vpls
+    assert (W, H, N) == (7680, 4320, 4096)
+    vd, at = s.vpls(); sh, df = s.cubemaps(); csm = s.csm(0); fp = s.frame_params(0)
+    y0, rows = 2700, 270                                   # a band of the lower half (floor, column bases: the expensive rows)
+    gb, pgb = s.gbuffer(0, y0, rows), s.gbuffer(-1, y0, rows)
+    # (1) band handle vs the oracle on the same band
+    gp = VplGiPass(W, H, y0, rows, s.cube_res, s.csm_res, s.denoise_iters)
+    gp.set_vpls(vd, at); gp.set_atlases(sh, df); gp.set_csm(csm); gp.set_gbuffer(gb, pgb); gp.bind()
+    gp.cull(fp); V = gp.visible_count(); gp.color(fp); gp.tile_lists(fp); gp.gather(fp)
+    band_res = gp.plane(_abi.PLANE_GI_RESERVOIR)
+    gp.denoise(fp)
+    cu = dict(V=V, visible=gp.output("vplVisibleIndices"), updated=gp.output("vplUpdatedData"), entries=gp.output("shadowDiffuseIndices"),
+              stage1=gp.output("vplStage1Results"), stage2=gp.output("vplVisiblePerTile"), gi_color=gp.plane(_abi.PLANE_GI_COLOR),
+              gi_reservoir=band_res, combined=gp.output("lightingOut"), gi_illum=gp.plane(_abi.PLANE_GI_ILLUM),
+              history=gp.plane(_abi.PLANE_HISTORY), pass_reservoirs=[])
+    gp.close()
+    o = OracleFrame(W, rows, s.cube_res, s.csm_res, s.denoise_iters, y_offset=y0, full_height=H)
+    o.frame(fp, gb, pgb, vd, at, csm, sh, df)
+    orc = dict(visible=o.visible, updated=o.updated, entries=o.entries, stage1=o.stage1, stage2=o.stage2, gi_color=o.gi_color,
+               gi_reservoir=o.gi_reservoir, pass_reservoirs=[], combined=o.combined, gi_illum=o.gi_illum, history=o.history)
+    rep, bad = compare_frame(cu, orc)
+    assert not bad, bad
+    assert 0 < V <= N and rep["stage2_lists_exact"]
+    del o, gb, pgb
+    # (2) the whole view, once, through sgi_frame
+    gbw, pgbw = s.gbuffer(0), s.gbuffer(-1)
+    gp = VplGiPass(W, H, 0, H, s.cube_res, s.csm_res, s.denoise_iters)
+    gp.set_vpls(vd, at); gp.set_atlases(sh, df); gp.set_csm(csm); gp.set_gbuffer(gbw, pgbw); gp.bind()
+    gp.frame(fp)
+    vis = gp.output("vplVisibleIndices")
+    assert vis[0] == V and np.array_equal(vis[:V + 1], cu["visible"][:V + 1]) and np.all(np.diff(vis[1:V + 1]) > 0)
+    s2 = gp.output("vplVisiblePerTile")
+    assert s2[:, 0].min() >= 0 and s2[:, 0].max() <= 12
+    tx = W // 5
+    assert np.array_equal(s2[(y0 // 5) * tx:((y0 + rows) // 5) * tx], cu["stage2"])          # tile lists are per tile
+    assert np.array_equal(gp.plane(_abi.PLANE_GI_RESERVOIR)[y0:y0 + rows].view(np.uint16), band_res.view(np.uint16))
+    assert np.all(gp.plane(_abi.PLANE_HISTORY) == np.float16(1.0))
+    first = gp.output("lightingOut").view(np.uint16).copy()
+    assert np.isfinite(gp.output("lightingOut").astype(np.float32)).all()
+    gp.reset_history()
+    gp.set_gbuffer(gbw, pgbw); gp.bind()
+    gp.frame(fp)
+    assert np.array_equal(gp.output("lightingOut").view(np.uint16), first)                    # deterministic
+    gp.close()
