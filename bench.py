@@ -426,6 +426,81 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+
+# ---- second split: independent camera views, one whole view per GPU, no exchange at all ---------------
+def run_views(args, rank, world, local_rank):
+    """`--split views`: every rank renders its OWN whole view of the workload (a different camera yaw per rank) — the batch
+    axis of BASELINE.json's configs[4].  No data-path collective; weak scaling: value = views x pixels x VPLs / time."""
+    import torch
+    import torch.distributed as dist
+    from stratusgfx_b200.gipass import VplGiPass
+    from stratusgfx_b200.scene import Scene
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scene = Scene(args.workload, yaw_deg_per_frame=3.0)
+    view = rank                                       # frame index = view index: 3 degrees of yaw apart
+    W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
+    vd, at = scene.vpls(); sh, df = scene.cubemaps(); csm = scene.csm(view)
+    fp = scene.frame_params(view)
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(side):
+        gp = VplGiPass(W, H, 0, H, scene.cube_res, scene.csm_res, iters, device=local_rank, use_torch_stream=True)
+        gp.set_gbuffer(scene.gbuffer(view), scene.gbuffer(view - 1)); gp.set_vpls(vd, at); gp.set_atlases(sh, df); gp.set_csm(csm); gp.bind()
+
+        def fence():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for i in range(args.warmup):
+            fp.time = 1000.0 + 16.0 * i
+            gp.frame(fp)
+        fence()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start(); time.sleep(0.25)
+        launches0 = gp.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        e0.record()
+        for i in range(args.steps):
+            fp.time = 1000.0 + 16.0 * (args.warmup + i)
+            gp.frame(fp)
+        e1.record()
+        fence()
+        ms_total = e0.elapsed_time(e1)
+        launches = gp.launch_count() - launches0
+        V = gp.visible_count()
+        if world > 1:
+            t = torch.tensor([ms_total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        ab = algorithmic_bytes(W * H, (W // 5) * (H // 5), N, V, iters)
+        line = {"metric": METRIC, "value": world * W * H * N / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
+                           "parallelism": f"{world} independent camera views, one whole view per GPU, no exchange (the batch axis of configs[4]); a step = one frame of every view",
+                           "visible_vpls_view0": V, "storage": "f16/unorm8 planes"},
+                "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"kernel": "frame", "bound": "hbm", "achieved": round(ab["frame"] / (ms_step * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round(ab["frame"] / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "note": "whole frame of one view: algorithmic bytes of SURVEY.md 8(d) over the frame time, per GPU"},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    gp.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +511,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--balance", type=int, default=2, help="measured band-balancing rounds before the timed region (N > 1)")
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
+    ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")
     ap.add_argument("--bands", default="p2p", choices=["p2p", "apron"], help="multi-GPU halo strategy (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -447,7 +523,10 @@ def main():
     else:
         if world != max(args.gpus, 1) and world == 1 and args.gpus > 1:
             raise SystemExit("launch multi-GPU runs with torchrun (one rank per GPU)")
-        run_ours(args, rank, world, local_rank)
+        if args.split == "views":
+            run_views(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
