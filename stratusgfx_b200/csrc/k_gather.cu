@@ -597,7 +597,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
-                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int counterSel, bool* signalled) {
+                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int64_t* persistentLaunches, bool* signalled) {
     if (signalled) *signalled = false;
     BandLinks plain = links;                 // the kernels without the in-kernel signal
     plain.doneCounter = nullptr;
@@ -611,6 +611,9 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
         const int cap = max(1, min(fc.totalNumLights, SGI_MAX_TOTAL_VPLS_PER_FRAME));
         const int bytes = cap * kTableBytesPerVpl;
         const int units = ((bd.W + 31) / 32) * bd.rows;
+        // the two work counters alternate between PERSISTENT launches (each launch re-arms the other one), so the parity is
+        // counted here and not per sgi_gather call: a tile-list or legacy launch in between must not flip it
+        const int counterSel = (int)((*persistentLaunches)++ & 1);
         // producers of the in-kernel signal: the 32-pixel segments of the rows pushed to a neighbour (pass 0 is pushed only when fused)
         BandLinks armed = links;
         if (armed.doneCounter != nullptr) {

@@ -193,6 +193,8 @@ int sgi_resize(SgiHandle h, int32_t width, int32_t full_height, int32_t y_offset
     if (checkDims(width, full_height, y_offset, rows) != SGI_OK) return fail(h, SGI_ERR_INVALID_ARG, "sgi_resize: bad dimensions");
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->tileStream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->copyStream));       // a band's rows may still be travelling to the owner's image
     sgi::detachPeers(h);
     freePlanes(h);
     h->banded = false;                      // a resized handle is a plain whole-range handle again; call sgi_band_setup to re-band
@@ -316,7 +318,7 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
                                fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
-                               h->gatherCounters, (int)(h->gatherLaunches++ & 1), &signalled);
+                               h->gatherCounters, &h->gatherLaunches, &signalled);
     if (h->banded && fuse && !signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it

@@ -259,7 +259,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
                  const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos,
-                 int* unitCounters /* two ints: work counters of the persistent gather */, int counterSel,
+                 int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
                  bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,

@@ -417,3 +417,21 @@ def test_c5_8k_4096vpl_band_parity_and_whole_view_properties(built):
     gp.frame(fp)
     assert np.array_equal(gp.output("lightingOut").view(np.uint16), first)                    # deterministic
     gp.close()
+
+
+def test_gather_modes_can_alternate_on_one_handle(tiny):
+    """Stochastic -> tile-list -> stochastic on the same handle: the persistent gather's two work counters alternate per
+    persistent launch, so a tile-list launch in between must not leave the next stochastic launch without work."""
+    gp = make_pass(tiny)
+    gp.set_gbuffer(tiny.gb[0], tiny.gb[-1]); gp.bind()
+    fp = tiny.fp[0].copy()
+    outs = []
+    for mode in (_abi.GATHER_STOCHASTIC, _abi.GATHER_TILE_LIST, _abi.GATHER_STOCHASTIC, _abi.GATHER_STOCHASTIC, _abi.GATHER_TILE_LIST, _abi.GATHER_STOCHASTIC):
+        fp.gatherMode = mode
+        gp.cull(fp); gp.color(fp); gp.tile_lists(fp); gp.gather(fp)
+        outs.append((mode, gp.plane(_abi.PLANE_GI_RESERVOIR).view(np.uint16).copy()))
+    sto = [o for m, o in outs if m == _abi.GATHER_STOCHASTIC]
+    til = [o for m, o in outs if m == _abi.GATHER_TILE_LIST]
+    assert sto[0].any() and all(np.array_equal(sto[0], o) for o in sto[1:])
+    assert all(np.array_equal(til[0], o) for o in til[1:]) and not np.array_equal(til[0], sto[0])
+    gp.close()
