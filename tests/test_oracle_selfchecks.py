@@ -305,3 +305,21 @@ def test_vpl_prepass_equals_stable_sort_restatement(n, seed):
         assert np.array_equal(vd[:, 0:3], rec["position"][order]) and np.all(vd[:, 3] == 1.0) and np.all(vd[:, 4:12] == 0.0)
         assert np.array_equal(vd[:, 12], rec["radius"][order]) and np.array_equal(vd[:, 13], rec["farPlane"][order])
         assert np.array_equal(at[:, 0], rec["atlasIndex"][order]) and np.array_equal(at[:, 1], rec["atlasLayer"][order])
+
+
+# ---- golden fixture made with the reference's glm (tests/golden/make_glm_golden.py) -------------------------------------
+def _load_glm_golden():
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_glm_golden.json")
+    return json.load(open(path))
+
+
+def test_own_maths_oracle_reproduces_the_glm_golden_fixture(built):
+    """The fixture was computed by the oracle source compiled against the reference's vendored glm; the oracle's own maths
+    layer must give the same integer outputs and the same bytes for every float plane — on any box, reference tree or not."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_glm_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_glm_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    got, want = mod.compute("own"), _load_glm_golden()
+    assert got["frames"] == want["frames"]
+    assert got["prepass"] == want["prepass"]

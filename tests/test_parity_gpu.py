@@ -435,3 +435,32 @@ def test_gather_modes_can_alternate_on_one_handle(tiny):
     assert sto[0].any() and all(np.array_equal(sto[0], o) for o in sto[1:])
     assert all(np.array_equal(til[0], o) for o in til[1:]) and not np.array_equal(til[0], sto[0])
     gp.close()
+
+
+def test_cuda_integer_outputs_match_the_glm_golden_fixture(tiny):
+    """Committed fixture (tests/golden/tiny_glm_golden.json, made with the reference's glm): the CUDA path's visible list,
+    atlas entries, per-tile lists and pre-pass order must equal it exactly, with no oracle in the loop."""
+    import json
+    import os
+    from stratusgfx_b200.prepass import frustum_planes
+    from tests.test_oracle_selfchecks import _random_lights
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_glm_golden.json")))
+    cu = run_cuda_staged(tiny)
+    for f in range(2):
+        g = gold["frames"][f]
+        V = g["V"]
+        assert cu[f]["V"] == V and cu[f]["visible"][:V + 1].tolist() == g["visible"]
+        assert cu[f]["entries"][:V].reshape(-1).tolist() == g["entries"]
+        cnt = cu[f]["stage2"][:, 0]
+        assert cnt.tolist() == g["stage2_counts"]
+        mask = np.arange(12)[None, :] < cnt[:, None]
+        assert cu[f]["stage2"][:, 1:][mask].tolist() == g["stage2_indices"]
+    p = gold["prepass"]
+    rec = _random_lights(p["n"], p["seed"])
+    gp = make_pass(tiny)
+    gp.set_lights(rec)
+    gp.vpl_prepass(list(tiny.fp[0].viewPosition), frustum_planes(list(tiny.fp[0].invProjectionView)))
+    gp.synchronize()
+    count = int(gp.t["vplCountDevice"].cpu().numpy()[0])
+    assert gp.t["prepassOrder"].cpu().numpy()[:count].tolist() == p["order"]
+    gp.close()
