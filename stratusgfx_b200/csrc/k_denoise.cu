@@ -192,6 +192,8 @@ __device__ __forceinline__ int boundaryFirst(int p, int n) {
 template <bool FINAL>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
+    SGI_PDL_WAIT();                                          // (experiment, see sgi_internal.h) the previous pass / the gather is complete from here on
+    SGI_PDL_LAUNCH_DEPENDENTS();
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
     const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
@@ -325,8 +327,8 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
             if (io.links.producers == 0) io.links.doneCounter = nullptr;
             else if (signalled) *signalled = true;
         }
-        if (final_) atrousKernel<true><<<grid, block, 0, stream>>>(fc, bd, io);
-        else atrousKernel<false><<<grid, block, 0, stream>>>(fc, bd, io);
+        if (final_) SGI_LAUNCH_CHAINED(atrousKernel<true>, grid, block, 0, stream, fc, bd, io);
+        else SGI_LAUNCH_CHAINED(atrousKernel<false>, grid, block, 0, stream, fc, bd, io);
     }
     return 1;
 }
