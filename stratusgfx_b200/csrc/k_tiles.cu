@@ -387,7 +387,7 @@ int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
     return 1;
 }
 
-int launchStage2(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
+int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
                  const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, int* patchScratch) {
     const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.crows / SGI_TILE_DIVISOR;
     if (tilesX <= 0 || tilesY <= 0) return 0;

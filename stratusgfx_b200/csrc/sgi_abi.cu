@@ -280,7 +280,7 @@ static int tileListsOn(SgiHandle h, const SgiFrameParams* fp, cudaStream_t strea
     int n = launchStage1(stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch,
                          h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->posRadius);
     // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
-    n += launchStage2(stream, fc, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
+    n += launchStage2(stream, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
     h->tileListsValid = true;
     return postLaunch(h, n);
 }

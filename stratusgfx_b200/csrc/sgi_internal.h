@@ -275,7 +275,7 @@ int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t
 int patchScratchInts(const BandDims& bd);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius);
-int launchStage2(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
+int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
                  const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, int* patchScratch);
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
