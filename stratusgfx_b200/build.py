@@ -47,10 +47,31 @@ def build_native(force=False, verbose=False):
     return LIB
 
 
+HOST_DIR = os.path.join(_HERE, "host")
+HOST_BIN = os.path.join(HOST_DIR, "host_frame")
+
+
+def build_host(force=False):
+    """The C++ host side above the C-ABI (host/stratus_gi_backend.h) and its driver program (host/host_frame.cpp): g++ against
+    the two in-tree libraries and the CUDA runtime (device memory only)."""
+    src = os.path.join(HOST_DIR, "host_frame.cpp")
+    deps = [src, os.path.join(HOST_DIR, "stratus_gi_backend.h"), os.path.join(_HERE, "..", "include", "stratusgi.h"), LIB]
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) >= _newest(deps):
+        return HOST_BIN
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(cuda, "include"), src, "-o", HOST_BIN,
+                           "-L" + CSRC, "-L" + os.path.join(_HERE, "scene"), "-L" + os.path.join(cuda, "lib64"),
+                           "-l:libstratusgi.so", "-l:libsgi_scene.so", "-lcudart",
+                           "-Wl,-rpath,$ORIGIN/../csrc", "-Wl,-rpath,$ORIGIN/../scene", "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return HOST_BIN
+
+
 def build_all(force=False, verbose=False):
     from .scene import build as build_scene
     build_scene(force)
-    return build_native(force, verbose)
+    lib = build_native(force, verbose)
+    build_host(force)
+    return lib
 
 
 if __name__ == "__main__":
