@@ -78,3 +78,41 @@ def test_two_rank_gloo_bands_reproduce_the_whole_frame(built, tmp_path, cuts):
     whole = run_oracle(SceneData(workload), keep_passes=False)[0]["combined"]
     # apron rows make every owned row see exactly the taps it would see in the whole frame
     assert np.array_equal(assembled.view(np.uint16), whole.view(np.uint16))
+
+
+# ---- property tests of the host-side band planning (hypothesis) ------------------------------------------------------------
+def test_balanced_cuts_are_always_a_valid_partition():
+    """Whatever the measured times, balance_cuts must return cuts on the 5-row tile grid that start at 0, end at the frame
+    height, increase strictly and leave every band at least as tall as the halo — i.e. something bands_from_cuts accepts."""
+    from hypothesis import given, settings, strategies as st
+    from stratusgfx_b200.bands import TILE, balance_cuts, bands_from_cuts, halo_rows, plan_bands
+
+    @settings(max_examples=200, deadline=None)
+    @given(world=st.sampled_from([2, 3, 4, 8]), tiles_per_band=st.integers(5, 120), iters=st.integers(1, 5),
+           times=st.lists(st.floats(1e-3, 10.0, allow_nan=False, allow_infinity=False), min_size=8, max_size=8))
+    def check(world, tiles_per_band, iters, times):
+        halo = halo_rows(iters)
+        height = world * tiles_per_band * TILE
+        if height // world < halo:
+            return
+        bands = plan_bands(height, world, halo)
+        cuts = balance_cuts(bands, times[:world], height, halo)
+        assert cuts[0] == 0 and cuts[-1] == height and len(cuts) == world + 1
+        assert all(c % TILE == 0 for c in cuts) and all(b - a >= max(halo, TILE) for a, b in zip(cuts, cuts[1:]))
+        out = bands_from_cuts(cuts, height, halo)
+        assert [b.b0 for b in out] == cuts[:-1] and [b.b1 for b in out] == cuts[1:]
+        for b in out:                                   # held rows = owned rows + halo, clipped to the frame
+            assert b.y0 == max(0, b.b0 - halo) and b.y1 == min(height, b.b1 + halo)
+        # equal times leave equal bands where they were
+        same = balance_cuts(bands, [1.0] * world, height, halo)
+        assert same == [r * (height // world) for r in range(world)] + [height]
+
+    check()
+
+
+def test_halo_rows_cover_the_reach_of_the_widest_pass():
+    from stratusgfx_b200.bands import TILE, halo_rows
+    for iters in range(1, 7):
+        reach = 2 * (1 << (iters - 1)) if iters > 1 else 0          # 2 * (multiplier + 1), multiplier = 2^(iters-1) - 1 (BE:1920)
+        h = halo_rows(iters)
+        assert h >= reach and h % TILE == 0 and h - reach < TILE
