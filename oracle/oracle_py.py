@@ -36,7 +36,27 @@ def build(force=False):
         out_glm = os.path.join(ref_dir, "liboracle_glm.so")
         if force or not os.path.exists(out_glm) or os.path.getmtime(out_glm) < newest:
             subprocess.check_call(["g++"] + _FLAGS + ["-DORACLE_USE_GLM", "-I" + _REFERENCE_ROOT, "-o", out_glm, src])
+        # the reference headers that compile here (StratusMath.h, StratusGpuCommon.h), unmodified, behind a shim (oracle/ref_shim.cpp)
+        shim = os.path.join(_HERE, "ref_shim.cpp")
+        engine = os.path.join(_REFERENCE_ROOT, "Source", "Engine")
+        out_ref = os.path.join(ref_dir, "libref_stratus.so")
+        if os.path.isdir(engine) and (force or not os.path.exists(out_ref) or os.path.getmtime(out_ref) < os.path.getmtime(shim)):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DGLM_FORCE_PURE",
+                                   "-I" + os.path.join(_HERE, "ref_stubs"), "-I" + engine, "-I" + _REFERENCE_ROOT,
+                                   "-I" + os.path.join(_REFERENCE_ROOT, "glm"), "-o", out_ref, shim])
     return out
+
+
+def reference_shim():
+    """ctypes handle of oracle/_ref/libref_stratus.so (reference code compiled here), or None where it was never built."""
+    path = os.path.join(_HERE, "_ref", "libref_stratus.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_is_sphere_in_frustum.argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+    L.ref_layout.argtypes = [C.c_void_p]
+    L.ref_init_vpl_frame_data.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    return L
 
 
 class OrcDims(C.Structure):

@@ -464,3 +464,23 @@ def test_cuda_integer_outputs_match_the_glm_golden_fixture(tiny):
     count = int(gp.t["vplCountDevice"].cpu().numpy()[0])
     assert gp.t["prepassOrder"].cpu().numpy()[:count].tolist() == p["order"]
     gp.close()
+
+
+def test_vpl_prepass_frustum_boundary_cases(tiny):
+    """Spheres that touch a frustum plane from outside (distance == -radius) are kept, a float ulp further out they are dropped:
+    the cases of tests/test_reference_shim.py::test_reference_frustum_test_boundary_semantics, on the device."""
+    from oracle import oracle_py as O
+    from stratusgfx_b200.prepass import LIGHT_DTYPE
+    planes = np.array([[1, 0, 0, 0], [-1, 0, 0, 100], [0, 1, 0, 0], [0, -1, 0, 100], [0, 0, 1, 0], [0, 0, -1, 100]], np.float32)
+    rec = np.zeros(6, LIGHT_DTYPE)
+    rec["position"] = [[-2, 50, 50], [-2.0000002, 50, 50], [50, 102, 50], [50, 50, -1.9999999], [50, 50, 50], [103, 50, 50]]
+    rec["radius"] = 2.0; rec["farPlane"] = 2.0; rec["intensity"] = 1.0
+    vd, at, order = O.vpl_prepass(rec, [50, 50, 50], planes)
+    assert sorted(order.tolist()) == [0, 2, 3, 4]
+    gp = make_pass(tiny)
+    gp.set_lights(rec)
+    gp.vpl_prepass([50, 50, 50], planes)
+    gp.synchronize()
+    count = int(gp.t["vplCountDevice"].cpu().numpy()[0])
+    assert count == 4 and np.array_equal(gp.t["prepassOrder"].cpu().numpy()[:4], order)
+    gp.close()
