@@ -9,7 +9,9 @@
 // (no OpenGL).  What pins this file instead: (1) the maths layer is cross-checked bit
 // for bit against the reference's own vendored glm (oracle/_ref build, -DORACLE_USE_GLM);
 // (2) the self-checks of SURVEY.md §8(c) in tests/test_oracle_selfchecks.py;
-// (3) frozen RNG known answers (tests/golden/).
+// (3) frozen RNG known answers and a fixture made with the glm-backed build (tests/golden/);
+// (4) for the pre-pass and the wire formats only: the reference's own StratusMath.h / StratusGpuCommon.h compiled
+//     behind oracle/ref_shim.cpp (tests/test_reference_shim.py).
 //
 // Each function follows one shader entry point; citations are relative to the
 // StratusGFX tree.  GL fixed-function semantics (texel addressing, cube-face
