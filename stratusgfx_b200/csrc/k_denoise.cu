@@ -165,6 +165,14 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 
+// -DSGI_ATROUS_V2 (experiment, off by default; results are bit-identical by construction): 32-bit element indices for the tap
+// addresses (one IMAD.WIDE per load instead of an LEA pair; a band never holds 2^32 pixels) and the four accumulations of a
+// tap as two packed fma.rn.f32x2 (FFMA2 on sm_100a; IEEE per lane, and fma(w, 1, a) == a + w)
+SGI_DEV unsigned long long pack2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+SGI_DEV void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+SGI_DEV unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
 SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -221,12 +229,18 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     }
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
     float acc[kLat][4];
+#ifdef SGI_ATROUS_V2
+    unsigned long long accRG[kLat], accBW[kLat];            // packed (r, g) and (b, sum of weights)
+#endif
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
         const int ly = min(c0 + (m0 + k) * s + r, rows - 1);
         cen[k] = __ldg(io.guide + (size_t)ly * W + x);
         cen[k].w *= kLog2e;
         acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+#ifdef SGI_ATROUS_V2
+        accRG[k] = pack2(0.0f, 0.0f); accBW[k] = pack2(0.0f, 0.0f);
+#endif
     }
     int txs[5];
     #pragma unroll
@@ -235,16 +249,29 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     #pragma unroll
     for (int c = 0; c < kLat + 4; ++c) {
         // band-local clamp == CLAMP_TO_EDGE on a whole frame
+#ifdef SGI_ATROUS_V2
+        const unsigned int rowBase = (unsigned int)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * (unsigned int)W;
+#else
         const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
         const float4* __restrict__ rowG = io.guide + rowBase;
         const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
+#endif
         #pragma unroll
         for (int d = 0; d < 5; ++d) {
+#ifdef SGI_ATROUS_V2
+            const unsigned int idx = rowBase + (unsigned int)txs[d];
+            const float4 gq = __ldg(io.guide + idx);
+            const uint2 rv = __ldg(io.shadowsIn + idx);
+#else
             const float4 gq = __ldg(rowG + txs[d]);
             const uint2 rv = __ldg(rowS + txs[d]);
+#endif
             // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly
             const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
             const float tq = gq.w * kLog2e;
+#ifdef SGI_ATROUS_V2
+            const unsigned long long cRG = pack2(rr, rg), cB1 = pack2(rb, 1.0f);
+#endif
             #pragma unroll
             for (int k = 0; k < kLat; ++k) {
                 const int dy = c - 2 - k;
@@ -255,11 +282,20 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
                     const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
                     w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
                 }
+#ifdef SGI_ATROUS_V2
+                const unsigned long long ww = pack2(w, w);
+                accRG[k] = fma2(ww, cRG, accRG[k]); accBW[k] = fma2(ww, cB1, accBW[k]);
+#else
                 acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
                 acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
+#endif
             }
         }
     }
+#ifdef SGI_ATROUS_V2
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) { unpack2(accRG[k], acc[k][0], acc[k][1]); unpack2(accBW[k], acc[k][2], acc[k][3]); }
+#endif
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
