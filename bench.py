@@ -39,12 +39,46 @@ def workload_text(s):
 
 # ---- clocks during the timed region (B200_PROFILING.md) -----------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons while the timed region runs.  Two samplers run side by side: NVML (nvidia_ml_py) polled
+    every ~2 ms from a thread — the timed region of a 1.3-ms frame is short, nvidia-smi's 100-ms loop would see one or two
+    samples of it — and `nvidia-smi -lms 100` as the fallback when NVML is unusable.  Any failure degrades to "unavailable";
+    it never breaks the bench."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}     # nvmlClocksEventReason*
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml_sm, self.nvml_max, self.nvml_reasons, self._stop, self.nvml_thread = [], None, 0, False, None
+        self._begin, self._end = 0, None
+
+    def mark_begin(self):          # the timed region starts: only NVML samples taken between the marks are reported
+        self._begin = len(self.nvml_sm)
+        self.nvml_reasons = 0
+
+    def mark_end(self):
+        self._end = len(self.nvml_sm)
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop:
+                self.nvml_sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.nvml_reasons |= int(get_reasons(h))
+                time.sleep(0.002)
+        except Exception:
+            self.nvml_sm = []          # NVML unusable: the nvidia-smi rows are used instead
 
     def start(self):
+        try:
+            self.nvml_thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.nvml_thread.start()
+        except Exception:
+            self.nvml_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -58,15 +92,23 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        self._stop = True
+        if self.nvml_thread is not None:
+            self.nvml_thread.join(timeout=1.0)
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.nvml_sm:
+            inside = self.nvml_sm[self._begin:self._end] or self.nvml_sm
+            reasons = sorted(n for n in self.NAMES if self.nvml_reasons & self.BITS[n])
+            return {"sm_mhz": float(np.median(inside)), "sm_max_mhz": self.nvml_max, "samples": len(inside), "reasons": reasons,
+                    "source": "nvml, 2 ms poll, samples inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -75,10 +117,10 @@ class ClockSampler:
                 sm.append(float(f[0])); mx = float(f[1])
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---- algorithmic bytes per stage, for the roofline -----------------------------------------------
@@ -300,6 +342,8 @@ def run_ours(args, rank, world, local_rank):
     launches0 = gp.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    if rank == 0:
+        sampler.mark_begin()
     e0.record()
     t_host0 = time.perf_counter()
     for i in range(args.steps):
@@ -308,6 +352,8 @@ def run_ours(args, rank, world, local_rank):
     finish()                                  # the last frame's image is assembled (and the look-ahead broadcast drained) inside the timed region
     e1.record()
     fence()
+    if rank == 0:
+        sampler.mark_end()
     ms_total = e0.elapsed_time(e1)
     launches = gp.launch_count() - launches0
     if world > 1:
@@ -466,12 +512,16 @@ def run_views(args, rank, world, local_rank):
         launches0 = gp.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fence()
+        if rank == 0:
+            sampler.mark_begin()
         e0.record()
         for i in range(args.steps):
             fp.time = 1000.0 + 16.0 * (args.warmup + i)
             gp.frame(fp)
         e1.record()
         fence()
+        if rank == 0:
+            sampler.mark_end()
         ms_total = e0.elapsed_time(e1)
         launches = gp.launch_count() - launches0
         V = gp.visible_count()
