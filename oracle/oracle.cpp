@@ -318,6 +318,27 @@ int orc_uses_glm(void) {
 #endif
 }
 
+// ---- test hooks: the restated pure-maths functions, callable one at a time (tests/test_reference_glsl.py holds them against the
+// reference's own GLSL text compiled as C++, oracle/make_ref_glsl.py) ----
+// a: fragPosition, baseColor, normal, viewDir, specularLightPos, diffuseLightPos, lightColor (7 x vec3), then viewDist, lightRadius,
+//    roughness, metallic, ambientOcclusion, shadowFactor (6 floats), then baseReflectance (vec3): 30 floats
+void orc_test_vpl_lighting(const SgiFrameParams* fp, const float* a, float* out3) {
+    auto v = [&](int i) { return vec3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); };
+    const vec3 r = calculateVirtualPointLighting2(*fp, v(0), v(1), v(2), v(3), v(4), v(5), v(6), a[21], a[22], a[23], a[24], a[25], a[26],
+                                                  vec3(a[27], a[28], a[29]));
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+void orc_test_world_pos(float u, float v, float depth, const float* invPV16, float* out3) {
+    const vec3 r = worldPositionFromDepth(vec2(u, v), depth, loadMat(invPV16));
+    out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+float orc_test_shadow1(const void* atlas, int res, int layer, float farPlane, const float* fragPos, const float* lightPos, float lightNormalDot, float minBias) {
+    const void* atlases[SGI_MAX_TOTAL_SHADOW_ATLASES] = {atlas};
+    SgiAtlasEntry e; e.index = 0; e.layer = layer;
+    return calculateShadowValue1Sample(atlases, e, res, farPlane, vec3(fragPos[0], fragPos[1], fragPos[2]), vec3(lightPos[0], lightPos[1], lightPos[2]), lightNormalDot, minBias);
+}
+float orc_test_attenuation(const float* dir3, float radius) { return vplDiffuseAttenuation(vec3(dir3[0], dir3[1], dir3[2]), radius); }
+
 // a1: viscull_vpls.cs:47-106.  Canonical order = ascending original index, which is one legal
 // interleaving of the reference's 8 racing helper threads and what its serial variant (:108-119) did.
 int orc_cull(const SgiFrameParams* fp, const OrcDims* dm, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,

@@ -44,7 +44,66 @@ def build(force=False):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-DGLM_FORCE_PURE",
                                    "-I" + os.path.join(_HERE, "ref_stubs"), "-I" + engine, "-I" + _REFERENCE_ROOT,
                                    "-I" + os.path.join(_REFERENCE_ROOT, "glm"), "-o", out_ref, shim])
+        # the reference's own GLSL text for the gather's pure-maths functions, compiled as C++ against its glm (oracle/make_ref_glsl.py)
+        try:
+            from oracle import make_ref_glsl
+        except ImportError:
+            import make_ref_glsl
+        make_ref_glsl.build(force)
     return out
+
+
+def reference_glsl():
+    """ctypes handle of oracle/_ref/libref_glsl.so (the reference's GLSL functions compiled here), or None where it was never built."""
+    path = os.path.join(_HERE, "_ref", "libref_glsl.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.refglsl_set_uniforms.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_float]
+    L.refglsl_vpl_lighting.argtypes = [C.c_void_p, C.c_void_p]
+    L.refglsl_world_pos.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.refglsl_random3.argtypes = [C.c_float] * 3
+    L.refglsl_random3.restype = C.c_float
+    L.refglsl_hash3.argtypes = [C.c_float] * 3
+    L.refglsl_hash3.restype = C.c_uint32
+    L.refglsl_attenuation.argtypes = [C.c_void_p, C.c_float]
+    L.refglsl_attenuation.restype = C.c_float
+    L.refglsl_bound_hdr.argtypes = [C.c_float]
+    L.refglsl_bound_hdr.restype = C.c_float
+    L.refglsl_gather.argtypes = [C.c_void_p]
+    return L
+
+
+class RefGatherArgs(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int), ("cubeRes", C.c_int), ("numAtlases", C.c_int)] + \
+               [(n, C.c_void_p) for n in ("depth", "normal4", "albedo4", "refl2", "rma4", "ssaoH", "screenH4", "viewPosition", "invProjectionView")] + \
+               [("time", C.c_float), ("minGiOcclusionFactor", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("lightData", "numVisible", "shadowIndices", "shadowAtlases", "colorOut3", "reservoirOut4")]
+
+
+def reference_glsl_gather(ref, fp, gb, updated, visible, entries, shadow_atlas, cube_res):
+    """vpl_pbr_gi.fs (the reference's shader text compiled as C++) over one frame: float `color` [H,W,3] and `reservoir` [H,W,4]
+    as written by the shader, before the 16F framebuffer store.  `updated`/`visible`/`entries` are the coloured compacted VPL
+    table, the visible list and shadowDiffuseIndices (the outputs of the two stages before the gather)."""
+    H, W = gb.depth.shape
+    color = np.zeros((H, W, 3), np.float32)
+    res = np.zeros((H, W, 4), np.float32)
+    a = RefGatherArgs()
+    a.W, a.H, a.cubeRes, a.numAtlases = W, H, cube_res, int(shadow_atlas.shape[0])
+    tab = _atlas_ptrs(shadow_atlas)
+    vp = np.ascontiguousarray(list(fp.viewPosition), np.float32)
+    ipv = np.ascontiguousarray(list(fp.invProjectionView), np.float32)
+    fog = np.ascontiguousarray(list(fp.fogColor), np.float32)
+    ref.refglsl_set_uniforms(int(fp.usePerceptualRoughness), float(fp.minRoughness), _p(fog), float(fp.fogDensity))
+    keep = [np.ascontiguousarray(x) for x in (gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao, gb.screen,
+                                              updated, visible, entries)]
+    (a.depth, a.normal4, a.albedo4, a.refl2, a.rma4, a.ssaoH, a.screenH4, a.lightData, a.numVisible, a.shadowIndices) = [x.ctypes.data for x in keep]
+    a.viewPosition, a.invProjectionView = vp.ctypes.data, ipv.ctypes.data
+    a.time, a.minGiOcclusionFactor = float(fp.time), float(fp.minGiOcclusionFactor)
+    a.shadowAtlases = C.addressof(tab)
+    a.colorOut3, a.reservoirOut4 = color.ctypes.data, res.ctypes.data
+    ref.refglsl_gather(C.addressof(a))
+    return color, res
 
 
 def reference_shim():
@@ -102,6 +161,10 @@ def lib(variant="own"):
         L.orc_stage2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_denoise_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_vpl_prepass.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_test_vpl_lighting.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_test_world_pos.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_test_attenuation.argtypes = [C.c_void_p, C.c_float]
+        L.orc_test_attenuation.restype = C.c_float
         _libs[variant] = L
     return _libs[variant]
 

@@ -1,0 +1,117 @@
+"""The reference's own GLSL, compiled: oracle/make_ref_glsl.py turns the texture-free functions of pbr2.glsl, pbr.glsl, fog.glsl and
+common.glsl that the VPL gather calls into C++ against the reference's vendored glm (oracle/_ref/libref_glsl.so).  The oracle's
+restatement of the same functions must agree with that shader text bit for bit.  Skipped where the library was never built
+(it is built wherever /root/reference exists and travels with the repository)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from stratusgfx_b200._abi import FrameParams
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    from oracle import oracle_py
+    ref = oracle_py.reference_glsl()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree)")
+    return oracle_py.lib(), ref
+
+
+def _bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def test_rng_of_the_shader_text(libs):
+    """hash(uvec3) / floatConstruct / random(vec3) (common.glsl:183-214): pure integer arithmetic on the float bits."""
+    orc, ref = libs
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        x, y, t = np.float32(rng.integers(0, 7680) + 0.5), np.float32(rng.integers(0, 4320) + 0.5), np.float32(1000.0 + 16.0 * rng.integers(0, 100000))
+        assert orc.orc_hash3(x, y, t) == ref.refglsl_hash3(x, y, t)
+        assert _bits(orc.orc_random3(x, y, t)) == _bits(ref.refglsl_random3(x, y, t))
+
+
+def test_world_position_from_depth_of_the_shader_text(libs):
+    """worldPositionFromDepth (common.glsl:143-155) on the scene's own inverse projection-view matrices."""
+    from stratusgfx_b200.scene import Scene
+    orc, ref = libs
+    rng = np.random.default_rng(2)
+    for wl in ("tiny", "c3"):
+        fp = Scene(wl, yaw_deg_per_frame=0.25).frame_params(3)
+        m = np.ascontiguousarray(list(fp.invProjectionView), np.float32)
+        a, b = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        for _ in range(2000):
+            u, v, d = np.float32(rng.random()), np.float32(rng.random()), np.float32(rng.random())
+            orc.orc_test_world_pos(u, v, d, m.ctypes.data, a.ctypes.data)
+            ref.refglsl_world_pos(u, v, d, m.ctypes.data, b.ctypes.data)
+            assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_vpl_attenuation_of_the_shader_text(libs):
+    orc, ref = libs
+    rng = np.random.default_rng(3)
+    for _ in range(4000):
+        d = np.ascontiguousarray(rng.normal(0, 200, 3), np.float32)
+        r = np.float32(rng.choice([5.0, 50.0, 500.0]))
+        assert _bits(orc.orc_test_attenuation(d.ctypes.data, r)) == _bits(ref.refglsl_attenuation(d.ctypes.data, r))
+    assert ref.refglsl_bound_hdr(1e6) == 65504.0 and ref.refglsl_bound_hdr(3.5) == 3.5
+
+
+@pytest.mark.parametrize("perceptual,min_rough,fog_density", [(1, 0.08, 0.0), (0, 0.08, 0.0), (1, 0.3, 0.002)])
+def test_virtual_point_lighting_of_the_shader_text(libs, perceptual, min_rough, fog_density):
+    """calculateVirtualPointLighting2 (pbr2.glsl:613-657) and everything under it — calculateLighting_Lambert_SeparateDiffuseSpecular,
+    BRDF_Lambert_SeparateDiffuseSpecular, BRDF_Base, BRDF_DotProducts, singleScatteringBRDF_Specular, NDF_GGX, Visibility_G_SmithGGX,
+    Fr_Fresnel_Schlick, RemapRoughness, vplDiffuseAttenuation, applyFog — on random surfaces and lights: the oracle's restatement must
+    return the bytes the shader text returns."""
+    orc, ref = libs
+    fp = FrameParams()
+    fp.usePerceptualRoughness, fp.minRoughness, fp.fogDensity = perceptual, min_rough, fog_density
+    fog = np.array([0.5, 0.6, 0.7], np.float32)
+    for i in range(3):
+        fp.fogColor[i] = float(fog[i])
+    ref.refglsl_set_uniforms(perceptual, min_rough, fog.ctypes.data, fog_density)
+    rng = np.random.default_rng(4)
+    a, o1, o2 = np.zeros(30, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+    nonzero = 0
+    for _ in range(5000):
+        unit = lambda: (lambda v: v / np.linalg.norm(v))(rng.normal(0, 1, 3))
+        a[0:3] = rng.uniform(-100, 100, 3)                     # fragPosition
+        a[3:6] = np.maximum(rng.integers(0, 256, 3) / 255.0, 0.01)   # baseColor, floored as the gather does (vpl_pbr_gi.fs:118)
+        a[6:9] = unit(); a[9:12] = unit()                       # normal, viewDir
+        a[12:15] = a[0:3] + rng.normal(0, 60, 3); a[15:18] = a[12:15] + rng.normal(0, 3, 3)    # specular / diffuse light position
+        a[18:21] = rng.uniform(0, 30, 3)                        # lightColor
+        a[21] = rng.uniform(1, 900); a[22] = rng.choice([50.0, 500.0])       # viewDist, lightRadius
+        a[23] = max(0.5, rng.integers(0, 256) / 255.0); a[24] = rng.choice([0.0, 0.0, rng.random()])   # roughness, metallic
+        a[25] = np.clip(rng.random(), 0.35, 1.0); a[26] = rng.choice([0.0, 1.0, rng.random()])        # ambient occlusion, shadow factor
+        a[27:30] = rng.integers(0, 256) / 255.0                 # baseReflectance (vec3(r))
+        orc.orc_test_vpl_lighting(C.addressof(fp), a.ctypes.data, o1.ctypes.data)
+        ref.refglsl_vpl_lighting(a.ctypes.data, o2.ctypes.data)
+        assert np.array_equal(_bits(o1), _bits(o2)), (a, o1, o2)
+        nonzero += int(np.any(o2 != 0))
+    assert nonzero > 1000                                        # (lights behind the surface or fully shadowed give exactly 0 in both)
+
+
+@pytest.mark.parametrize("workload,frame", [("tiny", 0), ("tiny", 1), ("c1", 0)])
+def test_whole_gather_shader_text_against_the_oracle(libs, workload, frame):
+    """vpl_pbr_gi.fs as a whole: `performLightingCalculations` — the sample budget, the draw / re-draw loop with `--i; continue;`,
+    the cube-shadow test, the occlusion floor and re-weighting, the BRDF chain, `boundHDR` — compiled from the reference's shader
+    text and run over a full frame.  After the RGB16F / RGBA16F store (IEEE round-to-nearest-even) its two outputs must be the
+    oracle's planes bit for bit: every light choice, every shadow verdict and every radiance value of every pixel."""
+    from oracle.oracle_py import OracleFrame, reference_glsl_gather
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData(workload, frames=frame + 1)
+    s = d.scene
+    o = OracleFrame(d.W, d.H, s.cube_res, s.csm_res, s.denoise_iters)
+    fp, gb = d.fp[frame], d.gb[frame]
+    o.cull(fp, d.vpl_data, d.atlas_by_vpl, d.csm[frame])
+    o.color(fp, d.shadow_atlas, d.diffuse_atlas)
+    o.gather(fp, gb)
+    color, res = reference_glsl_gather(ref, fp, gb, o.updated, o.visible, o.entries, d.shadow_atlas, s.cube_res)
+    with np.errstate(over="ignore"):
+        color_h, res_h = color.astype(np.float16), res.astype(np.float16)
+    assert np.array_equal(color_h.view(np.uint16), o.gi_color[..., :3].view(np.uint16))
+    assert np.array_equal(res_h.view(np.uint16), o.gi_reservoir.view(np.uint16))
+    assert float(res[..., :3].max()) > 0.0 and 1.0 <= float(res[..., 3].min()) and float(res[..., 3].max()) <= 6.0
