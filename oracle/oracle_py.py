@@ -71,7 +71,58 @@ def reference_glsl():
     L.refglsl_bound_hdr.argtypes = [C.c_float]
     L.refglsl_bound_hdr.restype = C.c_float
     L.refglsl_gather.argtypes = [C.c_void_p]
+    L.refglsl_denoise_pass.argtypes = [C.c_void_p]
     return L
+
+
+class RefDenoiseArgs(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int), ("multiplier", C.c_int), ("mergeReservoirs", C.c_int), ("final_", C.c_int),
+                ("time", C.c_float), ("framesPerSecond", C.c_float)] + \
+               [(n, C.c_void_p) for n in ("numVisible", "screenH4", "velocityH2", "normal4", "ids", "depth", "prevNormal4", "prevIds", "prevDepth",
+                                          "indirectIlluminationH4", "indirectShadowsH4", "prevIndirectIlluminationH4", "historyDepthH",
+                                          "combinedOut3", "giOut3", "reservoirOut4", "historyOut")]
+
+
+def _to_half(a):
+    with np.errstate(over="ignore"):
+        return a.astype(np.float16)          # the 16F framebuffer store: IEEE round-to-nearest-even, overflow to infinity
+
+
+class ReferenceGlslDenoiser:
+    """The host loop of StratusRendererBackend.cpp:1879-1952 around vpl_pbr_gi_denoise.fs compiled from the reference's shader text
+    (refglsl_denoise_pass): Fbo1/Fbo2 ping-pong, multiplier 2^i - 1, merge pass first, final pass last, swap with the previous-frame
+    FBO.  Attachments are stored as binary16 between passes, as the reference's RGB16F / RGBA16F / R16F targets do."""
+
+    def __init__(self, ref, W, H, denoise_iters):
+        self.ref, self.W, self.H, self.iters = ref, W, H, denoise_iters
+        self.prev_gi = np.zeros((H, W, 4), np.float16)
+        self.prev_history = np.zeros((H, W), np.float16)
+
+    def frame(self, fp, gb, prev_gb, num_visible, gi_color_h4, gi_reservoir_h4):
+        H, W = self.H, self.W
+        nv = np.array([num_visible], np.int32)
+        illum, shadows = np.ascontiguousarray(gi_color_h4), np.ascontiguousarray(gi_reservoir_h4)
+        passes = []
+        for i in range(self.iters):
+            a = RefDenoiseArgs()
+            a.W, a.H, a.multiplier = W, H, (1 << i) - 1
+            a.mergeReservoirs, a.final_ = (1 if i < 1 else 0), (1 if i + 1 == self.iters else 0)
+            a.time, a.framesPerSecond = float(fp.time), float(np.float32(1.0 / fp.deltaSeconds))
+            combined, gi = np.zeros((H, W, 3), np.float32), np.zeros((H, W, 3), np.float32)
+            res, hist = np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32)
+            keep = [np.ascontiguousarray(x) for x in (nv, gb.screen, gb.velocity, gb.normal, gb.id, gb.depth, prev_gb.normal, prev_gb.id, prev_gb.depth,
+                                                      illum, shadows, self.prev_gi, self.prev_history)]
+            (a.numVisible, a.screenH4, a.velocityH2, a.normal4, a.ids, a.depth, a.prevNormal4, a.prevIds, a.prevDepth,
+             a.indirectIlluminationH4, a.indirectShadowsH4, a.prevIndirectIlluminationH4, a.historyDepthH) = [x.ctypes.data for x in keep]
+            a.combinedOut3, a.giOut3, a.reservoirOut4, a.historyOut = combined.ctypes.data, gi.ctypes.data, res.ctypes.data, hist.ctypes.data
+            self.ref.refglsl_denoise_pass(C.addressof(a))
+            pad = lambda v3: np.concatenate([_to_half(v3), np.ones((H, W, 1), np.float16)], axis=-1)      # RGB16F read back as (r, g, b, 1)
+            fbo = dict(combined=pad(combined), gi=pad(gi), reservoir=_to_half(res), history=_to_half(hist))
+            illum, shadows = fbo["gi"], fbo["reservoir"]
+            passes.append(fbo)
+        last = passes[-1]
+        self.prev_gi, self.prev_history = last["gi"].copy(), last["history"].copy()
+        return passes
 
 
 class RefGatherArgs(C.Structure):

@@ -115,3 +115,36 @@ def test_whole_gather_shader_text_against_the_oracle(libs, workload, frame):
     assert np.array_equal(color_h.view(np.uint16), o.gi_color[..., :3].view(np.uint16))
     assert np.array_equal(res_h.view(np.uint16), o.gi_reservoir.view(np.uint16))
     assert float(res[..., :3].max()) > 0.0 and 1.0 <= float(res[..., 3].min()) and float(res[..., 3].max()) <= 6.0
+
+
+@pytest.mark.parametrize("workload,frames,yaw", [("tiny", 3, 0.0), ("tiny", 3, 0.25), ("c1", 1, 0.0)])
+def test_whole_denoiser_shader_text_against_the_oracle(libs, workload, frames, yaw):
+    """vpl_pbr_gi_denoise.fs as a whole — computeMergedReservoir (pass 0), the 25-tap filter with filterInput's pow/exp weights
+    (à-trous passes), the reprojection, the history reset decision, the temporal mix and the re-modulation (final pass) — compiled
+    from the reference's shader text and driven through the reference's host loop (BE:1879-1952) over several frames, static and
+    moving camera.  After the 16F stores, every pass's reservoir and the final pass's combined colour, GI and history planes must
+    equal the oracle's bit for bit."""
+    from oracle.oracle_py import OracleFrame, ReferenceGlslDenoiser
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData(workload, frames=frames, yaw_deg_per_frame=yaw)
+    s = d.scene
+    o = OracleFrame(d.W, d.H, s.cube_res, s.csm_res, s.denoise_iters)
+    rd = ReferenceGlslDenoiser(ref, d.W, d.H, s.denoise_iters)
+    resets = 0
+    for f in range(frames):
+        fp, gb, pgb = d.fp[f], d.gb[f], d.gb[f - 1]
+        o.cull(fp, d.vpl_data, d.atlas_by_vpl, d.csm[f]); o.color(fp, d.shadow_atlas, d.diffuse_atlas); o.gather(fp, gb)
+        passes = rd.frame(fp, gb, pgb, int(o.visible[0]), o.gi_color, o.gi_reservoir)      # same gather output into both denoisers
+        o.denoise(fp, gb, pgb, keep_passes=True)
+        for i, fbo in enumerate(passes):
+            assert np.array_equal(fbo["reservoir"].view(np.uint16), o.pass_reservoirs[i].view(np.uint16)), (f, i)
+        last = passes[-1]
+        assert np.array_equal(last["history"].view(np.uint16), o.history.view(np.uint16)), f
+        assert np.array_equal(last["gi"][..., :3].view(np.uint16), o.gi_illum[..., :3].view(np.uint16)), f
+        assert np.array_equal(last["combined"][..., :3].view(np.uint16), o.combined[..., :3].view(np.uint16)), f
+        resets += int(np.sum(last["history"] == np.float16(1.0))) if f > 0 else 0
+    if yaw != 0.0:
+        assert resets > 0                      # a moving camera resets the history somewhere (disocclusion): the decision path ran
+    elif frames > 1:
+        assert resets == 0 and float(o.history.max()) == float(frames)
