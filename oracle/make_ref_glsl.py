@@ -30,9 +30,9 @@ OUT_DIR = os.path.join(HERE, "_ref")
 
 # (file, function names in the order they are needed; every overload of a name is taken)
 WANTED = [
-    ("common.glsl", ["boundHDR", "saturate", "worldPositionFromDepth", "hash", "floatConstruct", "random", "sampleNormalWithOffset", "sampleNormal"]),
+    ("common.glsl", ["boundHDR", "saturate", "computeTexelSize", "worldPositionFromDepth", "hash", "floatConstruct", "random", "sampleNormalWithOffset", "sampleNormal"]),
     ("fog.glsl", ["applyFog"]),
-    ("pbr.glsl", ["calculateShadowValue1Sample", "vplDiffuseAttenuation", "vplSpecularAttenuation"]),
+    ("pbr.glsl", ["calculateShadowValue1Sample", "sampleShadowTexture", "calculateInfiniteShadowValue", "vplDiffuseAttenuation", "vplSpecularAttenuation"]),
     ("pbr2.glsl", ["NDF_GGX", "Visibility_G_SmithGGX", "Fr_Fresnel_Schlick", "Fd_Lambert", "singleScatteringBRDF_Specular",
                    "singleScatteringBRDF_Diffuse_Lambert", "RemapRoughness", "BRDF_Base", "BRDF_DotProducts",
                    "BRDF_Lambert_SeparateDiffuseSpecular", "calculateLighting_Lambert_SeparateDiffuseSpecular",
@@ -42,8 +42,15 @@ WANTED = [
 ]
 SHADER_CONSTS = [("vpl_pbr_gi_denoise.fs", ["sigmaZ", "sigmaN", "dminmax"])]        # file-scope `const T name = value;` the functions read
 SHADER_DEFINES = [("vpl_pbr_gi.fs", ["STANDARD_MAX_SAMPLES_PER_PIXEL", "ABSOLUTE_MAX_SAMPLES_PER_PIXEL", "MAX_RESAMPLES_PER_PIXEL"])]
-DEFINES = ["PI", "PREVENT_DIV_BY_ZERO", "HALF_FLOAT_MAX"]       # taken from common.glsl
-TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray)"
+DEFINES = ["PI", "PREVENT_DIV_BY_ZERO", "HALF_FLOAT_MAX", "FLOAT_MAX"]       # taken from common.glsl
+# the compute shaders: (file, nested namespace, name main() is emitted under, macros to take along)
+COMPUTE = [
+    ("vpl_light_color.cs", "cs_color", "color_main", []),
+    ("vpl_tiled_deferred_culling_stage1.cs", "cs_stage1", "stage1_main", []),
+    ("vpl_tiled_deferred_culling_stage2.cs", "cs_stage2", "stage2_main", ["SHUFFLE_DOWN"]),
+    ("viscull_vpls.cs", "cs_cull", "cull_main", []),
+]
+TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray|sampler2DArrayShadow)"
 
 
 def strip_comments(text):
@@ -65,8 +72,16 @@ def extract(text, name):
             j += 1
             if depth == 0:
                 break
+        if re.search(r"\bsamplerCube\b|\bsampler2DArray\b(?!Shadow)", text[m.start():j]):
+            continue                                    # an overload for a sampler type these shaders never use
         out.append(text[m.start():j])
     return out
+
+
+def extract_macro(text, name):
+    """A function-like `#define name(...)` with its continuation lines."""
+    m = re.search(r"^#define\s+" + re.escape(name) + r"\b.*?(?<!\\)\n", text, flags=re.M | re.S)
+    return m.group(0)
 
 
 def adapt(code):
@@ -75,8 +90,14 @@ def adapt(code):
     # parameter qualifiers
     code = re.sub(r"\b(?:out|inout)\s+(" + TYPES + r")\s+(\w+)", r"\1& \2", code)
     code = re.sub(r"\bin\s+(" + TYPES + r")\s+(\w+)", r"\1 \2", code)
-    # `v.rgb += expr;` (a swizzle as an l-value, vpl_pbr_gi_denoise.fs:232): glm's swizzle functions return copies, so spell it out
-    code = re.sub(r"(\b\w+)\.(?:rgb|xyz)\s*\+=\s*([^;]+);", r"swizzleAdd3(\1, \2);", code)
+    # swizzles as l-values (`v.rgb += e;`, `c[i].xyz = e;`, `p.xy = e;`): glm's swizzle functions return copies, so spell them out
+    lhs = r"((?:\b\w+)(?:\[[^\]]+\])?)"
+    code = re.sub(lhs + r"\.(?:rgb|xyz)\s*\+=\s*([^;]+);", r"swizzleAdd3(\1, \2);", code)
+    code = re.sub(lhs + r"\.(?:rgb|xyz)\s*=(?!=)\s*([^;]+);", r"swizzleSet3(\1, \2);", code)
+    code = re.sub(lhs + r"\.(?:rg|xy)\s*\+=\s*([^;]+);", r"swizzleAdd2(\1, \2);", code)
+    code = re.sub(lhs + r"\.(?:rg|xy)\s*=(?!=)\s*([^;]+);", r"swizzleSet2(\1, \2);", code)
+    # GLSL array constructors: `float a[2] = float[](x, y);`
+    code = re.sub(r"=\s*float\[\]\(([^;]*)\);", r"= {\1};", code)
     # multi-component swizzles used as values
     code = re.sub(r"\.((?:[xyzw]{2,4})|(?:[rgba]{2,4}))\b(?!\s*\()", r".\1()", code)
     return code
@@ -89,6 +110,9 @@ PRELUDE = r'''// GENERATED by oracle/make_ref_glsl.py from the reference's GLSL 
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <pthread.h>
+#include <thread>
+#include <vector>
 namespace refglsl {
 using namespace glm;
 // the uniforms these functions read (pbr2.glsl: usePerceptualRoughness, minRoughness; fog.glsl: fogColor, fogDensity)
@@ -152,10 +176,13 @@ static inline vec4 textureOffset(const sampler2D& s, vec2 uv, ivec2 offset) { re
 // textureSize returns ivec2 in GLSL; every use in these shaders converts it to float at once (`1.0 / textureSize(t, 0).xy`, `vec2 wh = textureSize(..)`)
 static inline vec2 textureSize(const sampler2D& s, int) { return vec2((float)s.W, (float)s.H); }
 template <class V, class S> static inline void swizzleAdd3(V& v, const S& s) { v.x += s.x; v.y += s.y; v.z += s.z; }
+template <class V, class S> static inline void swizzleSet3(V& v, const S& s) { const vec3 t(s); v.x = t.x; v.y = t.y; v.z = t.z; }
+template <class V, class S> static inline void swizzleAdd2(V& v, const S& s) { v.x += s.x; v.y += s.y; }
+template <class V, class S> static inline void swizzleSet2(V& v, const S& s) { const vec2 t(s); v.x = t.x; v.y = t.y; }
 static inline vec4 texture(const sampler2DRect& s, vec2 pixelCoords) {       // rectangle textures are addressed in pixels
     return fetchTexel(s.data, s.fmt, s.W, clampi((int)std::floor(pixelCoords.x), 0, s.W - 1), clampi((int)std::floor(pixelCoords.y), 0, s.H - 1));
 }
-struct samplerCubeArray { const unsigned short* data = nullptr; int res = 0; };      // DEPTH_COMPONENT16, [layer][face][res][res], NEAREST
+struct samplerCubeArray { const unsigned short* data = nullptr; int res = 0; const unsigned char* rgba8 = nullptr; };   // DEPTH_COMPONENT16 (or RGBA8), [layer][face][res][res], NEAREST
 static inline vec4 texture(const samplerCubeArray& s, vec4 dirLayer) {      // GL 4.6 table 8.19 (major axis, sc, tc), then the texel of the face
     const float x = dirLayer.x, y = dirLayer.y, z = dirLayer.z, ax = std::fabs(x), ay = std::fabs(y), az = std::fabs(z);
     int face; float sc, tc, ma;
@@ -165,9 +192,39 @@ static inline vec4 texture(const samplerCubeArray& s, vec4 dirLayer) {      // G
     const float sCoord = (sc / ma + 1.0f) / 2.0f, tCoord = (tc / ma + 1.0f) / 2.0f;
     const int i = clampi((int)std::floor(sCoord * (float)s.res), 0, s.res - 1), j = clampi((int)std::floor(tCoord * (float)s.res), 0, s.res - 1);
     const int layer = (int)dirLayer.w;
-    const unsigned short t = s.data[(((size_t)layer * 6 + face) * s.res + j) * s.res + i];
+    const size_t texel = (((size_t)layer * 6 + face) * s.res + j) * s.res + i;
+    if (s.rgba8 != nullptr) { const unsigned char* c = s.rgba8 + 4 * texel; return vec4(c[0] / 255.0f, c[1] / 255.0f, c[2] / 255.0f, c[3] / 255.0f); }
+    const unsigned short t = s.data[texel];
     return vec4((float)t / 65535.0f, 0.0f, 0.0f, 1.0f);
 }
+static inline vec4 textureLod(const samplerCubeArray& s, vec4 dirLayer, int) { return texture(s, dirLayer); }
+// sampler2DArrayShadow, LINEAR + compare LEQUAL (hardware PCF, SURVEY.md Appendix A4): the reference value is compared with the four
+// bilinear neighbours and the 0/1 results are blended with 8-bit sub-texel weights, in the operation order of oracle.cpp's shadowArrayPcf
+struct sampler2DArrayShadow { const float* data = nullptr; int res = 0; int layers = 4; };
+static inline float texture(const sampler2DArrayShadow& s, vec4 c) {         // c = (u, v, layer, reference depth)
+    const int layer = clampi((int)std::floor(c.z + 0.5f), 0, s.layers - 1);
+    const float* m = s.data + (size_t)layer * s.res * s.res;
+    const float fu = c.x * (float)s.res - 0.5f, fv = c.y * (float)s.res - 0.5f;
+    const float i0f = std::floor(fu), j0f = std::floor(fv);
+    const float a = std::floor((fu - i0f) * 256.0f + 0.5f) * (1.0f / 256.0f), b = std::floor((fv - j0f) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const int i0 = clampi((int)i0f, 0, s.res - 1), i1 = clampi((int)i0f + 1, 0, s.res - 1), j0 = clampi((int)j0f, 0, s.res - 1), j1 = clampi((int)j0f + 1, 0, s.res - 1);
+    auto lit = [&](int i, int j) { return c.w <= m[(size_t)j * s.res + i] ? 1.0f : 0.0f; };
+    return (1.0f - a) * (1.0f - b) * lit(i0, j0) + a * (1.0f - b) * lit(i1, j0) + (1.0f - a) * b * lit(i0, j1) + a * b * lit(i1, j1);
+}
+static inline vec3 textureSize(const sampler2DArrayShadow& s, int) { return vec3((float)s.res, (float)s.res, (float)s.layers); }
+// ---- compute-shader built-ins (per invocation) and the uniforms pbr.glsl declares for the sun's cascaded shadow map ----
+static thread_local uvec3 gl_NumWorkGroups, gl_WorkGroupSize, gl_WorkGroupID, gl_LocalInvocationID, gl_GlobalInvocationID;
+static thread_local uint gl_LocalInvocationIndex;
+static void (*barrierHook)() = nullptr;
+static inline void barrier() { if (barrierHook) barrierHook(); }
+static inline int atomicAdd(int& mem, int v) { return __atomic_fetch_add(&mem, v, __ATOMIC_SEQ_CST); }
+static vec3 infiniteLightDirection; static float infiniteLightZnear = 0.0f, infiniteLightZfar = 1.0f, infiniteLightDepthBias = 0.0f;
+static sampler2DArrayShadow infiniteLightShadowMap; static vec4 cascadePlanes[3]; static mat4 cascadeProjViews[4];
+struct VplStage1PerTileOutputs { vec4 averageLocalPosition; vec4 averageLocalNormal; };        // vpl_common.glsl
+#define MAX_VPLS_PER_TILE 12
+#define MAX_TOTAL_VPLS_BEFORE_CULLING 10000
+#define MAX_TOTAL_VPLS_PER_FRAME 4480
+struct VplStage2PerTileOutputs { int numVisible; int indices[MAX_VPLS_PER_TILE]; };
 // ---- the interface blocks and uniforms of vpl_pbr_gi.fs (declarations restated; values set by refglsl_gather) ----
 #define MAX_TOTAL_SHADOW_ATLASES 14
 struct VplData { vec4 position; vec4 color; vec4 specularPosition; float radius; float farPlane; float intensity; float _1; };      // vpl_common.glsl:48-56
@@ -284,8 +341,98 @@ void refglsl_denoise_pass(const RefDenoiseArgs* a) {
             a->historyOut[p] = newHistoryDepth;
         }
 }
+
+// ---- the four compute shaders.  A dispatch is emulated invocation by invocation with the built-ins set as GL defines them;
+//      invocations of a work group run one after the other where only invocation 0 reads `shared` data after the barrier
+//      (stage 1: it runs last), and as 1024 real threads with a real barrier where the phases depend on each other (the cull) ----
+typedef struct RefColorArgs {
+    int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
+    const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
+} RefColorArgs;
+void refglsl_color(const RefColorArgs* a) {
+    using namespace refglsl;
+    infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+    cs_color::infiniteLightColor = glm::vec3(a->sunColor[0], a->sunColor[1], a->sunColor[2]);
+    cs_color::lightData = (VplData*)a->lightData; cs_color::numVisible = a->numVisible; cs_color::diffuseIndices = (const AtlasEntry*)a->diffuseIndices;
+    for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) {
+        cs_color::shadowCubeMaps[i].data = a->shadowAtlases[i]; cs_color::shadowCubeMaps[i].res = a->cubeRes; cs_color::shadowCubeMaps[i].rgba8 = nullptr;
+        cs_color::diffuseCubeMaps[i].data = nullptr; cs_color::diffuseCubeMaps[i].res = a->cubeRes; cs_color::diffuseCubeMaps[i].rgba8 = a->diffuseAtlases[i];
+    }
+    gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
+    for (unsigned g = 0; g < 1024; ++g) {
+        gl_GlobalInvocationID = gl_LocalInvocationID = glm::uvec3(g, 0, 0); gl_LocalInvocationIndex = g;
+        cs_color::color_main();
+    }
+}
+typedef struct RefStage1Args { int W, H; const float* depth; const unsigned char* normal4; const float* invProjectionView; void* out; } RefStage1Args;
+void refglsl_stage1(const RefStage1Args* a) {
+    using namespace refglsl;
+    auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
+    cs_stage1::gDepth = tex(a->depth, R32F); cs_stage1::gNormal = tex(a->normal4, RGBA8);
+    std::memcpy(&cs_stage1::invProjectionView[0][0], a->invProjectionView, 64);
+    cs_stage1::vplNumVisiblePerTile = (VplStage1PerTileOutputs*)a->out;
+    const unsigned tilesX = a->W / 5, tilesY = a->H / 5;                    // DispatchCompute(viewportWidth / tileXDivisor, viewportHeight / tileYDivisor, 1)
+    gl_NumWorkGroups = glm::uvec3(tilesX, tilesY, 1); gl_WorkGroupSize = glm::uvec3(5, 5, 1);
+    for (unsigned ty = 0; ty < tilesY; ++ty)
+        for (unsigned tx = 0; tx < tilesX; ++tx) {
+            gl_WorkGroupID = glm::uvec3(tx, ty, 0);
+            for (unsigned k = 1; k <= 25; ++k) {                             // invocations 1..24, then invocation 0 (the one that reads the shared arrays)
+                const unsigned idx = k % 25, lx = idx % 5, ly = idx / 5;
+                gl_LocalInvocationID = glm::uvec3(lx, ly, 0); gl_LocalInvocationIndex = idx;
+                gl_GlobalInvocationID = glm::uvec3(tx * 5 + lx, ty * 5 + ly, 0);
+                cs_stage1::stage1_main();
+            }
+        }
+}
+typedef struct RefStage2Args {
+    int tilesX, tilesY; const float* viewPosition; const void* lightData; const void* stage1Data; int numVisible; const int* vplVisibleIndex; void* out;
+} RefStage2Args;
+void refglsl_stage2(const RefStage2Args* a) {
+    using namespace refglsl;
+    cs_stage2::viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
+    cs_stage2::lightData = (const VplData*)a->lightData; cs_stage2::stage1Data = (const VplStage1PerTileOutputs*)a->stage1Data;
+    cs_stage2::numVisible = a->numVisible; cs_stage2::vplVisibleIndex = a->vplVisibleIndex; cs_stage2::vplNumVisiblePerTile = (VplStage2PerTileOutputs*)a->out;
+    gl_WorkGroupSize = glm::uvec3(32, 2, 1); gl_NumWorkGroups = glm::uvec3(a->tilesX / 32, a->tilesY / 2, 1);      // BE:1774-1778
+    for (unsigned gy = 0; gy < gl_NumWorkGroups.y * 2; ++gy)
+        for (unsigned gx = 0; gx < gl_NumWorkGroups.x * 32; ++gx) {
+            gl_GlobalInvocationID = glm::uvec3(gx, gy, 0); gl_WorkGroupID = glm::uvec3(gx / 32, gy / 2, 0);
+            gl_LocalInvocationID = glm::uvec3(gx % 32, gy % 2, 0); gl_LocalInvocationIndex = (gy % 2) * 32 + gx % 32;
+            cs_stage2::stage2_main();
+        }
+}
+typedef struct RefCullArgs {
+    int totalNumLights, csmRes; const float* sunDir; const float* cascadeProjViews; const float* cascadePlanes; const float* csm;
+    const void* lightData; void* updatedLightData; int* vplVisibleIndex;
+} RefCullArgs;
+static pthread_barrier_t g_cullBarrier;
+static void cullBarrierWait() { pthread_barrier_wait(&g_cullBarrier); }
+void refglsl_cull(const RefCullArgs* a) {
+    using namespace refglsl;
+    infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+    for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
+    for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
+    infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
+    cs_cull::totalNumLights = a->totalNumLights; cs_cull::lightData = (const VplData*)a->lightData;
+    cs_cull::updatedLightData = (VplData*)a->updatedLightData; cs_cull::vplVisibleIndex = a->vplVisibleIndex;
+    const unsigned n = 1024;                                                 // one work group of local_size_x = 1024 (BE:1603)
+    pthread_barrier_init(&g_cullBarrier, nullptr, n);
+    barrierHook = cullBarrierWait;
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < n; ++t)
+        threads.emplace_back([t]() {
+            gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
+            gl_LocalInvocationID = gl_GlobalInvocationID = glm::uvec3(t, 0, 0); gl_LocalInvocationIndex = t;
+            cs_cull::cull_main();
+        });
+    for (auto& th : threads) th.join();
+    barrierHook = nullptr;
+    pthread_barrier_destroy(&g_cullBarrier);
+}
 }
 '''
+
+
+CS_PRE = {'cs_color': 'static vec3 infiniteLightColor;\nstatic VplData* lightData; static const int* numVisible; static const AtlasEntry* diffuseIndices;\nstatic samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'static sampler2D gDepth, gNormal; static mat4 invProjectionView;\nstatic VplStage1PerTileOutputs* vplNumVisiblePerTile;\nstatic vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'static vec3 viewPosition;\nstatic const VplData* lightData; static const VplStage1PerTileOutputs* stage1Data; static int numVisible; static const int* vplVisibleIndex;\nstatic VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n'}
 
 
 def generate():
@@ -314,6 +461,13 @@ def generate():
             if n == "main":
                 defs = [re.sub(r"\bvoid\s+main\s*\(", "void denoise_main(", d) for d in defs]
             parts += [adapt(d) + "\n" for d in defs]
+    for fname, ns, main_name, macros in COMPUTE:
+        text = strip_comments(open(os.path.join(SHADERS, fname)).read())
+        parts.append(f"\n// ---- from Source/Shaders/{fname} ----\nnamespace {ns} {{\n" + CS_PRE[ns])
+        for mac in macros:
+            parts.append(extract_macro(text, mac) + "\n")
+        (d,) = extract(text, "main")
+        parts.append(adapt(re.sub(r"\bvoid\s+main\s*\(", f"void {main_name}(", d)) + f"\n}}  // namespace {ns}\n")
     parts.append(EPILOGUE)
     return "".join(parts)
 
@@ -326,7 +480,7 @@ def build(force=False):
     if not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(os.path.abspath(__file__)):
         return lib
     open(src, "w").write(generate())
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + REF, "-o", lib, src])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I" + REF, "-o", lib, src])
     return lib
 
 

@@ -72,7 +72,93 @@ def reference_glsl():
     L.refglsl_bound_hdr.restype = C.c_float
     L.refglsl_gather.argtypes = [C.c_void_p]
     L.refglsl_denoise_pass.argtypes = [C.c_void_p]
+    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull"):
+        getattr(L, name).argtypes = [C.c_void_p]
     return L
+
+
+class RefColorArgs(C.Structure):
+    _fields_ = [("cubeRes", C.c_int), ("numAtlases", C.c_int)] + [(n, C.c_void_p) for n in ("sunDir", "sunColor", "lightData", "numVisible", "diffuseIndices",
+                                                                                        "shadowAtlases", "diffuseAtlases")]
+
+
+class RefStage1Args(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int)] + [(n, C.c_void_p) for n in ("depth", "normal4", "invProjectionView", "out")]
+
+
+class RefStage2Args(C.Structure):
+    _fields_ = [("tilesX", C.c_int), ("tilesY", C.c_int), ("viewPosition", C.c_void_p), ("lightData", C.c_void_p), ("stage1Data", C.c_void_p),
+                ("numVisible", C.c_int), ("vplVisibleIndex", C.c_void_p), ("out", C.c_void_p)]
+
+
+class RefCullArgs(C.Structure):
+    _fields_ = [("totalNumLights", C.c_int), ("csmRes", C.c_int)] + [(n, C.c_void_p) for n in ("sunDir", "cascadeProjViews", "cascadePlanes", "csm",
+                                                                                              "lightData", "updatedLightData", "vplVisibleIndex")]
+
+
+def _f32(x):
+    return np.ascontiguousarray(np.array(x, np.float32).reshape(-1))
+
+
+def reference_glsl_cull(ref, fp, vpl_data, csm, csm_res):
+    """viscull_vpls.cs (shader text, one work group of 1024 real threads).  Returns (updatedLightData [4480,16], vplVisibleIndex [N+1]).
+    The eight helper invocations race for the output slots as they do on a GPU, so the ORDER of the list is not defined."""
+    n = int(fp.totalNumLights)
+    updated = np.zeros((MAX_TOTAL_VPLS_PER_FRAME + 1, 16), np.float32)
+    visible = np.zeros(n + 2, np.int32)
+    a = RefCullArgs()
+    a.totalNumLights, a.csmRes = n, csm_res
+    keep = [_f32(list(fp.infiniteLightDirection)), _f32([list(m) for m in fp.cascadeProjViews]), _f32([list(p) for p in fp.cascadePlanes]),
+            np.ascontiguousarray(csm, np.float32), np.ascontiguousarray(vpl_data, np.float32)]
+    a.sunDir, a.cascadeProjViews, a.cascadePlanes, a.csm, a.lightData = [x.ctypes.data for x in keep]
+    a.updatedLightData, a.vplVisibleIndex = updated.ctypes.data, visible.ctypes.data
+    ref.refglsl_cull(C.addressof(a))
+    return updated, visible
+
+
+def reference_glsl_color(ref, fp, updated, visible, entries, shadow_atlas, diffuse_atlas, cube_res):
+    """vpl_light_color.cs (shader text) in place on a copy of the compacted table; returns the coloured table."""
+    out = np.ascontiguousarray(updated, np.float32).copy()
+    a = RefColorArgs()
+    a.cubeRes, a.numAtlases = cube_res, int(shadow_atlas.shape[0])
+    sh, df = _atlas_ptrs(shadow_atlas), _atlas_ptrs(diffuse_atlas)
+    keep = [_f32(list(fp.infiniteLightDirection)), _f32(list(fp.infiniteLightColor)), np.ascontiguousarray(visible, np.int32), np.ascontiguousarray(entries, np.int32)]
+    a.sunDir, a.sunColor, a.numVisible, a.diffuseIndices = [x.ctypes.data for x in keep]
+    a.lightData = out.ctypes.data
+    a.shadowAtlases, a.diffuseAtlases = C.addressof(sh), C.addressof(df)
+    ref.refglsl_color(C.addressof(a))
+    return out
+
+
+def reference_glsl_stage1(ref, fp, gb):
+    """vpl_tiled_deferred_culling_stage1.cs (shader text): [tiles, 8] float32."""
+    H, W = gb.depth.shape
+    out = np.zeros(((W // 5) * (H // 5), 8), np.float32)
+    a = RefStage1Args()
+    a.W, a.H = W, H
+    keep = [np.ascontiguousarray(gb.depth), np.ascontiguousarray(gb.normal), _f32(list(fp.invProjectionView))]
+    a.depth, a.normal4, a.invProjectionView = [x.ctypes.data for x in keep]
+    a.out = out.ctypes.data
+    ref.refglsl_stage1(C.addressof(a))
+    return out
+
+
+def reference_glsl_stage2(ref, fp, W, H, vpl_data, stage1, visible):
+    """vpl_tiled_deferred_culling_stage2.cs (shader text): [tiles, 13] int32.  The shader's `numVisible` / `vplVisibleIndex[]` are the
+    count and the list that follows it in the cull's output (slot 0 holds the count)."""
+    tx, ty = W // 5, H // 5
+    if tx % 32 or ty % 2:
+        raise ValueError("the reference dispatches whole 32x2-tile work groups (BE:1774-1778): tile grid must be a multiple of 32 x 2")
+    out = np.zeros((tx * ty, 13), np.int32)
+    v = int(visible[0])
+    idx = np.ascontiguousarray(visible[1:1 + v], np.int32)
+    a = RefStage2Args()
+    a.tilesX, a.tilesY, a.numVisible = tx, ty, v
+    keep = [_f32(list(fp.viewPosition)), np.ascontiguousarray(vpl_data, np.float32), np.ascontiguousarray(stage1, np.float32)]
+    a.viewPosition, a.lightData, a.stage1Data = [x.ctypes.data for x in keep]
+    a.vplVisibleIndex, a.out = idx.ctypes.data, out.ctypes.data
+    ref.refglsl_stage2(C.addressof(a))
+    return out
 
 
 class RefDenoiseArgs(C.Structure):

@@ -148,3 +148,51 @@ def test_whole_denoiser_shader_text_against_the_oracle(libs, workload, frames, y
         assert resets > 0                      # a moving camera resets the history somewhere (disocclusion): the decision path ran
     elif frames > 1:
         assert resets == 0 and float(o.history.max()) == float(frames)
+
+
+# ---- the compute shaders of the path, compiled from the shader text ----------------------------------------------------------
+@pytest.mark.parametrize("workload", ["tiny", "c1", "c3"])
+def test_cull_shader_text_against_the_oracle(libs, workload):
+    """viscull_vpls.cs main() run as one work group of 1024 real threads with a real barrier(), with calculateInfiniteShadowValue /
+    sampleShadowTexture / computeTexelSize from pbr.glsl and common.glsl.  The visible SET and count must equal the oracle's; the
+    shader's eight helper invocations race for the slots (atomicAdd), so its order is one interleaving and the oracle's ascending
+    order another (the shader's own serial variant, :108-119); each slot must hold the VPL its index names."""
+    from oracle.oracle_py import OracleFrame, reference_glsl_cull
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData(workload, frames=1)
+    s = d.scene
+    o = OracleFrame(d.W, d.H, s.cube_res, s.csm_res, s.denoise_iters)
+    V = o.cull(d.fp[0], d.vpl_data, d.atlas_by_vpl, d.csm[0])
+    updated, visible = reference_glsl_cull(ref, d.fp[0], d.vpl_data, d.csm[0], s.csm_res)
+    assert int(visible[0]) == V and 0 < V < d.N
+    assert sorted(visible[1:V + 1].tolist()) == o.visible[1:V + 1].tolist()
+    assert np.array_equal(updated[:V].view(np.uint32), d.vpl_data[visible[1:V + 1]].view(np.uint32))
+
+
+@pytest.mark.parametrize("workload", ["tiny", "c1"])
+def test_color_and_tile_shader_texts_against_the_oracle(libs, workload):
+    """vpl_light_color.cs, vpl_tiled_deferred_culling_stage1.cs (25 invocations per tile, shared arrays, invocation 0 sums in index
+    order) and ..._stage2.cs (the insertion with SHUFFLE_DOWN) from the shader text: the coloured table, the per-tile means and the
+    per-tile lists must be the oracle's bit for bit."""
+    from oracle.oracle_py import OracleFrame, reference_glsl_color, reference_glsl_stage1, reference_glsl_stage2
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData(workload, frames=1)
+    s = d.scene
+    fp, gb = d.fp[0], d.gb[0]
+    o = OracleFrame(d.W, d.H, s.cube_res, s.csm_res, s.denoise_iters)
+    V = o.cull(fp, d.vpl_data, d.atlas_by_vpl, d.csm[0])
+    before = o.updated.copy()
+    o.color(fp, d.shadow_atlas, d.diffuse_atlas)
+    colored = reference_glsl_color(ref, fp, before, o.visible, o.entries, d.shadow_atlas, d.diffuse_atlas, s.cube_res)
+    assert np.array_equal(colored[:V].view(np.uint32), o.updated[:V].view(np.uint32))
+    assert not np.array_equal(colored[:V, 4:12], before[:V, 4:12])                      # colour and specular position were written
+    o.tile_lists(fp, gb, d.vpl_data)
+    s1 = reference_glsl_stage1(ref, fp, gb)
+    assert np.array_equal(s1.view(np.uint32), o.stage1.view(np.uint32))
+    s2 = reference_glsl_stage2(ref, fp, d.W, d.H, d.vpl_data, o.stage1, o.visible)
+    cnt = o.stage2[:, 0]
+    assert np.array_equal(s2[:, 0], cnt) and cnt.max() <= 12 and cnt.max() > 0
+    mask = np.arange(12)[None, :] < cnt[:, None]
+    assert np.array_equal(s2[:, 1:][mask], o.stage2[:, 1:][mask])
