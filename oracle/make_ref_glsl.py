@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""Compile the REFERENCE's own GLSL text for the pure-maths part of the GI gather as C++ against the reference's vendored glm.
-TEST INFRASTRUCTURE (the checker's checker).
+"""Compile the REFERENCE's own GLSL text for the GI path as C++ against the reference's vendored glm.  TEST INFRASTRUCTURE
+(the checker's checker).
 
-The shaders of StratusGFX need an OpenGL driver to run, but the functions the VPL gather calls for its radiance — the BRDF chain of
-Source/Shaders/pbr2.glsl, the VPL attenuation of pbr.glsl, applyFog of fog.glsl, worldPositionFromDepth and the hash/random
-functions of common.glsl — sample no texture, and GLSL of that kind is C++ once glm supplies the vector types (glm exists to
-mirror GLSL).  This script reads those functions from where they lie under /root/reference, applies a handful of purely
-lexical adaptations —
+The shaders of StratusGFX need an OpenGL driver to run as GLSL, but GLSL of this kind is C++ once glm supplies the vector types
+(glm exists to mirror GLSL), and the reference vendors glm.  This script reads the six shaders of the path and the library files
+they include from where they lie under /root/reference/Source/Shaders, extracts by name the functions the path executes — main()
+of viscull_vpls.cs, vpl_light_color.cs, vpl_tiled_deferred_culling_stage1.cs, ..._stage2.cs and vpl_pbr_gi_denoise.fs,
+performLightingCalculations of vpl_pbr_gi.fs, and everything they call in pbr.glsl, pbr2.glsl, fog.glsl and common.glsl, with the
+macros they use — and applies purely lexical adaptations:
 
-    float literals get an `f` suffix                 (GLSL literals are 32-bit floats, C++ literals are doubles)
-    `in T x` -> `T x`,  `out|inout T x` -> `T& x`    (parameter qualifiers)
-    `.xyz` -> `.xyz()`                               (multi-component swizzles are member functions in glm 0.9.8 on GCC)
+    float literals get an `f` suffix                       (GLSL literals are 32-bit floats, C++ literals are doubles)
+    `in T x` -> `T x`,  `out|inout T x` -> `T& x`          (parameter qualifiers)
+    `.xyz` -> `.xyz()`                                     (multi-component swizzles are member functions in glm 0.9.8 on GCC)
+    `v.xyz += e;` / `v.xy = e;` -> swizzleAdd3(v, e) ...   (swizzles as l-values: glm's swizzle functions return copies)
+    `float a[2] = float[](x, y);` -> `= {x, y};`           (array constructors)
+    `void main(` -> `void <shader>_main(`                  (one translation unit holds several shaders)
 
-— writes the result to oracle/_ref/ref_glsl_gen.cpp (generated, git-ignored, never committed), appends C entry points and
-compiles it to oracle/_ref/libref_glsl.so.  tests/test_reference_glsl.py then holds the oracle's restatement of the same
-functions against it bit for bit.  Nothing of the reference is copied into the repository.
+What an OpenGL driver would supply is written out in the prelude from the GL 4.6 specification and is NOT
+reference code: samplers (texel fetch at texel centres, bilinear filter with 8-bit sub-texel weights, cube-map face selection,
+hardware PCF), interface blocks and uniforms as globals, compute built-ins, barrier() (real: the cull runs as 1024 threads),
+`shared` arrays.  The result goes to oracle/_ref/ref_glsl_gen.cpp (generated, git-ignored, never committed) and is compiled to
+oracle/_ref/libref_glsl.so.  tests/test_reference_glsl.py holds every stage of the oracle against it bit for bit, and
+tests/golden/make_shader_text_golden.py chains the compiled shaders into a fixture that no oracle code touched.
+Nothing of the reference is copied into the repository.
 
     python oracle/make_ref_glsl.py          (also run by oracle/oracle_py.py::build when the reference tree is present)
 """

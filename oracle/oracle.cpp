@@ -4,14 +4,21 @@
 // bench.py's cpu_baseline / --impl reference legs may load this library; the CUDA
 // product (stratusgfx_b200/csrc) never links, calls or falls back to it.
 //
-// PARITY UNPINNED BY THE REFERENCE: StratusGFX ships no golden vectors, known-answer
-// tests or fixtures for this path and its GLSL cannot run here
-// (no OpenGL).  What pins this file instead: (1) the maths layer is cross-checked bit
-// for bit against the reference's own vendored glm (oracle/_ref build, -DORACLE_USE_GLM);
+// HOW PARITY IS PINNED.  StratusGFX ships no golden vectors, known-answer tests or fixtures for this path,
+// and its GLSL cannot run here as GLSL (no OpenGL).  What this file is held against instead:
+// (0) THE REFERENCE'S OWN SHADER TEXT, compiled: oracle/make_ref_glsl.py turns the six shaders of the path (viscull_vpls.cs,
+//     vpl_light_color.cs, tiled culling stage 1 / stage 2, vpl_pbr_gi.fs, vpl_pbr_gi_denoise.fs) and every pbr.glsl / pbr2.glsl /
+//     fog.glsl / common.glsl function they call into C++ against the reference's vendored glm by a few lexical rules, with the GL
+//     fixed function (texel fetch, cube face selection, hardware PCF, 16F stores, work-group scheduling) stubbed from the GL 4.6
+//     specification.  tests/test_reference_glsl.py: every stage of this oracle equals that shader text bit for bit on whole frames
+//     (the cull as a set); tests/golden/tiny_shader_text_golden.json is a whole two-frame chain computed without this file;
+// (1) the maths layer is cross-checked bit for bit against the reference's own vendored glm (oracle/_ref build, -DORACLE_USE_GLM);
 // (2) the self-checks of SURVEY.md §8(c) in tests/test_oracle_selfchecks.py;
 // (3) frozen RNG known answers and a fixture made with the glm-backed build (tests/golden/);
-// (4) for the pre-pass and the wire formats only: the reference's own StratusMath.h / StratusGpuCommon.h compiled
-//     behind oracle/ref_shim.cpp (tests/test_reference_shim.py).
+// (4) for the pre-pass and the wire formats: the reference's own StratusMath.h / StratusGpuCommon.h compiled behind
+//     oracle/ref_shim.cpp (tests/test_reference_shim.py).
+// What stays unpinned: the GL fixed-function stubs themselves (this file's and the shim's follow the same reading of the
+// specification, Appendix A of SURVEY.md) — no OpenGL driver exists in this image to check them against.
 //
 // Each function follows one shader entry point; citations are relative to the
 // StratusGFX tree.  GL fixed-function semantics (texel addressing, cube-face

@@ -323,3 +323,37 @@ def test_own_maths_oracle_reproduces_the_glm_golden_fixture(built):
     got, want = mod.compute("own"), _load_glm_golden()
     assert got["frames"] == want["frames"]
     assert got["prepass"] == want["prepass"]
+
+
+def test_own_maths_oracle_reproduces_the_shader_text_golden_fixture(built):
+    """tests/golden/tiny_shader_text_golden.json was computed WITHOUT this oracle: the reference's six shaders compiled from their GLSL
+    text (oracle/make_ref_glsl.py) and chained as the backend chains them.  The oracle must give the same visible lists, atlas
+    entries and per-tile lists and the same bytes for every float plane of both frames — on any box, reference tree or not."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_glm_golden", os.path.join(here, "golden", "make_glm_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden", "tiny_shader_text_golden.json")))
+    got = mod.compute("own")
+    assert got["frames"] == want["frames"]
+    assert want["frames"] == _load_glm_golden()["frames"]          # the two fixtures (shader text, glm-backed oracle) agree field by field
+
+
+def test_shader_text_fixture_is_reproducible_where_the_reference_is(built):
+    from oracle import oracle_py
+    if oracle_py.reference_glsl() is None:
+        pytest.skip("oracle/_ref/libref_glsl.so not built (needs the reference tree)")
+    import importlib.util
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    try:
+        spec = importlib.util.spec_from_file_location("make_shader_text_golden", os.path.join(here, "golden", "make_shader_text_golden.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        got = mod.compute()
+    finally:
+        sys.path.remove(os.path.join(here, "golden"))
+    want = json.load(open(os.path.join(here, "golden", "tiny_shader_text_golden.json")))
+    assert got["frames"] == want["frames"]

@@ -438,13 +438,17 @@ def test_gather_modes_can_alternate_on_one_handle(tiny):
 
 
 def test_cuda_integer_outputs_match_the_glm_golden_fixture(tiny):
-    """Committed fixture (tests/golden/tiny_glm_golden.json, made with the reference's glm): the CUDA path's visible list,
-    atlas entries, per-tile lists and pre-pass order must equal it exactly, with no oracle in the loop."""
+    """Committed fixtures (tests/golden/tiny_shader_text_golden.json: the reference's shader text compiled and chained;
+    tiny_glm_golden.json: the oracle built against the reference's glm; identical field by field): the CUDA path's visible list,
+    atlas entries, per-tile lists and pre-pass order must equal them exactly, with no oracle in the loop."""
     import json
     import os
     from stratusgfx_b200.prepass import frustum_planes
     from tests.test_oracle_selfchecks import _random_lights
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_glm_golden.json")))
+    # the same frames computed from the reference's shader text alone (tests/golden/make_shader_text_golden.py)
+    text = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_shader_text_golden.json")))
+    assert text["frames"] == gold["frames"]
     cu = run_cuda_staged(tiny)
     for f in range(2):
         g = gold["frames"][f]
