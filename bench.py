@@ -177,6 +177,8 @@ def cpu_sample_run(scene, steps, warmup):
         times.append(time.perf_counter() - t)
     t_step = float(np.mean(times[warmup:]))
     value = scene.width * rows * scene.num_vpls / t_step / 1e9
+    # kind "port": oracle/oracle.cpp, which tests/test_reference_glsl.py holds bit for bit against the reference's own shader text
+    # compiled with its glm (oracle/make_ref_glsl.py); the compiled text itself is single-threaded (shader globals), so the port is timed
     return dict(value=value, unit=UNIT, cores=cores, kind="port",
                 sample=f"rows {y0}..{y0 + rows} of {scene.width}x{H} ({rows}/{H} of the frame), whole VPL set, {steps} step(s) after {warmup} warm-up, mean",
                 ms_per_step=t_step * 1e3, V=int(o.visible[0]))
