@@ -196,3 +196,27 @@ def test_color_and_tile_shader_texts_against_the_oracle(libs, workload):
     assert np.array_equal(s2[:, 0], cnt) and cnt.max() <= 12 and cnt.max() > 0
     mask = np.arange(12)[None, :] < cnt[:, None]
     assert np.array_equal(s2[:, 1:][mask], o.stage2[:, 1:][mask])
+
+
+@pytest.mark.parametrize("num_vpls", [1, 2, 5])
+def test_gather_and_denoiser_shader_text_with_very_few_vpls(libs, num_vpls):
+    """One and two VPLs: `maxRandomIndex = numVisible[0] - 1` is 0 or 1, so every draw picks VPL 0 (the last VPL is never drawn,
+    vpl_pbr_gi.fs:146-151) — the degenerate ends of the draw loop must match the shader text as well."""
+    from oracle.oracle_py import OracleFrame, ReferenceGlslDenoiser, reference_glsl_gather
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData("tiny", frames=1, num_vpls=num_vpls)
+    s = d.scene
+    o = OracleFrame(d.W, d.H, s.cube_res, s.csm_res, s.denoise_iters)
+    fp, gb = d.fp[0], d.gb[0]
+    V = o.cull(fp, d.vpl_data, d.atlas_by_vpl, d.csm[0])
+    if V == 0:
+        pytest.skip("no VPL of this tiny set is visible to the sun")
+    o.color(fp, d.shadow_atlas, d.diffuse_atlas); o.gather(fp, gb)
+    color, res = reference_glsl_gather(ref, fp, gb, o.updated, o.visible, o.entries, d.shadow_atlas, s.cube_res)
+    with np.errstate(over="ignore"):
+        assert np.array_equal(res.astype(np.float16).view(np.uint16), o.gi_reservoir.view(np.uint16))
+        assert np.array_equal(color.astype(np.float16).view(np.uint16), o.gi_color[..., :3].view(np.uint16))
+    passes = ReferenceGlslDenoiser(ref, d.W, d.H, s.denoise_iters).frame(fp, gb, d.gb[-1], V, o.gi_color, o.gi_reservoir)
+    o.denoise(fp, gb, d.gb[-1], keep_passes=True)
+    assert np.array_equal(passes[-1]["combined"][..., :3].view(np.uint16), o.combined[..., :3].view(np.uint16))
