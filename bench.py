@@ -14,6 +14,7 @@ over NCCL, each rank runs its band (+ a 30-row apron so the à-trous passes need
 and the lit bands are gathered to rank 0 — strong scaling of one frame.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -184,16 +185,107 @@ def cpu_sample_run(scene, steps, warmup):
                 ms_per_step=t_step * 1e3, V=int(o.visible[0]))
 
 
+def cpu_reference_text_run(scene, steps, warmup):
+    """Times the REFERENCE'S OWN SHADER TEXT (oracle/_ref/libref_glsl.so: the six shaders of the path compiled from their GLSL against
+    the reference's glm by oracle/make_ref_glsl.py, kind "reference") on rows [y0, y0+rows) of the workload's frame, fragments and
+    work groups spread over all host threads.  The cull and the colouring run on the whole VPL set, the tile stages on the band's
+    tile rows, the gather and the four denoise passes on the band's rows of full-height planes (taps that leave the band read
+    rows this sample never computed: same work, and the results are not used — correctness of this code against the oracle and the
+    CUDA path is the business of tests/test_reference_glsl.py)."""
+    from oracle import oracle_py as O
+    ref = O.reference_glsl()
+    if ref is None:
+        raise RuntimeError("oracle/_ref/libref_glsl.so is not there")
+    W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
+    if (W // 5) % 32 or (H // 5) % 2:
+        raise RuntimeError("the reference's stage-2 dispatch needs a tile grid of whole 32x2 groups")
+    rows = min(CPU_SAMPLE_ROWS, H) // 10 * 10
+    y0 = ((H - rows) // 2) // 10 * 10
+    y1 = y0 + rows
+    fp = scene.frame_params(0)
+    gb, pgb = scene.gbuffer(0), scene.gbuffer(-1)
+    vd, at = scene.vpls()
+    sh, df = scene.cubemaps()
+    csm = scene.csm(0)
+    cores = int(O.lib().orc_num_threads())
+    half = lambda shape: np.zeros(shape, np.float16)
+    prev_gi, prev_hist = half((H, W, 4)), half((H, W))
+    gi_color, gi_res = half((H, W, 4)), half((H, W, 4))
+    gi_color[..., 3] = 1.0
+    fbo = [dict(gi=half((H, W, 4)), reservoir=half((H, W, 4))) for _ in range(2)]
+    for b in fbo:
+        b["gi"][..., 3] = 1.0
+    times, V = [], 0
+    for i in range(warmup + steps):
+        fp.time = 1000.0 + 16.0 * i
+        t = time.perf_counter()
+        _, vis = O.reference_glsl_cull(ref, fp, vd, csm, scene.csm_res)
+        V = int(vis[0])
+        idx = np.sort(vis[1:V + 1])
+        visible = np.concatenate([[V], idx]).astype(np.int32)
+        updated = np.zeros((4480, 16), np.float32); updated[:V] = vd[idx]
+        entries = np.zeros((4480, 2), np.int32); entries[:V] = at[idx]                 # the host's shadowDiffuseIndices (BE:1690-1701)
+        updated = O.reference_glsl_color(ref, fp, updated, visible, entries, sh, df, scene.cube_res)
+        stage1 = O.reference_glsl_stage1(ref, fp, gb, tile_rows=(y0 // 5, y1 // 5))
+        O.reference_glsl_stage2(ref, fp, W, H, vd, stage1, visible, tile_rows=(y0 // 5, y1 // 5))
+        color, res = O.reference_glsl_gather(ref, fp, gb, updated, visible, entries, sh, scene.cube_res, rows=(y0, y1))
+        with np.errstate(over="ignore"):
+            gi_color[y0:y1, :, :3] = color[y0:y1]; gi_res[y0:y1] = res[y0:y1]
+        illum, shadows = gi_color, gi_res
+        for p in range(iters):                                                         # the host loop of BE:1879-1952
+            a = O.RefDenoiseArgs()
+            a.W, a.H, a.multiplier, a.rowBegin, a.rowEnd = W, H, (1 << p) - 1, y0, y1
+            a.mergeReservoirs, a.final_ = (1 if p < 1 else 0), (1 if p + 1 == iters else 0)
+            a.time, a.framesPerSecond = float(fp.time), float(np.float32(1.0 / fp.deltaSeconds))
+            nv = np.array([V], np.int32)
+            combined, gi = np.zeros((H, W, 3), np.float32), np.zeros((H, W, 3), np.float32)
+            rsv, hist = np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32)
+            (a.numVisible, a.screenH4, a.velocityH2, a.normal4, a.ids, a.depth, a.prevNormal4, a.prevIds, a.prevDepth, a.indirectIlluminationH4,
+             a.indirectShadowsH4, a.prevIndirectIlluminationH4, a.historyDepthH) = [x.ctypes.data for x in (
+                nv, gb.screen, gb.velocity, gb.normal, gb.id, gb.depth, pgb.normal, pgb.id, pgb.depth, illum, shadows, prev_gi, prev_hist)]
+            a.combinedOut3, a.giOut3, a.reservoirOut4, a.historyOut = combined.ctypes.data, gi.ctypes.data, rsv.ctypes.data, hist.ctypes.data
+            ref.refglsl_denoise_pass(ctypes.addressof(a))
+            out = fbo[p % 2]
+            with np.errstate(over="ignore"):
+                out["gi"][y0:y1, :, :3] = gi[y0:y1]; out["reservoir"][y0:y1] = rsv[y0:y1]
+                if p + 1 == iters:
+                    prev_hist[y0:y1] = hist[y0:y1]
+            illum, shadows = out["gi"], out["reservoir"]
+        prev_gi[y0:y1] = illum[y0:y1]
+        times.append(time.perf_counter() - t)
+    t_step = float(np.mean(times[warmup:]))
+    return dict(value=W * rows * N / t_step / 1e9, unit=UNIT, cores=cores, kind="reference",
+                sample=f"the reference's own shader text (compiled: oracle/make_ref_glsl.py) on rows {y0}..{y1} of {W}x{H} ({rows}/{H} of the frame), whole VPL set, "
+                       f"{steps} step(s) after {warmup} warm-up, mean",
+                ms_per_step=t_step * 1e3, V=V)
+
+
+def cpu_arm(scene, steps, warmup):
+    """The CPU arm: the reference's compiled shader text when oracle/_ref/libref_glsl.so travelled with the repository (kind
+    "reference"), else the oracle port (kind "port")."""
+    try:
+        r = cpu_reference_text_run(scene, steps, warmup)
+        try:        # for transparency: the hand-written port of the same shaders on the same band (it is ~5x faster than the compiled text)
+            r["port_value"] = cpu_sample_run(scene, 1, 1)["value"]
+        except Exception:
+            r["port_value"] = None
+        return r
+    except Exception as e:          # never let the baseline break the bench: fall back to the port and say why
+        r = cpu_sample_run(scene, steps, warmup)
+        r["sample"] += f" (oracle port; the compiled reference shader text was not usable: {type(e).__name__}: {e})"
+        return r
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     from stratusgfx_b200.scene import Scene
     scene = Scene(args.workload)
-    r = cpu_sample_run(scene, args.steps, args.warmup)
+    r = cpu_arm(scene, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_text(scene), "sample": r["sample"]},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "port_value") if k in r},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -463,8 +555,8 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": roofline,
                 "stages": per_stage}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_sample_run(scene, 1, 1)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            r = cpu_arm(scene, 1, 1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "port_value") if k in r}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -124,10 +124,10 @@ PRELUDE = r'''// GENERATED by oracle/make_ref_glsl.py from the reference's GLSL 
 namespace refglsl {
 using namespace glm;
 // the uniforms these functions read (pbr2.glsl: usePerceptualRoughness, minRoughness; fog.glsl: fogColor, fogDensity)
-static bool usePerceptualRoughness = true;
-static float minRoughness = 0.08f;
-static vec3 fogColor = vec3(0.5f);
-static float fogDensity = 0.0f;
+static thread_local bool usePerceptualRoughness = true;
+static thread_local float minRoughness = 0.08f;
+static thread_local vec3 fogColor = vec3(0.5f);
+static thread_local float fogDensity = 0.0f;
 // GLSL converts int arguments to float implicitly (pbr.glsl: `mix(10, 1, ...)`)
 // (the using-declaration keeps glm::mix in the overload set: a function declared in this namespace would otherwise hide it)
 using glm::mix;
@@ -226,8 +226,8 @@ static thread_local uint gl_LocalInvocationIndex;
 static void (*barrierHook)() = nullptr;
 static inline void barrier() { if (barrierHook) barrierHook(); }
 static inline int atomicAdd(int& mem, int v) { return __atomic_fetch_add(&mem, v, __ATOMIC_SEQ_CST); }
-static vec3 infiniteLightDirection; static float infiniteLightZnear = 0.0f, infiniteLightZfar = 1.0f, infiniteLightDepthBias = 0.0f;
-static sampler2DArrayShadow infiniteLightShadowMap; static vec4 cascadePlanes[3]; static mat4 cascadeProjViews[4];
+static thread_local vec3 infiniteLightDirection; static thread_local float infiniteLightZnear = 0.0f, infiniteLightZfar = 1.0f, infiniteLightDepthBias = 0.0f;
+static thread_local sampler2DArrayShadow infiniteLightShadowMap; static thread_local vec4 cascadePlanes[3]; static thread_local mat4 cascadeProjViews[4];
 struct VplStage1PerTileOutputs { vec4 averageLocalPosition; vec4 averageLocalNormal; };        // vpl_common.glsl
 #define MAX_VPLS_PER_TILE 12
 #define MAX_TOTAL_VPLS_BEFORE_CULLING 10000
@@ -237,18 +237,21 @@ struct VplStage2PerTileOutputs { int numVisible; int indices[MAX_VPLS_PER_TILE];
 #define MAX_TOTAL_SHADOW_ATLASES 14
 struct VplData { vec4 position; vec4 color; vec4 specularPosition; float radius; float farPlane; float intensity; float _1; };      // vpl_common.glsl:48-56
 struct AtlasEntry { int index; int layer; };
-static vec2 fsTexCoords; static vec4 gl_FragCoord;
-static vec3 color; static vec4 reservoir;                                            // the two fragment outputs
-static sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient, screen, historyDepth;
-static sampler2DRect ssao;
-static vec3 viewPosition; static mat4 invProjectionView; static float time; static float minGiOcclusionFactor = 0.95f;
-static const VplData* lightData; static const int* numVisible; static const AtlasEntry* shadowIndices;
-static samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];
+// (thread_local: every host thread that runs fragments owns a copy of the shader's globals, so the full-screen passes can be
+//  spread over the host's cores; compiled with -ftls-model=local-dynamic: one TLS base lookup per function; initial-exec does not fit the static TLS block of a dlopen-ed library)
+#define PERINV static thread_local
+PERINV vec2 fsTexCoords; PERINV vec4 gl_FragCoord;
+PERINV vec3 color; PERINV vec4 reservoir;                                            // the two fragment outputs
+PERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient, screen, historyDepth;
+PERINV sampler2DRect ssao;
+PERINV vec3 viewPosition; PERINV mat4 invProjectionView; PERINV float time; PERINV float minGiOcclusionFactor = 0.95f;
+PERINV const VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* shadowIndices;
+PERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];
 // ---- the same for vpl_pbr_gi_denoise.fs ----
-static vec3 combinedColor, giColor; static vec4 reservoirValue; static float newHistoryDepth;       // the four fragment outputs
-static sampler2D albedo, velocity, normal, ids, depth, prevNormal, prevIds, prevDepth, indirectIllumination, indirectShadows, prevIndirectIllumination;
-static int multiplier = 0, passNumber = 0, numReservoirNeighbors = 10; static bool final = false, mergeReservoirs = false;
-static float framesPerSecond = 60.0f;
+PERINV vec3 combinedColor, giColor; PERINV vec4 reservoirValue; PERINV float newHistoryDepth;       // the four fragment outputs
+PERINV sampler2D albedo, velocity, normal, ids, depth, prevNormal, prevIds, prevDepth, indirectIllumination, indirectShadows, prevIndirectIllumination;
+PERINV int multiplier = 0, passNumber = 0, numReservoirNeighbors = 10; PERINV bool final = false, mergeReservoirs = false;
+PERINV float framesPerSecond = 60.0f;
 '''
 
 EPILOGUE = r'''
@@ -284,7 +287,9 @@ float refglsl_shadow1(const unsigned short* atlas, int res, int layer, float far
 
 // One full-screen pass of vpl_pbr_gi.fs: main() is `performLightingCalculations(textureLod(screen, fsTexCoords, 0).rgb, gl_FragCoord.xy, fsTexCoords)`
 // for every fragment of a W x H quad (fragment centres at (x + 0.5, y + 0.5), texture coordinates (x + 0.5) / W, (y + 0.5) / H).
-// Outputs are the float values written to `color` and `reservoir` before the RGB16F / RGBA16F framebuffer store.
+// Outputs are the float values written to `color` and `reservoir` before the RGB16F / RGBA16F framebuffer store.  Rows
+// [rowBegin, rowEnd) only (0, H = the whole quad; a sub-range is bench.py's bounded CPU sample); fragments are spread over the
+// host's threads, each with its own copy of the shader's globals.
 typedef struct RefGatherArgs {
     int W, H, cubeRes, numAtlases;
     const float* depth; const unsigned char* normal4; const unsigned char* albedo4; const unsigned char* refl2; const unsigned char* rma4;
@@ -292,28 +297,36 @@ typedef struct RefGatherArgs {
     const float* viewPosition; const float* invProjectionView; float time; float minGiOcclusionFactor;
     const void* lightData; const int* numVisible; const void* shadowIndices; const unsigned short* const* shadowAtlases;
     float* colorOut3; float* reservoirOut4;
+    int rowBegin, rowEnd;
+    int usePerceptualRoughness; float minRoughness; float fogColor[3]; float fogDensity;
 } RefGatherArgs;
 void refglsl_gather(const RefGatherArgs* a) {
     using namespace refglsl;
-    auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
-    gDepth = tex(a->depth, R32F); gNormal = tex(a->normal4, RGBA8); gAlbedo = tex(a->albedo4, RGBA8); gBaseReflectivity = tex(a->refl2, RG8);
-    gRoughnessMetallicAmbient = tex(a->rma4, RGBA8);
-    screen = tex(a->depth, R32F); historyDepth = tex(a->depth, R32F);        // bound by the reference but without effect on the outputs (any texture serves)
-    ssao.data = a->ssaoH; ssao.W = a->W; ssao.H = a->H; ssao.fmt = R16F;
-    viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
-    std::memcpy(&invProjectionView[0][0], a->invProjectionView, 64);
-    refglsl::time = a->time; minGiOcclusionFactor = a->minGiOcclusionFactor;
-    lightData = (const VplData*)a->lightData; numVisible = a->numVisible; shadowIndices = (const AtlasEntry*)a->shadowIndices;
-    for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) { shadowCubeMaps[i].data = a->shadowAtlases[i]; shadowCubeMaps[i].res = a->cubeRes; }
-    for (int y = 0; y < a->H; ++y)
-        for (int x = 0; x < a->W; ++x) {
-            gl_FragCoord = glm::vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
-            fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
-            performLightingCalculations(glm::vec3(textureLod(screen, fsTexCoords, 0)), glm::vec2(gl_FragCoord), fsTexCoords);
-            const size_t p = (size_t)y * a->W + x;
-            a->colorOut3[3 * p] = color.x; a->colorOut3[3 * p + 1] = color.y; a->colorOut3[3 * p + 2] = color.z;
-            a->reservoirOut4[4 * p] = reservoir.x; a->reservoirOut4[4 * p + 1] = reservoir.y; a->reservoirOut4[4 * p + 2] = reservoir.z; a->reservoirOut4[4 * p + 3] = reservoir.w;
-        }
+    #pragma omp parallel
+    {
+        auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
+        gDepth = tex(a->depth, R32F); gNormal = tex(a->normal4, RGBA8); gAlbedo = tex(a->albedo4, RGBA8); gBaseReflectivity = tex(a->refl2, RG8);
+        gRoughnessMetallicAmbient = tex(a->rma4, RGBA8);
+        screen = tex(a->depth, R32F); historyDepth = tex(a->depth, R32F);    // bound by the reference but without effect on the outputs (any texture serves)
+        ssao.data = a->ssaoH; ssao.W = a->W; ssao.H = a->H; ssao.fmt = R16F;
+        viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
+        std::memcpy(&invProjectionView[0][0], a->invProjectionView, 64);
+        refglsl::time = a->time; minGiOcclusionFactor = a->minGiOcclusionFactor;
+        usePerceptualRoughness = a->usePerceptualRoughness != 0; minRoughness = a->minRoughness;
+        fogColor = glm::vec3(a->fogColor[0], a->fogColor[1], a->fogColor[2]); fogDensity = a->fogDensity;
+        lightData = (const VplData*)a->lightData; numVisible = a->numVisible; shadowIndices = (const AtlasEntry*)a->shadowIndices;
+        for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) { shadowCubeMaps[i].data = a->shadowAtlases[i]; shadowCubeMaps[i].res = a->cubeRes; }
+        #pragma omp for schedule(dynamic, 2)
+        for (int y = a->rowBegin; y < a->rowEnd; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                gl_FragCoord = glm::vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+                fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                performLightingCalculations(glm::vec3(textureLod(screen, fsTexCoords, 0)), glm::vec2(gl_FragCoord), fsTexCoords);
+                const size_t p = (size_t)y * a->W + x;
+                a->colorOut3[3 * p] = color.x; a->colorOut3[3 * p + 1] = color.y; a->colorOut3[3 * p + 2] = color.z;
+                a->reservoirOut4[4 * p] = reservoir.x; a->reservoirOut4[4 * p + 1] = reservoir.y; a->reservoirOut4[4 * p + 2] = reservoir.z; a->reservoirOut4[4 * p + 3] = reservoir.w;
+            }
+    }
 }
 
 // One full-screen pass of vpl_pbr_gi_denoise.fs (its main(), emitted as denoise_main()).  Float outputs before the framebuffer store.
@@ -326,87 +339,106 @@ typedef struct RefDenoiseArgs {
     const unsigned short* indirectIlluminationH4; const unsigned short* indirectShadowsH4; const unsigned short* prevIndirectIlluminationH4;
     const unsigned short* historyDepthH;
     float* combinedOut3; float* giOut3; float* reservoirOut4; float* historyOut;
+    int rowBegin, rowEnd;
 } RefDenoiseArgs;
 void refglsl_denoise_pass(const RefDenoiseArgs* a) {
     using namespace refglsl;
-    auto tex = [&](const void* d, TexFormat f, TexFilter filt) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; s.filter = filt; return s; };
-    // filters as the reference creates these textures (SURVEY.md Appendix A1): only the reprojected previous-frame reads are really bilinear
-    screen = tex(a->screenH4, RGBA16F, NEAREST); velocity = tex(a->velocityH2, RG16F, NEAREST); normal = tex(a->normal4, RGBA8, NEAREST);
-    ids = tex(a->ids, R32F, NEAREST); depth = tex(a->depth, R32F, NEAREST);
-    prevNormal = tex(a->prevNormal4, RGBA8, LINEAR); prevIds = tex(a->prevIds, R32F, NEAREST); prevDepth = tex(a->prevDepth, R32F, LINEAR);
-    indirectIllumination = tex(a->indirectIlluminationH4, RGBA16F, NEAREST); indirectShadows = tex(a->indirectShadowsH4, RGBA16F, NEAREST);
-    prevIndirectIllumination = tex(a->prevIndirectIlluminationH4, RGBA16F, LINEAR); historyDepth = tex(a->historyDepthH, R16F, NEAREST);
-    multiplier = a->multiplier; mergeReservoirs = a->mergeReservoirs != 0; final = a->final_ != 0;
-    refglsl::time = a->time; framesPerSecond = a->framesPerSecond; numVisible = a->numVisible;
-    for (int y = 0; y < a->H; ++y)
-        for (int x = 0; x < a->W; ++x) {
-            gl_FragCoord = glm::vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
-            fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
-            denoise_main();
-            const size_t p = (size_t)y * a->W + x;
-            for (int c = 0; c < 3; ++c) { a->combinedOut3[3 * p + c] = combinedColor[c]; a->giOut3[3 * p + c] = giColor[c]; }
-            for (int c = 0; c < 4; ++c) a->reservoirOut4[4 * p + c] = reservoirValue[c];
-            a->historyOut[p] = newHistoryDepth;
-        }
+    #pragma omp parallel
+    {
+        auto tex = [&](const void* d, TexFormat f, TexFilter filt) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; s.filter = filt; return s; };
+        // filters as the reference creates these textures (SURVEY.md Appendix A1): only the reprojected previous-frame reads are really bilinear
+        screen = tex(a->screenH4, RGBA16F, NEAREST); velocity = tex(a->velocityH2, RG16F, NEAREST); normal = tex(a->normal4, RGBA8, NEAREST);
+        ids = tex(a->ids, R32F, NEAREST); depth = tex(a->depth, R32F, NEAREST);
+        prevNormal = tex(a->prevNormal4, RGBA8, LINEAR); prevIds = tex(a->prevIds, R32F, NEAREST); prevDepth = tex(a->prevDepth, R32F, LINEAR);
+        indirectIllumination = tex(a->indirectIlluminationH4, RGBA16F, NEAREST); indirectShadows = tex(a->indirectShadowsH4, RGBA16F, NEAREST);
+        prevIndirectIllumination = tex(a->prevIndirectIlluminationH4, RGBA16F, LINEAR); historyDepth = tex(a->historyDepthH, R16F, NEAREST);
+        multiplier = a->multiplier; mergeReservoirs = a->mergeReservoirs != 0; final = a->final_ != 0;
+        refglsl::time = a->time; framesPerSecond = a->framesPerSecond; numVisible = a->numVisible;
+        #pragma omp for schedule(dynamic, 2)
+        for (int y = a->rowBegin; y < a->rowEnd; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                gl_FragCoord = glm::vec4((float)x + 0.5f, (float)y + 0.5f, 0.0f, 1.0f);
+                fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                denoise_main();
+                const size_t p = (size_t)y * a->W + x;
+                for (int c = 0; c < 3; ++c) { a->combinedOut3[3 * p + c] = combinedColor[c]; a->giOut3[3 * p + c] = giColor[c]; }
+                for (int c = 0; c < 4; ++c) a->reservoirOut4[4 * p + c] = reservoirValue[c];
+                a->historyOut[p] = newHistoryDepth;
+            }
+    }
 }
 
 // ---- the four compute shaders.  A dispatch is emulated invocation by invocation with the built-ins set as GL defines them;
 //      invocations of a work group run one after the other where only invocation 0 reads `shared` data after the barrier
-//      (stage 1: it runs last), and as 1024 real threads with a real barrier where the phases depend on each other (the cull) ----
+//      (stage 1: it runs last), and as 1024 real threads with a real barrier where the phases depend on each other (the cull).
+//      Work groups are spread over the host's threads ----
 typedef struct RefColorArgs {
     int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
     const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
 } RefColorArgs;
 void refglsl_color(const RefColorArgs* a) {
     using namespace refglsl;
-    infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
-    cs_color::infiniteLightColor = glm::vec3(a->sunColor[0], a->sunColor[1], a->sunColor[2]);
-    cs_color::lightData = (VplData*)a->lightData; cs_color::numVisible = a->numVisible; cs_color::diffuseIndices = (const AtlasEntry*)a->diffuseIndices;
-    for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) {
-        cs_color::shadowCubeMaps[i].data = a->shadowAtlases[i]; cs_color::shadowCubeMaps[i].res = a->cubeRes; cs_color::shadowCubeMaps[i].rgba8 = nullptr;
-        cs_color::diffuseCubeMaps[i].data = nullptr; cs_color::diffuseCubeMaps[i].res = a->cubeRes; cs_color::diffuseCubeMaps[i].rgba8 = a->diffuseAtlases[i];
-    }
-    gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
-    for (unsigned g = 0; g < 1024; ++g) {
-        gl_GlobalInvocationID = gl_LocalInvocationID = glm::uvec3(g, 0, 0); gl_LocalInvocationIndex = g;
-        cs_color::color_main();
+    #pragma omp parallel
+    {
+        infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+        cs_color::infiniteLightColor = glm::vec3(a->sunColor[0], a->sunColor[1], a->sunColor[2]);
+        cs_color::lightData = (VplData*)a->lightData; cs_color::numVisible = a->numVisible; cs_color::diffuseIndices = (const AtlasEntry*)a->diffuseIndices;
+        for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) {
+            cs_color::shadowCubeMaps[i].data = a->shadowAtlases[i]; cs_color::shadowCubeMaps[i].res = a->cubeRes; cs_color::shadowCubeMaps[i].rgba8 = nullptr;
+            cs_color::diffuseCubeMaps[i].data = nullptr; cs_color::diffuseCubeMaps[i].res = a->cubeRes; cs_color::diffuseCubeMaps[i].rgba8 = a->diffuseAtlases[i];
+        }
+        gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
+        #pragma omp for schedule(static)
+        for (int g = 0; g < 1024; ++g) {
+            gl_GlobalInvocationID = gl_LocalInvocationID = glm::uvec3((unsigned)g, 0, 0); gl_LocalInvocationIndex = (unsigned)g;
+            cs_color::color_main();
+        }
     }
 }
-typedef struct RefStage1Args { int W, H; const float* depth; const unsigned char* normal4; const float* invProjectionView; void* out; } RefStage1Args;
+typedef struct RefStage1Args { int W, H; const float* depth; const unsigned char* normal4; const float* invProjectionView; void* out; int tileRowBegin, tileRowEnd; } RefStage1Args;
 void refglsl_stage1(const RefStage1Args* a) {
     using namespace refglsl;
-    auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
-    cs_stage1::gDepth = tex(a->depth, R32F); cs_stage1::gNormal = tex(a->normal4, RGBA8);
-    std::memcpy(&cs_stage1::invProjectionView[0][0], a->invProjectionView, 64);
-    cs_stage1::vplNumVisiblePerTile = (VplStage1PerTileOutputs*)a->out;
     const unsigned tilesX = a->W / 5, tilesY = a->H / 5;                    // DispatchCompute(viewportWidth / tileXDivisor, viewportHeight / tileYDivisor, 1)
-    gl_NumWorkGroups = glm::uvec3(tilesX, tilesY, 1); gl_WorkGroupSize = glm::uvec3(5, 5, 1);
-    for (unsigned ty = 0; ty < tilesY; ++ty)
-        for (unsigned tx = 0; tx < tilesX; ++tx) {
-            gl_WorkGroupID = glm::uvec3(tx, ty, 0);
-            for (unsigned k = 1; k <= 25; ++k) {                             // invocations 1..24, then invocation 0 (the one that reads the shared arrays)
-                const unsigned idx = k % 25, lx = idx % 5, ly = idx / 5;
-                gl_LocalInvocationID = glm::uvec3(lx, ly, 0); gl_LocalInvocationIndex = idx;
-                gl_GlobalInvocationID = glm::uvec3(tx * 5 + lx, ty * 5 + ly, 0);
-                cs_stage1::stage1_main();
+    #pragma omp parallel
+    {
+        auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
+        cs_stage1::gDepth = tex(a->depth, R32F); cs_stage1::gNormal = tex(a->normal4, RGBA8);
+        std::memcpy(&cs_stage1::invProjectionView[0][0], a->invProjectionView, 64);
+        cs_stage1::vplNumVisiblePerTile = (VplStage1PerTileOutputs*)a->out;
+        gl_NumWorkGroups = glm::uvec3(tilesX, tilesY, 1); gl_WorkGroupSize = glm::uvec3(5, 5, 1);
+        #pragma omp for schedule(dynamic, 1)
+        for (int ty = a->tileRowBegin; ty < a->tileRowEnd; ++ty)
+            for (unsigned tx = 0; tx < tilesX; ++tx) {
+                gl_WorkGroupID = glm::uvec3(tx, (unsigned)ty, 0);
+                for (unsigned k = 1; k <= 25; ++k) {                         // invocations 1..24, then invocation 0 (the one that reads the shared arrays)
+                    const unsigned idx = k % 25, lx = idx % 5, ly = idx / 5;
+                    gl_LocalInvocationID = glm::uvec3(lx, ly, 0); gl_LocalInvocationIndex = idx;
+                    gl_GlobalInvocationID = glm::uvec3(tx * 5 + lx, (unsigned)ty * 5 + ly, 0);
+                    cs_stage1::stage1_main();
+                }
             }
-        }
+    }
 }
 typedef struct RefStage2Args {
     int tilesX, tilesY; const float* viewPosition; const void* lightData; const void* stage1Data; int numVisible; const int* vplVisibleIndex; void* out;
+    int tileRowBegin, tileRowEnd;
 } RefStage2Args;
 void refglsl_stage2(const RefStage2Args* a) {
     using namespace refglsl;
-    cs_stage2::viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
-    cs_stage2::lightData = (const VplData*)a->lightData; cs_stage2::stage1Data = (const VplStage1PerTileOutputs*)a->stage1Data;
-    cs_stage2::numVisible = a->numVisible; cs_stage2::vplVisibleIndex = a->vplVisibleIndex; cs_stage2::vplNumVisiblePerTile = (VplStage2PerTileOutputs*)a->out;
-    gl_WorkGroupSize = glm::uvec3(32, 2, 1); gl_NumWorkGroups = glm::uvec3(a->tilesX / 32, a->tilesY / 2, 1);      // BE:1774-1778
-    for (unsigned gy = 0; gy < gl_NumWorkGroups.y * 2; ++gy)
-        for (unsigned gx = 0; gx < gl_NumWorkGroups.x * 32; ++gx) {
-            gl_GlobalInvocationID = glm::uvec3(gx, gy, 0); gl_WorkGroupID = glm::uvec3(gx / 32, gy / 2, 0);
-            gl_LocalInvocationID = glm::uvec3(gx % 32, gy % 2, 0); gl_LocalInvocationIndex = (gy % 2) * 32 + gx % 32;
-            cs_stage2::stage2_main();
-        }
+    #pragma omp parallel
+    {
+        cs_stage2::viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
+        cs_stage2::lightData = (const VplData*)a->lightData; cs_stage2::stage1Data = (const VplStage1PerTileOutputs*)a->stage1Data;
+        cs_stage2::numVisible = a->numVisible; cs_stage2::vplVisibleIndex = a->vplVisibleIndex; cs_stage2::vplNumVisiblePerTile = (VplStage2PerTileOutputs*)a->out;
+        gl_WorkGroupSize = glm::uvec3(32, 2, 1); gl_NumWorkGroups = glm::uvec3(a->tilesX / 32, a->tilesY / 2, 1);      // BE:1774-1778
+        #pragma omp for schedule(dynamic, 1)
+        for (int gy = a->tileRowBegin; gy < a->tileRowEnd; ++gy)
+            for (unsigned gx = 0; gx < gl_NumWorkGroups.x * 32; ++gx) {
+                gl_GlobalInvocationID = glm::uvec3(gx, (unsigned)gy, 0); gl_WorkGroupID = glm::uvec3(gx / 32, (unsigned)gy / 2, 0);
+                gl_LocalInvocationID = glm::uvec3(gx % 32, (unsigned)gy % 2, 0); gl_LocalInvocationIndex = ((unsigned)gy % 2) * 32 + gx % 32;
+                cs_stage2::stage2_main();
+            }
+    }
 }
 typedef struct RefCullArgs {
     int totalNumLights, csmRes; const float* sunDir; const float* cascadeProjViews; const float* cascadePlanes; const float* csm;
@@ -416,10 +448,6 @@ static pthread_barrier_t g_cullBarrier;
 static void cullBarrierWait() { pthread_barrier_wait(&g_cullBarrier); }
 void refglsl_cull(const RefCullArgs* a) {
     using namespace refglsl;
-    infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
-    for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
-    for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
-    infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
     cs_cull::totalNumLights = a->totalNumLights; cs_cull::lightData = (const VplData*)a->lightData;
     cs_cull::updatedLightData = (VplData*)a->updatedLightData; cs_cull::vplVisibleIndex = a->vplVisibleIndex;
     const unsigned n = 1024;                                                 // one work group of local_size_x = 1024 (BE:1603)
@@ -427,7 +455,12 @@ void refglsl_cull(const RefCullArgs* a) {
     barrierHook = cullBarrierWait;
     std::vector<std::thread> threads;
     for (unsigned t = 0; t < n; ++t)
-        threads.emplace_back([t]() {
+        threads.emplace_back([t, a]() {
+            // the uniforms are per thread (see PERINV): every invocation's thread sets its own copy
+            infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+            for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
+            for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
+            infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
             gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
             gl_LocalInvocationID = gl_GlobalInvocationID = glm::uvec3(t, 0, 0); gl_LocalInvocationIndex = t;
             cs_cull::cull_main();
@@ -440,7 +473,7 @@ void refglsl_cull(const RefCullArgs* a) {
 '''
 
 
-CS_PRE = {'cs_color': 'static vec3 infiniteLightColor;\nstatic VplData* lightData; static const int* numVisible; static const AtlasEntry* diffuseIndices;\nstatic samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'static sampler2D gDepth, gNormal; static mat4 invProjectionView;\nstatic VplStage1PerTileOutputs* vplNumVisiblePerTile;\nstatic vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'static vec3 viewPosition;\nstatic const VplData* lightData; static const VplStage1PerTileOutputs* stage1Data; static int numVisible; static const int* vplVisibleIndex;\nstatic VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n'}
+CS_PRE = {'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n'}
 
 
 def generate():
@@ -488,7 +521,8 @@ def build(force=False):
     if not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(os.path.abspath(__file__)):
         return lib
     open(src, "w").write(generate())
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I" + REF, "-o", lib, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fopenmp", "-ftls-model=local-dynamic", "-ffp-contract=off",
+                           "-I" + REF, "-o", lib, src])
     return lib
 
 

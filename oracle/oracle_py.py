@@ -83,12 +83,13 @@ class RefColorArgs(C.Structure):
 
 
 class RefStage1Args(C.Structure):
-    _fields_ = [("W", C.c_int), ("H", C.c_int)] + [(n, C.c_void_p) for n in ("depth", "normal4", "invProjectionView", "out")]
+    _fields_ = [("W", C.c_int), ("H", C.c_int)] + [(n, C.c_void_p) for n in ("depth", "normal4", "invProjectionView", "out")] + \
+               [("tileRowBegin", C.c_int), ("tileRowEnd", C.c_int)]
 
 
 class RefStage2Args(C.Structure):
     _fields_ = [("tilesX", C.c_int), ("tilesY", C.c_int), ("viewPosition", C.c_void_p), ("lightData", C.c_void_p), ("stage1Data", C.c_void_p),
-                ("numVisible", C.c_int), ("vplVisibleIndex", C.c_void_p), ("out", C.c_void_p)]
+                ("numVisible", C.c_int), ("vplVisibleIndex", C.c_void_p), ("out", C.c_void_p), ("tileRowBegin", C.c_int), ("tileRowEnd", C.c_int)]
 
 
 class RefCullArgs(C.Structure):
@@ -130,12 +131,13 @@ def reference_glsl_color(ref, fp, updated, visible, entries, shadow_atlas, diffu
     return out
 
 
-def reference_glsl_stage1(ref, fp, gb):
+def reference_glsl_stage1(ref, fp, gb, tile_rows=None):
     """vpl_tiled_deferred_culling_stage1.cs (shader text): [tiles, 8] float32."""
     H, W = gb.depth.shape
     out = np.zeros(((W // 5) * (H // 5), 8), np.float32)
     a = RefStage1Args()
     a.W, a.H = W, H
+    a.tileRowBegin, a.tileRowEnd = (0, H // 5) if tile_rows is None else tile_rows
     keep = [np.ascontiguousarray(gb.depth), np.ascontiguousarray(gb.normal), _f32(list(fp.invProjectionView))]
     a.depth, a.normal4, a.invProjectionView = [x.ctypes.data for x in keep]
     a.out = out.ctypes.data
@@ -143,7 +145,7 @@ def reference_glsl_stage1(ref, fp, gb):
     return out
 
 
-def reference_glsl_stage2(ref, fp, W, H, vpl_data, stage1, visible):
+def reference_glsl_stage2(ref, fp, W, H, vpl_data, stage1, visible, tile_rows=None):
     """vpl_tiled_deferred_culling_stage2.cs (shader text): [tiles, 13] int32.  The shader's `numVisible` / `vplVisibleIndex[]` are the
     count and the list that follows it in the cull's output (slot 0 holds the count)."""
     tx, ty = W // 5, H // 5
@@ -154,6 +156,7 @@ def reference_glsl_stage2(ref, fp, W, H, vpl_data, stage1, visible):
     idx = np.ascontiguousarray(visible[1:1 + v], np.int32)
     a = RefStage2Args()
     a.tilesX, a.tilesY, a.numVisible = tx, ty, v
+    a.tileRowBegin, a.tileRowEnd = (0, ty) if tile_rows is None else tile_rows
     keep = [_f32(list(fp.viewPosition)), np.ascontiguousarray(vpl_data, np.float32), np.ascontiguousarray(stage1, np.float32)]
     a.viewPosition, a.lightData, a.stage1Data = [x.ctypes.data for x in keep]
     a.vplVisibleIndex, a.out = idx.ctypes.data, out.ctypes.data
@@ -166,7 +169,8 @@ class RefDenoiseArgs(C.Structure):
                 ("time", C.c_float), ("framesPerSecond", C.c_float)] + \
                [(n, C.c_void_p) for n in ("numVisible", "screenH4", "velocityH2", "normal4", "ids", "depth", "prevNormal4", "prevIds", "prevDepth",
                                           "indirectIlluminationH4", "indirectShadowsH4", "prevIndirectIlluminationH4", "historyDepthH",
-                                          "combinedOut3", "giOut3", "reservoirOut4", "historyOut")]
+                                          "combinedOut3", "giOut3", "reservoirOut4", "historyOut")] + \
+               [("rowBegin", C.c_int), ("rowEnd", C.c_int)]
 
 
 def _to_half(a):
@@ -179,8 +183,9 @@ class ReferenceGlslDenoiser:
     (refglsl_denoise_pass): Fbo1/Fbo2 ping-pong, multiplier 2^i - 1, merge pass first, final pass last, swap with the previous-frame
     FBO.  Attachments are stored as binary16 between passes, as the reference's RGB16F / RGBA16F / R16F targets do."""
 
-    def __init__(self, ref, W, H, denoise_iters):
+    def __init__(self, ref, W, H, denoise_iters, rows=None):
         self.ref, self.W, self.H, self.iters = ref, W, H, denoise_iters
+        self.rows = (0, H) if rows is None else rows                  # rows of the full-height planes to process (bounded samples)
         self.prev_gi = np.zeros((H, W, 4), np.float16)
         self.prev_history = np.zeros((H, W), np.float16)
 
@@ -192,6 +197,7 @@ class ReferenceGlslDenoiser:
         for i in range(self.iters):
             a = RefDenoiseArgs()
             a.W, a.H, a.multiplier = W, H, (1 << i) - 1
+            a.rowBegin, a.rowEnd = self.rows
             a.mergeReservoirs, a.final_ = (1 if i < 1 else 0), (1 if i + 1 == self.iters else 0)
             a.time, a.framesPerSecond = float(fp.time), float(np.float32(1.0 / fp.deltaSeconds))
             combined, gi = np.zeros((H, W, 3), np.float32), np.zeros((H, W, 3), np.float32)
@@ -215,10 +221,12 @@ class RefGatherArgs(C.Structure):
     _fields_ = [("W", C.c_int), ("H", C.c_int), ("cubeRes", C.c_int), ("numAtlases", C.c_int)] + \
                [(n, C.c_void_p) for n in ("depth", "normal4", "albedo4", "refl2", "rma4", "ssaoH", "screenH4", "viewPosition", "invProjectionView")] + \
                [("time", C.c_float), ("minGiOcclusionFactor", C.c_float)] + \
-               [(n, C.c_void_p) for n in ("lightData", "numVisible", "shadowIndices", "shadowAtlases", "colorOut3", "reservoirOut4")]
+               [(n, C.c_void_p) for n in ("lightData", "numVisible", "shadowIndices", "shadowAtlases", "colorOut3", "reservoirOut4")] + \
+               [("rowBegin", C.c_int), ("rowEnd", C.c_int), ("usePerceptualRoughness", C.c_int), ("minRoughness", C.c_float),
+                ("fogColor", C.c_float * 3), ("fogDensity", C.c_float)]
 
 
-def reference_glsl_gather(ref, fp, gb, updated, visible, entries, shadow_atlas, cube_res):
+def reference_glsl_gather(ref, fp, gb, updated, visible, entries, shadow_atlas, cube_res, rows=None):
     """vpl_pbr_gi.fs (the reference's shader text compiled as C++) over one frame: float `color` [H,W,3] and `reservoir` [H,W,4]
     as written by the shader, before the 16F framebuffer store.  `updated`/`visible`/`entries` are the coloured compacted VPL
     table, the visible list and shadowDiffuseIndices (the outputs of the two stages before the gather)."""
@@ -230,8 +238,10 @@ def reference_glsl_gather(ref, fp, gb, updated, visible, entries, shadow_atlas, 
     tab = _atlas_ptrs(shadow_atlas)
     vp = np.ascontiguousarray(list(fp.viewPosition), np.float32)
     ipv = np.ascontiguousarray(list(fp.invProjectionView), np.float32)
-    fog = np.ascontiguousarray(list(fp.fogColor), np.float32)
-    ref.refglsl_set_uniforms(int(fp.usePerceptualRoughness), float(fp.minRoughness), _p(fog), float(fp.fogDensity))
+    a.usePerceptualRoughness, a.minRoughness, a.fogDensity = int(fp.usePerceptualRoughness), float(fp.minRoughness), float(fp.fogDensity)
+    for i in range(3):
+        a.fogColor[i] = float(fp.fogColor[i])
+    a.rowBegin, a.rowEnd = (0, H) if rows is None else rows          # rows: (begin, end) of the full-height planes to shade (bounded samples)
     keep = [np.ascontiguousarray(x) for x in (gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao, gb.screen,
                                               updated, visible, entries)]
     (a.depth, a.normal4, a.albedo4, a.refl2, a.rma4, a.ssaoH, a.screenH4, a.lightData, a.numVisible, a.shadowIndices) = [x.ctypes.data for x in keep]
