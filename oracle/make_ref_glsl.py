@@ -19,8 +19,8 @@ macros they use — and applies purely lexical adaptations:
 What an OpenGL driver would supply is written out in the prelude from the GL 4.6 specification and is NOT
 reference code: samplers (texel fetch at texel centres, bilinear filter with 8-bit sub-texel weights, cube-map face selection,
 hardware PCF), interface blocks and uniforms as globals, compute built-ins, barrier() (real: the cull runs as 1024 threads),
-`shared` arrays.  The result goes to oracle/_ref/ref_glsl_gen.cpp (generated, git-ignored, never committed) and is compiled to
-oracle/_ref/libref_glsl.so.  tests/test_reference_glsl.py holds every stage of the oracle against it bit for bit, and
+`shared` arrays.  The result goes to oracle/_ref/ref_glsl_gen.cpp (generated, git-ignored, never committed, deleted after the compile unless
+SGI_KEEP_GENERATED=1) and is compiled to oracle/_ref/libref_glsl.so.  tests/test_reference_glsl.py holds every stage of the oracle against it bit for bit, and
 tests/golden/make_shader_text_golden.py chains the compiled shaders into a fixture that no oracle code touched.
 Nothing of the reference is copied into the repository.
 
@@ -523,6 +523,8 @@ def build(force=False):
     open(src, "w").write(generate())
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fopenmp", "-ftls-model=local-dynamic", "-ffp-contract=off",
                            "-I" + REF, "-o", lib, src])
+    if os.environ.get("SGI_KEEP_GENERATED", "") != "1":
+        os.remove(src)                  # the adapted shader text is reference material: only the compiled library stays on disk
     return lib
 
 
