@@ -40,11 +40,14 @@ OUT_DIR = os.path.join(HERE, "_ref")
 WANTED = [
     ("common.glsl", ["boundHDR", "saturate", "computeTexelSize", "worldPositionFromDepth", "hash", "floatConstruct", "random", "sampleNormalWithOffset", "sampleNormal"]),
     ("fog.glsl", ["applyFog"]),
-    ("pbr.glsl", ["calculateShadowValue1Sample", "sampleShadowTexture", "calculateInfiniteShadowValue", "vplDiffuseAttenuation", "vplSpecularAttenuation"]),
+    ("pbr.glsl", ["calculateShadowValue8Samples", "calculateShadowValue1Sample", "quadraticAttenuation", "sampleShadowTexture", "calculateInfiniteShadowValue", "vplDiffuseAttenuation", "vplSpecularAttenuation"]),
     ("pbr2.glsl", ["NDF_GGX", "Visibility_G_SmithGGX", "Fr_Fresnel_Schlick", "Fd_Lambert", "singleScatteringBRDF_Specular",
                    "singleScatteringBRDF_Diffuse_Lambert", "RemapRoughness", "BRDF_Base", "BRDF_DotProducts",
                    "BRDF_Lambert_SeparateDiffuseSpecular", "calculateLighting_Lambert_SeparateDiffuseSpecular",
-                   "calculateVirtualPointLighting2"]),
+                   "calculateVirtualPointLighting2",
+                   # the deferred direct-lighting pass: Burley diffuse + the same specular lobe
+                   "Fd_Fresnel_Schlick", "Fd_Burley", "singleScatteringBRDF_Diffuse_Burley", "BRDF_Burley", "calculateLighting_Burley",
+                   "calculateDirectionalLighting", "calculatePointLighting2"]),
     ("vpl_pbr_gi.fs", ["performLightingCalculations"]),          # the whole body of the gather shader (main() only forwards to it)
     ("vpl_pbr_gi_denoise.fs", ["filterInput", "computeMergedReservoir", "main"]),     # the denoiser: main() is emitted as denoise_main()
 ]
@@ -57,6 +60,7 @@ COMPUTE = [
     ("vpl_tiled_deferred_culling_stage1.cs", "cs_stage1", "stage1_main", []),
     ("vpl_tiled_deferred_culling_stage2.cs", "cs_stage2", "stage2_main", ["SHUFFLE_DOWN"]),
     ("viscull_vpls.cs", "cs_cull", "cull_main", []),
+    ("pbr.fs", "fs_direct", "direct_main", []),           # widening row f3: the deferred direct-lighting pass that produces `screen`
 ]
 TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray|sampler2DArrayShadow)"
 
@@ -227,6 +231,7 @@ static void (*barrierHook)() = nullptr;
 static inline void barrier() { if (barrierHook) barrierHook(); }
 static inline int atomicAdd(int& mem, int v) { return __atomic_fetch_add(&mem, v, __ATOMIC_SEQ_CST); }
 static thread_local vec3 infiniteLightDirection; static thread_local float infiniteLightZnear = 0.0f, infiniteLightZfar = 1.0f, infiniteLightDepthBias = 0.0f;
+static thread_local float pointLightAmbientIntensity = 0.003f;            // pbr.glsl:66
 static thread_local sampler2DArrayShadow infiniteLightShadowMap; static thread_local vec4 cascadePlanes[3]; static thread_local mat4 cascadeProjViews[4];
 struct VplStage1PerTileOutputs { vec4 averageLocalPosition; vec4 averageLocalNormal; };        // vpl_common.glsl
 #define MAX_VPLS_PER_TILE 12
@@ -372,6 +377,47 @@ void refglsl_denoise_pass(const RefDenoiseArgs* a) {
 //      invocations of a work group run one after the other where only invocation 0 reads `shared` data after the barrier
 //      (stage 1: it runs last), and as 1024 real threads with a real barrier where the phases depend on each other (the cull).
 //      Work groups are spread over the host's threads ----
+// One full-screen pass of pbr.fs (deferred direct lighting: point lights without and with cube shadows, the sun with its cascaded shadow map).
+typedef struct RefDirectArgs {
+    int W, H, cubeRes, numAtlases, csmRes, numLights, numShadowLights, rowBegin, rowEnd;
+    const float* depth; const unsigned char* normal4; const unsigned char* albedo4; const unsigned char* refl2; const unsigned char* rma4; const unsigned short* ssaoH;
+    const float* viewPosition; const float* invProjectionView; const float* sunDir; const float* sunColor; const float* cascadeProjViews; const float* cascadePlanes; const float* csm;
+    const void* nonShadowCasters; const void* shadowCasters; const void* shadowIndices; const unsigned short* const* shadowAtlases;
+    float emissionStrength; float depthBias, zNear, zFar;
+    float* colorOut3;
+} RefDirectArgs;
+void refglsl_direct_lighting(const RefDirectArgs* a) {
+    using namespace refglsl;
+    #pragma omp parallel
+    {
+        auto tex = [&](const void* d, TexFormat f) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; return s; };
+        fs_direct::gDepth = tex(a->depth, R32F); fs_direct::gNormal = tex(a->normal4, RGBA8); fs_direct::gAlbedo = tex(a->albedo4, RGBA8);
+        fs_direct::gBaseReflectivity = tex(a->refl2, RG8); fs_direct::gRoughnessMetallicAmbient = tex(a->rma4, RGBA8);
+        fs_direct::ssao.data = a->ssaoH; fs_direct::ssao.W = a->W; fs_direct::ssao.H = a->H; fs_direct::ssao.fmt = R16F;
+        std::memcpy(&fs_direct::invProjectionView[0][0], a->invProjectionView, 64);
+        fs_direct::windowWidth = (float)a->W; fs_direct::windowHeight = (float)a->H;
+        fs_direct::viewPosition = glm::vec3(a->viewPosition[0], a->viewPosition[1], a->viewPosition[2]);
+        fs_direct::emissionStrength = a->emissionStrength;
+        fs_direct::numLights = a->numLights; fs_direct::numShadowLights = a->numShadowLights;
+        fs_direct::nonShadowCasters = (const fs_direct::PointLight*)a->nonShadowCasters; fs_direct::shadowCasters = (const fs_direct::PointLight*)a->shadowCasters;
+        fs_direct::shadowIndices = (const AtlasEntry*)a->shadowIndices;
+        for (int i = 0; i < a->numAtlases && i < MAX_TOTAL_SHADOW_ATLASES; ++i) { fs_direct::shadowCubeMaps[i].data = a->shadowAtlases[i]; fs_direct::shadowCubeMaps[i].res = a->cubeRes; }
+        fs_direct::infiniteLightColor = glm::vec3(a->sunColor[0], a->sunColor[1], a->sunColor[2]);
+        infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+        infiniteLightDepthBias = a->depthBias; infiniteLightZnear = a->zNear; infiniteLightZfar = a->zFar;
+        for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
+        for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
+        infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
+        #pragma omp for schedule(dynamic, 2)
+        for (int y = a->rowBegin; y < a->rowEnd; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                fs_direct::fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                fs_direct::direct_main();
+                const size_t p = (size_t)y * a->W + x;
+                for (int c = 0; c < 3; ++c) a->colorOut3[3 * p + c] = fs_direct::fsColor[c];
+            }
+    }
+}
 typedef struct RefColorArgs {
     int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
     const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
@@ -473,7 +519,7 @@ void refglsl_cull(const RefCullArgs* a) {
 '''
 
 
-CS_PRE = {'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n'}
+CS_PRE = {'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n', 'fs_direct': '#define INFINITE_LIGHTING_ENABLED\nstruct PointLight { vec4 position; vec4 color; float radius; float farPlane; float _1[2]; };        // pbr.fs:15-21\nPERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient; PERINV sampler2DRect ssao;\nPERINV mat4 invProjectionView; PERINV float windowWidth, windowHeight; PERINV vec3 viewPosition; PERINV float emissionStrength = 0.0f;\nPERINV int numLights = 0, numShadowLights = 0; PERINV const PointLight* nonShadowCasters; PERINV const PointLight* shadowCasters;\nPERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES]; PERINV const AtlasEntry* shadowIndices;\nPERINV vec3 infiniteLightColor; PERINV vec2 fsTexCoords; PERINV vec3 fsColor;\n'}
 
 
 def generate():

@@ -72,7 +72,7 @@ def reference_glsl():
     L.refglsl_bound_hdr.restype = C.c_float
     L.refglsl_gather.argtypes = [C.c_void_p]
     L.refglsl_denoise_pass.argtypes = [C.c_void_p]
-    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull"):
+    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull", "refglsl_direct_lighting"):
         getattr(L, name).argtypes = [C.c_void_p]
     return L
 
@@ -95,6 +95,44 @@ class RefStage2Args(C.Structure):
 class RefCullArgs(C.Structure):
     _fields_ = [("totalNumLights", C.c_int), ("csmRes", C.c_int)] + [(n, C.c_void_p) for n in ("sunDir", "cascadeProjViews", "cascadePlanes", "csm",
                                                                                               "lightData", "updatedLightData", "vplVisibleIndex")]
+
+
+class RefDirectArgs(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("W", "H", "cubeRes", "numAtlases", "csmRes", "numLights", "numShadowLights", "rowBegin", "rowEnd")] + \
+               [(n, C.c_void_p) for n in ("depth", "normal4", "albedo4", "refl2", "rma4", "ssaoH", "viewPosition", "invProjectionView", "sunDir", "sunColor",
+                                          "cascadeProjViews", "cascadePlanes", "csm", "nonShadowCasters", "shadowCasters", "shadowIndices", "shadowAtlases")] + \
+               [(n, C.c_float) for n in ("emissionStrength", "depthBias", "zNear", "zFar")] + [("colorOut3", C.c_void_p)]
+
+
+def reference_glsl_direct_lighting(ref, fp, gb, csm, csm_res, shadow_atlas, cube_res, lights=None, shadow_lights=None, shadow_entries=None,
+                                   sun_color=None, emission_strength=0.0, depth_bias=0.0, z_near=1.0, z_far=1000.0, rows=None):
+    """pbr.fs (the reference's deferred direct-lighting pass, compiled from its shader text): float RGB of
+    `fsColor` before the RGB16F store — what the GI path receives as `screen`.  lights / shadow_lights: float32 [n, 12] PointLight
+    records (position xyzw, colour xyzw, radius, farPlane, 2 pad); shadow_entries: int32 [n, 2] atlas entries of the shadow casters."""
+    H, W = gb.depth.shape
+    out = np.zeros((H, W, 3), np.float32)
+    z = lambda n, dt: np.zeros((max(n, 1), 12 if dt == np.float32 else 2), dt)
+    lights = z(0, np.float32) if lights is None else np.ascontiguousarray(lights, np.float32)
+    shadow_lights = z(0, np.float32) if shadow_lights is None else np.ascontiguousarray(shadow_lights, np.float32)
+    shadow_entries = z(0, np.int32) if shadow_entries is None else np.ascontiguousarray(shadow_entries, np.int32)
+    a = RefDirectArgs()
+    a.W, a.H, a.cubeRes, a.numAtlases, a.csmRes = W, H, cube_res, int(shadow_atlas.shape[0]), csm_res
+    a.numLights = 0 if lights is None or lights.shape[1] != 12 or not lights.any() else int(lights.shape[0])
+    a.numShadowLights = 0 if not shadow_lights.any() else int(shadow_lights.shape[0])
+    a.rowBegin, a.rowEnd = (0, H) if rows is None else rows
+    tab = _atlas_ptrs(shadow_atlas)
+    sun = list(fp.infiniteLightColor) if sun_color is None else sun_color
+    keep = [np.ascontiguousarray(x) for x in (gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao)] + \
+           [_f32(list(fp.viewPosition)), _f32(list(fp.invProjectionView)), _f32(list(fp.infiniteLightDirection)), _f32(sun),
+            _f32([list(m) for m in fp.cascadeProjViews]), _f32([list(p) for p in fp.cascadePlanes]), np.ascontiguousarray(csm, np.float32),
+            lights, shadow_lights, shadow_entries]
+    (a.depth, a.normal4, a.albedo4, a.refl2, a.rma4, a.ssaoH, a.viewPosition, a.invProjectionView, a.sunDir, a.sunColor, a.cascadeProjViews,
+     a.cascadePlanes, a.csm, a.nonShadowCasters, a.shadowCasters, a.shadowIndices) = [x.ctypes.data for x in keep]
+    a.shadowAtlases = C.addressof(tab)
+    a.emissionStrength, a.depthBias, a.zNear, a.zFar = float(emission_strength), float(depth_bias), float(z_near), float(z_far)
+    a.colorOut3 = out.ctypes.data
+    ref.refglsl_direct_lighting(C.addressof(a))
+    return out
 
 
 def _f32(x):

@@ -220,3 +220,30 @@ def test_gather_and_denoiser_shader_text_with_very_few_vpls(libs, num_vpls):
     passes = ReferenceGlslDenoiser(ref, d.W, d.H, s.denoise_iters).frame(fp, gb, d.gb[-1], V, o.gi_color, o.gi_reservoir)
     o.denoise(fp, gb, d.gb[-1], keep_passes=True)
     assert np.array_equal(passes[-1]["combined"][..., :3].view(np.uint16), o.combined[..., :3].view(np.uint16))
+
+
+def test_direct_lighting_shader_text_runs_and_behaves(libs):
+    """pbr.fs (widening row f3, the pass that produces the GI path's `screen` input) compiled from the shader text: no CUDA
+    counterpart exists yet, so this only fixes its behaviour — emissive pass-through with every light off, linearity in the sun's
+    colour, sun shadows darkening, and a point light adding energy around itself."""
+    from oracle.oracle_py import reference_glsl_direct_lighting
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    d = SceneData("tiny", frames=1)
+    s, fp, gb = d.scene, d.fp[0], d.gb[0]
+    common = dict(csm=d.csm[0], csm_res=s.csm_res, shadow_atlas=d.shadow_atlas, cube_res=s.cube_res)
+    # every light off: fsColor = boundHDR(emissive * emissionStrength), emissive = (albedo.a, baseReflectivity.g, rma.b)
+    off = reference_glsl_direct_lighting(ref, fp, gb, sun_color=[0, 0, 0], emission_strength=2.0, **common)
+    emissive = np.stack([gb.albedo[..., 3] / np.float32(255), gb.baseReflectivity[..., 1] / np.float32(255),
+                         gb.roughnessMetallicAmbient[..., 2] / np.float32(255)], -1).astype(np.float32)
+    assert np.array_equal(off, emissive * np.float32(2.0))
+    sun1 = reference_glsl_direct_lighting(ref, fp, gb, **common)
+    sun2 = reference_glsl_direct_lighting(ref, fp, gb, sun_color=[2 * c for c in fp.infiniteLightColor], **common)
+    assert np.isfinite(sun1).all() and sun1.min() >= 0.0 and sun1.max() > 0.0
+    assert np.allclose(sun2, 2.0 * sun1, rtol=1e-5, atol=1e-7)                       # the sun's colour enters linearly
+    lit = sun1.sum(-1) > 0
+    assert 0.02 < lit.mean() < 0.98                                                   # some pixels are lit by the sun, some are in its shadow
+    light = np.zeros((1, 12), np.float32)
+    light[0, 0:4] = [0.0, 15.0, 0.0, 1.0]; light[0, 4:8] = [400.0, 400.0, 400.0, 1.0]; light[0, 8] = 40.0; light[0, 9] = 40.0
+    withp = reference_glsl_direct_lighting(ref, fp, gb, lights=light, **common)
+    assert (withp >= sun1 - 1e-6).all() and float((withp - sun1).sum()) > 0.0
