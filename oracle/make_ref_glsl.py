@@ -210,17 +210,19 @@ static inline vec4 texture(const samplerCubeArray& s, vec4 dirLayer) {      // G
     return vec4((float)t / 65535.0f, 0.0f, 0.0f, 1.0f);
 }
 static inline vec4 textureLod(const samplerCubeArray& s, vec4 dirLayer, int) { return texture(s, dirLayer); }
-// sampler2DArrayShadow, LINEAR + compare LEQUAL (hardware PCF, SURVEY.md Appendix A4): the reference value is compared with the four
-// bilinear neighbours and the 0/1 results are blended with 8-bit sub-texel weights, in the operation order of oracle.cpp's shadowArrayPcf
+// sampler2DArrayShadow, LINEAR + compare LEQUAL (hardware PCF, SURVEY.md Appendix A4): the reference value (clamped to [0, 1] as for
+// a fixed-point depth format) is compared with the four bilinear neighbours and the 0/1 results are blended with the bilinear
+// weights, in the operation order of oracle.cpp's shadowArrayPcf — the same reading of the GL filter on both sides
 struct sampler2DArrayShadow { const float* data = nullptr; int res = 0; int layers = 4; };
 static inline float texture(const sampler2DArrayShadow& s, vec4 c) {         // c = (u, v, layer, reference depth)
     const int layer = clampi((int)std::floor(c.z + 0.5f), 0, s.layers - 1);
     const float* m = s.data + (size_t)layer * s.res * s.res;
     const float fu = c.x * (float)s.res - 0.5f, fv = c.y * (float)s.res - 0.5f;
     const float i0f = std::floor(fu), j0f = std::floor(fv);
-    const float a = std::floor((fu - i0f) * 256.0f + 0.5f) * (1.0f / 256.0f), b = std::floor((fv - j0f) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const float a = fu - i0f, b = fv - j0f;
+    const float ref = glm::clamp(c.w, 0.0f, 1.0f);
     const int i0 = clampi((int)i0f, 0, s.res - 1), i1 = clampi((int)i0f + 1, 0, s.res - 1), j0 = clampi((int)j0f, 0, s.res - 1), j1 = clampi((int)j0f + 1, 0, s.res - 1);
-    auto lit = [&](int i, int j) { return c.w <= m[(size_t)j * s.res + i] ? 1.0f : 0.0f; };
+    auto lit = [&](int i, int j) { return ref <= m[(size_t)j * s.res + i] ? 1.0f : 0.0f; };
     return (1.0f - a) * (1.0f - b) * lit(i0, j0) + a * (1.0f - b) * lit(i1, j0) + (1.0f - a) * b * lit(i0, j1) + a * b * lit(i1, j1);
 }
 static inline vec3 textureSize(const sampler2DArrayShadow& s, int) { return vec3((float)s.res, (float)s.res, (float)s.layers); }
@@ -288,6 +290,18 @@ float refglsl_bound_hdr(float v) { return refglsl::boundHDR(v); }
 float refglsl_shadow1(const unsigned short* atlas, int res, int layer, float farPlane, const float* fragPos, const float* lightPos, float lightNormalDot, float minBias) {
     refglsl::samplerCubeArray s; s.data = atlas; s.res = res;
     return refglsl::calculateShadowValue1Sample(s, layer, farPlane, glm::vec3(fragPos[0], fragPos[1], fragPos[2]), glm::vec3(lightPos[0], lightPos[1], lightPos[2]), lightNormalDot, minBias);
+}
+
+float refglsl_sun_shadow(const float* sunDir, const float* cascadeProjViews16x4, const float* cascadePlanes4x3, const float* csm, int csmRes,
+                         const float* pos3, const float* normal3) {
+    using namespace refglsl;
+    infiniteLightDirection = glm::vec3(sunDir[0], sunDir[1], sunDir[2]);
+    for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], cascadeProjViews16x4 + 16 * c, 64);
+    for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(cascadePlanes4x3[4 * c], cascadePlanes4x3[4 * c + 1], cascadePlanes4x3[4 * c + 2], cascadePlanes4x3[4 * c + 3]);
+    infiniteLightShadowMap.data = csm; infiniteLightShadowMap.res = csmRes; infiniteLightShadowMap.layers = 4;
+    const glm::vec3 p(pos3[0], pos3[1], pos3[2]);
+    const glm::vec3 blends(glm::dot(cascadePlanes[0], glm::vec4(p, 1.0f)), glm::dot(cascadePlanes[1], glm::vec4(p, 1.0f)), glm::dot(cascadePlanes[2], glm::vec4(p, 1.0f)));
+    return calculateInfiniteShadowValue(glm::vec4(p, 1.0f), blends, glm::vec3(normal3[0], normal3[1], normal3[2]), false);
 }
 
 // One full-screen pass of vpl_pbr_gi.fs: main() is `performLightingCalculations(textureLod(screen, fsTexCoords, 0).rgb, gl_FragCoord.xy, fsTexCoords)`

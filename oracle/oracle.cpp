@@ -344,6 +344,18 @@ float orc_test_shadow1(const void* atlas, int res, int layer, float farPlane, co
     SgiAtlasEntry e; e.index = 0; e.layer = layer;
     return calculateShadowValue1Sample(atlases, e, res, farPlane, vec3(fragPos[0], fragPos[1], fragPos[2]), vec3(lightPos[0], lightPos[1], lightPos[2]), lightNormalDot, minBias);
 }
+// calculateInfiniteShadowValue(vec4(pos, 1), cascadeBlends(pos), normal, false) as the cull calls it (viscull_vpls.cs:64-68)
+float orc_test_sun_shadow(const SgiFrameParams* fp, const float* csm, int csmRes, const float* pos3, const float* normal3) {
+    mat4 cpv[4]; for (int i = 0; i < 4; ++i) cpv[i] = loadMat(fp->cascadeProjViews[i]);
+    const vec3 p(pos3[0], pos3[1], pos3[2]);
+    vec3 blends;
+    for (int i = 0; i < 3; ++i) {
+        const vec4 plane(fp->cascadePlanes[i][0], fp->cascadePlanes[i][1], fp->cascadePlanes[i][2], fp->cascadePlanes[i][3]);
+        const float b = dot(plane, vec4(p, 1.0f));
+        if (i == 0) blends.x = b; else if (i == 1) blends.y = b; else blends.z = b;
+    }
+    return calculateInfiniteShadowValue(*fp, cpv, csm, csmRes, vec4(p, 1.0f), blends, vec3(normal3[0], normal3[1], normal3[2]));
+}
 float orc_test_attenuation(const float* dir3, float radius) { return vplDiffuseAttenuation(vec3(dir3[0], dir3[1], dir3[2]), radius); }
 
 // a1: viscull_vpls.cs:47-106.  Canonical order = ascending original index, which is one legal

@@ -247,3 +247,31 @@ def test_direct_lighting_shader_text_runs_and_behaves(libs):
     light[0, 0:4] = [0.0, 15.0, 0.0, 1.0]; light[0, 4:8] = [400.0, 400.0, 400.0, 1.0]; light[0, 8] = 40.0; light[0, 9] = 40.0
     withp = reference_glsl_direct_lighting(ref, fp, gb, lights=light, **common)
     assert (withp >= sun1 - 1e-6).all() and float((withp - sun1).sum()) > 0.0
+
+
+def test_sun_shadow_value_of_the_shader_text(libs):
+    """calculateInfiniteShadowValue (pbr.glsl:158-227: cascade choice and blend, 3x3 PCF taps on two cascades) as a VALUE, not only
+    as the cull's visible / hidden decision: random points of the scene, sun direction and a tilted normal."""
+    from tests.parity_util import SceneData
+    orc, ref = libs
+    orc.orc_test_sun_shadow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    orc.orc_test_sun_shadow.restype = C.c_float
+    ref.refglsl_sun_shadow.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    ref.refglsl_sun_shadow.restype = C.c_float
+    rng = np.random.default_rng(9)
+    for wl in ("c1", "c3"):
+        d = SceneData(wl, frames=1)
+        fp, csm = d.fp[0], np.ascontiguousarray(d.csm[0], np.float32)
+        sun = np.ascontiguousarray(list(fp.infiniteLightDirection), np.float32)
+        cpv = np.ascontiguousarray([list(m) for m in fp.cascadeProjViews], np.float32).reshape(-1)
+        planes = np.ascontiguousarray([list(p) for p in fp.cascadePlanes], np.float32).reshape(-1)
+        values = []
+        for k in range(3000):
+            p = np.ascontiguousarray(d.vpl_data[rng.integers(0, d.N), :3] + rng.normal(0, 6, 3), np.float32)
+            n = sun if k % 2 == 0 else np.ascontiguousarray((lambda v: v / np.linalg.norm(v))(rng.normal(0, 1, 3)), np.float32)
+            a = orc.orc_test_sun_shadow(C.addressof(fp), csm.ctypes.data, d.scene.csm_res, p.ctypes.data, n.ctypes.data)
+            b = ref.refglsl_sun_shadow(sun.ctypes.data, cpv.ctypes.data, planes.ctypes.data, csm.ctypes.data, d.scene.csm_res, p.ctypes.data, n.ctypes.data)
+            assert _bits(a) == _bits(b), (wl, k, a, b)
+            values.append(b)
+        values = np.array(values)
+        assert (values == 0).any() and (values == 1).any() and ((values > 0) & (values < 1)).any()      # shadowed, lit and penumbra all occur
