@@ -259,6 +259,34 @@ int  sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers);
  * library was built without GL headers (this image has none). */
 int  sgi_register_gl(SgiHandle h, const uint32_t* gl_names, int32_t count);
 
+/* ---- deferred direct lighting: pbr.fs, the pass whose output is the `screen` plane of this path ----
+ * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_direct.cu). */
+typedef struct SgiPointLight {          /* GpuPointLight / `struct PointLight` (pbr.fs:15-21) */
+    float position[4];
+    float color[4];
+    float radius;
+    float farPlane;
+    float _pad[2];
+} SgiPointLight;
+
+typedef struct SgiDirectParams {
+    int32_t numLights;                  /* nonShadowCasters[numLights]                                  */
+    int32_t numShadowLights;            /* shadowCasters[numShadowLights], shadowIndices[numShadowLights] */
+    int32_t sunEnabled;                 /* INFINITE_LIGHTING_ENABLED                                    */
+    int32_t _pad;
+    const SgiPointLight* nonShadowCasters;   /* device */
+    const SgiPointLight* shadowCasters;      /* device */
+    const SgiAtlasEntry* shadowIndices;      /* device */
+    float   emissionStrength;
+    float   infiniteLightDepthBias, infiniteLightZnear, infiniteLightZfar;      /* pbr.glsl:53-56 */
+    float   pointLightAmbientIntensity;                                         /* pbr.glsl:66, 0.003 */
+    float   _pad2[3];
+    void*   screenOut;                  /* device half4 [rows][W]: boundHDR(colour + emissive * emissionStrength) */
+} SgiDirectParams;
+
+/* pbr.fs over the bound G-buffer, cube shadow atlases and sun shadow map; stream-ordered */
+int  sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp);
+
 /* VPL pre-pass: lights whose sphere touches the view frustum, ordered by distance to the viewer (equal distances keep
  * their input order, as std::multiset insertion does), the nearest 10000 written as the cull's input table.  Stream-ordered;
  * bind countOut as SgiBuffers.vplCountDevice and pass totalNumLights = min(numLights, 10000) to run a frame without

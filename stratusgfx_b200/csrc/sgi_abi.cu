@@ -258,6 +258,22 @@ int sgi_vpl_prepass(SgiHandle h, const SgiPrepassParams* pp) {
     return postLaunch(h, launchPrepass(h->stream, *pp, h->prepassKeys, h->prepassInside));
 }
 
+int sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp) {
+    if (!h || !fp || !dp) return SGI_ERR_INVALID_ARG;
+    if (dp->numLights < 0 || dp->numShadowLights < 0 || !dp->screenOut) return fail(h, SGI_ERR_INVALID_ARG, "sgi_direct_lighting: bad light counts or no output plane");
+    if ((dp->numLights > 0 && !dp->nonShadowCasters) || (dp->numShadowLights > 0 && (!dp->shadowCasters || !dp->shadowIndices)))
+        return fail(h, SGI_ERR_NOT_BOUND, "sgi_direct_lighting: light tables missing");
+    NEED(h, depth); NEED(h, normal); NEED(h, albedo); NEED(h, baseReflectivity); NEED(h, roughnessMetallicAmbient); NEED(h, ssao);
+    if (dp->sunEnabled) NEED(h, infiniteLightShadowMap);
+    if (dp->numShadowLights > 0) NEED(h, shadowCubeMaps[0]);
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    const int n = launchDirectLighting(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
+                                       (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
+                                       (const unsigned short*)h->buf.ssao, (const float*)h->buf.infiniteLightShadowMap, atlasTable(h), *dp, (uint2*)dp->screenOut);
+    return postLaunch(h, n);
+}
+
 int sgi_cull(SgiHandle h, const SgiFrameParams* fp) { return cullImpl(h, fp, false); }
 
 int sgi_color(SgiHandle h, const SgiFrameParams* fp) {

@@ -248,6 +248,10 @@ namespace sgi {
 
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
 bool preloadPrepassKernels(); int launchPrepass(cudaStream_t stream, const SgiPrepassParams& pp, unsigned long long* keys, int* inside);
+bool preloadDirectKernels();
+int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
+                         const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm, const AtlasTable& atlases,
+                         const SgiDirectParams& dp, uint2* out);
 bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels(); bool preloadDenoiseKernels(); bool preloadBandKernels();
 
 // each launcher enqueues its kernels on `stream` and returns the number of launches made

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import (BandParams, Buffers, CreateParams, FrameParams, PeerInfo, PrepassParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+from ._abi import (BandParams, Buffers, CreateParams, DirectParams, FrameParams, PeerInfo, PrepassParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
                    TILE_DIVISOR)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
@@ -47,6 +47,7 @@ def load_library():
     L.sgi_bind_device_buffers.argtypes = [H, C.POINTER(Buffers)]
     L.sgi_register_gl.argtypes = [H, C.c_void_p, C.c_int32]
     L.sgi_vpl_prepass.argtypes = [H, C.POINTER(PrepassParams)]
+    L.sgi_direct_lighting.argtypes = [H, C.POINTER(FrameParams), C.POINTER(DirectParams)]
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
@@ -203,6 +204,33 @@ class VplGiPass:
         pp.orderOut = self.t["prepassOrder"].data_ptr()
         pp.countOut = self.t["vplCountDevice"].data_ptr()
         self._check(self.L.sgi_vpl_prepass(self._h, C.byref(pp)))
+
+    # ---- the pass before this path: deferred direct lighting, pbr.fs (NOT YET VALIDATED ON A GPU, see csrc/k_direct.cu) ----
+    def direct_lighting(self, fp, lights=None, shadow_lights=None, shadow_entries=None, sun=True, emission_strength=0.0,
+                        depth_bias=0.0, z_near=1.0, z_far=1000.0, point_light_ambient=0.003):
+        """pbr.fs over the bound G-buffer -> a half4 [rows, W] plane (kept as self.t["directOut"]): the `screen` input of the GI path.
+        lights / shadow_lights: float32 [n, 12] PointLight records; shadow_entries: int32 [n, 2]."""
+        torch = self.torch
+        dp = DirectParams()
+        keep = []
+        def up(a, dt):
+            if a is None or len(a) == 0:
+                return None, 0
+            t = torch.from_numpy(np.ascontiguousarray(a, dt)).to(self.device); keep.append(t)
+            return t.data_ptr(), int(t.shape[0])
+        dp.nonShadowCasters, dp.numLights = up(lights, np.float32)
+        dp.shadowCasters, dp.numShadowLights = up(shadow_lights, np.float32)
+        dp.shadowIndices, _ = up(shadow_entries, np.int32)
+        dp.sunEnabled = 1 if sun else 0
+        dp.emissionStrength, dp.infiniteLightDepthBias = float(emission_strength), float(depth_bias)
+        dp.infiniteLightZnear, dp.infiniteLightZfar, dp.pointLightAmbientIntensity = float(z_near), float(z_far), float(point_light_ambient)
+        if "directOut" not in self.t:
+            self.t["directOut"] = torch.zeros((self.rows, self.width, 4), dtype=torch.float16, device=self.device)
+        dp.screenOut = self.t["directOut"].data_ptr()
+        torch.cuda.synchronize(self.device)
+        self._check(self.L.sgi_direct_lighting(self._h, C.byref(fp), C.byref(dp)))
+        self.synchronize()
+        return self.t["directOut"]
 
     # ---- the reference's pass interface --------------------------------------------------------------
     def PerformVirtualPointLightCullingStage1(self, fp):

@@ -31,6 +31,10 @@ def test_ctypes_layout_matches_header(tmp_path):
         "SgiBuffers": (_abi.Buffers, ["depth", "prevNormal", "ssao", "lightingOut", "vplData", "atlasEntryByVpl", "shadowCubeMaps",
                                       "diffuseCubeMaps", "infiniteLightShadowMap", "vplCountDevice"]),
         "SgiLightRecord": (_abi.LightRecord, ["position", "radius", "farPlane", "intensity", "atlasIndex", "atlasLayer"]),
+        "SgiPointLight": (_abi.PointLight, ["position", "color", "radius", "farPlane"]),
+        "SgiDirectParams": (_abi.DirectParams, ["numLights", "numShadowLights", "sunEnabled", "nonShadowCasters", "shadowCasters", "shadowIndices",
+                                                "emissionStrength", "infiniteLightDepthBias", "infiniteLightZnear", "infiniteLightZfar",
+                                                "pointLightAmbientIntensity", "screenOut"]),
         "SgiPrepassParams": (_abi.PrepassParams, ["viewPosition", "numLights", "frustumPlanes", "lights", "vplDataOut", "atlasEntryOut",
                                                   "orderOut", "countOut"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),
