@@ -9,7 +9,7 @@
 // STATUS: written at the end of round 1 without a GPU minute left — it compiles for sm_100a, it has NOT run on a GPU.  Its GPU
 // parity test (tests/test_zz_direct_lighting.py, against the reference's own pbr.fs compiled by oracle/make_ref_glsl.py) is opt-in
 // (SGI_RUN_UNVALIDATED=1) until it has passed on a B200; nothing else in the library calls this file.  Its logic is checked on
-// the host: tests/test_direct_kernel_on_host.py compiles this very file with g++ (SGI_HOST_EMULATION, tests/cuda_on_host/) and
+// the host: tests/test_direct_kernel_on_host.py compiles this very file with g++ (tests/cuda_on_host/host_tu.py) and
 // runs it thread by thread — bit-identical to the compiled shader text.
 //
 // First version: one thread per pixel, every operation in the exact IEEE chain of csrc/sgi_math.cuh in the shader's order (only
@@ -202,12 +202,10 @@ directKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 
 }  // namespace
 
-#ifndef SGI_HOST_EMULATION
 bool preloadDirectKernels() {
     cudaFuncAttributes a;
     return cudaFuncGetAttributes(&a, directKernel) == cudaSuccess;
 }
-#endif
 
 int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
                          const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm, const AtlasTable& atlases,
@@ -218,12 +216,7 @@ int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandD
     da.emissionStrength = dp.emissionStrength; da.depthBias = dp.infiniteLightDepthBias; da.zNear = dp.infiniteLightZnear; da.zFar = dp.infiniteLightZfar;
     da.pointLightAmbientIntensity = dp.pointLightAmbientIntensity;
     dim3 block(32, 8), grid((bd.W + 31) / 32, (bd.rows + 7) / 8);
-#ifdef SGI_HOST_EMULATION      // tests/cuda_on_host: the kernel function is called thread by thread by g++-compiled code
-    (void)stream;
-    SGI_HOST_LAUNCH(directKernel, grid, block, fc, bd, depth, normal, albedo, refl, rma, ssao, csm, atlases, da, out);
-#else
     directKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, csm, atlases, da, out);
-#endif
     return 1;
 }
 

@@ -1,12 +1,23 @@
-// cuda_host_shim.h — compile a barrier-free CUDA kernel of this repository with g++ and run it thread by thread on the host.
-// TEST INFRASTRUCTURE for kernels that have not met a GPU yet (csrc/k_direct.cu): it checks the kernel's LOGIC against the
-// reference's compiled shader text before any GPU minute is spent.  Every device intrinsic used by csrc/sgi_math.cuh is given its
-// IEEE host meaning (the translation unit is compiled with -ffp-contract=off, so a * b and a + b are never fused).
+// cuda_host_shim.h — compile a CUDA kernel of this repository with g++ and run it thread by thread on the host.
+// TEST INFRASTRUCTURE (see host_tu.py): it checks a kernel's LOGIC — index arithmetic, exact-arithmetic chains, what is stored
+// where — against the oracle / the reference's compiled shader text without a GPU: for kernels that have not met one yet
+// (csrc/k_direct.cu) and for compile-time variants queued for an A/B (csrc/k_denoise.cu, -DSGI_ATROUS_V2).  Every device
+// intrinsic is given its IEEE host meaning (-ffp-contract=off: a * b + c is never fused behind the code's back); the MUFU
+// approximations become libm calls, so radiance agrees to float rounding, not to the bit.  A thread-by-thread run cannot honour a
+// barrier or a warp collective: reaching one aborts the process instead of computing something else.
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>          // vector types (float4, uint2, dim3 ...) and the host API declarations; no device code
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(...)
 
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -21,6 +32,41 @@ static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4
 static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }                 // CUDA's global integer overloads
+static inline int max(int a, int b) { return a > b ? a : b; }
+
+// the helpers of csrc/ whose body is inline PTX (host_tu.py drops the originals)
+static inline void prefetchL2(const void*) {}
+static inline float lg2Fast(float x) { return std::log2(x); }                 // lg2.approx.ftz.f32
+static inline float ex2Fast(float x) { return std::exp2(x); }                 // ex2.approx.ftz.f32
+static inline unsigned long long pack2(float lo, float hi) {                  // mov.b64 %0, {lo, hi}
+    uint32_t a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4);
+    return (unsigned long long)a | ((unsigned long long)b << 32);
+}
+static inline void unpack2(unsigned long long v, float& lo, float& hi) {
+    const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32);
+    std::memcpy(&lo, &a, 4); std::memcpy(&hi, &b, 4);
+}
+static inline unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {      // fma.rn.f32x2: IEEE fma per lane
+    float a0, a1, b0, b1, c0, c1;
+    unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
+    return pack2(std::fma(a0, b0, c0), std::fma(a1, b1, c1));
+}
+static inline int ldAcquireSys(const int32_t* p) { return *(const volatile int32_t*)p; }
+static inline void stReleaseSys(int32_t* p, int v) { *(volatile int32_t*)p = v; }
+
+// what a thread-by-thread run cannot do
+[[noreturn]] static inline void sgiHostUnsupported(const char* what) {
+    std::fprintf(stderr, "cuda_host_shim: %s reached — this launch is not barrier-free, the host run would compute something else\n", what);
+    std::abort();
+}
+static inline void __syncthreads() { sgiHostUnsupported("__syncthreads()"); }
+static inline int __syncthreads_or(int) { sgiHostUnsupported("__syncthreads_or()"); }
+static inline void __syncwarp() { sgiHostUnsupported("__syncwarp()"); }
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) {}
+static inline long long clock64() { return 0; }
+static inline int atomicAdd(int* p, int v) { int old; _Pragma("omp atomic capture") { old = *p; *p += v; } return old; }
 
 // the per-thread built-ins; the launch emulation below sets them before every call of the kernel function
 static thread_local uint3 threadIdx, blockIdx;

@@ -1,12 +1,6 @@
-// direct_on_host.cpp — csrc/k_direct.cu compiled by g++ (tests/cuda_on_host/cuda_host_shim.h) behind a C entry point.
-#define SGI_HOST_EMULATION
-#define __device__
-#define __global__
-#define __forceinline__ inline
-#define __grid_constant__
-#define __launch_bounds__(...)
+// direct_on_host.cpp — csrc/k_direct.cu executed on the host: includes the translated copy host_tu.py wrote into _build/.
 #include "cuda_host_shim.h"
-#include "../../stratusgfx_b200/csrc/k_direct.cu"
+#include "k_direct.cu"             // tests/cuda_on_host/_build/k_direct.cu (-I _build comes first)
 
 extern "C" int host_direct_lighting(const SgiFrameParams* fp, int W, int H, int cubeRes, int csmRes, const float* depth, const uint32_t* normal,
                                     const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm,

@@ -1,0 +1,144 @@
+"""CUDA on the host — TEST INFRASTRUCTURE, never part of the product.
+
+A kernel of stratusgfx_b200/csrc that reaches no barrier and no warp collective on the inputs of a test can be executed thread
+by thread by ordinary C++: this module makes a host translation unit of it WITHOUT touching the sources.  The files of csrc/ are
+copied into a build directory under tests/cuda_on_host/_build/ (git-ignored) with a handful of lexical rules applied, and g++
+compiles a small wrapper that includes the copy:
+
+  1. `kernel<<<grid, block, smem, stream>>>(args);`         ->  `SGI_HOST_LAUNCH(kernel, grid, block, args);`  (cuda_host_shim.h:
+     one call of the kernel function per thread, CTAs spread over the host's cores by OpenMP)
+  2. the one-line helpers whose body is inline PTX (`lg2.approx`, `ex2.approx`, `prefetch`, `fma.rn.f32x2`, `ld.acquire` ...)
+     ->  dropped; cuda_host_shim.h defines functions of the same names with the IEEE / libm meaning
+  3. `cudaFuncGetAttributes(&a, kernel) == cudaSuccess`      ->  `true`  (the preload helpers have nothing to load)
+  4. `#ifdef __CUDACC__` in sgi_internal.h                   ->  `#if 1`  (the band helpers are compiled; with no neighbour attached
+     they return before their barrier — a barrier that IS reached aborts the process, see the shim)
+
+Everything else — the kernel body, its index arithmetic, its exact-arithmetic chains — is compiled as written, with
+-ffp-contract=off so that `a * b + c` is never fused behind the code's back.
+"""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "stratusgfx_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+HEADERS = ("sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh")
+
+# rule 2: helpers that the shim supplies (name -> only checked for presence, the definitions live in cuda_host_shim.h)
+PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys")
+
+_LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<((?:(?!<<<|>>>).)*)>>>\s*\(", re.S)
+
+
+def _matching(text, start, open_ch, close_ch):
+    """index just past the bracket that closes text[start] (string literals are skipped)"""
+    depth, i, n = 0, start, len(text)
+    while i < n:
+        c = text[i]
+        if c == '"':
+            i += 1
+            while text[i] != '"':
+                i += 2 if text[i] == "\\" else 1
+        elif c == open_ch:
+            depth += 1
+        elif c == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+    raise ValueError("unbalanced " + open_ch)
+
+
+def _split_top_level(s):
+    parts, depth, cur = [], 0, ""
+    for c in s:
+        if c in "([{":
+            depth += 1
+        elif c in ")]}":
+            depth -= 1
+        if c == "," and depth == 0:
+            parts.append(cur.strip()); cur = ""
+        else:
+            cur += c
+    parts.append(cur.strip())
+    return parts
+
+
+def _drop_ptx_helpers(text):
+    dropped = []
+    for name in PTX_HELPERS:
+        m = re.search(r"^[ \t]*(?:SGI_DEV|__device__ __forceinline__)[^\n;{]*\b" + name + r"\s*\(", text, re.M)
+        if not m:
+            continue
+        brace = text.index("{", m.end())
+        end = _matching(text, brace, "{", "}")
+        body = text[brace:end]
+        if "asm" not in body:
+            raise ValueError(f"{name}: expected an inline-PTX body")
+        text = text[:m.start()] + f"// [host emulation] {name}: defined by cuda_host_shim.h\n" + text[end:].lstrip("\n")
+        dropped.append(name)
+    return text, dropped
+
+
+def _rewrite_launches(text):
+    out, pos, count = "", 0, 0
+    while True:
+        m = _LAUNCH.search(text, pos)
+        if not m:
+            return out + text[pos:], count
+        if "//" in text[text.rfind("\n", 0, m.start()) + 1:m.start()]:      # inside a comment
+            out += text[pos:m.end()]; pos = m.end()
+            continue
+        cfg = _split_top_level(m.group(2))
+        if len(cfg) < 2:
+            raise ValueError("launch configuration: " + m.group(0))
+        close = _matching(text, m.end() - 1, "(", ")")
+        args = text[m.end():close - 1]
+        out += text[pos:m.start()] + f"SGI_HOST_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, {args})"
+        pos = close
+        count += 1
+
+
+def translate(text, name):
+    text, dropped = _drop_ptx_helpers(text)
+    text, launches = _rewrite_launches(text)
+    text = re.sub(r"cudaFuncGetAttributes\(&a,\s*[^)]*\)\s*==\s*cudaSuccess", "true", text)
+    if name == "sgi_internal.h":
+        text = text.replace("#ifdef __CUDACC__", "#if 1   // [host emulation] was: #ifdef __CUDACC__")
+    # (the griddepcontrol macros sit under #ifdef SGI_PDL, which a host build never defines)
+    code = "\n".join(l for l in re.sub(r"//[^\n]*", "", text).split("\n") if "griddepcontrol" not in l)
+    if re.search(r"\basm\b", code):
+        raise ValueError(f"{name}: inline PTX outside the known helpers — extend PTX_HELPERS and the shim")
+    return text, dropped, launches
+
+
+def make_build_dir(kernel_file):
+    """Translated copies of `kernel_file` and the csrc headers -> tests/cuda_on_host/_build/; returns the directory."""
+    os.makedirs(BUILD, exist_ok=True)
+    for f in HEADERS + (kernel_file,):
+        src = open(os.path.join(CSRC, f)).read()
+        text, _, _ = translate(src, f)
+        dst = os.path.join(BUILD, f)
+        if not os.path.exists(dst) or open(dst).read() != text:
+            open(dst, "w").write(text)
+    return BUILD
+
+
+def compile_wrapper(wrapper_cpp, kernel_file, out_name, defines=()):
+    """g++ the wrapper (which includes "_build/<kernel_file>") into a shared object; rebuilt when any input is newer."""
+    build = make_build_dir(kernel_file)
+    so = os.path.join(build, out_name)
+    srcs = [os.path.join(HERE, wrapper_cpp), os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + \
+           [os.path.join(CSRC, f) for f in HEADERS + (kernel_file,)]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
+        return so
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w",
+           "-I", build, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include")] + \
+          ["-D" + d for d in defines] + [os.path.join(HERE, wrapper_cpp), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stderr[-4000:])
+    return so

@@ -1,10 +1,9 @@
-"""csrc/k_direct.cu (widening row f3, never run on a GPU yet) compiled by g++ through tests/cuda_on_host/cuda_host_shim.h and executed
+"""csrc/k_direct.cu (widening row f3, never run on a GPU yet) compiled by g++ (tests/cuda_on_host/host_tu.py: a translated copy, the source is untouched) and executed
 thread by thread on the host, against the reference's own pbr.fs compiled by oracle/make_ref_glsl.py.  This checks the kernel's
 logic — light loops, shadow paths by view distance, cascade choice, Burley BRDF, emissive, boundHDR — before any GPU time is spent;
 what it cannot check is device-only behaviour (CUDA's powf / expf, launch geometry on real hardware)."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -15,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.fixture(scope="module")
-def host_kernel(built, tmp_path_factory):
+def host_kernel(built):
     from oracle import oracle_py
     ref = oracle_py.reference_glsl()
     if ref is None:
@@ -23,9 +22,8 @@ def host_kernel(built, tmp_path_factory):
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
-    out = str(tmp_path_factory.mktemp("cuda_on_host") / "libdirect_on_host.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-I" + os.path.join(cuda, "include"),
-                           "-o", out, os.path.join(HERE, "cuda_on_host", "direct_on_host.cpp")])
+    from tests.cuda_on_host.host_tu import compile_wrapper
+    out = compile_wrapper("direct_on_host.cpp", "k_direct.cu", "libdirect_on_host.so")
     L = C.CDLL(out)
     L.host_direct_lighting.argtypes = [C.POINTER(FrameParams)] + [C.c_int] * 4 + [C.c_void_p] * 8 + [C.c_int, C.POINTER(DirectParams), C.c_void_p]
     return L, ref
