@@ -197,14 +197,73 @@ __device__ __forceinline__ int boundaryFirst(int p, int n) {
     return p == 0 ? 0 : (p == 1 ? n - 1 : (p == 2 ? n - 2 : p - 2));
 }
 
+#ifdef SGI_ATROUS_V3
+// -DSGI_ATROUS_V3 (experiment, off by default; results are bit-identical by construction — same taps, same order, same
+// arithmetic): the tap spacing of the reference's passes (2, 4, 8) is a template parameter, and a thread whose (kLat+4) x 5 taps
+// all lie inside the held rows and columns (no CLAMP_TO_EDGE: every thread but those within 2 taps of an edge) addresses them as
+// one row pointer per plane, advanced by a constant stride, plus IMMEDIATE column offsets — instead of a clamp, an index and a
+// 64-bit LEA pair per load (~200 of the kernel's ~2200 instructions per thread).
+template <int S>
+SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
+    const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
+    const uint2* __restrict__ rowS = io.shadowsIn + ((size_t)firstRow * W + x);
+    const size_t stride = (size_t)S * W;
+#ifdef SGI_ATROUS_V2
+    unsigned long long accRG[kLat], accBW[kLat];            // with -DSGI_ATROUS_V2 as well: packed (r, g) and (b, sum of weights)
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) { accRG[k] = pack2(0.0f, 0.0f); accBW[k] = pack2(0.0f, 0.0f); }
+#endif
+    #pragma unroll
+    for (int c = 0; c < kLat + 4; ++c) {
+        #pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const float4 gq = __ldg(rowG + (d - 2) * S);
+            const uint2 rv = __ldg(rowS + (d - 2) * S);
+            const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
+            const float tq = gq.w * kLog2e;
+#ifdef SGI_ATROUS_V2
+            const unsigned long long cRG = pack2(rr, rg), cB1 = pack2(rb, 1.0f);
+#endif
+            #pragma unroll
+            for (int k = 0; k < kLat; ++k) {
+                const int dy = c - 2 - k;
+                if (dy < -2 || dy > 2) continue;
+                float w = 1.0f;
+                if (dy != 0 || d != 2) {
+                    const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
+                    w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
+                }
+#ifdef SGI_ATROUS_V2
+                const unsigned long long ww = pack2(w, w);
+                accRG[k] = fma2(ww, cRG, accRG[k]); accBW[k] = fma2(ww, cB1, accBW[k]);
+#else
+                acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
+                acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
+#endif
+            }
+        }
+        rowG += stride; rowS += stride;
+    }
+#ifdef SGI_ATROUS_V2
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) { unpack2(accRG[k], acc[k][0], acc[k][1]); unpack2(accBW[k], acc[k][2], acc[k][3]); }
+#endif
+}
+template <bool FINAL, int S>                                 // S = 0: the spacing is read from the pass parameters
+#else
 template <bool FINAL>
+#endif
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
     SGI_PDL_WAIT();                                          // (experiment, see sgi_internal.h) the previous pass / the gather is complete from here on
     SGI_PDL_LAUNCH_DEPENDENTS();
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
+#ifdef SGI_ATROUS_V3
+    const int s = S ? S : 1 + io.multiplier;
+#else
     const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
+#endif
     const int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
     const int t = by * kDnY + threadIdx.y;                   // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
@@ -242,6 +301,12 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
         accRG[k] = pack2(0.0f, 0.0f); accBW[k] = pack2(0.0f, 0.0f);
 #endif
     }
+#ifdef SGI_ATROUS_V3
+    const int firstRow = c0 + (m0 - 2) * s + r;              // row of tap line c = 0; the last one is firstRow + (kLat + 3) * s
+    const bool interior = S != 0 && x >= 2 * s && x + 2 * s < W && firstRow >= 0 && firstRow + (kLat + 3) * s < rows;
+    if (interior) atrousTapsInterior<(S ? S : 1)>(io, W, firstRow, x, cen, acc);
+    else {
+#endif
     int txs[5];
     #pragma unroll
     for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
@@ -296,6 +361,9 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     #pragma unroll
     for (int k = 0; k < kLat; ++k) { unpack2(accRG[k], acc[k][0], acc[k][1]); unpack2(accBW[k], acc[k][2], acc[k][3]); }
 #endif
+#ifdef SGI_ATROUS_V3
+    }   // generic (edge) path
+#endif
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
@@ -327,8 +395,19 @@ bool preloadDenoiseKernels() {
     ok = ok && cudaFuncGetAttributes(&a, prepareGuideKernel) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<false>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<true>) == cudaSuccess;
+#ifdef SGI_ATROUS_V3
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 0>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 0>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 2>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 2>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 4>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 4>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 8>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 8>) == cudaSuccess;
+#else
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true>) == cudaSuccess;
+#endif
     return ok;
 }
 
@@ -363,8 +442,18 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
             if (io.links.producers == 0) io.links.doneCounter = nullptr;
             else if (signalled) *signalled = true;
         }
+#ifdef SGI_ATROUS_V3
+#define SGI_ATROUS_LAUNCH(S_)                                                                             \
+        do {                                                                                              \
+            void (*kf)(const FrameConsts, BandDims, const DenoiseIO) = final_ ? atrousKernel<true, S_> : atrousKernel<false, S_>; \
+            SGI_LAUNCH_CHAINED(kf, grid, block, 0, stream, fc, bd, io);                                   \
+        } while (0)
+        if (s == 2) SGI_ATROUS_LAUNCH(2); else if (s == 4) SGI_ATROUS_LAUNCH(4); else if (s == 8) SGI_ATROUS_LAUNCH(8); else SGI_ATROUS_LAUNCH(0);
+#undef SGI_ATROUS_LAUNCH
+#else
         if (final_) SGI_LAUNCH_CHAINED(atrousKernel<true>, grid, block, 0, stream, fc, bd, io);
         else SGI_LAUNCH_CHAINED(atrousKernel<false>, grid, block, 0, stream, fc, bd, io);
+#endif
     }
     return 1;
 }

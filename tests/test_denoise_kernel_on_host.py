@@ -63,14 +63,22 @@ def test_denoiser_kernels_on_the_host_match_the_oracle(host_denoiser, yaw):
         assert len(np.unique(orc[1]["history"].view(np.uint16))) > 1          # some pixels were reset, some accumulated
 
 
-def test_atrous_v2_variant_is_bit_identical_to_the_default_build(host_denoiser):
-    """-DSGI_ATROUS_V2 only re-associates nothing: same taps, same order, IEEE fma per lane — every output byte must agree."""
+@pytest.mark.parametrize("workload,macro,iters", [("tiny", "SGI_ATROUS_V2", 4), ("tiny", "SGI_ATROUS_V3", 4), ("tiny", "SGI_ATROUS_V3", 5),
+                                                  ("c1", "SGI_ATROUS_V3", 4), ("c1", "SGI_ATROUS_V2+SGI_ATROUS_V3", 4)])
+def test_queued_atrous_variants_are_bit_identical_to_the_default_build(host_denoiser, workload, macro, iters):
+    """The compile-time variants queued for a GPU A/B change no arithmetic — V2: 32-bit tap indices and IEEE fma per lane of a
+    packed pair; V3: spacing as a template parameter (2, 4, 8; 16 in the 5-pass run falls back to the generic kernel) and
+    pointer + immediate addressing for threads whose taps need no clamp; both together — so every output byte must agree with the
+    default."""
     from tests.parity_util import SceneData, run_oracle
-    L2 = _load(("SGI_ATROUS_V2",), "libdenoise_on_host_v2.so")
-    d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.5)
-    orc = run_oracle(d)
-    for f in range(2):
-        a = _run(host_denoiser, d, orc, f, d.scene.denoise_iters)
-        b = _run(L2, d, orc, f, d.scene.denoise_iters)
+    macros = tuple(macro.split("+"))
+    L2 = _load(macros, "libdenoise_on_host_" + "".join(m[-2:].lower() for m in macros) + ".so")
+    frames = 2 if workload == "tiny" else 1
+    d = SceneData(workload, frames=frames, yaw_deg_per_frame=1.5)
+    orc = run_oracle(d, keep_passes=False)
+    for f in range(frames):
+        a = _run(host_denoiser, d, orc, f, iters)
+        b = _run(L2, d, orc, f, iters)
         for x, y in zip(a, b):
             assert np.array_equal(x.view(np.uint16), y.view(np.uint16))
+        assert np.any(a[0][iters - 2].view(np.uint16) != 0)

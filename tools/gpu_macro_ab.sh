@@ -1,8 +1,9 @@
 #!/bin/bash
 # A/B of a compile-time experiment (-DSGI_PDL: programmatic dependent launch of the gather -> a-trous chain, csrc/sgi_internal.h;
-# -DSGI_ATROUS_V2: 32-bit tap indices + packed FFMA2 accumulation, csrc/k_denoise.cu): the default build, then the build with
+# -DSGI_ATROUS_V2: 32-bit tap indices + packed FFMA2 accumulation, -DSGI_ATROUS_V3: templated spacing + pointer/immediate
+# addressing of clamp-free threads, both in csrc/k_denoise.cu and combinable): the default build, then the build with
 # the given flags (compiled on the GPU box), each through the parity suite, the bench and the band probe; the default build is
-# restored at the end.   Usage: bash tools/gpu_macro_ab.sh <tag> "<nvcc flags>"     e.g.  ... r02_pdl "-DSGI_PDL"
+# restored at the end.   Usage: bash tools/gpu_macro_ab.sh <tag> "<nvcc flags>"     e.g.  ... r02_pdl "-DSGI_PDL"   |   ... r02_atrous "-DSGI_ATROUS_V2 -DSGI_ATROUS_V3"
 tag=${1:-macro}; flags=${2:--DSGI_PDL}; out=gpurun_out/$tag; mkdir -p $out
 run() {   # $1 = label
   timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_$1.log 2>&1; echo "$1 pytest exit $?"; tail -2 $out/pytest_$1.log
