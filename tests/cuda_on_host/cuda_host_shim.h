@@ -55,25 +55,38 @@ static inline unsigned long long fma2(unsigned long long a, unsigned long long b
 static inline int ldAcquireSys(const int32_t* p) { return *(const volatile int32_t*)p; }
 static inline void stReleaseSys(int32_t* p, int v) { *(volatile int32_t*)p = v; }
 
-// what a thread-by-thread run cannot do
+// the per-thread built-ins; the launch emulation below sets them before every call of the kernel function
+static thread_local uint3 threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned) {}
+static inline long long clock64() { return 0; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <typename T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
+template <typename T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
+
+// the host API calls a launch function of csrc/ makes around its kernels
+#define cudaMemsetAsync(p, v, n, stream) (std::memset((p), (v), (n)), cudaSuccess)
+#define cudaFuncSetAttribute(...) cudaSuccess
+#define cudaGetDevice(p) cudaErrorNoDevice
+#define cudaDeviceGetAttribute(...) cudaErrorNoDevice
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(...) cudaErrorNoDevice
+
+#ifndef SGI_HOST_LOCKSTEP
+// ---- mode 1 (default): one call of the kernel function per thread, CTAs spread over the host's cores.  A thread-by-thread run
+// cannot honour a barrier or a warp collective: reaching one aborts.
 [[noreturn]] static inline void sgiHostUnsupported(const char* what) {
     std::fprintf(stderr, "cuda_host_shim: %s reached — this launch is not barrier-free, the host run would compute something else\n", what);
     std::abort();
 }
 static inline void __syncthreads() { sgiHostUnsupported("__syncthreads()"); }
 static inline int __syncthreads_or(int) { sgiHostUnsupported("__syncthreads_or()"); }
-static inline void __syncwarp() { sgiHostUnsupported("__syncwarp()"); }
-static inline void __threadfence_system() {}
-static inline void __nanosleep(unsigned) {}
-static inline long long clock64() { return 0; }
-static inline int atomicAdd(int* p, int v) { int old; _Pragma("omp atomic capture") { old = *p; *p += v; } return old; }
+static inline void __syncwarp(unsigned = 0xffffffffu) { sgiHostUnsupported("__syncwarp()"); }
 
-// the per-thread built-ins; the launch emulation below sets them before every call of the kernel function
-static thread_local uint3 threadIdx, blockIdx;
-static thread_local dim3 blockDim, gridDim;
-
-// kernel<<<grid, block, smem, stream>>>(args...)  ->  one call per thread, blocks spread over the host's cores
-#define SGI_HOST_LAUNCH(kernel, grid, block, ...)                                                           \
+#define SGI_HOST_LAUNCH(kernel, grid, block, smem, ...)                                                     \
     do {                                                                                                    \
         const dim3 g_ = (grid), b_ = (block);                                                               \
         _Pragma("omp parallel for collapse(2) schedule(dynamic, 1)")                                        \
@@ -87,3 +100,117 @@ static thread_local dim3 blockDim, gridDim;
                     }                                                                                       \
             }                                                                                               \
     } while (0)
+
+#else
+// ---- mode 2 (-DSGI_HOST_LOCKSTEP): CTAs one after the other, every CUDA thread of the CTA an OS thread.  __syncthreads is a
+// barrier over the CTA's live threads, a warp collective a barrier over the live lanes of its mask with the operands exchanged
+// through a per-warp slot array; __shared__ variables are function-local statics (one CTA runs at a time), dynamic shared memory
+// is a per-CTA allocation.  A thread that returns from the kernel leaves the barriers it would have taken part in, as on a GPU.
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#define __shared__ static
+#define __noinline__
+
+namespace sgihost {
+struct FlexBarrier {                  // the expected count is re-evaluated when a participant leaves
+    std::mutex m; std::condition_variable cv; int arrived = 0; unsigned gen = 0;
+    template <class F> void wait(F expected) {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned g = gen;
+        if (++arrived >= expected()) { arrived = 0; ++gen; cv.notify_all(); }
+        else cv.wait(l, [&] { return gen != g; });
+    }
+    template <class F> void left(F expected) {
+        std::lock_guard<std::mutex> l(m);
+        if (arrived > 0 && arrived >= expected()) { arrived = 0; ++gen; cv.notify_all(); }
+    }
+};
+struct Warp { FlexBarrier bar; unsigned long long slot[32]; std::atomic<unsigned> exited{0}; unsigned present = 0; };
+struct Cta {
+    FlexBarrier bar; std::atomic<int> live{0}; std::atomic<int> orAcc[3]; std::vector<Warp> warps; void* dynSmem = nullptr;
+    explicit Cta(int n) : warps((n + 31) / 32) { live = n; for (auto& a : orAcc) a = 0; for (int t = 0; t < n; ++t) warps[t / 32].present |= 1u << (t % 32); }
+};
+static Cta* cta = nullptr;
+static thread_local int lane = 0, warpId = 0, orPhase = 0;
+static inline Warp& warp() { return cta->warps[warpId]; }
+static inline int liveLanes(Warp& w, unsigned mask) { return __builtin_popcount(mask & w.present & ~w.exited.load()); }
+template <typename T> static inline unsigned long long bits(T v) { unsigned long long u = 0; std::memcpy(&u, &v, sizeof(T)); return u; }
+template <typename T> static inline T from(unsigned long long u) { T v; std::memcpy(&v, &u, sizeof(T)); return v; }
+// every live lane of `mask` deposits a value, then reads the slot of `src(lane)`
+template <typename T, class F> static inline T exchange(unsigned mask, T v, F src) {
+    Warp& w = warp();
+    w.slot[lane] = bits(v);
+    w.bar.wait([&] { return liveLanes(w, mask); });
+    const int sl = src(lane);
+    const T r = ((mask >> sl) & 1u) ? from<T>(w.slot[sl]) : v;
+    w.bar.wait([&] { return liveLanes(w, mask); });
+    return r;
+}
+static inline void* dynSmem() { return cta->dynSmem; }
+
+template <class Body> static void runGrid(dim3 g, dim3 b, size_t smem, Body body) {
+    const int n = (int)(b.x * b.y * b.z);
+    for (unsigned bz = 0; bz < g.z; ++bz) for (unsigned by = 0; by < g.y; ++by) for (unsigned bx = 0; bx < g.x; ++bx) {
+        Cta c(n);
+        std::vector<unsigned long long> mem((smem + 15) / 8 + 2);
+        c.dynSmem = (void*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15);
+        cta = &c;
+        std::vector<std::thread> th;
+        th.reserve(n);
+        for (int t = 0; t < n; ++t) th.emplace_back([&, t] {
+            gridDim = g; blockDim = b; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            threadIdx.x = t % b.x; threadIdx.y = (t / b.x) % b.y; threadIdx.z = t / (b.x * b.y);
+            lane = t % 32; warpId = t / 32; orPhase = 0;
+            body();
+            Warp& w = c.warps[warpId];
+            w.exited.fetch_or(1u << lane);
+            w.bar.left([&] { return liveLanes(w, 0xffffffffu); });     // (a waiting partial-mask collective re-checks on its own arrival)
+            c.live.fetch_sub(1);
+            c.bar.left([&] { return c.live.load(); });
+        });
+        for (auto& x : th) x.join();
+        cta = nullptr;
+    }
+}
+}  // namespace sgihost
+
+static inline void __syncthreads() { sgihost::Cta& c = *sgihost::cta; c.bar.wait([&] { return c.live.load(); }); }
+static inline int __syncthreads_or(int p) {
+    sgihost::Cta& c = *sgihost::cta;
+    const int k = sgihost::orPhase++ % 3;
+    if (p) c.orAcc[k].fetch_or(1);
+    c.orAcc[(k + 1) % 3].store(0);
+    c.bar.wait([&] { return c.live.load(); });
+    return c.orAcc[k].load();
+}
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { sgihost::Warp& w = sgihost::warp(); w.bar.wait([&] { return sgihost::liveLanes(w, mask); }); }
+template <typename T> static inline T __shfl_sync(unsigned mask, T v, int srcLane, int width = 32) {
+    return sgihost::exchange(mask, v, [=](int l) { return (l & ~(width - 1)) | (srcLane & (width - 1)); });
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int laneMask, int width = 32) {
+    return sgihost::exchange(mask, v, [=](int l) { const int s = l ^ laneMask; return (s & ~(width - 1)) == (l & ~(width - 1)) ? s : l; });
+}
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    return sgihost::exchange(mask, v, [=](int l) { const int s = l - (int)delta; return s >= (l & ~(width - 1)) ? s : l; });
+}
+template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    return sgihost::exchange(mask, v, [=](int l) { const int s = l + (int)delta; return s <= (l | (width - 1)) ? s : l; });
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    sgihost::Warp& w = sgihost::warp();
+    w.slot[sgihost::lane] = pred ? 1ull : 0ull;
+    w.bar.wait([&] { return sgihost::liveLanes(w, mask); });
+    unsigned r = 0;
+    const unsigned in = mask & w.present & ~w.exited.load();
+    for (int l = 0; l < 32; ++l) if (((in >> l) & 1u) && w.slot[l]) r |= 1u << l;
+    w.bar.wait([&] { return sgihost::liveLanes(w, mask); });
+    return r;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
+
+#define SGI_HOST_LAUNCH(kernel, grid, block, smem, ...) sgihost::runGrid((grid), (block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#endif

@@ -5,13 +5,15 @@ by thread by ordinary C++: this module makes a host translation unit of it WITHO
 copied into a build directory under tests/cuda_on_host/_build/ (git-ignored) with a handful of lexical rules applied, and g++
 compiles a small wrapper that includes the copy:
 
-  1. `kernel<<<grid, block, smem, stream>>>(args);`         ->  `SGI_HOST_LAUNCH(kernel, grid, block, args);`  (cuda_host_shim.h:
-     one call of the kernel function per thread, CTAs spread over the host's cores by OpenMP)
+  1. `kernel<<<grid, block, smem, stream>>>(args);`         ->  `SGI_HOST_LAUNCH(kernel, grid, block, smem, args);`  (cuda_host_shim.h:
+     one call of the kernel function per thread, CTAs spread over the host's cores by OpenMP; or, with -DSGI_HOST_LOCKSTEP, one
+     OS thread per CUDA thread of a CTA with working barriers, shuffles and votes)
   2. the one-line helpers whose body is inline PTX (`lg2.approx`, `ex2.approx`, `prefetch`, `fma.rn.f32x2`, `ld.acquire` ...)
      ->  dropped; cuda_host_shim.h defines functions of the same names with the IEEE / libm meaning
   3. `cudaFuncGetAttributes(&a, kernel) == cudaSuccess`      ->  `true`  (the preload helpers have nothing to load)
   4. `#ifdef __CUDACC__` in sgi_internal.h                   ->  `#if 1`  (the band helpers are compiled; with no neighbour attached
-     they return before their barrier — a barrier that IS reached aborts the process, see the shim)
+     they return before their barrier — in the thread-by-thread mode a barrier that IS reached aborts the process, see the shim)
+  5. `extern __shared__ T name[];`                            ->  `T* name = (T*)sgihost::dynSmem();`
 
 Everything else — the kernel body, its index arithmetic, its exact-arithmetic chains — is compiled as written, with
 -ffp-contract=off so that `a * b + c` is never fused behind the code's back.
@@ -96,7 +98,8 @@ def _rewrite_launches(text):
             raise ValueError("launch configuration: " + m.group(0))
         close = _matching(text, m.end() - 1, "(", ")")
         args = text[m.end():close - 1]
-        out += text[pos:m.start()] + f"SGI_HOST_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, {args})"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out += text[pos:m.start()] + f"SGI_HOST_LAUNCH({m.group(1)}, {cfg[0]}, {cfg[1]}, {smem}, {args})"
         pos = close
         count += 1
 
@@ -105,6 +108,8 @@ def translate(text, name):
     text, dropped = _drop_ptx_helpers(text)
     text, launches = _rewrite_launches(text)
     text = re.sub(r"cudaFuncGetAttributes\(&a,\s*[^)]*\)\s*==\s*cudaSuccess", "true", text)
+    # rule 5: dynamic shared memory is a per-CTA allocation of the lockstep runtime
+    text = re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)sgihost::dynSmem();", text)
     if name == "sgi_internal.h":
         text = text.replace("#ifdef __CUDACC__", "#if 1   // [host emulation] was: #ifdef __CUDACC__")
     # (the griddepcontrol macros sit under #ifdef SGI_PDL, which a host build never defines)
@@ -114,10 +119,12 @@ def translate(text, name):
     return text, dropped, launches
 
 
-def make_build_dir(kernel_file):
-    """Translated copies of `kernel_file` and the csrc headers -> tests/cuda_on_host/_build/; returns the directory."""
+def make_build_dir(kernel_files):
+    """Translated copies of the kernel files and the csrc headers -> tests/cuda_on_host/_build/; returns the directory."""
+    if isinstance(kernel_files, str):
+        kernel_files = (kernel_files,)
     os.makedirs(BUILD, exist_ok=True)
-    for f in HEADERS + (kernel_file,):
+    for f in HEADERS + tuple(kernel_files):
         src = open(os.path.join(CSRC, f)).read()
         text, _, _ = translate(src, f)
         dst = os.path.join(BUILD, f)
@@ -126,19 +133,23 @@ def make_build_dir(kernel_file):
     return BUILD
 
 
-def compile_wrapper(wrapper_cpp, kernel_file, out_name, defines=()):
-    """g++ the wrapper (which includes "_build/<kernel_file>") into a shared object; rebuilt when any input is newer."""
-    build = make_build_dir(kernel_file)
+def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
+    """g++ the wrapper(s) (each includes one "_build/<kernel file>") into one shared object; rebuilt when any input is newer."""
+    if isinstance(wrapper_cpps, str):
+        wrapper_cpps = (wrapper_cpps,)
+    if isinstance(kernel_files, str):
+        kernel_files = (kernel_files,)
+    build = make_build_dir(kernel_files)
     so = os.path.join(build, out_name)
-    srcs = [os.path.join(HERE, wrapper_cpp), os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + \
-           [os.path.join(CSRC, f) for f in HEADERS + (kernel_file,)]
+    srcs = [os.path.join(HERE, w) for w in wrapper_cpps] + [os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + \
+           [os.path.join(CSRC, f) for f in HEADERS + tuple(kernel_files)]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-w",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-pthread", "-ffp-contract=off", "-w",
            "-I", build, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include")] + \
-          ["-D" + d for d in defines] + [os.path.join(HERE, wrapper_cpp), "-o", so]
+          ["-D" + d for d in defines] + [os.path.join(HERE, w) for w in wrapper_cpps] + ["-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + r.stderr[-4000:])
+        raise RuntimeError("g++ failed:\n" + r.stderr[-6000:])
     return so
