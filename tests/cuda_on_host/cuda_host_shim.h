@@ -32,6 +32,7 @@ static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4
 static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+#define __expf(x) std::exp((float)(x))                                          // (glibc declares, but does not export, a __expf)
 static inline int min(int a, int b) { return a < b ? a : b; }                 // CUDA's global integer overloads
 static inline int max(int a, int b) { return a > b ? a : b; }
 
@@ -39,6 +40,8 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline void prefetchL2(const void*) {}
 static inline float lg2Fast(float x) { return std::log2(x); }                 // lg2.approx.ftz.f32
 static inline float ex2Fast(float x) { return std::exp2(x); }                 // ex2.approx.ftz.f32
+static inline float sqrtApprox(float x) { return std::sqrt(x); }              // sqrt.approx.ftz.f32 (k_tiles.cu; estimate tier only)
+static inline float sqrtFast(float x) { return std::sqrt(x); }                // sqrt.approx.ftz.f32 (k_gather.cu; radiance tier)
 static inline unsigned long long pack2(float lo, float hi) {                  // mov.b64 %0, {lo, hi}
     uint32_t a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4);
     return (unsigned long long)a | ((unsigned long long)b << 32);

@@ -72,3 +72,89 @@ def test_prepass_frustum_boundary_cases_in_lockstep(host_prepass):
     assert sorted(order.tolist()) == [0, 2, 3, 4]
     _, _, got = _run_prepass(host_prepass, rec, [50, 50, 50], planes)
     assert np.array_equal(got, order)
+
+
+# ---- a1 + a2: visibility cull (ordered compaction by the last CTA) and colouring ------------------------------------------
+@pytest.fixture(scope="module")
+def host_frame_lib(built):
+    """k_vpl.cu, k_tiles.cu and k_gather.cu as three translation units of one library (as in csrc/: each has its own anonymous
+    namespace; fillFrameConsts of k_vpl.cu serves the others)."""
+    L = _lib("libframe_on_host.so", ("vpl_on_host.cpp", "tiles_on_host.cpp", "gather_on_host.cpp"), ("k_vpl.cu", "k_tiles.cu", "k_gather.cu"))
+    L.host_cull.argtypes = [C.POINTER(FrameParams)] + [C.c_int] * 4 + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p]
+    L.host_color.argtypes = [C.POINTER(FrameParams)] + [C.c_int] * 4 + [C.c_void_p] * 5 + [C.c_int]
+    L.host_tile_lists.argtypes = [C.POINTER(FrameParams), C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.host_gather.argtypes = [C.POINTER(FrameParams)] + [C.c_int] * 4 + [C.c_void_p] * 10 + [C.c_int] + [C.c_void_p] * 3
+    return L
+
+
+def _cull_color(L, d, f, fused):
+    from oracle.oracle_py import MAX_TOTAL_VPLS_PER_FRAME, _atlas_ptrs
+    s, fp = d.scene, d.fp[f]
+    n = fp.totalNumLights
+    updated = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 16), np.float32)
+    visible = np.zeros(n + 1, np.int32)
+    entries = np.zeros((MAX_TOTAL_VPLS_PER_FRAME, 2), np.int32)
+    sh, df = _atlas_ptrs(d.shadow_atlas), _atlas_ptrs(d.diffuse_atlas)
+    A = d.shadow_atlas.shape[0]
+    vd, at, csm = np.ascontiguousarray(d.vpl_data), np.ascontiguousarray(d.atlas_by_vpl), np.ascontiguousarray(d.csm[f])
+    L.host_cull(C.byref(fp), d.W, d.H, s.cube_res, s.csm_res, vd.ctypes.data, at.ctypes.data, csm.ctypes.data, updated.ctypes.data,
+                visible.ctypes.data, entries.ctypes.data, C.addressof(sh), C.addressof(df), A, 1 if fused else 0, None)
+    if not fused:
+        L.host_color(C.byref(fp), d.W, d.H, s.cube_res, s.csm_res, updated.ctypes.data, visible.ctypes.data, entries.ctypes.data,
+                     C.addressof(sh), C.addressof(df), A)
+    return updated, visible, entries
+
+
+@pytest.mark.parametrize("workload,fused", [("tiny", False), ("tiny", True), ("c1", True)])
+def test_cull_and_colour_kernels_in_lockstep_equal_the_oracle(host_frame_lib, workload, fused):
+    from tests.parity_util import SceneData, run_oracle
+    d = SceneData(workload, frames=1)
+    orc = run_oracle(d, keep_passes=False)[0]
+    updated, visible, entries = _cull_color(host_frame_lib, d, 0, fused)
+    V = int(orc["visible"][0])
+    assert V > 0 and int(visible[0]) == V and np.array_equal(visible[:V + 1], orc["visible"][:V + 1])
+    assert np.array_equal(entries[:V], orc["entries"][:V])
+    assert np.array_equal(updated[:V].view(np.uint32), orc["updated"][:V].view(np.uint32))
+
+
+# ---- a3 + a4: per-tile averages and the per-tile VPL lists (persistent stage 2) ----------------------------------------------
+@pytest.mark.parametrize("workload", ["tiny", "c1"])
+def test_tile_list_kernels_in_lockstep_equal_the_oracle(host_frame_lib, workload):
+    from tests.parity_util import SceneData, run_oracle
+    d = SceneData(workload, frames=1)
+    orc = run_oracle(d, keep_passes=False)[0]
+    tiles = (d.W // 5) * (d.H // 5)
+    stage1, stage2 = np.zeros((tiles, 8), np.float32), np.zeros((tiles, 13), np.int32)
+    gb = d.gb[0]
+    depth, normal = np.ascontiguousarray(gb.depth), np.ascontiguousarray(gb.normal)
+    updated, visible = np.ascontiguousarray(orc["updated"]), np.ascontiguousarray(orc["visible"])
+    host_frame_lib.host_tile_lists(C.byref(d.fp[0]), d.W, d.H, depth.ctypes.data, normal.ctypes.data, updated.ctypes.data, visible.ctypes.data,
+                                   stage1.ctypes.data, stage2.ctypes.data)
+    assert np.array_equal(stage1.view(np.uint32), orc["stage1"].view(np.uint32))
+    cnt = orc["stage2"][:, 0]
+    assert cnt.max() > 0 and np.array_equal(stage2[:, 0], cnt)
+    mask = np.arange(12)[None, :] < cnt[:, None]
+    assert np.array_equal(stage2[:, 1:][mask], orc["stage2"][:, 1:][mask])
+
+
+# ---- a5: the persistent stochastic gather with the fused denoise pass 0 -------------------------------------------------------
+@pytest.mark.parametrize("workload", ["tiny", "c1"])
+def test_gather_kernel_in_lockstep_matches_the_oracle(host_frame_lib, workload):
+    """Which VPLs a pixel draws, which cube texel it reads and the lit/shadowed verdict are exact decisions, so a wrong one shows
+    as a pixel far outside the radiance bar; the shading arithmetic itself is FMA / approximation tier (libm here)."""
+    from oracle.oracle_py import _atlas_ptrs
+    from tests.parity_util import SceneData, compare_radiance, run_oracle
+    d = SceneData(workload, frames=1)
+    orc = run_oracle(d, keep_passes=True)[0]
+    s, gb = d.scene, d.gb[0]
+    color, reservoir, merged = (np.zeros((d.H, d.W, 4), np.float16) for _ in range(3))
+    planes = [np.ascontiguousarray(a) for a in (gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao,
+                                                orc["updated"], orc["visible"], orc["entries"])]
+    sh = _atlas_ptrs(d.shadow_atlas)
+    host_frame_lib.host_gather(C.byref(d.fp[0]), d.W, d.H, s.cube_res, s.csm_res, *[a.ctypes.data for a in planes], C.addressof(sh),
+                               d.shadow_atlas.shape[0], color.ctypes.data, reservoir.ctypes.data, merged.ctypes.data)
+    for got, want, ch in ((color, orc["gi_color"], 3), (reservoir, orc["gi_reservoir"], 4), (merged, orc["pass_reservoirs"][0], 3)):
+        r = compare_radiance(got, want, ch)
+        assert r["ok"] and r["bit_exact"] > 0.99, r
+    # the sample count of every pixel (reservoir alpha: the sum of re-weighting factors, a chain of decisions) must agree exactly
+    assert np.array_equal(reservoir[..., 3].view(np.uint16), orc["gi_reservoir"][..., 3].view(np.uint16))
