@@ -59,8 +59,10 @@ static inline int ldAcquireSys(const int32_t* p) { return *(const volatile int32
 static inline void stReleaseSys(int32_t* p, int v) { *(volatile int32_t*)p = v; }
 
 // the per-thread built-ins; the launch emulation below sets them before every call of the kernel function
-static thread_local uint3 threadIdx, blockIdx;
-static thread_local dim3 blockDim, gridDim;
+// (inline variables: ONE instance per shared object even when it is built from several translation units — the inline device
+// functions of sgi_internal.h are merged across them by the linker and must see the same runtime state as the kernels)
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
 
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
@@ -77,6 +79,7 @@ static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add
 #define cudaGetDevice(p) cudaErrorNoDevice
 #define cudaDeviceGetAttribute(...) cudaErrorNoDevice
 #define cudaOccupancyMaxActiveBlocksPerMultiprocessor(...) cudaErrorNoDevice
+#define cudaIpcCloseMemHandle(p) cudaSuccess
 
 #ifndef SGI_HOST_LOCKSTEP
 // ---- mode 1 (default): one call of the kernel function per thread, CTAs spread over the host's cores.  A thread-by-thread run
@@ -136,8 +139,8 @@ struct Cta {
     FlexBarrier bar; std::atomic<int> live{0}; std::atomic<int> orAcc[3]; std::vector<Warp> warps; void* dynSmem = nullptr;
     explicit Cta(int n) : warps((n + 31) / 32) { live = n; for (auto& a : orAcc) a = 0; for (int t = 0; t < n; ++t) warps[t / 32].present |= 1u << (t % 32); }
 };
-static Cta* cta = nullptr;
-static thread_local int lane = 0, warpId = 0, orPhase = 0;
+inline Cta* cta = nullptr;
+inline thread_local int lane = 0, warpId = 0, orPhase = 0;
 static inline Warp& warp() { return cta->warps[warpId]; }
 static inline int liveLanes(Warp& w, unsigned mask) { return __builtin_popcount(mask & w.present & ~w.exited.load()); }
 template <typename T> static inline unsigned long long bits(T v) { unsigned long long u = 0; std::memcpy(&u, &v, sizeof(T)); return u; }

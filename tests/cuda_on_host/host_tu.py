@@ -14,6 +14,7 @@ compiles a small wrapper that includes the copy:
   4. `#ifdef __CUDACC__` in sgi_internal.h                   ->  `#if 1`  (the band helpers are compiled; with no neighbour attached
      they return before their barrier — in the thread-by-thread mode a barrier that IS reached aborts the process, see the shim)
   5. `extern __shared__ T name[];`                            ->  `T* name = (T*)sgihost::dynSmem();`
+  6. sgi_band.cu                                             ->  its `namespace sgi` half only (the extern "C" half is CUDA IPC plumbing)
 
 Everything else — the kernel body, its index arithmetic, its exact-arithmetic chains — is compiled as written, with
 -ffp-contract=off so that `a * b + c` is never fused behind the code's back.
@@ -110,6 +111,10 @@ def translate(text, name):
     text = re.sub(r"cudaFuncGetAttributes\(&a,\s*[^)]*\)\s*==\s*cudaSuccess", "true", text)
     # rule 5: dynamic shared memory is a per-CTA allocation of the lockstep runtime
     text = re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)sgihost::dynSmem();", text)
+    if name == "sgi_band.cu":
+        # rule 6: the extern "C" half of sgi_band.cu is CUDA IPC plumbing; the host run keeps the namespace sgi half (bandLinks,
+        # armInKernelSignal, signalNeighbours, the flag kernels)
+        text = text[:text.index("using namespace sgi;")]
     if name == "sgi_internal.h":
         text = text.replace("#ifdef __CUDACC__", "#if 1   // [host emulation] was: #ifdef __CUDACC__")
     # (the griddepcontrol macros sit under #ifdef SGI_PDL, which a host build never defines)

@@ -1,0 +1,129 @@
+"""Row bands with peer-to-peer halos and IN-KERNEL waits / signals, with MIDDLE bands, without a GPU.
+
+Every band is a process (as on the GPU box); the slabs neighbours store into are POSIX shared memory instead of CUDA IPC mappings;
+the band's gather and denoise kernels are the shipped ones, compiled for the host in lockstep mode (tests/cuda_on_host/), and the
+links / epochs / signals come from the translated csrc/sgi_band.cu.  Two frames (the second one starts with the wait for the
+neighbours' frame-complete flag and reads the history rows they pushed) on 3 and 4 bands must give, byte for byte, what ONE handle
+computes for the whole frame — a pass that read a halo row before its neighbour stored it, or a producer count that is off by one
+(dead-lock: the test times out), cannot pass.  The 2-GPU runs on hardware cover band 0 and band N-1 only; this covers the bands
+in between, with the in-kernel signal and with the host-launched signal kernel."""
+import ctypes as C
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+W, H, FRAMES = 160, 240, 2
+WORKLOAD = dict(workload="tiny", frames=FRAMES, yaw_deg_per_frame=1.5, height=H)
+
+
+class HostPeer(C.Structure):
+    _fields_ = [("present", C.c_int32), ("y_offset", C.c_int32), ("rows", C.c_int32), ("compute_y0", C.c_int32), ("compute_rows", C.c_int32),
+                ("rank", C.c_int32), ("base", C.c_void_p)]
+
+
+def _load():
+    from stratusgfx_b200._abi import FrameParams
+    from tests.cuda_on_host.host_tu import compile_wrapper
+    L = C.CDLL(compile_wrapper(("vpl_on_host.cpp", "gather_on_host.cpp", "denoise_lockstep_on_host.cpp", "bands_on_host.cpp"),
+                               ("k_vpl.cu", "k_gather.cu", "k_denoise.cu", "sgi_band.cu"), "libbands_on_host.so"))
+    L.host_band_slab_bytes.restype = C.c_int64
+    L.host_band_init.argtypes = [C.c_int] * 11 + [C.c_void_p, C.c_int, C.POINTER(HostPeer), C.POINTER(HostPeer), C.c_int]
+    L.host_band_frame.argtypes = [C.POINTER(FrameParams)] + [C.c_void_p] * 16 + [C.c_int, C.c_void_p]
+    return L
+
+
+def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_signal, out_name):
+    """One band process: attach every slab, run FRAMES frames, leave the lit owned rows in the output block."""
+    from multiprocessing import shared_memory
+    from oracle.oracle_py import _atlas_ptrs
+    from stratusgfx_b200.scene import Scene
+    L = _load()
+    world = len(bands)
+    shms = [shared_memory.SharedMemory(name=n) for n in shm_names]
+    out = shared_memory.SharedMemory(name=out_name)
+    base = [C.addressof(C.c_char.from_buffer(s.buf)) for s in shms]
+    me = bands[rank]
+    def peer(r):
+        if r < 0 or r >= world:
+            return HostPeer(0, 0, 0, 0, 0, 0, None)
+        b = bands[r]
+        return HostPeer(1, b.y0, b.rows, b.b0, b.b1 - b.b0, r, base[r])
+    up, down = peer(rank - 1), peer(rank + 1)
+    scene = Scene("tiny", height=H, yaw_deg_per_frame=1.5)
+    L.host_band_init(W, H, scene.cube_res, scene.csm_res, scene.denoise_iters, rank, world, me.y0, me.rows, me.b0, me.b1 - me.b0,
+                     base[rank], rows_max, C.byref(up), C.byref(down), 1 if kernel_signal else 0)
+    sh, _ = scene.cubemaps()
+    shp = _atlas_ptrs(sh)
+    lit = np.ndarray((FRAMES, H, W, 4), np.float16, buffer=out.buf)
+    for f in range(FRAMES):
+        fp = scene.frame_params(f)
+        gb, pgb = scene.gbuffer(f, me.y0, me.rows), scene.gbuffer(f - 1, me.y0, me.rows)
+        updated, visible, entries = (np.ascontiguousarray(a) for a in tables[f])
+        fp.totalNumLights = int(len(visible) - 1)
+        combined = np.zeros((me.rows, W, 4), np.float16)
+        keep = [np.ascontiguousarray(a) for a in (gb.depth, gb.normal, gb.albedo, gb.baseReflectivity, gb.roughnessMetallicAmbient, gb.ssao,
+                                                  gb.velocity, gb.id, gb.screen, pgb.normal, pgb.id, pgb.depth)]
+        rc = L.host_band_frame(C.byref(fp), *[a.ctypes.data for a in keep], updated.ctypes.data, visible.ctypes.data, entries.ctypes.data,
+                               C.addressof(shp), sh.shape[0], combined.ctypes.data)
+        assert rc == 0
+        lit[f, me.b0:me.b1] = combined[me.owned]
+    del lit
+    for s in shms + [out]:
+        s.close()
+
+
+def _run(world, tables, kernel_signal, timeout=240):
+    from multiprocessing import shared_memory
+    from stratusgfx_b200.bands import bands_from_cuts, halo_rows
+    L = _load()
+    cuts = {1: [0, H], 3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H]}[world]      # (5: unequal bands, the balanced plan)
+    bands = bands_from_cuts(cuts, H, halo_rows(4))
+    rows_max = max(b.rows for b in bands)
+    slab_bytes = int(L.host_band_slab_bytes(W, rows_max))
+    shms = [shared_memory.SharedMemory(create=True, size=slab_bytes) for _ in range(world)]
+    out = shared_memory.SharedMemory(create=True, size=FRAMES * H * W * 8)
+    try:
+        for s in shms:
+            np.ndarray(slab_bytes, np.uint8, buffer=s.buf)[:] = 0
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=_band_worker, args=(r, bands, [s.name for s in shms], slab_bytes, rows_max, tables, kernel_signal, out.name))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout)
+        hung = [p for p in procs if p.is_alive()]
+        for p in hung:
+            p.kill(); p.join()
+        assert not hung, f"{len(hung)} band process(es) still waiting after {timeout} s: dead-lock in the band flags"
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        return np.ndarray((FRAMES, H, W, 4), np.float16, buffer=out.buf).copy()
+    finally:
+        for s in shms + [out]:
+            s.close(); s.unlink()
+
+
+@pytest.fixture(scope="module")
+def whole_frame(built):
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    from tests.parity_util import SceneData, compare_radiance, run_oracle
+    d = SceneData(**WORKLOAD)
+    orc = run_oracle(d, keep_passes=False)
+    tables = [(o["updated"], o["visible"], o["entries"]) for o in orc]
+    lit = _run(1, tables, True)
+    for f in range(FRAMES):          # the one-handle host run is itself the oracle's frame (radiance bar)
+        r = compare_radiance(lit[f], orc[f]["combined"], 3)
+        assert r["ok"] and r["bit_exact"] > 0.99, (f, r)
+    return tables, lit
+
+
+@pytest.mark.parametrize("world,kernel_signal", [(3, True), (4, True), (4, False), (5, True)])
+def test_bands_with_middle_ranks_reproduce_the_whole_frame_bytes(whole_frame, world, kernel_signal):
+    tables, want = whole_frame
+    got = _run(world, tables, kernel_signal)
+    for f in range(FRAMES):
+        assert np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)), f
