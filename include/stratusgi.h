@@ -287,6 +287,23 @@ typedef struct SgiDirectParams {
 /* pbr.fs over the bound G-buffer, cube shadow atlases and sun shadow map; stream-ordered */
 int  sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp);
 
+/* ---- screen-space ambient occlusion (first half): ssao.fs + ssao_blur.fs, the two passes whose output
+ *      is the `ssao` plane of this path (RenderSsaoOcclude_ / RenderSsaoBlur_, StratusRendererBackend.cpp:1160-1204) ----
+ * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_ssao.cu).  Whole-frame handles only. */
+typedef struct SgiSsaoParams {
+    float   aspectRatio;                /* viewportWidth / viewportHeight                      (BE:1165)          */
+    float   projPlaneZDist;             /* 1 / tan(fovy / 2)                                   (BE:1167)          */
+    float   intensity;                  /* 5.0 in the reference                                (BE:1170)          */
+    float   _pad;
+    const void* structureBuffer;        /* device half4 [rows][W]: (dFdx z, dFdy z, z high part, z low part), pbr_geometry_pass.fs:61-75 */
+    const void* rotationLookup;         /* device half4 [4][4]: (cos, sin, 0, -) of InitSSAO_'s shuffled angles (BE:759-779)          */
+    void*   occlusionScratch;           /* device half [rows][W]: ssaoOcclusionTexture                              */
+    void*   ssaoOut;                    /* device half [rows][W]: ssaoOcclusionBlurredTexture = SgiBuffers.ssao     */
+} SgiSsaoParams;
+
+/* both passes over the structure buffer; stream-ordered */
+int  sgi_ssao(SgiHandle h, const SgiSsaoParams* sp);
+
 /* VPL pre-pass: lights whose sphere touches the view frustum, ordered by distance to the viewer (equal distances keep
  * their input order, as std::multiset insertion does), the nearest 10000 written as the cull's input table.  Stream-ordered;
  * bind countOut as SgiBuffers.vplCountDevice and pass totalNumLights = min(numLights, 10000) to run a frame without

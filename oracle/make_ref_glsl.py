@@ -61,6 +61,9 @@ COMPUTE = [
     ("vpl_tiled_deferred_culling_stage2.cs", "cs_stage2", "stage2_main", ["SHUFFLE_DOWN"]),
     ("viscull_vpls.cs", "cs_cull", "cull_main", []),
     ("pbr.fs", "fs_direct", "direct_main", []),           # widening row f3: the deferred direct-lighting pass that produces `screen`
+    # widening row f4 (first half): the two SSAO passes that produce the `ssao` plane the gather reads (BE:1160-1204)
+    ("ssao.fs", "fs_ssao", "ssao_main", [], ["saturate", "calculateAmbientOcclusion"]),
+    ("ssao_blur.fs", "fs_ssao_blur", "ssao_blur_main", [], ["blurAmbientOcclusion"]),
 ]
 TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray|sampler2DArrayShadow)"
 
@@ -151,8 +154,8 @@ static inline float halfToFloat(unsigned short h) {
 }
 enum TexFormat { R32F, RGBA8, RG8, R16F, RG16F, RGBA16F };
 enum TexFilter { NEAREST, LINEAR };
-struct sampler2D { const void* data = nullptr; int W = 0, H = 0; TexFormat fmt = R32F; TexFilter filter = NEAREST; };
-struct sampler2DRect { const void* data = nullptr; int W = 0, H = 0; TexFormat fmt = R16F; };
+struct sampler2D { const void* data = nullptr; int W = 0, H = 0; TexFormat fmt = R32F; TexFilter filter = NEAREST; bool repeat = false; };
+struct sampler2DRect { const void* data = nullptr; int W = 0, H = 0; TexFormat fmt = R16F; TexFilter filter = NEAREST; };
 static inline vec4 fetchTexel(const void* data, TexFormat fmt, int W, int i, int j) {
     const size_t p = (size_t)j * W + i;
     switch (fmt) {
@@ -166,7 +169,9 @@ static inline vec4 fetchTexel(const void* data, TexFormat fmt, int W, int i, int
     return vec4(0.0f);
 }
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-static inline vec4 textureNearest(const sampler2D& s, vec2 uv) {             // CLAMP_TO_EDGE
+static inline int wrapi(int v, int n) { const int m = v % n; return m < 0 ? m + n : m; }
+static inline vec4 textureNearest(const sampler2D& s, vec2 uv) {             // CLAMP_TO_EDGE, or REPEAT (the 4x4 SSAO rotation table, BE:776-778)
+    if (s.repeat) return fetchTexel(s.data, s.fmt, s.W, wrapi((int)std::floor(uv.x * (float)s.W), s.W), wrapi((int)std::floor(uv.y * (float)s.H), s.H));
     return fetchTexel(s.data, s.fmt, s.W, clampi((int)std::floor(uv.x * (float)s.W), 0, s.W - 1), clampi((int)std::floor(uv.y * (float)s.H), 0, s.H - 1));
 }
 // texture(): NEAREST picks the texel that contains the coordinate; LINEAR blends the four neighbours with 8-bit sub-texel weights
@@ -191,8 +196,18 @@ template <class V, class S> static inline void swizzleAdd3(V& v, const S& s) { v
 template <class V, class S> static inline void swizzleSet3(V& v, const S& s) { const vec3 t(s); v.x = t.x; v.y = t.y; v.z = t.z; }
 template <class V, class S> static inline void swizzleAdd2(V& v, const S& s) { v.x += s.x; v.y += s.y; }
 template <class V, class S> static inline void swizzleSet2(V& v, const S& s) { const vec2 t(s); v.x = t.x; v.y = t.y; }
-static inline vec4 texture(const sampler2DRect& s, vec2 pixelCoords) {       // rectangle textures are addressed in pixels
-    return fetchTexel(s.data, s.fmt, s.W, clampi((int)std::floor(pixelCoords.x), 0, s.W - 1), clampi((int)std::floor(pixelCoords.y), 0, s.H - 1));
+static inline vec4 texture(const sampler2DRect& s, vec2 pixelCoords) {       // rectangle textures are addressed in pixels; CLAMP_TO_EDGE
+    if (s.filter == NEAREST)
+        return fetchTexel(s.data, s.fmt, s.W, clampi((int)std::floor(pixelCoords.x), 0, s.W - 1), clampi((int)std::floor(pixelCoords.y), 0, s.H - 1));
+    // LINEAR (the structure buffer, BE:406-408): the same filter model as sampler2D above, in pixel units
+    const float fu = pixelCoords.x - 0.5f, fv = pixelCoords.y - 0.5f;
+    const float i0f = std::floor(fu), j0f = std::floor(fv);
+    const float a = std::floor((fu - i0f) * 256.0f + 0.5f) * (1.0f / 256.0f), b = std::floor((fv - j0f) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const int i0 = clampi((int)i0f, 0, s.W - 1), i1 = clampi((int)i0f + 1, 0, s.W - 1), j0 = clampi((int)j0f, 0, s.H - 1), j1 = clampi((int)j0f + 1, 0, s.H - 1);
+    const vec4 t00 = fetchTexel(s.data, s.fmt, s.W, i0, j0), t10 = fetchTexel(s.data, s.fmt, s.W, i1, j0), t01 = fetchTexel(s.data, s.fmt, s.W, i0, j1), t11 = fetchTexel(s.data, s.fmt, s.W, i1, j1);
+    vec4 r;
+    for (int c = 0; c < 4; ++c) r[c] = (1.0f - a) * (1.0f - b) * t00[c] + a * (1.0f - b) * t10[c] + (1.0f - a) * b * t01[c] + a * b * t11[c];
+    return r;
 }
 struct samplerCubeArray { const unsigned short* data = nullptr; int res = 0; const unsigned char* rgba8 = nullptr; };   // DEPTH_COMPONENT16 (or RGBA8), [layer][face][res][res], NEAREST
 static inline vec4 texture(const samplerCubeArray& s, vec4 dirLayer) {      // GL 4.6 table 8.19 (major axis, sc, tc), then the texel of the face
@@ -432,6 +447,47 @@ void refglsl_direct_lighting(const RefDirectArgs* a) {
             }
     }
 }
+typedef struct RefSsaoArgs {
+    int W, H; const unsigned short* structureH4; const unsigned short* rotationH4 /* 4x4 RGBA16F */; const unsigned short* occlusionH /* blur only */;
+    float aspectRatio, projPlaneZDist, intensity; float* out; int rowBegin, rowEnd;
+} RefSsaoArgs;
+void refglsl_ssao(const RefSsaoArgs* a) {                                   // RenderSsaoOcclude_ (BE:1160-1187)
+    using namespace refglsl;
+    #pragma omp parallel
+    {
+        fs_ssao::structureBuffer.data = a->structureH4; fs_ssao::structureBuffer.W = a->W; fs_ssao::structureBuffer.H = a->H;
+        fs_ssao::structureBuffer.fmt = RGBA16F; fs_ssao::structureBuffer.filter = LINEAR;                       // BE:406-408
+        fs_ssao::rotationLookup.data = a->rotationH4; fs_ssao::rotationLookup.W = 4; fs_ssao::rotationLookup.H = 4;
+        fs_ssao::rotationLookup.fmt = RGBA16F; fs_ssao::rotationLookup.filter = NEAREST; fs_ssao::rotationLookup.repeat = true;   // BE:776-778
+        fs_ssao::aspectRatio = a->aspectRatio; fs_ssao::projPlaneZDist = a->projPlaneZDist; fs_ssao::intensity = a->intensity;
+        fs_ssao::windowWidth = (float)a->W; fs_ssao::windowHeight = (float)a->H;
+        #pragma omp for schedule(dynamic, 4)
+        for (int y = a->rowBegin; y < a->rowEnd; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                fs_ssao::fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                fs_ssao::ssao_main();
+                a->out[(size_t)y * a->W + x] = fs_ssao::gLightFactor;
+            }
+    }
+}
+void refglsl_ssao_blur(const RefSsaoArgs* a) {                              // RenderSsaoBlur_ (BE:1189-1204)
+    using namespace refglsl;
+    #pragma omp parallel
+    {
+        fs_ssao_blur::structureBuffer.data = a->structureH4; fs_ssao_blur::structureBuffer.W = a->W; fs_ssao_blur::structureBuffer.H = a->H;
+        fs_ssao_blur::structureBuffer.fmt = RGBA16F; fs_ssao_blur::structureBuffer.filter = LINEAR;
+        fs_ssao_blur::occlusionBuffer.data = a->occlusionH; fs_ssao_blur::occlusionBuffer.W = a->W; fs_ssao_blur::occlusionBuffer.H = a->H;
+        fs_ssao_blur::occlusionBuffer.fmt = R16F; fs_ssao_blur::occlusionBuffer.filter = NEAREST;              // BE:491-493
+        fs_ssao_blur::windowWidth = (float)a->W; fs_ssao_blur::windowHeight = (float)a->H;
+        #pragma omp for schedule(dynamic, 4)
+        for (int y = a->rowBegin; y < a->rowEnd; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                fs_ssao_blur::fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                fs_ssao_blur::ssao_blur_main();
+                a->out[(size_t)y * a->W + x] = fs_ssao_blur::gLightFactor;
+            }
+    }
+}
 typedef struct RefColorArgs {
     int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
     const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
@@ -533,7 +589,9 @@ void refglsl_cull(const RefCullArgs* a) {
 '''
 
 
-CS_PRE = {'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n', 'fs_direct': '#define INFINITE_LIGHTING_ENABLED\nstruct PointLight { vec4 position; vec4 color; float radius; float farPlane; float _1[2]; };        // pbr.fs:15-21\nPERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient; PERINV sampler2DRect ssao;\nPERINV mat4 invProjectionView; PERINV float windowWidth, windowHeight; PERINV vec3 viewPosition; PERINV float emissionStrength = 0.0f;\nPERINV int numLights = 0, numShadowLights = 0; PERINV const PointLight* nonShadowCasters; PERINV const PointLight* shadowCasters;\nPERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES]; PERINV const AtlasEntry* shadowIndices;\nPERINV vec3 infiniteLightColor; PERINV vec2 fsTexCoords; PERINV vec3 fsColor;\n'}
+CS_PRE = {'fs_ssao': 'PERINV sampler2DRect structureBuffer; PERINV sampler2D rotationLookup;\nPERINV float aspectRatio, projPlaneZDist, windowHeight, windowWidth, intensity; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
+          'fs_ssao_blur': 'PERINV sampler2DRect structureBuffer, occlusionBuffer; PERINV float windowWidth, windowHeight; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
+          'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n', 'fs_direct': '#define INFINITE_LIGHTING_ENABLED\nstruct PointLight { vec4 position; vec4 color; float radius; float farPlane; float _1[2]; };        // pbr.fs:15-21\nPERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient; PERINV sampler2DRect ssao;\nPERINV mat4 invProjectionView; PERINV float windowWidth, windowHeight; PERINV vec3 viewPosition; PERINV float emissionStrength = 0.0f;\nPERINV int numLights = 0, numShadowLights = 0; PERINV const PointLight* nonShadowCasters; PERINV const PointLight* shadowCasters;\nPERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES]; PERINV const AtlasEntry* shadowIndices;\nPERINV vec3 infiniteLightColor; PERINV vec2 fsTexCoords; PERINV vec3 fsColor;\n'}
 
 
 def generate():
@@ -562,11 +620,16 @@ def generate():
             if n == "main":
                 defs = [re.sub(r"\bvoid\s+main\s*\(", "void denoise_main(", d) for d in defs]
             parts += [adapt(d) + "\n" for d in defs]
-    for fname, ns, main_name, macros in COMPUTE:
+    for fname, ns, main_name, macros, *more in COMPUTE:
         text = strip_comments(open(os.path.join(SHADERS, fname)).read())
         parts.append(f"\n// ---- from Source/Shaders/{fname} ----\nnamespace {ns} {{\n" + CS_PRE[ns])
         for mac in macros:
             parts.append(extract_macro(text, mac) + "\n")
+        for n in (more[0] if more else []):               # the shader's own functions main() calls
+            defs = extract(text, n)
+            if not defs:
+                raise SystemExit(f"{n} not found in {fname}")
+            parts += [adapt(d) + "\n" for d in defs]
         (d,) = extract(text, "main")
         parts.append(adapt(re.sub(r"\bvoid\s+main\s*\(", f"void {main_name}(", d)) + f"\n}}  // namespace {ns}\n")
     parts.append(EPILOGUE)

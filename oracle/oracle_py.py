@@ -72,7 +72,7 @@ def reference_glsl():
     L.refglsl_bound_hdr.restype = C.c_float
     L.refglsl_gather.argtypes = [C.c_void_p]
     L.refglsl_denoise_pass.argtypes = [C.c_void_p]
-    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull", "refglsl_direct_lighting"):
+    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull", "refglsl_direct_lighting", "refglsl_ssao", "refglsl_ssao_blur"):
         getattr(L, name).argtypes = [C.c_void_p]
     return L
 
@@ -137,6 +137,34 @@ def reference_glsl_direct_lighting(ref, fp, gb, csm, csm_res, shadow_atlas, cube
 
 def _f32(x):
     return np.ascontiguousarray(np.array(x, np.float32).reshape(-1))
+
+
+class RefSsaoArgs(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int), ("structureH4", C.c_void_p), ("rotationH4", C.c_void_p), ("occlusionH", C.c_void_p),
+                ("aspectRatio", C.c_float), ("projPlaneZDist", C.c_float), ("intensity", C.c_float), ("out", C.c_void_p),
+                ("rowBegin", C.c_int), ("rowEnd", C.c_int)]
+
+
+def reference_glsl_ssao(ref, structure, rotation, aspectRatio, projPlaneZDist, intensity=5.0):
+    """ssao.fs then ssao_blur.fs (the reference's shader text, compiled): (occlusion, blurred) as the
+    R16F render targets hold them (float16 [H, W]).  structure: half4 [H, W, 4]; rotation: half4 [4, 4, 4]."""
+    H, W = structure.shape[:2]
+    structure, rotation = np.ascontiguousarray(structure, np.float16), np.ascontiguousarray(rotation, np.float16)
+    a = RefSsaoArgs()
+    a.W, a.H, a.rowBegin, a.rowEnd = W, H, 0, H
+    a.structureH4, a.rotationH4 = structure.ctypes.data, rotation.ctypes.data
+    a.aspectRatio, a.projPlaneZDist, a.intensity = float(aspectRatio), float(projPlaneZDist), float(intensity)
+    tmp = np.zeros((H, W), np.float32)
+    a.out = tmp.ctypes.data
+    ref.refglsl_ssao(C.addressof(a))
+    with np.errstate(over="ignore"):
+        occlusion = tmp.astype(np.float16)               # the store into the R16F target (round to nearest even)
+    a.occlusionH = occlusion.ctypes.data
+    tmp2 = np.zeros((H, W), np.float32)
+    a.out = tmp2.ctypes.data
+    ref.refglsl_ssao_blur(C.addressof(a))
+    with np.errstate(over="ignore"):
+        return occlusion, tmp2.astype(np.float16)
 
 
 def reference_glsl_cull(ref, fp, vpl_data, csm, csm_res):

@@ -258,6 +258,14 @@ int sgi_vpl_prepass(SgiHandle h, const SgiPrepassParams* pp) {
     return postLaunch(h, launchPrepass(h->stream, *pp, h->prepassKeys, h->prepassInside));
 }
 
+int sgi_ssao(SgiHandle h, const SgiSsaoParams* sp) {
+    if (!h || !sp) return SGI_ERR_INVALID_ARG;
+    if (!sp->structureBuffer || !sp->rotationLookup || !sp->occlusionScratch || !sp->ssaoOut) return fail(h, SGI_ERR_NOT_BOUND, "sgi_ssao: structureBuffer, rotationLookup, occlusionScratch and ssaoOut are required");
+    if (h->banded || h->cp.rows != h->cp.full_height) return fail(h, SGI_ERR_UNSUPPORTED, "sgi_ssao: whole-frame handles only (the taps of a band would need halo rows)");
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    return postLaunch(h, launchSsao(h->stream, bandDims(h), *sp));
+}
+
 int sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp) {
     if (!h || !fp || !dp) return SGI_ERR_INVALID_ARG;
     if (dp->numLights < 0 || dp->numShadowLights < 0 || !dp->screenOut) return fail(h, SGI_ERR_INVALID_ARG, "sgi_direct_lighting: bad light counts or no output plane");

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import (BandParams, Buffers, CreateParams, DirectParams, FrameParams, PeerInfo, PrepassParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+from ._abi import (BandParams, Buffers, CreateParams, DirectParams, FrameParams, PeerInfo, PrepassParams, SsaoParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
                    TILE_DIVISOR)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
@@ -48,6 +48,7 @@ def load_library():
     L.sgi_register_gl.argtypes = [H, C.c_void_p, C.c_int32]
     L.sgi_vpl_prepass.argtypes = [H, C.POINTER(PrepassParams)]
     L.sgi_direct_lighting.argtypes = [H, C.POINTER(FrameParams), C.POINTER(DirectParams)]
+    L.sgi_ssao.argtypes = [H, C.POINTER(SsaoParams)]
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
@@ -204,6 +205,23 @@ class VplGiPass:
         pp.orderOut = self.t["prepassOrder"].data_ptr()
         pp.countOut = self.t["vplCountDevice"].data_ptr()
         self._check(self.L.sgi_vpl_prepass(self._h, C.byref(pp)))
+
+    # ---- the passes that produce the `ssao` input plane: ssao.fs + ssao_blur.fs (NOT YET VALIDATED ON A GPU, see csrc/k_ssao.cu) ----
+    def ssao(self, structure, rotation, aspectRatio, projPlaneZDist, intensity=5.0):
+        """RenderSsaoOcclude_ + RenderSsaoBlur_ over a structure buffer (half4 [rows, W, 4]) -> the half [rows, W] plane, kept as
+        self.t["ssao"] (the plane bind() hands to the gather) and returned as a torch tensor."""
+        torch = self.torch
+        self.t["structure"] = torch.from_numpy(np.ascontiguousarray(structure, np.float16)).to(self.device)
+        self.t["ssaoRotation"] = torch.from_numpy(np.ascontiguousarray(rotation, np.float16)).to(self.device)
+        for k in ("ssaoOcclusion", "ssao"):
+            if k not in self.t or tuple(self.t[k].shape) != (self.rows, self.width) or self.t[k].dtype != torch.float16:
+                self.t[k] = torch.zeros((self.rows, self.width), dtype=torch.float16, device=self.device)
+        sp = SsaoParams()
+        sp.aspectRatio, sp.projPlaneZDist, sp.intensity = float(aspectRatio), float(projPlaneZDist), float(intensity)
+        sp.structureBuffer, sp.rotationLookup = self.t["structure"].data_ptr(), self.t["ssaoRotation"].data_ptr()
+        sp.occlusionScratch, sp.ssaoOut = self.t["ssaoOcclusion"].data_ptr(), self.t["ssao"].data_ptr()
+        self._check(self.L.sgi_ssao(self._h, C.byref(sp)))
+        return self.t["ssao"]
 
     # ---- the pass before this path: deferred direct lighting, pbr.fs (NOT YET VALIDATED ON A GPU, see csrc/k_direct.cu) ----
     def direct_lighting(self, fp, lights=None, shadow_lights=None, shadow_entries=None, sun=True, emission_strength=0.0,

@@ -45,6 +45,8 @@ def _load():
         _lib.sgs_cubemaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.sgs_csm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.sgs_sun_visibility.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.sgs_ssao_rotation_table.argtypes = [C.c_void_p]
+        _lib.sgs_fovy_degrees.restype = C.c_double
         _lib.sgs_float_to_half.restype = C.c_uint16
         _lib.sgs_float_to_half.argtypes = [C.c_float]
     return _lib

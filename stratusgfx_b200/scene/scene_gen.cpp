@@ -18,6 +18,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
+#include <numeric>
+#include <random>
 #include <vector>
 #include <algorithm>
 #include "../../include/stratusgi.h"
@@ -526,5 +529,18 @@ int sgs_sun_visibility(void* p, uint8_t* out) {
 }
 
 uint16_t sgs_float_to_half(float f) { return f2h(f); }
+
+// The engine-side constant input of the SSAO pass: InitSSAO_ (StratusRendererBackend.cpp:759-779) shuffles k = 0..15 with a
+// default-constructed std::default_random_engine and stores (cos, sin, 0) of 2*pi*k/16 in a 4x4 RGB16F texture.  out: 16 x 3 floats.
+void sgs_ssao_rotation_table(float* out) {
+    std::vector<float> ks(16);
+    std::iota(ks.begin(), ks.end(), 0.0f);
+    std::shuffle(ks.begin(), ks.end(), std::default_random_engine{});
+    for (size_t i = 0; i < ks.size(); ++i) {
+        const float r = 2.0f * float(M_PI) * ks[i] / 16.0f;
+        out[i * 3] = std::cos(r); out[i * 3 + 1] = std::sin(r); out[i * 3 + 2] = 0.0f;
+    }
+}
+double sgs_fovy_degrees(void) { return kFovY; }
 
 }  // extern "C"

@@ -35,6 +35,7 @@ def test_ctypes_layout_matches_header(tmp_path):
         "SgiDirectParams": (_abi.DirectParams, ["numLights", "numShadowLights", "sunEnabled", "nonShadowCasters", "shadowCasters", "shadowIndices",
                                                 "emissionStrength", "infiniteLightDepthBias", "infiniteLightZnear", "infiniteLightZfar",
                                                 "pointLightAmbientIntensity", "screenOut"]),
+        "SgiSsaoParams": (_abi.SsaoParams, ["aspectRatio", "projPlaneZDist", "intensity", "structureBuffer", "rotationLookup", "occlusionScratch", "ssaoOut"]),
         "SgiPrepassParams": (_abi.PrepassParams, ["viewPosition", "numLights", "frustumPlanes", "lights", "vplDataOut", "atlasEntryOut",
                                                   "orderOut", "countOut"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),
