@@ -33,6 +33,10 @@ public:
     // UpdatePointLights_ (BE:1359-1392), virtual-point-light branch, + InitVplFrameData_ (BE:1281-1292): on the device
     void UpdatePointLights_(const SgiPrepassParams& lights) { Check_(sgi_vpl_prepass(handle_, &lights)); }
 
+    // RenderSsaoOcclude_ + RenderSsaoBlur_ (BE:1160-1204): ssao.fs and ssao_blur.fs, producing the `ssao` plane of BindBuffers.
+    // (csrc/k_ssao.cu is prepared but has not run on a GPU yet, see include/stratusgi.h)
+    void RenderSsao_(const SgiSsaoParams& ssao) { Check_(sgi_ssao(handle_, &ssao)); }
+
     // PerformVirtualPointLightCullingStage1_ (BE:1578-1612): viscull_vpls.cs, without the fence
     void PerformVirtualPointLightCullingStage1_(const SgiFrameParams& frame) {
         if (frame.totalNumLights == 0) return;                                       // BE:1582
