@@ -304,6 +304,18 @@ typedef struct SgiSsaoParams {
 /* both passes over the structure buffer; stream-ordered */
 int  sgi_ssao(SgiHandle h, const SgiSsaoParams* sp);
 
+/* ---- temporal anti-aliasing (second half): taa.fs, PerformTaaPostFx_ (BE:2324-2354) ----
+ * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_taa.cu).  Whole-frame handles only. */
+typedef struct SgiTaaParams {
+    const void* screen;                 /* device rgba8 [rows][W]: finalScreenBuffer (the FXAA target, BE:694-699)                   */
+    const void* prevScreen;             /* device rgba8 [rows][W]: previousFrameBuffer (RGB8, BE:450-455; alpha ignored)             */
+    const void* velocity;               /* device half2 [rows][W]: currentFrame.velocity                                             */
+    void*   colorOut;                   /* device half4 [rows][W]: taaFbo (rgb, 0.0625)                                              */
+    void*   historyOut;                 /* device rgba8 [rows][W] or NULL: the blit into previousFrameBuffer (BE:2347-2353); may not alias prevScreen */
+} SgiTaaParams;
+
+int  sgi_taa(SgiHandle h, const SgiTaaParams* tp);
+
 /* VPL pre-pass: lights whose sphere touches the view frustum, ordered by distance to the viewer (equal distances keep
  * their input order, as std::multiset insertion does), the nearest 10000 written as the cull's input table.  Stream-ordered;
  * bind countOut as SgiBuffers.vplCountDevice and pass totalNumLights = min(numLights, 10000) to run a frame without

@@ -48,6 +48,7 @@ WANTED = [
                    # the deferred direct-lighting pass: Burley diffuse + the same specular lobe
                    "Fd_Fresnel_Schlick", "Fd_Burley", "singleScatteringBRDF_Diffuse_Burley", "BRDF_Burley", "calculateLighting_Burley",
                    "calculateDirectionalLighting", "calculatePointLighting2"]),
+    ("aa_common.glsl", ["tonemap", "inverseTonemap"]),          # Reinhard pair used by taa.fs (widening row f4, second half)
     ("vpl_pbr_gi.fs", ["performLightingCalculations"]),          # the whole body of the gather shader (main() only forwards to it)
     ("vpl_pbr_gi_denoise.fs", ["filterInput", "computeMergedReservoir", "main"]),     # the denoiser: main() is emitted as denoise_main()
 ]
@@ -64,6 +65,7 @@ COMPUTE = [
     # widening row f4 (first half): the two SSAO passes that produce the `ssao` plane the gather reads (BE:1160-1204)
     ("ssao.fs", "fs_ssao", "ssao_main", [], ["saturate", "calculateAmbientOcclusion"]),
     ("ssao_blur.fs", "fs_ssao_blur", "ssao_blur_main", [], ["blurAmbientOcclusion"]),
+    ("taa.fs", "fs_taa", "taa_main", [], []),              # widening row f4 (second half): temporal anti-aliasing (BE:2324-2354)
 ]
 TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray|sampler2DArrayShadow)"
 
@@ -488,6 +490,24 @@ void refglsl_ssao_blur(const RefSsaoArgs* a) {                              // R
             }
     }
 }
+typedef struct RefTaaArgs { int W, H; const unsigned char* screen4; const unsigned char* prevScreen4; const unsigned short* velocityH2; float* out4; } RefTaaArgs;
+void refglsl_taa(const RefTaaArgs* a) {                                     // PerformTaaPostFx_ (BE:2324-2344), the shader part
+    using namespace refglsl;
+    #pragma omp parallel
+    {
+        auto tex = [&](const void* d, TexFormat f, TexFilter filt) { sampler2D s; s.data = d; s.W = a->W; s.H = a->H; s.fmt = f; s.filter = filt; return s; };
+        fs_taa::screen = tex(a->screen4, RGBA8, LINEAR);                     // fxaaFbo2: RGBA8, LINEAR (BE:694-696)
+        fs_taa::prevScreen = tex(a->prevScreen4, RGBA8, LINEAR);             // previousFrameBuffer: RGB8, LINEAR (BE:450-452); alpha is never read
+        fs_taa::velocity = tex(a->velocityH2, RG16F, NEAREST);               // BE:412-414
+        #pragma omp for schedule(dynamic, 4)
+        for (int y = 0; y < a->H; ++y)
+            for (int x = 0; x < a->W; ++x) {
+                fs_taa::fsTexCoords = glm::vec2(((float)x + 0.5f) / (float)a->W, ((float)y + 0.5f) / (float)a->H);
+                fs_taa::taa_main();
+                for (int c = 0; c < 4; ++c) a->out4[4 * ((size_t)y * a->W + x) + c] = fs_taa::color[c];
+            }
+    }
+}
 typedef struct RefColorArgs {
     int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
     const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
@@ -590,6 +610,7 @@ void refglsl_cull(const RefCullArgs* a) {
 
 
 CS_PRE = {'fs_ssao': 'PERINV sampler2DRect structureBuffer; PERINV sampler2D rotationLookup;\nPERINV float aspectRatio, projPlaneZDist, windowHeight, windowWidth, intensity; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
+          'fs_taa': 'PERINV sampler2D screen, prevScreen, velocity, previousVelocity; PERINV vec2 fsTexCoords; PERINV vec4 color;\n',
           'fs_ssao_blur': 'PERINV sampler2DRect structureBuffer, occlusionBuffer; PERINV float windowWidth, windowHeight; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
           'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n', 'fs_direct': '#define INFINITE_LIGHTING_ENABLED\nstruct PointLight { vec4 position; vec4 color; float radius; float farPlane; float _1[2]; };        // pbr.fs:15-21\nPERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient; PERINV sampler2DRect ssao;\nPERINV mat4 invProjectionView; PERINV float windowWidth, windowHeight; PERINV vec3 viewPosition; PERINV float emissionStrength = 0.0f;\nPERINV int numLights = 0, numShadowLights = 0; PERINV const PointLight* nonShadowCasters; PERINV const PointLight* shadowCasters;\nPERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES]; PERINV const AtlasEntry* shadowIndices;\nPERINV vec3 infiniteLightColor; PERINV vec2 fsTexCoords; PERINV vec3 fsColor;\n'}
 

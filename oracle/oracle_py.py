@@ -72,7 +72,7 @@ def reference_glsl():
     L.refglsl_bound_hdr.restype = C.c_float
     L.refglsl_gather.argtypes = [C.c_void_p]
     L.refglsl_denoise_pass.argtypes = [C.c_void_p]
-    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull", "refglsl_direct_lighting", "refglsl_ssao", "refglsl_ssao_blur"):
+    for name in ("refglsl_color", "refglsl_stage1", "refglsl_stage2", "refglsl_cull", "refglsl_direct_lighting", "refglsl_ssao", "refglsl_ssao_blur", "refglsl_taa"):
         getattr(L, name).argtypes = [C.c_void_p]
     return L
 
@@ -137,6 +137,24 @@ def reference_glsl_direct_lighting(ref, fp, gb, csm, csm_res, shadow_atlas, cube
 
 def _f32(x):
     return np.ascontiguousarray(np.array(x, np.float32).reshape(-1))
+
+
+class RefTaaArgs(C.Structure):
+    _fields_ = [("W", C.c_int), ("H", C.c_int), ("screen4", C.c_void_p), ("prevScreen4", C.c_void_p), ("velocityH2", C.c_void_p), ("out4", C.c_void_p)]
+
+
+def reference_glsl_taa(ref, screen, prev_screen, velocity):
+    """taa.fs (the reference's shader text, compiled): the RGBA16F target as float16 [H, W, 4].
+    screen / prev_screen: uint8 [H, W, 4]; velocity: float16 [H, W, 2]."""
+    H, W = screen.shape[:2]
+    keep = [np.ascontiguousarray(screen, np.uint8), np.ascontiguousarray(prev_screen, np.uint8), np.ascontiguousarray(velocity, np.float16)]
+    out = np.zeros((H, W, 4), np.float32)
+    a = RefTaaArgs()
+    a.W, a.H = W, H
+    a.screen4, a.prevScreen4, a.velocityH2, a.out4 = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, out.ctypes.data
+    ref.refglsl_taa(C.addressof(a))
+    with np.errstate(over="ignore"):
+        return out.astype(np.float16)
 
 
 class RefSsaoArgs(C.Structure):

@@ -266,6 +266,15 @@ int sgi_ssao(SgiHandle h, const SgiSsaoParams* sp) {
     return postLaunch(h, launchSsao(h->stream, bandDims(h), *sp));
 }
 
+int sgi_taa(SgiHandle h, const SgiTaaParams* tp) {
+    if (!h || !tp) return SGI_ERR_INVALID_ARG;
+    if (!tp->screen || !tp->prevScreen || !tp->velocity || !tp->colorOut) return fail(h, SGI_ERR_NOT_BOUND, "sgi_taa: screen, prevScreen, velocity and colorOut are required");
+    if (tp->historyOut && tp->historyOut == tp->prevScreen) return fail(h, SGI_ERR_INVALID_ARG, "sgi_taa: historyOut may not alias prevScreen (other pixels still read it)");
+    if (h->banded || h->cp.rows != h->cp.full_height) return fail(h, SGI_ERR_UNSUPPORTED, "sgi_taa: whole-frame handles only");
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    return postLaunch(h, launchTaa(h->stream, bandDims(h), *tp));
+}
+
 int sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp) {
     if (!h || !fp || !dp) return SGI_ERR_INVALID_ARG;
     if (dp->numLights < 0 || dp->numShadowLights < 0 || !dp->screenOut) return fail(h, SGI_ERR_INVALID_ARG, "sgi_direct_lighting: bad light counts or no output plane");

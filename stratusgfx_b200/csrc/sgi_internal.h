@@ -249,6 +249,7 @@ namespace sgi {
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
 bool preloadPrepassKernels(); int launchPrepass(cudaStream_t stream, const SgiPrepassParams& pp, unsigned long long* keys, int* inside);
 bool preloadDirectKernels();
+bool preloadTaaKernels(); int launchTaa(cudaStream_t stream, const BandDims& bd, const SgiTaaParams& tp);
 bool preloadSsaoKernels(); int launchSsao(cudaStream_t stream, const BandDims& bd, const SgiSsaoParams& sp);
 int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
                          const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm, const AtlasTable& atlases,

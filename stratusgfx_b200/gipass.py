@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import _abi
-from ._abi import (BandParams, Buffers, CreateParams, DirectParams, FrameParams, PeerInfo, PrepassParams, SsaoParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
+from ._abi import (BandParams, Buffers, CreateParams, DirectParams, FrameParams, PeerInfo, PrepassParams, SsaoParams, TaaParams, MAX_TOTAL_SHADOW_ATLASES, MAX_TOTAL_VPLS_PER_FRAME,
                    TILE_DIVISOR)
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libstratusgi.so")
@@ -49,6 +49,7 @@ def load_library():
     L.sgi_vpl_prepass.argtypes = [H, C.POINTER(PrepassParams)]
     L.sgi_direct_lighting.argtypes = [H, C.POINTER(FrameParams), C.POINTER(DirectParams)]
     L.sgi_ssao.argtypes = [H, C.POINTER(SsaoParams)]
+    L.sgi_taa.argtypes = [H, C.POINTER(TaaParams)]
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
@@ -222,6 +223,22 @@ class VplGiPass:
         sp.occlusionScratch, sp.ssaoOut = self.t["ssaoOcclusion"].data_ptr(), self.t["ssao"].data_ptr()
         self._check(self.L.sgi_ssao(self._h, C.byref(sp)))
         return self.t["ssao"]
+
+    # ---- the resolve at the end of the frame: taa.fs (NOT YET VALIDATED ON A GPU, see csrc/k_taa.cu) ----
+    def taa(self, screen, prev_screen, velocity):
+        """PerformTaaPostFx_ over uint8 [rows, W, 4] current / previous LDR frames and the half2 velocity plane ->
+        (half4 [rows, W, 4] resolved colour, uint8 [rows, W, 4] next history), torch tensors kept in self.t."""
+        torch = self.torch
+        self.t["taaScreen"] = torch.from_numpy(np.ascontiguousarray(screen, np.uint8)).to(self.device)
+        self.t["taaPrev"] = torch.from_numpy(np.ascontiguousarray(prev_screen, np.uint8)).to(self.device)
+        self.t["taaVelocity"] = torch.from_numpy(np.ascontiguousarray(velocity, np.float16)).to(self.device)
+        self.t["taaOut"] = torch.zeros((self.rows, self.width, 4), dtype=torch.float16, device=self.device)
+        self.t["taaHistory"] = torch.zeros((self.rows, self.width, 4), dtype=torch.uint8, device=self.device)
+        tp = TaaParams()
+        tp.screen, tp.prevScreen, tp.velocity = self.t["taaScreen"].data_ptr(), self.t["taaPrev"].data_ptr(), self.t["taaVelocity"].data_ptr()
+        tp.colorOut, tp.historyOut = self.t["taaOut"].data_ptr(), self.t["taaHistory"].data_ptr()
+        self._check(self.L.sgi_taa(self._h, C.byref(tp)))
+        return self.t["taaOut"], self.t["taaHistory"]
 
     # ---- the pass before this path: deferred direct lighting, pbr.fs (NOT YET VALIDATED ON A GPU, see csrc/k_direct.cu) ----
     def direct_lighting(self, fp, lights=None, shadow_lights=None, shadow_entries=None, sun=True, emission_strength=0.0,

@@ -37,6 +37,9 @@ public:
     // (csrc/k_ssao.cu is prepared but has not run on a GPU yet, see include/stratusgi.h)
     void RenderSsao_(const SgiSsaoParams& ssao) { Check_(sgi_ssao(handle_, &ssao)); }
 
+    // PerformTaaPostFx_ (BE:2324-2354): taa.fs and the blit into the history (csrc/k_taa.cu: prepared, not yet run on a GPU)
+    void PerformTaaPostFx_(const SgiTaaParams& taa) { Check_(sgi_taa(handle_, &taa)); }
+
     // PerformVirtualPointLightCullingStage1_ (BE:1578-1612): viscull_vpls.cs, without the fence
     void PerformVirtualPointLightCullingStage1_(const SgiFrameParams& frame) {
         if (frame.totalNumLights == 0) return;                                       // BE:1582

@@ -36,6 +36,7 @@ def test_ctypes_layout_matches_header(tmp_path):
                                                 "emissionStrength", "infiniteLightDepthBias", "infiniteLightZnear", "infiniteLightZfar",
                                                 "pointLightAmbientIntensity", "screenOut"]),
         "SgiSsaoParams": (_abi.SsaoParams, ["aspectRatio", "projPlaneZDist", "intensity", "structureBuffer", "rotationLookup", "occlusionScratch", "ssaoOut"]),
+        "SgiTaaParams": (_abi.TaaParams, ["screen", "prevScreen", "velocity", "colorOut", "historyOut"]),
         "SgiPrepassParams": (_abi.PrepassParams, ["viewPosition", "numLights", "frustumPlanes", "lights", "vplDataOut", "atlasEntryOut",
                                                   "orderOut", "countOut"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First single-GPU visit of a new round, in one gpurun call (about 12 minutes of box time):
-#   1. the GPU parity suite on the default build, plus the opt-in tests of the direct-lighting and SSAO kernels (never run on a GPU yet)
+#   1. the GPU parity suite on the default build, plus the opt-in tests of the direct-lighting, SSAO and TAA kernels (never run on a GPU yet)
 #   2. the default bench line
 #   3. A/B of the queued compile-time variants of DESIGN.md section 9, each through the parity suite and the bench
 #      (all were shown byte-identical to the default build on the host, tests/test_denoise_kernel_on_host.py)
@@ -13,7 +13,7 @@ bench() {   # $1 = label
 import json; d=json.loads(open('$out/bench_$1.json').read().strip().splitlines()[-1]); print('$1', 'frame ms', round(d['ms_per_step'],4), {k: v.get('ms') for k, v in d['stages'].items()})"
 }
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_default.log 2>&1; echo "default pytest exit $?"; tail -2 $out/pytest_default.log
-SGI_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_zz_direct_lighting.py tests/test_zz_ssao.py -m gpu -q > $out/pytest_direct.log 2>&1; echo "direct-lighting + SSAO pytest exit $?"; tail -3 $out/pytest_direct.log
+SGI_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_zz_direct_lighting.py tests/test_zz_ssao.py tests/test_zz_taa.py -m gpu -q > $out/pytest_direct.log 2>&1; echo "direct-lighting + SSAO + TAA pytest exit $?"; tail -3 $out/pytest_direct.log
 bench default
 for v in "V3:-DSGI_ATROUS_V3" "V2V3:-DSGI_ATROUS_V2 -DSGI_ATROUS_V3" "PDL:-DSGI_PDL" "PDLV2V3:-DSGI_PDL -DSGI_ATROUS_V2 -DSGI_ATROUS_V3"; do
   label=${v%%:*}; flags=${v#*:}
