@@ -73,6 +73,43 @@ template <typename T> static inline T __ldcg(const T* p) { return *(const volati
 template <typename T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
 
+#ifdef SGI_HOST_RUNTIME
+// ---- the CUDA runtime as the ABI layer (csrc/sgi_abi.cu, csrc/sgi_band.cu) uses it, on host memory: "device" allocations are
+// malloc blocks filled with a 0xCD pattern (a read of memory the library never wrote shows up), copies and memsets are synchronous,
+// streams and events are opaque tokens, there is exactly one device, and nothing inter-process (CUDA IPC) is available.
+#ifndef SGI_HOST_FILL
+#define SGI_HOST_FILL 0xCD
+#endif
+namespace sgihost {
+inline cudaError_t hostMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); if (!*p) return cudaErrorMemoryAllocation; std::memset(*p, SGI_HOST_FILL, n ? n : 1); return cudaSuccess; }
+inline cudaError_t hostFree(void* p) { std::free(p); return cudaSuccess; }
+inline cudaError_t hostToken(void** p) { static char token; *p = &token; return cudaSuccess; }
+}
+#define cudaGetDeviceCount(p) (*(p) = 1, cudaSuccess)
+#define cudaSetDevice(d) cudaSuccess
+#define cudaGetLastError() cudaSuccess
+#define cudaGetErrorString(e) "host emulation"
+#define cudaMalloc(pp, n) sgihost::hostMalloc((void**)(pp), (n))
+#define cudaMallocHost(pp, n) sgihost::hostMalloc((void**)(pp), (n))
+#define cudaFree(p) sgihost::hostFree((void*)(p))
+#define cudaFreeHost(p) sgihost::hostFree((void*)(p))
+#define cudaMemcpyAsync(dst, src, n, kind, stream) (std::memcpy((dst), (src), (n)), cudaSuccess)
+#define cudaMemcpy(dst, src, n, kind) (std::memcpy((dst), (src), (n)), cudaSuccess)
+#define cudaStreamCreateWithFlags(ps, flags) sgihost::hostToken((void**)(ps))
+#define cudaStreamCreateWithPriority(ps, flags, prio) sgihost::hostToken((void**)(ps))
+#define cudaDeviceGetStreamPriorityRange(lo, hi) (*(lo) = 0, *(hi) = 0, cudaSuccess)
+#define cudaEventCreateWithFlags(pe, flags) sgihost::hostToken((void**)(pe))
+#define cudaEventRecord(e, s) cudaSuccess
+#define cudaStreamWaitEvent(s, e, f) cudaSuccess
+#define cudaStreamSynchronize(s) cudaSuccess
+#define cudaStreamDestroy(s) cudaSuccess
+#define cudaEventDestroy(e) cudaSuccess
+#define cudaIpcGetMemHandle(ph, p) cudaErrorNotSupported
+#define cudaIpcOpenMemHandle(pp, h, f) cudaErrorNotSupported
+#define cudaDeviceCanAccessPeer(pc, a, b) (*(pc) = 0, cudaSuccess)
+#define cudaDeviceEnablePeerAccess(d, f) cudaErrorNotSupported
+#endif
+
 // the host API calls a launch function of csrc/ makes around its kernels
 #define cudaMemsetAsync(p, v, n, stream) (std::memset((p), (v), (n)), cudaSuccess)
 #define cudaFuncSetAttribute(...) cudaSuccess

@@ -105,13 +105,13 @@ def _rewrite_launches(text):
         count += 1
 
 
-def translate(text, name):
+def translate(text, name, whole_band_file=False):
     text, dropped = _drop_ptx_helpers(text)
     text, launches = _rewrite_launches(text)
     text = re.sub(r"cudaFuncGetAttributes\(&a,\s*[^)]*\)\s*==\s*cudaSuccess", "true", text)
     # rule 5: dynamic shared memory is a per-CTA allocation of the lockstep runtime
     text = re.sub(r"extern\s+__shared__\s+([\w:]+)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)sgihost::dynSmem();", text)
-    if name == "sgi_band.cu":
+    if name == "sgi_band.cu" and not whole_band_file:
         # rule 6: the extern "C" half of sgi_band.cu is CUDA IPC plumbing; the host run keeps the namespace sgi half (bandLinks,
         # armInKernelSignal, signalNeighbours, the flag kernels)
         text = text[:text.index("using namespace sgi;")]
@@ -124,18 +124,29 @@ def translate(text, name):
     return text, dropped, launches
 
 
-def make_build_dir(kernel_files):
+def make_build_dir(kernel_files, build=BUILD, whole_band_file=False):
     """Translated copies of the kernel files and the csrc headers -> tests/cuda_on_host/_build/; returns the directory."""
     if isinstance(kernel_files, str):
         kernel_files = (kernel_files,)
-    os.makedirs(BUILD, exist_ok=True)
+    os.makedirs(build, exist_ok=True)
     for f in HEADERS + tuple(kernel_files):
         src = open(os.path.join(CSRC, f)).read()
-        text, _, _ = translate(src, f)
-        dst = os.path.join(BUILD, f)
+        text, _, _ = translate(src, f, whole_band_file)
+        dst = os.path.join(build, f)
         if not os.path.exists(dst) or open(dst).read() != text:
             open(dst, "w").write(text)
-    return BUILD
+    return build
+
+
+def _gxx(sources, so, build, defines):
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-pthread", "-ffp-contract=off", "-w",
+           "-I", build, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include")] + \
+          ["-D" + d for d in defines] + list(sources) + ["-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stderr[-6000:])
+    return so
 
 
 def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
@@ -150,11 +161,27 @@ def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
            [os.path.join(CSRC, f) for f in HEADERS + tuple(kernel_files)]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
-    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-pthread", "-ffp-contract=off", "-w",
-           "-I", build, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include")] + \
-          ["-D" + d for d in defines] + [os.path.join(HERE, w) for w in wrapper_cpps] + ["-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + r.stderr[-6000:])
-    return so
+    return _gxx([os.path.join(HERE, w) for w in wrapper_cpps], so, build, defines)
+
+
+ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
+
+
+def compile_whole_library():
+    """EVERY translation unit of libstratusgi.so — the C ABI included — for the host, in lockstep mode and over the CUDA-runtime
+    stand-ins of cuda_host_shim.h (-DSGI_HOST_RUNTIME): tests/cuda_on_host/_build_abi/libstratusgi_host.so exports the symbols
+    of include/stratusgi.h.  TEST INFRASTRUCTURE: it lets the host-side state machine of csrc/sgi_abi.cu and the bodies of the GPU
+    tests run where there is no GPU; nothing in the product loads it."""
+    build = make_build_dir(ABI_FILES, os.path.join(HERE, "_build_abi"), whole_band_file=True)
+    so = os.path.join(build, "libstratusgi_host.so")
+    srcs = [os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in HEADERS + ABI_FILES]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
+        return so
+    wrappers = []
+    for f in ABI_FILES:
+        w = os.path.join(build, "tu_" + f.replace(".cu", ".cpp"))
+        text = f'// generated by host_tu.py\n#define SGI_HOST_LOCKSTEP\n#define SGI_HOST_RUNTIME\n#include "cuda_host_shim.h"\n#include "{f}"\n'
+        if not os.path.exists(w) or open(w).read() != text:
+            open(w, "w").write(text)
+        wrappers.append(w)
+    return _gxx(wrappers, so, build, ())
