@@ -104,7 +104,7 @@ inline cudaError_t hostToken(void** p) { static char token; *p = &token; return 
 #define cudaStreamSynchronize(s) cudaSuccess
 #define cudaStreamDestroy(s) cudaSuccess
 #define cudaEventDestroy(e) cudaSuccess
-#define cudaIpcGetMemHandle(ph, p) cudaErrorNotSupported
+#define cudaIpcGetMemHandle(ph, p) (std::memset((ph), 0, sizeof(*(ph))), cudaSuccess)      /* (only same-process peers can attach) */
 #define cudaIpcOpenMemHandle(pp, h, f) cudaErrorNotSupported
 #define cudaDeviceCanAccessPeer(pc, a, b) (*(pc) = 0, cudaSuccess)
 #define cudaDeviceEnablePeerAccess(d, f) cudaErrorNotSupported

@@ -8,6 +8,8 @@ import ctypes as C
 import os
 import types
 
+import numpy as np
+
 from stratusgfx_b200 import _abi, gipass
 from stratusgfx_b200._abi import Buffers, CreateParams, MAX_TOTAL_VPLS_PER_FRAME, TILE_DIVISOR
 
@@ -62,6 +64,12 @@ class HostGiPass(gipass.VplGiPass):
         self.t["vplVisiblePerTile"] = torch.zeros((max(tiles, 1), 13), dtype=torch.int32)
         self.t["lightingOut"] = torch.zeros((rows, width, 4), dtype=torch.float16)
         self.tiles = tiles
+
+    def frame_image(self):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self._check(self.L.sgi_frame_image(self._h, C.byref(ptr), C.byref(nbytes)))
+        raw = np.ctypeslib.as_array((C.c_uint16 * (nbytes.value // 2)).from_address(ptr.value))
+        return self.torch.from_numpy(raw.view(np.float16).reshape(self.full_height, self.width, 4).copy())
 
     def output(self, name):
         return super().output(name).copy()          # (.cpu().numpy() of a CPU tensor is a view of the live buffer, not a download)

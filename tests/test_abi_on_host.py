@@ -86,3 +86,43 @@ def test_denoise_iteration_count_on_the_host(tiny, iters):
     from tests import test_parity_gpu as G
     with gpu_tests_on_the_host():
         G.test_denoise_iteration_count_is_a_parameter(tiny, iters)
+
+
+def test_p2p_bands_through_the_abi_with_a_middle_band(built):
+    """sgi_band_setup / export / attach (same-process peers), the band branches of sgi_gather and sgi_denoise_pass, the image
+    transfer into band 0 and sgi_frame_image, on 3 bands over two frames of a turning camera.  A host launch is synchronous, so
+    the bands advance stage by stage (every in-kernel wait is already satisfied when it is reached); on a GPU the same calls run
+    concurrently on one stream per band (tests/test_parity_gpu.py::test_p2p_row_bands_reproduce_the_whole_frame)."""
+    from stratusgfx_b200._abi import PEER_DOWN, PEER_ROOT, PEER_UP
+    from stratusgfx_b200.bands import bands_from_cuts, halo_rows
+    from tests.parity_util import SceneData, band_of, make_pass, run_cuda_staged
+    d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.5, height=240)
+    iters = d.scene.denoise_iters
+    with gpu_tests_on_the_host():
+        whole = run_cuda_staged(d)
+        bands = bands_from_cuts([0, 80, 160, 240], d.H, halo_rows(iters))
+        gps = [make_pass(d, b.y0, b.rows) for b in bands]
+        for gp, b in zip(gps, bands):
+            gp.band_setup(b.b0, b.b1 - b.b0, b.rank, 3, owns_frame_image=(b.rank == 0))
+        infos = [gp.band_export() for gp in gps]
+        for gp, b in zip(gps, bands):
+            if b.rank > 0: gp.band_attach(PEER_UP, infos[b.rank - 1])
+            if b.rank + 1 < 3: gp.band_attach(PEER_DOWN, infos[b.rank + 1])
+            if b.rank != 0: gp.band_attach(PEER_ROOT, infos[0])
+        for f in range(2):
+            fp = d.fp[f]
+            order = gps if f % 2 == 0 else gps[::-1]
+            for gp, b in zip(gps, bands):
+                gp.set_gbuffer(band_of(d.gb[f], b.y0, b.rows), band_of(d.gb[f - 1], b.y0, b.rows)); gp.set_csm(d.csm[f]); gp.bind()
+            for gp in order:
+                gp.cull(fp); gp.color(fp)
+            for gp in order:
+                gp.gather(fp)
+            for p in range(iters):
+                for gp in order:
+                    gp.denoise_pass(fp, p)
+            image = gps[0].frame_image().cpu().numpy()
+            assert np.array_equal(image.view(np.uint16), whole[f]["combined"].view(np.uint16)), f
+        assert [gp.band_timeouts() for gp in gps] == [0, 0, 0]
+        for gp in gps:
+            gp.close()
