@@ -138,9 +138,9 @@ def make_build_dir(kernel_files, build=BUILD, whole_band_file=False):
     return build
 
 
-def _gxx(sources, so, build, defines):
+def _gxx(sources, so, build, defines, extra=()):
     cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-pthread", "-ffp-contract=off", "-w",
+    cmd = ["g++", "-O2", *extra, "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-pthread", "-ffp-contract=off", "-w",
            "-I", build, "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include")] + \
           ["-D" + d for d in defines] + list(sources) + ["-o", so]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -167,13 +167,13 @@ def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
 ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
 
 
-def compile_whole_library():
+def compile_whole_library(sanitize=False):
     """EVERY translation unit of libstratusgi.so — the C ABI included — for the host, in lockstep mode and over the CUDA-runtime
     stand-ins of cuda_host_shim.h (-DSGI_HOST_RUNTIME): tests/cuda_on_host/_build_abi/libstratusgi_host.so exports the symbols
     of include/stratusgi.h.  TEST INFRASTRUCTURE: it lets the host-side state machine of csrc/sgi_abi.cu and the bodies of the GPU
     tests run where there is no GPU; nothing in the product loads it."""
     build = make_build_dir(ABI_FILES, os.path.join(HERE, "_build_abi"), whole_band_file=True)
-    so = os.path.join(build, "libstratusgi_host.so")
+    so = os.path.join(build, "libstratusgi_host_asan.so" if sanitize else "libstratusgi_host.so")
     srcs = [os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in HEADERS + ABI_FILES]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
@@ -184,4 +184,6 @@ def compile_whole_library():
         if not os.path.exists(w) or open(w).read() != text:
             open(w, "w").write(text)
         wrappers.append(w)
-    return _gxx(wrappers, so, build, ())
+    # sanitize: AddressSanitizer over kernels and ABI (every "device" allocation is its own malloc block, so a read or write past a
+    # plane is reported) — tools/asan_on_host.py; the process needs LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    return _gxx(wrappers, so, build, (), ("-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=address") if sanitize else ())
