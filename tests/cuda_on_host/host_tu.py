@@ -173,7 +173,8 @@ def compile_whole_library(sanitize=False):
     of include/stratusgi.h.  TEST INFRASTRUCTURE: it lets the host-side state machine of csrc/sgi_abi.cu and the bodies of the GPU
     tests run where there is no GPU; nothing in the product loads it."""
     build = make_build_dir(ABI_FILES, os.path.join(HERE, "_build_abi"), whole_band_file=True)
-    so = os.path.join(build, "libstratusgi_host_asan.so" if sanitize else "libstratusgi_host.so")
+    sanitize = "address" if sanitize is True else sanitize
+    so = os.path.join(build, f"libstratusgi_host_{sanitize}.so" if sanitize else "libstratusgi_host.so")
     srcs = [os.path.join(HERE, "cuda_host_shim.h"), os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in HEADERS + ABI_FILES]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
@@ -184,6 +185,8 @@ def compile_whole_library(sanitize=False):
         if not os.path.exists(w) or open(w).read() != text:
             open(w, "w").write(text)
         wrappers.append(w)
-    # sanitize: AddressSanitizer over kernels and ABI (every "device" allocation is its own malloc block, so a read or write past a
-    # plane is reported) — tools/asan_on_host.py; the process needs LD_PRELOAD=$(gcc -print-file-name=libasan.so)
-    return _gxx(wrappers, so, build, (), ("-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=address") if sanitize else ())
+    # sanitize = "address": AddressSanitizer over kernels and ABI (every "device" allocation is its own malloc block, so a read or
+    # write past a plane is reported); "thread": ThreadSanitizer over the lockstep runtime (two threads of a CTA touching the same
+    # shared or global word without a barrier / collective in between are reported — a race check).  tools/sanitize_on_host.py;
+    # the process needs LD_PRELOAD=$(gcc -print-file-name=libasan.so | libtsan.so)
+    return _gxx(wrappers, so, build, (), ("-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + sanitize) if sanitize else ())

@@ -1,11 +1,16 @@
-"""Memory check of the kernels and the C ABI without a GPU: the whole library built for the host (tests/cuda_on_host/host_tu.py) with
-AddressSanitizer, driven by the GPU suite's own test bodies.  Every "device" allocation is its own malloc block and the caller's
-buffers are ordinary heap tensors, so a kernel that reads or writes past the end of a plane — which a GPU forgives inside an
-allocation granule — is reported with the source line.
+"""Memory check and race check of the kernels and the C ABI without a GPU: the whole library built for the host
+(tests/cuda_on_host/host_tu.py) with AddressSanitizer or ThreadSanitizer, driven by the GPU suite's own test bodies.
 
-    python tools/asan_on_host.py            # re-executes itself under LD_PRELOAD=libasan.so
+    python tools/sanitize_on_host.py address      # re-executes itself under LD_PRELOAD=libasan.so   (9 minutes on 8 cores)
+    python tools/sanitize_on_host.py thread       # ... libtsan.so
 
-Covers: two staged frames of a turning camera against the oracle, sgi_frame, the tile-list gather mode, 1-3 denoise passes, the
+address: every "device" allocation is its own malloc block and the caller's buffers are ordinary heap tensors, so a kernel that
+reads or writes past the end of a plane — which a GPU forgives inside an allocation granule — is reported with the source line.
+thread: in lockstep mode every CUDA thread of a CTA is an OS thread and barriers / warp collectives are the only synchronisation,
+so two threads of a CTA touching the same shared-memory or global word without one in between are reported (what compute-sanitizer's
+racecheck looks for).  CTAs run one after the other, so races between CTAs are not visible to it.
+
+Covers: two staged frames of a turning camera against the oracle, sgi_frame, the tile-list gather mode, 1 and 3 denoise passes, the
 golden fixture, one / two / no visible VPL, more visible VPLs than the per-frame cap, resize, the pre-pass (0 .. 2048 lights and the
 frustum boundary cases) and the three kernels that have not met a GPU yet (direct lighting, SSAO, TAA)."""
 import os
@@ -17,12 +22,20 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "address"
+    if kind not in ("address", "thread"):
+        print(__doc__); return 2
     if os.environ.get("SGI_ASAN_CHILD") != "1":
         from tests.cuda_on_host.host_tu import compile_whole_library
-        lib = compile_whole_library(sanitize=True)
-        asan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
-        env = dict(os.environ, SGI_ASAN_CHILD="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", SGI_HOST_LIB_OVERRIDE=lib)
-        return subprocess.call([sys.executable, os.path.abspath(__file__)], env=env)
+        lib = compile_whole_library(sanitize=kind)
+        rt = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if kind == "address" else "libtsan.so")], text=True).strip()
+        env = dict(os.environ, SGI_ASAN_CHILD="1", LD_PRELOAD=rt, SGI_HOST_LIB_OVERRIDE=lib, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1",
+                   TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=2")
+        if kind == "thread":
+            env["OMP_NUM_THREADS"] = "1"      # libgomp is not instrumented: its own barriers would look like races (oracle, scene generator)
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), kind], env=env)
+        print("exit code", rc, "(a sanitizer report ends the run with a non-zero code)")
+        return rc
     from tests import test_parity_gpu as G, test_zz_direct_lighting as D, test_zz_ssao as S, test_zz_taa as T
     from tests.host_gipass import gpu_tests_on_the_host
     from tests.parity_util import SceneData, compare_frame, make_pass, run_cuda_staged, run_oracle
@@ -53,7 +66,7 @@ def main():
         S.test_ssao_against_the_compiled_shader_text(None, "tiny")
         T.test_taa_against_the_compiled_shader_text(None, "tiny", 1.5)
         print("pre-pass, direct lighting, SSAO, TAA: clean", flush=True)
-    print("ADDRESS SANITIZER: NO REPORT")
+    print(kind.upper(), "SANITIZER: NO REPORT")
     return 0
 
 
