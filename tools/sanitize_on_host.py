@@ -3,6 +3,7 @@
 
     python tools/sanitize_on_host.py address      # re-executes itself under LD_PRELOAD=libasan.so   (9 minutes on 8 cores)
     python tools/sanitize_on_host.py thread       # ... libtsan.so
+    python tools/sanitize_on_host.py undefined    # ... libubsan.so (misaligned vector accesses, signed overflow, bad shifts, float -> int overflow)
 
 address: every "device" allocation is its own malloc block and the caller's buffers are ordinary heap tensors, so a kernel that
 reads or writes past the end of a plane — which a GPU forgives inside an allocation granule — is reported with the source line.
@@ -23,14 +24,14 @@ sys.path.insert(0, ROOT)
 
 def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "address"
-    if kind not in ("address", "thread"):
+    if kind not in ("address", "thread", "undefined"):
         print(__doc__); return 2
     if os.environ.get("SGI_ASAN_CHILD") != "1":
         from tests.cuda_on_host.host_tu import compile_whole_library
         lib = compile_whole_library(sanitize=kind)
-        rt = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if kind == "address" else "libtsan.so")], text=True).strip()
+        rt = subprocess.check_output(["gcc", "-print-file-name=" + {"address": "libasan.so", "thread": "libtsan.so", "undefined": "libubsan.so"}[kind]], text=True).strip()
         env = dict(os.environ, SGI_ASAN_CHILD="1", LD_PRELOAD=rt, SGI_HOST_LIB_OVERRIDE=lib, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1",
-                   TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=2")
+                   TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=2", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
         if kind == "thread":
             env["OMP_NUM_THREADS"] = "1"      # libgomp is not instrumented: its own barriers would look like races (oracle, scene generator)
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), kind], env=env)
