@@ -55,8 +55,8 @@ static inline unsigned long long fma2(unsigned long long a, unsigned long long b
     unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
     return pack2(std::fma(a0, b0, c0), std::fma(a1, b1, c1));
 }
-static inline int ldAcquireSys(const int32_t* p) { return *(const volatile int32_t*)p; }
-static inline void stReleaseSys(int32_t* p, int v) { *(volatile int32_t*)p = v; }
+static inline int ldAcquireSys(const int32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }      // ld.acquire.sys.global.s32
+static inline void stReleaseSys(int32_t* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }       // st.release.sys.global.s32
 
 // the per-thread built-ins; the launch emulation below sets them before every call of the kernel function
 // (inline variables: ONE instance per shared object even when it is built from several translation units — the inline device

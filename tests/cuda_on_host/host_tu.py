@@ -149,7 +149,7 @@ def _gxx(sources, so, build, defines, extra=()):
     return so
 
 
-def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
+def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=(), extra=()):
     """g++ the wrapper(s) (each includes one "_build/<kernel file>") into one shared object; rebuilt when any input is newer."""
     if isinstance(wrapper_cpps, str):
         wrapper_cpps = (wrapper_cpps,)
@@ -161,7 +161,7 @@ def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=()):
            [os.path.join(CSRC, f) for f in HEADERS + tuple(kernel_files)]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
         return so
-    return _gxx([os.path.join(HERE, w) for w in wrapper_cpps], so, build, defines)
+    return _gxx([os.path.join(HERE, w) for w in wrapper_cpps], so, build, defines, extra)
 
 
 ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
