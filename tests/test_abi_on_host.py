@@ -57,14 +57,17 @@ def test_opt_in_gpu_tests_of_the_unvalidated_kernels_run_on_the_host(built):
 
 # ---- the bodies of GPU-suite tests (tests/test_parity_gpu.py), unchanged, over the host-built library --------------------------
 _FAST = ["test_fused_frame_call_equals_staged_calls", "test_reference_method_names_drive_the_same_path", "test_zero_lights_is_a_no_op",
-         "test_unbound_buffers_and_bad_passes_are_errors", "test_gather_modes_can_alternate_on_one_handle",
-         "test_cuda_integer_outputs_match_the_glm_golden_fixture"]
-_FAST_BUILT = ["test_single_vpl_and_two_vpls", "test_no_visible_vpl", "test_resize_then_run"]
-_SLOW_BUILT = ["test_more_visible_vpls_than_the_per_frame_cap", "test_tile_list_gather_mode", "test_row_bands_with_apron_reproduce_the_whole_frame"]
+         "test_unbound_buffers_and_bad_passes_are_errors"]
+_SLOW = ["test_gather_modes_can_alternate_on_one_handle", "test_cuda_integer_outputs_match_the_glm_golden_fixture"]
+_FAST_BUILT = ["test_no_visible_vpl", "test_resize_then_run"]
+_SLOW_BUILT = ["test_single_vpl_and_two_vpls", "test_more_visible_vpls_than_the_per_frame_cap", "test_tile_list_gather_mode",
+               "test_row_bands_with_apron_reproduce_the_whole_frame"]
 
 
-@pytest.mark.parametrize("name", _FAST)
+@pytest.mark.parametrize("name", _FAST + _SLOW)
 def test_gpu_suite_body_on_the_host(tiny, name):
+    if name in _SLOW and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("10-20 s on the host: set SGI_HOST_SUITE=full")
     from tests import test_parity_gpu as G
     with gpu_tests_on_the_host():
         getattr(G, name)(tiny)
@@ -72,8 +75,8 @@ def test_gpu_suite_body_on_the_host(tiny, name):
 
 @pytest.mark.parametrize("name", _FAST_BUILT + _SLOW_BUILT)
 def test_gpu_suite_edge_cases_on_the_host(built, name):
-    """Single VPL, no visible VPL, resize on every run; the per-frame cap, the tile-list gather mode and apron bands (3 minutes
-    together) with SGI_HOST_SUITE=full."""
+    """No visible VPL and resize on every run; one / two VPLs, the per-frame cap, the tile-list gather mode and apron bands (3 minutes
+    together) with SGI_HOST_SUITE=full (tools/sanitize_on_host.py runs them all)."""
     if name in _SLOW_BUILT and os.environ.get("SGI_HOST_SUITE", "") != "full":
         pytest.skip("slow on the host: set SGI_HOST_SUITE=full")
     from tests import test_parity_gpu as G
@@ -96,11 +99,11 @@ def test_p2p_bands_through_the_abi_with_a_middle_band(built):
     from stratusgfx_b200._abi import PEER_DOWN, PEER_ROOT, PEER_UP
     from stratusgfx_b200.bands import bands_from_cuts, halo_rows
     from tests.parity_util import SceneData, band_of, make_pass, run_cuda_staged
-    d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.5, height=240)
+    d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.5, height=180)
     iters = d.scene.denoise_iters
     with gpu_tests_on_the_host():
         whole = run_cuda_staged(d)
-        bands = bands_from_cuts([0, 80, 160, 240], d.H, halo_rows(iters))
+        bands = bands_from_cuts([0, 60, 120, 180], d.H, halo_rows(iters))
         gps = [make_pass(d, b.y0, b.rows) for b in bands]
         for gp, b in zip(gps, bands):
             gp.band_setup(b.b0, b.b1 - b.b0, b.rank, 3, owns_frame_image=(b.rank == 0))

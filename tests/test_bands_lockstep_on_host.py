@@ -123,6 +123,8 @@ def whole_frame(built):
 
 @pytest.mark.parametrize("world,kernel_signal", [(3, True), (4, True), (4, False), (5, True)])
 def test_bands_with_middle_ranks_reproduce_the_whole_frame_bytes(whole_frame, world, kernel_signal):
+    if not kernel_signal and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("host-launched signals (the path the 4- and 8-GPU hardware runs used): set SGI_HOST_SUITE=full")
     tables, want = whole_frame
     got = _run(world, tables, kernel_signal)
     for f in range(FRAMES):

@@ -140,6 +140,8 @@ def test_tile_list_kernels_in_lockstep_equal_the_oracle(host_frame_lib, workload
 # ---- a5: the persistent stochastic gather with the fused denoise pass 0 -------------------------------------------------------
 @pytest.mark.parametrize("workload", ["tiny", "c1"])
 def test_gather_kernel_in_lockstep_matches_the_oracle(host_frame_lib, workload):
+    if workload == "c1" and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("c1 through the gather takes 10 s on the host: set SGI_HOST_SUITE=full")
     """Which VPLs a pixel draws, which cube texel it reads and the lit/shadowed verdict are exact decisions, so a wrong one shows
     as a pixel far outside the radiance bar; the shading arithmetic itself is FMA / approximation tier (libm here)."""
     from oracle.oracle_py import _atlas_ptrs
