@@ -1,7 +1,7 @@
 #!/bin/bash
 # First single-GPU visit of a new round, in one gpurun call (about 12 minutes of box time):
 #   1. the GPU parity suite on the default build, plus the opt-in tests of the direct-lighting, SSAO and TAA kernels (never run on a GPU yet)
-#   2. the default bench line
+#   2. the default bench line, then compute-sanitizer memcheck and racecheck on the small end-to-end tests
 #   3. A/B of the queued compile-time variants of DESIGN.md section 9, each through the parity suite and the bench
 #      (all were shown byte-identical to the default build on the host, tests/test_denoise_kernel_on_host.py)
 #   4. the default build restored
@@ -15,6 +15,11 @@ import json; d=json.loads(open('$out/bench_$1.json').read().strip().splitlines()
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_default.log 2>&1; echo "default pytest exit $?"; tail -2 $out/pytest_default.log
 SGI_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_zz_direct_lighting.py tests/test_zz_ssao.py tests/test_zz_taa.py -m gpu -q > $out/pytest_direct.log 2>&1; echo "direct-lighting + SSAO + TAA pytest exit $?"; tail -3 $out/pytest_direct.log
 bench default
+# compute-sanitizer on the small end-to-end test (the host-side sanitizer passes of tools/sanitize_on_host.py found nothing; this is the device's word)
+for tool in memcheck racecheck; do
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "tiny_two_frames or fused_frame_call" > $out/sanitizer_$tool.log 2>&1
+  echo "compute-sanitizer $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $out/sanitizer_$tool.log | tail -3
+done
 for v in "V3:-DSGI_ATROUS_V3" "V2V3:-DSGI_ATROUS_V2 -DSGI_ATROUS_V3" "PDL:-DSGI_PDL" "PDLV2V3:-DSGI_PDL -DSGI_ATROUS_V2 -DSGI_ATROUS_V3"; do
   label=${v%%:*}; flags=${v#*:}
   SGI_EXTRA_NVCC_FLAGS="$flags" python -m stratusgfx_b200.build --force > $out/build_$label.log 2>&1 || { echo "$label: build failed"; continue; }
