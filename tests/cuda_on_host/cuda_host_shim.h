@@ -149,6 +149,9 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { sgiHostUnsupported("__sy
 // barrier over the CTA's live threads, a warp collective a barrier over the live lanes of its mask with the operands exchanged
 // through a per-warp slot array; __shared__ variables are function-local statics (one CTA runs at a time), dynamic shared memory
 // is a per-CTA allocation.  A thread that returns from the kernel leaves the barriers it would have taken part in, as on a GPU.
+// Limits (none is met by the kernels of csrc/): a lane that exits while others wait in a PARTIAL-mask collective re-evaluates that
+// wait with the full mask; __shfl reads of a lane outside the mask return the caller's own value; CTAs of one launch never overlap,
+// so a kernel whose CTAs wait for each other would hang here (the band kernels wait for OTHER bands only).
 #include <atomic>
 #include <condition_variable>
 #include <mutex>
