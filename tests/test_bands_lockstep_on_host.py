@@ -78,7 +78,7 @@ def _run(world, tables, kernel_signal, timeout=240):
     from multiprocessing import shared_memory
     from stratusgfx_b200.bands import bands_from_cuts, halo_rows
     L = _load()
-    cuts = {1: [0, H], 3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H]}[world]      # (5: unequal bands, the balanced plan)
+    cuts = {1: [0, H], 3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H], 8: list(range(0, H + 1, 30))}[world]      # (5: unequal bands, the balanced plan)
     bands = bands_from_cuts(cuts, H, halo_rows(4))
     rows_max = max(b.rows for b in bands)
     slab_bytes = int(L.host_band_slab_bytes(W, rows_max))
@@ -121,8 +121,10 @@ def whole_frame(built):
     return tables, lit
 
 
-@pytest.mark.parametrize("world,kernel_signal", [(3, True), (4, True), (4, False), (5, True)])
+@pytest.mark.parametrize("world,kernel_signal", [(3, True), (4, True), (4, False), (5, True), (8, True)])
 def test_bands_with_middle_ranks_reproduce_the_whole_frame_bytes(whole_frame, world, kernel_signal):
+    if world == 8 and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("8 bands of 30 rows (halo 20): set SGI_HOST_SUITE=full")
     if not kernel_signal and os.environ.get("SGI_HOST_SUITE", "") != "full":
         pytest.skip("host-launched signals (the path the 4- and 8-GPU hardware runs used): set SGI_HOST_SUITE=full")
     tables, want = whole_frame

@@ -49,7 +49,7 @@ def main():
     d = SceneData("tiny", frames=FRAMES, yaw_deg_per_frame=1.5, height=H)
     orc = run_oracle(d, keep_passes=False)
     tables = [tuple(np.ascontiguousarray(o[k]) for k in ("updated", "visible", "entries")) for o in orc]
-    cuts = {3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H]}[world]
+    cuts = {3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H], 8: list(range(0, H + 1, 30))}[world]
     bands = bands_from_cuts(cuts, H, halo_rows(4))
     rows_max = max(b.rows for b in bands)
     libs = []
