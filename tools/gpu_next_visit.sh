@@ -20,7 +20,7 @@ for tool in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -m gpu -q -k "tiny_two_frames or fused_frame_call" > $out/sanitizer_$tool.log 2>&1
   echo "compute-sanitizer $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" $out/sanitizer_$tool.log | tail -3
 done
-for v in "V3:-DSGI_ATROUS_V3" "V2V3:-DSGI_ATROUS_V2 -DSGI_ATROUS_V3" "PDL:-DSGI_PDL" "PDLV2V3:-DSGI_PDL -DSGI_ATROUS_V2 -DSGI_ATROUS_V3"; do
+for v in "KEY64:-DSGI_STAGE2_KEY64" "V3:-DSGI_ATROUS_V3" "V2V3:-DSGI_ATROUS_V2 -DSGI_ATROUS_V3" "PDL:-DSGI_PDL" "ALL:-DSGI_PDL -DSGI_ATROUS_V2 -DSGI_ATROUS_V3 -DSGI_STAGE2_KEY64"; do
   label=${v%%:*}; flags=${v#*:}
   SGI_EXTRA_NVCC_FLAGS="$flags" python -m stratusgfx_b200.build --force > $out/build_$label.log 2>&1 || { echo "$label: build failed"; continue; }
   timeout 600 python -m pytest tests/test_parity_gpu.py -m gpu -x -q > $out/pytest_$label.log 2>&1; echo "$label pytest exit $?"; tail -1 $out/pytest_$label.log
