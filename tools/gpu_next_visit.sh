@@ -1,11 +1,11 @@
 #!/bin/bash
-# First single-GPU visit of a new round, in one gpurun call (about 12 minutes of box time):
+# First single-GPU visit of a new round, in one gpurun call (about 25 minutes of box time):
 #   1. the GPU parity suite on the default build, plus the opt-in tests of the direct-lighting, SSAO and TAA kernels (never run on a GPU yet)
 #   2. the default bench line, then compute-sanitizer memcheck and racecheck on the small end-to-end tests
 #   3. A/B of the queued compile-time variants of DESIGN.md section 9, each through the parity suite and the bench
 #      (all were shown byte-identical to the default build on the host, tests/test_denoise_kernel_on_host.py)
 #   4. the default build restored
-# Usage: /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_next_visit.sh r02a'
+# Usage: /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_next_visit.sh r02a'
 tag=${1:-next}; out=gpurun_out/$tag; mkdir -p $out
 bench() {   # $1 = label
   timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > $out/bench_$1.json 2> $out/bench_$1.err
