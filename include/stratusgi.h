@@ -345,6 +345,13 @@ int  sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer);
 int  sgi_frame_image(SgiHandle h, void** out_ptr, int64_t* out_bytes);
 /* nonzero when a peer wait timed out since creation (a neighbour died or never signalled) */
 int  sgi_band_timeouts(SgiHandle h, int32_t* out_count);
+/* Motion limit of a band.  The final denoise pass reads the PREVIOUS frame's normal / depth / id / GI / history at
+ * uv - velocity (vpl_pbr_gi_denoise.fs:280,352-360).  A band only has the rows it holds: its own, plus the halo rows, whose
+ * G-buffer the caller supplies and whose GI / history the neighbour's final pass stores.  The halo height is the caller's
+ * choice (y_offset / rows of the handle; at least the à-trous reach, which sgi_band_setup enforces), so it must also cover
+ * the largest vertical motion of a frame: halo >= ceil(max |velocity.y| * full_height) + 1 rows.  Taps beyond the held rows
+ * are clamped to them and counted; a nonzero count means this band's image differs from the whole-frame result there. */
+int  sgi_band_reprojection_misses(SgiHandle h, int32_t* out_count);
 
 /* the blocking variant of the visible count (what BE:1675-1678 maps the buffer for) */
 int  sgi_visible_count(SgiHandle h, int32_t* out_count);

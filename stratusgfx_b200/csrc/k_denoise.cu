@@ -87,6 +87,9 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
 
     // reprojected reads; rows are band-local (previous-frame planes hold the same rows)
     Bilin k = bilinSetup(pu, pv, W, bd.fullH);
+    // a band whose halo is shorter than the frame's vertical motion reads a clamped row here: counted, so the caller can widen
+    // the halo (the held rows are the caller's choice, include/stratusgi.h "Row bands")
+    bool miss = k.j0 < bd.yOffset || k.j0 >= bd.yOffset + rows || (k.b != 0.0f && k.j1 >= bd.yOffset + rows);
     k.j0 = iclamp(k.j0 - bd.yOffset, 0, rows - 1); k.j1 = iclamp(k.j1 - bd.yOffset, 0, rows - 1);
     const size_t q00 = (size_t)k.j0 * W + k.i0, q10 = (size_t)k.j0 * W + k.i1, q01 = (size_t)k.j1 * W + k.i0, q11 = (size_t)k.j1 * W + k.i1;
     float prevCenterDepth; f3 pn, prevGi;
@@ -112,7 +115,10 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
     }
     const float currId = __ldg(io.ids + p);
     const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
-    const int nj = iclamp(iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1) - bd.yOffset, 0, rows - 1);
+    const int njFrame = iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1);
+    const int nj = iclamp(njFrame - bd.yOffset, 0, rows - 1);
+    miss = miss || njFrame < bd.yOffset || njFrame >= bd.yOffset + rows;
+    if (miss && io.links.reprojMisses != nullptr) atomicAdd(io.links.reprojMisses, 1);
     const float prevId = __ldg(io.prevIds + (size_t)nj * W + ni);
 
     // the history-reset decision `similarity < 0.99` (:410-418), exact.  Shortcut: when the reprojected tap is the same texel with

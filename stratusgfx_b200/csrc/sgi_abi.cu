@@ -158,7 +158,8 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (cudaMemsetAsync(h->cullTicket, 0, sizeof(unsigned int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->prepassInside, sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
-    if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels())) return bail(SGI_ERR_CUDA);
+    if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels() &&
+          preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels())) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
     *out = h;
     return SGI_OK;
@@ -239,6 +240,7 @@ static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo) {
     const int n = launchCull(h->stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
                              h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket,
                              colorToo ? &atl : nullptr, h->buf.vplCountDevice);
+    h->tileListsValid = false;      // tilePos holds positions into the previous cull's compacted table
     return postLaunch(h, n);
 }
 
@@ -326,7 +328,7 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     const bool tileMode = fp->gatherMode == SGI_GATHER_TILE_LIST;
     if (tileMode) {
         NEED(h, vplVisiblePerTile);
-        if (!h->tileListsValid) return fail(h, SGI_ERR_NOT_BOUND, "sgi_gather: SGI_GATHER_TILE_LIST needs sgi_tile_lists first (since the last bind)");
+        if (!h->tileListsValid) return fail(h, SGI_ERR_NOT_BOUND, "sgi_gather: SGI_GATHER_TILE_LIST needs sgi_tile_lists first (since the last bind and the last cull)");
     }
     NEED(h, depth); NEED(h, normal); NEED(h, albedo); NEED(h, baseReflectivity); NEED(h, roughnessMetallicAmbient); NEED(h, ssao);
     NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, shadowDiffuseIndices); NEED(h, shadowCubeMaps[0]);
@@ -473,12 +475,19 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         SGI_CUDA(h, cudaSetDevice(h->cp.device));
         SGI_CUDA(h, cudaEventRecord(h->evFork, h->stream));
         SGI_CUDA(h, cudaStreamWaitEvent(h->tileStream, h->evFork, 0));
-        if ((rc = tileListsOn(h, fp, h->tileStream)) != SGI_OK) return rc;
+        rc = tileListsOn(h, fp, h->tileStream);
+        // whatever the side stream holds by now is joined before this call returns, on the error paths too: its kernels read
+        // vplUpdatedData / the visible list, which the caller may rebind or the next cull overwrites
         SGI_CUDA(h, cudaEventRecord(h->evJoin, h->tileStream));
+        if (rc != SGI_OK) { cudaStreamWaitEvent(h->stream, h->evJoin, 0); return rc; }
     }
-    if ((rc = sgi_gather(h, fp)) != SGI_OK) return rc;
-    rc = sgi_denoise(h, fp);
-    if (fork) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evJoin, 0));
+    rc = sgi_gather(h, fp);
+    if (rc == SGI_OK) rc = sgi_denoise(h, fp);
+    if (fork) {
+        const std::string keep = h->lastError;
+        const cudaError_t e = cudaStreamWaitEvent(h->stream, h->evJoin, 0);
+        if (rc == SGI_OK) SGI_CUDA(h, e); else h->lastError = keep;
+    }
     return rc;
 }
 

@@ -112,6 +112,7 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
         L.timeouts = h->flags + 2;
     }
     if (final_) {
+        L.reprojMisses = h->flags + 3;
         const int parity = (int)(h->frameNo & 1);
         if (h->band.owns_frame_image) L.image = (uint2*)h->frameImage[parity];
         else if (imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached && h->peer[SGI_PEER_ROOT].info.off_image[parity] >= 0)
@@ -209,13 +210,29 @@ int sgi_band_setup(SgiHandle h, const SgiBandParams* bp) {
         h->lastError = "sgi_band_setup: y_offset, compute_y0 and compute_rows must be multiples of 5 (tiles never straddle bands)";
         return SGI_ERR_INVALID_ARG;
     }
+    {
+        // an inner edge must hold at least the reach of the widest à-trous pass, 2*(multiplier+1) = 2^iters rows (BE:1920): the
+        // neighbour fills exactly the held rows beyond the computed ones, and taps beyond them would be clamped silently
+        const int iters = h->cp.denoise_iters;
+        const int reach = iters > 1 ? 2 * (1 << (iters - 1)) : 0;
+        const int top = bp->compute_y0 - y0, bottom = y1 - (bp->compute_y0 + bp->compute_rows);
+        if ((bp->rank > 0 && top < reach) || (bp->rank + 1 < bp->world && bottom < reach)) {
+            h->lastError = "sgi_band_setup: an inner edge holds fewer halo rows than the à-trous reach 2^denoise_iters (SGI_HALO_ROWS covers 4 iterations)";
+            return SGI_ERR_INVALID_ARG;
+        }
+    }
     SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
     SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
     SGI_CUDA_B(h, cudaStreamSynchronize(h->copyStream));
     detachPeers(h);
     h->banded = true;
     h->band = *bp;
-    return sgiAllocPlanesForBand(h);
+    const int rc = sgiAllocPlanesForBand(h);
+    if (rc != SGI_OK) return rc;
+    // the slab (flags and halo rows) is zeroed on the stream: that must have happened before a neighbour that attaches after this
+    // call returns can store pass-0 rows or raise a flag in it
+    SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
+    return SGI_OK;
 }
 
 int sgi_band_export(SgiHandle h, SgiPeerInfo* out) {
@@ -241,6 +258,13 @@ int sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer) {
     if (!h->banded) { h->lastError = "sgi_band_attach: call sgi_band_setup first"; return SGI_ERR_INVALID_ARG; }
     if (which == SGI_PEER_UP && peer->rank != h->band.rank - 1) { h->lastError = "sgi_band_attach: SGI_PEER_UP must be band rank-1"; return SGI_ERR_INVALID_ARG; }
     if (which == SGI_PEER_DOWN && peer->rank != h->band.rank + 1) { h->lastError = "sgi_band_attach: SGI_PEER_DOWN must be band rank+1"; return SGI_ERR_INVALID_ARG; }
+    if (which != SGI_PEER_ROOT) {
+        // the neighbour's halo on my side is filled by MY kernels from the rows I compute: it may not reach beyond them
+        const int myC0 = h->band.compute_y0, myC1 = h->band.compute_y0 + h->band.compute_rows;
+        const bool ok = which == SGI_PEER_UP ? (peer->compute_y0 + peer->compute_rows == myC0 && peer->y_offset + peer->rows <= myC1)
+                                             : (peer->compute_y0 == myC1 && peer->y_offset >= myC0);
+        if (!ok) { h->lastError = "sgi_band_attach: the neighbour's computed rows must adjoin mine and its halo may not be taller than my band"; return SGI_ERR_INVALID_ARG; }
+    }
     SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
     SgiHandle_::Peer& p = h->peer[which];
     if (p.attached) { h->lastError = "sgi_band_attach: peer already attached"; return SGI_ERR_INVALID_ARG; }
@@ -292,6 +316,17 @@ int sgi_band_timeouts(SgiHandle h, int32_t* out_count) {
     if (!h->banded) return SGI_OK;
     SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
     SGI_CUDA_B(h, cudaMemcpyAsync(h->pinnedCount, h->flags + 2, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
+    *out_count = *h->pinnedCount;
+    return SGI_OK;
+}
+
+int sgi_band_reprojection_misses(SgiHandle h, int32_t* out_count) {
+    if (!h || !out_count) return SGI_ERR_INVALID_ARG;
+    *out_count = 0;
+    if (!h->banded) return SGI_OK;
+    SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA_B(h, cudaMemcpyAsync(h->pinnedCount, h->flags + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
     *out_count = *h->pinnedCount;
     return SGI_OK;

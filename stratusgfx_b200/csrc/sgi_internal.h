@@ -36,6 +36,9 @@ struct BandLinks {
     const int32_t* waitDown;   // this handle's flags[1] (written by the band below) or nullptr
     int waitEpoch;
     int32_t* timeouts;
+    // final pass of a band: reprojected previous-frame taps (vpl_pbr_gi_denoise.fs:280,352-360) that fall outside the rows this
+    // handle holds are clamped to them and counted here (sgi_band_reprojection_misses); nullptr on whole-frame handles
+    int32_t* reprojMisses;
     // in-kernel signal: the CTAs (gather: 32-pixel row segments) that store rows into a neighbour's halo are scheduled first and
     // counted; the last of them releases the neighbours' flags, so the neighbours see this pass's boundary rows a pass-time
     // before they need them and ranks no longer wait for each other stage by stage.  doneCounter == nullptr: the host
@@ -274,7 +277,7 @@ int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
 int waitAllBands(SgiHandle_* h, int64_t frameNo);
 bool imagePushByKernel();
 void detachPeers(SgiHandle_* h);
-constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [4] producer counter of the in-kernel signal, [8+r] band r's image rows landed
+constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [3] reprojection taps outside the held rows, [4] producer counter of the in-kernel signal, [8+r] band r's image rows landed
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
 int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int epoch, int32_t* timeouts);
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);

@@ -58,6 +58,7 @@ def load_library():
     L.sgi_band_attach.argtypes = [H, C.c_int32, C.POINTER(PeerInfo)]
     L.sgi_frame_image.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.sgi_band_timeouts.argtypes = [H, C.POINTER(C.c_int32)]
+    L.sgi_band_reprojection_misses.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_visible_count.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_get_plane.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.sgi_download_plane.argtypes = [H, C.c_int32, C.c_void_p, C.c_int64]
@@ -311,6 +312,12 @@ class VplGiPass:
     def band_timeouts(self):
         n = C.c_int32()
         self._check(self.L.sgi_band_timeouts(self._h, C.byref(n)))
+        return n.value
+
+    def band_reprojection_misses(self):
+        """Reprojected previous-frame taps of the final passes so far that fell outside the held rows (halo shorter than the motion)."""
+        n = C.c_int32()
+        self._check(self.L.sgi_band_reprojection_misses(self._h, C.byref(n)))
         return n.value
 
     def frame_image(self):
