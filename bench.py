@@ -9,9 +9,13 @@ Metric: Gpixel·VPL/s = W·H·N_vpl / t_frame / 1e9, ms_per_ste
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4] [--impl ours|reference]
 
 N > 1 is launched by torchrun, one rank per GPU; the frame is split into horizontal row bands
-(SURVEY.md §8e): every step rank 0 broadcasts the VPL table and the frame's refreshed cube maps
-over NCCL, each rank runs its band (+ a 30-row apron so the à-trous passes need no halo exchange),
-and the lit bands are gathered to rank 0 — strong scaling of one frame.
+ — strong scaling of one frame.  Every step rank 0 broadcasts the VPL table and
+the frame's refreshed cube maps over NCCL (one packed buffer, issued a frame ahead); each rank runs the pass
+on its band, whose halo rows the neighbouring bands' kernels fill through NVLink peer stores ordered by epoch
+flags (csrc/sgi_band.cu); the lit rows of every band travel to rank 0's frame image by copy-engine transfers.
+After the timed region rank 0 replays the same frames on one whole-frame handle and compares the assembled
+image with it byte for byte ("image_equals_single_gpu").  `--bands apron` is the exchange-free comparison
+(30 redundant rows per inner edge + an NCCL gather), `--split views` gives every GPU its own camera view.
 """
 import argparse
 import ctypes
@@ -276,9 +280,28 @@ def cpu_arm(scene, steps, warmup):
         return r
 
 
+def set_host_threads(share=1):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank.  The CPU arm is one process on rank 0 and uses every core this process may
+    run on (share = 1); the ranks of a multi-GPU run split the cores between them for the procedural scene generation (share =
+    world), which is host-side set-up outside every timed region.  Returns the thread count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = max(1, n // max(1, share))
+    os.environ["OMP_NUM_THREADS"] = str(n)          # read by libgomp when the host libraries are loaded
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)      # and for a runtime that is already initialised
+    except OSError:
+        pass
+    return n
+
+
+def use_all_host_cores():
+    return set_host_threads(1)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    use_all_host_cores()
     from stratusgfx_b200.scene import Scene
     scene = Scene(args.workload)
     r = cpu_arm(scene, args.steps, args.warmup)
@@ -304,6 +327,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        set_host_threads(world)
     scene = Scene(args.workload)
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
     p2p = world > 1 and args.bands == "p2p"
@@ -435,6 +459,8 @@ def run_ours(args, rank, world, local_rank):
         time.sleep(0.25)
     launches0 = gp.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if p2p:
+        gp.band_stats()                       # restart the account of in-kernel waits: only the timed region is reported
     fence()
     if rank == 0:
         sampler.mark_begin()
@@ -459,6 +485,39 @@ def run_ours(args, rank, world, local_rank):
     value = W * H * N / (ms_step * 1e-3) / 1e9
     V = gp.visible_count()
     band_timeouts = gp.band_timeouts() if p2p else 0
+    band_spin = None
+    if p2p:
+        # in-kernel waits of the timed region that found a neighbour's flag behind, per rank: count per frame, summed and longest
+        # wait in microseconds (waits of different CTAs overlap, so the sum is an upper bound of the time lost)
+        st = gp.band_stats()
+        khz = (clocks or {}).get("sm_mhz") or 1965.0
+        mine = {"rank": rank, "waits_per_frame": round(st["waits_that_spun"] / args.steps, 2),
+                "spin_sum_us_per_frame": round(st["spin_sum_kcycles"] * 1024 / khz / args.steps, 2),
+                "spin_max_us": round(st["spin_max_kcycles"] * 1024 / khz, 2), "host_enqueue_ms": round(host_enqueue_ms, 4)}
+        band_spin = [None] * world
+        dist.all_gather_object(band_spin, mine)
+
+    # ---- the assembled image against one GPU: rank 0 replays the same frames (same `time` sequence, hence the same temporal
+    # history) on a whole-frame handle and compares the lit image byte for byte ----
+    image_equal = None
+    if world > 1 and not args.no_image_check:
+        if rank == 0:
+            set_host_threads(1)               # the other ranks idle at the barrier below
+            img = (gp.frame_image() if p2p else full_out).clone()
+            one = VplGiPass(W, H, 0, H, scene.cube_res, scene.csm_res, iters, device=local_rank, use_torch_stream=True)
+            one.set_gbuffer(scene.gbuffer(0), scene.gbuffer(-1)); one.set_vpls(vd, at); one.set_atlases(sh, df); one.set_csm(csm); one.bind()
+            fp1 = scene.frame_params(0)
+            for i in range(args.warmup + args.steps):
+                fp1.time = 1000.0 + 16.0 * i
+                one.frame(fp1)
+            one.synchronize(); torch.cuda.synchronize(dev)
+            ref_img = one.t["lightingOut"]
+            a, b = img.view(torch.int16)[..., :3], ref_img.view(torch.int16)[..., :3]
+            diff = int((a != b).any(dim=-1).sum().item())
+            image_equal = {"equal": diff == 0, "pixels_differing": diff, "frames_replayed": args.warmup + args.steps}
+            one.close()
+            del img
+        fence()
 
     # ---- per-stage device times (CUDA events on the launching stream), for the roofline ----
     stages, stage_launches = {}, {}
@@ -537,7 +596,7 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": d["gbs"], "peak": peak, "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_source": peak_src, "share_of_step": round(stages[dom] / sum(stages.values()), 4),
-                    "frame_algorithmic_bytes": int(ab["frame"]), "frame_hbm_frac": round(ab["frame"] / (sum(stages.values()) * 1e-3) / 1e9 / peak, 4),
+                    "frame_algorithmic_bytes": int(ab["frame"]), "frame_hbm_frac": round(ab["frame"] / (ms_step * 1e-3) / 1e9 / peak, 4),
                     "note": "the dominant kernel is FP32-issue/L1 bound, not HBM bound (DESIGN.md section 3); frac is its algorithmic bytes against the measured HBM peak"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -546,6 +605,7 @@ def run_ours(args, rank, world, local_rank):
                                f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of VPL table + 5 cube maps per frame ({'issued one frame ahead' if prefetch else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
                                f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
                            "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
+                           "image_equals_single_gpu": (image_equal or {}).get("equal"), "image_check": image_equal, "band_spin": band_spin,
                            "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log,
                            "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
                 "clocks": clocks,
@@ -555,6 +615,7 @@ def run_ours(args, rank, world, local_rank):
                 "roofline": roofline,
                 "stages": per_stage}
         if world == 1 and not args.no_cpu_baseline:
+            use_all_host_cores()
             r = cpu_arm(scene, 1, 1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "port_value") if k in r}
         else:
@@ -580,6 +641,7 @@ def run_views(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        set_host_threads(world)
     scene = Scene(args.workload, yaw_deg_per_frame=3.0)
     view = rank                                       # frame index = view index: 3 degrees of yaw apart
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
@@ -655,6 +717,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--balance", type=int, default=2, help="measured band-balancing rounds before the timed region (N > 1)")
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
+    ap.add_argument("--no-image-check", action="store_true", help="N > 1: skip the byte comparison of the assembled image with a single-GPU replay")
     ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")
     ap.add_argument("--bands", default="p2p", choices=["p2p", "apron"], help="multi-GPU halo strategy (N > 1)")
     args = ap.parse_args()

@@ -215,6 +215,29 @@ typedef struct SgiPrepassParams {
     int32_t*       countOut;           /* device int32: N = min(lights in the frustum, 10000)                         */
 } SgiPrepassParams;
 
+/* ---- VPL cube shadow / diffuse map production: the producer of the atlases the gather and the
+ *      colouring stage read.  Replaces the per-light loop of UpdatePointLights_ (BE:1426-1575: clear the light's cube layer to
+ *      depth 1 / colour 0, six 90-degree views through shadow.vs, fragments through shadowVpl.fs:16-36) for scenes handed over
+ *      as a list of axis-aligned boxes — the geometry of this repository's procedural workloads.  A texel's fragment is found by
+ *      casting the ray through the texel centre (the inverse of the cube-face table) instead of by
+ *      rasterising triangles; its value is the shader's: depth = saturate(length(fsPosition - lightPos) / farPlane) stored as
+ *      unorm16, colour = the surface's base colour stored as unorm8.  A ray that hits nothing keeps the cleared texel. */
+typedef struct SgiSceneBox {       /* 32 bytes */
+    float   lo[3];
+    float   hi[3];
+    uint8_t albedo[4];             /* rgb used, a ignored (the diffuse texel is written with a = 255)         */
+    int32_t insideOut;             /* 1: the box is a room seen from inside (its far faces are the surfaces)   */
+} SgiSceneBox;
+
+typedef struct SgiCubeRenderParams {
+    int32_t numBoxes;                  /* <= SGI_MAX_SCENE_BOXES                                                     */
+    int32_t numMaps;                   /* lights whose maps are rendered by this call (maxShadowUpdatesPerFrame = 5
+                                          per frame in the reference, StratusRendererBackend.h:378; any count here)  */
+    const SgiSceneBox* boxes;          /* device [numBoxes]                                                          */
+    const int32_t* vplIndices;         /* device [numMaps]: indices into the bound vplData / atlasEntryByVpl tables  */
+} SgiCubeRenderParams;
+#define SGI_MAX_SCENE_BOXES 256
+
 typedef struct SgiHandle_* SgiHandle;
 
 /* ---- multi-GPU row bands with peer-to-peer halos (no reference counterpart — the
@@ -258,6 +281,10 @@ int  sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers);
 /* GL-interop hand-over (GLuint names).  Returns SGI_ERR_UNSUPPORTED when the
  * library was built without GL headers (this image has none). */
 int  sgi_register_gl(SgiHandle h, const uint32_t* gl_names, int32_t count);
+
+/* renders the cube_res^2 x 6 depth and diffuse maps of the listed lights into their atlas layers (the bound shadowCubeMaps /
+ * diffuseCubeMaps at atlasEntryByVpl[vplIndices[k]]); stream-ordered, needs vplData, atlasEntryByVpl and the atlases bound */
+int  sgi_render_vpl_cubemaps(SgiHandle h, const SgiCubeRenderParams* rp);
 
 /* ---- deferred direct lighting: pbr.fs, the pass whose output is the `screen` plane of this path ----
  * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_direct.cu). */
@@ -345,6 +372,10 @@ int  sgi_band_attach(SgiHandle h, int32_t which, const SgiPeerInfo* peer);
 int  sgi_frame_image(SgiHandle h, void** out_ptr, int64_t* out_bytes);
 /* nonzero when a peer wait timed out since creation (a neighbour died or never signalled) */
 int  sgi_band_timeouts(SgiHandle h, int32_t* out_count);
+/* Diagnostics of the band protocol (blocking).  out[0], out[1]: last epochs received from the upper / lower neighbour; out[2]:
+ * time-outs; out[3]: reprojection misses; out[5], out[6], out[7]: in-kernel waits since the last call that found the neighbour's
+ * flag behind — how many, their summed and their longest duration, in units of 1024 SM clock cycles. */
+int  sgi_band_stats(SgiHandle h, int32_t out[8]);
 /* Motion limit of a band.  The final denoise pass reads the PREVIOUS frame's normal / depth / id / GI / history at
  * uv - velocity (vpl_pbr_gi_denoise.fs:280,352-360).  A band only has the rows it holds: its own, plus the halo rows, whose
  * G-buffer the caller supplies and whose GI / history the neighbour's final pass stores.  The halo height is the caller's

@@ -127,8 +127,9 @@ PRELUDE = r'''// GENERATED by oracle/make_ref_glsl.py from the reference's GLSL 
 #include <cmath>
 #include <cstddef>
 #include <cstring>
-#include <pthread.h>
-#include <thread>
+#include <omp.h>
+#include <ucontext.h>
+#include <memory>
 #include <vector>
 namespace refglsl {
 using namespace glm;
@@ -580,30 +581,67 @@ typedef struct RefCullArgs {
     int totalNumLights, csmRes; const float* sunDir; const float* cascadeProjViews; const float* cascadePlanes; const float* csm;
     const void* lightData; void* updatedLightData; int* vplVisibleIndex;
 } RefCullArgs;
-static pthread_barrier_t g_cullBarrier;
-static void cullBarrierWait() { pthread_barrier_wait(&g_cullBarrier); }
+// viscull_vpls.cs is ONE work group of 1024 invocations with four barrier()s (BE:1603).  The invocations run as coroutines
+// (ucontext) spread over the OpenMP pool: barrier() yields to the pool thread's scheduler, which resumes its next invocation and,
+// once all of its invocations have arrived, meets the other pool threads at a real barrier.  (An earlier version created 1024 OS
+// threads per frame, which cost more than the shader's own work.)
+struct CullCo { ucontext_t ctx; unsigned t; bool done; std::unique_ptr<char[]> stack; };
+static const size_t kCullStack = 128 * 1024;
+static thread_local ucontext_t* g_coSched = nullptr;
+static thread_local CullCo* g_coCur = nullptr;
+static int g_cullAlive = 0;
+static void cullCoYield() { swapcontext(&g_coCur->ctx, g_coSched); }
+static void cullCoEntry() {
+    refglsl::cs_cull::cull_main();
+    g_coCur->done = true;
+    swapcontext(&g_coCur->ctx, g_coSched);
+}
 void refglsl_cull(const RefCullArgs* a) {
     using namespace refglsl;
     cs_cull::totalNumLights = a->totalNumLights; cs_cull::lightData = (const VplData*)a->lightData;
     cs_cull::updatedLightData = (VplData*)a->updatedLightData; cs_cull::vplVisibleIndex = a->vplVisibleIndex;
     const unsigned n = 1024;                                                 // one work group of local_size_x = 1024 (BE:1603)
-    pthread_barrier_init(&g_cullBarrier, nullptr, n);
-    barrierHook = cullBarrierWait;
-    std::vector<std::thread> threads;
-    for (unsigned t = 0; t < n; ++t)
-        threads.emplace_back([t, a]() {
-            // the uniforms are per thread (see PERINV): every invocation's thread sets its own copy
-            infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
-            for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
-            for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
-            infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
-            gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
-            gl_LocalInvocationID = gl_GlobalInvocationID = glm::uvec3(t, 0, 0); gl_LocalInvocationIndex = t;
-            cs_cull::cull_main();
-        });
-    for (auto& th : threads) th.join();
+    barrierHook = cullCoYield;
+    #pragma omp parallel
+    {
+        // the uniforms are per thread (see PERINV): every pool thread sets its own copy
+        infiniteLightDirection = glm::vec3(a->sunDir[0], a->sunDir[1], a->sunDir[2]);
+        for (int c = 0; c < 4; ++c) std::memcpy(&cascadeProjViews[c][0][0], a->cascadeProjViews + 16 * c, 64);
+        for (int c = 0; c < 3; ++c) cascadePlanes[c] = glm::vec4(a->cascadePlanes[4 * c], a->cascadePlanes[4 * c + 1], a->cascadePlanes[4 * c + 2], a->cascadePlanes[4 * c + 3]);
+        infiniteLightShadowMap.data = a->csm; infiniteLightShadowMap.res = a->csmRes; infiniteLightShadowMap.layers = 4;
+        gl_NumWorkGroups = glm::uvec3(1, 1, 1); gl_WorkGroupSize = glm::uvec3(1024, 1, 1); gl_WorkGroupID = glm::uvec3(0);
+        const unsigned nt = (unsigned)omp_get_num_threads(), id = (unsigned)omp_get_thread_num();
+        std::vector<CullCo> cos((n + nt - 1 - id) / nt);
+        ucontext_t sched;
+        g_coSched = &sched;
+        for (size_t k = 0; k < cos.size(); ++k) {
+            CullCo& co = cos[k];
+            co.t = id + (unsigned)k * nt; co.done = false; co.stack.reset(new char[kCullStack]);             // uninitialised on purpose
+            getcontext(&co.ctx);
+            co.ctx.uc_stack.ss_sp = co.stack.get(); co.ctx.uc_stack.ss_size = kCullStack; co.ctx.uc_link = &sched;
+            makecontext(&co.ctx, cullCoEntry, 0);
+        }
+        for (;;) {
+            #pragma omp single
+            g_cullAlive = 0;
+            int alive = 0;
+            for (CullCo& co : cos) {
+                if (co.done) continue;
+                g_coCur = &co;
+                gl_LocalInvocationID = gl_GlobalInvocationID = glm::uvec3(co.t, 0, 0); gl_LocalInvocationIndex = co.t;
+                swapcontext(&sched, &co.ctx);                  // runs until the invocation's next barrier() or its end
+                if (!co.done) ++alive;
+            }
+            #pragma omp atomic
+            g_cullAlive += alive;
+            #pragma omp barrier
+            const bool more = g_cullAlive != 0;                // the same on every pool thread (barriers sit in uniform control flow)
+            #pragma omp barrier
+            if (!more) break;
+        }
+        g_coSched = nullptr; g_coCur = nullptr;
+    }
     barrierHook = nullptr;
-    pthread_barrier_destroy(&g_cullBarrier);
 }
 }
 '''

@@ -795,4 +795,71 @@ int orc_denoise_pass(const SgiFrameParams* fp, const OrcDims* dm, const OrcDenoi
     return 0;
 }
 
+// ---- widening row f2: VPL cube shadow / diffuse map production (BE:1426-1575, shadowVpl.fs:16-36) ------------------------------
+// The reference rasterises the scene's meshes six times per light; here the scene is a list of axis-aligned boxes and the fragment
+// of a texel is found by casting the ray through the texel centre (inverse of the cube-face table).  That
+// part has no reference text (a rasteriser is fixed function); everything from the fragment on is shadowVpl.fs:
+//     lightDistance = length(fsPosition.xyz - lightPos);  lightDistance = saturate(lightDistance / farPlane);  (:27-30)
+//     gl_FragDepth = lightDistance;  color = baseColor.rgb;                                                      (:33-35)
+// stored as unorm16 depth (round to nearest) and unorm8 colour.  Cleared texels (no hit): depth 1, colour 0 (BE:1452-1456).
+inline vec3 cubeTexelDirection(int face, float sc, float tc) {
+    switch (face) {       // inverse of GL 4.6 table 8.19
+        case 0: return vec3(1.0f, -tc, -sc);
+        case 1: return vec3(-1.0f, -tc, sc);
+        case 2: return vec3(sc, 1.0f, tc);
+        case 3: return vec3(sc, -1.0f, -tc);
+        case 4: return vec3(sc, -tc, 1.0f);
+        default: return vec3(-sc, -tc, -1.0f);
+    }
+}
+inline float shadowVplDepth(vec3 fsPosition, vec3 lightPos, float farPlane) {      // shadowVpl.fs:27-30
+    float lightDistance = length(fsPosition - lightPos);
+    lightDistance = saturate(lightDistance / farPlane);
+    return lightDistance;
+}
+float orc_shadow_vpl_depth(const float* fsPosition3, const float* lightPos3, float farPlane) {
+    return shadowVplDepth(vec3(fsPosition3[0], fsPosition3[1], fsPosition3[2]), vec3(lightPos3[0], lightPos3[1], lightPos3[2]), farPlane);
+}
+int orc_render_vpl_cubemaps(const SgiSceneBox* boxes, int numBoxes, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
+                            const int32_t* vplIndices, int numMaps, int res, void* const* shadowAtlases, void* const* diffuseAtlases) {
+    const float fres = (float)res;
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int m = 0; m < numMaps * 6; ++m) {
+        const int k = vplIndices[m / 6], face = m % 6;
+        const SgiVplData& v = lightData[k];
+        const SgiAtlasEntry e = atlasByVpl[k];
+        const vec3 o(v.position[0], v.position[1], v.position[2]);
+        uint16_t* depth = (uint16_t*)shadowAtlases[e.index] + ((size_t)e.layer * 6 + face) * res * res;
+        uint8_t* diffuse = (uint8_t*)diffuseAtlases[e.index] + ((size_t)e.layer * 6 + face) * res * res * 4;
+        for (int j = 0; j < res; ++j) for (int i = 0; i < res; ++i) {
+            const float sc = 2.0f * (((float)i + 0.5f) / fres) - 1.0f, tc = 2.0f * (((float)j + 0.5f) / fres) - 1.0f;
+            const vec3 d = cubeTexelDirection(face, sc, tc);
+            float best = 3.402823466e+38f; int hit = -1;
+            for (int b = 0; b < numBoxes; ++b) {
+                const SgiSceneBox& bx = boxes[b];
+                float t0 = -3.402823466e+38f, t1 = 3.402823466e+38f; bool miss = false;
+                for (int a = 0; a < 3; ++a) {
+                    if (d[a] == 0.0f) { if (o[a] < bx.lo[a] || o[a] > bx.hi[a]) miss = true; continue; }
+                    const float inv = 1.0f / d[a];
+                    float ta = (bx.lo[a] - o[a]) * inv, tb = (bx.hi[a] - o[a]) * inv;
+                    if (ta > tb) { const float tmp = ta; ta = tb; tb = tmp; }
+                    if (ta > t0) t0 = ta;
+                    if (tb < t1) t1 = tb;
+                }
+                if (miss || t0 > t1) continue;
+                const float t = bx.insideOut ? t1 : t0;
+                if (t > 1e-6f && t < best) { best = t; hit = b; }
+            }
+            const size_t q = (size_t)j * res + i;
+            if (hit < 0) { depth[q] = 65535; diffuse[q * 4 + 0] = diffuse[q * 4 + 1] = diffuse[q * 4 + 2] = diffuse[q * 4 + 3] = 0; continue; }
+            const vec3 fsPosition = o + d * best;
+            const float z = shadowVplDepth(fsPosition, o, v.farPlane);
+            depth[q] = (uint16_t)floor(z * 65535.0f + 0.5f);
+            for (int c = 0; c < 3; ++c) diffuse[q * 4 + c] = boxes[hit].albedo[c];
+            diffuse[q * 4 + 3] = 255;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -99,6 +99,17 @@ class TaaParams(C.Structure):
     _fields_ = [("screen", C.c_void_p), ("prevScreen", C.c_void_p), ("velocity", C.c_void_p), ("colorOut", C.c_void_p), ("historyOut", C.c_void_p)]
 
 
+MAX_SCENE_BOXES = 256
+
+
+class SceneBox(C.Structure):
+    _fields_ = [("lo", C.c_float * 3), ("hi", C.c_float * 3), ("albedo", C.c_uint8 * 4), ("insideOut", C.c_int32)]
+
+
+class CubeRenderParams(C.Structure):
+    _fields_ = [("numBoxes", C.c_int32), ("numMaps", C.c_int32), ("boxes", C.c_void_p), ("vplIndices", C.c_void_p)]
+
+
 class PrepassParams(C.Structure):
     _fields_ = [("viewPosition", C.c_float * 3), ("numLights", C.c_int32), ("frustumPlanes", (C.c_float * 4) * 6),
                 ("lights", C.c_void_p), ("vplDataOut", C.c_void_p), ("atlasEntryOut", C.c_void_p), ("orderOut", C.c_void_p),
@@ -123,8 +134,8 @@ class PeerInfo(C.Structure):
 
 ABI_SYMBOLS = [
     "sgi_create", "sgi_destroy", "sgi_resize", "sgi_bind_device_buffers", "sgi_register_gl",
-    "sgi_band_setup", "sgi_band_export", "sgi_band_attach", "sgi_frame_image", "sgi_band_timeouts", "sgi_band_reprojection_misses",
-    "sgi_vpl_prepass", "sgi_direct_lighting", "sgi_ssao", "sgi_taa", "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
+    "sgi_band_setup", "sgi_band_export", "sgi_band_attach", "sgi_frame_image", "sgi_band_timeouts", "sgi_band_reprojection_misses", "sgi_band_stats",
+    "sgi_vpl_prepass", "sgi_render_vpl_cubemaps", "sgi_direct_lighting", "sgi_ssao", "sgi_taa", "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
     "sgi_visible_count", "sgi_get_plane", "sgi_download_plane", "sgi_reset_history", "sgi_synchronize", "sgi_stream",
     "sgi_launch_count", "sgi_last_error", "sgi_version",
 ]

@@ -171,14 +171,6 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 
-// -DSGI_ATROUS_V2 (experiment, off by default; results are bit-identical by construction): 32-bit element indices for the tap
-// addresses (one IMAD.WIDE per load instead of an LEA pair; a band never holds 2^32 pixels) and the four accumulations of a
-// tap as two packed fma.rn.f32x2 (FFMA2 on sm_100a; IEEE per lane, and fma(w, 1, a) == a + w)
-SGI_DEV unsigned long long pack2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-SGI_DEV void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-SGI_DEV unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
-}
 SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -203,73 +195,50 @@ __device__ __forceinline__ int boundaryFirst(int p, int n) {
     return p == 0 ? 0 : (p == 1 ? n - 1 : (p == 2 ? n - 2 : p - 2));
 }
 
-#ifdef SGI_ATROUS_V3
-// -DSGI_ATROUS_V3 (experiment, off by default; results are bit-identical by construction — same taps, same order, same
-// arithmetic): the tap spacing of the reference's passes (2, 4, 8) is a template parameter, and a thread whose (kLat+4) x 5 taps
-// all lie inside the held rows and columns (no CLAMP_TO_EDGE: every thread but those within 2 taps of an edge) addresses them as
-// one row pointer per plane, advanced by a constant stride, plus IMMEDIATE column offsets — instead of a clamp, an index and a
-// 64-bit LEA pair per load (~200 of the kernel's ~2200 instructions per thread).
+// The tap spacing of the reference's passes (2, 4, 8: multiplier 1, 3, 7, BE:1920) is a template parameter; S = 0 reads it from the
+// pass parameters (other iteration counts).  A thread whose (kLat+4) x 5 taps all lie inside the held rows and columns — every
+// thread but those within two taps of an edge — addresses them as one row pointer per plane, advanced by a constant stride, plus
+// IMMEDIATE column offsets; the others take the clamped path below (CLAMP_TO_EDGE).  Both paths read the same taps in the same
+// order with the same arithmetic, so their outputs are the same bytes.  (Round 2 A/B on c4, profiles/r02a: 0.166 -> 0.148 ms per
+// non-final pass against per-tap clamps and 64-bit index arithmetic on every thread.)
+SGI_DEV void atrousTap(const float4 (&cen)[kLat], float (&acc)[kLat][4], int c, int d, float4 gq, uint2 rv) {
+    // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly
+    const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
+    const float tq = gq.w * kLog2e;
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) {
+        const int dy = c - 2 - k;
+        if (dy < -2 || dy > 2) continue;
+        float w = 1.0f;                              // centre tap (:156)
+        if (dy != 0 || d != 2) {
+            // max(0, n.n')^128 * exp(-|z - z'|)   (sigmaN = 128, sigmaZ = 1, :93-98, :169-173)
+            const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
+            w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
+        }
+        acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
+        acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
+    }
+}
 template <int S>
 SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
     const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
     const uint2* __restrict__ rowS = io.shadowsIn + ((size_t)firstRow * W + x);
     const size_t stride = (size_t)S * W;
-#ifdef SGI_ATROUS_V2
-    unsigned long long accRG[kLat], accBW[kLat];            // with -DSGI_ATROUS_V2 as well: packed (r, g) and (b, sum of weights)
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) { accRG[k] = pack2(0.0f, 0.0f); accBW[k] = pack2(0.0f, 0.0f); }
-#endif
     #pragma unroll
     for (int c = 0; c < kLat + 4; ++c) {
         #pragma unroll
-        for (int d = 0; d < 5; ++d) {
-            const float4 gq = __ldg(rowG + (d - 2) * S);
-            const uint2 rv = __ldg(rowS + (d - 2) * S);
-            const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
-            const float tq = gq.w * kLog2e;
-#ifdef SGI_ATROUS_V2
-            const unsigned long long cRG = pack2(rr, rg), cB1 = pack2(rb, 1.0f);
-#endif
-            #pragma unroll
-            for (int k = 0; k < kLat; ++k) {
-                const int dy = c - 2 - k;
-                if (dy < -2 || dy > 2) continue;
-                float w = 1.0f;
-                if (dy != 0 || d != 2) {
-                    const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
-                    w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
-                }
-#ifdef SGI_ATROUS_V2
-                const unsigned long long ww = pack2(w, w);
-                accRG[k] = fma2(ww, cRG, accRG[k]); accBW[k] = fma2(ww, cB1, accBW[k]);
-#else
-                acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
-                acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
-#endif
-            }
-        }
+        for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + (d - 2) * S), __ldg(rowS + (d - 2) * S));
         rowG += stride; rowS += stride;
     }
-#ifdef SGI_ATROUS_V2
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) { unpack2(accRG[k], acc[k][0], acc[k][1]); unpack2(accBW[k], acc[k][2], acc[k][3]); }
-#endif
 }
-template <bool FINAL, int S>                                 // S = 0: the spacing is read from the pass parameters
-#else
-template <bool FINAL>
-#endif
+template <bool FINAL, int S>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
-    SGI_PDL_WAIT();                                          // (experiment, see sgi_internal.h) the previous pass / the gather is complete from here on
+    SGI_PDL_WAIT();                                          // (chained launches, sgi_internal.h) the previous pass / the gather is complete from here on
     SGI_PDL_LAUNCH_DEPENDENTS();
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
-#ifdef SGI_ATROUS_V3
-    const int s = S ? S : 1 + io.multiplier;
-#else
-    const int s = 1 + io.multiplier;                         // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
-#endif
+    const int s = S ? S : 1 + io.multiplier;                 // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
     const int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
     const int t = by * kDnY + threadIdx.y;                   // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
@@ -294,82 +263,30 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     }
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
     float acc[kLat][4];
-#ifdef SGI_ATROUS_V2
-    unsigned long long accRG[kLat], accBW[kLat];            // packed (r, g) and (b, sum of weights)
-#endif
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
         const int ly = min(c0 + (m0 + k) * s + r, rows - 1);
         cen[k] = __ldg(io.guide + (size_t)ly * W + x);
         cen[k].w *= kLog2e;
         acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
-#ifdef SGI_ATROUS_V2
-        accRG[k] = pack2(0.0f, 0.0f); accBW[k] = pack2(0.0f, 0.0f);
-#endif
     }
-#ifdef SGI_ATROUS_V3
     const int firstRow = c0 + (m0 - 2) * s + r;              // row of tap line c = 0; the last one is firstRow + (kLat + 3) * s
     const bool interior = S != 0 && x >= 2 * s && x + 2 * s < W && firstRow >= 0 && firstRow + (kLat + 3) * s < rows;
     if (interior) atrousTapsInterior<(S ? S : 1)>(io, W, firstRow, x, cen, acc);
     else {
-#endif
-    int txs[5];
-    #pragma unroll
-    for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
-
-    #pragma unroll
-    for (int c = 0; c < kLat + 4; ++c) {
-        // band-local clamp == CLAMP_TO_EDGE on a whole frame
-#ifdef SGI_ATROUS_V2
-        const unsigned int rowBase = (unsigned int)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * (unsigned int)W;
-#else
-        const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
-        const float4* __restrict__ rowG = io.guide + rowBase;
-        const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
-#endif
+        int txs[5];
         #pragma unroll
-        for (int d = 0; d < 5; ++d) {
-#ifdef SGI_ATROUS_V2
-            const unsigned int idx = rowBase + (unsigned int)txs[d];
-            const float4 gq = __ldg(io.guide + idx);
-            const uint2 rv = __ldg(io.shadowsIn + idx);
-#else
-            const float4 gq = __ldg(rowG + txs[d]);
-            const uint2 rv = __ldg(rowS + txs[d]);
-#endif
-            // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly
-            const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
-            const float tq = gq.w * kLog2e;
-#ifdef SGI_ATROUS_V2
-            const unsigned long long cRG = pack2(rr, rg), cB1 = pack2(rb, 1.0f);
-#endif
+        for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
+        #pragma unroll
+        for (int c = 0; c < kLat + 4; ++c) {
+            // band-local clamp == CLAMP_TO_EDGE on a whole frame
+            const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
+            const float4* __restrict__ rowG = io.guide + rowBase;
+            const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
             #pragma unroll
-            for (int k = 0; k < kLat; ++k) {
-                const int dy = c - 2 - k;
-                if (dy < -2 || dy > 2) continue;
-                float w = 1.0f;                              // centre tap (:156)
-                if (dy != 0 || d != 2) {
-                    // max(0, n.n')^128 * exp(-|z - z'|)   (sigmaN = 128, sigmaZ = 1, :93-98, :169-173)
-                    const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
-                    w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
-                }
-#ifdef SGI_ATROUS_V2
-                const unsigned long long ww = pack2(w, w);
-                accRG[k] = fma2(ww, cRG, accRG[k]); accBW[k] = fma2(ww, cB1, accBW[k]);
-#else
-                acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
-                acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
-#endif
-            }
+            for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + txs[d]), __ldg(rowS + txs[d]));
         }
     }
-#ifdef SGI_ATROUS_V2
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) { unpack2(accRG[k], acc[k][0], acc[k][1]); unpack2(accBW[k], acc[k][2], acc[k][3]); }
-#endif
-#ifdef SGI_ATROUS_V3
-    }   // generic (edge) path
-#endif
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
@@ -401,7 +318,6 @@ bool preloadDenoiseKernels() {
     ok = ok && cudaFuncGetAttributes(&a, prepareGuideKernel) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<false>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<true>) == cudaSuccess;
-#ifdef SGI_ATROUS_V3
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 0>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 0>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 2>) == cudaSuccess;
@@ -410,10 +326,6 @@ bool preloadDenoiseKernels() {
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 4>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 8>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true, 8>) == cudaSuccess;
-#else
-    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false>) == cudaSuccess;
-    ok = ok && cudaFuncGetAttributes(&a, atrousKernel<true>) == cudaSuccess;
-#endif
     return ok;
 }
 
@@ -448,7 +360,6 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
             if (io.links.producers == 0) io.links.doneCounter = nullptr;
             else if (signalled) *signalled = true;
         }
-#ifdef SGI_ATROUS_V3
 #define SGI_ATROUS_LAUNCH(S_)                                                                             \
         do {                                                                                              \
             void (*kf)(const FrameConsts, BandDims, const DenoiseIO) = final_ ? atrousKernel<true, S_> : atrousKernel<false, S_>; \
@@ -456,10 +367,6 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         } while (0)
         if (s == 2) SGI_ATROUS_LAUNCH(2); else if (s == 4) SGI_ATROUS_LAUNCH(4); else if (s == 8) SGI_ATROUS_LAUNCH(8); else SGI_ATROUS_LAUNCH(0);
 #undef SGI_ATROUS_LAUNCH
-#else
-        if (final_) SGI_LAUNCH_CHAINED(atrousKernel<true>, grid, block, 0, stream, fc, bd, io);
-        else SGI_LAUNCH_CHAINED(atrousKernel<false>, grid, block, 0, stream, fc, bd, io);
-#endif
     }
     return 1;
 }

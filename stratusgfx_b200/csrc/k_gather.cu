@@ -47,7 +47,6 @@ constexpr float PI_F = 3.14159265359f;
 constexpr float PREVENT_DIV_BY_ZERO = 0.00001f;
 constexpr float HALF_FLOAT_MAX = 65504.0f;
 constexpr float kMargin = 1e-5f;
-constexpr int kGatherThreadsX = 32, kGatherThreadsY = 8;
 
 SGI_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 SGI_DEV float rcpFast(float x) { return __fdividef(1.0f, x); }
@@ -181,9 +180,9 @@ constexpr int kTableBytesPerVpl = 48;                                // three fl
 constexpr int kTableBytesTwoCtas = 110 * 1024;                       // two CTAs per SM while 2 x (table + 1 KB reserve) <= 227 KB
 constexpr int kTileCtaX = 8, kTileCtaY = 2;                          // tiles per CTA in tile-list mode: 40 x 10 pixels, one thread per pixel
 
-template <int MODE>      // SGI_GATHER_STOCHASTIC (the reference's live shader) or SGI_GATHER_TILE_LIST
-__global__ void __launch_bounds__(MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY * 25 : kGatherThreadsX * kGatherThreadsY, MODE == SGI_GATHER_TILE_LIST ? 2 : 4)
-gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
+// ---- tile-list mode (SGI_GATHER_TILE_LIST): one thread per pixel, one CTA per 8 x 2 tiles ----------------------------------------
+__global__ void __launch_bounds__(kTileCtaX * kTileCtaY * 25, 2)
+gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
              const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
              const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
              const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
@@ -192,9 +191,9 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int ly = blockIdx.y * blockDim.y + threadIdx.y;
     // ---- tile-list mode: stage this CTA's 8x2 tiles' VPL lists through shared memory ----
-    __shared__ StagedLight sLight[MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY * SGI_MAX_VPLS_PER_TILE : 1];
-    __shared__ int sCount[MODE == SGI_GATHER_TILE_LIST ? kTileCtaX * kTileCtaY : 1];
-    if (MODE == SGI_GATHER_TILE_LIST) {
+    __shared__ StagedLight sLight[kTileCtaX * kTileCtaY * SGI_MAX_VPLS_PER_TILE];
+    __shared__ int sCount[kTileCtaX * kTileCtaY];
+    {
         const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.rows / SGI_TILE_DIVISOR;
         const int t = threadIdx.y * blockDim.x + threadIdx.x;
         if (t < kTileCtaX * kTileCtaY * SGI_MAX_VPLS_PER_TILE) {
@@ -275,43 +274,11 @@ gatherKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     }
 
     f3 vplColor = mk3(0.0f);
-    float seedZ = fc.time;
     float validSamples = 0.0f;
     const int V = __ldg(numVisible);
-    const float maxRandomIndexF = (float)(V - 1);
     const float minGi = fc.minGiOcclusionFactor;
 
-    if (MODE == SGI_GATHER_STOCHASTIC) {
-        // V <= 0: undefined in the reference (stale lights); defined here as "no light".
-        // The shader's single loop re-draws with `--i; continue;` (vpl_pbr_gi.fs:164-171).  Here the re-draws of one sample run in
-        // an inner loop (the same sequence of draws per pixel), so that the lanes of a warp reach the expensive shading part
-        // together: it then executes max-over-lanes(sampleCount) times per warp instead of max-over-lanes(samples + re-draws).
-        const uint32_t seedXY = __float_as_uint(pcx) ^ hash1(__float_as_uint(pcy));     // the draw-invariant part of hash(uvec3)
-        for (int i = 0, resamples = 0; V > 0 && i < sampleCount; ++i) {
-            const float4* L; float4 lp, rfi; f3 lightPosition, lightMinusFrag; float lightRadius, d2; int lightIndex;
-            while (true) {
-                const float rnd = floatConstruct(hash1(seedXY ^ hash1(__float_as_uint(seedZ))));     // random(vec3(gl_FragCoord.xy, time)), common.glsl:210-214
-                seedZ = fadd(seedZ, 10000.0f);
-                lightIndex = (int)fmul(maxRandomIndexF, rnd);
-                L = reinterpret_cast<const float4*>(lightData + lightIndex);
-                lp = __ldg(L);
-                rfi = __ldg(L + 3);                                 // radius, farPlane, intensity, pad
-                lightPosition = mk3(lp.x, lp.y, lp.z);
-                lightMinusFrag = lightPosition - px.fragPos;        // exact (single rounding per component)
-                lightRadius = rfi.x;
-                d2 = dotFast(lightMinusFrag, lightMinusFrag);
-                if (resamples >= 5) break;
-                if (!behindOrOutOfRange(px.normal, lightMinusFrag, d2, lightRadius)) break;
-                ++resamples;
-            }
-            const float4 lc = __ldg(L + 1);
-            const float4 sp = __ldg(L + 2);
-            SgiAtlasEntry entry; entry.index = 0; entry.layer = 0;
-            if (shadowsOn) entry = shadowIndices[lightIndex];
-            shadeAcceptedLight(px, lightPosition, lightMinusFrag, d2, lightRadius, rfi.y, mk3(lc.x, lc.y, lc.z), mk3(sp.x, sp.y, sp.z), entry, shadowsOn, minGi,
-                               cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
-        }
-    } else {
+    {
         // Tile-list mode (no live reference counterpart: the tile lookup of vpl_pbr_gi.fs:86-97 is commented out): every VPL of
         // the pixel's 5x5 tile list, in list order, through the same per-light body; a VPL behind the pixel or out of range is
         // skipped (the stochastic shader would re-draw).  Deterministic: no random numbers.
@@ -370,6 +337,7 @@ SGI_DEV void bandWaitWarp(const BandLinks& L, bool needUp, bool needDown) {
             if (up) ok = spinUntil(L.waitUp, L.waitEpoch, t0) && ok;
             if (down) ok = spinUntil(L.waitDown, L.waitEpoch, t0) && ok;
             if (!ok) atomicAdd(L.timeouts, 1);
+            bandSpinAccount(L, t0);
         }
         __syncwarp();
     }
@@ -568,8 +536,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
 // (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
 bool preloadGatherKernels() {
     cudaFuncAttributes a; bool ok = true;
-    ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_STOCHASTIC>) == cudaSuccess;
-    ok = ok && cudaFuncGetAttributes(&a, gatherKernel<SGI_GATHER_TILE_LIST>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, gatherTileListKernel) == cudaSuccess;
     // the persistent kernel keeps the VPL table in dynamic shared memory: up to 4480 x 48 B = 210 KB of the SM's 227 KB
     ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytesTwoCtas) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SGI_MAX_TOTAL_VPLS_PER_FRAME * kTableBytesPerVpl) == cudaSuccess;
@@ -589,12 +556,6 @@ static int smCount() {
     return cached[dev];
 }
 
-// SGI_GATHER_LEGACY=1 selects the one-CTA-per-32x8-pixels kernel with global-memory VPL reads (kept for A/B timing)
-static bool legacyGather() {
-    static const bool v = [] { const char* e = getenv("SGI_GATHER_LEGACY"); return e && e[0] == '1'; }();
-    return v;
-}
-
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
@@ -606,15 +567,15 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
     if (tileLists != nullptr) {
         dim3 block(kTileCtaX * SGI_TILE_DIVISOR, kTileCtaY * SGI_TILE_DIVISOR);
         dim3 grid((bd.W + block.x - 1) / block.x, (bd.rows + block.y - 1) / block.y);
-        gatherKernel<SGI_GATHER_TILE_LIST><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+        gatherTileListKernel<<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
                                                                        colorOut, reservoirOut, guideOut, mergedOut, plain, tileLists, tilePos);
-    } else if (!legacyGather()) {
+    } else {
         // persistent: every SM holds the table once (two 512-thread CTAs while two copies fit, else one 1024-thread CTA)
         const int cap = max(1, min(fc.totalNumLights, SGI_MAX_TOTAL_VPLS_PER_FRAME));
         const int bytes = cap * kTableBytesPerVpl;
         const int units = ((bd.W + 31) / 32) * bd.rows;
         // the two work counters alternate between PERSISTENT launches (each launch re-arms the other one), so the parity is
-        // counted here and not per sgi_gather call: a tile-list or legacy launch in between must not flip it
+        // counted here and not per sgi_gather call: a tile-list launch in between must not flip it
         const int counterSel = (int)((*persistentLaunches)++ & 1);
         // producers of the in-kernel signal: the 32-pixel segments of the rows pushed to a neighbour (pass 0 is pushed only when fused)
         BandLinks armed = links;
@@ -638,11 +599,6 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
             SGI_LAUNCH_CHAINED(gatherStochasticKernel<1024>, dim3(grid), dim3(1024), bytes, stream, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
                                colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
         }
-    } else {
-        dim3 block(kGatherThreadsX, kGatherThreadsY);
-        dim3 grid((bd.W + kGatherThreadsX - 1) / kGatherThreadsX, (bd.rows + kGatherThreadsY - 1) / kGatherThreadsY);
-        gatherKernel<SGI_GATHER_STOCHASTIC><<<grid, block, 0, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                                                                        colorOut, reservoirOut, guideOut, mergedOut, plain, nullptr, nullptr);
     }
     return 1;
 }

@@ -151,22 +151,6 @@ stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
 // sqrt/rcp: they only have to be conservative, and their margins (1e-4 relative; 4e-5 on the pre-test) are >100x the error
 // of either evaluation.  `posRadius` is stage 1's 16-byte packing of vplUpdatedData (entry k = (position, radius) of
 // lightData[visible[k+1]]; neither is touched by the colouring stage).
-#ifdef SGI_STAGE2_KEY64
-// -DSGI_STAGE2_KEY64 (experiment, off by default; the lists are the same by construction): a list entry is ONE 64-bit key, the
-// order-preserving integer image of the ratio (sign flipped for positive floats, all bits for negative ones) above the list
-// position, so the lexicographic (ratio, position) test of every slot of the insertion network and of the four-way merge is a
-// single unsigned 64-bit comparison instead of two float comparisons, an integer one and their combination.
-SGI_DEV unsigned long long makeKey(float ratio, int position) {
-    const unsigned int b = __float_as_uint(ratio);
-    const unsigned int m = b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
-    return ((unsigned long long)m << 32) | (unsigned int)position;
-}
-SGI_DEV float keyRatio(unsigned long long k) {
-    const unsigned int m = (unsigned int)(k >> 32);
-    return __uint_as_float(m ^ ((m & 0x80000000u) ? 0x80000000u : 0xffffffffu));
-}
-constexpr unsigned long long kEmptyKey = ((unsigned long long)(0x7f7fffffu ^ 0x80000000u) << 32) | 0x7fffffffull;      // (FLOAT_MAX, 0x7fffffff)
-#endif
 __global__ void __launch_bounds__(kS2Threads)
 stage2Kernel(int tilesX, int tileY0, int tilesY, int patchesX, int numPatches, const SgiVplStage1PerTileOutputs* __restrict__ stage1,
              const float4* __restrict__ posRadius, const int32_t* __restrict__ visible, SgiVplStage2PerTileOutputs* __restrict__ out,
@@ -264,96 +248,6 @@ stage2Kernel(int tilesX, int tileY0, int tilesY, int patchesX, int numPatches, c
         // (the first round's barrier orders the scatter before the reads of sOrder)
 
         // ---- 2./3. rounds of kS2Round candidates, nearest first ----
-#ifdef SGI_STAGE2_KEY64
-        unsigned long long key[SGI_MAX_VPLS_PER_TILE];      // (order-preserving image of the ratio) << 32 | list position
-        #pragma unroll
-        for (int i = 0; i < SGI_MAX_VPLS_PER_TILE; ++i) key[i] = kEmptyKey;
-        int count = 0;
-        float w = 1.0f, w2 = 1.0f;   // min(1, bound of the tile's 12th-best ratio) and its square: only lights with ratio at or below it can change the list
-        for (int q0 = 0; q0 < M; q0 += kS2Round) {                        // (uniform) usually one round
-            const int n = min(kS2Round, M - q0);
-            __syncthreads();                                               // the previous round's readers are done
-            if (tid < n) {
-                const int j = sOrder[q0 + tid];
-                sCand[tid] = __ldg(posRadius + j);
-                sCandPos[tid] = j;
-            }
-            __syncthreads();
-            for (int q1 = 0; q1 < n; q1 += kS2Lanes * kS2Exchange) {      // (uniform)
-                #pragma unroll
-                for (int e = 0; e < kS2Exchange; ++e) {
-                    const int q = q1 + e * kS2Lanes + g;
-                    if (q >= n || !active) continue;
-                    const float4 L = sCand[q];
-                    const float lr = L.w;
-                    const f3 lightMinusFrag = mk3(L.x, L.y, L.z) - fragPos;
-                    // cheap conservative pre-test: a light surely farther than the threshold cannot be in the tile's list
-                    const float d2e = __fmaf_rn(lightMinusFrag.z, lightMinusFrag.z, __fmaf_rn(lightMinusFrag.y, lightMinusFrag.y, lightMinusFrag.x * lightMinusFrag.x));
-                    if (d2e > lr * lr * (1.0f + 4e-5f) * w2) continue;
-                    // ... nor can one that is surely behind the tile
-                    const float se = __fmaf_rn(normal.z, lightMinusFrag.z, __fmaf_rn(normal.y, lightMinusFrag.y, normal.x * lightMinusFrag.x));
-                    if (se < 0.0f && se * se > 1e-10f * d2e) continue;
-                    // exact evaluation in the shader's operation order (stage2.cs:86-94)
-                    const float sideCheck = dot(normal, lightMinusFrag);
-                    if (sideCheck < 0.0f) continue;
-                    const float ratio = fdiv(length(lightMinusFrag), lr);
-                    if (ratio > 1.0f) continue;
-                    if (ratio != ratio) continue;                         // (a NaN ratio never enters the list: every comparison with it is false)
-                    unsigned long long ck = makeKey(ratio, sCandPos[q]);
-                    if (!(ck < key[SGI_MAX_VPLS_PER_TILE - 1])) continue;  // worse than this lane's 12th: no slot can take it
-                    // insert before the first entry that is larger in (ratio, list position) order, shifting the rest down
-                    bool inserted = false;
-                    #pragma unroll
-                    for (int sl = 0; sl < SGI_MAX_VPLS_PER_TILE; ++sl) {
-                        const bool take = inserted || ck < key[sl];
-                        const unsigned long long t = key[sl];
-                        key[sl] = take ? ck : t;
-                        ck = take ? t : ck;
-                        inserted = take;
-                    }
-                    if (count < SGI_MAX_VPLS_PER_TILE) ++count;
-                }
-                // threshold exchange between the 4 lanes of the tile (every lane of the warp takes part)
-                const float a12 = keyRatio(key[SGI_MAX_VPLS_PER_TILE - 1]), a6 = keyRatio(key[5]), a3 = keyRatio(key[2]);
-                float m12 = fminf(a12, __shfl_xor_sync(0xffffffffu, a12, 1)); m12 = fminf(m12, __shfl_xor_sync(0xffffffffu, m12, 2));
-                float m6 = fmaxf(a6, __shfl_xor_sync(0xffffffffu, a6, 1)); m6 = fminf(m6, __shfl_xor_sync(0xffffffffu, m6, 2));
-                float m3 = fmaxf(a3, __shfl_xor_sync(0xffffffffu, a3, 1)); m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, 2));
-                w = fminf(fminf(m12, 1.0f), fminf(m6, m3));
-                w2 = w * w * (1.0f + 1e-6f);    // ties at the 12th ratio are decided by list position: keep them in the pre-test
-            }
-            if (q0 + kS2Round >= M) break;                                 // (uniform) that was the last round
-            // the patch's loosest threshold: can anything that remains still matter?
-            const float wm = warpMax(active ? w : 0.0f);
-            if (lane == 0) sRed[warp][0] = wm;
-            __syncthreads();
-            float wPatch = sRed[0][0];
-            #pragma unroll
-            for (int wv = 1; wv < kS2Warps; ++wv) wPatch = fmaxf(wPatch, sRed[wv][0]);
-            const float nextLb = (float)sBinOf[sOrder[q0 + kS2Round]] / (float)kS2Bins;      // the rest has sqrt(lb) >= bin / 32
-            if (nextLb * nextLb > wPatch * 1.0001f) break;                 // uniform
-        }
-
-        // ---- 4. merge the tile's four sorted lists: 12 rounds of the lexicographic minimum of the four heads ----
-        int total = count + __shfl_xor_sync(0xffffffffu, count, 1);
-        total += __shfl_xor_sync(0xffffffffu, total, 2);
-        total = min(total, SGI_MAX_VPLS_PER_TILE);
-        int mine[SGI_MAX_VPLS_PER_TILE / kS2Lanes];                        // lane g keeps (and stores) entries g, g+4, g+8 of the merged list
-        #pragma unroll
-        for (int r = 0; r < SGI_MAX_VPLS_PER_TILE; ++r) {
-            unsigned long long mk = key[0];
-            #pragma unroll
-            for (int o = 1; o < kS2Lanes; o <<= 1) {
-                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, mk, o);
-                mk = ok < mk ? ok : mk;
-            }
-            if (mk == key[0]) {                                            // this lane's head won (list positions are unique): pop it
-                #pragma unroll
-                for (int sl = 0; sl + 1 < SGI_MAX_VPLS_PER_TILE; ++sl) key[sl] = key[sl + 1];
-                key[SGI_MAX_VPLS_PER_TILE - 1] = kEmptyKey;
-            }
-            if ((r & (kS2Lanes - 1)) == g) mine[r / kS2Lanes] = (int)(unsigned int)(mk & 0xffffffffull);
-        }
-#else
         float dist[SGI_MAX_VPLS_PER_TILE];
         int pos[SGI_MAX_VPLS_PER_TILE];        // list positions; turned into VPL indices at the end
         #pragma unroll
@@ -445,7 +339,6 @@ stage2Kernel(int tilesX, int tileY0, int tilesY, int patchesX, int numPatches, c
             }
             if ((r & (kS2Lanes - 1)) == g) mine[r / kS2Lanes] = mp;
         }
-#endif
         if (active) {
             int32_t* o = reinterpret_cast<int32_t*>(out + tile);
             if (g == 0) o[0] = total;

@@ -159,7 +159,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->prepassInside, sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels() &&
-          preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels())) return bail(SGI_ERR_CUDA);
+          preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels() && preloadCubemapKernels())) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
     *out = h;
     return SGI_OK;
@@ -258,6 +258,17 @@ int sgi_vpl_prepass(SgiHandle h, const SgiPrepassParams* pp) {
         h->prepassCap = cap;
     }
     return postLaunch(h, launchPrepass(h->stream, *pp, h->prepassKeys, h->prepassInside));
+}
+
+int sgi_render_vpl_cubemaps(SgiHandle h, const SgiCubeRenderParams* rp) {
+    if (!h || !rp) return SGI_ERR_INVALID_ARG;
+    if (rp->numMaps < 0 || rp->numMaps > SGI_MAX_TOTAL_VPLS_BEFORE_CULLING || rp->numBoxes < 0 || rp->numBoxes > SGI_MAX_SCENE_BOXES)
+        return fail(h, SGI_ERR_INVALID_ARG, "sgi_render_vpl_cubemaps: numMaps or numBoxes out of range");
+    if (rp->numMaps == 0) return SGI_OK;
+    if (!rp->vplIndices || (rp->numBoxes > 0 && !rp->boxes)) return fail(h, SGI_ERR_NOT_BOUND, "sgi_render_vpl_cubemaps: boxes and vplIndices are required");
+    NEED(h, vplData); NEED(h, atlasEntryByVpl); NEED(h, shadowCubeMaps[0]); NEED(h, diffuseCubeMaps[0]);
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    return postLaunch(h, launchCubemaps(h->stream, *rp, h->buf.vplData, h->buf.atlasEntryByVpl, h->cp.cube_res, atlasTable(h)));
 }
 
 int sgi_ssao(SgiHandle h, const SgiSsaoParams* sp) {

@@ -321,6 +321,17 @@ int sgi_band_timeouts(SgiHandle h, int32_t* out_count) {
     return SGI_OK;
 }
 
+int sgi_band_stats(SgiHandle h, int32_t out[8]) {
+    if (!h || !out) return SGI_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!h->banded) return SGI_OK;
+    SGI_CUDA_B(h, cudaSetDevice(h->cp.device));
+    SGI_CUDA_B(h, cudaStreamSynchronize(h->stream));
+    SGI_CUDA_B(h, cudaMemcpy(out, h->flags, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    SGI_CUDA_B(h, cudaMemset(h->flags + 5, 0, 3 * sizeof(int32_t)));       // the spin account restarts
+    return SGI_OK;
+}
+
 int sgi_band_reprojection_misses(SgiHandle h, int32_t* out_count) {
     if (!h || !out_count) return SGI_ERR_INVALID_ARG;
     *out_count = 0;

@@ -118,6 +118,17 @@ __device__ __forceinline__ bool spinUntil(const int32_t* flag, int epoch, long l
     }
     return true;
 }
+// waits that found the flag behind are accounted in flags[5..7] of this handle (sgi_band_stats): how many, their summed and their
+// longest duration in units of 1024 SM cycles — the evidence for "waiting for a neighbour" against "slower kernel"
+__device__ __forceinline__ void bandSpinAccount(const BandLinks& L, long long t0) {
+    const long long dt = clock64() - t0;
+    if (dt > 2048) {
+        int32_t* st = L.timeouts + 3;
+        atomicAdd(st + 0, 1);
+        atomicAdd(st + 1, (int)(dt >> 10));
+        atomicMax(st + 2, (int)(dt >> 10));
+    }
+}
 // Called by EVERY thread of a CTA.  If some thread needs a halo, thread 0 spins on the neighbour's flag and the CTA
 // proceeds after a barrier (acquire + bar.sync orders the CTA's later loads/stores after the neighbour's release).
 __device__ __forceinline__ void bandWaitCta(const BandLinks& L, bool needUp, bool needDown) {
@@ -131,6 +142,7 @@ __device__ __forceinline__ void bandWaitCta(const BandLinks& L, bool needUp, boo
             if (up) ok = spinUntil(L.waitUp, L.waitEpoch, t0) && ok;
             if (down) ok = spinUntil(L.waitDown, L.waitEpoch, t0) && ok;
             if (!ok) atomicAdd(L.timeouts, 1);
+            bandSpinAccount(L, t0);
         }
         __syncthreads();
     }
@@ -252,6 +264,7 @@ namespace sgi {
 void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
 bool preloadPrepassKernels(); int launchPrepass(cudaStream_t stream, const SgiPrepassParams& pp, unsigned long long* keys, int* inside);
 bool preloadDirectKernels();
+bool preloadCubemapKernels(); int launchCubemaps(cudaStream_t stream, const SgiCubeRenderParams& rp, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl, int res, const AtlasTable& atlases);
 bool preloadTaaKernels(); int launchTaa(cudaStream_t stream, const BandDims& bd, const SgiTaaParams& tp);
 bool preloadSsaoKernels(); int launchSsao(cudaStream_t stream, const BandDims& bd, const SgiSsaoParams& sp);
 int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
@@ -277,7 +290,7 @@ int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
 int waitAllBands(SgiHandle_* h, int64_t frameNo);
 bool imagePushByKernel();
 void detachPeers(SgiHandle_* h);
-constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [3] reprojection taps outside the held rows, [4] producer counter of the in-kernel signal, [8+r] band r's image rows landed
+constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [3] reprojection taps outside the held rows, [4] producer counter, [5..7] waits that spun: count, summed and longest duration (1024 cycles) of the in-kernel signal, [8+r] band r's image rows landed
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
 int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int epoch, int32_t* timeouts);
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);

@@ -47,6 +47,7 @@ def load_library():
     L.sgi_bind_device_buffers.argtypes = [H, C.POINTER(Buffers)]
     L.sgi_register_gl.argtypes = [H, C.c_void_p, C.c_int32]
     L.sgi_vpl_prepass.argtypes = [H, C.POINTER(PrepassParams)]
+    L.sgi_render_vpl_cubemaps.argtypes = [H, C.c_void_p]
     L.sgi_direct_lighting.argtypes = [H, C.POINTER(FrameParams), C.POINTER(DirectParams)]
     L.sgi_ssao.argtypes = [H, C.POINTER(SsaoParams)]
     L.sgi_taa.argtypes = [H, C.POINTER(TaaParams)]
@@ -59,6 +60,7 @@ def load_library():
     L.sgi_frame_image.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.sgi_band_timeouts.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_band_reprojection_misses.argtypes = [H, C.POINTER(C.c_int32)]
+    L.sgi_band_stats.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_visible_count.argtypes = [H, C.POINTER(C.c_int32)]
     L.sgi_get_plane.argtypes = [H, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.sgi_download_plane.argtypes = [H, C.c_int32, C.c_void_p, C.c_int64]
@@ -208,6 +210,19 @@ class VplGiPass:
         pp.countOut = self.t["vplCountDevice"].data_ptr()
         self._check(self.L.sgi_vpl_prepass(self._h, C.byref(pp)))
 
+    # ---- VPL cube shadow / diffuse map production (include/stratusgi.h sgi_render_vpl_cubemaps) ----
+    def set_scene_boxes(self, boxes_u8):
+        """boxes_u8: uint8 [n, 32] SgiSceneBox records (Scene.boxes())."""
+        self.t["sceneBoxes"] = self.torch.from_numpy(np.ascontiguousarray(boxes_u8, np.uint8)).to(self.device)
+
+    def render_vpl_cubemaps(self, vpl_indices):
+        """Renders the cube depth + diffuse maps of the listed VPLs (indices into the bound vplData table) into their atlas layers."""
+        from ._abi import CubeRenderParams
+        idx = vpl_indices if hasattr(vpl_indices, "data_ptr") else self.torch.as_tensor(np.asarray(vpl_indices, np.int32), device=self.device)
+        self.t["cubeRenderIdx"] = idx                      # kept alive until the stream has consumed it
+        rp = CubeRenderParams(int(self.t["sceneBoxes"].shape[0]), int(idx.numel()), self.t["sceneBoxes"].data_ptr(), idx.data_ptr())
+        self._check(self.L.sgi_render_vpl_cubemaps(self._h, C.byref(rp)))
+
     # ---- the passes that produce the `ssao` input plane: ssao.fs + ssao_blur.fs (NOT YET VALIDATED ON A GPU, see csrc/k_ssao.cu) ----
     def ssao(self, structure, rotation, aspectRatio, projPlaneZDist, intensity=5.0):
         """RenderSsaoOcclude_ + RenderSsaoBlur_ over a structure buffer (half4 [rows, W, 4]) -> the half [rows, W] plane, kept as
@@ -313,6 +328,13 @@ class VplGiPass:
         n = C.c_int32()
         self._check(self.L.sgi_band_timeouts(self._h, C.byref(n)))
         return n.value
+
+    def band_stats(self):
+        """Raw protocol counters (include/stratusgi.h sgi_band_stats); the spin account restarts with every call."""
+        out = (C.c_int32 * 8)()
+        self._check(self.L.sgi_band_stats(self._h, out))
+        return {"epoch_up": out[0], "epoch_down": out[1], "timeouts": out[2], "reprojection_misses": out[3],
+                "waits_that_spun": out[5], "spin_sum_kcycles": out[6], "spin_max_kcycles": out[7]}
 
     def band_reprojection_misses(self):
         """Reprojected previous-frame taps of the final passes so far that fell outside the held rows (halo shorter than the motion)."""

@@ -42,6 +42,7 @@ def _load():
         _lib.sgs_frame_params.argtypes = [C.c_void_p, C.c_int, C.POINTER(FrameParams)]
         _lib.sgs_gbuffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
         _lib.sgs_vpls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.sgs_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib.sgs_cubemaps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib.sgs_csm.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.sgs_sun_visibility.argtypes = [C.c_void_p, C.c_void_p]
@@ -134,6 +135,15 @@ class Scene:
         atlas = np.zeros((n, 2), np.int32)
         _load().sgs_vpls(self._h, _ptr(data), _ptr(atlas))
         return data, atlas
+
+    def boxes(self):
+        """The scene's geometry as SgiSceneBox records (numpy structured array viewable as bytes): what
+        sgi_render_vpl_cubemaps casts its texel rays against."""
+        from .._abi import SceneBox
+        n = _load().sgs_boxes(self._h, None, 0)
+        arr = (SceneBox * n)()
+        _load().sgs_boxes(self._h, C.cast(arr, C.c_void_p), n)
+        return np.frombuffer(bytes(arr), np.uint8).reshape(n, C.sizeof(SceneBox)).copy()
 
     def num_atlases(self):
         return min(MAX_TOTAL_SHADOW_ATLASES, (self.num_vpls + MAX_TOTAL_SHADOWS_PER_ATLAS - 1) // MAX_TOTAL_SHADOWS_PER_ATLAS)

@@ -466,6 +466,22 @@ int sgs_gbuffer(void* p, int frame, int y0, int rows, float* depth, uint8_t* nor
     return 0;
 }
 
+// The scene's geometry as the box list sgi_render_vpl_cubemaps consumes (float bounds; every bound of the procedural scenes is
+// exactly representable).  Returns the number of boxes; `out` may be NULL to query it.
+int sgs_boxes(void* p, SgiSceneBox* out, int capacity) {
+    Scene& s = *(Scene*)p;
+    const int n = (int)s.boxes.size();
+    if (out) for (int b = 0; b < n && b < capacity; ++b) {
+        const Box& bx = s.boxes[b];
+        out[b].lo[0] = (float)bx.lo.x; out[b].lo[1] = (float)bx.lo.y; out[b].lo[2] = (float)bx.lo.z;
+        out[b].hi[0] = (float)bx.hi.x; out[b].hi[1] = (float)bx.hi.y; out[b].hi[2] = (float)bx.hi.z;
+        for (int c = 0; c < 3; ++c) out[b].albedo[c] = bx.albedo[c];
+        out[b].albedo[3] = 255;
+        out[b].insideOut = bx.insideOut ? 1 : 0;
+    }
+    return n;
+}
+
 int sgs_vpls(void* p, SgiVplData* out, SgiAtlasEntry* atlas) {
     Scene& s = *(Scene*)p;
     if (out) std::memcpy(out, s.vpls.data(), sizeof(SgiVplData) * s.N);

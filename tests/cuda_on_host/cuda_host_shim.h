@@ -72,6 +72,11 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> static inline T __ldcg(const T* p) { return *(const volatile T*)p; }
 template <typename T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, int v) { return __atomic_fetch_add(p, (unsigned)v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T atomicMax(T* p, T v) {
+    T old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 
 #ifdef SGI_HOST_RUNTIME
 // ---- the CUDA runtime as the ABI layer (csrc/sgi_abi.cu, csrc/sgi_band.cu) uses it, on host memory: "device" allocations are

@@ -164,7 +164,7 @@ def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=(), extra=()):
     return _gxx([os.path.join(HERE, w) for w in wrapper_cpps], so, build, defines, extra)
 
 
-ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
+ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_cubemaps.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
 
 
 def compile_whole_library(sanitize=False):

@@ -26,9 +26,7 @@ class HostPeer(C.Structure):
 def _load():
     from stratusgfx_b200._abi import FrameParams
     from tests.cuda_on_host.host_tu import compile_wrapper
-    # SGI_BANDS_DEFINES=SGI_ATROUS_V2,SGI_ATROUS_V3 runs the band processes on a queued compile-time variant (the whole-frame
-    # reference of the test stays the default build: the variants must give its bytes in band mode too)
-    defines = tuple(x for x in os.environ.get("SGI_BANDS_DEFINES", "").split(",") if x)
+    defines = ()
     L = C.CDLL(compile_wrapper(("vpl_on_host.cpp", "gather_on_host.cpp", "denoise_lockstep_on_host.cpp", "bands_on_host.cpp"),
                                ("k_vpl.cu", "k_gather.cu", "k_denoise.cu", "sgi_band.cu"),
                                "libbands_on_host" + "".join("_" + x[-2:].lower() for x in defines) + ".so", defines))
@@ -123,16 +121,6 @@ def whole_frame(built):
         r = compare_radiance(lit[f], orc[f]["combined"], 3)
         assert r["ok"] and r["bit_exact"] > 0.99, (f, r)
     return tables, lit
-
-
-def test_queued_atrous_variants_give_the_default_bytes_in_band_mode(whole_frame, monkeypatch):
-    if os.environ.get("SGI_HOST_SUITE", "") != "full":
-        pytest.skip("set SGI_HOST_SUITE=full")
-    tables, want = whole_frame                              # computed by the default build before the variable is set
-    monkeypatch.setenv("SGI_BANDS_DEFINES", "SGI_ATROUS_V2,SGI_ATROUS_V3")
-    got = _run(4, tables, True)
-    for f in range(FRAMES):
-        assert np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)), f
 
 
 @pytest.mark.parametrize("world,kernel_signal", [(3, True), (4, True), (4, False), (5, True), (8, True)])

@@ -1,6 +1,6 @@
 """csrc/k_denoise.cu compiled by g++ (tests/cuda_on_host/host_tu.py: a translated copy, the source is untouched) and executed thread
-by thread on the host — the shipped kernels' LOGIC against the CPU oracle without a GPU, and the queued -DSGI_ATROUS_V2 variant
-(32-bit tap indices, packed fma.rn.f32x2 accumulation) against the default build, which it must equal bit for bit.
+by thread on the host — the shipped kernels' LOGIC (the clamp-free interior path and the clamped edge path of the à-trous
+kernel, the final pass's temporal epilogue) against the CPU oracle without a GPU.
 
 The MUFU approximations (lg2/ex2) are libm calls here, so radiance is compared under the parity bar of tests/parity_util.py
 (1e-3 relative per pixel or 60 dB PSNR) like on the GPU; the history plane — the one decision of this shader — must be exact."""
@@ -61,24 +61,3 @@ def test_denoiser_kernels_on_the_host_match_the_oracle(host_denoiser, yaw):
         assert np.array_equal(hist.view(np.uint16), orc[f]["history"].view(np.uint16))
     if yaw:
         assert len(np.unique(orc[1]["history"].view(np.uint16))) > 1          # some pixels were reset, some accumulated
-
-
-@pytest.mark.parametrize("workload,macro,iters", [("tiny", "SGI_ATROUS_V2", 4), ("tiny", "SGI_ATROUS_V3", 4), ("tiny", "SGI_ATROUS_V3", 5),
-                                                  ("c1", "SGI_ATROUS_V3", 4), ("c1", "SGI_ATROUS_V2+SGI_ATROUS_V3", 4)])
-def test_queued_atrous_variants_are_bit_identical_to_the_default_build(host_denoiser, workload, macro, iters):
-    """The compile-time variants queued for a GPU A/B change no arithmetic — V2: 32-bit tap indices and IEEE fma per lane of a
-    packed pair; V3: spacing as a template parameter (2, 4, 8; 16 in the 5-pass run falls back to the generic kernel) and
-    pointer + immediate addressing for threads whose taps need no clamp; both together — so every output byte must agree with the
-    default."""
-    from tests.parity_util import SceneData, run_oracle
-    macros = tuple(macro.split("+"))
-    L2 = _load(macros, "libdenoise_on_host_" + "".join(m[-2:].lower() for m in macros) + ".so")
-    frames = 2 if workload == "tiny" else 1
-    d = SceneData(workload, frames=frames, yaw_deg_per_frame=1.5)
-    orc = run_oracle(d, keep_passes=False)
-    for f in range(frames):
-        a = _run(host_denoiser, d, orc, f, iters)
-        b = _run(L2, d, orc, f, iters)
-        for x, y in zip(a, b):
-            assert np.array_equal(x.view(np.uint16), y.view(np.uint16))
-        assert np.any(a[0][iters - 2].view(np.uint16) != 0)

@@ -160,28 +160,3 @@ def test_gather_kernel_in_lockstep_matches_the_oracle(host_frame_lib, workload):
         assert r["ok"] and r["bit_exact"] > 0.99, r
     # the sample count of every pixel (reservoir alpha: the sum of re-weighting factors, a chain of decisions) must agree exactly
     assert np.array_equal(reservoir[..., 3].view(np.uint16), orc["gi_reservoir"][..., 3].view(np.uint16))
-
-
-def test_stage2_key64_variant_builds_the_same_lists(built):
-    """-DSGI_STAGE2_KEY64 (queued for a GPU A/B: one 64-bit key per list entry instead of a (ratio, position) pair) must give the
-    oracle's lists bit for bit, like the default build."""
-    from tests.parity_util import SceneData, run_oracle
-    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
-        pytest.skip("CUDA headers not found")
-    from tests.cuda_on_host.host_tu import compile_wrapper
-    L = C.CDLL(compile_wrapper(("vpl_on_host.cpp", "tiles_on_host.cpp"), ("k_vpl.cu", "k_tiles.cu"), "libtiles_key64_on_host.so", ("SGI_STAGE2_KEY64",)))
-    L.host_tile_lists.argtypes = [C.POINTER(FrameParams), C.c_int, C.c_int] + [C.c_void_p] * 6
-    for workload in ("tiny", "c1"):
-        d = SceneData(workload, frames=1)
-        orc = run_oracle(d, keep_passes=False)[0]
-        tiles = (d.W // 5) * (d.H // 5)
-        stage1, stage2 = np.zeros((tiles, 8), np.float32), np.zeros((tiles, 13), np.int32)
-        depth, normal = np.ascontiguousarray(d.gb[0].depth), np.ascontiguousarray(d.gb[0].normal)
-        updated, visible = np.ascontiguousarray(orc["updated"]), np.ascontiguousarray(orc["visible"])
-        L.host_tile_lists(C.byref(d.fp[0]), d.W, d.H, depth.ctypes.data, normal.ctypes.data, updated.ctypes.data, visible.ctypes.data,
-                          stage1.ctypes.data, stage2.ctypes.data)
-        cnt = orc["stage2"][:, 0]
-        assert cnt.max() > 0 and np.array_equal(stage2[:, 0], cnt), workload
-        mask = np.arange(12)[None, :] < cnt[:, None]
-        assert np.array_equal(stage2[:, 1:][mask], orc["stage2"][:, 1:][mask]), workload
