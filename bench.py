@@ -388,17 +388,19 @@ def run_ours(args, rank, world, local_rank):
     # per-step NCCL traffic of the band split: VPL table + atlas entries + the <= 5 cube maps refreshed this frame, packed
     # into ONE byte buffer (one broadcast; NCCL has no 16-bit integer type) that the pass reads in place
     refreshed = [int(at[i, 0]) * 320 + int(at[i, 1]) for i in range(min(5, N))]
+    device_maps = args.maps == "device"        # the refreshed maps are rendered on every GPU instead of travelling with the tables
     if world > 1:
         R = scene.cube_res
-        nb_v, nb_a, nb_m = N * 64, N * 8, len(refreshed) * 6 * R * R * 2
+        nb_v, nb_a, nb_m = N * 64, N * 8, (0 if device_maps else len(refreshed) * 6 * R * R * 2)
         packed = torch.empty(nb_v + nb_a + nb_m, dtype=torch.uint8, device=dev)
         v_view = packed[:nb_v].view(torch.float32).view(N, 16)
         a_view = packed[nb_v:nb_v + nb_a].view(torch.int32).view(N, 2)
-        maps_buf = packed[nb_v + nb_a:].view(torch.int16).view(len(refreshed), 6, R, R)
+        maps_buf = packed[nb_v + nb_a:].view(torch.int16).view(-1, 6, R, R)
         v_view.copy_(gp.t["vplData"]); a_view.copy_(gp.t["atlasEntryByVpl"])
         gp.t["vplData"], gp.t["atlasEntryByVpl"] = v_view, a_view
         sa = gp.t["shadowAtlas"].view(-1, 6, R, R)
-        maps_buf.copy_(torch.stack([sa[s] for s in refreshed]))
+        if not device_maps:
+            maps_buf.copy_(torch.stack([sa[s] for s in refreshed]))
         refreshed_idx = torch.tensor(refreshed, dtype=torch.int64, device=dev)
         gp.bind()
         if p2p:
@@ -406,33 +408,68 @@ def run_ours(args, rank, world, local_rank):
         else:
             full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
 
-    # The per-frame tables are what the CPU side of the renderer has ready before the frame starts, so their broadcast is
-    # issued one frame ahead (async NCCL broadcast into a staging buffer while the previous frame computes) and only a
-    # 0.2 MB device copy sits in the frame's critical path.  --no-prefetch broadcasts at the start of the frame instead.
+    # What the renderer produces BEFORE the GI pass of a frame — the VPL table (CPU side), the refreshed cube maps and the
+    # visibility cull (BE:1982 -> BE:1395, long before BE:2043-2044) — is prepared for frame i+1 on a second, higher-priority
+    # stream while frame i runs its denoise passes: the table broadcast lands in place, the maps are refreshed (copied from the
+    # broadcast, or rendered on the device with --maps device), then sgi_cull_early culls and colours.  The main stream holds
+    # nothing but sgi_frame, which starts at the gather.  --no-early keeps everything on the main stream (round-1 behaviour).
+    use_early = not args.no_early
     prefetch = world > 1 and not args.no_prefetch
     pending = [None]
-    if prefetch:
-        stage = torch.empty_like(packed)
+    early = torch.cuda.Stream(device=dev, priority=-1) if use_early else None
+    early_ptr = early.cuda_stream if use_early else None
+    fp_next = fp.copy()
+    if device_maps:
+        gp.set_scene_boxes(scene.boxes())
+        refreshed_vpls = torch.arange(min(5, N), dtype=torch.int32, device=dev)       # the lights popped from lightsToUpdate this frame
+        torch.cuda.synchronize(dev)
+    if world > 1:
         src_tables = packed.clone()          # rank 0's "CPU-produced" tables of the next frame (synthetic: the same every frame)
+        if not use_early and prefetch:
+            stage = torch.empty_like(packed)
 
-    def issue_broadcast():
+    def refresh_maps(stream_ptr):
+        if device_maps:
+            gp.render_vpl_cubemaps(refreshed_vpls, stream=stream_ptr)
+        elif world > 1:
+            sa.index_copy_(0, refreshed_idx, maps_buf)        # the refreshed cube maps into their atlas layers: one scatter
+
+    def issue_broadcast(buf):
         if rank == 0:
-            stage.copy_(src_tables)
-        pending[0] = dist.broadcast(stage, 0, async_op=True)
+            buf.copy_(src_tables)
+        pending[0] = dist.broadcast(buf, 0, async_op=True)
+
+    def prepare_next(i_next):
+        """Everything frame i_next needs before its gather, on the early stream (enqueued right after frame i_next - 1)."""
+        with torch.cuda.stream(early):
+            gp.early_begin(early_ptr)                          # frame i_next - 1 has read the tables and the atlases
+            if world > 1:
+                if pending[0] is None:
+                    issue_broadcast(packed)
+                pending[0].wait()                              # stream-ordered: the tables of frame i_next are in `packed`
+            refresh_maps(early_ptr)
+            fp_next.time = 1000.0 + 16.0 * i_next
+            gp.cull_early(fp_next, early_ptr, True)
+            if world > 1:
+                issue_broadcast(packed)                        # the tables of frame i_next + 1 travel while frame i_next computes
 
     def step(i):
         fp.time = 1000.0 + 16.0 * i
-        if world > 1:
-            if prefetch:
-                if pending[0] is None:
-                    issue_broadcast()
-                pending[0].wait()                              # stream-ordered: the pass's stream waits for NCCL's
-                packed.copy_(stage)
-                issue_broadcast()                              # the next frame's tables travel while this frame computes
-            else:
-                broadcast_frame_inputs(dist, [packed])
-            sa.index_copy_(0, refreshed_idx, maps_buf)        # the refreshed cube maps into their atlas layers: one scatter
-        gp.frame(fp)
+        if use_early:
+            gp.frame(fp)
+            prepare_next(i + 1)
+        else:
+            if world > 1:
+                if prefetch:
+                    if pending[0] is None:
+                        issue_broadcast(stage)
+                    pending[0].wait()                              # stream-ordered: the pass's stream waits for NCCL's
+                    packed.copy_(stage)
+                    issue_broadcast(stage)                         # the next frame's tables travel while this frame computes
+                else:
+                    broadcast_frame_inputs(dist, [packed])
+            refresh_maps(None)
+            gp.frame(fp)
         if world > 1 and not p2p:
             gather_bands(dist, gp.t["lightingOut"][me.owned], full_out, bands, rank)
         # p2p: every band's lit rows travel to rank 0's frame image after its final pass (copy engine, during the next frame);
@@ -441,8 +478,15 @@ def run_ours(args, rank, world, local_rank):
     def finish():
         if p2p and rank == 0:
             gp.frame_image_wait()
-        if prefetch and pending[0] is not None:
-            pending[0].wait(); pending[0] = None
+        if pending[0] is not None:
+            if use_early:
+                with torch.cuda.stream(early):
+                    pending[0].wait()
+            else:
+                pending[0].wait()
+            pending[0] = None
+        if use_early:
+            side.wait_stream(early)           # the look-ahead work of the frame after the last one is inside the timed region too
 
     def fence():
         if world > 1:
@@ -505,7 +549,12 @@ def run_ours(args, rank, world, local_rank):
             set_host_threads(1)               # the other ranks idle at the barrier below
             img = (gp.frame_image() if p2p else full_out).clone()
             one = VplGiPass(W, H, 0, H, scene.cube_res, scene.csm_res, iters, device=local_rank, use_torch_stream=True)
-            one.set_gbuffer(scene.gbuffer(0), scene.gbuffer(-1)); one.set_vpls(vd, at); one.set_atlases(sh, df); one.set_csm(csm); one.bind()
+            one.set_gbuffer(scene.gbuffer(0), scene.gbuffer(-1)); one.set_vpls(vd, at); one.set_atlases(sh, df); one.set_csm(csm)
+            if device_maps:
+                one.set_scene_boxes(scene.boxes())
+            one.bind()
+            if device_maps:
+                one.render_vpl_cubemaps(refreshed_vpls)          # the same five maps, rendered the same way (idempotent)
             fp1 = scene.frame_params(0)
             for i in range(args.warmup + args.steps):
                 fp1.time = 1000.0 + 16.0 * i
@@ -602,9 +651,11 @@ def run_ours(args, rank, world, local_rank):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
                            "parallelism": "single GPU" if world == 1 else (
-                               f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of VPL table + 5 cube maps per frame ({'issued one frame ahead' if prefetch else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
+                               f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of the VPL table{'' if device_maps else ' + 5 cube maps'} per frame ({'issued one frame ahead' if (prefetch or use_early) else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
                                f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
                            "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
+                           "look_ahead": ("cull + colouring" + (" + table broadcast" if world > 1 else "") + " + cube-map refresh of frame i+1 on a second stream under frame i's denoise passes (sgi_early_begin / sgi_cull_early; the reference culls at BE:1395, long before the GI pass at BE:2043)") if use_early else "off: everything on one stream",
+                           "refreshed_cube_maps": ("rendered on the device every frame (sgi_render_vpl_cubemaps, 5 maps)" if device_maps else ("copied from the per-frame broadcast (5 maps)" if world > 1 else "resident (uploaded once)")),
                            "image_equals_single_gpu": (image_equal or {}).get("equal"), "image_check": image_equal, "band_spin": band_spin,
                            "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log,
                            "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
@@ -716,6 +767,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--balance", type=int, default=2, help="measured band-balancing rounds before the timed region (N > 1)")
+    ap.add_argument("--no-early", action="store_true", help="keep the table broadcast, the cube-map refresh and the cull on the main stream (no look-ahead stream)")
+    ap.add_argument("--maps", default="broadcast", choices=["broadcast", "device"], help="the <= 5 cube maps refreshed per frame: copied from rank 0's broadcast (N > 1; N = 1: resident) or rendered on every GPU by sgi_render_vpl_cubemaps")
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
     ap.add_argument("--no-image-check", action="store_true", help="N > 1: skip the byte comparison of the assembled image with a single-GPU replay")
     ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")

@@ -235,6 +235,7 @@ typedef struct SgiCubeRenderParams {
                                           per frame in the reference, StratusRendererBackend.h:378; any count here)  */
     const SgiSceneBox* boxes;          /* device [numBoxes]                                                          */
     const int32_t* vplIndices;         /* device [numMaps]: indices into the bound vplData / atlasEntryByVpl tables  */
+    void*   stream;                    /* CUDA stream to enqueue on; NULL = the handle's stream (see sgi_early_begin) */
 } SgiCubeRenderParams;
 #define SGI_MAX_SCENE_BOXES 256
 
@@ -287,7 +288,7 @@ int  sgi_register_gl(SgiHandle h, const uint32_t* gl_names, int32_t count);
 int  sgi_render_vpl_cubemaps(SgiHandle h, const SgiCubeRenderParams* rp);
 
 /* ---- deferred direct lighting: pbr.fs, the pass whose output is the `screen` plane of this path ----
- * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_direct.cu). */
+ * (csrc/k_direct.cu; parity against the reference's compiled shader text: tests/test_zz_*.py) */
 typedef struct SgiPointLight {          /* GpuPointLight / `struct PointLight` (pbr.fs:15-21) */
     float position[4];
     float color[4];
@@ -316,7 +317,7 @@ int  sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectP
 
 /* ---- screen-space ambient occlusion (first half): ssao.fs + ssao_blur.fs, the two passes whose output
  *      is the `ssao` plane of this path (RenderSsaoOcclude_ / RenderSsaoBlur_, StratusRendererBackend.cpp:1160-1204) ----
- * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_ssao.cu).  Whole-frame handles only. */
+ * (csrc/k_ssao.cu; parity against the reference's compiled shader text: tests/test_zz_*.py)  Whole-frame handles only. */
 typedef struct SgiSsaoParams {
     float   aspectRatio;                /* viewportWidth / viewportHeight                      (BE:1165)          */
     float   projPlaneZDist;             /* 1 / tan(fovy / 2)                                   (BE:1167)          */
@@ -332,7 +333,7 @@ typedef struct SgiSsaoParams {
 int  sgi_ssao(SgiHandle h, const SgiSsaoParams* sp);
 
 /* ---- temporal anti-aliasing (second half): taa.fs, PerformTaaPostFx_ (BE:2324-2354) ----
- * NOT YET VALIDATED ON A GPU (written at the end of round 1; see csrc/k_taa.cu).  Whole-frame handles only. */
+ * (csrc/k_taa.cu; parity against the reference's compiled shader text: tests/test_zz_*.py)  Whole-frame handles only. */
 typedef struct SgiTaaParams {
     const void* screen;                 /* device rgba8 [rows][W]: finalScreenBuffer (the FXAA target, BE:694-699)                   */
     const void* prevScreen;             /* device rgba8 [rows][W]: previousFrameBuffer (RGB8, BE:450-455; alpha ignored)             */
@@ -383,6 +384,22 @@ int  sgi_band_stats(SgiHandle h, int32_t out[8]);
  * the largest vertical motion of a frame: halo >= ceil(max |velocity.y| * full_height) + 1 rows.  Taps beyond the held rows
  * are clamped to them and counted; a nonzero count means this band's image differs from the whole-frame result there. */
 int  sgi_band_reprojection_misses(SgiHandle h, int32_t* out_count);
+
+/* ---- the cull where the reference runs it: EARLY.  In RenderScene the visibility cull is part of UpdatePointLights_ (BE:1982 ->
+ *      BE:1395), followed by the cube-map updates, the geometry pass, SSAO and the direct lighting before the GI pass consumes its
+ *      result (BE:2043-2044).  These two calls give a caller the same freedom on a second CUDA stream: the cull (and, when the
+ *      next frame's atlases are already final, the colouring stage) of frame i+1 runs under the denoise passes of frame i, and
+ *      sgi_frame(i+1) starts at the gather.  Outputs go to the same caller-owned buffers as sgi_cull / sgi_color.
+ *        sgi_early_begin(h, stream)     `stream` waits until the frame last enqueued on this handle has finished READING the
+ *                                       compacted tables and the cube atlases (its gather and tile-list stages).  After this call
+ *                                       the caller may enqueue, on `stream`, its uploads of the next frame's VPL table / CSM and
+ *                                       its cube-map refresh (e.g. sgi_render_vpl_cubemaps with the same stream).
+ *        sgi_cull_early(h, fp, stream, with_color)   enqueues sgi_cull (with_color != 0: + sgi_color) for the next frame on
+ *                                       `stream`.  The next sgi_frame on this handle waits for it instead of running its own; its
+ *                                       lights / sun / cascade parameters must be the ones given here (else SGI_ERR_INVALID_ARG).
+ *                                       An explicit sgi_cull in between supersedes the early result. */
+int  sgi_early_begin(SgiHandle h, void* stream);
+int  sgi_cull_early(SgiHandle h, const SgiFrameParams* fp, void* stream, int32_t with_color);
 
 /* the blocking variant of the visible count (what BE:1675-1678 maps the buffer for) */
 int  sgi_visible_count(SgiHandle h, int32_t* out_count);

@@ -66,6 +66,7 @@ COMPUTE = [
     ("ssao.fs", "fs_ssao", "ssao_main", [], ["saturate", "calculateAmbientOcclusion"]),
     ("ssao_blur.fs", "fs_ssao_blur", "ssao_blur_main", [], ["blurAmbientOcclusion"]),
     ("taa.fs", "fs_taa", "taa_main", [], []),              # widening row f4 (second half): temporal anti-aliasing (BE:2324-2354)
+    ("shadowVpl.fs", "fs_shadow_vpl", "shadow_vpl_main", [], []),      # widening row f2: the fragment stage of the VPL cube-map pass (BE:1426-1575)
 ]
 TYPES = r"(?:float|int|uint|bool|vec2|vec3|vec4|uvec2|uvec3|uvec4|ivec2|mat4|void|sampler2D|sampler2DRect|samplerCubeArray|sampler2DArrayShadow)"
 
@@ -509,6 +510,17 @@ void refglsl_taa(const RefTaaArgs* a) {                                     // P
             }
     }
 }
+// shadowVpl.fs main() for one fragment: world position, light, far plane, base colour -> gl_FragDepth and the colour output
+void refglsl_shadow_vpl(const float* fsPosition3, const float* lightPos3, float farPlane, const float* baseColor4, float* depthOut, float* color3Out) {
+    using namespace refglsl;
+    fs_shadow_vpl::materials[0].diffuseColor = glm::vec4(baseColor4[0], baseColor4[1], baseColor4[2], baseColor4[3]);
+    fs_shadow_vpl::materials[0].flags = 0u; fs_shadow_vpl::materialIndices[0] = 0; fs_shadow_vpl::fsDrawID = 0;
+    fs_shadow_vpl::fsPosition = glm::vec4(fsPosition3[0], fsPosition3[1], fsPosition3[2], 1.0f);
+    fs_shadow_vpl::lightPos = glm::vec3(lightPos3[0], lightPos3[1], lightPos3[2]); fs_shadow_vpl::farPlane = farPlane;
+    fs_shadow_vpl::shadow_vpl_main();
+    *depthOut = fs_shadow_vpl::gl_FragDepth;
+    for (int c = 0; c < 3; ++c) color3Out[c] = fs_shadow_vpl::color[c];
+}
 typedef struct RefColorArgs {
     int cubeRes, numAtlases; const float* sunDir; const float* sunColor; void* lightData; const int* numVisible; const void* diffuseIndices;
     const unsigned short* const* shadowAtlases; const unsigned char* const* diffuseAtlases;
@@ -647,7 +659,15 @@ void refglsl_cull(const RefCullArgs* a) {
 '''
 
 
-CS_PRE = {'fs_ssao': 'PERINV sampler2DRect structureBuffer; PERINV sampler2D rotationLookup;\nPERINV float aspectRatio, projPlaneZDist, windowHeight, windowWidth, intensity; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
+CS_PRE = {'fs_shadow_vpl': ('// what the material system and alpha_test.glsl supply, reduced to the untextured, opaque case the box scenes are\n'
+                            'struct Material { vec4 diffuseColor; unsigned flags; sampler2D diffuseMap; };\n'
+                            'static const unsigned GPU_DIFFUSE_MAPPED = 2u;\n'
+                            'static inline bool bitwiseAndBool(unsigned a, unsigned b) { return (a & b) != 0u; }\n'
+                            'static inline vec4 FLOAT4_TO_VEC4(vec4 v) { return v; }\n'
+                            'static inline void runAlphaTest(float) {}\n'
+                            'PERINV Material materials[1]; PERINV int materialIndices[1]; PERINV int fsDrawID;\n'
+                            'PERINV vec4 fsPosition; PERINV vec2 fsTexCoords; PERINV vec3 lightPos; PERINV float farPlane; PERINV float gl_FragDepth; PERINV vec3 color;\n'),
+          'fs_ssao': 'PERINV sampler2DRect structureBuffer; PERINV sampler2D rotationLookup;\nPERINV float aspectRatio, projPlaneZDist, windowHeight, windowWidth, intensity; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
           'fs_taa': 'PERINV sampler2D screen, prevScreen, velocity, previousVelocity; PERINV vec2 fsTexCoords; PERINV vec4 color;\n',
           'fs_ssao_blur': 'PERINV sampler2DRect structureBuffer, occlusionBuffer; PERINV float windowWidth, windowHeight; PERINV vec2 fsTexCoords; PERINV float gLightFactor;\n',
           'cs_color': 'PERINV vec3 infiniteLightColor;\nPERINV VplData* lightData; PERINV const int* numVisible; PERINV const AtlasEntry* diffuseIndices;\nPERINV samplerCubeArray diffuseCubeMaps[MAX_TOTAL_SHADOW_ATLASES], shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES];\n', 'cs_stage1': 'PERINV sampler2D gDepth, gNormal; PERINV mat4 invProjectionView;\nPERINV VplStage1PerTileOutputs* vplNumVisiblePerTile;\nPERINV vec3 localPositions[25], localNormals[25];          // `shared`, sized gl_WorkGroupSize.x * gl_WorkGroupSize.y = 5 * 5\n', 'cs_stage2': 'PERINV vec3 viewPosition;\nPERINV const VplData* lightData; PERINV const VplStage1PerTileOutputs* stage1Data; PERINV int numVisible; PERINV const int* vplVisibleIndex;\nPERINV VplStage2PerTileOutputs* vplNumVisiblePerTile;\n', 'cs_cull': 'static int totalNumLights;\nstatic const VplData* lightData; static VplData* updatedLightData; static int* vplVisibleIndex;\nstatic bool lightVisible[MAX_TOTAL_VPLS_BEFORE_CULLING]; static int lightVisibleIndex;      // `shared`\n', 'fs_direct': '#define INFINITE_LIGHTING_ENABLED\nstruct PointLight { vec4 position; vec4 color; float radius; float farPlane; float _1[2]; };        // pbr.fs:15-21\nPERINV sampler2D gDepth, gNormal, gAlbedo, gBaseReflectivity, gRoughnessMetallicAmbient; PERINV sampler2DRect ssao;\nPERINV mat4 invProjectionView; PERINV float windowWidth, windowHeight; PERINV vec3 viewPosition; PERINV float emissionStrength = 0.0f;\nPERINV int numLights = 0, numShadowLights = 0; PERINV const PointLight* nonShadowCasters; PERINV const PointLight* shadowCasters;\nPERINV samplerCubeArray shadowCubeMaps[MAX_TOTAL_SHADOW_ATLASES]; PERINV const AtlasEntry* shadowIndices;\nPERINV vec3 infiniteLightColor; PERINV vec2 fsTexCoords; PERINV vec3 fsColor;\n'}

@@ -428,6 +428,25 @@ def vpl_prepass(lights, view_position, frustum_planes, variant="own"):
     return vd[:count], at[:count], order[:count]
 
 
+def render_vpl_cubemaps(boxes_u8, vpl_data, atlas_by_vpl, vpl_indices, res, shadow_atlas, diffuse_atlas, variant="own"):
+    """Widening row f2 on the CPU (orc_render_vpl_cubemaps): renders the cube depth + diffuse maps of the listed VPLs in place into
+    `shadow_atlas` (uint16 [A,320,6,R,R]) and `diffuse_atlas` (uint8 [A,320,6,R,R,4]).  boxes_u8: uint8 [n,32] SgiSceneBox records."""
+    L = lib(variant)
+    boxes = np.ascontiguousarray(boxes_u8, np.uint8)
+    idx = np.ascontiguousarray(vpl_indices, np.int32)
+    vd = np.ascontiguousarray(vpl_data, np.float32); at = np.ascontiguousarray(atlas_by_vpl, np.int32)
+    L.orc_render_vpl_cubemaps(_p(boxes), int(boxes.shape[0]), _p(vd), _p(at), _p(idx), int(idx.shape[0]), int(res),
+                              _atlas_ptrs(shadow_atlas), _atlas_ptrs(diffuse_atlas))
+
+
+def shadow_vpl_depth(fs_position, light_pos, far_plane, variant="own"):
+    L = lib(variant)
+    L.orc_shadow_vpl_depth.restype = C.c_float
+    L.orc_shadow_vpl_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+    a = np.ascontiguousarray(fs_position, np.float32); b = np.ascontiguousarray(light_pos, np.float32)
+    return float(L.orc_shadow_vpl_depth(_p(a), _p(b), float(far_plane)))
+
+
 class OracleFrame:
     """Whole-frame CPU pipeline over numpy buffers, keeping temporal state between frames."""
 

@@ -107,7 +107,7 @@ class SceneBox(C.Structure):
 
 
 class CubeRenderParams(C.Structure):
-    _fields_ = [("numBoxes", C.c_int32), ("numMaps", C.c_int32), ("boxes", C.c_void_p), ("vplIndices", C.c_void_p)]
+    _fields_ = [("numBoxes", C.c_int32), ("numMaps", C.c_int32), ("boxes", C.c_void_p), ("vplIndices", C.c_void_p), ("stream", C.c_void_p)]
 
 
 class PrepassParams(C.Structure):
@@ -135,7 +135,7 @@ class PeerInfo(C.Structure):
 ABI_SYMBOLS = [
     "sgi_create", "sgi_destroy", "sgi_resize", "sgi_bind_device_buffers", "sgi_register_gl",
     "sgi_band_setup", "sgi_band_export", "sgi_band_attach", "sgi_frame_image", "sgi_band_timeouts", "sgi_band_reprojection_misses", "sgi_band_stats",
-    "sgi_vpl_prepass", "sgi_render_vpl_cubemaps", "sgi_direct_lighting", "sgi_ssao", "sgi_taa", "sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
+    "sgi_vpl_prepass", "sgi_render_vpl_cubemaps", "sgi_direct_lighting", "sgi_ssao", "sgi_taa", "sgi_cull", "sgi_early_begin", "sgi_cull_early", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise_pass", "sgi_denoise", "sgi_frame",
     "sgi_visible_count", "sgi_get_plane", "sgi_download_plane", "sgi_reset_history", "sgi_synchronize", "sgi_stream",
     "sgi_launch_count", "sgi_last_error", "sgi_version",
 ]

@@ -6,13 +6,10 @@
 // singleScatteringBRDF_Specular :102-115, singleScatteringBRDF_Diffuse_Burley :117-126, Fd_Burley :91-96], applyFog (fog.glsl:37-41),
 // quadraticAttenuation / calculateShadowValue8Samples / calculateShadowValue1Sample / calculateInfiniteShadowValue (pbr.glsl).
 //
-// STATUS: written at the end of round 1 without a GPU minute left — it compiles for sm_100a, it has NOT run on a GPU.  Its GPU
-// parity test (tests/test_zz_direct_lighting.py, against the reference's own pbr.fs compiled by oracle/make_ref_glsl.py) is opt-in
-// (SGI_RUN_UNVALIDATED=1) until it has passed on a B200; nothing else in the library calls this file.  Its logic is checked on
-// the host: tests/test_direct_kernel_on_host.py compiles this very file with g++ (tests/cuda_on_host/host_tu.py) and
-// runs it thread by thread — bit-identical to the compiled shader text.
+// Parity: bit-identical on a B200 to the reference's own pbr.fs compiled by oracle/make_ref_glsl.py (tests/test_zz_direct_lighting.py,
+// profiles/r02a), and on the host, where tests/test_direct_kernel_on_host.py compiles this very file with g++ and runs it thread by thread.
 //
-// First version: one thread per pixel, every operation in the exact IEEE chain of csrc/sgi_math.cuh in the shader's order (only
+// One thread per pixel, every operation in the exact IEEE chain of csrc/sgi_math.cuh in the shader's order (only
 // pow/exp come from the CUDA maths library), so that the first comparison with the shader text is about logic, not rounding.
 #include "sgi_internal.h"
 #include "sgi_math.cuh"

@@ -12,10 +12,8 @@
 // IEEE operations in the shader's / glm's evaluation order) and the output equals the compiled shader text bit for bit; the
 // LINEAR fetch is the filter model of the denoiser's reprojected reads (8-bit sub-texel weights).
 //
-// STATUS: written at the end of round 1 without a GPU minute left — it compiles for sm_100a, it has NOT run on a GPU.  Its logic is
-// checked on the host (tests/test_ssao_kernel_on_host.py: this file compiled by g++ through tests/cuda_on_host/, bit-identical to the
-// reference's ssao.fs / ssao_blur.fs compiled by oracle/make_ref_glsl.py); its GPU test (tests/test_zz_ssao.py) is opt-in
-// (SGI_RUN_UNVALIDATED=1) and nothing else in the library calls it.  Whole-frame handles only (no band halos yet).
+// Parity: bit-identical on a B200 to the reference's ssao.fs / ssao_blur.fs compiled by oracle/make_ref_glsl.py (tests/test_zz_ssao.py,
+// profiles/r02a), and on the host (tests/test_ssao_kernel_on_host.py).  Whole-frame handles only (no band halos yet).
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 

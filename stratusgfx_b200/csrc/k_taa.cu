@@ -10,9 +10,8 @@
 // bit for bit; the filtered read is the 8-bit sub-texel weight model of SURVEY.md Appendix A1.  The history store follows the GL
 // float -> UNORM8 conversion (clamp to [0,1], scale by 255, round to nearest) applied to the binary16 value the blit reads.
 //
-// STATUS: written at the end of round 1 without a GPU minute left — it compiles for sm_100a, it has NOT run on a GPU.  Its logic is
-// checked on the host (tests/test_taa_kernel_on_host.py, bit-identical to the reference's taa.fs compiled by oracle/make_ref_glsl.py);
-// its GPU test (tests/test_zz_taa.py) is opt-in (SGI_RUN_UNVALIDATED=1) and nothing else in the library calls it.
+// Parity: bit-identical on a B200 to the reference's taa.fs compiled by oracle/make_ref_glsl.py (tests/test_zz_taa.py, profiles/r02a),
+// and on the host (tests/test_taa_kernel_on_host.py).
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 

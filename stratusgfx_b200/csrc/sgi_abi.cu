@@ -146,6 +146,8 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
         if (cudaStreamCreateWithPriority(&h->tileStream, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evTablesFree, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evEarly, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evFinal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evCopyDone, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
@@ -175,6 +177,8 @@ int sgi_destroy(SgiHandle h) {
     if (h->evCopyDone) cudaEventDestroy(h->evCopyDone);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->evTablesFree) cudaEventDestroy(h->evTablesFree);
+    if (h->evEarly) cudaEventDestroy(h->evEarly);
     sgi::detachPeers(h);
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
@@ -228,8 +232,16 @@ static int postLaunch(SgiHandle h, int n) {
     return SGI_OK;
 }
 
-static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo) {
+static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo, cudaStream_t stream = nullptr) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
+    if (stream == nullptr) {
+        stream = h->stream;
+        if (h->earlyPending) {                   // an explicit cull supersedes a pending early one: order after it, then overwrite
+            SGI_CUDA(h, cudaSetDevice(h->cp.device));
+            SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evEarly, 0));
+            h->earlyPending = false;
+        }
+    }
     if (fp->totalNumLights < 0 || fp->totalNumLights > SGI_MAX_TOTAL_VPLS_BEFORE_CULLING) return fail(h, SGI_ERR_INVALID_ARG, "sgi_cull: totalNumLights out of range");
     NEED(h, vplData); NEED(h, vplUpdatedData); NEED(h, vplVisibleIndices); NEED(h, infiniteLightShadowMap);
     if (h->buf.atlasEntryByVpl && !h->buf.shadowDiffuseIndices) return fail(h, SGI_ERR_NOT_BOUND, "buffer not bound: shadowDiffuseIndices");
@@ -237,7 +249,7 @@ static int cullImpl(SgiHandle h, const SgiFrameParams* fp, bool colorToo) {
     FrameConsts fc; fillFrameConsts(fp, &fc);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     const AtlasTable atl = atlasTable(h);
-    const int n = launchCull(h->stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
+    const int n = launchCull(stream, fc, bandDims(h), h->buf.vplData, h->buf.atlasEntryByVpl, (const float*)h->buf.infiniteLightShadowMap,
                              h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices, h->cullBallots, h->cullTicket,
                              colorToo ? &atl : nullptr, h->buf.vplCountDevice);
     h->tileListsValid = false;      // tilePos holds positions into the previous cull's compacted table
@@ -268,7 +280,7 @@ int sgi_render_vpl_cubemaps(SgiHandle h, const SgiCubeRenderParams* rp) {
     if (!rp->vplIndices || (rp->numBoxes > 0 && !rp->boxes)) return fail(h, SGI_ERR_NOT_BOUND, "sgi_render_vpl_cubemaps: boxes and vplIndices are required");
     NEED(h, vplData); NEED(h, atlasEntryByVpl); NEED(h, shadowCubeMaps[0]); NEED(h, diffuseCubeMaps[0]);
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
-    return postLaunch(h, launchCubemaps(h->stream, *rp, h->buf.vplData, h->buf.atlasEntryByVpl, h->cp.cube_res, atlasTable(h)));
+    return postLaunch(h, launchCubemaps(rp->stream ? (cudaStream_t)rp->stream : h->stream, *rp, h->buf.vplData, h->buf.atlasEntryByVpl, h->cp.cube_res, atlasTable(h)));
 }
 
 int sgi_ssao(SgiHandle h, const SgiSsaoParams* sp) {
@@ -305,6 +317,24 @@ int sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectPa
 }
 
 int sgi_cull(SgiHandle h, const SgiFrameParams* fp) { return cullImpl(h, fp, false); }
+
+int sgi_early_begin(SgiHandle h, void* stream) {
+    if (!h || !stream) return SGI_ERR_INVALID_ARG;
+    SGI_CUDA(h, cudaSetDevice(h->cp.device));
+    if (h->tablesFreeRecorded) SGI_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->evTablesFree, 0));
+    if (h->joinOutstanding) SGI_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->evJoin, 0));
+    return SGI_OK;
+}
+
+int sgi_cull_early(SgiHandle h, const SgiFrameParams* fp, void* stream, int32_t with_color) {
+    if (!h || !fp || !stream) return SGI_ERR_INVALID_ARG;
+    if (h->earlyPending) return fail(h, SGI_ERR_INVALID_ARG, "sgi_cull_early: the previous early cull has not been consumed by sgi_frame / sgi_cull yet");
+    const int rc = cullImpl(h, fp, with_color != 0, (cudaStream_t)stream);
+    if (rc != SGI_OK) return rc;
+    SGI_CUDA(h, cudaEventRecord(h->evEarly, (cudaStream_t)stream));
+    h->earlyPending = true; h->earlyColored = with_color != 0; h->earlyParams = *fp;
+    return SGI_OK;
+}
 
 int sgi_color(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
@@ -366,6 +396,8 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
                                fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
                                h->gatherCounters, &h->gatherLaunches, &signalled);
     if (h->banded && fuse && !signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
+    SGI_CUDA(h, cudaEventRecord(h->evTablesFree, h->stream));      // the compacted tables and the atlases have been read (sgi_early_begin)
+    h->tablesFreeRecorded = true;
     h->guideValid = true;
     // pass 0 of the denoiser (centre-texel merge) is a per-pixel function of the reservoir: the gather has written it
     // into vplGIDenoisedFbo1's reservoir attachment already, valid for a pass-0 call with the same `time`
@@ -424,6 +456,7 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
                          h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
     if (copyOut && h->copyPending) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evCopyDone, 0));   // the previous frame's rows have left `combined`
     n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_, &signalled);
+    if (merge) SGI_CUDA(h, cudaEventRecord(h->evTablesFree, h->stream));      // an unfused pass 0 reads the visible count after the gather
     if (h->banded) {
         // the pass's boundary CTAs released the neighbours' flags themselves; otherwise a one-thread kernel does it after the pass
         if (!signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
@@ -468,7 +501,20 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
     if (fp->totalNumLights == 0) return SGI_OK;      // `if (perVPLDistToViewer.size() == 0) return;` (BE:1582, 1675, 1817)
     // cull + colour in one launch when the atlas assignment is available on the device (the cull's last CTA colours
     // the compacted table); otherwise the two reference dispatches separately
-    if (h->bound && h->buf.atlasEntryByVpl && h->buf.shadowDiffuseIndices && h->buf.diffuseCubeMaps[0] && h->buf.shadowCubeMaps[0]) {
+    if (h->earlyPending) {
+        // the cull (and, if the caller said the atlases were final, the colouring) of this frame already ran on the early stream
+        // (sgi_cull_early): the main stream only waits for it.  The frame must be the one the early cull was given.
+        const SgiFrameParams& e = h->earlyParams;
+        if (e.totalNumLights != fp->totalNumLights || std::memcmp(e.cascadeProjViews, fp->cascadeProjViews, sizeof(e.cascadeProjViews)) != 0 ||
+            std::memcmp(e.cascadePlanes, fp->cascadePlanes, sizeof(e.cascadePlanes)) != 0 ||
+            std::memcmp(e.infiniteLightDirection, fp->infiniteLightDirection, sizeof(e.infiniteLightDirection)) != 0 ||
+            std::memcmp(e.infiniteLightColor, fp->infiniteLightColor, sizeof(e.infiniteLightColor)) != 0)
+            return fail(h, SGI_ERR_INVALID_ARG, "sgi_frame: the pending sgi_cull_early ran with different lights / sun / cascades than this frame");
+        SGI_CUDA(h, cudaSetDevice(h->cp.device));
+        SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evEarly, 0));
+        h->earlyPending = false;
+        if (!h->earlyColored && (rc = sgi_color(h, fp)) != SGI_OK) return rc;
+    } else if (h->bound && h->buf.atlasEntryByVpl && h->buf.shadowDiffuseIndices && h->buf.diffuseCubeMaps[0] && h->buf.shadowCubeMaps[0]) {
         if ((rc = cullImpl(h, fp, true)) != SGI_OK) return rc;
     } else {
         if ((rc = sgi_cull(h, fp)) != SGI_OK) return rc;
@@ -490,6 +536,7 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         // whatever the side stream holds by now is joined before this call returns, on the error paths too: its kernels read
         // vplUpdatedData / the visible list, which the caller may rebind or the next cull overwrites
         SGI_CUDA(h, cudaEventRecord(h->evJoin, h->tileStream));
+        h->joinOutstanding = true;
         if (rc != SGI_OK) { cudaStreamWaitEvent(h->stream, h->evJoin, 0); return rc; }
     }
     rc = sgi_gather(h, fp);

@@ -214,6 +214,13 @@ struct SgiHandle_ {
     // not read the lists): forked after the cull, joined at the end of the frame
     cudaStream_t tileStream = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // sgi_early_begin / sgi_cull_early: the cull (+ colouring) of the NEXT frame runs on a caller-chosen second stream under the
+    // current frame's denoise passes.  evTablesFree: the current frame's last reader of the compacted tables and the atlases on
+    // the main stream (the gather) is done; evJoin covers the tile stages; evEarly: the early cull is complete.
+    cudaEvent_t evTablesFree = nullptr, evEarly = nullptr;
+    bool tablesFreeRecorded = false, joinOutstanding = false;
+    bool earlyPending = false, earlyColored = false;
+    SgiFrameParams earlyParams{};   // what the pending early cull ran with: the frame that consumes it must agree
     // row bands: a non-owner band sends its lit rows to the owner's frame image with a copy-engine transfer on this stream
     // after its final pass (the transfer overlaps the next frame), then raises its flag in the owner's slab
     cudaStream_t copyStream = nullptr;

@@ -54,6 +54,8 @@ def load_library():
     for name in ("sgi_cull", "sgi_color", "sgi_tile_lists", "sgi_gather", "sgi_denoise", "sgi_frame"):
         getattr(L, name).argtypes = [H, C.POINTER(FrameParams)]
     L.sgi_denoise_pass.argtypes = [H, C.POINTER(FrameParams), C.c_int32]
+    L.sgi_early_begin.argtypes = [H, C.c_void_p]
+    L.sgi_cull_early.argtypes = [H, C.POINTER(FrameParams), C.c_void_p, C.c_int32]
     L.sgi_band_setup.argtypes = [H, C.POINTER(BandParams)]
     L.sgi_band_export.argtypes = [H, C.POINTER(PeerInfo)]
     L.sgi_band_attach.argtypes = [H, C.c_int32, C.POINTER(PeerInfo)]
@@ -215,15 +217,16 @@ class VplGiPass:
         """boxes_u8: uint8 [n, 32] SgiSceneBox records (Scene.boxes())."""
         self.t["sceneBoxes"] = self.torch.from_numpy(np.ascontiguousarray(boxes_u8, np.uint8)).to(self.device)
 
-    def render_vpl_cubemaps(self, vpl_indices):
-        """Renders the cube depth + diffuse maps of the listed VPLs (indices into the bound vplData table) into their atlas layers."""
+    def render_vpl_cubemaps(self, vpl_indices, stream=None):
+        """Renders the cube depth + diffuse maps of the listed VPLs (indices into the bound vplData table) into their atlas layers
+        (on `stream`, a raw CUDA stream pointer, when given: see early_begin)."""
         from ._abi import CubeRenderParams
         idx = vpl_indices if hasattr(vpl_indices, "data_ptr") else self.torch.as_tensor(np.asarray(vpl_indices, np.int32), device=self.device)
         self.t["cubeRenderIdx"] = idx                      # kept alive until the stream has consumed it
-        rp = CubeRenderParams(int(self.t["sceneBoxes"].shape[0]), int(idx.numel()), self.t["sceneBoxes"].data_ptr(), idx.data_ptr())
+        rp = CubeRenderParams(int(self.t["sceneBoxes"].shape[0]), int(idx.numel()), self.t["sceneBoxes"].data_ptr(), idx.data_ptr(), stream)
         self._check(self.L.sgi_render_vpl_cubemaps(self._h, C.byref(rp)))
 
-    # ---- the passes that produce the `ssao` input plane: ssao.fs + ssao_blur.fs (NOT YET VALIDATED ON A GPU, see csrc/k_ssao.cu) ----
+    # ---- the passes that produce the `ssao` input plane: ssao.fs + ssao_blur.fs (csrc/k_ssao.cu) ----
     def ssao(self, structure, rotation, aspectRatio, projPlaneZDist, intensity=5.0):
         """RenderSsaoOcclude_ + RenderSsaoBlur_ over a structure buffer (half4 [rows, W, 4]) -> the half [rows, W] plane, kept as
         self.t["ssao"] (the plane bind() hands to the gather) and returned as a torch tensor."""
@@ -240,7 +243,7 @@ class VplGiPass:
         self._check(self.L.sgi_ssao(self._h, C.byref(sp)))
         return self.t["ssao"]
 
-    # ---- the resolve at the end of the frame: taa.fs (NOT YET VALIDATED ON A GPU, see csrc/k_taa.cu) ----
+    # ---- the resolve at the end of the frame: taa.fs (csrc/k_taa.cu) ----
     def taa(self, screen, prev_screen, velocity):
         """PerformTaaPostFx_ over uint8 [rows, W, 4] current / previous LDR frames and the half2 velocity plane ->
         (half4 [rows, W, 4] resolved colour, uint8 [rows, W, 4] next history), torch tensors kept in self.t."""
@@ -256,7 +259,7 @@ class VplGiPass:
         self._check(self.L.sgi_taa(self._h, C.byref(tp)))
         return self.t["taaOut"], self.t["taaHistory"]
 
-    # ---- the pass before this path: deferred direct lighting, pbr.fs (NOT YET VALIDATED ON A GPU, see csrc/k_direct.cu) ----
+    # ---- the pass before this path: deferred direct lighting, pbr.fs (csrc/k_direct.cu) ----
     def direct_lighting(self, fp, lights=None, shadow_lights=None, shadow_entries=None, sun=True, emission_strength=0.0,
                         depth_bias=0.0, z_near=1.0, z_far=1000.0, point_light_ambient=0.003):
         """pbr.fs over the bound G-buffer -> a half4 [rows, W] plane (kept as self.t["directOut"]): the `screen` input of the GI path.
@@ -302,6 +305,15 @@ class VplGiPass:
     # ---- finer-grained entry points --------------------------------------------------------------------
     def cull(self, fp): self._check(self.L.sgi_cull(self._h, C.byref(fp)))
     def color(self, fp): self._check(self.L.sgi_color(self._h, C.byref(fp)))
+
+    def early_begin(self, stream):
+        """`stream` (raw CUDA stream pointer) waits until the frame in flight has finished reading the tables and the atlases."""
+        self._check(self.L.sgi_early_begin(self._h, stream))
+
+    def cull_early(self, fp, stream, with_color=True):
+        """The next frame's cull (+ colouring) on `stream`; the next frame() waits for it instead of running its own."""
+        self._check(self.L.sgi_cull_early(self._h, C.byref(fp), stream, 1 if with_color else 0))
+
     def tile_lists(self, fp): self._check(self.L.sgi_tile_lists(self._h, C.byref(fp)))
     def gather(self, fp): self._check(self.L.sgi_gather(self._h, C.byref(fp)))
     def denoise_pass(self, fp, i): self._check(self.L.sgi_denoise_pass(self._h, C.byref(fp), i))

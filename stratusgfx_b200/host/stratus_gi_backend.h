@@ -32,12 +32,15 @@ public:
 
     // UpdatePointLights_ (BE:1359-1392), virtual-point-light branch, + InitVplFrameData_ (BE:1281-1292): on the device
     void UpdatePointLights_(const SgiPrepassParams& lights) { Check_(sgi_vpl_prepass(handle_, &lights)); }
+    // the second half of UpdatePointLights_ (BE:1426-1575): the cube shadow / diffuse maps of the lights in frame_->lightsToUpdate,
+    // at most maxShadowUpdatesPerFrame of them per frame (StratusRendererBackend.h:378), rendered into their atlas layers
+    void UpdatePointLightShadowMaps_(const SgiCubeRenderParams& lightsToUpdate) { Check_(sgi_render_vpl_cubemaps(handle_, &lightsToUpdate)); }
 
     // RenderSsaoOcclude_ + RenderSsaoBlur_ (BE:1160-1204): ssao.fs and ssao_blur.fs, producing the `ssao` plane of BindBuffers.
     // (csrc/k_ssao.cu is prepared but has not run on a GPU yet, see include/stratusgi.h)
     void RenderSsao_(const SgiSsaoParams& ssao) { Check_(sgi_ssao(handle_, &ssao)); }
 
-    // PerformTaaPostFx_ (BE:2324-2354): taa.fs and the blit into the history (csrc/k_taa.cu: prepared, not yet run on a GPU)
+    // PerformTaaPostFx_ (BE:2324-2354): taa.fs and the blit into the history (csrc/k_taa.cu)
     void PerformTaaPostFx_(const SgiTaaParams& taa) { Check_(sgi_taa(handle_, &taa)); }
 
     // PerformVirtualPointLightCullingStage1_ (BE:1578-1612): viscull_vpls.cs, without the fence

@@ -55,8 +55,16 @@ def test_opt_in_gpu_tests_of_the_unvalidated_kernels_run_on_the_host(built):
         T.test_taa_against_the_compiled_shader_text(built, "tiny", 1.5)
 
 
+def test_cube_map_production_gpu_test_body_runs_on_the_host(built):
+    """tests/test_zz_cubemaps.py over the host-built library: csrc/k_cubemaps.cu in lockstep mode against the oracle, bit for bit."""
+    from tests import test_zz_cubemaps as Cm
+    with gpu_tests_on_the_host():
+        Cm.check_cubemaps("tiny", "all")
+        Cm.test_rendered_maps_feed_the_frame(built)
+
+
 # ---- the bodies of GPU-suite tests (tests/test_parity_gpu.py), unchanged, over the host-built library --------------------------
-_FAST = ["test_fused_frame_call_equals_staged_calls", "test_reference_method_names_drive_the_same_path", "test_zero_lights_is_a_no_op",
+_FAST = ["test_fused_frame_call_equals_staged_calls", "test_early_cull_gives_the_frames_of_the_serial_order", "test_reference_method_names_drive_the_same_path", "test_zero_lights_is_a_no_op",
          "test_unbound_buffers_and_bad_passes_are_errors"]
 _SLOW = ["test_gather_modes_can_alternate_on_one_handle", "test_cuda_integer_outputs_match_the_glm_golden_fixture"]
 _FAST_BUILT = ["test_no_visible_vpl", "test_resize_then_run"]

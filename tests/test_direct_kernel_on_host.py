@@ -1,4 +1,4 @@
-"""csrc/k_direct.cu (widening row f3, never run on a GPU yet) compiled by g++ (tests/cuda_on_host/host_tu.py: a translated copy, the source is untouched) and executed
+"""csrc/k_direct.cu (widening row f3) compiled by g++ (tests/cuda_on_host/host_tu.py: a translated copy, the source is untouched) and executed
 thread by thread on the host, against the reference's own pbr.fs compiled by oracle/make_ref_glsl.py.  This checks the kernel's
 logic — light loops, shadow paths by view distance, cascade choice, Burley BRDF, emissive, boundHDR — before any GPU time is spent;
 what it cannot check is device-only behaviour (CUDA's powf / expf, launch geometry on real hardware)."""

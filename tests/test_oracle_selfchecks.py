@@ -357,3 +357,27 @@ def test_shader_text_fixture_is_reproducible_where_the_reference_is(built):
         sys.path.remove(os.path.join(here, "golden"))
     want = json.load(open(os.path.join(here, "golden", "tiny_shader_text_golden.json")))
     assert got["frames"] == want["frames"]
+
+
+def test_oracle_cube_maps_agree_with_the_scene_generator():
+    """Widening row f2: orc_render_vpl_cubemaps (float, the spec the CUDA kernel is held to bit for bit) against the scene
+    generator's double-precision maps — the atlases every other test reads: the same surface except on silhouettes, the depth
+    within one unorm16 step."""
+    from oracle import oracle_py as O
+    from stratusgfx_b200.scene import Scene
+    for workload in ("tiny", "c1"):
+        s = Scene(workload)
+        vd, at = s.vpls()
+        sh, df = s.cubemaps()
+        got_d, got_c = np.zeros_like(sh), np.zeros_like(df)
+        idx = np.arange(s.num_vpls, dtype=np.int32)
+        O.render_vpl_cubemaps(s.boxes(), vd, at, idx, s.cube_res, got_d, got_c)
+        slots = at[:, 0] * 320 + at[:, 1]
+        R = s.cube_res
+        a = got_d.reshape(-1, 6, R, R)[slots].astype(np.int32); b = sh.reshape(-1, 6, R, R)[slots].astype(np.int32)
+        assert np.mean(a == b) > 0.99 and np.mean(np.abs(a - b) <= 1) > 0.999, workload
+        ca = got_c.reshape(-1, 6, R, R, 4)[slots]; cb = df.reshape(-1, 6, R, R, 4)[slots]
+        assert np.mean(np.all(ca == cb, axis=-1)) > 0.999, workload
+        # untouched layers stay untouched
+        mask = np.ones(got_d.reshape(-1, 6, R, R).shape[0], bool); mask[slots] = False
+        assert not got_d.reshape(-1, 6, R, R)[mask].any()

@@ -275,3 +275,24 @@ def test_sun_shadow_value_of_the_shader_text(libs):
             values.append(b)
         values = np.array(values)
         assert (values == 0).any() and (values == 1).any() and ((values > 0) & (values < 1)).any()      # shadowed, lit and penumbra all occur
+
+
+def test_cube_map_fragment_stage_equals_the_shader_text(libs):
+    """Widening row f2: the fragment stage of the VPL cube-map pass — shadowVpl.fs main(), compiled from the shader text — against
+    the oracle's restatement (oracle.cpp::shadowVplDepth), bit for bit on random fragments, the far-plane clamp included; and the
+    colour output is the material's base colour unchanged."""
+    from oracle import oracle_py as O
+    _, ref = libs
+    rng = np.random.default_rng(7)
+    ref.refglsl_shadow_vpl.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    for k in range(4000):
+        light = rng.uniform(-200, 200, 3).astype(np.float32)
+        far = np.float32(rng.choice([50.0, 500.0, 123.456]))
+        frag = (light + rng.normal(0, 1, 3) * rng.choice([0.01, 1.0, 40.0, 400.0, 2000.0])).astype(np.float32)
+        base = rng.uniform(0, 1, 4).astype(np.float32)
+        depth, colour = np.zeros(1, np.float32), np.zeros(3, np.float32)
+        ref.refglsl_shadow_vpl(frag.ctypes.data, light.ctypes.data, float(far), base.ctypes.data, depth.ctypes.data, colour.ctypes.data)
+        want = np.float32(O.shadow_vpl_depth(frag, light, float(far)))
+        assert depth[0].view(np.uint32) == want.view(np.uint32), (k, depth[0], want)
+        assert np.array_equal(colour, base[:3])
+        assert 0.0 <= depth[0] <= 1.0

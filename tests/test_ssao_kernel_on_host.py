@@ -1,4 +1,4 @@
-"""csrc/k_ssao.cu (widening row f4, first half; never run on a GPU yet) compiled by g++ (tests/cuda_on_host/host_tu.py) and executed
+"""csrc/k_ssao.cu (widening row f4, first half) compiled by g++ (tests/cuda_on_host/host_tu.py) and executed
 thread by thread on the host, against the reference's own ssao.fs and ssao_blur.fs compiled by oracle/make_ref_glsl.py.  Both
 passes are exact-tier arithmetic, so the two R16F planes must agree bit for bit."""
 import ctypes as C

@@ -1,4 +1,4 @@
-"""csrc/k_taa.cu (widening row f4, second half; never run on a GPU yet) compiled by g++ (tests/cuda_on_host/host_tu.py) and executed
+"""csrc/k_taa.cu (widening row f4, second half) compiled by g++ (tests/cuda_on_host/host_tu.py) and executed
 thread by thread on the host, against the reference's own taa.fs compiled by oracle/make_ref_glsl.py: the RGBA16F target must agree
 bit for bit, and the history plane must be the GL float -> UNORM8 conversion of it."""
 import ctypes as C

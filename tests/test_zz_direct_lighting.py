@@ -1,13 +1,9 @@
 """Widening row f3 — deferred direct lighting (pbr.fs) on the device, against the reference's own shader text compiled by
-oracle/make_ref_glsl.py.  The kernel (csrc/k_direct.cu) was written at the end of round 1 with no GPU time left: this test is
-OPT-IN (SGI_RUN_UNVALIDATED=1) until it has passed on a B200, and nothing else depends on the kernel."""
-import os
-
+oracle/make_ref_glsl.py.  Green on a B200 since round 2 (profiles/r02a); the same body runs over the host-built library in the CPU suite."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SGI_RUN_UNVALIDATED", "") != "1",
-                                                  reason="csrc/k_direct.cu has not been validated on a GPU yet (set SGI_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("workload", ["tiny", "c1"])

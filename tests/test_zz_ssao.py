@@ -1,15 +1,11 @@
 """Widening row f4, first half — the two SSAO passes (ssao.fs, ssao_blur.fs) on the device through sgi_ssao, against the reference's
-own shader text compiled by oracle/make_ref_glsl.py.  The kernels (csrc/k_ssao.cu) were written at the end of round 1 with no GPU
-time left: this test is OPT-IN (SGI_RUN_UNVALIDATED=1) until it has passed on a B200, and nothing else depends on the kernels.
-Their logic already equals the shader text bit for bit on the host (tests/test_ssao_kernel_on_host.py); every operation is an
-IEEE one that CUDA rounds as the CPU does, so the bar here is the same: both R16F planes bit-exact."""
-import os
-
+own shader text compiled by oracle/make_ref_glsl.py.  The kernels' logic equals the
+shader text bit for bit on the host too (tests/test_ssao_kernel_on_host.py); every operation is an IEEE one that CUDA rounds as the
+CPU does, so the bar is both R16F planes bit-exact (green on a B200 since round 2, profiles/r02a)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SGI_RUN_UNVALIDATED", "") != "1",
-                                                  reason="csrc/k_ssao.cu has not been validated on a GPU yet (set SGI_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("workload", ["tiny", "c1"])

@@ -1,15 +1,11 @@
 """Widening row f4, second half — temporal anti-aliasing (taa.fs) on the device through sgi_taa, against the reference's own shader
-text compiled by oracle/make_ref_glsl.py.  The kernel (csrc/k_taa.cu) was written at the end of round 1 with no GPU time left: this
-test is OPT-IN (SGI_RUN_UNVALIDATED=1) until it has passed on a B200, and nothing else depends on the kernel.  Its logic already
-equals the shader text bit for bit on the host (tests/test_taa_kernel_on_host.py); every operation is an IEEE one that CUDA rounds
+text compiled by oracle/make_ref_glsl.py.  Green on a B200 since round 2 (profiles/r02a).  The kernel's logic
+equals the shader text bit for bit on the host too (tests/test_taa_kernel_on_host.py); every operation is an IEEE one that CUDA rounds
 as the CPU does, so the bar here is the same."""
-import os
-
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SGI_RUN_UNVALIDATED", "") != "1",
-                                                  reason="csrc/k_taa.cu has not been validated on a GPU yet (set SGI_RUN_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("workload,yaw", [("tiny", 1.5), ("c1", 3.0)])
