@@ -69,21 +69,29 @@ prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* _
     guide[p] = make_float4(nn.x, nn.y, nn.z, __ldg(depth + p));
 }
 
-// ---- final-pass epilogue: temporal accumulation + re-modulation (vpl_pbr_gi_denoise.fs:337-434) ------------
-// `centerDepth` comes from the guide plane (a bit copy of the depth texel), so the depth plane is not read again here
-SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 centerNormal, float centerDepth, f3 shadowFactor) {
+// ---- temporal pre-pass (vpl_pbr_gi_denoise.fs:337-425 without the terms that depend on this frame's filtered radiance) --------
+// Everything of the final pass's temporal half that does NOT need the filter's result — the reprojected reads of the previous
+// frame (depth, normal, GI: LINEAR; ids: NEAREST), the history-reset decision, the new history length — is a per-pixel function of
+// planes that exist when the frame starts.  It runs as its own streaming kernel on the side stream, under the gather (which is
+// bound by instruction issue, not by DRAM), and leaves (prevGi.rgb, 1 / history) in a float4 plane; the final pass then only
+// blends and re-modulates (finalEpilogue below: three loads, two stores).  Inside the final à-trous pass the same code cost ten
+// dependent loads per output at 35 % occupancy (80 registers) — half of that kernel's 0.31 ms.
+// The arithmetic is unchanged: the decision `similarity < 0.99` (:410-418) and the stored history are exact tier.
+__global__ void __launch_bounds__(256)
+temporalKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
     const int W = bd.W, rows = bd.rows;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ly = bd.c0 + blockIdx.y * 8 + (threadIdx.x >> 5);        // computed rows only
+    if (x >= W || ly >= bd.c0 + bd.crows) return;
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * W + x;
     const float u = fdiv(fadd((float)x, 0.5f), (float)W), v = fdiv(fadd((float)y, 0.5f), (float)bd.fullH);
-    const f4 screenColor = loadHalf4(io.screen, p);
-    const f4 gi4 = loadHalf4(io.illum, p);
-    const f3 gi = mk3(gi4.x, gi4.y, gi4.z);
     const uint32_t vel = __ldg(io.velocity + p);
     const float pu = fsub(u, h2f((unsigned short)(vel & 0xffffu))), pv = fsub(v, h2f((unsigned short)(vel >> 16)));
     float historyAccum = h2f(__ldg(io.historyIn + p));
     float accumMultiplier = 1.0f;
-    const f3 currGi = shadowFactor;
+    const float centerDepth = __ldg(io.depth + p);
+    const uint32_t normalBits = __ldg(io.normal + p);
 
     // reprojected reads; rows are band-local (previous-frame planes hold the same rows)
     Bilin k = bilinSetup(pu, pv, W, bd.fullH);
@@ -124,8 +132,9 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
     // the history-reset decision `similarity < 0.99` (:410-418), exact.  Shortcut: when the reprojected tap is the same texel with
     // the same normal bits, depth and id as the current pixel (every pixel of a static camera), prevCenterNormal is bit-identical
     // to centerNormal, so wn = fl(n.n) = 1 +- 3e-7, wz = exp(-0) = 1, wid = 1 and the test cannot fire.
-    const bool sameTexel = onTexel && prevNormalBits == __ldg(io.normal + p) && prevCenterDepth == centerDepth && currId == prevId;
+    const bool sameTexel = onTexel && prevNormalBits == normalBits && prevCenterDepth == centerDepth && currId == prevId;
     if (!sameTexel) {
+        const f3 centerNormal = decodeNormal(normalBits);        // bit-identical to the guide plane's normal
         const f3 prevCenterNormal = normalize(pn * 2.0f - 1.0f);
         const float wn = vmax(0.0f, dot(centerNormal, prevCenterNormal));
         const float wz = expf(-fabsf(fsub(centerDepth, prevCenterDepth)));
@@ -135,16 +144,27 @@ SGI_DEV void finalEpilogue(const FrameConsts& fc, const BandDims& bd, const Deno
     }
     historyAccum = vmin(fadd(1.0f, fmul(historyAccum, accumMultiplier)), fc.framesPerSecond);
     const float maxAccumulationFactor = __fdividef(1.0f, historyAccum);      // radiance tier (the stored history itself is exact)
-    const f3 illumAvg = mix(prevGi, currGi, maxAccumulationFactor);
+    io.historyOut[p] = f2h(historyAccum);
+    io.temporal[p] = make_float4(prevGi.x, prevGi.y, prevGi.z, maxAccumulationFactor);
+}
+
+// ---- final-pass epilogue: blend with the reprojected history and re-modulate (vpl_pbr_gi_denoise.fs:424-434) --------------
+SGI_DEV void finalEpilogue(const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 shadowFactor) {
+    const int W = bd.W;
+    const int y = ly + bd.yOffset;
+    const size_t p = (size_t)ly * W + x;
+    const float4 t = __ldg(io.temporal + p);                 // (prevGi.rgb, 1 / history) from temporalKernel
+    const f4 screenColor = loadHalf4(io.screen, p);
+    const f4 gi4 = loadHalf4(io.illum, p);
+    const f3 gi = mk3(gi4.x, gi4.y, gi4.z);
+    const f3 illumAvg = mix(mk3(t.x, t.y, t.z), shadowFactor, t.w);
     const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
     const uint2 cv = packHalf4(combined.x, combined.y, combined.z, 1.0f), gv = packHalf4(illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
-    const unsigned short hv = f2h(historyAccum);
     io.combinedOut[p] = cv;
     io.giOut[p] = gv;
-    io.historyOut[p] = hv;
-    // row bands: this frame's GI/history boundary rows go to the neighbours' halos (reprojection may land there next
-    // frame), and the lit pixel goes straight into the root band's frame image — the "gather", overlapped with the pass
-    pushGiHistory(io.links, y, x, W, gv, hv);
+    // row bands: this frame's GI boundary rows go to the neighbours' halos (reprojection may land there next frame; the history
+    // plane is only ever read at the pixel itself), and — with SGI_IMAGE_PUSH=kernel — the lit pixel into the owner's frame image
+    pushGi(io.links, y, x, W, gv);
     if (io.links.image != nullptr) io.links.image[(size_t)y * W + x] = cv;
 }
 
@@ -165,7 +185,7 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
     const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
     io.reservoirOut[p] = rv;
     pushRes(io.links, y, x, bd.W, rv);
-    if (FINAL) finalEpilogue(fc, bd, io, x, ly, centerNormal, centerDepth, shadowFactor);
+    if (FINAL) finalEpilogue(bd, io, x, ly, shadowFactor);
 }
 
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
@@ -233,7 +253,7 @@ SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x,
 }
 template <bool FINAL, int S>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
-atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_constant__ DenoiseIO io) {
+atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __grid_constant__ DenoiseIO io) {
     SGI_PDL_WAIT();                                          // (chained launches, sgi_internal.h) the previous pass / the gather is complete from here on
     SGI_PDL_LAUNCH_DEPENDENTS();
     const int W = bd.W, rows = bd.rows;
@@ -251,14 +271,11 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
     if (live) {
 
     if (FINAL) {
-        // the temporal epilogue reads ten more planes per output, first touched in this kernel: ask L2 for them now so the
-        // DRAM latency overlaps the filter loop (the reprojected previous-frame taps sit at or near the same pixel)
+        // the epilogue reads three more planes per output, first touched in this kernel: ask L2 for them now
         #pragma unroll
         for (int k = 0; k < kLat; ++k) {
             const size_t p = (size_t)min(c0 + (m0 + k) * s + r, cEnd - 1) * W + x;
-            prefetchL2(io.screen + p); prefetchL2(io.illum + p); prefetchL2(io.velocity + p); prefetchL2(io.historyIn + p);
-            prefetchL2(io.ids + p); prefetchL2(io.normal + p); prefetchL2(io.prevDepth + p); prefetchL2(io.prevNormal + p);
-            prefetchL2(io.prevGi + p); prefetchL2(io.prevIds + p);
+            prefetchL2(io.temporal + p); prefetchL2(io.screen + p); prefetchL2(io.illum + p);
         }
     }
     float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
@@ -296,7 +313,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
         const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
         io.reservoirOut[(size_t)ly * W + x] = rv;
         pushRes(io.links, ly + bd.yOffset, x, W, rv);
-        if (FINAL) finalEpilogue(fc, bd, io, x, ly, mk3(cen[k].x, cen[k].y, cen[k].z), __ldg(&io.guide[(size_t)ly * W + x].w), shadowFactor);
+        if (FINAL) finalEpilogue(bd, io, x, ly, shadowFactor);
     }
     }   // live
     if (io.links.doneCounter != nullptr) {                   // (uniform per CTA) a producer CTA counts itself once all its threads have stored
@@ -316,6 +333,7 @@ atrousKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_c
 bool preloadDenoiseKernels() {
     cudaFuncAttributes a; bool ok = true;
     ok = ok && cudaFuncGetAttributes(&a, prepareGuideKernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, temporalKernel) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<false>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, mergeKernel<true>) == cudaSuccess;
     ok = ok && cudaFuncGetAttributes(&a, atrousKernel<false, 0>) == cudaSuccess;
@@ -332,6 +350,12 @@ bool preloadDenoiseKernels() {
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide) {
     const size_t n = (size_t)bd.W * bd.rows;
     prepareGuideKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, normal, depth, guide);
+    return 1;
+}
+
+int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io) {
+    dim3 grid((bd.W + 31) / 32, (bd.crows + 7) / 8);
+    temporalKernel<<<grid, 256, 0, stream>>>(fc, bd, io);
     return 1;
 }
 

@@ -83,7 +83,10 @@ SGI_DEV int cubeTexelDecided(f3 d, int res) {
     const float inv = rcpFast(ma), fres = (float)res;
     const float se = fma_(sc * inv, 0.5f, 0.5f) * fres, te = fma_(tc * inv, 0.5f, 0.5f) * fres;
     const float sf = floorf(se), tf = floorf(te);
-    const float eps = 1e-4f;
+    // disagreement between this estimate and the exact chain is at most 32 * (|sc/ma| * (2^-23 + 2^-24) * 0.5 + 2^-24) + 32 * 0.5 * 3 * 2^-24
+    // < 8e-6 texels for res = 32 (rcp.approx: 1 ulp; one product, one fma; the exact side: one division, one add): 3e-5 keeps a
+    // factor 4 and sends 3x fewer lanes to the exact fallback than the 1e-4 of round 1
+    const float eps = 3e-5f * (fres * (1.0f / 32.0f));
     const bool sure = (se - sf > eps) && (sf + 1.0f - se > eps) && (te - tf > eps) && (tf + 1.0f - te > eps);
     if (!sure) return exactCubeTexel(d, res);
     const int i = iclamp((int)sf, 0, res - 1), j = iclamp((int)tf, 0, res - 1);

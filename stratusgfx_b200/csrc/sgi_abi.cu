@@ -34,7 +34,7 @@ static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h
 static BandDims bandDims(const SgiHandle h);
 
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->slab, (void**)&h->patchScratch, (void**)&h->tilePos};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->temporal, &h->slab, (void**)&h->patchScratch, (void**)&h->tilePos};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
     h->resA = h->resB = nullptr;
     h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
@@ -68,6 +68,7 @@ static int allocPlanes(SgiHandle h) {
     void** half4s[] = {&h->giColor, &h->giReservoir, &h->combined};
     for (void** p : half4s) SGI_CUDA(h, cudaMalloc(p, n * 8));
     SGI_CUDA(h, cudaMalloc(&h->guide, n * 16));
+    SGI_CUDA(h, cudaMalloc(&h->temporal, n * 16));
     SGI_CUDA(h, cudaMalloc((void**)&h->patchScratch, (size_t)patchScratchInts(bandDims(h)) * sizeof(int)));
     {
         const size_t tiles = (size_t)(h->cp.width / SGI_TILE_DIVISOR) * (size_t)(h->cp.rows / SGI_TILE_DIVISOR);
@@ -75,6 +76,7 @@ static int allocPlanes(SgiHandle h) {
     }
     h->guideValid = false;
     h->tileListsValid = false;
+    h->temporalDone = false;
     // per-frame clears to (0,0,0,1) only matter for planes that are read before written; the previous-frame FBO is
     // never cleared and starts at zero.  Reservoir halo rows start at zero too.
     SGI_CUDA(h, cudaMemsetAsync(h->slab, 0, off, h->stream));
@@ -148,6 +150,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
         if (cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evTablesFree, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evEarly, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaEventCreateWithFlags(&h->evTemporal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evFinal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evCopyDone, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
@@ -179,6 +182,7 @@ int sgi_destroy(SgiHandle h) {
     if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->evTablesFree) cudaEventDestroy(h->evTablesFree);
     if (h->evEarly) cudaEventDestroy(h->evEarly);
+    if (h->evTemporal) cudaEventDestroy(h->evTemporal);
     sgi::detachPeers(h);
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
@@ -215,6 +219,7 @@ int sgi_bind_device_buffers(SgiHandle h, const SgiBuffers* buffers) {
     h->guideValid = false;
     h->pass0Fused = false;
     h->tileListsValid = false;
+    h->temporalDone = false;
     return SGI_OK;
 }
 
@@ -382,6 +387,7 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
         // a new band frame starts here.  Neighbours must be done with the previous frame (their final pass read the halo rows
         // this gather is about to overwrite) before the boundary rows of pass 0 are pushed into their memory.
         ++h->frameNo;
+        h->gatherDoneThisFrame = true;
         const int prevDone = h->frameNo > 1 ? sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters) : 0;
         if (fuse) {
             links = sgi::bandLinks(h, 0, false, prevDone);               // the CTAs that push wait inside the kernel
@@ -403,6 +409,41 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
     // into vplGIDenoisedFbo1's reservoir attachment already, valid for a pass-0 call with the same `time`
     h->pass0Fused = h->cp.denoise_iters > 1;
     h->pass0Time = fp->time;
+    return postLaunch(h, n);
+}
+
+// The temporal pre-pass of the frame in flight (k_denoise.cu temporalKernel): reads the previous frame's GI / history / G-buffer
+// planes and this frame's velocity / id / normal / depth, writes this frame's history and the (prevGi, 1 / history) plane the final
+// pass blends with.  sgi_frame forks it onto the side stream at the start of the frame; a caller of the staged entry points gets it
+// on the main stream right before the final pass.
+static int temporalOn(SgiHandle h, const SgiFrameParams* fp, cudaStream_t stream) {
+    NEED(h, depth); NEED(h, normal); NEED(h, velocity); NEED(h, id); NEED(h, prevNormal); NEED(h, prevId); NEED(h, prevDepth);
+    FrameConsts fc; fillFrameConsts(fp, &fc);
+    DenoiseIO io;
+    std::memset(&io, 0, sizeof(io));
+    io.velocity = (const uint32_t*)h->buf.velocity; io.normal = (const uint32_t*)h->buf.normal;
+    io.ids = (const float*)h->buf.id; io.depth = (const float*)h->buf.depth;
+    io.prevNormal = (const uint32_t*)h->buf.prevNormal; io.prevIds = (const float*)h->buf.prevId; io.prevDepth = (const float*)h->buf.prevDepth;
+    io.prevGi = (const uint2*)h->giIllum[h->cur ^ 1];
+    io.historyIn = (const unsigned short*)h->history[h->cur ^ 1];
+    io.historyOut = (unsigned short*)h->history[h->cur];
+    io.temporal = (float4*)h->temporal;
+    io.links = sgi::noLinks();
+    int n = 0;
+    if (h->banded) {
+        io.links.reprojMisses = h->flags + 3;
+        // the reprojected taps may land in halo rows of the previous frame's GI plane, which the neighbours' final passes stored:
+        // wait (in stream order) until both have completed that frame.  frameNo still counts the previous frame here when this
+        // runs before the frame's gather.
+        const int64_t prevFrame = h->gatherDoneThisFrame ? h->frameNo - 1 : h->frameNo;
+        if (prevFrame > 0) {
+            const int32_t* f0 = h->peer[SGI_PEER_UP].attached ? h->flags + 0 : nullptr;
+            const int32_t* f1 = h->peer[SGI_PEER_DOWN].attached ? h->flags + 1 : nullptr;
+            n += sgi::launchWaitFlags(stream, f0, f1, sgi::bandEpoch(prevFrame, h->cp.denoise_iters), h->flags + 2);
+        }
+    }
+    n += launchTemporal(stream, fc, bandDims(h), io);
+    h->temporalDone = true;
     return postLaunch(h, n);
 }
 
@@ -451,6 +492,11 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         // (with SGI_IMAGE_PUSH=kernel the final pass's flag also tells the owner that the image rows landed: host-launched signal)
         if (!(final_ && sgi::imagePushByKernel())) sgi::armInKernelSignal(h, &io.links, sgi::bandEpoch(h->frameNo, pass + 1));
     }
+    if (final_) {
+        if (!h->temporalDone) { const int rc = temporalOn(h, fp, h->stream); if (rc != SGI_OK) return rc; }
+        else if (h->temporalForked) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evTemporal, 0));
+        io.temporal = (float4*)h->temporal;
+    }
     bool signalled = false;
     const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && !sgi::imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached &&
                          h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
@@ -482,7 +528,7 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
             h->imageWaitedFrame = h->frameNo - 1;
         }
     }
-    if (final_) { h->cur ^= 1; h->guideValid = false; }   // swap with the previous-frame FBO (BE:1949-1951)
+    if (final_) { h->cur ^= 1; h->guideValid = false; h->temporalDone = false; h->temporalForked = false; h->gatherDoneThisFrame = false; }   // swap with the previous-frame FBO (BE:1949-1951)
     return postLaunch(h, n);
 }
 
@@ -499,6 +545,16 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
     int rc;
     if (fp->totalNumLights == 0) return SGI_OK;      // `if (perVPLDistToViewer.size() == 0) return;` (BE:1582, 1675, 1817)
+    // The temporal pre-pass only reads planes that exist when the frame starts, so it goes to the side stream first of all and runs
+    // under the cull and the gather (which leave the DRAM idle); the final denoise pass waits for it.
+    if (h->bound && h->buf.velocity && h->buf.id && h->buf.prevNormal && h->buf.prevId && h->buf.prevDepth && h->buf.depth && h->buf.normal && !h->temporalDone) {
+        SGI_CUDA(h, cudaSetDevice(h->cp.device));
+        SGI_CUDA(h, cudaEventRecord(h->evFork, h->stream));
+        SGI_CUDA(h, cudaStreamWaitEvent(h->tileStream, h->evFork, 0));
+        if ((rc = temporalOn(h, fp, h->tileStream)) != SGI_OK) return rc;
+        SGI_CUDA(h, cudaEventRecord(h->evTemporal, h->tileStream));
+        h->temporalForked = true;
+    }
     // cull + colour in one launch when the atlas assignment is available on the device (the cull's last CTA colours
     // the compacted table); otherwise the two reference dispatches separately
     if (h->earlyPending) {

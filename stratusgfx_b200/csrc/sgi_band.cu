@@ -96,14 +96,14 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
         PushTarget& t = which == SGI_PEER_UP ? L.up : L.down;
         const SgiPeerInfo& pi = p.info;
         t.res = (uint2*)(p.base + pi.off_res[resIndex]);
-        if (final_) { t.gi = (uint2*)(p.base + pi.off_gi[h->cur]); t.hist = (unsigned short*)(p.base + pi.off_hist[h->cur]); }
+        if (final_) t.gi = (uint2*)(p.base + pi.off_gi[h->cur]);
         t.yOffset = pi.y_offset;
         // the neighbour's halo on my side: its held rows minus its computed rows, intersected with the rows I compute
         const int lo = which == SGI_PEER_UP ? pi.compute_y0 + pi.compute_rows : pi.y_offset;
         const int hi = which == SGI_PEER_UP ? pi.y_offset + pi.rows : pi.compute_y0;
         t.firstRow = lo > myC0 ? lo : myC0;
         t.lastRow = hi < myC1 ? hi : myC1;
-        if (t.firstRow >= t.lastRow) { t.res = nullptr; t.gi = nullptr; t.hist = nullptr; }
+        if (t.firstRow >= t.lastRow) { t.res = nullptr; t.gi = nullptr; }
     }
     if (waitEpoch != 0) {          // my flags[0] is written by the band above, flags[1] by the band below
         L.waitUp = h->peer[SGI_PEER_UP].attached ? h->flags + 0 : nullptr;

@@ -23,7 +23,6 @@ struct BandDims {
 struct PushTarget {
     uint2* res;                // neighbour's reservoir plane written by this pass (half4), or nullptr
     uint2* gi;                 // neighbour's GI plane of this frame (half4; final pass)
-    unsigned short* hist;      // neighbour's history plane of this frame (half; final pass)
     int yOffset;               // neighbour's first held frame row
     int firstRow, lastRow;     // frame rows [firstRow, lastRow) of mine that the neighbour holds as halo
 };
@@ -167,13 +166,9 @@ __device__ __forceinline__ void pushRes(const BandLinks& L, int y, int x, int W,
     if (L.up.res != nullptr && y >= L.up.firstRow && y < L.up.lastRow) L.up.res[(size_t)(y - L.up.yOffset) * W + x] = v;
     if (L.down.res != nullptr && y >= L.down.firstRow && y < L.down.lastRow) L.down.res[(size_t)(y - L.down.yOffset) * W + x] = v;
 }
-__device__ __forceinline__ void pushGiHistory(const BandLinks& L, int y, int x, int W, uint2 gi, unsigned short hist) {
-    if (L.up.gi != nullptr && y >= L.up.firstRow && y < L.up.lastRow) {
-        const size_t q = (size_t)(y - L.up.yOffset) * W + x; L.up.gi[q] = gi; L.up.hist[q] = hist;
-    }
-    if (L.down.gi != nullptr && y >= L.down.firstRow && y < L.down.lastRow) {
-        const size_t q = (size_t)(y - L.down.yOffset) * W + x; L.down.gi[q] = gi; L.down.hist[q] = hist;
-    }
+__device__ __forceinline__ void pushGi(const BandLinks& L, int y, int x, int W, uint2 gi) {
+    if (L.up.gi != nullptr && y >= L.up.firstRow && y < L.up.lastRow) L.up.gi[(size_t)(y - L.up.yOffset) * W + x] = gi;
+    if (L.down.gi != nullptr && y >= L.down.firstRow && y < L.down.lastRow) L.down.gi[(size_t)(y - L.down.yOffset) * W + x] = gi;
 }
 #endif
 
@@ -187,6 +182,7 @@ struct DenoiseIO {
     const float* prevIds;
     const float* prevDepth;
     const float4* guide;          // library-owned: (decoded normal, depth) of every pixel of this frame
+    float4* temporal;             // library-owned: (reprojected previous GI, 1 / history) of every pixel — temporalKernel writes, the final pass reads
     const uint2* illum;           // half4: the demodulation plane (vplGIFbo attachment 0)
     const uint2* shadowsIn;       // half4: reservoir input of this pass
     const uint2* prevGi;          // half4
@@ -241,6 +237,11 @@ struct SgiHandle_ {
     unsigned short* tilePos = nullptr;   // [tiles][12] per-tile lists as positions in the compacted VPL table (tile-list gather)
     bool tileListsValid = false;    // sgi_tile_lists ran since the last bind
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
+    void* temporal = nullptr;       // float4 (reprojected previous GI, 1 / history): the temporal pre-pass of this frame (k_denoise.cu)
+    bool temporalDone = false;      // launched for the frame in flight (sgi_frame forks it; the final pass launches it if nobody did)
+    bool temporalForked = false;    // ... on the side stream: the final pass waits for evTemporal
+    bool gatherDoneThisFrame = false;   // (bands) frameNo already counts the frame in flight
+    cudaEvent_t evTemporal = nullptr;
     bool guideValid = false;        // set by the gather (or the first denoise pass), cleared by bind and the final pass
     bool pass0Fused = false;        // the gather of this frame already wrote denoise pass 0 into resA, for `pass0Time`
     float pass0Time = 0.0f;
@@ -313,6 +314,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos,
                  int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
                  bool* signalled /* out: the kernel releases the neighbours' flags itself */);
+int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
                       bool* signalled /* out: the kernel releases the neighbours' flags itself */);

@@ -18,7 +18,7 @@ struct HostPeer { int32_t present, y_offset, rows, compute_y0, compute_rows, ran
 namespace {
 struct State {
     SgiHandle_ h;
-    std::vector<float4> guide;
+    std::vector<float4> guide, temporal;
     std::vector<uint2> giColor, giReservoir;
     int gatherCounters[2] = {0, 0};
     bool kernelSignal = true;
@@ -69,6 +69,7 @@ extern "C" int host_band_init(int W, int fullH, int cubeRes, int csmRes, int ite
     }
     const size_t n = (size_t)W * rows;
     st->guide.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
+    st->temporal.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
     st->giColor.assign(n, make_uint2(0u, 0u)); st->giReservoir.assign(n, make_uint2(0u, 0u));
     st->kernelSignal = kernelSignal != 0;
     return 0;
@@ -116,6 +117,20 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
         if (h.banded) {
             io.links = bandLinks(&h, pass % 2, final_, bandEpoch(h.frameNo, pass));
             if (st->kernelSignal) armInKernelSignal(&h, &io.links, bandEpoch(h.frameNo, pass + 1));
+        }
+        if (final_) {
+            // the temporal pre-pass (temporalOn, csrc/sgi_abi.cu): after the neighbours have completed the previous frame, whose
+            // final passes stored the GI halo rows the reprojected taps may read
+            io.temporal = st->temporal.data();
+            DenoiseIO tio = io;
+            tio.links = noLinks();
+            if (h.banded) {
+                tio.links.reprojMisses = h.flags + 3;
+                if (h.frameNo > 1)
+                    launchWaitFlags(nullptr, h.peer[SGI_PEER_UP].attached ? h.flags + 0 : nullptr, h.peer[SGI_PEER_DOWN].attached ? h.flags + 1 : nullptr,
+                                    bandEpoch(h.frameNo - 1, iters), h.flags + 2);
+            }
+            launchTemporal(nullptr, fc, bd, tio);
         }
         signalled = false;
         launchDenoisePass(nullptr, fc, bd, io, false, final_, &signalled);

@@ -17,6 +17,7 @@ extern "C" int host_denoise(const SgiFrameParams* fp, int W, int H, int iters, c
     const size_t P = (size_t)W * H;
     std::vector<float4> guide(P);
     std::vector<uint2> res[2] = {std::vector<uint2>(P), std::vector<uint2>(P)};
+    std::vector<float4> temporal(P);
     sgi::launchPrepareGuide(nullptr, bd, normal, depth, guide.data());
     for (int pass = 0; pass < iters; ++pass) {
         const bool merge = pass < 1, final_ = pass + 1 == iters;
@@ -31,6 +32,8 @@ extern "C" int host_denoise(const SgiFrameParams* fp, int W, int H, int iters, c
         io.combinedOut = (uint2*)combinedOutH4; io.giOut = (uint2*)giOutH4; io.historyOut = historyOut;
         io.multiplier = (1 << pass) - 1;
         io.guide = guide.data();
+        io.temporal = temporal.data();
+        if (final_) sgi::launchTemporal(nullptr, fc, bd, io);      // the temporal pre-pass (sgi_frame runs it on the side stream at the start of the frame)
         sgi::launchDenoisePass(nullptr, fc, bd, io, merge, final_, nullptr);
         std::memcpy((uint2*)passReservoirsH4 + (size_t)pass * P, res[pass % 2].data(), P * sizeof(uint2));
     }
