@@ -69,6 +69,8 @@ prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* _
     guide[p] = make_float4(nn.x, nn.y, nn.z, __ldg(depth + p));
 }
 
+SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- temporal pre-pass (vpl_pbr_gi_denoise.fs:337-425 without the terms that depend on this frame's filtered radiance) --------
 // Everything of the final pass's temporal half that does NOT need the filter's result — the reprojected reads of the previous
 // frame (depth, normal, GI: LINEAR; ids: NEAREST), the history-reset decision, the new history length — is a per-pixel function of
@@ -85,13 +87,17 @@ temporalKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid
     if (x >= W || ly >= bd.c0 + bd.crows) return;
     const int y = ly + bd.yOffset;
     const size_t p = (size_t)ly * W + x;
+    // the reprojected taps sit at or next to this pixel: ask L2 for those lines while the velocity (which decides the exact
+    // addresses) is still on its way, so the kernel pays one DRAM latency per thread instead of two
+    prefetchL2(io.prevDepth + p); prefetchL2(io.prevNormal + p); prefetchL2(io.prevGi + p); prefetchL2(io.prevIds + p);
     const float u = fdiv(fadd((float)x, 0.5f), (float)W), v = fdiv(fadd((float)y, 0.5f), (float)bd.fullH);
     const uint32_t vel = __ldg(io.velocity + p);
-    const float pu = fsub(u, h2f((unsigned short)(vel & 0xffffu))), pv = fsub(v, h2f((unsigned short)(vel >> 16)));
     float historyAccum = h2f(__ldg(io.historyIn + p));
-    float accumMultiplier = 1.0f;
     const float centerDepth = __ldg(io.depth + p);
     const uint32_t normalBits = __ldg(io.normal + p);
+    const float currId = __ldg(io.ids + p);
+    const float pu = fsub(u, h2f((unsigned short)(vel & 0xffffu))), pv = fsub(v, h2f((unsigned short)(vel >> 16)));
+    float accumMultiplier = 1.0f;
 
     // reprojected reads; rows are band-local (previous-frame planes hold the same rows)
     Bilin k = bilinSetup(pu, pv, W, bd.fullH);
@@ -121,7 +127,6 @@ temporalKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid
         const f4 g00 = loadHalf4(io.prevGi, q00), g10 = loadHalf4(io.prevGi, q10), g01 = loadHalf4(io.prevGi, q01), g11 = loadHalf4(io.prevGi, q11);
         prevGi = mk3(bilinMix(k, g00.x, g10.x, g01.x, g11.x), bilinMix(k, g00.y, g10.y, g01.y, g11.y), bilinMix(k, g00.z, g10.z, g01.z, g11.z));
     }
-    const float currId = __ldg(io.ids + p);
     const int ni = iclamp((int)floorf(fmul(pu, (float)W)), 0, W - 1);
     const int njFrame = iclamp((int)floorf(fmul(pv, (float)bd.fullH)), 0, bd.fullH - 1);
     const int nj = iclamp(njFrame - bd.yOffset, 0, rows - 1);
@@ -191,7 +196,6 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 
-SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 

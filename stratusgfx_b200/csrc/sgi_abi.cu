@@ -152,6 +152,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
         if (cudaEventCreateWithFlags(&h->evEarly, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evTemporal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking) != cudaSuccess) return bail(SGI_ERR_CUDA);
+        if (cudaStreamCreateWithPriority(&h->auxStream, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evFinal, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evCopyDone, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
     }
@@ -176,6 +177,7 @@ int sgi_destroy(SgiHandle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->tileStream) { cudaStreamSynchronize(h->tileStream); cudaStreamDestroy(h->tileStream); }
     if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
+    if (h->auxStream) { cudaStreamSynchronize(h->auxStream); cudaStreamDestroy(h->auxStream); }
     if (h->evFinal) cudaEventDestroy(h->evFinal);
     if (h->evCopyDone) cudaEventDestroy(h->evCopyDone);
     if (h->evFork) cudaEventDestroy(h->evFork);
@@ -204,6 +206,7 @@ int sgi_resize(SgiHandle h, int32_t width, int32_t full_height, int32_t y_offset
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));
     SGI_CUDA(h, cudaStreamSynchronize(h->tileStream));
     SGI_CUDA(h, cudaStreamSynchronize(h->copyStream));       // a band's rows may still be travelling to the owner's image
+    SGI_CUDA(h, cudaStreamSynchronize(h->auxStream));
     sgi::detachPeers(h);
     freePlanes(h);
     h->banded = false;                      // a resized handle is a plain whole-range handle again; call sgi_band_setup to re-band
@@ -545,18 +548,6 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
     if (!h || !fp) return SGI_ERR_INVALID_ARG;
     int rc;
     if (fp->totalNumLights == 0) return SGI_OK;      // `if (perVPLDistToViewer.size() == 0) return;` (BE:1582, 1675, 1817)
-    // The temporal pre-pass only reads planes that exist when the frame starts, so it goes to the side stream first of all and runs
-    // under the cull and the gather (which leave the DRAM idle); the final denoise pass waits for it.
-    if (h->bound && h->buf.velocity && h->buf.id && h->buf.prevNormal && h->buf.prevId && h->buf.prevDepth && h->buf.depth && h->buf.normal && !h->temporalDone) {
-        SGI_CUDA(h, cudaSetDevice(h->cp.device));
-        SGI_CUDA(h, cudaEventRecord(h->evFork, h->stream));
-        SGI_CUDA(h, cudaStreamWaitEvent(h->tileStream, h->evFork, 0));
-        if ((rc = temporalOn(h, fp, h->tileStream)) != SGI_OK) return rc;
-        SGI_CUDA(h, cudaEventRecord(h->evTemporal, h->tileStream));
-        h->temporalForked = true;
-    }
-    // cull + colour in one launch when the atlas assignment is available on the device (the cull's last CTA colours
-    // the compacted table); otherwise the two reference dispatches separately
     if (h->earlyPending) {
         // the cull (and, if the caller said the atlases were final, the colouring) of this frame already ran on the early stream
         // (sgi_cull_early): the main stream only waits for it.  The frame must be the one the early cull was given.
@@ -596,6 +587,17 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         if (rc != SGI_OK) { cudaStreamWaitEvent(h->stream, h->evJoin, 0); return rc; }
     }
     rc = sgi_gather(h, fp);
+    // The temporal pre-pass (reprojection, history decision) streams 56 bytes per pixel and needs nothing of this frame's gather
+    // or filter: it runs on its own stream under the two non-final à-trous passes, which are bound by MUFU / issue slots and leave
+    // the DRAM idle; the final pass waits for it.  (Not under the gather: its 512-thread, 98 KB CTAs cannot become resident while a
+    // stream of small CTAs keeps refilling the SMs — measured, profiles/r02d.)
+    if (rc == SGI_OK && h->cp.denoise_iters > 2 && h->buf.velocity && h->buf.id && h->buf.prevNormal && h->buf.prevId && h->buf.prevDepth && !h->temporalDone) {
+        SGI_CUDA(h, cudaStreamWaitEvent(h->auxStream, h->evTablesFree, 0));     // recorded by sgi_gather after its launch
+        if ((rc = temporalOn(h, fp, h->auxStream)) == SGI_OK) {
+            SGI_CUDA(h, cudaEventRecord(h->evTemporal, h->auxStream));
+            h->temporalForked = true;
+        }
+    }
     if (rc == SGI_OK) rc = sgi_denoise(h, fp);
     if (fork) {
         const std::string keep = h->lastError;
@@ -664,6 +666,7 @@ int sgi_synchronize(SgiHandle h) {
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));
     SGI_CUDA(h, cudaStreamSynchronize(h->tileStream));
     SGI_CUDA(h, cudaStreamSynchronize(h->copyStream));
+    SGI_CUDA(h, cudaStreamSynchronize(h->auxStream));
     return SGI_OK;
 }
 

@@ -220,6 +220,7 @@ struct SgiHandle_ {
     // row bands: a non-owner band sends its lit rows to the owner's frame image with a copy-engine transfer on this stream
     // after its final pass (the transfer overlaps the next frame), then raises its flag in the owner's slab
     cudaStream_t copyStream = nullptr;
+    cudaStream_t auxStream = nullptr;     // the temporal pre-pass of sgi_frame (low priority, under the non-final à-trous passes)
     cudaEvent_t evFinal = nullptr, evCopyDone = nullptr;
     bool copyPending = false;
     int64_t imageWaitedFrame = 0;   // owner: last frame whose image the stream has waited for

@@ -14,7 +14,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames):
+def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames, yaw=0.25, halo=None):
     """One process per band; peer descriptors travel as bytes (all_gather_object), memory is attached with CUDA IPC."""
     import torch
     import torch.distributed as dist
@@ -29,9 +29,9 @@ def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames):
     from stratusgfx_b200.bands import connect_bands, halo_rows, plan_bands
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
-    scene = Scene(workload, yaw_deg_per_frame=0.25)
+    scene = Scene(workload, yaw_deg_per_frame=yaw)
     W, H = scene.width, scene.height
-    bands = plan_bands(H, world, halo_rows(scene.denoise_iters))
+    bands = plan_bands(H, world, halo_rows(scene.denoise_iters) if halo is None else halo)
     me = bands[rank]
     vd, at = scene.vpls()
     sh, df = scene.cubemaps()
@@ -49,19 +49,35 @@ def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames):
         if rank == 0:
             np.save(out_path % f, gp.frame_image().cpu().numpy())
     assert gp.band_timeouts() == 0
+    with open((out_path % 0) + f".misses{rank}", "w") as fh:
+        fh.write(str(gp.band_reprojection_misses()))
     dist.barrier()
     gp.close()
     dist.destroy_process_group()
 
 
-def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3):
+def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3, yaw=0.25, halo=None, expect_equal=True):
     import torch.multiprocessing as mp
     from tests.parity_util import SceneData, run_cuda_staged
     out_path = str(tmp_path / "p2p_frame%d.npy")
-    mp.spawn(_p2p_worker, args=(world, _free_port(), workload, out_path, share_gpu, frames), nprocs=world, join=True)
-    single = run_cuda_staged(SceneData(workload, frames=frames, yaw_deg_per_frame=0.25))
-    for f in range(frames):
-        assert np.array_equal(np.load(out_path % f).view(np.uint16), single[f]["combined"].view(np.uint16)), f
+    mp.spawn(_p2p_worker, args=(world, _free_port(), workload, out_path, share_gpu, frames, yaw, halo), nprocs=world, join=True)
+    misses = sum(int(open((out_path % 0) + f".misses{r}").read()) for r in range(world))
+    single = run_cuda_staged(SceneData(workload, frames=frames, yaw_deg_per_frame=yaw))
+    equal = all(np.array_equal(np.load(out_path % f).view(np.uint16), single[f]["combined"].view(np.uint16)) for f in range(frames))
+    if expect_equal:
+        assert misses == 0 and equal
+    return misses, equal
+
+
+def test_fast_camera_needs_a_halo_as_tall_as_the_motion(built, tmp_path):
+    """The final pass reads the previous frame at uv - velocity (vpl_pbr_gi_denoise.fs:280,352-360).  A 20-degree yaw per frame
+    moves the corner pixels of c1 by about 50 rows: with the default 20-row halo the two bands count reprojection taps outside
+    their held rows (sgi_band_reprojection_misses) and the assembled image differs from the one-GPU frame; with a 60-row halo —
+    the halo height is the caller's choice — there is no miss and the image is the one-GPU frame byte for byte."""
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    misses, equal = _check_p2p(tmp_path / "a", 2, share_gpu=True, workload="c1", frames=2, yaw=20.0, halo=None, expect_equal=False)
+    assert misses > 0 and not equal
+    _check_p2p(tmp_path / "b", 2, share_gpu=True, workload="c1", frames=2, yaw=20.0, halo=60)
 
 
 def test_p2p_bands_over_cuda_ipc_two_processes_on_one_gpu(built, tmp_path):
