@@ -9,8 +9,8 @@
 // The scenes of this repository are lists of axis-aligned boxes, so the fragment of a texel is found by casting the ray through
 // the texel centre — the inverse of the cube-face table the gather's lookup uses (sgi_math.cuh cubeTexel),
 // so a direction that the gather maps to texel (face, j, i) is answered by the surface that texel's own ray hit — instead of by
-// rasterising triangles.  One CTA renders one face of one light: the box list sits in shared memory, a thread owns texels
-// t, t + blockDim, ...; a warp's 32 texels are one texel row, so both stores are coalesced (64 B + 128 B).
+// rasterising triangles.  Four CTAs render one face of one light: the box list sits in shared memory, a thread owns one texel of
+// the CTA's quarter (more at larger faces); a warp's 32 texels are one texel row, so both stores are coalesced (64 B + 128 B).
 //
 // All arithmetic is the exact tier (sgi_math.cuh: explicit round-to-nearest multiplies / adds / IEEE division and square root in
 // the oracle's order, no FMA): every texel is an integer output, compared bit for bit with oracle.cpp::orc_render_vpl_cubemaps.
@@ -24,6 +24,8 @@ namespace {
 
 constexpr float kFloatMax = 3.402823466e+38f;
 constexpr int kCubeThreads = 256;
+constexpr int kCubeSlices = 4;          // CTAs per face: one texel per thread at the reference's 32 x 32 faces (the ray loop is the kernel's
+                                        // latency), and CTAs small enough to find a slot next to the frame's own kernels (sgi_early_begin)
 
 SGI_DEV f3 cubeTexelDirection(int face, float sc, float tc) {     // inverse of GL 4.6 table 8.19
     switch (face) {
@@ -53,7 +55,8 @@ cubemapKernel(const SgiSceneBox* __restrict__ boxes, int numBoxes, const SgiVplD
         sBox[b] = s;
     }
     __syncthreads();
-    const int k = __ldg(vplIndices + blockIdx.x / 6), face = blockIdx.x % 6;
+    const int slice = blockIdx.x % kCubeSlices, mf = blockIdx.x / kCubeSlices;
+    const int k = __ldg(vplIndices + mf / 6), face = mf % 6;
     const float4* L = reinterpret_cast<const float4*>(lightData + k);
     const float4 lp = __ldg(L), rfi = __ldg(L + 3);
     const float o[3] = {lp.x, lp.y, lp.z};
@@ -63,7 +66,9 @@ cubemapKernel(const SgiSceneBox* __restrict__ boxes, int numBoxes, const SgiVplD
     unsigned short* __restrict__ depth = const_cast<unsigned short*>(atlases.shadow[e.index]) + base;
     uchar4* __restrict__ diffuse = const_cast<uchar4*>(atlases.diffuse[e.index]) + base;
     const float fres = (float)res;
-    for (int q = threadIdx.x; q < res * res; q += kCubeThreads) {
+    const int perSlice = (res * res + kCubeSlices - 1) / kCubeSlices;
+    const int qEnd = min(res * res, (slice + 1) * perSlice);
+    for (int q = slice * perSlice + threadIdx.x; q < qEnd; q += kCubeThreads) {
         const int j = q / res, i = q - j * res;
         const float sc = fsub(fmul(2.0f, fdiv(fadd((float)i, 0.5f), fres)), 1.0f), tc = fsub(fmul(2.0f, fdiv(fadd((float)j, 0.5f), fres)), 1.0f);
         const f3 dv = cubeTexelDirection(face, sc, tc);
@@ -111,7 +116,7 @@ bool preloadCubemapKernels() {
 
 int launchCubemaps(cudaStream_t stream, const SgiCubeRenderParams& rp, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl, int res, const AtlasTable& atlases) {
     if (rp.numMaps <= 0) return 0;
-    cubemapKernel<<<rp.numMaps * 6, kCubeThreads, 0, stream>>>(rp.boxes, rp.numBoxes, lightData, atlasByVpl, rp.vplIndices, res, atlases);
+    cubemapKernel<<<rp.numMaps * 6 * kCubeSlices, kCubeThreads, 0, stream>>>(rp.boxes, rp.numBoxes, lightData, atlasByVpl, rp.vplIndices, res, atlases);
     return 1;
 }
 

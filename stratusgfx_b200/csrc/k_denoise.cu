@@ -268,7 +268,9 @@ atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __gr
     const int g = t / s, r = t - g * s;
     const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
     const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
-    const bool live = x < W && c0 + m0 * s + r < cEnd;
+    bool live = x < W && c0 + m0 * s + r < cEnd;
+    if (!FINAL && io.skipX1 > io.skipX0 && x >= io.skipX0 && x < io.skipX1 && c0 + m0 * s + r >= io.skipY0 && c0 + (m0 + kLat - 1) * s + r < io.skipY1)
+        live = false;                                        // all four outputs belong to the TMA-staged kernel's rectangle
     // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
     // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
     bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
@@ -312,6 +314,7 @@ atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __gr
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
         if (ly >= cEnd) break;
+        if (!FINAL && x >= io.skipX0 && x < io.skipX1 && ly >= io.skipY0 && ly < io.skipY1) continue;
         const float invDenom = __fdividef(1.0f, vmax(PREVENT_DIV_BY_ZERO, acc[k][3]));      // radiance tier (see header)
         const f3 shadowFactor = mk3(acc[k][0] * invDenom, acc[k][1] * invDenom, acc[k][2] * invDenom);
         const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
@@ -377,6 +380,17 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int s = 1 + io.multiplier;
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
+#ifndef SGI_HOST_RUNTIME
+        if (!final_ && atrousTmaEnabled() && io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr &&
+            io.links.waitDown == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
+            // A/B (SGI_ATROUS_TMA=1, whole-frame handles): the interior lattice tiles through the TMA-staged kernel, the border
+            // (CLAMP_TO_EDGE taps) through the kernel below
+            int ix0, ix1, iy0, iy1;
+            if (launchAtrousTma(stream, bd.W, bd.rows, s, io.guide, io.shadowsIn, io.reservoirOut, &ix0, &ix1, &iy0, &iy1)) {
+                io.skipX0 = ix0 * s; io.skipX1 = ix1 * s; io.skipY0 = iy0 * s; io.skipY1 = iy1 * s;
+            }
+        }
+#endif
         if (io.links.doneCounter != nullptr) {   // producers of the in-kernel signal: the CTA rows whose slab holds rows pushed to a neighbour
             int producerRows = 0;
             for (int by = 0; by < (int)grid.y; ++by) {

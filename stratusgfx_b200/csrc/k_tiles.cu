@@ -63,7 +63,8 @@ constexpr int kPatchClasses = 8;
 __global__ void __launch_bounds__(kS1Threads)
 stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
              SgiVplStage1PerTileOutputs* __restrict__ out, int* __restrict__ classCount, int* __restrict__ classList, int maxPatches,
-             const SgiVplData* __restrict__ lightTable, const int32_t* __restrict__ visible, float4* __restrict__ posRadius) {
+             const SgiVplData* __restrict__ lightTable, const int32_t* __restrict__ visible, float4* __restrict__ posRadius,
+             int32_t* __restrict__ visibleCopy) {
     __shared__ float sRed[kS1Threads / 32][2][6];
     // tiles of the band's computed rows only; outputs stay indexed by held tile row
     const int tilesX = bd.W / SGI_TILE_DIVISOR, tileY0 = bd.c0 / SGI_TILE_DIVISOR, tilesYCompute = bd.crows / SGI_TILE_DIVISOR;
@@ -74,6 +75,9 @@ stage1Kernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
             const float4 lp = __ldg(reinterpret_cast<const float4*>(lightTable + j));
             posRadius[j] = make_float4(lp.x, lp.y, lp.z, __ldg(&lightTable[j].radius));
         }
+        // ... and copies the visible list: after this kernel the tile stages read library memory only, so the caller's tables
+        // are free for the next frame's cull while stage 2 is still running (sgi_early_begin)
+        for (int j = tid; j <= V; j += kS1Threads) visibleCopy[j] = j == 0 ? V : __ldg(visible + j);
     }
     const int tx = blockIdx.x * kS1X + (tid % kS1X), ty = tileY0 + blockIdx.y * kS1Y + (tid / kS1X);
     const bool active = tx < tilesX && ty < tileY0 + tilesYCompute;
@@ -377,13 +381,14 @@ static int maxPatchesOf(const BandDims& bd) { return patchScratchInts(bd) / kPat
 // layout of the scratch: [0, 8) class counters, [8] stage 2's patch counter, [16, 16 + 8 * maxPatches) class lists
 
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
-                 SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius) {
+                 SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius,
+                 int32_t* visibleCopy) {
     const int tilesX = bd.W / SGI_TILE_DIVISOR, tilesY = bd.crows / SGI_TILE_DIVISOR;
     if (tilesX <= 0 || tilesY <= 0) return 0;
     cudaMemsetAsync(patchScratch, 0, 2 * kPatchClasses * sizeof(int), stream);
     dim3 grid((tilesX + kS1X - 1) / kS1X, (tilesY + kS1Y - 1) / kS1Y);
     stage1Kernel<<<grid, kS1Threads, 0, stream>>>(fc, bd, depth, normal, out, patchScratch, patchScratch + 2 * kPatchClasses, maxPatchesOf(bd),
-                                                  lightTable, visible, posRadius);
+                                                  lightTable, visible, posRadius, visibleCopy);
     return 1;
 }
 

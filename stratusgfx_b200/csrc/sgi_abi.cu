@@ -158,6 +158,8 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     }
     if (cudaMalloc(&h->cullBallots, 512 * sizeof(uint32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->posRadius, SGI_MAX_TOTAL_VPLS_PER_FRAME * sizeof(float4)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaMalloc((void**)&h->visibleCopy, (SGI_MAX_TOTAL_VPLS_PER_FRAME + 1) * sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&h->evStage1, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc(&h->cullTicket, sizeof(unsigned int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->gatherCounters, 2 * sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMemsetAsync(h->gatherCounters, 0, 2 * sizeof(int), h->stream) != cudaSuccess) return bail(SGI_ERR_CUDA);
@@ -189,6 +191,8 @@ int sgi_destroy(SgiHandle h) {
     freePlanes(h);
     if (h->cullBallots) cudaFree(h->cullBallots);
     if (h->posRadius) cudaFree(h->posRadius);
+    if (h->visibleCopy) cudaFree(h->visibleCopy);
+    if (h->evStage1) cudaEventDestroy(h->evStage1);
     if (h->cullTicket) cudaFree(h->cullTicket);
     if (h->gatherCounters) cudaFree(h->gatherCounters);
     if (h->prepassKeys) cudaFree(h->prepassKeys);
@@ -330,7 +334,7 @@ int sgi_early_begin(SgiHandle h, void* stream) {
     if (!h || !stream) return SGI_ERR_INVALID_ARG;
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     if (h->tablesFreeRecorded) SGI_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->evTablesFree, 0));
-    if (h->joinOutstanding) SGI_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->evJoin, 0));
+    if (h->stage1Outstanding) SGI_CUDA(h, cudaStreamWaitEvent((cudaStream_t)stream, h->evStage1, 0));      // stage 2 reads stage 1's copies
     return SGI_OK;
 }
 
@@ -362,9 +366,13 @@ static int tileListsOn(SgiHandle h, const SgiFrameParams* fp, cudaStream_t strea
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     const BandDims bd = bandDims(h);
     int n = launchStage1(stream, fc, bd, (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, h->buf.vplStage1Results, h->patchScratch,
-                         h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->posRadius);
+                         h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->posRadius, h->visibleCopy);
+    if (stream != h->stream) {               // forked (sgi_frame): from here on the tile stages read library memory only
+        SGI_CUDA(h, cudaEventRecord(h->evStage1, stream));
+        h->stage1Outstanding = true;
+    }
     // the compacted table (entry k = lightData[visible[k+1]], written by the cull) stands in for the indexed reads of stage2.cs:81-82
-    n += launchStage2(stream, bd, h->buf.vplStage1Results, h->posRadius, h->buf.vplVisibleIndices, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
+    n += launchStage2(stream, bd, h->buf.vplStage1Results, h->posRadius, h->visibleCopy, h->buf.vplVisiblePerTile, h->tilePos, h->patchScratch);
     h->tileListsValid = true;
     return postLaunch(h, n);
 }
@@ -583,7 +591,6 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         // whatever the side stream holds by now is joined before this call returns, on the error paths too: its kernels read
         // vplUpdatedData / the visible list, which the caller may rebind or the next cull overwrites
         SGI_CUDA(h, cudaEventRecord(h->evJoin, h->tileStream));
-        h->joinOutstanding = true;
         if (rc != SGI_OK) { cudaStreamWaitEvent(h->stream, h->evJoin, 0); return rc; }
     }
     rc = sgi_gather(h, fp);

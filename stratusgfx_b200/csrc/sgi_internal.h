@@ -194,6 +194,8 @@ struct DenoiseIO {
     uint2* giOut;                 // half4 (final pass)
     unsigned short* historyOut;   // half  (final pass)
     int multiplier;
+    // outputs inside this pixel rectangle (band-local rows) were written by the TMA-staged kernel (k_atrous_tma.cu): atrousKernel skips them
+    int skipX0, skipX1, skipY0, skipY1;
 };
 
 }  // namespace sgi
@@ -212,9 +214,9 @@ struct SgiHandle_ {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // sgi_early_begin / sgi_cull_early: the cull (+ colouring) of the NEXT frame runs on a caller-chosen second stream under the
     // current frame's denoise passes.  evTablesFree: the current frame's last reader of the compacted tables and the atlases on
-    // the main stream (the gather) is done; evJoin covers the tile stages; evEarly: the early cull is complete.
+    // the main stream (the gather) is done; evStage1 covers the forked tile stages; evEarly: the early cull is complete.
     cudaEvent_t evTablesFree = nullptr, evEarly = nullptr;
-    bool tablesFreeRecorded = false, joinOutstanding = false;
+    bool tablesFreeRecorded = false;
     bool earlyPending = false, earlyColored = false;
     SgiFrameParams earlyParams{};   // what the pending early cull ran with: the frame that consumes it must agree
     // row bands: a non-owner band sends its lit rows to the owner's frame image with a copy-engine transfer on this stream
@@ -235,6 +237,9 @@ struct SgiHandle_ {
     int cur = 0;
     int* patchScratch = nullptr;    // stage-1 -> stage-2 patch size classes (k_tiles.cu)
     float4* posRadius = nullptr;         // [SGI_MAX_TOTAL_VPLS_PER_FRAME] (position, radius) of the compacted VPLs, packed by stage 1 for stage 2
+    int32_t* visibleCopy = nullptr;      // [SGI_MAX_TOTAL_VPLS_PER_FRAME + 1] stage 1's copy of the visible list for stage 2
+    cudaEvent_t evStage1 = nullptr;      // stage 1 of the forked tile stages is done: the caller's tables are free (sgi_early_begin)
+    bool stage1Outstanding = false;
     unsigned short* tilePos = nullptr;   // [tiles][12] per-tile lists as positions in the compacted VPL table (tile-list gather)
     bool tileListsValid = false;    // sgi_tile_lists ran since the last bind
     void* guide = nullptr;          // float4 (normalize(normal*2-1), depth), rebuilt once per frame
@@ -305,7 +310,8 @@ int launchWaitAllBands(cudaStream_t stream, const int32_t* flags, int world, int
 int launchSignal(cudaStream_t stream, int32_t* a, int32_t* b, int epoch, int32_t* c, int valueC);
 int patchScratchInts(const BandDims& bd);
 int launchStage1(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
-                 SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius);
+                 SgiVplStage1PerTileOutputs* out, int* patchScratch, const SgiVplData* lightTable, const int32_t* visible, float4* posRadius,
+                 int32_t* visibleCopy /* [SGI_MAX_TOTAL_VPLS_PER_FRAME + 1]: stage 2 reads this copy, not the caller's list */);
 int launchStage2(cudaStream_t stream, const BandDims& bd, const SgiVplStage1PerTileOutputs* stage1, const float4* posRadius,
                  const int32_t* visible, SgiVplStage2PerTileOutputs* out, unsigned short* tilePos, int* patchScratch);
 int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal,
@@ -316,6 +322,8 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
                  bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
+bool atrousTmaEnabled();        // SGI_ATROUS_TMA=1 (A/B of the shared-memory / TMA staging, k_atrous_tma.cu)
+bool launchAtrousTma(cudaStream_t stream, int W, int rows, int s, const float4* guide, const uint2* in, uint2* out, int* ix0, int* ix1, int* iy0, int* iy1);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
                       bool* signalled /* out: the kernel releases the neighbours' flags itself */);

@@ -17,7 +17,8 @@ extern "C" int host_tile_lists(const SgiFrameParams* fp, int W, int H, const flo
     std::vector<float4> posRadius(SGI_MAX_TOTAL_VPLS_PER_FRAME);
     const size_t tiles = (size_t)(W / SGI_TILE_DIVISOR) * (H / SGI_TILE_DIVISOR);
     std::vector<unsigned short> tilePos((tiles ? tiles : 1) * SGI_MAX_VPLS_PER_TILE);
-    int n = sgi::launchStage1(nullptr, fc, bd, depth, normal, stage1, patchScratch.data(), updated, visible, posRadius.data());
-    n += sgi::launchStage2(nullptr, bd, stage1, posRadius.data(), visible, stage2, tilePos.data(), patchScratch.data());
+    std::vector<int32_t> visibleCopy(SGI_MAX_TOTAL_VPLS_PER_FRAME + 1);
+    int n = sgi::launchStage1(nullptr, fc, bd, depth, normal, stage1, patchScratch.data(), updated, visible, posRadius.data(), visibleCopy.data());
+    n += sgi::launchStage2(nullptr, bd, stage1, posRadius.data(), visibleCopy.data(), stage2, tilePos.data(), patchScratch.data());
     return n;
 }

@@ -70,14 +70,16 @@ def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3, yaw=0.25, ha
 
 
 def test_fast_camera_needs_a_halo_as_tall_as_the_motion(built, tmp_path):
-    """The final pass reads the previous frame at uv - velocity (vpl_pbr_gi_denoise.fs:280,352-360).  A 20-degree yaw per frame
-    moves the corner pixels of c1 by about 50 rows: with the default 20-row halo the two bands count reprojection taps outside
-    their held rows (sgi_band_reprojection_misses) and the assembled image differs from the one-GPU frame; with a 60-row halo —
-    the halo height is the caller's choice — there is no miss and the image is the one-GPU frame byte for byte."""
+    """The final pass reads the previous frame at uv - velocity (vpl_pbr_gi_denoise.fs:280,352-360).  A 12-degree yaw per frame
+    moves pixels of c1 by up to ~50 rows away from the horizon line: with four bands of 90 rows and the default 20-row halo the
+    bands count reprojection taps outside their held rows (sgi_band_reprojection_misses) and the assembled image differs from the
+    one-GPU frame; with a 60-row halo — the halo height is the caller's choice — there is no miss and the image is the one-GPU
+    frame byte for byte.  (Two bands would not do: a yaw never moves a pixel across the horizon line, which is their cut.)"""
     (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
-    misses, equal = _check_p2p(tmp_path / "a", 2, share_gpu=True, workload="c1", frames=2, yaw=20.0, halo=None, expect_equal=False)
+    misses, equal = _check_p2p(tmp_path / "a", 4, share_gpu=True, workload="c1", frames=2, yaw=12.0, halo=None, expect_equal=False)
     assert misses > 0 and not equal
-    _check_p2p(tmp_path / "b", 2, share_gpu=True, workload="c1", frames=2, yaw=20.0, halo=60)
+    _check_p2p(tmp_path / "b", 4, share_gpu=True, workload="c1", frames=2, yaw=12.0, halo=60)
+
 
 
 def test_p2p_bands_over_cuda_ipc_two_processes_on_one_gpu(built, tmp_path):
