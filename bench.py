@@ -332,7 +332,8 @@ def run_ours(args, rank, world, local_rank):
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
     p2p = world > 1 and args.bands == "p2p"
     halo = halo_rows(iters)
-    apron = halo if p2p else APRON
+    isolated = world > 1 and args.bands == "isolated"     # diagnosis: band geometry and halo rows, but no neighbour attached (wrong seams)
+    apron = halo if (p2p or isolated) else APRON
     bands = plan_bands(H, world, apron)
     vd, at = scene.vpls()
     sh, df = scene.cubemaps()
@@ -405,6 +406,8 @@ def run_ours(args, rank, world, local_rank):
         gp.bind()
         if p2p:
             connect_bands(dist, gp, me, world)           # band_setup + CUDA IPC attach of the neighbours and of rank 0's frame image
+        elif isolated:
+            gp.band_setup(me.b0, me.b1 - me.b0, me.rank, world, owns_frame_image=False)
         else:
             full_out = torch.empty((H, W, 4), dtype=torch.float16, device=dev) if rank == 0 else None
 
@@ -470,7 +473,7 @@ def run_ours(args, rank, world, local_rank):
                     broadcast_frame_inputs(dist, [packed])
             refresh_maps(None)
             gp.frame(fp)
-        if world > 1 and not p2p:
+        if world > 1 and not p2p and not isolated:
             gather_bands(dist, gp.t["lightingOut"][me.owned], full_out, bands, rank)
         # p2p: every band's lit rows travel to rank 0's frame image after its final pass (copy engine, during the next frame);
         # rank 0's stream waits for them one frame late, and for the last frame in finish()
@@ -544,7 +547,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- the assembled image against one GPU: rank 0 replays the same frames (same `time` sequence, hence the same temporal
     # history) on a whole-frame handle and compares the lit image byte for byte ----
     image_equal = None
-    if world > 1 and not args.no_image_check:
+    if world > 1 and not args.no_image_check and not isolated:
         if rank == 0:
             set_host_threads(1)               # the other ranks idle at the barrier below
             img = (gp.frame_image() if p2p else full_out).clone()
@@ -772,7 +775,7 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
     ap.add_argument("--no-image-check", action="store_true", help="N > 1: skip the byte comparison of the assembled image with a single-GPU replay")
     ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")
-    ap.add_argument("--bands", default="p2p", choices=["p2p", "apron"], help="multi-GPU halo strategy (N > 1)")
+    ap.add_argument("--bands", default="p2p", choices=["p2p", "apron", "isolated"], help="multi-GPU halo strategy (N > 1); `isolated` = band handles without neighbours, a timing diagnosis whose seams are wrong")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -1,6 +1,7 @@
 // k_atrous_tma.cu — the non-final à-trous pass with its taps staged through shared memory by TMA (north_star: "bandwidth-bound
-// stencils with shared-memory halos").  An A/B partner of atrousKernel (k_denoise.cu), selected per
-// process with SGI_ATROUS_TMA=1 for whole-frame handles; same taps, same order, same arithmetic, so the outputs are the same bytes.
+// stencils with shared-memory halos").  It serves the interior of whole-frame handles; atrousKernel (k_denoise.cu) serves the
+// border tiles, the final pass and row bands.  Same taps, same order, same arithmetic: the outputs are the same bytes
+// (checked on c2 and c4, profiles/r02g).
 //
 // A pass with tap spacing s only ever combines pixels of one residue class (x mod s, y mod s): the frame is s*s independent
 // "lattice images" of (W/s) x (rows/s) points on which the filter is a dense 5x5 stencil.  A CTA owns kRes consecutive x residues,
@@ -13,7 +14,6 @@
 // Tiles whose halo would leave the plane (TMA fills zeros there, the shader wants CLAMP_TO_EDGE) and planes whose extent is not a
 // multiple of the spacing keep the clamped global-memory path of k_denoise.cu (the launcher runs atrousKernel on them).
 #include <cuda.h>
-#include <cstdlib>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 
@@ -168,14 +168,9 @@ bool launchOne(cudaStream_t stream, int W, int rows, const float4* guide, const 
 
 }  // namespace
 
-bool atrousTmaEnabled() {
-    static const bool v = [] { const char* e = getenv("SGI_ATROUS_TMA"); return e && e[0] == '1'; }();
-    return v;
-}
-
 // Launches the TMA kernel on the interior tiles of a whole-frame plane; returns false when the plane does not qualify (then the
-// caller runs atrousKernel on everything).  On success [*x0,*x1) x [*y0,*y1) is the pixel rectangle... expressed in LATTICE points
-// per residue: lattice columns [ix0, ix1) and rows [iy0, iy1) of every residue class were written; the caller covers the rest.
+// caller runs atrousKernel on everything).  On success the lattice columns [ix0, ix1) and rows [iy0, iy1) of every residue class
+// were written — the pixel rectangle [ix0*s, ix1*s) x [iy0*s, iy1*s); the caller covers the rest.
 bool launchAtrousTma(cudaStream_t stream, int W, int rows, int s, const float4* guide, const uint2* in, uint2* out, int* ix0, int* ix1, int* iy0, int* iy1) {
     if (s == 2) return launchOne<2>(stream, W, rows, guide, in, out, ix0, ix1, iy0, iy1);
     if (s == 4) return launchOne<4>(stream, W, rows, guide, in, out, ix0, ix1, iy0, iy1);

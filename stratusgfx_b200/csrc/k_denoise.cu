@@ -168,7 +168,7 @@ SGI_DEV void finalEpilogue(const BandDims& bd, const DenoiseIO& io, int x, int l
     io.combinedOut[p] = cv;
     io.giOut[p] = gv;
     // row bands: this frame's GI boundary rows go to the neighbours' halos (reprojection may land there next frame; the history
-    // plane is only ever read at the pixel itself), and — with SGI_IMAGE_PUSH=kernel — the lit pixel into the owner's frame image
+    // plane is only ever read at the pixel itself); the owner band also stores its own lit rows into its frame image
     pushGi(io.links, y, x, W, gv);
     if (io.links.image != nullptr) io.links.image[(size_t)y * W + x] = cv;
 }
@@ -268,9 +268,14 @@ atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __gr
     const int g = t / s, r = t - g * s;
     const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
     const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
-    bool live = x < W && c0 + m0 * s + r < cEnd;
-    if (!FINAL && io.skipX1 > io.skipX0 && x >= io.skipX0 && x < io.skipX1 && c0 + m0 * s + r >= io.skipY0 && c0 + (m0 + kLat - 1) * s + r < io.skipY1)
-        live = false;                                        // all four outputs belong to the TMA-staged kernel's rectangle
+    if (!FINAL && io.skipX1 > io.skipX0) {
+        // whole-frame handles: the interior lattice tiles were written by the TMA-staged kernel (k_atrous_tma.cu); a CTA whose
+        // outputs all lie inside that rectangle leaves at once (uniform), the others skip the covered outputs one by one
+        int lo, hi;
+        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+        if ((int)blockIdx.x * kDnX >= io.skipX0 && (int)blockIdx.x * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
+    }
+    const bool live = x < W && c0 + m0 * s + r < cEnd;
     // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
     // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
     bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
@@ -380,11 +385,11 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int s = 1 + io.multiplier;
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
-#ifndef SGI_HOST_RUNTIME
-        if (!final_ && atrousTmaEnabled() && io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr &&
+#ifdef __CUDACC__                        // (the host-emulation builds of tests/cuda_on_host have no TMA: they run atrousKernel on everything)
+        if (!final_ && io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr &&
             io.links.waitDown == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
-            // A/B (SGI_ATROUS_TMA=1, whole-frame handles): the interior lattice tiles through the TMA-staged kernel, the border
-            // (CLAMP_TO_EDGE taps) through the kernel below
+            // whole-frame handles: the interior lattice tiles through the TMA-staged kernel (taps from shared memory: 0.150 -> 0.144-0.147 ms
+            // per pass on c4, same bytes; profiles/r02g), the border tiles (CLAMP_TO_EDGE taps) through the kernel below
             int ix0, ix1, iy0, iy1;
             if (launchAtrousTma(stream, bd.W, bd.rows, s, io.guide, io.shadowsIn, io.reservoirOut, &ix0, &ix1, &iy0, &iy1)) {
                 io.skipX0 = ix0 * s; io.skipX1 = ix1 * s; io.skipY0 = iy0 * s; io.skipY1 = iy1 * s;

@@ -143,8 +143,6 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     {
         int lo = 0, hi = 0;
         if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return bail(SGI_ERR_CUDA);      // lo = least priority
-        const char* e = getenv("SGI_TILE_STREAM_PRIO");          // "equal": same priority as a default stream (A/B timing)
-        if (e && e[0] == 'e') lo = 0;
         if (cudaStreamCreateWithPriority(&h->tileStream, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
         if (cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess) return bail(SGI_ERR_CUDA);
@@ -500,8 +498,7 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         // pass p reads the neighbours' pass p-1 rows from this handle's halo: wait (in stream order) for their flags
         // (inside the kernel, by the CTAs whose taps reach the halo; interior CTAs start at once)
         io.links = sgi::bandLinks(h, pass % 2, final_, pass >= 1 ? sgi::bandEpoch(h->frameNo, pass) : 0);
-        // (with SGI_IMAGE_PUSH=kernel the final pass's flag also tells the owner that the image rows landed: host-launched signal)
-        if (!(final_ && sgi::imagePushByKernel())) sgi::armInKernelSignal(h, &io.links, sgi::bandEpoch(h->frameNo, pass + 1));
+        sgi::armInKernelSignal(h, &io.links, sgi::bandEpoch(h->frameNo, pass + 1));
     }
     if (final_) {
         if (!h->temporalDone) { const int rc = temporalOn(h, fp, h->stream); if (rc != SGI_OK) return rc; }
@@ -509,7 +506,7 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         io.temporal = (float4*)h->temporal;
     }
     bool signalled = false;
-    const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && !sgi::imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached &&
+    const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && h->peer[SGI_PEER_ROOT].attached &&
                          h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
     if (copyOut && h->copyPending) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evCopyDone, 0));   // the previous frame's rows have left `combined`
     n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_, &signalled);
@@ -579,9 +576,8 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
     // The stochastic gather (the reference's live shader) and the denoiser do not read the per-tile lists, so the two tile
     // stages run on a low-priority side stream next to them: forked here, joined at the end of the frame.  Their long,
     // thinly populated tail (a few loose patches) then overlaps with the gather instead of idling the SMs.  The tile-list
-    // gather consumes the lists, so that mode stays serial.  SGI_SERIAL_TILE_LISTS=1 keeps everything on one stream.
-    static const bool serialLists = [] { const char* e = getenv("SGI_SERIAL_TILE_LISTS"); return e && e[0] == '1'; }();
-    const bool fork = lists && fp->gatherMode == SGI_GATHER_STOCHASTIC && !serialLists;
+    // gather consumes the lists, so that mode stays serial.
+    const bool fork = lists && fp->gatherMode == SGI_GATHER_STOCHASTIC;
     if (lists && !fork) { if ((rc = sgi_tile_lists(h, fp)) != SGI_OK) return rc; }
     if (fork) {
         SGI_CUDA(h, cudaSetDevice(h->cp.device));

@@ -114,9 +114,7 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
     if (final_) {
         L.reprojMisses = h->flags + 3;
         const int parity = (int)(h->frameNo & 1);
-        if (h->band.owns_frame_image) L.image = (uint2*)h->frameImage[parity];
-        else if (imagePushByKernel() && h->peer[SGI_PEER_ROOT].attached && h->peer[SGI_PEER_ROOT].info.off_image[parity] >= 0)
-            L.image = (uint2*)(h->peer[SGI_PEER_ROOT].base + h->peer[SGI_PEER_ROOT].info.off_image[parity]);
+        if (h->band.owns_frame_image) L.image = (uint2*)h->frameImage[parity];      // the owner's own rows; the other bands' rows arrive by copy engine (sgi_abi.cu)
     }
     return L;
 }
@@ -136,16 +134,14 @@ int signalNeighbours(SgiHandle_* h, int epoch, bool final_) {
     int32_t* c = nullptr;
     if (final_) {
         if (h->band.owns_frame_image) c = h->flags + 8 + h->band.rank;
-        else if (imagePushByKernel()) { if (int32_t* root = peerFlags(h, SGI_PEER_ROOT)) c = root + 8 + h->band.rank; }
     }
     return launchSignal(h->stream, a, b, epoch, c, (int)(uint32_t)h->frameNo);
 }
 
 void armInKernelSignal(SgiHandle_* h, BandLinks* L, int epoch) {
-    static const bool off = [] { const char* e = getenv("SGI_BAND_SIGNAL"); return e && e[0] == 'k'; }();      // SGI_BAND_SIGNAL=kernel: always the signal kernel
     int32_t* up = peerFlags(h, SGI_PEER_UP);
     int32_t* down = peerFlags(h, SGI_PEER_DOWN);
-    if (off || h->bandDone == nullptr || (up == nullptr && down == nullptr)) return;
+    if (h->bandDone == nullptr || (up == nullptr && down == nullptr)) return;
     L->doneCounter = h->bandDone;
     L->sigUp = up ? up + 1 : nullptr;
     L->sigDown = down ? down + 0 : nullptr;
@@ -159,14 +155,6 @@ int signalOwnerRowsDone(SgiHandle_* h) {
 
 int waitAllBands(SgiHandle_* h, int64_t frameNo) {
     return launchWaitAllBands(h->stream, h->flags + 8, h->band.world, (int)(uint32_t)frameNo, h->flags + 2);
-}
-
-// SGI_IMAGE_PUSH=kernel: the final pass of every band stores its lit rows into the owner's frame image itself (NVLink peer
-// stores); default: a copy-engine transfer after the final pass (sgi_abi.cu), which keeps 7/8 of the frame's bytes converging
-// on one GPU out of the final pass's critical path
-bool imagePushByKernel() {
-    static const bool v = [] { const char* e = getenv("SGI_IMAGE_PUSH"); return e && e[0] == 'k'; }();
-    return v;
 }
 
 void detachPeers(SgiHandle_* h) {

@@ -302,7 +302,6 @@ inline int bandEpoch(int64_t frameNo, int stage) { return (int)(uint32_t)(frameN
 int waitNeighbours(SgiHandle_* h, int epoch);
 int signalNeighbours(SgiHandle_* h, int epoch, bool final_);
 int waitAllBands(SgiHandle_* h, int64_t frameNo);
-bool imagePushByKernel();
 void detachPeers(SgiHandle_* h);
 constexpr int kBandFlags = 64;       // int32 flags per handle: [0] up neighbour's epoch, [1] down neighbour's, [2] time-outs, [3] reprojection taps outside the held rows, [4] producer counter, [5..7] waits that spun: count, summed and longest duration (1024 cycles) of the in-kernel signal, [8+r] band r's image rows landed
 int launchWaitFlags(cudaStream_t stream, const int32_t* f0, const int32_t* f1, int epoch, int32_t* timeouts);
@@ -322,7 +321,6 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
                  bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
-bool atrousTmaEnabled();        // SGI_ATROUS_TMA=1 (A/B of the shared-memory / TMA staging, k_atrous_tma.cu)
 bool launchAtrousTma(cudaStream_t stream, int W, int rows, int s, const float4* guide, const uint2* in, uint2* out, int* ix0, int* ix1, int* iy0, int* iy1);
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
