@@ -622,6 +622,29 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    # ---- what bounds e2e: the host -> device link(s).  Every rank copies exactly its per-frame input set (pinned host memory ->
+    # its device slot) five times, all ranks at once, nothing else running: the aggregate rate is the ceiling of `e2e`, and
+    # bytes / rate is the time the copies alone need per frame ----
+    probe_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    probe_stream = torch.cuda.Stream(device=dev)
+    fence()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(probe_stream):
+        pe0.record()
+        for _ in range(5):
+            for k, v in host.items():
+                pipe.slots[0][k].copy_(v, non_blocking=True)
+        pe1.record()
+    probe_stream.synchronize()
+    probe_ms = pe0.elapsed_time(pe1) / 5.0
+    fence()
+    probe = {"bytes_per_rank": int(probe_bytes), "ms_per_frame_copy": round(probe_ms, 4), "gbs_per_rank": round(probe_bytes / (probe_ms * 1e-3) / 1e9, 2)}
+    if world > 1:
+        allp = [None] * world
+        dist.all_gather_object(allp, probe)
+        probe = {"bytes_per_rank": [q["bytes_per_rank"] for q in allp], "ms_per_frame_copy": [q["ms_per_frame_copy"] for q in allp],
+                 "gbs_per_rank": [q["gbs_per_rank"] for q in allp],
+                 "aggregate_gbs": round(sum(q["bytes_per_rank"] for q in allp) / (max(q["ms_per_frame_copy"] for q in allp) * 1e-3) / 1e9, 2)}
     h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     if world > 1:
         t = torch.tensor([float(h2d), float(d2h)], device=dev)
@@ -664,7 +687,9 @@ def run_ours(args, rank, world, local_rank):
                            "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
                 "clocks": clocks,
                 "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass"},
+                        "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass",
+                        "h2d_probe": probe,
+                        "bound": "host->device link: the probe copies each rank's per-frame input set with nothing else running, all ranks at once; e2e cannot be shorter than ms_per_frame_copy (max over ranks)"},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
                 "stages": per_stage}

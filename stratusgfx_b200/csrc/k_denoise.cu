@@ -258,8 +258,6 @@ SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x,
 template <bool FINAL, int S>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __grid_constant__ DenoiseIO io) {
-    SGI_PDL_WAIT();                                          // (chained launches, sgi_internal.h) the previous pass / the gather is complete from here on
-    SGI_PDL_LAUNCH_DEPENDENTS();
     const int W = bd.W, rows = bd.rows;
     const int x = blockIdx.x * kDnX + threadIdx.x;
     const int s = S ? S : 1 + io.multiplier;                 // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
@@ -410,7 +408,7 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
 #define SGI_ATROUS_LAUNCH(S_)                                                                             \
         do {                                                                                              \
             void (*kf)(const FrameConsts, BandDims, const DenoiseIO) = final_ ? atrousKernel<true, S_> : atrousKernel<false, S_>; \
-            SGI_LAUNCH_CHAINED(kf, grid, block, 0, stream, fc, bd, io);                                   \
+            kf<<<grid, block, 0, stream>>>(fc, bd, io);                                   \
         } while (0)
         if (s == 2) SGI_ATROUS_LAUNCH(2); else if (s == 4) SGI_ATROUS_LAUNCH(4); else if (s == 8) SGI_ATROUS_LAUNCH(8); else SGI_ATROUS_LAUNCH(0);
 #undef SGI_ATROUS_LAUNCH

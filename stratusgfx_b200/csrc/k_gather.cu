@@ -354,8 +354,6 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
                        const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
                        uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
                        const __grid_constant__ BandLinks links, int tableCap, int* __restrict__ unitCounters, int counterSel) {
-    SGI_PDL_WAIT();                                         // (experiment, see sgi_internal.h) the cull / colouring is complete from here on
-    SGI_PDL_LAUNCH_DEPENDENTS();
     extern __shared__ float4 sTab[];
     float4* __restrict__ sPos = sTab;                       // (position, radius)
     float4* __restrict__ sCol = sTab + tableCap;            // (colour, farPlane)
@@ -595,11 +593,11 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
         }
         if (bytes <= kTableBytesTwoCtas) {
             const int grid = max(1, min(2 * smCount(), (units + 15) / 16));
-            SGI_LAUNCH_CHAINED(gatherStochasticKernel<512>, dim3(grid), dim3(512), bytes, stream, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+            gatherStochasticKernel<512><<<dim3(grid), dim3(512), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
                                colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
         } else {
             const int grid = max(1, min(smCount(), (units + 31) / 32));
-            SGI_LAUNCH_CHAINED(gatherStochasticKernel<1024>, dim3(grid), dim3(1024), bytes, stream, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+            gatherStochasticKernel<1024><<<dim3(grid), dim3(1024), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
                                colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
         }
     }

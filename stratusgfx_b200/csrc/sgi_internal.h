@@ -78,29 +78,6 @@ struct AtlasTable {
 };
 
 #ifdef __CUDACC__
-// -DSGI_PDL (experiment, off by default: `SGI_EXTRA_NVCC_FLAGS=-DSGI_PDL python -m stratusgfx_b200.build --force`): the
-// gather -> à-trous -> à-trous -> final chain is launched with programmatic stream serialization, so the next kernel's CTAs
-// are scheduled while the previous kernel drains and only block at SGI_PDL_WAIT(), which sits before their first read of
-// the previous kernel's output.  Without the macro the launches are plain <<<>>> and the kernels contain no extra code.
-#ifdef SGI_PDL
-#define SGI_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
-#define SGI_PDL_LAUNCH_DEPENDENTS() asm volatile("griddepcontrol.launch_dependents;")
-template <typename... KArgs, typename... Args>
-inline cudaError_t launchChained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-#define SGI_LAUNCH_CHAINED(kernel, grid, block, smem, stream, ...) launchChained(kernel, grid, block, smem, stream, __VA_ARGS__)
-#else
-#define SGI_PDL_WAIT()
-#define SGI_PDL_LAUNCH_DEPENDENTS()
-#define SGI_LAUNCH_CHAINED(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#endif
 __device__ __forceinline__ int ldAcquireSys(const int32_t* p) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

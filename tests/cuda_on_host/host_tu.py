@@ -117,8 +117,7 @@ def translate(text, name, whole_band_file=False):
         text = text[:text.index("using namespace sgi;")]
     if name == "sgi_internal.h":
         text = text.replace("#ifdef __CUDACC__", "#if 1   // [host emulation] was: #ifdef __CUDACC__")
-    # (the griddepcontrol macros sit under #ifdef SGI_PDL, which a host build never defines)
-    code = "\n".join(l for l in re.sub(r"//[^\n]*", "", text).split("\n") if "griddepcontrol" not in l)
+    code = re.sub(r"//[^\n]*", "", text)
     if re.search(r"\basm\b", code):
         raise ValueError(f"{name}: inline PTX outside the known helpers — extend PTX_HELPERS and the shim")
     return text, dropped, launches

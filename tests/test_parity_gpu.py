@@ -111,45 +111,35 @@ def _second_stream(gp):
 
 def test_early_cull_gives_the_frames_of_the_serial_order(tiny):
     """sgi_early_begin / sgi_cull_early: the cull + colouring of frame f+1 enqueued on a second stream right after frame f (the
-    reference's call order, BE:1395 before BE:2043) — the frames must be the bytes of the serial order, the visible lists too; a
-    frame whose parameters differ from the early cull's is refused; an explicit cull supersedes a pending early one."""
+    reference's call order, BE:1395 before BE:2043) — the frames must be the bytes of the serial order, the visible lists and the
+    per-tile lists too; a frame whose parameters differ from the early cull's is refused; an explicit cull supersedes a pending
+    early one."""
     from stratusgfx_b200.gipass import StratusGiError
     staged = run_cuda_staged(tiny)
     gp = make_pass(tiny)
     st, ptr = _second_stream(gp)
-    frames = [0, 1, 0, 1]
     gp.set_gbuffer(tiny.gb[0], tiny.gb[-1]); gp.set_csm(tiny.csm[0]); gp.bind()
-    want_hist = None
-    for k, f in enumerate(frames):
-        gp.frame(tiny.fp[f])                               # k = 0 culls itself, later frames consume the early result
-        if k < 2:                                          # the first two frames are the staged run's frames (same history)
-            assert np.array_equal(gp.output("lightingOut").view(np.uint16), staged[f]["combined"].view(np.uint16)), k
-            assert np.array_equal(gp.output("vplVisibleIndices"), staged[f]["visible"][: gp.output("vplVisibleIndices").shape[0]]), k
-            assert np.array_equal(gp.output("vplVisiblePerTile"), staged[f]["stage2"]), k
-        if k + 1 < len(frames):
-            nf = frames[k + 1]
-            gp.synchronize()                               # (the test swaps whole input planes between frames; a renderer's are per-frame resources)
-            gp.set_gbuffer(tiny.gb[nf], tiny.gb[nf - 1]); gp.set_csm(tiny.csm[nf]); gp.bind()
-            gp.early_begin(ptr)
-            gp.cull_early(tiny.fp[nf], ptr, with_color=(k % 2 == 0))
-    last = gp.output("lightingOut").copy()
-    gp.close()
-    # the same four frames without the early calls
-    gp = make_pass(tiny)
-    for k, f in enumerate(frames):
-        gp.set_gbuffer(tiny.gb[f], tiny.gb[f - 1]); gp.set_csm(tiny.csm[f]); gp.bind()
-        gp.frame(tiny.fp[f])
-    assert np.array_equal(gp.output("lightingOut").view(np.uint16), last.view(np.uint16))
-    # refusals
-    gp.early_begin(ptr)
-    gp.cull_early(tiny.fp[0], ptr)
+    for f in range(3):                                     # frame 0 culls itself; 1 and 2 consume an early cull (with, without colouring)
+        gp.frame(tiny.fp[f % 2])
+        if f < 2:                                          # the staged run's frames (same history)
+            assert np.array_equal(gp.output("lightingOut").view(np.uint16), staged[f]["combined"].view(np.uint16)), f
+            nv = gp.output("vplVisibleIndices")
+            assert np.array_equal(nv, staged[f]["visible"][: nv.shape[0]]), f
+            assert np.array_equal(gp.output("vplVisiblePerTile"), staged[f]["stage2"]), f
+        else:                                              # frame 0's inputs again: the same lists as frame 0
+            assert np.array_equal(gp.output("vplVisiblePerTile"), staged[0]["stage2"])
+        nf = (f + 1) % 2
+        gp.synchronize()                                   # (the test swaps whole input planes between frames; a renderer's are per-frame resources)
+        gp.set_gbuffer(tiny.gb[nf], tiny.gb[nf - 1]); gp.set_csm(tiny.csm[nf]); gp.bind()
+        gp.early_begin(ptr)
+        gp.cull_early(tiny.fp[nf], ptr, with_color=(f % 2 == 0))
+    # refusals (an early cull for frame 1's inputs is pending here)
     with pytest.raises(StratusGiError):
-        gp.cull_early(tiny.fp[0], ptr)                     # not consumed yet
-    other = tiny.fp[0].copy(); other.totalNumLights -= 1
+        gp.cull_early(tiny.fp[1], ptr)                     # not consumed yet
+    other = tiny.fp[1].copy(); other.totalNumLights -= 1
     with pytest.raises(StratusGiError):
         gp.frame(other)                                    # a different frame than the early cull was given
-    gp.cull(tiny.fp[0])                                    # explicit cull: supersedes the pending one
-    gp.color(tiny.fp[0]); gp.tile_lists(tiny.fp[0]); gp.gather(tiny.fp[0]); gp.denoise(tiny.fp[0])
+    gp.cull(tiny.fp[1])                                    # explicit cull: supersedes the pending one
     gp.synchronize()
     gp.close()
 
