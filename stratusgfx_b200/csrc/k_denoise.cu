@@ -30,16 +30,17 @@
 // of a warp are consecutive in x, so every request is fully coalesced.  Each output accumulates its
 // taps in the same order (dy ascending, dx ascending) wherever it sits in a band, so a row band with an
 // apron reproduces the whole-frame bytes.
+#include <mutex>
+#include <vector>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 #include "sgi_merge.cuh"
+#include "sgi_denoise.cuh"
 
 namespace sgi {
 namespace {
 
-constexpr float PREVENT_DIV_BY_ZERO = 0.00001f;
 constexpr int kDnX = 32, kDnY = 8;
-constexpr int kLat = 4;                       // à-trous: outputs per thread, consecutive on the tap lattice of its column
 
 struct Bilin { int i0, i1, j0, j1; float a, b; };
 SGI_DEV Bilin bilinSetup(float u, float v, int W, int H) {
@@ -153,26 +154,6 @@ temporalKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid
     io.temporal[p] = make_float4(prevGi.x, prevGi.y, prevGi.z, maxAccumulationFactor);
 }
 
-// ---- final-pass epilogue: blend with the reprojected history and re-modulate (vpl_pbr_gi_denoise.fs:424-434) --------------
-SGI_DEV void finalEpilogue(const BandDims& bd, const DenoiseIO& io, int x, int ly, f3 shadowFactor) {
-    const int W = bd.W;
-    const int y = ly + bd.yOffset;
-    const size_t p = (size_t)ly * W + x;
-    const float4 t = __ldg(io.temporal + p);                 // (prevGi.rgb, 1 / history) from temporalKernel
-    const f4 screenColor = loadHalf4(io.screen, p);
-    const f4 gi4 = loadHalf4(io.illum, p);
-    const f3 gi = mk3(gi4.x, gi4.y, gi4.z);
-    const f3 illumAvg = mix(mk3(t.x, t.y, t.z), shadowFactor, t.w);
-    const f3 combined = mk3(screenColor.x, screenColor.y, screenColor.z) + gi * illumAvg;
-    const uint2 cv = packHalf4(combined.x, combined.y, combined.z, 1.0f), gv = packHalf4(illumAvg.x, illumAvg.y, illumAvg.z, 1.0f);
-    io.combinedOut[p] = cv;
-    io.giOut[p] = gv;
-    // row bands: this frame's GI boundary rows go to the neighbours' halos (reprojection may land there next frame; the history
-    // plane is only ever read at the pixel itself); the owner band also stores its own lit rows into its frame image
-    pushGi(io.links, y, x, W, gv);
-    if (io.links.image != nullptr) io.links.image[(size_t)y * W + x] = cv;
-}
-
 // ---- pass 0: mergeReservoirs, the centre texel only (computeMergedReservoir with minmaxNearest = 0, :259-264) ----
 template <bool FINAL>
 __global__ void __launch_bounds__(kDnX * kDnY)
@@ -194,10 +175,6 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 }
 
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
-constexpr float kLog2e = 1.4426950408889634f;
-
-SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // Rows a CTA row `by` of the à-trous grid can output (band-local, a superset for spacings > kDnY): thread rows kDnY*by .. +kDnY-1
 // are lattice groups g = t / s, each kLat*s rows tall.  Host and device use the same formula to decide which CTAs push rows to
@@ -225,24 +202,6 @@ __device__ __forceinline__ int boundaryFirst(int p, int n) {
 // IMMEDIATE column offsets; the others take the clamped path below (CLAMP_TO_EDGE).  Both paths read the same taps in the same
 // order with the same arithmetic, so their outputs are the same bytes.  (Round 2 A/B on c4, profiles/r02a: 0.166 -> 0.148 ms per
 // non-final pass against per-tap clamps and 64-bit index arithmetic on every thread.)
-SGI_DEV void atrousTap(const float4 (&cen)[kLat], float (&acc)[kLat][4], int c, int d, float4 gq, uint2 rv) {
-    // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly
-    const float rr = h2f((unsigned short)(rv.x & 0xffffu)), rg = h2f((unsigned short)(rv.x >> 16)), rb = h2f((unsigned short)(rv.y & 0xffffu));
-    const float tq = gq.w * kLog2e;
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) {
-        const int dy = c - 2 - k;
-        if (dy < -2 || dy > 2) continue;
-        float w = 1.0f;                              // centre tap (:156)
-        if (dy != 0 || d != 2) {
-            // max(0, n.n')^128 * exp(-|z - z'|)   (sigmaN = 128, sigmaZ = 1, :93-98, :169-173)
-            const float wn = fmaxf(__fmaf_rn(cen[k].z, gq.z, __fmaf_rn(cen[k].y, gq.y, __fmul_rn(cen[k].x, gq.x))), 0.0f);
-            w = ex2Fast(__fmaf_rn(128.0f, lg2Fast(wn), -fabsf(cen[k].w - tq)));
-        }
-        acc[k][0] = __fmaf_rn(w, rr, acc[k][0]); acc[k][1] = __fmaf_rn(w, rg, acc[k][1]);
-        acc[k][2] = __fmaf_rn(w, rb, acc[k][2]); acc[k][3] += w;
-    }
-}
 template <int S>
 SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
     const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
@@ -259,19 +218,21 @@ template <bool FINAL, int S>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __grid_constant__ DenoiseIO io) {
     const int W = bd.W, rows = bd.rows;
-    const int x = blockIdx.x * kDnX + threadIdx.x;
     const int s = S ? S : 1 + io.multiplier;                 // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
-    const int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
+    int bx = (int)blockIdx.x;
+    int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
+    if (io.borderCtas != nullptr) { const int2 c = __ldg(io.borderCtas + blockIdx.x); bx = c.x; by = c.y; }      // compact launch on the frame's border
+    const int x = bx * kDnX + threadIdx.x;
     const int t = by * kDnY + threadIdx.y;                   // lattice column-of-rows id: residue r, group g
     const int g = t / s, r = t - g * s;
     const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
     const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
-    if (!FINAL && io.skipX1 > io.skipX0) {
-        // whole-frame handles: the interior lattice tiles were written by the TMA-staged kernel (k_atrous_tma.cu); a CTA whose
-        // outputs all lie inside that rectangle leaves at once (uniform), the others skip the covered outputs one by one
+    if (io.skipX1 > io.skipX0) {
+        // whole-frame handles: the interior was written by the TMA-staged kernel (k_atrous_tma.cu); a CTA whose outputs all lie
+        // inside that rectangle leaves at once (uniform), the others skip the covered outputs one by one
         int lo, hi;
         atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
-        if ((int)blockIdx.x * kDnX >= io.skipX0 && (int)blockIdx.x * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
+        if (bx * kDnX >= io.skipX0 && bx * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
     }
     const bool live = x < W && c0 + m0 * s + r < cEnd;
     // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
@@ -317,9 +278,8 @@ atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __gr
     for (int k = 0; k < kLat; ++k) {
         const int ly = c0 + (m0 + k) * s + r;
         if (ly >= cEnd) break;
-        if (!FINAL && x >= io.skipX0 && x < io.skipX1 && ly >= io.skipY0 && ly < io.skipY1) continue;
-        const float invDenom = __fdividef(1.0f, vmax(PREVENT_DIV_BY_ZERO, acc[k][3]));      // radiance tier (see header)
-        const f3 shadowFactor = mk3(acc[k][0] * invDenom, acc[k][1] * invDenom, acc[k][2] * invDenom);
+        if (x >= io.skipX0 && x < io.skipX1 && ly >= io.skipY0 && ly < io.skipY1) continue;
+        const f3 shadowFactor = atrousResolve(acc[k]);
         const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
         io.reservoirOut[(size_t)ly * W + x] = rv;
         pushRes(io.links, ly + bd.yOffset, x, W, rv);
@@ -357,6 +317,36 @@ bool preloadDenoiseKernels() {
     return ok;
 }
 
+#ifdef __CUDACC__
+// The CTAs (x tile, CTA row) of atrousKernel's grid that reach outside the rectangle the TMA kernel wrote, as a device array: built
+// once per (device, plane size, spacing) and kept for the life of the process (a few KB).
+static const int2* borderCtaList(const BandDims& bd, int s, int gridX, int gridY, int x0, int x1, int y0, int y1, int* count) {
+    struct Entry { int dev, W, rows, s, x0, x1, y0, y1, n; int2* ptr; };
+    static std::vector<Entry> cache;
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Entry& e : cache)
+        if (e.dev == dev && e.W == bd.W && e.rows == bd.rows && e.s == s && e.x0 == x0 && e.x1 == x1 && e.y0 == y0 && e.y1 == y1) { *count = e.n; return e.ptr; }
+    std::vector<int2> list;
+    for (int by = 0; by < gridY; ++by) {
+        int lo, hi;
+        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+        for (int bx = 0; bx < gridX; ++bx)
+            if (!(bx * kDnX >= x0 && bx * kDnX + kDnX <= x1 && lo >= y0 && hi <= y1)) list.push_back(make_int2(bx, by));
+    }
+    Entry e{dev, bd.W, bd.rows, s, x0, x1, y0, y1, (int)list.size(), nullptr};
+    if (!list.empty()) {
+        if (cudaMalloc((void**)&e.ptr, list.size() * sizeof(int2)) != cudaSuccess) { *count = 0; cudaGetLastError(); return nullptr; }
+        cudaMemcpy(e.ptr, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    }
+    cache.push_back(e);
+    *count = e.n;
+    return e.ptr;
+}
+#endif
+
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide) {
     const size_t n = (size_t)bd.W * bd.rows;
     prepareGuideKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, normal, depth, guide);
@@ -384,13 +374,17 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
 #ifdef __CUDACC__                        // (the host-emulation builds of tests/cuda_on_host have no TMA: they run atrousKernel on everything)
-        if (!final_ && io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr &&
-            io.links.waitDown == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
-            // whole-frame handles: the interior lattice tiles through the TMA-staged kernel (taps from shared memory: 0.150 -> 0.144-0.147 ms
-            // per pass on c4, same bytes; profiles/r02g), the border tiles (CLAMP_TO_EDGE taps) through the kernel below
-            int ix0, ix1, iy0, iy1;
-            if (launchAtrousTma(stream, bd.W, bd.rows, s, io.guide, io.shadowsIn, io.reservoirOut, &ix0, &ix1, &iy0, &iy1)) {
-                io.skipX0 = ix0 * s; io.skipX1 = ix1 * s; io.skipY0 = iy0 * s; io.skipY1 = iy1 * s;
+        if (io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr && io.links.waitDown == nullptr &&
+            io.links.image == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
+            // whole-frame handles: the interior through the TMA-staged kernel (taps from shared memory: 0.150 -> 0.122 ms per pass on
+            // c4, same bytes; profiles/r02i), the frame's border (CLAMP_TO_EDGE taps) through the kernel below on a compact CTA list
+            int x0, x1, y0, y1;
+            if (launchAtrousTma(stream, bd, io, final_, &x0, &x1, &y0, &y1)) {
+                io.skipX0 = x0; io.skipX1 = x1; io.skipY0 = y0; io.skipY1 = y1;
+                int count = 0;
+                io.borderCtas = borderCtaList(bd, s, (int)grid.x, (int)grid.y, x0, x1, y0, y1, &count);
+                if (io.borderCtas != nullptr) grid = dim3((unsigned)count, 1);
+                if (count == 0) return 1;
             }
         }
 #endif

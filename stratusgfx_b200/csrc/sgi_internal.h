@@ -171,8 +171,10 @@ struct DenoiseIO {
     uint2* giOut;                 // half4 (final pass)
     unsigned short* historyOut;   // half  (final pass)
     int multiplier;
-    // outputs inside this pixel rectangle (band-local rows) were written by the TMA-staged kernel (k_atrous_tma.cu): atrousKernel skips them
+    // outputs inside this pixel rectangle (band-local rows) were written by the TMA-staged kernel (k_atrous_tma.cu): atrousKernel skips
+    // them, and runs on the compact list of CTAs (x tile, CTA row) that reach outside the rectangle instead of on its whole grid
     int skipX0, skipX1, skipY0, skipY1;
+    const int2* borderCtas;
 };
 
 }  // namespace sgi
@@ -298,7 +300,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
                  bool* signalled /* out: the kernel releases the neighbours' flags itself */);
 int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
-bool launchAtrousTma(cudaStream_t stream, int W, int rows, int s, const float4* guide, const uint2* in, uint2* out, int* ix0, int* ix1, int* iy0, int* iy1);
+bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int* x0, int* x1, int* y0, int* y1);   // k_atrous_tma.cu
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
                       bool* signalled /* out: the kernel releases the neighbours' flags itself */);
