@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(CSRC, "libstratusgi.so")
 CU_SOURCES = ["sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_cubemaps.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu", "k_atrous_tma.cu"]
-HEADERS = ["sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", os.path.join("..", "..", "include", "stratusgi.h")]
+HEADERS = ["sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", "sgi_denoise.cuh", os.path.join("..", "..", "include", "stratusgi.h")]
 
 # -fmad=false: the integer outputs of this path hinge on float comparisons, so no mul+add may be
 # contracted behind the source's back (see csrc/sgi_math.cuh).  IEEE sqrt/div are nvcc defaults.

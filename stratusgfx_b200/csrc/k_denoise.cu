@@ -185,23 +185,6 @@ __host__ __device__ inline void atrousSlab(int by, int s, int c0, int cEnd, int*
     const int h = c0 + (gHi + 1) * kLat * s;
     *hi = h < cEnd ? h : cEnd;
 }
-__host__ __device__ inline bool slabPushes(const BandLinks& L, int lo, int hi, int yOffset) {      // band-local rows [lo, hi)
-    const int a = lo + yOffset, b = hi + yOffset;
-    return (L.up.res != nullptr && a < L.up.lastRow && b > L.up.firstRow) || (L.down.res != nullptr && a < L.down.lastRow && b > L.down.firstRow);
-}
-// CTA rows in launch order when the kernel signals its neighbours itself: the first, the last and the second-last row of the grid
-// (the ones that hold the band's boundary rows) before the interior
-__device__ __forceinline__ int boundaryFirst(int p, int n) {
-    if (n <= 3) return p;
-    return p == 0 ? 0 : (p == 1 ? n - 1 : (p == 2 ? n - 2 : p - 2));
-}
-
-// The tap spacing of the reference's passes (2, 4, 8: multiplier 1, 3, 7, BE:1920) is a template parameter; S = 0 reads it from the
-// pass parameters (other iteration counts).  A thread whose (kLat+4) x 5 taps all lie inside the held rows and columns — every
-// thread but those within two taps of an edge — addresses them as one row pointer per plane, advanced by a constant stride, plus
-// IMMEDIATE column offsets; the others take the clamped path below (CLAMP_TO_EDGE).  Both paths read the same taps in the same
-// order with the same arithmetic, so their outputs are the same bytes.  (Round 2 A/B on c4, profiles/r02a: 0.166 -> 0.148 ms per
-// non-final pass against per-tap clamps and 64-bit index arithmetic on every thread.)
 template <int S>
 SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
     const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
@@ -234,7 +217,9 @@ atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __gr
         atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
         if (bx * kDnX >= io.skipX0 && bx * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
     }
-    const bool live = x < W && c0 + m0 * s + r < cEnd;
+    bool live = x < W && c0 + m0 * s + r < cEnd;
+    // (border launch) a thread whose four outputs all lie inside the TMA kernel's rectangle has nothing to do
+    if (io.skipX1 > io.skipX0 && x >= io.skipX0 && x < io.skipX1 && c0 + m0 * s + r >= io.skipY0 && c0 + (m0 + kLat - 1) * s + r < io.skipY1) live = false;
     // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
     // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
     bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);

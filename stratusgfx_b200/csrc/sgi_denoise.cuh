@@ -14,6 +14,24 @@ constexpr int kLat = 4;                       // à-trous: outputs per thread, c
 SGI_DEV float lg2Fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+__host__ __device__ inline bool slabPushes(const BandLinks& L, int lo, int hi, int yOffset) {      // band-local rows [lo, hi)
+    const int a = lo + yOffset, b = hi + yOffset;
+    return (L.up.res != nullptr && a < L.up.lastRow && b > L.up.firstRow) || (L.down.res != nullptr && a < L.down.lastRow && b > L.down.firstRow);
+}
+// CTA rows in launch order when the kernel signals its neighbours itself: the first, the last and the second-last row of the grid
+// (the ones that hold the band's boundary rows) before the interior
+__device__ __forceinline__ int boundaryFirst(int p, int n) {
+    if (n <= 3) return p;
+    return p == 0 ? 0 : (p == 1 ? n - 1 : (p == 2 ? n - 2 : p - 2));
+}
+
+// The tap spacing of the reference's passes (2, 4, 8: multiplier 1, 3, 7, BE:1920) is a template parameter; S = 0 reads it from the
+// pass parameters (other iteration counts).  A thread whose (kLat+4) x 5 taps all lie inside the held rows and columns — every
+// thread but those within two taps of an edge — addresses them as one row pointer per plane, advanced by a constant stride, plus
+// IMMEDIATE column offsets; the others take the clamped path below (CLAMP_TO_EDGE).  Both paths read the same taps in the same
+// order with the same arithmetic, so their outputs are the same bytes.  (Round 2 A/B on c4, profiles/r02a: 0.166 -> 0.148 ms per
+// non-final pass against per-tap clamps and 64-bit index arithmetic on every thread.)
+
 // one loaded tap (guide gq, reservoir rv) at tap line c (0 .. kLat+3) and column d (0 .. 4) into the kLat outputs it serves
 SGI_DEV void atrousTap(const float4 (&cen)[kLat], float (&acc)[kLat][4], int c, int d, float4 gq, uint2 rv) {
     // the input of every pass >= 1 is the previous pass's vec4(shadowFactor, 1.0): alpha is 1 exactly

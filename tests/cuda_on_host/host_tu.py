@@ -27,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "stratusgfx_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
-HEADERS = ("sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh")
+HEADERS = ("sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", "sgi_denoise.cuh")
 
 # rule 2: helpers that the shim supplies (name -> only checked for presence, the definitions live in cuda_host_shim.h)
 PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys", "sqrtApprox", "sqrtFast")
