@@ -49,8 +49,15 @@ constexpr float HALF_FLOAT_MAX = 65504.0f;
 constexpr float kMargin = 1e-5f;
 
 SGI_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-SGI_DEV float rcpFast(float x) { return __fdividef(1.0f, x); }
+// radiance tier and margin estimates: one MUFU each (the non-ftz forms nvcc emits for the fast-division, reciprocal-square-root
+// and exponential intrinsics carry a denormal-range rescue of three to four more instructions per call; no operand of this
+// file gets near that range)
+SGI_DEV float rcpFast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SGI_DEV float rsqrtFast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float sqrtFast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+constexpr float kLog2e = 1.4426950408889634f;
+SGI_DEV float expFast(float x) { return ex2Fast(x * kLog2e); }
 SGI_DEV float dotFast(f3 a, f3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
 SGI_DEV float satFast(float x) { return __saturatef(x); }
 
@@ -67,30 +74,35 @@ __device__ __noinline__ bool exactShadowed(f3 fragDir, float lightNormalDot, flo
     return fsub(currentDepth, bias) > fmul(texelDepth, farPlane);
 }
 
-// cube texel with exact semantics: estimate s*res, t*res; only a coordinate within 1e-4 of a texel edge
-// (or a near-tie between major axes) needs the exact division chain
-SGI_DEV int cubeTexelDecided(f3 d, int res) {
+// Cube texel with exact semantics.  The face is chosen by exact comparisons of the inputs (GL 4.6 table 8.19: signs folded in with
+// bit operations, -0 as a major component only when the direction is all zeros, which the NaN of the estimate sends to the exact
+// chain).  The texel coordinates are estimated as se = fma(sc * rcp(ma), res/2, res/2) and only a coordinate within `eps` of a texel
+// edge needs the exact division chain of cubeTexel (sgi_math.cuh).  Bound: q = fl(sc/ma), qe = sc * rcp.approx(ma) differ by at most
+// |q| 2^-22 (1 ulp of the reciprocal, one product, one division); the exact chain fl(fl(fl(q + 1) / 2) res) is within
+// res (2^-25 + 2^-24) of (q + 1) res / 2 and the estimate within res 2^-24 of (qe + 1) res / 2, so |se - exact| <=
+// res (|q| 2^-23 + 2.5 * 2^-24) and eps = res 2^-22 (|qe| + 1) keeps a factor 1.6 to 2 over it.  (Round 1 used a flat 1e-4 texels,
+// round 2 first 3e-5: pixels that lie in the plane of a VPL — a floor pixel under a floor VPL — have |q| ~ 1e-6, that is se within
+// 1e-5 .. 1e-4 of the middle edge, and took the exact chain on 70 % of the warp iterations; profiles/r02k.)
+SGI_DEV int cubeTexelDecided(f3 d, int res, float halfRes, float epsK) {
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    // major axis and (sc, tc) of GL 4.6 table 8.19 as selects (no divergent branches)
     const bool xMajor = ax >= ay && ax >= az, yMajor = !xMajor && ay >= az;
+    const uint32_t bx = __float_as_uint(d.x), by = __float_as_uint(d.y), bz = __float_as_uint(d.z), kSign = 0x80000000u;
     const float ma = xMajor ? ax : (yMajor ? ay : az);
-    const float dm = xMajor ? d.x : (yMajor ? d.y : d.z);           // signed major component
-    const bool pos = dm >= 0.0f;
-    const int face = (xMajor ? 0 : (yMajor ? 2 : 4)) + (pos ? 0 : 1);
-    const float sc = xMajor ? (pos ? -d.z : d.z) : (yMajor ? d.x : (pos ? d.x : -d.x));
-    const float tc = yMajor ? (pos ? d.z : -d.z) : -d.y;
-    // the face choice above uses exact comparisons of the inputs, so it is already the exact one
-    const float inv = rcpFast(ma), fres = (float)res;
-    const float se = fma_(sc * inv, 0.5f, 0.5f) * fres, te = fma_(tc * inv, 0.5f, 0.5f) * fres;
+    const uint32_t major = xMajor ? bx : (yMajor ? by : bz);                                  // its sign bit: the negative face
+    const int face = (xMajor ? 0 : (yMajor ? 2 : 4)) + (int)(major >> 31);
+    // sc: +x: -z, -x: z | y: x | +z: x, -z: -x          tc: +y: z, -y: -z | others: -y
+    const float sc = __uint_as_float(xMajor ? (bz ^ (~bx & kSign)) : (yMajor ? bx : (bx ^ (bz & kSign))));
+    const float tc = __uint_as_float(yMajor ? (bz ^ (by & kSign)) : (by ^ kSign));
+    const float inv = rcpFast(ma);
+    const float qs = sc * inv, qt = tc * inv;
+    const float se = fma_(qs, halfRes, halfRes), te = fma_(qt, halfRes, halfRes);
     const float sf = floorf(se), tf = floorf(te);
-    // disagreement between this estimate and the exact chain is at most 32 * (|sc/ma| * (2^-23 + 2^-24) * 0.5 + 2^-24) + 32 * 0.5 * 3 * 2^-24
-    // < 8e-6 texels for res = 32 (rcp.approx: 1 ulp; one product, one fma; the exact side: one division, one add): 3e-5 keeps a
-    // factor 4 and sends 3x fewer lanes to the exact fallback than the 1e-4 of round 1
-    const float eps = 3e-5f * (fres * (1.0f / 32.0f));
-    const bool sure = (se - sf > eps) && (sf + 1.0f - se > eps) && (te - tf > eps) && (tf + 1.0f - te > eps);
+    const float es = fma_(fabsf(qs), epsK, epsK), et = fma_(fabsf(qt), epsK, epsK);
+    // eps < frac < 1 - eps  <=>  |frac - 0.5| < 0.5 - eps   (false for a NaN estimate)
+    const bool sure = fabsf((se - sf) - 0.5f) < 0.5f - es && fabsf((te - tf) - 0.5f) < 0.5f - et;
     if (!sure) return exactCubeTexel(d, res);
-    const int i = iclamp((int)sf, 0, res - 1), j = iclamp((int)tf, 0, res - 1);
-    return (face * res + j) * res + i;
+    // a sure coordinate lies strictly inside [0, res): no clamp
+    return (face * res + (int)tf) * res + (int)sf;
 }
 
 struct PixelConsts {   // per-pixel values that do not depend on the light
@@ -104,16 +116,16 @@ SGI_DEV f3 shadeFast(const PixelConsts& px, f3 specularLightPos, f3 diffuseLight
     const f3 Ls = mk3(specularLightPos.x - px.fragPos.x, specularLightPos.y - px.fragPos.y, specularLightPos.z - px.fragPos.z);
     const f3 Ld = mk3(diffuseLightPos.x - px.fragPos.x, diffuseLightPos.y - px.fragPos.y, diffuseLightPos.z - px.fragPos.z);
     const float ds2 = dotFast(Ls, Ls), dd2 = dotFast(Ld, Ld);
-    const float is = rsqrtf(ds2), id = rsqrtf(dd2);
+    const float is = rsqrtFast(ds2), id = rsqrtFast(dd2);
     // vplDiffuseAttenuation for both directions (pbr.glsl:260-267): 1 / (mix(10,1,exp(-3*ratio))*radius + dist^2)
     const float rs = fminf(ds2 * is * invRadius, 1.0f), rd = fminf(dd2 * id * invRadius, 1.0f);
-    const float es = __expf(-3.0f * rs), ed = __expf(-3.0f * rd);
+    const float es = ex2Fast(rs * (-3.0f * kLog2e)), ed = ex2Fast(rd * (-3.0f * kLog2e));
     const float attS = rcpFast(fma_(fma_(es, -9.0f, 10.0f), lightRadius, ds2));
     const float attD = rcpFast(fma_(fma_(ed, -9.0f, 10.0f), lightRadius, dd2));
     // specular lobe
     const f3 L = mk3(Ls.x * is, Ls.y * is, Ls.z * is);
     f3 H = mk3(px.viewDir.x + L.x, px.viewDir.y + L.y, px.viewDir.z + L.z);
-    const float ih = rsqrtf(dotFast(H, H));
+    const float ih = rsqrtFast(dotFast(H, H));
     const float NdotL = satFast(dotFast(px.normal, L));
     const float NdotH = satFast(dotFast(px.normal, H) * ih);
     const float LdotH = satFast(dotFast(L, H) * ih);
@@ -145,27 +157,40 @@ SGI_DEV bool behindOrOutOfRange(f3 normal, f3 lightMinusFrag, float d2, float li
     return exactRedraw(normal, lightMinusFrag, lightRadius);
 }
 
+// what does not change from light to light in the shadow lookup
+struct CubeConsts {
+    int res, texelsPerLayer;
+    float halfRes, epsK;       // res / 2, res * 2^-22 (cubeTexelDecided)
+};
+SGI_DEV CubeConsts cubeConsts(int cubeRes) {
+    CubeConsts c;
+    c.res = cubeRes; c.texelsPerLayer = 6 * cubeRes * cubeRes;
+    c.halfRes = 0.5f * (float)cubeRes; c.epsK = (float)cubeRes * (1.0f / 4194304.0f);
+    return c;
+}
+
 // one accepted light: shadow test, occlusion floor, re-weighting and shading (vpl_pbr_gi.fs:173-198)
 SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 lightMinusFrag, float d2, float lightRadius, float farPlane,
-                                f3 lightColor, f3 specularPosition, SgiAtlasEntry entry, bool shadowsOn, float minGi, int cubeRes,
-                                int texelsPerLayer, const AtlasTable& atlases, f3& vplColor, float& validSamples) {
+                                f3 lightColor, f3 specularPosition, int entryBits /* atlas index << 16 | layer */, bool shadowsOn, float minGi,
+                                const CubeConsts& cc, const AtlasTable& atlases, f3& vplColor, float& validSamples) {
     const float invRadius = rcpFast(lightRadius);
-    const float distance = d2 * rsqrtf(d2);
+    const float distance = d2 * rsqrtFast(d2);
     const float distanceRatio = satFast(2.0f * distance * invRadius);
     float shadowFactor = 0.0f;
     if (shadowsOn) {
         // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1: texel choice and the lit/shadowed verdict are decisions
         const f3 fragDir = px.fragPos - lightPosition;
-        const unsigned short texel = __ldg(atlases.shadow[entry.index] + (size_t)entry.layer * texelsPerLayer + cubeTexelDecided(fragDir, cubeRes));
-        const float texelDepth = unorm16(texel);
+        const uint32_t offset = (uint32_t)(entryBits & 0xffff) * (uint32_t)cc.texelsPerLayer + (uint32_t)cubeTexelDecided(fragDir, cc.res, cc.halfRes, cc.epsK);
+        const uint32_t texel = __ldg(atlases.shadow[entryBits >> 16] + offset);
+        const float texelDepthEst = (float)texel * (1.0f / 65535.0f);      // within an ulp of the exact unorm16 (margin below: 8e-5)
         const float lightNormalDot = dotFast(lightMinusFrag, px.normal);
         const float biasFactor = fmaxf(0.1f, satFast(lightNormalDot) * 0.03f);
-        const float lhs = distance * (1.0f - biasFactor), rhs = texelDepth * farPlane;
+        const float lhs = distance * (1.0f - biasFactor), rhs = texelDepthEst * farPlane;
         const float gap = lhs - rhs;
         // lightNormalDot only matters through saturate(.)*0.03 vs 0.1, i.e. when it exceeds 3.33: never borderline for the verdict's margin
         bool shadowed;
         if (fabsf(gap) > 8.0f * kMargin * fmaxf(lhs, rhs)) shadowed = gap > 0.0f;
-        else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), texelDepth, farPlane);
+        else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), unorm16(texel), farPlane);
         shadowFactor = shadowed ? 1.0f : 0.0f;
     }
     shadowFactor = fminf(shadowFactor, fma_(distanceRatio, 1.0f - minGi, minGi));
@@ -175,6 +200,17 @@ SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 ligh
     const f3 tmpColor = shadeFast(px, specularPosition, lightPosition, lightColor, lightRadius, invRadius);
     const float lit = 1.0f - shadowFactor;
     vplColor = mk3(fma_(lit, tmpColor.x, vplColor.x), fma_(lit, tmpColor.y, vplColor.y), fma_(lit, tmpColor.z, vplColor.z));
+}
+
+// Denoise pass 0 of one channel on the binary16 reservoir just stored: f2h(a / denom), a and denom binary16 values, denom >= 1.
+// The quotient is needed to 11 bits only, so it is estimated as a * rcp(denom) — within 4 ulp (binary32) of the IEEE quotient — and
+// only an estimate within 8 ulp of a binary16 rounding boundary (a midpoint of two neighbours: low 13 mantissa bits 0x1000), or
+// below binary16's normal range (boundaries are spaced differently there), takes the exact division.  a = 0 gives 0 on both routes.
+SGI_DEV unsigned short mergedChannel(float a, float denom, float invDenom) {
+    const float q = a * invDenom;
+    const uint32_t b = __float_as_uint(q);
+    const bool sure = (((b + 8u - 0x1000u) & 0x1fffu) > 16u && q >= 6.2e-5f) || a == 0.0f;
+    return f2h(sure ? q : fdiv(a, denom));
 }
 
 // tile-list mode: the <= 12 VPLs of a tile as the kernel stages them in shared memory
@@ -229,8 +265,7 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
                 links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
     if (x >= bd.W || ly >= bd.rows) return;
     const size_t p = (size_t)ly * bd.W + x;
-    const int cubeRes = bd.cubeRes;
-    const int texelsPerLayer = 6 * cubeRes * cubeRes;
+    const CubeConsts cc = cubeConsts(bd.cubeRes);
 
     // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
     const float depth = __ldg(gDepth + p);
@@ -264,7 +299,7 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
         if (fc.usePerceptualRoughness) rr = rr * rr;
         rr = fmaxf(fmaxf(0.0f, fc.minRoughness), rr);
         px.r2 = rr * rr;
-        const float iv = rsqrtf(dotFast(toView, toView));
+        const float iv = rsqrtFast(dotFast(toView, toView));
         px.viewDir = mk3(toView.x * iv, toView.y * iv, toView.z * iv);
         px.NdotV = satFast(dotFast(px.normal, px.viewDir));
         px.ggxvTerm = sqrtFast(fma_(fma_(-px.r2, px.NdotV, px.NdotV), px.NdotV, px.r2));
@@ -273,7 +308,7 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
         // diffuseColor / (diffuseDivisor + eps) / PI   and   f0 * specularMultiplier
         px.diffuseOverPi = mk3(om * baseColor.x * inv.x * (1.0f / PI_F), om * baseColor.y * inv.y * (1.0f / PI_F), om * baseColor.z * inv.z * (1.0f / PI_F));
         px.f0 = mk3(fma_(baseColor.x, metallic, f0s) * inv.x, fma_(baseColor.y, metallic, f0s) * inv.y, fma_(baseColor.z, metallic, f0s) * inv.z);
-        px.fogAo = __expf(-fc.fogDensity * distToCamera) * ambientOcclusion;
+        px.fogAo = expFast(-fc.fogDensity * distToCamera) * ambientOcclusion;
     }
 
     f3 vplColor = mk3(0.0f);
@@ -294,10 +329,8 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
             const float lightRadius = sl.posRadius.w;
             const float d2 = dotFast(lightMinusFrag, lightMinusFrag);
             if (behindOrOutOfRange(px.normal, lightMinusFrag, d2, lightRadius)) continue;
-            const int eb = __float_as_int(sl.specEntry.w);
-            SgiAtlasEntry entry; entry.index = eb >> 16; entry.layer = eb & 0xffff;
             shadeAcceptedLight(px, lightPosition, lightMinusFrag, d2, lightRadius, sl.colorFar.w, mk3(sl.colorFar.x, sl.colorFar.y, sl.colorFar.z),
-                               mk3(sl.specEntry.x, sl.specEntry.y, sl.specEntry.z), entry, shadowsOn, minGi, cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
+                               mk3(sl.specEntry.x, sl.specEntry.y, sl.specEntry.z), __float_as_int(sl.specEntry.w), shadowsOn, minGi, cc, atlases, vplColor, validSamples);
         }
     }
     validSamples = fmaxf(validSamples, 1.0f);
@@ -313,9 +346,12 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
         // Denoise pass 0 on the binary16 reservoir just stored.  mergeCentreTexel (sgi_merge.cuh) reduces to rgb / max(1e-5, a)
         // here: the normal is unit length, |z - z| = 0, and with a >= 1 and 1 <= V <= 4480 the single candidate's acceptance
         // ratio probability / cw is x / x = 1 exactly, which every draw in [0,1) passes.  V <= 0 leaves the reservoir empty.
-        const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha));
-        const f3 m = V > 0 ? mk3(h2f(hr), h2f(hg), h2f(hb)) / denom : mk3(0.0f);
-        const uint2 mv = packHalf4(m.x, m.y, m.z, 1.0f);
+        const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha)), invDenom = rcpFast(denom);
+        uint2 mv = make_uint2(0u, 0x3c000000u);                      // (0, 0, 0, 1)
+        if (V > 0) {
+            mv.x = (uint32_t)mergedChannel(h2f(hr), denom, invDenom) | ((uint32_t)mergedChannel(h2f(hg), denom, invDenom) << 16);
+            mv.y |= (uint32_t)mergedChannel(h2f(hb), denom, invDenom);
+        }
         mergedOut[p] = mv;
         pushRes(links, y, x, bd.W, mv);
     }
@@ -346,14 +382,31 @@ SGI_DEV void bandWaitWarp(const BandLinks& L, bool needUp, bool needDown) {
     }
 }
 
-template <int THREADS>
+// per-column / per-row values of the pixel grid that the shader recomputes for every fragment: built once per handle
+// geometry by coordTableKernel with the exact operations of the shader (fsTexCoords = gl_FragCoord.xy / resolution)
+struct CoordTables {
+    const float* u;            // [W]     (x + 0.5) / W
+    const float2* row;         // [rows]  ((y + 0.5) / fullH, bits of hash(floatBitsToUint(y + 0.5))) for frame row y = yOffset + local row
+};
+__global__ void coordTableKernel(BandDims bd, float* __restrict__ u, float2* __restrict__ row) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < bd.W) u[i] = fdiv(fadd((float)i, 0.5f), (float)bd.W);
+    if (i < bd.rows) {
+        const float pcy = fadd((float)(i + bd.yOffset), 0.5f);
+        row[i] = make_float2(fdiv(pcy, (float)bd.fullH), __uint_as_float(hash1(__float_as_uint(pcy))));
+    }
+}
+
+// BANDS = false: a whole-frame handle (no neighbour, no halo rows): the band branches are not compiled in
+template <int THREADS, bool BANDS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* __restrict__ gDepth, const uint32_t* __restrict__ gNormal,
                        const uint32_t* __restrict__ gAlbedo, const uint16_t* __restrict__ gRefl, const uint32_t* __restrict__ gRma,
                        const unsigned short* __restrict__ ssao, const SgiVplData* __restrict__ lightData, const int32_t* __restrict__ numVisible,
                        const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
                        uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
-                       const __grid_constant__ BandLinks links, int tableCap, int* __restrict__ unitCounters, int counterSel) {
+                       const __grid_constant__ BandLinks links, int tableCap, int* __restrict__ unitCounters, int counterSel,
+                       CoordTables tabs, uint32_t unitsXMagic /* ceil(2^32 / unitsX), or 0: divide */) {
     extern __shared__ float4 sTab[];
     float4* __restrict__ sPos = sTab;                       // (position, radius)
     float4* __restrict__ sCol = sTab + tableCap;            // (colour, farPlane)
@@ -373,8 +426,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     const int lane = threadIdx.x & 31;
     const int unitsX = (bd.W + 31) >> 5;
     const int units = unitsX * bd.rows;
-    const int cubeRes = bd.cubeRes;
-    const int texelsPerLayer = 6 * cubeRes * cubeRes;
+    const CubeConsts cc = cubeConsts(bd.cubeRes);
     const m4 invPV = loadMat(fc.invPV);
     const f3 viewPosition = mk3(fc.viewPos[0], fc.viewPos[1], fc.viewPos[2]);
     const float maxRandomIndexF = (float)(V - 1);
@@ -385,7 +437,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     // all of its CTAs are resident from the start (sgi_frame runs the tile-list stages next to it on a side stream).  Counter
     // [frame & 1] serves this launch; the other one is re-armed for the next launch on this stream.
     int topLo = 0, nTop = 0, botLo = 0, nBot = 0;               // band-local row ranges pushed to the upper / lower neighbour
-    if (links.doneCounter != nullptr) {
+    if (BANDS && links.doneCounter != nullptr) {
         if (links.up.res != nullptr) { topLo = links.up.firstRow - bd.yOffset; nTop = links.up.lastRow - links.up.firstRow; }
         if (links.down.res != nullptr) { botLo = links.down.firstRow - bd.yOffset; nBot = links.down.lastRow - links.down.firstRow; }
         if (nTop > 0 && nBot > 0 && topLo + nTop > botLo) { nTop = 0; nBot = 0; }      // overlapping ranges (a very thin band): plain order
@@ -403,21 +455,23 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         }
         const int thisUnit = unit++;
         // row order: the rows whose pass-0 output goes to a neighbour's halo first (top range, bottom range), then the rest
-        int ly = thisUnit / unitsX;
+        int ly = unitsXMagic != 0u ? (int)__umulhi((uint32_t)thisUnit, unitsXMagic) : thisUnit / unitsX;
         const int x = (thisUnit - ly * unitsX) * 32 + lane;
-        if (ly < nTop) ly = topLo + ly;
-        else if (ly < nTop + nBot) ly = botLo + (ly - nTop);
-        else {
-            ly -= nTop + nBot;
-            if (nTop > 0 && ly >= topLo) ly += nTop;
-            if (nBot > 0 && ly >= botLo) ly += nBot;
+        if (BANDS) {
+            if (ly < nTop) ly = topLo + ly;
+            else if (ly < nTop + nBot) ly = botLo + (ly - nTop);
+            else {
+                ly -= nTop + nBot;
+                if (nTop > 0 && ly >= topLo) ly += nTop;
+                if (nBot > 0 && ly >= botLo) ly += nBot;
+            }
         }
         const int y = ly + bd.yOffset;
         do {
         // row bands: a warp that will store pass-0 rows into a neighbour's halo first waits until that neighbour has finished
         // the previous frame (its final pass read those halo rows)
-        bandWaitWarp(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
-                     links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
+        if (BANDS) bandWaitWarp(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
+                                links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
         if (x >= bd.W) continue;
         const size_t p = (size_t)ly * bd.W + x;
 
@@ -426,10 +480,10 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         PixelConsts px;
         px.normal = decodeNormal(__ldg(gNormal + p));
         guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
-        if (ly < bd.c0 || ly >= bd.c0 + bd.crows) continue;      // halo row of a band: only the guide plane is needed here
-        const float pcx = fadd((float)x, 0.5f), pcy = fadd((float)y, 0.5f);          // gl_FragCoord.xy
-        const float u = fdiv(pcx, (float)bd.W), v = fdiv(pcy, (float)bd.fullH);       // fsTexCoords
-        px.fragPos = worldPositionFromDepth(u, v, depth, invPV);
+        if (BANDS && (ly < bd.c0 || ly >= bd.c0 + bd.crows)) continue;      // halo row of a band: only the guide plane is needed here
+        const float pcx = fadd((float)x, 0.5f);                                      // gl_FragCoord.x
+        const float2 rowV = __ldg(tabs.row + ly);                                    // fsTexCoords.y and hash(gl_FragCoord.y) of this row
+        px.fragPos = worldPositionFromDepth(__ldg(tabs.u + x), rowV.x, depth, invPV);
         const f3 toView = viewPosition - px.fragPos;
         const float distToCamera = length(toView);
         const uint32_t alb = __ldg(gAlbedo + p);
@@ -447,7 +501,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         // draw k: rand = random(vec3(gl_FragCoord.xy, time + 10000 k)); the hash of the third component is the same for every
         // pixel and comes precomputed in fc.hashZ (common.glsl:199-214).  `--i; continue;` re-draws without consuming a sample,
         // at most 5 times per pixel; after that every draw is accepted.
-        const uint32_t seedXY = __float_as_uint(pcx) ^ hash1(__float_as_uint(pcy));
+        const uint32_t seedXY = __float_as_uint(pcx) ^ __float_as_uint(rowV.y);
         uint32_t q0 = 0u, q1 = 0u, q2 = 0u;          // accepted VPL positions, six 16-bit slots in sample order
         int accepted = 0, resamples = 0;
         #pragma unroll
@@ -478,7 +532,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             if (fc.usePerceptualRoughness) rr = rr * rr;
             rr = fmaxf(fmaxf(0.0f, fc.minRoughness), rr);
             px.r2 = rr * rr;
-            const float iv = rsqrtf(dotFast(toView, toView));
+            const float iv = rsqrtFast(dotFast(toView, toView));
             px.viewDir = mk3(toView.x * iv, toView.y * iv, toView.z * iv);
             px.NdotV = satFast(dotFast(px.normal, px.viewDir));
             px.ggxvTerm = sqrtFast(fma_(fma_(-px.r2, px.NdotV, px.NdotV), px.NdotV, px.r2));
@@ -487,7 +541,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             // diffuseColor / (diffuseDivisor + eps) / PI   and   f0 * specularMultiplier
             px.diffuseOverPi = mk3(om * baseColor.x * inv.x * (1.0f / PI_F), om * baseColor.y * inv.y * (1.0f / PI_F), om * baseColor.z * inv.z * (1.0f / PI_F));
             px.f0 = mk3(fma_(baseColor.x, metallic, f0s) * inv.x, fma_(baseColor.y, metallic, f0s) * inv.y, fma_(baseColor.z, metallic, f0s) * inv.z);
-            px.fogAo = __expf(-fc.fogDensity * distToCamera) * ambientOcclusion;
+            px.fogAo = expFast(-fc.fogDensity * distToCamera) * ambientOcclusion;
         }
 
         // ---- phase 2: shade the accepted VPLs in sample order (vpl_pbr_gi.fs:173-198) ----
@@ -499,10 +553,8 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             const float4 pr = sPos[lightIndex], cf = sCol[lightIndex], se = sSpec[lightIndex];
             const f3 lightPosition = mk3(pr.x, pr.y, pr.z);
             const f3 lightMinusFrag = lightPosition - px.fragPos;
-            const int eb = __float_as_int(se.w);
-            SgiAtlasEntry entry; entry.index = eb >> 16; entry.layer = eb & 0xffff;
             shadeAcceptedLight(px, lightPosition, lightMinusFrag, dotFast(lightMinusFrag, lightMinusFrag), pr.w, cf.w, mk3(cf.x, cf.y, cf.z), mk3(se.x, se.y, se.z),
-                               entry, shadowsOn, minGi, cubeRes, texelsPerLayer, atlases, vplColor, validSamples);
+                               __float_as_int(se.w), shadowsOn, minGi, cc, atlases, vplColor, validSamples);
         }
         validSamples = fmaxf(validSamples, 1.0f);
         const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
@@ -517,14 +569,17 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
             // Denoise pass 0 on the binary16 reservoir just stored.  mergeCentreTexel (sgi_merge.cuh) reduces to rgb / max(1e-5, a)
             // here: the normal is unit length, |z - z| = 0, and with a >= 1 and 1 <= V <= 4480 the single candidate's acceptance
             // ratio probability / cw is x / x = 1 exactly, which every draw in [0,1) passes.  V <= 0 leaves the reservoir empty.
-            const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha));
-            const f3 m = V > 0 ? mk3(h2f(hr), h2f(hg), h2f(hb)) / denom : mk3(0.0f);
-            const uint2 mv = packHalf4(m.x, m.y, m.z, 1.0f);
+            const float denom = vmax(PREVENT_DIV_BY_ZERO, h2f(ha)), invDenom = rcpFast(denom);
+            uint2 mv = make_uint2(0u, 0x3c000000u);                      // (0, 0, 0, 1)
+            if (V > 0) {
+                mv.x = (uint32_t)mergedChannel(h2f(hr), denom, invDenom) | ((uint32_t)mergedChannel(h2f(hg), denom, invDenom) << 16);
+                mv.y |= (uint32_t)mergedChannel(h2f(hb), denom, invDenom);
+            }
             mergedOut[p] = mv;
-            pushRes(links, y, x, bd.W, mv);
+            if (BANDS) pushRes(links, y, x, bd.W, mv);
         }
         } while (false);                                           // (`continue` above leaves the pixel, not the segment)
-        if (links.doneCounter != nullptr && pushesRow(links, y)) { // warp-uniform: this segment stored rows into a neighbour's halo
+        if (BANDS && links.doneCounter != nullptr && pushesRow(links, y)) { // warp-uniform: this segment stored rows into a neighbour's halo
             __syncwarp();
             if (lane == 0) producerDone(links);
         }
@@ -535,15 +590,32 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
 
 // CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
 // (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+using GatherFn = void (*)(const FrameConsts, BandDims, const float*, const uint32_t*, const uint32_t*, const uint16_t*, const uint32_t*, const unsigned short*,
+                          const SgiVplData*, const int32_t*, const SgiAtlasEntry*, const AtlasTable, uint2*, uint2*, float4*, uint2*, const BandLinks, int, int*, int,
+                          CoordTables, uint32_t);
+static GatherFn gatherFn(bool wide, bool bands) {
+    if (wide) return bands ? gatherStochasticKernel<1024, true> : gatherStochasticKernel<1024, false>;
+    return bands ? gatherStochasticKernel<512, true> : gatherStochasticKernel<512, false>;
+}
+
 bool preloadGatherKernels() {
     cudaFuncAttributes a; bool ok = true;
     ok = ok && cudaFuncGetAttributes(&a, gatherTileListKernel) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, coordTableKernel) == cudaSuccess;
     // the persistent kernel keeps the VPL table in dynamic shared memory: up to 4480 x 48 B = 210 KB of the SM's 227 KB
-    ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTableBytesTwoCtas) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(gatherStochasticKernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SGI_MAX_TOTAL_VPLS_PER_FRAME * kTableBytesPerVpl) == cudaSuccess;
-    ok = ok && cudaFuncGetAttributes(&a, gatherStochasticKernel<512>) == cudaSuccess;
-    ok = ok && cudaFuncGetAttributes(&a, gatherStochasticKernel<1024>) == cudaSuccess;
+    for (int wide = 0; wide < 2; ++wide) for (int bands = 0; bands < 2; ++bands) {
+        GatherFn f = gatherFn(wide != 0, bands != 0);
+        ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, wide ? SGI_MAX_TOTAL_VPLS_PER_FRAME * kTableBytesPerVpl : kTableBytesTwoCtas) == cudaSuccess;
+        ok = ok && cudaFuncGetAttributes(&a, f) == cudaSuccess;
+    }
     return ok;
+}
+
+// (x + 0.5) / W per column and ((y + 0.5) / fullH, hash(y + 0.5)) per held row: once per handle geometry (allocPlanes)
+int launchCoordTables(cudaStream_t stream, const BandDims& bd, float* u, float2* row) {
+    const int n = max(bd.W, bd.rows);
+    coordTableKernel<<<(n + 255) / 256, 256, 0, stream>>>(bd, u, row);
+    return 1;
 }
 
 static int smCount() {
@@ -561,7 +633,8 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  const uint32_t* albedo, const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao,
                  const SgiVplData* updated, const int32_t* visible, const SgiAtlasEntry* entries, const AtlasTable& atlases,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
-                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int64_t* persistentLaunches, bool* signalled) {
+                 const SgiVplStage2PerTileOutputs* tileLists, const unsigned short* tilePos, int* unitCounters, int64_t* persistentLaunches, bool* signalled,
+                 const float* coordU, const float2* coordRow) {
     if (signalled) *signalled = false;
     BandLinks plain = links;                 // the kernels without the in-kernel signal
     plain.doneCounter = nullptr;
@@ -591,15 +664,18 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
             if (armed.producers == 0) armed.doneCounter = nullptr;
             else if (signalled) *signalled = true;
         }
-        if (bytes <= kTableBytesTwoCtas) {
-            const int grid = max(1, min(2 * smCount(), (units + 15) / 16));
-            gatherStochasticKernel<512><<<dim3(grid), dim3(512), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                               colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
-        } else {
-            const int grid = max(1, min(smCount(), (units + 31) / 32));
-            gatherStochasticKernel<1024><<<dim3(grid), dim3(1024), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                               colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel);
-        }
+        const bool bands = bd.c0 != 0 || bd.crows != bd.rows || links.up.res != nullptr || links.down.res != nullptr || links.waitUp != nullptr ||
+                           links.waitDown != nullptr || links.doneCounter != nullptr;
+        const bool wide = bytes > kTableBytesTwoCtas;
+        const uint32_t unitsX = (uint32_t)((bd.W + 31) / 32);
+        // row of a unit = unit / unitsX as one multiply-high: exact while unit * unitsX < 2^32 (8K: 2.5e8)
+        const uint32_t magic = (unitsX > 1u && (uint64_t)units * unitsX < (1ull << 32)) ? (uint32_t)((1ull << 32) / unitsX) + 1u : 0u;
+        CoordTables tabs; tabs.u = coordU; tabs.row = coordRow;
+        const int threads = wide ? 1024 : 512;
+        const int grid = wide ? max(1, min(smCount(), (units + 31) / 32)) : max(1, min(2 * smCount(), (units + 15) / 16));
+        GatherFn kf = gatherFn(wide, bands);
+        kf<<<dim3(grid), dim3(threads), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
+                               colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel, tabs, magic);
     }
     return 1;
 }

@@ -34,7 +34,8 @@ static size_t pixels(const SgiHandle h) { return (size_t)h->cp.width * (size_t)h
 static BandDims bandDims(const SgiHandle h);
 
 static void freePlanes(SgiHandle h) {
-    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->temporal, &h->slab, (void**)&h->patchScratch, (void**)&h->tilePos};
+    void** ps[] = {&h->giColor, &h->giReservoir, &h->combined, &h->guide, &h->temporal, &h->slab, (void**)&h->patchScratch, (void**)&h->tilePos,
+                   (void**)&h->coordU, (void**)&h->coordRow};
     for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
     h->resA = h->resB = nullptr;
     h->giIllum[0] = h->giIllum[1] = h->history[0] = h->history[1] = nullptr;
@@ -74,6 +75,9 @@ static int allocPlanes(SgiHandle h) {
         const size_t tiles = (size_t)(h->cp.width / SGI_TILE_DIVISOR) * (size_t)(h->cp.rows / SGI_TILE_DIVISOR);
         SGI_CUDA(h, cudaMalloc((void**)&h->tilePos, (tiles > 0 ? tiles : 1) * SGI_MAX_VPLS_PER_TILE * sizeof(unsigned short)));
     }
+    SGI_CUDA(h, cudaMalloc((void**)&h->coordU, (size_t)h->cp.width * sizeof(float)));
+    SGI_CUDA(h, cudaMalloc((void**)&h->coordRow, (size_t)h->cp.rows * sizeof(float2)));
+    sgi::launchCoordTables(h->stream, bandDims(h), h->coordU, h->coordRow);
     h->guideValid = false;
     h->tileListsValid = false;
     h->temporalDone = false;
@@ -409,7 +413,7 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
                                fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
-                               h->gatherCounters, &h->gatherLaunches, &signalled);
+                               h->gatherCounters, &h->gatherLaunches, &signalled, h->coordU, h->coordRow);
     if (h->banded && fuse && !signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     SGI_CUDA(h, cudaEventRecord(h->evTablesFree, h->stream));      // the compacted tables and the atlases have been read (sgi_early_begin)
     h->tablesFreeRecorded = true;

@@ -246,6 +246,8 @@ struct SgiHandle_ {
     int prepassCap = 0;
     int* prepassInside = nullptr;   // lights inside the frustum (before the 10000 cap)
     int* gatherCounters = nullptr;  // two work counters of the persistent gather, used alternately (k_gather.cu)
+    float* coordU = nullptr;        // [width] (x + 0.5) / W, and [rows] ((y + 0.5) / fullH, hash(y + 0.5)): rebuilt with the planes
+    float2* coordRow = nullptr;
     int64_t gatherLaunches = 0;
     uint32_t* cullBallots = nullptr;
     unsigned int* cullTicket = nullptr;
@@ -298,7 +300,9 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
                  uint2* colorOut, uint2* reservoirOut, float4* guideOut, uint2* mergedOut, const BandLinks& links,
                  const SgiVplStage2PerTileOutputs* tileLists /* non-null: tile-list mode */, const unsigned short* tilePos,
                  int* unitCounters /* two ints: work counters of the persistent gather */, int64_t* persistentLaunches /* selects the counter */,
-                 bool* signalled /* out: the kernel releases the neighbours' flags itself */);
+                 bool* signalled /* out: the kernel releases the neighbours' flags itself */,
+                 const float* coordU, const float2* coordRow /* launchCoordTables */);
+int launchCoordTables(cudaStream_t stream, const BandDims& bd, float* u /* [W] */, float2* row /* [rows] */);   // k_gather.cu: per-column / per-row texture coordinates
 int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
 bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int* x0, int* x1, int* y0, int* y1);   // k_atrous_tma.cu
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);

@@ -96,8 +96,11 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
         if (st->kernelSignal) armInKernelSignal(&h, &links, bandEpoch(h.frameNo, 1));
     }
     bool signalled = false;
+    std::vector<float> coordU((size_t)bd.W);
+    std::vector<float2> coordRow((size_t)bd.rows);
+    launchCoordTables(nullptr, bd, coordU.data(), coordRow.data());
     launchGather(nullptr, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atl, st->giColor.data(), st->giReservoir.data(),
-                 st->guide.data(), (uint2*)h.resA, links, nullptr, nullptr, st->gatherCounters, &h.gatherLaunches, &signalled);
+                 st->guide.data(), (uint2*)h.resA, links, nullptr, nullptr, st->gatherCounters, &h.gatherLaunches, &signalled, coordU.data(), coordRow.data());
     if (h.banded && !signalled) signalNeighbours(&h, bandEpoch(h.frameNo, 1), false);
     // ---- sgi_denoise_pass 1 .. iters-1 (pass 0 was written by the gather) ----
     for (int pass = 1; pass < iters; ++pass) {

@@ -27,6 +27,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b,
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __saturatef(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
@@ -41,6 +42,8 @@ static inline void prefetchL2(const void*) {}
 static inline float lg2Fast(float x) { return std::log2(x); }                 // lg2.approx.ftz.f32
 static inline float ex2Fast(float x) { return std::exp2(x); }                 // ex2.approx.ftz.f32
 static inline float sqrtApprox(float x) { return std::sqrt(x); }              // sqrt.approx.ftz.f32 (k_tiles.cu; estimate tier only)
+static inline float rcpFast(float x) { return 1.0f / x; }                           // rcp.approx.ftz.f32 (k_gather.cu; radiance tier and margin estimates)
+static inline float rsqrtFast(float x) { return 1.0f / std::sqrt(x); }              // rsqrt.approx.ftz.f32
 static inline float sqrtFast(float x) { return std::sqrt(x); }                // sqrt.approx.ftz.f32 (k_gather.cu; radiance tier)
 static inline unsigned long long pack2(float lo, float hi) {                  // mov.b64 %0, {lo, hi}
     uint32_t a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4);

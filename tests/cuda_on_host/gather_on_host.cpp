@@ -23,6 +23,10 @@ extern "C" int host_gather(const SgiFrameParams* fp, int W, int H, int cubeRes, 
     int counters[2] = {0, 0};
     int64_t launches = 0;
     bool signalled = false;
+    std::vector<float> coordU((size_t)W);
+    std::vector<float2> coordRow((size_t)H);
+    sgi::launchCoordTables(nullptr, bd, coordU.data(), coordRow.data());
     return sgi::launchGather(nullptr, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atl, (uint2*)colorOutH4,
-                             (uint2*)reservoirOutH4, guide.data(), (uint2*)mergedOutH4, links, nullptr, nullptr, counters, &launches, &signalled);
+                             (uint2*)reservoirOutH4, guide.data(), (uint2*)mergedOutH4, links, nullptr, nullptr, counters, &launches, &signalled,
+                             coordU.data(), coordRow.data());
 }

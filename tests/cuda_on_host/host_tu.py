@@ -30,7 +30,7 @@ BUILD = os.path.join(HERE, "_build")
 HEADERS = ("sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", "sgi_denoise.cuh")
 
 # rule 2: helpers that the shim supplies (name -> only checked for presence, the definitions live in cuda_host_shim.h)
-PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys", "sqrtApprox", "sqrtFast")
+PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "rcpFast", "rsqrtFast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys", "sqrtApprox", "sqrtFast")
 
 _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<((?:(?!<<<|>>>).)*)>>>\s*\(", re.S)
 
