@@ -56,6 +56,7 @@ SGI_DEV float rcpFast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f
 SGI_DEV float rsqrtFast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 SGI_DEV float sqrtFast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr float kLog2e = 1.4426950408889634f;
 SGI_DEV float expFast(float x) { return ex2Fast(x * kLog2e); }
 SGI_DEV float dotFast(f3 a, f3 b) { return fma_(a.z, b.z, fma_(a.y, b.y, a.x * b.x)); }
@@ -169,19 +170,22 @@ SGI_DEV CubeConsts cubeConsts(int cubeRes) {
     return c;
 }
 
-// one accepted light: shadow test, occlusion floor, re-weighting and shading (vpl_pbr_gi.fs:173-198)
+// the shadow-map texel a fragment sees of one light (calculateShadowValue1Sample, pbr.glsl:116-136: the texel choice is a decision)
+SGI_DEV uint32_t loadShadowTexel(f3 fragPos, float4 posRadius, int entryBits /* atlas index << 16 | layer */, const CubeConsts& cc, const AtlasTable& atlases) {
+    const f3 fragDir = fragPos - mk3(posRadius.x, posRadius.y, posRadius.z);
+    const uint32_t offset = (uint32_t)(entryBits & 0xffff) * (uint32_t)cc.texelsPerLayer + (uint32_t)cubeTexelDecided(fragDir, cc.res, cc.halfRes, cc.epsK);
+    return __ldg(atlases.shadow[entryBits >> 16] + offset);
+}
+
+// one accepted light: shadow verdict on the texel loaded above, occlusion floor, re-weighting and shading (vpl_pbr_gi.fs:173-198)
 SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 lightMinusFrag, float d2, float lightRadius, float farPlane,
-                                f3 lightColor, f3 specularPosition, int entryBits /* atlas index << 16 | layer */, bool shadowsOn, float minGi,
-                                const CubeConsts& cc, const AtlasTable& atlases, f3& vplColor, float& validSamples) {
+                                f3 lightColor, f3 specularPosition, uint32_t texel, bool shadowsOn, float minGi, f3& vplColor, float& validSamples) {
     const float invRadius = rcpFast(lightRadius);
     const float distance = d2 * rsqrtFast(d2);
     const float distanceRatio = satFast(2.0f * distance * invRadius);
     float shadowFactor = 0.0f;
     if (shadowsOn) {
-        // calculateShadowValue1Sample (pbr.glsl:116-136), minBias 0.1: texel choice and the lit/shadowed verdict are decisions
-        const f3 fragDir = px.fragPos - lightPosition;
-        const uint32_t offset = (uint32_t)(entryBits & 0xffff) * (uint32_t)cc.texelsPerLayer + (uint32_t)cubeTexelDecided(fragDir, cc.res, cc.halfRes, cc.epsK);
-        const uint32_t texel = __ldg(atlases.shadow[entryBits >> 16] + offset);
+        // minBias 0.1; the lit / shadowed verdict is a decision
         const float texelDepthEst = (float)texel * (1.0f / 65535.0f);      // within an ulp of the exact unorm16 (margin below: 8e-5)
         const float lightNormalDot = dotFast(lightMinusFrag, px.normal);
         const float biasFactor = fmaxf(0.1f, satFast(lightNormalDot) * 0.03f);
@@ -190,7 +194,7 @@ SGI_DEV void shadeAcceptedLight(const PixelConsts& px, f3 lightPosition, f3 ligh
         // lightNormalDot only matters through saturate(.)*0.03 vs 0.1, i.e. when it exceeds 3.33: never borderline for the verdict's margin
         bool shadowed;
         if (fabsf(gap) > 8.0f * kMargin * fmaxf(lhs, rhs)) shadowed = gap > 0.0f;
-        else shadowed = exactShadowed(fragDir, dot(lightPosition - px.fragPos, px.normal), unorm16(texel), farPlane);
+        else shadowed = exactShadowed(px.fragPos - lightPosition, dot(lightPosition - px.fragPos, px.normal), unorm16(texel), farPlane);
         shadowFactor = shadowed ? 1.0f : 0.0f;
     }
     shadowFactor = fminf(shadowFactor, fma_(distanceRatio, 1.0f - minGi, minGi));
@@ -329,8 +333,9 @@ gatherTileListKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const 
             const float lightRadius = sl.posRadius.w;
             const float d2 = dotFast(lightMinusFrag, lightMinusFrag);
             if (behindOrOutOfRange(px.normal, lightMinusFrag, d2, lightRadius)) continue;
+            const uint32_t texel = shadowsOn ? loadShadowTexel(px.fragPos, sl.posRadius, __float_as_int(sl.specEntry.w), cc, atlases) : 0u;
             shadeAcceptedLight(px, lightPosition, lightMinusFrag, d2, lightRadius, sl.colorFar.w, mk3(sl.colorFar.x, sl.colorFar.y, sl.colorFar.z),
-                               mk3(sl.specEntry.x, sl.specEntry.y, sl.specEntry.z), __float_as_int(sl.specEntry.w), shadowsOn, minGi, cc, atlases, vplColor, validSamples);
+                               mk3(sl.specEntry.x, sl.specEntry.y, sl.specEntry.z), texel, shadowsOn, minGi, vplColor, validSamples);
         }
     }
     validSamples = fmaxf(validSamples, 1.0f);
@@ -444,19 +449,11 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     }
     int* __restrict__ counter = unitCounters + (counterSel & 1);
     if (blockIdx.x == 0 && threadIdx.x == 0) unitCounters[(counterSel & 1) ^ 1] = 0;
-    int unit = 0, unitEnd = 0;
-    while (true) {
-        if (unit >= unitEnd) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(counter, kUnitChunk);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= units) break;
-            unit = base; unitEnd = min(base + kUnitChunk, units);
-        }
-        const int thisUnit = unit++;
-        // row order: the rows whose pass-0 output goes to a neighbour's halo first (top range, bottom range), then the rest
-        int ly = unitsXMagic != 0u ? (int)__umulhi((uint32_t)thisUnit, unitsXMagic) : thisUnit / unitsX;
-        const int x = (thisUnit - ly * unitsX) * 32 + lane;
+    // unit -> (band-local row, first column).  Row order: the rows whose pass-0 output goes to a neighbour's halo first (top range,
+    // bottom range), then the rest
+    auto unitRow = [&](int u, int* ux) -> int {
+        int ly = unitsXMagic != 0u ? (int)__umulhi((uint32_t)u, unitsXMagic) : u / unitsX;
+        *ux = (u - ly * unitsX) * 32;
         if (BANDS) {
             if (ly < nTop) ly = topLo + ly;
             else if (ly < nTop + nBot) ly = botLo + (ly - nTop);
@@ -466,29 +463,65 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
                 if (nBot > 0 && ly >= botLo) ly += nBot;
             }
         }
+        return ly;
+    };
+    // The counter is read one chunk ahead (the atomic's round trip, ~700 cycles, is over before its value is needed), and while a
+    // unit is processed the G-buffer lines of the warp's next unit are on their way into L2.
+    int nextBase = 0;
+    if (lane == 0) nextBase = atomicAdd(counter, kUnitChunk);
+    int unit = 0, unitEnd = 0;
+    while (true) {
+        if (unit >= unitEnd) {
+            const int base = __shfl_sync(0xffffffffu, nextBase, 0);
+            if (base >= units) break;
+            if (lane == 0) nextBase = atomicAdd(counter, kUnitChunk);
+            unit = base; unitEnd = min(base + kUnitChunk, units);
+        }
+        const int thisUnit = unit++;
+        int ux;
+        const int ly = unitRow(thisUnit, &ux);
+        const int x = ux + lane;
         const int y = ly + bd.yOffset;
         do {
         // row bands: a warp that will store pass-0 rows into a neighbour's halo first waits until that neighbour has finished
         // the previous frame (its final pass read those halo rows)
         if (BANDS) bandWaitWarp(links, links.up.res != nullptr && y >= links.up.firstRow && y < links.up.lastRow,
                                 links.down.res != nullptr && y >= links.down.firstRow && y < links.down.lastRow);
+        const int nb = __shfl_sync(0xffffffffu, nextBase, 0);        // (the warp is converged here)
         if (x >= bd.W) continue;
         const size_t p = (size_t)ly * bd.W + x;
 
-        // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
+        // every G-buffer value of the pixel is requested before the first one is used (one exposed memory latency per unit instead
+        // of one per plane: the exact divisions below are calls on their slow path, which the compiler does not move loads across)
         const float depth = __ldg(gDepth + p);
+        const uint32_t nrm = __ldg(gNormal + p);
+        const uint32_t alb = __ldg(gAlbedo + p);
+        const uint32_t rma = __ldg(gRma + p);
+        const uint32_t aoBits = __ldg(ssao + p), reflBits = __ldg(gRefl + p);
+        const float2 rowV = __ldg(tabs.row + ly);                                    // fsTexCoords.y and hash(gl_FragCoord.y) of this row
+        const float texU = __ldg(tabs.u + x);
+        if (unit < unitEnd) {                      // the chunk's next unit: the next 32 pixels of the row-major planes (W % 32 == 0), else close by
+            const size_t pn = p + 32;
+            prefetchL2(gDepth + pn); prefetchL2(gNormal + pn); prefetchL2(gAlbedo + pn); prefetchL2(gRma + pn); prefetchL2(ssao + pn); prefetchL2(gRefl + pn);
+        } else {
+            if (nb < units) {
+                int nx;
+                const int nly = unitRow(nb, &nx);
+                const size_t pn = (size_t)nly * bd.W + min(nx + lane, bd.W - 1);
+                prefetchL2(gDepth + pn); prefetchL2(gNormal + pn); prefetchL2(gAlbedo + pn); prefetchL2(gRma + pn); prefetchL2(ssao + pn); prefetchL2(gRefl + pn);
+            }
+        }
+
+        // ---- per-pixel set-up: exact (feeds the sample budget, the 500-unit shadow cut-off and every re-draw test) ----
         PixelConsts px;
-        px.normal = decodeNormal(__ldg(gNormal + p));
+        px.normal = decodeNormal(nrm);
         guideOut[p] = make_float4(px.normal.x, px.normal.y, px.normal.z, depth);
         if (BANDS && (ly < bd.c0 || ly >= bd.c0 + bd.crows)) continue;      // halo row of a band: only the guide plane is needed here
         const float pcx = fadd((float)x, 0.5f);                                      // gl_FragCoord.x
-        const float2 rowV = __ldg(tabs.row + ly);                                    // fsTexCoords.y and hash(gl_FragCoord.y) of this row
-        px.fragPos = worldPositionFromDepth(__ldg(tabs.u + x), rowV.x, depth, invPV);
+        px.fragPos = worldPositionFromDepth(texU, rowV.x, depth, invPV);
         const f3 toView = viewPosition - px.fragPos;
         const float distToCamera = length(toView);
-        const uint32_t alb = __ldg(gAlbedo + p);
         const f3 baseColor = mk3(vmax(unorm8(alb & 0xffu), 0.01f), vmax(unorm8((alb >> 8) & 0xffu), 0.01f), vmax(unorm8((alb >> 16) & 0xffu), 0.01f));
-        const uint32_t rma = __ldg(gRma + p);
         const float roughness = vmax(0.5f, unorm8(rma & 0xffu));
         const float roughnessWeight = fsub(1.0f, roughness);
         const float distRatioToCamera = vmin(fsub(1.0f, fdiv(distToCamera, 1000.0f)), 1.0f);
@@ -526,8 +559,8 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         // ---- per-pixel set-up: radiance tier (BRDF_Base pbr2.glsl:146-168 and everything light-independent) ----
         {
             const float metallic = unorm8((rma >> 8) & 0xffu);
-            const float ambientOcclusion = vclamp(h2f(__ldg(ssao + p)), 0.35f, 1.0f);
-            const float refl = unorm8((uint32_t)__ldg(gRefl + p) & 0xffu);
+            const float ambientOcclusion = vclamp(h2f((unsigned short)aoBits), 0.35f, 1.0f);
+            const float refl = unorm8(reflBits & 0xffu);
             float rr = roughness;
             if (fc.usePerceptualRoughness) rr = rr * rr;
             rr = fmaxf(fmaxf(0.0f, fc.minRoughness), rr);
@@ -545,16 +578,22 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         }
 
         // ---- phase 2: shade the accepted VPLs in sample order (vpl_pbr_gi.fs:173-198) ----
+        // The shadow-map texel of sample s + 1 is requested before sample s is shaded: its latency (an L2 hit at best: the maps of
+        // ~1000 visible VPLs do not fit the L1 left next to the table) passes under ~150 instructions of shading.
         f3 vplColor = mk3(0.0f);
         float validSamples = 0.0f;
+        auto sampleIndex = [&](int s) -> int { return (int)(((s < 2 ? q0 : (s < 4 ? q1 : q2)) >> ((s & 1) * 16)) & 0xffffu); };
+        uint32_t texelNext = 0u;
+        if (shadowsOn && accepted > 0) { const int i0 = sampleIndex(0); texelNext = loadShadowTexel(px.fragPos, sPos[i0], __float_as_int(sSpec[i0].w), cc, atlases); }
         for (int s = 0; s < accepted; ++s) {
-            const uint32_t qw = s < 2 ? q0 : (s < 4 ? q1 : q2);
-            const int lightIndex = (int)((qw >> ((s & 1) * 16)) & 0xffffu);
+            const int lightIndex = sampleIndex(s);
+            const uint32_t texel = texelNext;
+            if (shadowsOn && s + 1 < accepted) { const int i1 = sampleIndex(s + 1); texelNext = loadShadowTexel(px.fragPos, sPos[i1], __float_as_int(sSpec[i1].w), cc, atlases); }
             const float4 pr = sPos[lightIndex], cf = sCol[lightIndex], se = sSpec[lightIndex];
             const f3 lightPosition = mk3(pr.x, pr.y, pr.z);
             const f3 lightMinusFrag = lightPosition - px.fragPos;
             shadeAcceptedLight(px, lightPosition, lightMinusFrag, dotFast(lightMinusFrag, lightMinusFrag), pr.w, cf.w, mk3(cf.x, cf.y, cf.z), mk3(se.x, se.y, se.z),
-                               __float_as_int(se.w), shadowsOn, minGi, cc, atlases, vplColor, validSamples);
+                               texel, shadowsOn, minGi, vplColor, validSamples);
         }
         validSamples = fmaxf(validSamples, 1.0f);
         const f3 color = baseColor + PREVENT_DIV_BY_ZERO;
