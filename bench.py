@@ -318,7 +318,7 @@ def run_reference(args, rank):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from stratusgfx_b200.bands import (APRON, balance_cuts, bands_from_cuts, broadcast_frame_inputs, connect_bands, gather_bands, halo_rows,
+    from stratusgfx_b200.bands import (APRON, balance_cuts, bands_from_cuts, broadcast_frame_inputs, connect_bands, gather_bands, halo_rows, recompute_rows,
                                        plan_bands)
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
@@ -330,8 +330,9 @@ def run_ours(args, rank, world, local_rank):
         set_host_threads(world)
     scene = Scene(args.workload)
     W, H, N, iters = scene.width, scene.height, scene.num_vpls, scene.denoise_iters
-    p2p = world > 1 and args.bands == "p2p"
-    halo = halo_rows(iters)
+    p2p = world > 1 and args.bands in ("p2p", "recompute")
+    recompute = world > 1 and args.bands == "recompute"      # SGI_HALO_RECOMPUTE: no exchange inside the frame (include/stratusgi.h)
+    halo = recompute_rows(iters) if recompute else halo_rows(iters)
     isolated = world > 1 and args.bands == "isolated"     # diagnosis: band geometry and halo rows, but no neighbour attached (wrong seams)
     apron = halo if (p2p or isolated) else APRON
     bands = plan_bands(H, world, apron)
@@ -405,7 +406,7 @@ def run_ours(args, rank, world, local_rank):
         refreshed_idx = torch.tensor(refreshed, dtype=torch.int64, device=dev)
         gp.bind()
         if p2p:
-            connect_bands(dist, gp, me, world)           # band_setup + CUDA IPC attach of the neighbours and of rank 0's frame image
+            connect_bands(dist, gp, me, world, halo_mode=1 if recompute else 0)           # band_setup + CUDA IPC attach of the neighbours and of rank 0's frame image
         elif isolated:
             gp.band_setup(me.b0, me.b1 - me.b0, me.rank, world, owns_frame_image=False)
         else:
@@ -677,7 +678,7 @@ def run_ours(args, rank, world, local_rank):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
                            "parallelism": "single GPU" if world == 1 else (
-                               f"{world} row bands of {band} rows + {halo}-row halos filled by the neighbours' kernels through NVLink peer stores (CUDA IPC), one NCCL broadcast of the VPL table{'' if device_maps else ' + 5 cube maps'} per frame ({'issued one frame ahead' if (prefetch or use_early) else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
+                               f"{world} row bands of {band} rows + {halo}-row halos " + ("on which the band recomputes the gather and the non-final passes itself (28/24/16 rows; only the final pass's GI rows travel, NVLink peer stores)" if recompute else "filled by the neighbours' kernels through NVLink peer stores (CUDA IPC)") + f", one NCCL broadcast of the VPL table{'' if device_maps else ' + 5 cube maps'} per frame ({'issued one frame ahead' if (prefetch or use_early) else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
                                f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
                            "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
                            "look_ahead": ("cull + colouring" + (" + table broadcast" if world > 1 else "") + " + cube-map refresh of frame i+1 on a second stream under frame i's denoise passes (sgi_early_begin / sgi_cull_early; the reference culls at BE:1395, long before the GI pass at BE:2043)") if use_early else "off: everything on one stream",
@@ -800,7 +801,7 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
     ap.add_argument("--no-image-check", action="store_true", help="N > 1: skip the byte comparison of the assembled image with a single-GPU replay")
     ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")
-    ap.add_argument("--bands", default="p2p", choices=["p2p", "apron", "isolated"], help="multi-GPU halo strategy (N > 1); `isolated` = band handles without neighbours, a timing diagnosis whose seams are wrong")
+    ap.add_argument("--bands", default="p2p", choices=["p2p", "recompute", "apron", "isolated"], help="multi-GPU halo strategy (N > 1); `isolated` = band handles without neighbours, a timing diagnosis whose seams are wrong")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

@@ -259,7 +259,18 @@ typedef struct SgiBandParams {
     int32_t rank;              /* band index, 0 = top                                                        */
     int32_t world;             /* number of bands                                                            */
     int32_t owns_frame_image;  /* 1: allocate the full_height x width half4 frame images bands store into    */
+    int32_t halo_mode;         /* SGI_HALO_EXCHANGE or SGI_HALO_RECOMPUTE (below); the same on every band    */
 } SgiBandParams;
+/* How a band gets the reservoir rows its à-trous taps read beyond its own rows.
+ *   SGI_HALO_EXCHANGE:  the neighbours' kernels store the boundary rows of EVERY pass into this handle's halo rows (one exchange
+ *                       and one pair of flags per pass: three per frame with four denoise passes).
+ *   SGI_HALO_RECOMPUTE: the band computes the gather and the non-final passes on as many of its halo rows as the later passes
+ *                       will read — pass p on the computed rows +- sum_{j>p} 2^(j+1) rows (28, 24, 16, 0 with four passes) — from the
+ *                       G-buffer halo rows the caller supplies anyway.  Same arithmetic on the same inputs as the neighbour, so the
+ *                       same bytes; +10 % work on a 270-row band and no exchange or wait inside the frame.  Only the final pass's GI
+ *                       rows (next frame's reprojection) and the lit rows (frame image) still travel.  Needs
+ *                       2^(denoise_iters+1) - 4 held rows beyond every inner edge (28 -> 30 on the tile grid). */
+enum { SGI_HALO_EXCHANGE = 0, SGI_HALO_RECOMPUTE = 1 };
 
 typedef struct SgiPeerInfo {   /* plain data; exchanged between band processes (e.g. all_gather) */
     uint8_t  mem_handle[64];   /* cudaIpcMemHandle_t of the handle's shared slab                             */

@@ -122,7 +122,10 @@ PEER_UP, PEER_DOWN, PEER_ROOT = 0, 1, 2
 
 class BandParams(C.Structure):
     _fields_ = [("compute_y0", C.c_int32), ("compute_rows", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("owns_frame_image", C.c_int32)]
+                ("owns_frame_image", C.c_int32), ("halo_mode", C.c_int32)]
+
+
+HALO_EXCHANGE, HALO_RECOMPUTE = 0, 1      # SgiBandParams.halo_mode
 
 
 class PeerInfo(C.Structure):

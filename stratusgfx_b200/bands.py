@@ -10,7 +10,10 @@ One process per GPU (torch.distributed; NCCL on the GPU box, gloo in the CPU tes
        peer-to-peer (default): the band holds halo_rows() extra rows per inner edge; the neighbours' kernels store
          their boundary rows of every pass straight into them over NVLink (csrc/sgi_band.cu), ordered by epoch flags;
          the final pass also stores the lit rows into rank 0's frame image, so there is no separate gather;
-       apron (comparison): the band holds APRON = 30 extra rows and recomputes them redundantly (reach 4 + 8 + 16 = 28),
+       recompute (SGI_HALO_RECOMPUTE): the band holds recompute_rows() extra rows per inner edge and computes the gather and the
+         non-final passes on as many of them as its later passes read (28 / 24 / 16 rows): same bytes, no exchange inside the
+         frame; only the final pass's GI rows (next frame's reprojection) and the lit rows travel;
+       apron (comparison): the band holds APRON = 30 extra rows and recomputes ALL passes on them redundantly (reach 4 + 8 + 16 = 28),
          no exchange, then
   3. (apron mode only) the lit bands are gathered to rank 0 with NCCL.
 
@@ -46,6 +49,13 @@ def halo_rows(denoise_iters):
     """Rows a band must hold beyond its own for ONE à-trous pass of the widest spacing: 2*(multiplier+1) with
     multiplier = 2^i - 1 (StratusRendererBackend.cpp:1920), rounded up to the tile grid.  4 iterations -> 16 -> 20."""
     reach = 2 * (1 << max(denoise_iters - 1, 0)) if denoise_iters > 1 else 0
+    return (reach + TILE - 1) // TILE * TILE
+
+
+def recompute_rows(denoise_iters):
+    """Rows a band must hold beyond its own in SGI_HALO_RECOMPUTE mode: the summed reach of all à-trous passes,
+    2^(iters+1) - 4 (4 + 8 + 16 = 28 for 4 iterations), rounded up to the tile grid -> 30."""
+    reach = (1 << (denoise_iters + 1)) - 4 if denoise_iters > 1 else 0
     return (reach + TILE - 1) // TILE * TILE
 
 
@@ -112,12 +122,12 @@ def balance_cuts(bands, times, height, min_rows):
     return cuts
 
 
-def connect_bands(dist, gp, band, world, root=0):
+def connect_bands(dist, gp, band, world, root=0, halo_mode=0):
     """Peer-to-peer mode: band_setup on this rank's pass, all-gather the peer descriptors (plain bytes), attach the
     neighbours and the frame-image owner.  Works with NCCL (GPU box) and gloo (tests) alike: only host bytes travel."""
     import torch
     from ._abi import PEER_DOWN, PEER_ROOT, PEER_UP, PeerInfo
-    gp.band_setup(band.b0, band.b1 - band.b0, band.rank, world, owns_frame_image=(band.rank == root))
+    gp.band_setup(band.b0, band.b1 - band.b0, band.rank, world, owns_frame_image=(band.rank == root), halo_mode=halo_mode)
     mine = gp.band_export()
     raw = bytes(mine)
     infos = [None] * world

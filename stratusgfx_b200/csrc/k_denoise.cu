@@ -359,7 +359,7 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
 #ifdef __CUDACC__                        // (the host-emulation builds of tests/cuda_on_host have no TMA: they run atrousKernel on everything)
-        if (io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr && io.links.waitDown == nullptr &&
+        if (!pushTarget(io.links.up) && !pushTarget(io.links.down) && io.links.waitUp == nullptr && io.links.waitDown == nullptr &&
             io.links.image == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
             // whole-frame handles: the interior through the TMA-staged kernel (taps from shared memory: 0.150 -> 0.122 ms per pass on
             // c4, same bytes; profiles/r02i), the frame's border (CLAMP_TO_EDGE taps) through the kernel below on a compact CTA list

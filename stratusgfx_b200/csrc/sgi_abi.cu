@@ -110,6 +110,21 @@ static BandDims bandDims(const SgiHandle h) {
     return bd;
 }
 
+// SGI_HALO_RECOMPUTE (include/stratusgi.h): pass `pass` of a band is computed on its own rows plus the rows the LATER passes of
+// this band will read beyond them, sum_{j > pass} 2^(j+1), clipped to the held rows (a band at the frame's edge holds none there)
+static bool recomputesHalo(const SgiHandle h) { return h->banded && h->band.halo_mode == SGI_HALO_RECOMPUTE; }
+static BandDims bandDimsForPass(const SgiHandle h, int pass) {
+    BandDims bd = bandDims(h);
+    if (!recomputesHalo(h)) return bd;
+    int ext = 0;
+    for (int j = pass + 1; j < h->cp.denoise_iters; ++j) ext += 2 << j;
+    const int up = ext < bd.c0 ? ext : bd.c0;
+    const int below = bd.rows - (bd.c0 + bd.crows);
+    const int down = ext < below ? ext : below;
+    bd.c0 -= up; bd.crows += up + down;
+    return bd;
+}
+
 static AtlasTable atlasTable(const SgiHandle h) {
     AtlasTable t;
     for (int i = 0; i < SGI_MAX_TOTAL_SHADOW_ATLASES; ++i) {
@@ -402,19 +417,23 @@ int sgi_gather(SgiHandle h, const SgiFrameParams* fp) {
         ++h->frameNo;
         h->gatherDoneThisFrame = true;
         const int prevDone = h->frameNo > 1 ? sgi::bandEpoch(h->frameNo - 1, h->cp.denoise_iters) : 0;
-        if (fuse) {
+        if (recomputesHalo(h)) {
+            // nothing of this band's gather or non-final passes leaves the GPU, so there is nothing to wait for here: the
+            // neighbours' "previous frame complete" flag is awaited by the temporal pre-pass, which the final pass (the only
+            // kernel that stores into a neighbour: its GI rows) is ordered after
+        } else if (fuse) {
             links = sgi::bandLinks(h, 0, false, prevDone);               // the CTAs that push wait inside the kernel
             sgi::armInKernelSignal(h, &links, sgi::bandEpoch(h->frameNo, 1));
         } else if (prevDone) n += sgi::waitNeighbours(h, prevDone);
     }
     bool signalled = false;
-    n += launchGather(h->stream, fc, bandDims(h), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
+    n += launchGather(h->stream, fc, bandDimsForPass(h, 0), (const float*)h->buf.depth, (const uint32_t*)h->buf.normal, (const uint32_t*)h->buf.albedo,
                                (const uint16_t*)h->buf.baseReflectivity, (const uint32_t*)h->buf.roughnessMetallicAmbient,
                                (const unsigned short*)h->buf.ssao, h->buf.vplUpdatedData, h->buf.vplVisibleIndices, h->buf.shadowDiffuseIndices,
                                atlasTable(h), (uint2*)h->giColor, (uint2*)h->giReservoir, (float4*)h->guide,
                                fuse ? (uint2*)h->resA : nullptr, links, tileMode ? h->buf.vplVisiblePerTile : nullptr, h->tilePos,
                                h->gatherCounters, &h->gatherLaunches, &signalled, h->coordU, h->coordRow);
-    if (h->banded && fuse && !signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
+    if (h->banded && fuse && !signalled && !recomputesHalo(h)) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, 1), false);
     SGI_CUDA(h, cudaEventRecord(h->evTablesFree, h->stream));      // the compacted tables and the atlases have been read (sgi_early_begin)
     h->tablesFreeRecorded = true;
     h->guideValid = true;
@@ -498,7 +517,15 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
         n += launchPrepareGuide(h->stream, bandDims(h), (const uint32_t*)h->buf.normal, (const float*)h->buf.depth, (float4*)h->guide);
         h->guideValid = true;
     }
-    if (h->banded) {
+    const bool recompute = recomputesHalo(h);
+    if (h->banded && recompute) {
+        // the halo rows this pass reads were computed by this band's previous pass; only the final pass stores into the
+        // neighbours (GI rows of the next frame's reprojection) and releases their "frame complete" flags
+        if (final_) {
+            io.links = sgi::bandLinks(h, pass % 2, true, 0);
+            sgi::armInKernelSignal(h, &io.links, sgi::bandEpoch(h->frameNo, pass + 1));
+        }
+    } else if (h->banded) {
         // pass p reads the neighbours' pass p-1 rows from this handle's halo: wait (in stream order) for their flags
         // (inside the kernel, by the CTAs whose taps reach the halo; interior CTAs start at once)
         io.links = sgi::bandLinks(h, pass % 2, final_, pass >= 1 ? sgi::bandEpoch(h->frameNo, pass) : 0);
@@ -513,11 +540,12 @@ int sgi_denoise_pass(SgiHandle h, const SgiFrameParams* fp, int32_t pass) {
     const bool copyOut = h->banded && final_ && !h->band.owns_frame_image && h->peer[SGI_PEER_ROOT].attached &&
                          h->peer[SGI_PEER_ROOT].info.off_image[(int)(h->frameNo & 1)] >= 0;
     if (copyOut && h->copyPending) SGI_CUDA(h, cudaStreamWaitEvent(h->stream, h->evCopyDone, 0));   // the previous frame's rows have left `combined`
-    n += launchDenoisePass(h->stream, fc, bandDims(h), io, merge, final_, &signalled);
+    n += launchDenoisePass(h->stream, fc, bandDimsForPass(h, pass), io, merge, final_, &signalled);
     if (merge) SGI_CUDA(h, cudaEventRecord(h->evTablesFree, h->stream));      // an unfused pass 0 reads the visible count after the gather
     if (h->banded) {
         // the pass's boundary CTAs released the neighbours' flags themselves; otherwise a one-thread kernel does it after the pass
-        if (!signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
+        if (recompute && !final_) {}             // nobody waits for a non-final pass of a band that recomputes its halo
+        else if (!signalled) n += sgi::signalNeighbours(h, sgi::bandEpoch(h->frameNo, pass + 1), final_);
         else if (final_) n += sgi::signalOwnerRowsDone(h);
         if (copyOut) {
             // the band's lit rows -> the owner's frame image of this parity, by the copy engine, then this band's flag in the

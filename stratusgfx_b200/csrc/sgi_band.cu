@@ -95,7 +95,8 @@ BandLinks bandLinks(SgiHandle_* h, int resIndex, bool final_, int waitEpoch) {
         if (!p.attached) continue;
         PushTarget& t = which == SGI_PEER_UP ? L.up : L.down;
         const SgiPeerInfo& pi = p.info;
-        t.res = (uint2*)(p.base + pi.off_res[resIndex]);
+        // SGI_HALO_RECOMPUTE: no reservoir rows travel (only the final pass has links at all, for its GI rows)
+        t.res = h->band.halo_mode == SGI_HALO_RECOMPUTE ? nullptr : (uint2*)(p.base + pi.off_res[resIndex]);
         if (final_) t.gi = (uint2*)(p.base + pi.off_gi[h->cur]);
         t.yOffset = pi.y_offset;
         // the neighbour's halo on my side: its held rows minus its computed rows, intersected with the rows I compute
@@ -206,6 +207,13 @@ int sgi_band_setup(SgiHandle h, const SgiBandParams* bp) {
         const int top = bp->compute_y0 - y0, bottom = y1 - (bp->compute_y0 + bp->compute_rows);
         if ((bp->rank > 0 && top < reach) || (bp->rank + 1 < bp->world && bottom < reach)) {
             h->lastError = "sgi_band_setup: an inner edge holds fewer halo rows than the à-trous reach 2^denoise_iters (SGI_HALO_ROWS covers 4 iterations)";
+            return SGI_ERR_INVALID_ARG;
+        }
+        if (bp->halo_mode != SGI_HALO_EXCHANGE && bp->halo_mode != SGI_HALO_RECOMPUTE) { h->lastError = "sgi_band_setup: unknown halo_mode"; return SGI_ERR_INVALID_ARG; }
+        // SGI_HALO_RECOMPUTE: pass 0 is recomputed on the reach of ALL later passes, sum_{p>=1} 2^(p+1) = 2^(iters+1) - 4 rows
+        const int recompute = iters > 1 ? (1 << (iters + 1)) - 4 : 0;
+        if (bp->halo_mode == SGI_HALO_RECOMPUTE && ((bp->rank > 0 && top < recompute) || (bp->rank + 1 < bp->world && bottom < recompute))) {
+            h->lastError = "sgi_band_setup: SGI_HALO_RECOMPUTE needs 2^(denoise_iters+1) - 4 held rows beyond every inner edge (28 for 4 iterations)";
             return SGI_ERR_INVALID_ARG;
         }
     }

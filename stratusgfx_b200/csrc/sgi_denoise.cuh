@@ -16,7 +16,7 @@ SGI_DEV float ex2Fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f
 
 __host__ __device__ inline bool slabPushes(const BandLinks& L, int lo, int hi, int yOffset) {      // band-local rows [lo, hi)
     const int a = lo + yOffset, b = hi + yOffset;
-    return (L.up.res != nullptr && a < L.up.lastRow && b > L.up.firstRow) || (L.down.res != nullptr && a < L.down.lastRow && b > L.down.firstRow);
+    return (pushTarget(L.up) && a < L.up.lastRow && b > L.up.firstRow) || (pushTarget(L.down) && a < L.down.lastRow && b > L.down.firstRow);
 }
 // CTA rows in launch order when the kernel signals its neighbours itself: the first, the last and the second-last row of the grid
 // (the ones that hold the band's boundary rows) before the interior

@@ -135,8 +135,9 @@ __device__ __forceinline__ void producerDone(const BandLinks& L) {
         if (L.sigDown != nullptr) stReleaseSys(L.sigDown, L.sigEpoch);
     }
 }
+__host__ __device__ inline bool pushTarget(const PushTarget& t) { return t.res != nullptr || t.gi != nullptr; }      // something of mine goes there
 __device__ __forceinline__ bool pushesRow(const BandLinks& L, int y) {      // frame row y is stored into a neighbour's halo
-    return (L.up.res != nullptr && y >= L.up.firstRow && y < L.up.lastRow) || (L.down.res != nullptr && y >= L.down.firstRow && y < L.down.lastRow);
+    return (pushTarget(L.up) && y >= L.up.firstRow && y < L.up.lastRow) || (pushTarget(L.down) && y >= L.down.firstRow && y < L.down.lastRow);
 }
 // store a band's boundary pixel into the neighbours' halo rows (plain st.global on peer-mapped pointers: NVLink writes)
 __device__ __forceinline__ void pushRes(const BandLinks& L, int y, int x, int W, uint2 v) {

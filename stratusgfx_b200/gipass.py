@@ -323,8 +323,8 @@ class VplGiPass:
     def reset_history(self): self._check(self.L.sgi_reset_history(self._h))
 
     # ---- row bands with peer-to-peer halos (include/stratusgi.h "multi-GPU row bands") -------------------------
-    def band_setup(self, compute_y0, compute_rows, rank, world, owns_frame_image=False):
-        bp = BandParams(compute_y0, compute_rows, rank, world, 1 if owns_frame_image else 0)
+    def band_setup(self, compute_y0, compute_rows, rank, world, owns_frame_image=False, halo_mode=0):
+        bp = BandParams(compute_y0, compute_rows, rank, world, 1 if owns_frame_image else 0, int(halo_mode))
         self._check(self.L.sgi_band_setup(self._h, C.byref(bp)))
         self.band = bp
 

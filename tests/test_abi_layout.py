@@ -40,7 +40,7 @@ def test_ctypes_layout_matches_header(tmp_path):
         "SgiPrepassParams": (_abi.PrepassParams, ["viewPosition", "numLights", "frustumPlanes", "lights", "vplDataOut", "atlasEntryOut",
                                                   "orderOut", "countOut"]),
         "SgiVplData": (_abi.VplData, ["color", "specularPosition", "radius", "intensity"]),
-        "SgiBandParams": (_abi.BandParams, ["compute_y0", "compute_rows", "rank", "world", "owns_frame_image"]),
+        "SgiBandParams": (_abi.BandParams, ["compute_y0", "compute_rows", "rank", "world", "owns_frame_image", "halo_mode"]),
         "SgiPeerInfo": (_abi.PeerInfo, ["mem_handle", "local_base", "off_res", "off_gi", "off_hist", "off_flags", "off_image",
                                         "y_offset", "rows", "compute_y0", "compute_rows", "rank", "device", "pid"]),
     }

@@ -99,22 +99,24 @@ def test_denoise_iteration_count_on_the_host(tiny, iters):
         G.test_denoise_iteration_count_is_a_parameter(tiny, iters)
 
 
-def test_p2p_bands_through_the_abi_with_a_middle_band(built):
+@pytest.mark.parametrize("halo_mode", [0, 1], ids=["exchange", "recompute"])
+def test_p2p_bands_through_the_abi_with_a_middle_band(built, halo_mode):
     """sgi_band_setup / export / attach (same-process peers), the band branches of sgi_gather and sgi_denoise_pass, the image
     transfer into band 0 and sgi_frame_image, on 3 bands over two frames of a turning camera.  A host launch is synchronous, so
     the bands advance stage by stage (every in-kernel wait is already satisfied when it is reached); on a GPU the same calls run
     concurrently on one stream per band (tests/test_parity_gpu.py::test_p2p_row_bands_reproduce_the_whole_frame)."""
     from stratusgfx_b200._abi import PEER_DOWN, PEER_ROOT, PEER_UP
-    from stratusgfx_b200.bands import bands_from_cuts, halo_rows
+    from stratusgfx_b200.bands import bands_from_cuts, halo_rows, recompute_rows
     from tests.parity_util import SceneData, band_of, make_pass, run_cuda_staged
     d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.5, height=180)
     iters = d.scene.denoise_iters
     with gpu_tests_on_the_host():
         whole = run_cuda_staged(d)
-        bands = bands_from_cuts([0, 60, 120, 180], d.H, halo_rows(iters))
+        # halo_mode 1 = SGI_HALO_RECOMPUTE: the bands compute the non-final passes on their halo rows themselves (28 / 24 / 16 rows)
+        bands = bands_from_cuts([0, 60, 120, 180], d.H, (recompute_rows if halo_mode else halo_rows)(iters))
         gps = [make_pass(d, b.y0, b.rows) for b in bands]
         for gp, b in zip(gps, bands):
-            gp.band_setup(b.b0, b.b1 - b.b0, b.rank, 3, owns_frame_image=(b.rank == 0))
+            gp.band_setup(b.b0, b.b1 - b.b0, b.rank, 3, owns_frame_image=(b.rank == 0), halo_mode=halo_mode)
         infos = [gp.band_export() for gp in gps]
         for gp, b in zip(gps, bands):
             if b.rank > 0: gp.band_attach(PEER_UP, infos[b.rank - 1])

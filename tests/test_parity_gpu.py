@@ -193,14 +193,14 @@ def test_row_bands_with_apron_reproduce_the_whole_frame(built):
         gp.close()
 
 
-def _run_p2p_bands_in_one_process(d, world, frames):
+def _run_p2p_bands_in_one_process(d, world, frames, halo_mode=0):
     """`world` band handles on one GPU in one process, linked through sgi_band_attach (same-process peer pointers)."""
-    from stratusgfx_b200.bands import halo_rows, plan_bands
+    from stratusgfx_b200.bands import halo_rows, plan_bands, recompute_rows
     from stratusgfx_b200._abi import PEER_DOWN, PEER_ROOT, PEER_UP
-    bands = plan_bands(d.H, world, halo_rows(d.scene.denoise_iters))
+    bands = plan_bands(d.H, world, (recompute_rows if halo_mode else halo_rows)(d.scene.denoise_iters))
     gps = [make_pass(d, b.y0, b.rows) for b in bands]
     for gp, b in zip(gps, bands):
-        gp.band_setup(b.b0, b.b1 - b.b0, b.rank, world, owns_frame_image=(b.rank == 0))
+        gp.band_setup(b.b0, b.b1 - b.b0, b.rank, world, owns_frame_image=(b.rank == 0), halo_mode=halo_mode)
     infos = [gp.band_export() for gp in gps]
     for gp, b in zip(gps, bands):
         if b.rank > 0: gp.band_attach(PEER_UP, infos[b.rank - 1])
@@ -238,6 +238,41 @@ def test_p2p_row_bands_reproduce_the_whole_frame(built, world):
     for b, t in zip(bands, tiles):          # tile lists of the band's own tile rows
         r0, r1 = (b.b0 - b.y0) // 5, (b.b1 - b.y0) // 5
         assert np.array_equal(t[r0 * tx:r1 * tx], whole[2]["stage2"][b.b0 // 5 * tx:b.b1 // 5 * tx])
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_row_bands_that_recompute_their_halo_reproduce_the_whole_frame(built, world):
+    """SGI_HALO_RECOMPUTE (include/stratusgi.h): a band computes the gather and the non-final passes on the halo rows its later
+    passes read (28 / 24 / 16 rows) instead of receiving them; only the final pass's GI rows and the lit rows travel.  Same
+    arithmetic on the same inputs, so three frames of a moving camera must give the whole-frame bytes; a halo shorter than
+    28 rows is refused."""
+    from stratusgfx_b200.bands import recompute_rows
+    from stratusgfx_b200.gipass import StratusGiError
+    assert recompute_rows(4) == 30 and recompute_rows(5) == 60 and recompute_rows(1) == 0
+    d = SceneData("c1", frames=3, yaw_deg_per_frame=0.25)
+    whole = run_cuda_staged(d)
+    bands, images, timeouts, tiles = _run_p2p_bands_in_one_process(d, world, 3, halo_mode=1)
+    assert timeouts == [0] * world
+    for f in range(3):
+        assert np.array_equal(images[f].view(np.uint16), whole[f]["combined"].view(np.uint16)), f
+    tx = d.W // 5
+    for b, t in zip(bands, tiles):
+        r0, r1 = (b.b0 - b.y0) // 5, (b.b1 - b.y0) // 5
+        assert np.array_equal(t[r0 * tx:r1 * tx], whole[2]["stage2"][b.b0 // 5 * tx:b.b1 // 5 * tx])
+    gp = make_pass(d, 0, d.H // 2 + 20)                  # 20 halo rows: enough to exchange, not to recompute
+    with pytest.raises(StratusGiError):
+        gp.band_setup(0, d.H // 2, 0, 2, owns_frame_image=True, halo_mode=1)
+    gp.close()
+
+
+def test_row_bands_that_recompute_their_halo_five_iterations(built):
+    d = SceneData("c1", frames=2, yaw_deg_per_frame=0.25)
+    d.scene.denoise_iters = 5
+    whole = run_cuda_staged(d)
+    bands, images, timeouts, _ = _run_p2p_bands_in_one_process(d, 2, 2, halo_mode=1)
+    assert timeouts == [0, 0]
+    for f in range(2):
+        assert np.array_equal(images[f].view(np.uint16), whole[f]["combined"].view(np.uint16)), f
 
 
 def test_p2p_row_bands_five_iterations_need_a_wider_halo(built):
