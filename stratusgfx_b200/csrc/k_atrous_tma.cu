@@ -58,15 +58,26 @@ template <int S> struct TileGeom {
 template <int S, bool FINAL>
 __global__ void __launch_bounds__(kThreads, FINAL ? 3 : 4)
 atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_constant__ CUtensorMap resMap, BandDims bd, const __grid_constant__ DenoiseIO io,
-                int ixFirst, int ixLast, int iyFirst, int iyLast) {
+                int ixFirst, int ixLast, int iyFirst, int iyLast, int nBorder, int gridX) {
     using G = TileGeom<S>;
     __shared__ __align__(128) float4 sGuide[G::kPoints];
     __shared__ __align__(128) uint2 sRes[G::kPoints];
     __shared__ __align__(8) uint64_t bar;
-    // blockIdx.x enumerates (lattice tile column, x residue group), blockIdx.y (lattice tile row, y residue)
+    // The first nBorder CTAs of the launch are the CTAs of atrousKernel's grid that reach outside the rectangle the tiles cover
+    // (CLAMP_TO_EDGE taps at the plane's edges, the rows and columns the lattice tiles leave over): clamped global-memory taps, the
+    // same code as k_denoise.cu.  One launch instead of two: the ~15 us of a second, dependent kernel (launch gap + one wave of
+    // 11-us CTAs) were 10 % of a whole-frame pass and half of a pass on an eighth of the frame (profiles/r02n).
+    if ((int)blockIdx.x < nBorder) {
+        const int2 c = __ldg(io.borderCtas + blockIdx.x);
+        atrousCta<FINAL, S>(bd, io, c.x, c.y, (int)threadIdx.x & (kDnX - 1), (int)threadIdx.x / kDnX);
+        return;
+    }
+    // then (lattice tile column, x residue group) x (lattice tile row, y residue)
     constexpr int groupsX = S / G::kRes;
-    const int tx = blockIdx.x / groupsX, rx0 = (blockIdx.x - tx * groupsX) * G::kRes;
-    const int ty = blockIdx.y / S, ry = blockIdx.y - ty * S;
+    const int blk = (int)blockIdx.x - nBorder;
+    const int bxT = blk % gridX, byT = blk / gridX;
+    const int tx = bxT / groupsX, rx0 = (bxT - tx * groupsX) * G::kRes;
+    const int ty = byT / S, ry = byT - ty * S;
     // first lattice point of the tile; the last tile of a row / column ends where the interior ends
     const int ix0 = min(ixFirst + tx * G::kTX, ixLast), iy0 = min(iyFirst + ty * kTY, iyLast);
     if (threadIdx.x == 0) {
@@ -136,7 +147,7 @@ bool latticeMap(CUtensorMap* map, const void* plane, int texelWords, int W, int 
     EncodeTiledFn enc = encodeTiled();
     if (!enc) return false;
     const cuuint64_t texel = (cuuint64_t)texelWords * 4;
-    const cuuint64_t dims[4] = {(cuuint64_t)texelWords * s, (cuuint64_t)(W / s), (cuuint64_t)s, (cuuint64_t)(rows / s)};
+    const cuuint64_t dims[4] = {(cuuint64_t)texelWords * s, (cuuint64_t)(W / s), (cuuint64_t)s, (cuuint64_t)(rows / s)};      // whole multiples of the spacing
     const cuuint64_t strides[3] = {texel * s, texel * W, texel * W * s};              // bytes, dimensions 1..3
     const cuuint32_t box[4] = {(cuuint32_t)(texelWords * res), (cuuint32_t)px, 1u, (cuuint32_t)py};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
@@ -144,33 +155,55 @@ bool latticeMap(CUtensorMap* map, const void* plane, int texelWords, int W, int 
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int S, bool FINAL>
-bool launchOne(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, int* x0, int* x1, int* y0, int* y1) {
+// The rectangle of pixels the tiles cover, for a handle that computes band-local rows [c0, c0 + crows): whole lattice rows inside
+// that range whose taps stay inside the held plane (two lattice points from every edge; rows / columns beyond the last whole
+// multiple of the spacing are left to the border CTAs as well).
+template <int S>
+bool planTiles(const BandDims& bd, int* ixLo, int* ixHi, int* iyLo, int* iyHi) {
     using G = TileGeom<S>;
     const int W = bd.W, rows = bd.rows;
-    if (W % S || rows % S || ((size_t)W * 8 * S) % 16) return false;
+    if (((size_t)W * 8 * S) % 16) return false;
     const int LX = W / S, LY = rows / S;
-    // interior lattice points: the taps of [2, LX - 2) x [2, LY - 2) stay inside the lattice image
-    if (LX - 4 < G::kTX || LY - 4 < kTY) return false;
-    const int tilesX = (LX - 4 + G::kTX - 1) / G::kTX, tilesY = (LY - 4 + kTY - 1) / kTY;
+    *ixLo = 2; *ixHi = LX - 2;
+    *iyLo = max(2, (bd.c0 + S - 1) / S); *iyHi = min(LY - 2, (bd.c0 + bd.crows) / S);
+    return *ixHi - *ixLo >= G::kTX && *iyHi - *iyLo >= kTY;
+}
+
+template <int S, bool FINAL>
+bool launchOne(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, int nBorder) {
+    using G = TileGeom<S>;
+    int ixLo, ixHi, iyLo, iyHi;
+    if (!planTiles<S>(bd, &ixLo, &ixHi, &iyLo, &iyHi)) return false;
+    const int tilesX = (ixHi - ixLo + G::kTX - 1) / G::kTX, tilesY = (iyHi - iyLo + kTY - 1) / kTY;
     CUtensorMap gm, rm;
-    if (!latticeMap(&gm, io.guide, 4, W, rows, S, G::kRes, G::kPX, G::kPY, true) || !latticeMap(&rm, io.shadowsIn, 2, W, rows, S, G::kRes, G::kPX, G::kPY, false)) return false;
-    dim3 grid(tilesX * (S / G::kRes), tilesY * S);
-    atrousTmaKernel<S, FINAL><<<grid, kThreads, 0, stream>>>(gm, rm, bd, io, 2, LX - 2 - G::kTX, 2, LY - 2 - kTY);
-    *x0 = 2 * S; *x1 = (LX - 2) * S; *y0 = 2 * S; *y1 = (LY - 2) * S;
+    if (!latticeMap(&gm, io.guide, 4, bd.W, bd.rows, S, G::kRes, G::kPX, G::kPY, true) || !latticeMap(&rm, io.shadowsIn, 2, bd.W, bd.rows, S, G::kRes, G::kPX, G::kPY, false)) return false;
+    const int gridX = tilesX * (S / G::kRes), gridY = tilesY * S;
+    atrousTmaKernel<S, FINAL><<<dim3((unsigned)(nBorder + gridX * gridY)), kThreads, 0, stream>>>(gm, rm, bd, io, ixLo, ixHi - G::kTX, iyLo, iyHi - kTY, nBorder, gridX);
     return true;
 }
 
 }  // namespace
 
-// Launches the TMA kernel on the interior of a whole-frame plane; returns false when the plane does not qualify (then the caller
-// runs atrousKernel on everything).  On success the pixel rectangle [*x0, *x1) x [*y0, *y1) was written; the caller covers the rest.
-bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int* x0, int* x1, int* y0, int* y1) {
+static_assert(kThreads == kDnX * kDnY, "the border CTAs run atrousCta with atrousKernel's thread geometry");
+
+// The pixel rectangle [*x0, *x1) x [*y0, *y1) (band-local rows) the TMA tiles of a pass would cover; false when the plane or the
+// spacing does not qualify (then atrousKernel runs on everything).
+bool planAtrousTma(const BandDims& bd, int s, int* x0, int* x1, int* y0, int* y1) {
+    int ixLo, ixHi, iyLo, iyHi;
+    const bool ok = s == 2 ? planTiles<2>(bd, &ixLo, &ixHi, &iyLo, &iyHi) : s == 4 ? planTiles<4>(bd, &ixLo, &ixHi, &iyLo, &iyHi) :
+                    s == 8 ? planTiles<8>(bd, &ixLo, &ixHi, &iyLo, &iyHi) : false;
+    if (!ok || encodeTiled() == nullptr) return false;
+    *x0 = ixLo * s; *x1 = ixHi * s; *y0 = iyLo * s; *y1 = iyHi * s;
+    return true;
+}
+
+// One launch for the whole pass: io.borderCtas[0 .. nBorder) (CTAs of atrousKernel's grid outside the rectangle of planAtrousTma,
+// io.skip* = that rectangle) followed by the lattice tiles.
+bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int nBorder) {
     const int s = 1 + io.multiplier;
-    if (bd.c0 != 0 || bd.crows != bd.rows) return false;
-    if (s == 2) return final_ ? launchOne<2, true>(stream, bd, io, x0, x1, y0, y1) : launchOne<2, false>(stream, bd, io, x0, x1, y0, y1);
-    if (s == 4) return final_ ? launchOne<4, true>(stream, bd, io, x0, x1, y0, y1) : launchOne<4, false>(stream, bd, io, x0, x1, y0, y1);
-    if (s == 8) return final_ ? launchOne<8, true>(stream, bd, io, x0, x1, y0, y1) : launchOne<8, false>(stream, bd, io, x0, x1, y0, y1);
+    if (s == 2) return final_ ? launchOne<2, true>(stream, bd, io, nBorder) : launchOne<2, false>(stream, bd, io, nBorder);
+    if (s == 4) return final_ ? launchOne<4, true>(stream, bd, io, nBorder) : launchOne<4, false>(stream, bd, io, nBorder);
+    if (s == 8) return final_ ? launchOne<8, true>(stream, bd, io, nBorder) : launchOne<8, false>(stream, bd, io, nBorder);
     return false;
 }
 

@@ -40,8 +40,6 @@
 namespace sgi {
 namespace {
 
-constexpr int kDnX = 32, kDnY = 8;
-
 struct Bilin { int i0, i1, j0, j1; float a, b; };
 SGI_DEV Bilin bilinSetup(float u, float v, int W, int H) {
     const float fu = fsub(fmul(u, (float)W), 0.5f), fv = fsub(fmul(v, (float)H), 0.5f);
@@ -69,8 +67,6 @@ prepareGuideKernel(size_t n, const uint32_t* __restrict__ normal, const float* _
     const f3 nn = decodeNormal(__ldg(normal + p));
     guide[p] = make_float4(nn.x, nn.y, nn.z, __ldg(depth + p));
 }
-
-SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- temporal pre-pass (vpl_pbr_gi_denoise.fs:337-425 without the terms that depend on this frame's filtered radiance) --------
 // Everything of the final pass's temporal half that does NOT need the filter's result — the reprojected reads of the previous
@@ -176,109 +172,13 @@ mergeKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const __grid_co
 
 // ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326) -------------------------------
 
-// Rows a CTA row `by` of the à-trous grid can output (band-local, a superset for spacings > kDnY): thread rows kDnY*by .. +kDnY-1
-// are lattice groups g = t / s, each kLat*s rows tall.  Host and device use the same formula to decide which CTAs push rows to
-// a neighbour (the producers of the in-kernel signal).
-__host__ __device__ inline void atrousSlab(int by, int s, int c0, int cEnd, int* lo, int* hi) {
-    const int gLo = (by * kDnY) / s, gHi = (by * kDnY + kDnY - 1) / s;
-    *lo = c0 + gLo * kLat * s;
-    const int h = c0 + (gHi + 1) * kLat * s;
-    *hi = h < cEnd ? h : cEnd;
-}
-template <int S>
-SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
-    const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
-    const uint2* __restrict__ rowS = io.shadowsIn + ((size_t)firstRow * W + x);
-    const size_t stride = (size_t)S * W;
-    #pragma unroll
-    for (int c = 0; c < kLat + 4; ++c) {
-        #pragma unroll
-        for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + (d - 2) * S), __ldg(rowS + (d - 2) * S));
-        rowG += stride; rowS += stride;
-    }
-}
 template <bool FINAL, int S>
 __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __grid_constant__ DenoiseIO io) {
-    const int W = bd.W, rows = bd.rows;
-    const int s = S ? S : 1 + io.multiplier;                 // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
     int bx = (int)blockIdx.x;
     int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
     if (io.borderCtas != nullptr) { const int2 c = __ldg(io.borderCtas + blockIdx.x); bx = c.x; by = c.y; }      // compact launch on the frame's border
-    const int x = bx * kDnX + threadIdx.x;
-    const int t = by * kDnY + threadIdx.y;                   // lattice column-of-rows id: residue r, group g
-    const int g = t / s, r = t - g * s;
-    const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
-    const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
-    if (io.skipX1 > io.skipX0) {
-        // whole-frame handles: the interior was written by the TMA-staged kernel (k_atrous_tma.cu); a CTA whose outputs all lie
-        // inside that rectangle leaves at once (uniform), the others skip the covered outputs one by one
-        int lo, hi;
-        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
-        if (bx * kDnX >= io.skipX0 && bx * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
-    }
-    bool live = x < W && c0 + m0 * s + r < cEnd;
-    // (border launch) a thread whose four outputs all lie inside the TMA kernel's rectangle has nothing to do
-    if (io.skipX1 > io.skipX0 && x >= io.skipX0 && x < io.skipX1 && c0 + m0 * s + r >= io.skipY0 && c0 + (m0 + kLat - 1) * s + r < io.skipY1) live = false;
-    // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
-    // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
-    bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
-    if (live) {
-
-    if (FINAL) {
-        // the epilogue reads three more planes per output, first touched in this kernel: ask L2 for them now
-        #pragma unroll
-        for (int k = 0; k < kLat; ++k) {
-            const size_t p = (size_t)min(c0 + (m0 + k) * s + r, cEnd - 1) * W + x;
-            prefetchL2(io.temporal + p); prefetchL2(io.screen + p); prefetchL2(io.illum + p);
-        }
-    }
-    float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
-    float acc[kLat][4];
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) {
-        const int ly = min(c0 + (m0 + k) * s + r, rows - 1);
-        cen[k] = __ldg(io.guide + (size_t)ly * W + x);
-        cen[k].w *= kLog2e;
-        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
-    }
-    const int firstRow = c0 + (m0 - 2) * s + r;              // row of tap line c = 0; the last one is firstRow + (kLat + 3) * s
-    const bool interior = S != 0 && x >= 2 * s && x + 2 * s < W && firstRow >= 0 && firstRow + (kLat + 3) * s < rows;
-    if (interior) atrousTapsInterior<(S ? S : 1)>(io, W, firstRow, x, cen, acc);
-    else {
-        int txs[5];
-        #pragma unroll
-        for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
-        #pragma unroll
-        for (int c = 0; c < kLat + 4; ++c) {
-            // band-local clamp == CLAMP_TO_EDGE on a whole frame
-            const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
-            const float4* __restrict__ rowG = io.guide + rowBase;
-            const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
-            #pragma unroll
-            for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + txs[d]), __ldg(rowS + txs[d]));
-        }
-    }
-    #pragma unroll
-    for (int k = 0; k < kLat; ++k) {
-        const int ly = c0 + (m0 + k) * s + r;
-        if (ly >= cEnd) break;
-        if (x >= io.skipX0 && x < io.skipX1 && ly >= io.skipY0 && ly < io.skipY1) continue;
-        const f3 shadowFactor = atrousResolve(acc[k]);
-        const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
-        io.reservoirOut[(size_t)ly * W + x] = rv;
-        pushRes(io.links, ly + bd.yOffset, x, W, rv);
-        if (FINAL) finalEpilogue(bd, io, x, ly, shadowFactor);
-    }
-    }   // live
-    if (io.links.doneCounter != nullptr) {                   // (uniform per CTA) a producer CTA counts itself once all its threads have stored
-        int lo, hi;
-        atrousSlab(by, s, c0, cEnd, &lo, &hi);
-        if (lo < hi && slabPushes(io.links, lo, hi, bd.yOffset)) {
-            __syncthreads();
-            if (threadIdx.x == 0 && threadIdx.y == 0) producerDone(io.links);
-        }
-    }
+    atrousCta<FINAL, S>(bd, io, bx, by, (int)threadIdx.x, (int)threadIdx.y);
 }
 
 }  // namespace
@@ -306,14 +206,14 @@ bool preloadDenoiseKernels() {
 // The CTAs (x tile, CTA row) of atrousKernel's grid that reach outside the rectangle the TMA kernel wrote, as a device array: built
 // once per (device, plane size, spacing) and kept for the life of the process (a few KB).
 static const int2* borderCtaList(const BandDims& bd, int s, int gridX, int gridY, int x0, int x1, int y0, int y1, int* count) {
-    struct Entry { int dev, W, rows, s, x0, x1, y0, y1, n; int2* ptr; };
+    struct Entry { int dev, W, rows, c0, crows, s, x0, x1, y0, y1, n; int2* ptr; };
     static std::vector<Entry> cache;
     static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
     for (const Entry& e : cache)
-        if (e.dev == dev && e.W == bd.W && e.rows == bd.rows && e.s == s && e.x0 == x0 && e.x1 == x1 && e.y0 == y0 && e.y1 == y1) { *count = e.n; return e.ptr; }
+        if (e.dev == dev && e.W == bd.W && e.rows == bd.rows && e.c0 == bd.c0 && e.crows == bd.crows && e.s == s && e.x0 == x0 && e.x1 == x1 && e.y0 == y0 && e.y1 == y1) { *count = e.n; return e.ptr; }
     std::vector<int2> list;
     for (int by = 0; by < gridY; ++by) {
         int lo, hi;
@@ -321,7 +221,7 @@ static const int2* borderCtaList(const BandDims& bd, int s, int gridX, int gridY
         for (int bx = 0; bx < gridX; ++bx)
             if (!(bx * kDnX >= x0 && bx * kDnX + kDnX <= x1 && lo >= y0 && hi <= y1)) list.push_back(make_int2(bx, by));
     }
-    Entry e{dev, bd.W, bd.rows, s, x0, x1, y0, y1, (int)list.size(), nullptr};
+    Entry e{dev, bd.W, bd.rows, bd.c0, bd.crows, s, x0, x1, y0, y1, (int)list.size(), nullptr};
     if (!list.empty()) {
         if (cudaMalloc((void**)&e.ptr, list.size() * sizeof(int2)) != cudaSuccess) { *count = 0; cudaGetLastError(); return nullptr; }
         cudaMemcpy(e.ptr, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice);
@@ -359,17 +259,20 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
 #ifdef __CUDACC__                        // (the host-emulation builds of tests/cuda_on_host have no TMA: they run atrousKernel on everything)
-        if (!pushTarget(io.links.up) && !pushTarget(io.links.down) && io.links.waitUp == nullptr && io.links.waitDown == nullptr &&
-            io.links.image == nullptr && bd.c0 == 0 && bd.crows == bd.rows) {
-            // whole-frame handles: the interior through the TMA-staged kernel (taps from shared memory: 0.150 -> 0.122 ms per pass on
-            // c4, same bytes; profiles/r02i), the frame's border (CLAMP_TO_EDGE taps) through the kernel below on a compact CTA list
+        if (io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr && io.links.waitDown == nullptr) {
+            // No reservoir rows leave this pass and it waits for nobody: whole-frame handles and row bands that recompute their halo
+            // (SGI_HALO_RECOMPUTE; the final pass's GI and image rows are stored by the epilogue both kernels share).  The lattice
+            // tiles inside the computed rows go through the TMA-staged body (taps from shared memory: 0.150 -> 0.122 ms per pass on
+            // c4, same bytes; profiles/r02i), the CTAs of this grid that reach outside them (CLAMP_TO_EDGE taps at the plane's edges,
+            // leftover rows) run first IN THE SAME LAUNCH.  The neighbours' flags are then released by the signal kernel.
             int x0, x1, y0, y1;
-            if (launchAtrousTma(stream, bd, io, final_, &x0, &x1, &y0, &y1)) {
+            if (planAtrousTma(bd, s, &x0, &x1, &y0, &y1)) {
                 io.skipX0 = x0; io.skipX1 = x1; io.skipY0 = y0; io.skipY1 = y1;
+                io.links.doneCounter = nullptr;
                 int count = 0;
                 io.borderCtas = borderCtaList(bd, s, (int)grid.x, (int)grid.y, x0, x1, y0, y1, &count);
-                if (io.borderCtas != nullptr) grid = dim3((unsigned)count, 1);
-                if (count == 0) return 1;
+                if ((count == 0 || io.borderCtas != nullptr) && launchAtrousTma(stream, bd, io, final_, count)) return 1;
+                io = ioIn; io.skipX0 = io.skipX1 = io.skipY0 = io.skipY1 = 0; io.borderCtas = nullptr;      // (no tensor map: everything through atrousKernel)
             }
         }
 #endif

@@ -411,7 +411,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
                        const SgiAtlasEntry* __restrict__ shadowIndices, const __grid_constant__ AtlasTable atlases,
                        uint2* __restrict__ colorOut, uint2* __restrict__ reservoirOut, float4* __restrict__ guideOut, uint2* __restrict__ mergedOut,
                        const __grid_constant__ BandLinks links, int tableCap, int* __restrict__ unitCounters, int counterSel,
-                       CoordTables tabs, uint32_t unitsXMagic /* ceil(2^32 / unitsX), or 0: divide */) {
+                       CoordTables tabs, uint32_t unitsXMagic /* ceil(2^32 / unitsX), or 0: divide */, int unitChunk /* units per counter fetch */) {
     extern __shared__ float4 sTab[];
     float4* __restrict__ sPos = sTab;                       // (position, radius)
     float4* __restrict__ sCol = sTab + tableCap;            // (colour, farPlane)
@@ -468,14 +468,14 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
     // The counter is read one chunk ahead (the atomic's round trip, ~700 cycles, is over before its value is needed), and while a
     // unit is processed the G-buffer lines of the warp's next unit are on their way into L2.
     int nextBase = 0;
-    if (lane == 0) nextBase = atomicAdd(counter, kUnitChunk);
+    if (lane == 0) nextBase = atomicAdd(counter, unitChunk);
     int unit = 0, unitEnd = 0;
     while (true) {
         if (unit >= unitEnd) {
             const int base = __shfl_sync(0xffffffffu, nextBase, 0);
             if (base >= units) break;
-            if (lane == 0) nextBase = atomicAdd(counter, kUnitChunk);
-            unit = base; unitEnd = min(base + kUnitChunk, units);
+            if (lane == 0) nextBase = atomicAdd(counter, unitChunk);
+            unit = base; unitEnd = min(base + unitChunk, units);
         }
         const int thisUnit = unit++;
         int ux;
@@ -631,7 +631,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
 // (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
 using GatherFn = void (*)(const FrameConsts, BandDims, const float*, const uint32_t*, const uint32_t*, const uint16_t*, const uint32_t*, const unsigned short*,
                           const SgiVplData*, const int32_t*, const SgiAtlasEntry*, const AtlasTable, uint2*, uint2*, float4*, uint2*, const BandLinks, int, int*, int,
-                          CoordTables, uint32_t);
+                          CoordTables, uint32_t, int);
 static GatherFn gatherFn(bool wide, bool bands) {
     if (wide) return bands ? gatherStochasticKernel<1024, true> : gatherStochasticKernel<1024, false>;
     return bands ? gatherStochasticKernel<512, true> : gatherStochasticKernel<512, false>;
@@ -712,9 +712,12 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
         CoordTables tabs; tabs.u = coordU; tabs.row = coordRow;
         const int threads = wide ? 1024 : 512;
         const int grid = wide ? max(1, min(smCount(), (units + 31) / 32)) : max(1, min(2 * smCount(), (units + 15) / 16));
+        // two units per fetch halve the counter traffic; a short launch (a thin row band: < 24 units per warp) takes them one by one,
+        // so that its warps finish within one unit (6 us) of each other instead of two
+        const int unitChunk = units >= 24 * grid * (threads / 32) ? kUnitChunk : 1;
         GatherFn kf = gatherFn(wide, bands);
         kf<<<dim3(grid), dim3(threads), bytes, stream>>>(fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atlases,
-                               colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel, tabs, magic);
+                               colorOut, reservoirOut, guideOut, mergedOut, armed, cap, unitCounters, counterSel, tabs, magic, unitChunk);
     }
     return 1;
 }

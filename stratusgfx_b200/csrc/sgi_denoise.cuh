@@ -79,4 +79,112 @@ SGI_DEV void finalEpilogue(const BandDims& bd, const DenoiseIO& io, int x, int l
 }
 
 
+// ---- passes >= 1: 5x5 à-trous (filterInput :142-190 inside the tap loop :309-326), clamped global-memory taps ------------------
+constexpr int kDnX = 32, kDnY = 8;            // threads of a CTA: 32 columns x 8 lattice thread rows
+SGI_DEV void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Rows a CTA row `by` of the à-trous grid can output (band-local, a superset for spacings > kDnY): thread rows kDnY*by .. +kDnY-1
+// are lattice groups g = t / s, each kLat*s rows tall.  Host and device use the same formula to decide which CTAs push rows to
+// a neighbour (the producers of the in-kernel signal).
+__host__ __device__ inline void atrousSlab(int by, int s, int c0, int cEnd, int* lo, int* hi) {
+    const int gLo = (by * kDnY) / s, gHi = (by * kDnY + kDnY - 1) / s;
+    *lo = c0 + gLo * kLat * s;
+    const int h = c0 + (gHi + 1) * kLat * s;
+    *hi = h < cEnd ? h : cEnd;
+}
+template <int S>
+SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x, const float4 (&cen)[kLat], float (&acc)[kLat][4]) {
+    const float4* __restrict__ rowG = io.guide + ((size_t)firstRow * W + x);
+    const uint2* __restrict__ rowS = io.shadowsIn + ((size_t)firstRow * W + x);
+    const size_t stride = (size_t)S * W;
+    #pragma unroll
+    for (int c = 0; c < kLat + 4; ++c) {
+        #pragma unroll
+        for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + (d - 2) * S), __ldg(rowS + (d - 2) * S));
+        rowG += stride; rowS += stride;
+    }
+}
+// One CTA (bx, by) of the clamped à-trous grid, thread (tx, ty) of kDnX x kDnY.  It is the body of atrousKernel (k_denoise.cu: row
+// bands that exchange halos, planes the TMA kernel does not take) and of the border CTAs inside atrousTmaKernel's launch
+// (k_atrous_tma.cu: the part of a plane its tiles do not cover).
+template <bool FINAL, int S>
+SGI_DEV void atrousCta(const BandDims& bd, const DenoiseIO& io, int bx, int by, int tx, int ty) {
+    const int W = bd.W, rows = bd.rows;
+    const int s = S ? S : 1 + io.multiplier;                 // tap spacing: ivec2(dx,dy) + ivec2(dx,dy)*multiplier (:318)
+    const int x = bx * kDnX + tx;
+    const int t = by * kDnY + ty;                            // lattice column-of-rows id: residue r, group g
+    const int g = t / s, r = t - g * s;
+    const int m0 = g * kLat;                                 // lattice index of output 0: computed row c0 + (m0 + k)*s + r
+    const int c0 = bd.c0, cEnd = bd.c0 + bd.crows;           // only the band's own rows are computed; taps may read its halo rows
+    if (io.skipX1 > io.skipX0) {
+        // whole-frame handles: the interior was written by the TMA-staged kernel (k_atrous_tma.cu); a CTA whose outputs all lie
+        // inside that rectangle leaves at once (uniform), the others skip the covered outputs one by one
+        int lo, hi;
+        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+        if (bx * kDnX >= io.skipX0 && bx * kDnX + kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) return;
+    }
+    bool live = x < W && c0 + m0 * s + r < cEnd;
+    // (border launch) a thread whose four outputs all lie inside the TMA kernel's rectangle has nothing to do
+    if (io.skipX1 > io.skipX0 && x >= io.skipX0 && x < io.skipX1 && c0 + m0 * s + r >= io.skipY0 && c0 + (m0 + kLat - 1) * s + r < io.skipY1) live = false;
+    // row bands: taps of lattice rows m0-2 .. m0+kLat+1 reach into the halo only at the band's edges; those CTAs wait for the
+    // neighbour's previous pass (whose kernel stored the halo rows), every other CTA starts at once
+    bandWaitCta(io.links, live && m0 < 2, live && c0 + (m0 + kLat + 1) * s + r >= cEnd);
+    if (live) {
+
+    if (FINAL) {
+        // the epilogue reads three more planes per output, first touched in this kernel: ask L2 for them now
+        #pragma unroll
+        for (int k = 0; k < kLat; ++k) {
+            const size_t p = (size_t)min(c0 + (m0 + k) * s + r, cEnd - 1) * W + x;
+            prefetchL2(io.temporal + p); prefetchL2(io.screen + p); prefetchL2(io.illum + p);
+        }
+    }
+    float4 cen[kLat];                                        // centre guides (normal, depth*log2e)
+    float acc[kLat][4];
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) {
+        const int ly = min(c0 + (m0 + k) * s + r, rows - 1);
+        cen[k] = __ldg(io.guide + (size_t)ly * W + x);
+        cen[k].w *= kLog2e;
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+    }
+    const int firstRow = c0 + (m0 - 2) * s + r;              // row of tap line c = 0; the last one is firstRow + (kLat + 3) * s
+    const bool interior = S != 0 && x >= 2 * s && x + 2 * s < W && firstRow >= 0 && firstRow + (kLat + 3) * s < rows;
+    if (interior) atrousTapsInterior<(S ? S : 1)>(io, W, firstRow, x, cen, acc);
+    else {
+        int txs[5];
+        #pragma unroll
+        for (int d = 0; d < 5; ++d) txs[d] = iclamp(x + (d - 2) * s, 0, W - 1);
+        #pragma unroll
+        for (int c = 0; c < kLat + 4; ++c) {
+            // band-local clamp == CLAMP_TO_EDGE on a whole frame
+            const size_t rowBase = (size_t)iclamp(c0 + (m0 + c - 2) * s + r, 0, rows - 1) * W;
+            const float4* __restrict__ rowG = io.guide + rowBase;
+            const uint2* __restrict__ rowS = io.shadowsIn + rowBase;
+            #pragma unroll
+            for (int d = 0; d < 5; ++d) atrousTap(cen, acc, c, d, __ldg(rowG + txs[d]), __ldg(rowS + txs[d]));
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < kLat; ++k) {
+        const int ly = c0 + (m0 + k) * s + r;
+        if (ly >= cEnd) break;
+        if (x >= io.skipX0 && x < io.skipX1 && ly >= io.skipY0 && ly < io.skipY1) continue;
+        const f3 shadowFactor = atrousResolve(acc[k]);
+        const uint2 rv = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
+        io.reservoirOut[(size_t)ly * W + x] = rv;
+        pushRes(io.links, ly + bd.yOffset, x, W, rv);
+        if (FINAL) finalEpilogue(bd, io, x, ly, shadowFactor);
+    }
+    }   // live
+    if (io.links.doneCounter != nullptr) {                   // (uniform per CTA) a producer CTA counts itself once all its threads have stored
+        int lo, hi;
+        atrousSlab(by, s, c0, cEnd, &lo, &hi);
+        if (lo < hi && slabPushes(io.links, lo, hi, bd.yOffset)) {
+            __syncthreads();
+            if (tx == 0 && ty == 0) producerDone(io.links);
+        }
+    }
+}
+
 }  // namespace sgi

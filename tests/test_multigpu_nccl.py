@@ -14,7 +14,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames, yaw=0.25, halo=None):
+def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames, yaw=0.25, halo=None, halo_mode=0):
     """One process per band; peer descriptors travel as bytes (all_gather_object), memory is attached with CUDA IPC."""
     import torch
     import torch.distributed as dist
@@ -26,19 +26,19 @@ def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames, yaw=0.
         dist.init_process_group("gloo", rank=rank, world_size=world)          # both ranks on one GPU: NCCL refuses that, gloo carries the bytes
     else:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    from stratusgfx_b200.bands import connect_bands, halo_rows, plan_bands
+    from stratusgfx_b200.bands import connect_bands, halo_rows, plan_bands, recompute_rows
     from stratusgfx_b200.gipass import VplGiPass
     from stratusgfx_b200.scene import Scene
     scene = Scene(workload, yaw_deg_per_frame=yaw)
     W, H = scene.width, scene.height
-    bands = plan_bands(H, world, halo_rows(scene.denoise_iters) if halo is None else halo)
+    bands = plan_bands(H, world, (recompute_rows if halo_mode else halo_rows)(scene.denoise_iters) if halo is None else halo)
     me = bands[rank]
     vd, at = scene.vpls()
     sh, df = scene.cubemaps()
     gp = VplGiPass(W, H, me.y0, me.rows, scene.cube_res, scene.csm_res, scene.denoise_iters, device=device)
     gp.set_vpls(vd, at)
     gp.set_atlases(sh, df)
-    connect_bands(dist, gp, me, world)
+    connect_bands(dist, gp, me, world, halo_mode=halo_mode)
     for f in range(frames):
         gp.set_gbuffer(scene.gbuffer(f, me.y0, me.rows), scene.gbuffer(f - 1, me.y0, me.rows))
         gp.set_csm(scene.csm(f))
@@ -56,11 +56,11 @@ def _p2p_worker(rank, world, port, workload, out_path, share_gpu, frames, yaw=0.
     dist.destroy_process_group()
 
 
-def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3, yaw=0.25, halo=None, expect_equal=True):
+def _check_p2p(tmp_path, world, share_gpu, workload="c1", frames=3, yaw=0.25, halo=None, expect_equal=True, halo_mode=0):
     import torch.multiprocessing as mp
     from tests.parity_util import SceneData, run_cuda_staged
     out_path = str(tmp_path / "p2p_frame%d.npy")
-    mp.spawn(_p2p_worker, args=(world, _free_port(), workload, out_path, share_gpu, frames, yaw, halo), nprocs=world, join=True)
+    mp.spawn(_p2p_worker, args=(world, _free_port(), workload, out_path, share_gpu, frames, yaw, halo, halo_mode), nprocs=world, join=True)
     misses = sum(int(open((out_path % 0) + f".misses{r}").read()) for r in range(world))
     single = run_cuda_staged(SceneData(workload, frames=frames, yaw_deg_per_frame=yaw))
     equal = all(np.array_equal(np.load(out_path % f).view(np.uint16), single[f]["combined"].view(np.uint16)) for f in range(frames))
@@ -87,12 +87,26 @@ def test_p2p_bands_over_cuda_ipc_two_processes_on_one_gpu(built, tmp_path):
     _check_p2p(tmp_path, 2, share_gpu=True)
 
 
+def test_recompute_bands_over_cuda_ipc_three_processes_on_one_gpu(built, tmp_path):
+    """SGI_HALO_RECOMPUTE across processes (a middle band included): the GI rows of the final pass and the lit rows are what
+    still travels through the CUDA IPC mappings; the frames must be the one-GPU frames byte for byte."""
+    _check_p2p(tmp_path, 3, share_gpu=True, halo_mode=1)
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_p2p_bands_over_nvlink_equal_single_gpu_frames(built, tmp_path, world):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     _check_p2p(tmp_path, world, share_gpu=False, workload="c2", frames=2)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_recompute_bands_over_nvlink_equal_single_gpu_frames(built, tmp_path, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _check_p2p(tmp_path, world, share_gpu=False, workload="c2", frames=3, halo_mode=1)
 
 
 def _worker(rank, world, port, workload, out_path):
