@@ -11,11 +11,15 @@ Metric: Gpixel·VPL/s = W·H·N_vpl / t_frame / 1e9, ms_per_ste
 N > 1 is launched by torchrun, one rank per GPU; the frame is split into horizontal row bands
  — strong scaling of one frame.  Every step rank 0 broadcasts the VPL table and
 the frame's refreshed cube maps over NCCL (one packed buffer, issued a frame ahead); each rank runs the pass
-on its band, whose halo rows the neighbouring bands' kernels fill through NVLink peer stores ordered by epoch
-flags (csrc/sgi_band.cu); the lit rows of every band travel to rank 0's frame image by copy-engine transfers.
-After the timed region rank 0 replays the same frames on one whole-frame handle and compares the assembled
-image with it byte for byte ("image_equals_single_gpu").  `--bands apron` is the exchange-free comparison
-(30 redundant rows per inner edge + an NCCL gather), `--split views` gives every GPU its own camera view.
+on its band.  The reservoir rows a band's à-trous taps read beyond its own rows are, by default, computed by
+the band itself (`--bands recompute`, SGI_HALO_RECOMPUTE: the gather and the non-final passes run on 28 / 24 /
+16 halo rows as well; same bytes, no exchange inside the frame); `--bands p2p` is the exchange (the
+neighbours' kernels store every pass's boundary rows through NVLink peer stores ordered by epoch flags,
+csrc/sgi_band.cu).  In both, the final pass's GI rows go to the neighbours (next frame's reprojection) and the
+lit rows of every band travel to rank 0's frame image by copy-engine transfers.  After the timed region rank 0
+replays the same frames on one whole-frame handle and compares the assembled image with it byte for byte
+("image_equals_single_gpu").  `--bands apron` is the plain-handle comparison (30 redundant rows per inner
+edge for every pass + an NCCL gather), `--split views` gives every GPU its own camera view.
 """
 import argparse
 import ctypes
@@ -801,7 +805,8 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="broadcast the per-frame tables at the start of the frame instead of one frame ahead (N > 1)")
     ap.add_argument("--no-image-check", action="store_true", help="N > 1: skip the byte comparison of the assembled image with a single-GPU replay")
     ap.add_argument("--split", default="bands", choices=["bands", "views"], help="N > 1: row bands of one frame (default, strong scaling) or one independent camera view per GPU (weak scaling)")
-    ap.add_argument("--bands", default="p2p", choices=["p2p", "recompute", "apron", "isolated"], help="multi-GPU halo strategy (N > 1); `isolated` = band handles without neighbours, a timing diagnosis whose seams are wrong")
+    ap.add_argument("--bands", default="recompute", choices=["recompute", "p2p", "apron", "isolated"],
+                    help="multi-GPU halo strategy (N > 1). recompute (default): SGI_HALO_RECOMPUTE, the bands compute the non-final passes on their halo rows themselves; p2p: SGI_HALO_EXCHANGE, the neighbours' kernels store every pass's boundary rows; apron: plain handles, NCCL gather; isolated: band handles without neighbours, a timing diagnosis whose seams are wrong")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))

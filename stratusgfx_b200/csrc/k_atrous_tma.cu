@@ -1,7 +1,8 @@
 // k_atrous_tma.cu — the non-final à-trous pass with its taps staged through shared memory by TMA (north_star: "bandwidth-bound
-// stencils with shared-memory halos").  It serves the interior of whole-frame handles, final pass included; atrousKernel
-// (k_denoise.cu) serves the frame's border (CLAMP_TO_EDGE taps) and row bands.  The two kernels share the weight, accumulation and
-// epilogue code (sgi_denoise.cuh): same taps, same order, same arithmetic, the same bytes (checked on c2 and c4, profiles/r02g).
+// stencils with shared-memory halos").  It serves every pass that neither waits for a neighbour nor stores reservoir rows into
+// one: whole-frame handles and row bands that recompute their halo, final pass included; atrousKernel (k_denoise.cu) serves row
+// bands that exchange halos.  The two share the weight, accumulation and epilogue code (sgi_denoise.cuh): same taps, same order,
+// same arithmetic, the same bytes (checked on c2 and c4, profiles/r02g; the band tests of tests/test_parity_gpu.py).
 //
 // A pass with tap spacing s only ever combines pixels of one residue class (x mod s, y mod s): the frame is s*s independent
 // "lattice images" of (W/s) x (rows/s) points on which the filter is a dense 5x5 stencil.  A CTA owns kRes consecutive x residues,
@@ -11,10 +12,10 @@
 //     [ s texels (contiguous) ][ W/s lattice columns, stride s texels ][ s row residues, stride W texels ][ rows/s lattice rows, stride s*W texels ]
 // so the strided lattice lands DENSE in shared memory, one elected thread issues both copies and everybody waits on one mbarrier.
 // A lane's taps are then LDS.128 / LDS.64 at immediate offsets from one base address.
-// The tiles cover the lattice points whose taps stay inside the plane, [2, W/s - 2) x [2, rows/s - 2) of every residue class; the
-// last tile of a row / column is shifted back to end there (a few outputs are then computed twice, with the same result).  The two
-// lattice points next to each edge (TMA would fill zeros there, the shader wants CLAMP_TO_EDGE) and planes whose extent is not a
-// multiple of the spacing keep the clamped global-memory path of k_denoise.cu, launched on a compact list of border CTAs.
+// The tiles cover the lattice points whose taps stay inside the plane, [2, W/s - 2) x [2, rows/s - 2) of every residue class,
+// restricted to the rows the handle computes (a row band).  The two lattice points next to each edge (TMA would fill zeros there,
+// the shader wants CLAMP_TO_EDGE) and rows / columns beyond the last whole multiple of the spacing keep the clamped global-memory
+// path of k_denoise.cu: the CTAs of ITS grid that reach outside the tiles' rectangle are the first CTAs of this kernel's launch.
 #include <cuda.h>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
@@ -55,10 +56,12 @@ template <int S> struct TileGeom {
     static constexpr int kPoints = kPX * kRes * kPY;
 };
 
-template <int S, bool FINAL>
-__global__ void __launch_bounds__(kThreads, FINAL ? 3 : 4)
+// FINAL at four CTAs per SM as well (64 registers, 52 bytes of spills in the epilogue): 0.283 -> 0.263 ms for the final pass of c4
+// against three CTAs at 80 registers (profiles/r02p).  PARTIAL: see the last tile of a column below.
+template <int S, bool FINAL, bool PARTIAL>
+__global__ void __launch_bounds__(kThreads, 4)
 atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_constant__ CUtensorMap resMap, BandDims bd, const __grid_constant__ DenoiseIO io,
-                int ixFirst, int ixLast, int iyFirst, int iyLast, int nBorder, int gridX) {
+                int ixFirst, int ixLast, int iyFirst, int iyEnd, int nBorder, int gridX) {
     using G = TileGeom<S>;
     __shared__ __align__(128) float4 sGuide[G::kPoints];
     __shared__ __align__(128) uint2 sRes[G::kPoints];
@@ -78,8 +81,12 @@ atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_const
     const int bxT = blk % gridX, byT = blk / gridX;
     const int tx = bxT / groupsX, rx0 = (bxT - tx * groupsX) * G::kRes;
     const int ty = byT / S, ry = byT - ty * S;
-    // first lattice point of the tile; the last tile of a row / column ends where the interior ends
-    const int ix0 = min(ixFirst + tx * G::kTX, ixLast), iy0 = min(iyFirst + ty * kTY, iyLast);
+    // first lattice point of the tile.  The last tile of a row or column is shifted back to end where the interior ends (a few
+    // outputs are computed twice, with the same result).  PARTIAL (chosen by the launcher for planes of few lattice rows: a thin row
+    // band with spacing 8 has ~33 of them, and shifting a 16-row tile back would recompute up to 15): the last tile of a COLUMN
+    // keeps its place and leaves its lattice rows from iyEnd on uncomputed; its box may then reach past the tensor (zero fill), where
+    // only taps of uncomputed rows lie.
+    const int ix0 = min(ixFirst + tx * G::kTX, ixLast), iy0 = PARTIAL ? iyFirst + ty * kTY : min(iyFirst + ty * kTY, iyEnd - kTY);
     if (threadIdx.x == 0) {
         mbarInit(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -94,13 +101,14 @@ atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_const
         // the epilogue reads three more planes per output, first touched in this kernel: ask L2 for them while the tile is in flight
         #pragma unroll
         for (int k = 0; k < kLat; ++k) {
-            const size_t p = (size_t)((iy0 + grp * kLat + k) * S + ry) * bd.W + x;
+            const size_t p = (size_t)(min(iy0 + grp * kLat + k, iyEnd - 1) * S + ry) * bd.W + x;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(io.temporal + p));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(io.screen + p));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(io.illum + p));
         }
     }
     __syncthreads();                     // the barrier's initialisation is visible to the waiters
+    if (PARTIAL && iy0 + grp * kLat >= iyEnd) return;       // none of this group's four lattice rows is computed
     mbarWait(&bar, 0);
 
     // shared-memory index of the tap (lattice row j, column offset d): ((j * kPX + ixl + d) * kRes + rx), ixl * kRes + rx = col
@@ -123,6 +131,7 @@ atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_const
     }
     #pragma unroll
     for (int k = 0; k < kLat; ++k) {
+        if (PARTIAL && iy0 + grp * kLat + k >= iyEnd) break;
         const int ly = (iy0 + grp * kLat + k) * S + ry;
         const f3 shadowFactor = atrousResolve(acc[k]);
         io.reservoirOut[(size_t)ly * bd.W + x] = packHalf4(shadowFactor.x, shadowFactor.y, shadowFactor.z, 1.0f);
@@ -178,11 +187,27 @@ bool launchOne(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, int
     CUtensorMap gm, rm;
     if (!latticeMap(&gm, io.guide, 4, bd.W, bd.rows, S, G::kRes, G::kPX, G::kPY, true) || !latticeMap(&rm, io.shadowsIn, 2, bd.W, bd.rows, S, G::kRes, G::kPX, G::kPY, false)) return false;
     const int gridX = tilesX * (S / G::kRes), gridY = tilesY * S;
-    atrousTmaKernel<S, FINAL><<<dim3((unsigned)(nBorder + gridX * gridY)), kThreads, 0, stream>>>(gm, rm, bd, io, ixLo, ixHi - G::kTX, iyLo, iyHi - kTY, nBorder, gridX);
+    // few lattice rows and a last tile that would be shifted back by more than a quarter: leave it partial instead
+    const int rem = (iyHi - iyLo) % kTY;
+    const bool partial = rem != 0 && tilesY <= 8 && rem <= kTY - kLat;
+    auto kf = partial ? atrousTmaKernel<S, FINAL, true> : atrousTmaKernel<S, FINAL, false>;
+    kf<<<dim3((unsigned)(nBorder + gridX * gridY)), kThreads, 0, stream>>>(gm, rm, bd, io, ixLo, ixHi - G::kTX, iyLo, iyHi, nBorder, gridX);
     return true;
 }
 
 }  // namespace
+
+// CUDA loads kernels lazily on first launch, and that load can stall behind a kernel that is spinning on a band flag
+// (sgi_band.cu) — so every kernel of this file is loaded when the handle is created.
+template <int S> static bool preloadSpacing() {
+    cudaFuncAttributes a; bool ok = true;
+    ok = ok && cudaFuncGetAttributes(&a, atrousTmaKernel<S, false, false>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousTmaKernel<S, false, true>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousTmaKernel<S, true, false>) == cudaSuccess;
+    ok = ok && cudaFuncGetAttributes(&a, atrousTmaKernel<S, true, true>) == cudaSuccess;
+    return ok;
+}
+bool preloadAtrousTmaKernels() { return preloadSpacing<2>() && preloadSpacing<4>() && preloadSpacing<8>(); }
 
 static_assert(kThreads == kDnX * kDnY, "the border CTAs run atrousCta with atrousKernel's thread geometry");
 

@@ -184,7 +184,11 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (cudaMallocHost(&h->pinnedCount, sizeof(int32_t)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (cudaMalloc((void**)&h->prepassInside, sizeof(int)) != cudaSuccess) return bail(SGI_ERR_CUDA);
     if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels() &&
-          preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels() && preloadCubemapKernels())) return bail(SGI_ERR_CUDA);
+          preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels() && preloadCubemapKernels()
+#ifdef __CUDACC__
+          && preloadAtrousTmaKernels()            // (k_atrous_tma.cu is not part of the host-emulation builds)
+#endif
+          )) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);
     *out = h;
     return SGI_OK;

@@ -266,7 +266,7 @@ bool preloadSsaoKernels(); int launchSsao(cudaStream_t stream, const BandDims& b
 int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
                          const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm, const AtlasTable& atlases,
                          const SgiDirectParams& dp, uint2* out);
-bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels(); bool preloadDenoiseKernels(); bool preloadBandKernels();
+bool preloadAtrousTmaKernels(); bool preloadVplKernels(); bool preloadTileKernels(); bool preloadGatherKernels(); bool preloadDenoiseKernels(); bool preloadBandKernels();
 
 // each launcher enqueues its kernels on `stream` and returns the number of launches made
 int launchCull(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl,
