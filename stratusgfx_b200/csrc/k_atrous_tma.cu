@@ -71,8 +71,9 @@ atrousTmaKernel(const __grid_constant__ CUtensorMap guideMap, const __grid_const
     // same code as k_denoise.cu.  One launch instead of two: the ~15 us of a second, dependent kernel (launch gap + one wave of
     // 11-us CTAs) were 10 % of a whole-frame pass and half of a pass on an eighth of the frame (profiles/r02n).
     if ((int)blockIdx.x < nBorder) {
-        const int2 c = __ldg(io.borderCtas + blockIdx.x);
-        atrousCta<FINAL, S>(bd, io, c.x, c.y, (int)threadIdx.x & (kDnX - 1), (int)threadIdx.x / kDnX);
+        int bx, by;
+        borderCta(io, (int)blockIdx.x, &bx, &by);
+        atrousCta<FINAL, S>(bd, io, bx, by, (int)threadIdx.x & (kDnX - 1), (int)threadIdx.x / kDnX);
         return;
     }
     // then (lattice tile column, x residue group) x (lattice tile row, y residue)
@@ -222,7 +223,7 @@ bool planAtrousTma(const BandDims& bd, int s, int* x0, int* x1, int* y0, int* y1
     return true;
 }
 
-// One launch for the whole pass: io.borderCtas[0 .. nBorder) (CTAs of atrousKernel's grid outside the rectangle of planAtrousTma,
+// One launch for the whole pass: the nBorder border CTAs of io (CTAs of atrousKernel's grid outside the rectangle of planAtrousTma,
 // io.skip* = that rectangle) followed by the lattice tiles.
 bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int nBorder) {
     const int s = 1 + io.multiplier;

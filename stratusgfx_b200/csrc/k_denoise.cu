@@ -30,8 +30,6 @@
 // of a warp are consecutive in x, so every request is fully coalesced.  Each output accumulates its
 // taps in the same order (dy ascending, dx ascending) wherever it sits in a band, so a row band with an
 // apron reproduces the whole-frame bytes.
-#include <mutex>
-#include <vector>
 #include "sgi_internal.h"
 #include "sgi_math.cuh"
 #include "sgi_merge.cuh"
@@ -177,7 +175,6 @@ __global__ void __launch_bounds__(kDnX * kDnY, FINAL ? 3 : 4)
 atrousKernel(const __grid_constant__ FrameConsts /*fc*/, BandDims bd, const __grid_constant__ DenoiseIO io) {
     int bx = (int)blockIdx.x;
     int by = io.links.doneCounter != nullptr ? boundaryFirst((int)blockIdx.y, (int)gridDim.y) : (int)blockIdx.y;
-    if (io.borderCtas != nullptr) { const int2 c = __ldg(io.borderCtas + blockIdx.x); bx = c.x; by = c.y; }      // compact launch on the frame's border
     atrousCta<FINAL, S>(bd, io, bx, by, (int)threadIdx.x, (int)threadIdx.y);
 }
 
@@ -202,35 +199,6 @@ bool preloadDenoiseKernels() {
     return ok;
 }
 
-#ifdef __CUDACC__
-// The CTAs (x tile, CTA row) of atrousKernel's grid that reach outside the rectangle the TMA kernel wrote, as a device array: built
-// once per (device, plane size, spacing) and kept for the life of the process (a few KB).
-static const int2* borderCtaList(const BandDims& bd, int s, int gridX, int gridY, int x0, int x1, int y0, int y1, int* count) {
-    struct Entry { int dev, W, rows, c0, crows, s, x0, x1, y0, y1, n; int2* ptr; };
-    static std::vector<Entry> cache;
-    static std::mutex mu;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(mu);
-    for (const Entry& e : cache)
-        if (e.dev == dev && e.W == bd.W && e.rows == bd.rows && e.c0 == bd.c0 && e.crows == bd.crows && e.s == s && e.x0 == x0 && e.x1 == x1 && e.y0 == y0 && e.y1 == y1) { *count = e.n; return e.ptr; }
-    std::vector<int2> list;
-    for (int by = 0; by < gridY; ++by) {
-        int lo, hi;
-        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
-        for (int bx = 0; bx < gridX; ++bx)
-            if (!(bx * kDnX >= x0 && bx * kDnX + kDnX <= x1 && lo >= y0 && hi <= y1)) list.push_back(make_int2(bx, by));
-    }
-    Entry e{dev, bd.W, bd.rows, bd.c0, bd.crows, s, x0, x1, y0, y1, (int)list.size(), nullptr};
-    if (!list.empty()) {
-        if (cudaMalloc((void**)&e.ptr, list.size() * sizeof(int2)) != cudaSuccess) { *count = 0; cudaGetLastError(); return nullptr; }
-        cudaMemcpy(e.ptr, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice);
-    }
-    cache.push_back(e);
-    *count = e.n;
-    return e.ptr;
-}
-#endif
 
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide) {
     const size_t n = (size_t)bd.W * bd.rows;
@@ -269,10 +237,21 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
             if (planAtrousTma(bd, s, &x0, &x1, &y0, &y1)) {
                 io.skipX0 = x0; io.skipX1 = x1; io.skipY0 = y0; io.skipY1 = y1;
                 io.links.doneCounter = nullptr;
-                int count = 0;
-                io.borderCtas = borderCtaList(bd, s, (int)grid.x, (int)grid.y, x0, x1, y0, y1, &count);
-                if ((count == 0 || io.borderCtas != nullptr) && launchAtrousTma(stream, bd, io, final_, count)) return 1;
-                io = ioIn; io.skipX0 = io.skipX1 = io.skipY0 = io.skipY1 = 0; io.borderCtas = nullptr;      // (no tensor map: everything through atrousKernel)
+                // the CTAs of this grid that lie entirely inside the rectangle: x tiles [bx0, bx1) of the CTA rows [by0, by1)
+                io.borderGridX = (int)grid.x; io.borderGridY = (int)grid.y;
+                io.borderBx0 = (x0 + kDnX - 1) / kDnX; io.borderBx1 = x1 / kDnX;
+                io.borderBy0 = 0; io.borderBy1 = 0;
+                bool open_ = false;
+                for (int by = 0; by < (int)grid.y; ++by) {
+                    int lo, hi;
+                    atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+                    const bool inside = lo < hi && lo >= y0 && hi <= y1;
+                    if (inside && !open_) { io.borderBy0 = by; io.borderBy1 = by + 1; open_ = true; }
+                    else if (inside && io.borderBy1 == by) io.borderBy1 = by + 1;       // (the covered CTA rows are contiguous)
+                }
+                if (io.borderBx1 < io.borderBx0) io.borderBx1 = io.borderBx0;
+                if (launchAtrousTma(stream, bd, io, final_, borderCtaCount(io))) return 1;
+                io = ioIn;      // (no tensor map: everything through atrousKernel)
             }
         }
 #endif

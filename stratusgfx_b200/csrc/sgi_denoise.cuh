@@ -104,6 +104,27 @@ SGI_DEV void atrousTapsInterior(const DenoiseIO& io, int W, int firstRow, int x,
         rowG += stride; rowS += stride;
     }
 }
+// The border CTAs of a pass whose interior goes through the TMA tiles, enumerated without a table: the CTA rows above the covered
+// block, the two flanks of the covered rows, the CTA rows below.  Host (count) and device (index -> CTA) use the same order.
+__host__ __device__ inline int borderCtaCount(const DenoiseIO& io) {
+    const int flank = io.borderBx0 + (io.borderGridX - io.borderBx1);
+    return io.borderBy0 * io.borderGridX + (io.borderBy1 - io.borderBy0) * flank + (io.borderGridY - io.borderBy1) * io.borderGridX;
+}
+__device__ __forceinline__ void borderCta(const DenoiseIO& io, int i, int* bx, int* by) {
+    const int gx = io.borderGridX, top = io.borderBy0 * gx;
+    if (i < top) { *by = i / gx; *bx = i - *by * gx; return; }
+    i -= top;
+    const int flank = io.borderBx0 + (gx - io.borderBx1), mid = (io.borderBy1 - io.borderBy0) * flank;
+    if (i < mid) {
+        const int r = i / flank, j = i - r * flank;
+        *by = io.borderBy0 + r; *bx = j < io.borderBx0 ? j : io.borderBx1 + (j - io.borderBx0);
+        return;
+    }
+    i -= mid;
+    const int r = i / gx;
+    *by = io.borderBy1 + r; *bx = i - r * gx;
+}
+
 // One CTA (bx, by) of the clamped à-trous grid, thread (tx, ty) of kDnX x kDnY.  It is the body of atrousKernel (k_denoise.cu: row
 // bands that exchange halos, planes the TMA kernel does not take) and of the border CTAs inside atrousTmaKernel's launch
 // (k_atrous_tma.cu: the part of a plane its tiles do not cover).

@@ -172,10 +172,11 @@ struct DenoiseIO {
     uint2* giOut;                 // half4 (final pass)
     unsigned short* historyOut;   // half  (final pass)
     int multiplier;
-    // outputs inside this pixel rectangle (band-local rows) were written by the TMA-staged kernel (k_atrous_tma.cu): atrousKernel skips
-    // them, and runs on the compact list of CTAs (x tile, CTA row) that reach outside the rectangle instead of on its whole grid
+    // outputs inside this pixel rectangle (band-local rows) are written by the TMA-staged tiles (k_atrous_tma.cu); the CTAs of the
+    // clamped grid (gridX x gridY CTAs of kDnX x kDnY threads) that lie entirely inside it — x tiles [bx0, bx1) of CTA rows
+    // [by0, by1) — do not run, the others (the "border CTAs") skip the covered outputs one by one
     int skipX0, skipX1, skipY0, skipY1;
-    const int2* borderCtas;
+    int borderGridX, borderGridY, borderBx0, borderBx1, borderBy0, borderBy1;
 };
 
 }  // namespace sgi
