@@ -10,9 +10,10 @@ import json; d=json.loads(open('$out/bench.json').read().strip().splitlines()[-1
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err; echo "reference arm exit $?"; tail -c 400 $out/bench_reference.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launches.log 2>&1
 python tools/ncu_summary.py launches $out/launches.csv 2>/dev/null | head -18
-for spec in "gather:gatherStochasticKernel:4" "atrous_tma:atrousTmaKernel<2:3" "atrous_final:atrousTmaKernel<8:3" "temporal:temporalKernel:3" "stage2:stage2Kernel:3" "stage1:stage1Kernel:3"; do
-  name=${spec%%:*}; rest=${spec#*:}; rx=${rest%%:*}; skip=${rest#*:}
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s $skip -c 2 -f -o $out/prof_$name \
+# (atrous: launches 4-6 of atrousTmaKernel = the s = 2, 4 and 8 (final) passes of one frame)
+for spec in "gather:gatherStochasticKernel:4:2" "atrous:atrousTmaKernel:3:3" "temporal:temporalKernel:3:2" "stage2:stage2Kernel:3:2" "stage1:stage1Kernel:3:2"; do
+  name=${spec%%:*}; rest=${spec#*:}; rx=${rest%%:*}; rest=${rest#*:}; skip=${rest%%:*}; cnt=${rest#*:}
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s $skip -c $cnt -f -o $out/prof_$name \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_$name.log 2>&1
   echo "$name: $(ls -la $out/prof_$name.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
 done
