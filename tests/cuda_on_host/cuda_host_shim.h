@@ -1,7 +1,7 @@
 // cuda_host_shim.h — compile a CUDA kernel of this repository with g++ and run it thread by thread on the host.
 // TEST INFRASTRUCTURE (see host_tu.py): it checks a kernel's LOGIC — index arithmetic, exact-arithmetic chains, what is stored
 // where — against the oracle / the reference's compiled shader text without a GPU: for kernels that have not met one yet
-// (csrc/k_direct.cu) and for compile-time variants queued for an A/B (csrc/k_denoise.cu, -DSGI_ATROUS_V2).  Every device
+// (csrc/k_direct.cu) and for kernel changes that have not met a GPU yet.  Every device
 // intrinsic is given its IEEE host meaning (-ffp-contract=off: a * b + c is never fused behind the code's back); the MUFU
 // approximations become libm calls, so radiance agrees to float rounding, not to the bit.  A thread-by-thread run cannot honour a
 // barrier or a warp collective: reaching one aborts the process instead of computing something else.
