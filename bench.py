@@ -349,9 +349,15 @@ def run_ours(args, rank, world, local_rank):
         # denoise) on its own rows with a plain handle, the times are all-gathered and the cuts moved to equalise them
         for it in range(args.balance):
             b = bands[rank]
-            cal = VplGiPass(W, H, b.b0, b.b1 - b.b0, scene.cube_res, scene.csm_res, iters, device=local_rank)
-            cal.set_gbuffer(scene.gbuffer(0, b.b0, b.b1 - b.b0), scene.gbuffer(-1, b.b0, b.b1 - b.b0))
-            cal.set_vpls(vd, at); cal.set_atlases(sh, df); cal.set_csm(csm); cal.bind()
+            # recompute mode: the calibration handle is a band handle of the same geometry without peers, so that the rows a band
+            # recomputes beyond its inner edges (one edge for the first and the last band, two for the others) are in its time
+            c0, c1 = (b.y0, b.y0 + b.rows) if recompute else (b.b0, b.b1)
+            cal = VplGiPass(W, H, c0, c1 - c0, scene.cube_res, scene.csm_res, iters, device=local_rank)
+            cal.set_gbuffer(scene.gbuffer(0, c0, c1 - c0), scene.gbuffer(-1, c0, c1 - c0))
+            cal.set_vpls(vd, at); cal.set_atlases(sh, df); cal.set_csm(csm)
+            if recompute:
+                cal.band_setup(b.b0, b.b1 - b.b0, b.rank, world, owns_frame_image=False, halo_mode=1)
+            cal.bind()
             cfp = scene.frame_params(0)
             cs = torch.cuda.ExternalStream(cal.stream_ptr(), device=dev)
             # the row-dependent cost of a band = its whole frame (tile lists run next to the gather on the pass's side stream,
