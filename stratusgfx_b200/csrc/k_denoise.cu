@@ -235,21 +235,8 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
             // leftover rows) run first IN THE SAME LAUNCH.  The neighbours' flags are then released by the signal kernel.
             int x0, x1, y0, y1;
             if (planAtrousTma(bd, s, &x0, &x1, &y0, &y1)) {
-                io.skipX0 = x0; io.skipX1 = x1; io.skipY0 = y0; io.skipY1 = y1;
                 io.links.doneCounter = nullptr;
-                // the CTAs of this grid that lie entirely inside the rectangle: x tiles [bx0, bx1) of the CTA rows [by0, by1)
-                io.borderGridX = (int)grid.x; io.borderGridY = (int)grid.y;
-                io.borderBx0 = (x0 + kDnX - 1) / kDnX; io.borderBx1 = x1 / kDnX;
-                io.borderBy0 = 0; io.borderBy1 = 0;
-                bool open_ = false;
-                for (int by = 0; by < (int)grid.y; ++by) {
-                    int lo, hi;
-                    atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
-                    const bool inside = lo < hi && lo >= y0 && hi <= y1;
-                    if (inside && !open_) { io.borderBy0 = by; io.borderBy1 = by + 1; open_ = true; }
-                    else if (inside && io.borderBy1 == by) io.borderBy1 = by + 1;       // (the covered CTA rows are contiguous)
-                }
-                if (io.borderBx1 < io.borderBx0) io.borderBx1 = io.borderBx0;
+                borderGeometry(bd, s, (int)grid.x, (int)grid.y, x0, x1, y0, y1, &io);
                 if (launchAtrousTma(stream, bd, io, final_, borderCtaCount(io))) return 1;
                 io = ioIn;      // (no tensor map: everything through atrousKernel)
             }

@@ -501,7 +501,7 @@ gatherStochasticKernel(const __grid_constant__ FrameConsts fc, BandDims bd, cons
         const float2 rowV = __ldg(tabs.row + ly);                                    // fsTexCoords.y and hash(gl_FragCoord.y) of this row
         const float texU = __ldg(tabs.u + x);
         if (unit < unitEnd) {                      // the chunk's next unit: the next 32 pixels of the row-major planes (W % 32 == 0), else close by
-            const size_t pn = p + 32;
+            const size_t pn = min(p + 32, (size_t)bd.W * bd.rows - 1);
             prefetchL2(gDepth + pn); prefetchL2(gNormal + pn); prefetchL2(gAlbedo + pn); prefetchL2(gRma + pn); prefetchL2(ssao + pn); prefetchL2(gRefl + pn);
         } else {
             if (nb < units) {

@@ -110,7 +110,7 @@ __host__ __device__ inline int borderCtaCount(const DenoiseIO& io) {
     const int flank = io.borderBx0 + (io.borderGridX - io.borderBx1);
     return io.borderBy0 * io.borderGridX + (io.borderBy1 - io.borderBy0) * flank + (io.borderGridY - io.borderBy1) * io.borderGridX;
 }
-__device__ __forceinline__ void borderCta(const DenoiseIO& io, int i, int* bx, int* by) {
+__host__ __device__ inline void borderCta(const DenoiseIO& io, int i, int* bx, int* by) {
     const int gx = io.borderGridX, top = io.borderBy0 * gx;
     if (i < top) { *by = i / gx; *bx = i - *by * gx; return; }
     i -= top;
@@ -123,6 +123,24 @@ __device__ __forceinline__ void borderCta(const DenoiseIO& io, int i, int* bx, i
     i -= mid;
     const int r = i / gx;
     *by = io.borderBy1 + r; *bx = i - r * gx;
+}
+
+// The CTAs of the clamped grid (gridX x gridY, spacing s, computed rows [c0, c0 + crows)) that lie entirely inside the pixel
+// rectangle [x0, x1) x [y0, y1): x tiles [bx0, bx1) of the CTA rows [by0, by1) (contiguous: a slab's rows grow with by).
+__host__ inline void borderGeometry(const BandDims& bd, int s, int gridX, int gridY, int x0, int x1, int y0, int y1, DenoiseIO* io) {
+    io->skipX0 = x0; io->skipX1 = x1; io->skipY0 = y0; io->skipY1 = y1;
+    io->borderGridX = gridX; io->borderGridY = gridY;
+    io->borderBx0 = (x0 + kDnX - 1) / kDnX; io->borderBx1 = x1 / kDnX;
+    if (io->borderBx1 < io->borderBx0) io->borderBx1 = io->borderBx0;
+    io->borderBy0 = 0; io->borderBy1 = 0;
+    bool open_ = false;
+    for (int by = 0; by < gridY; ++by) {
+        int lo, hi;
+        atrousSlab(by, s, bd.c0, bd.c0 + bd.crows, &lo, &hi);
+        const bool inside = lo < hi && lo >= y0 && hi <= y1;
+        if (inside && !open_) { io->borderBy0 = by; io->borderBy1 = by + 1; open_ = true; }
+        else if (inside && io->borderBy1 == by) io->borderBy1 = by + 1;
+    }
 }
 
 // One CTA (bx, by) of the clamped à-trous grid, thread (tx, ty) of kDnX x kDnY.  It is the body of atrousKernel (k_denoise.cu: row

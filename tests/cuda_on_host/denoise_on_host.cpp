@@ -39,3 +39,26 @@ extern "C" int host_denoise(const SgiFrameParams* fp, int W, int H, int iters, c
     }
     return 0;
 }
+
+// The border CTAs of a pass whose interior goes through the TMA tiles (csrc/sgi_denoise.cuh: borderGeometry, borderCtaCount,
+// borderCta): the enumeration the launch uses, and — per CTA of the clamped grid — whether atrousCta's own test sends it home.
+extern "C" int host_border_enumeration(int W, int rows, int c0, int crows, int s, int x0, int x1, int y0, int y1, int* listBxBy, int cap,
+                                       int* gridXY, unsigned char* insideFlags /* [gridY][gridX] */) {
+    sgi::BandDims bd;
+    bd.W = W; bd.fullH = rows; bd.yOffset = 0; bd.rows = rows; bd.cubeRes = 0; bd.csmRes = 0; bd.c0 = c0; bd.crows = crows;
+    const int threadRows = ((crows + s * sgi::kLat - 1) / (s * sgi::kLat)) * s;
+    const int gx = (W + sgi::kDnX - 1) / sgi::kDnX, gy = (threadRows + sgi::kDnY - 1) / sgi::kDnY;
+    gridXY[0] = gx; gridXY[1] = gy;
+    sgi::DenoiseIO io;
+    std::memset(&io, 0, sizeof(io));
+    sgi::borderGeometry(bd, s, gx, gy, x0, x1, y0, y1, &io);
+    for (int by = 0; by < gy; ++by) {
+        int lo, hi;
+        sgi::atrousSlab(by, s, c0, c0 + crows, &lo, &hi);
+        for (int bx = 0; bx < gx; ++bx)      // the early exit of atrousCta
+            insideFlags[by * gx + bx] = (bx * sgi::kDnX >= io.skipX0 && bx * sgi::kDnX + sgi::kDnX <= io.skipX1 && lo >= io.skipY0 && hi <= io.skipY1) ? 1 : 0;
+    }
+    const int n = sgi::borderCtaCount(io);
+    for (int i = 0; i < n && i < cap; ++i) sgi::borderCta(io, i, listBxBy + 2 * i, listBxBy + 2 * i + 1);
+    return n;
+}

@@ -61,3 +61,31 @@ def test_denoiser_kernels_on_the_host_match_the_oracle(host_denoiser, yaw):
         assert np.array_equal(hist.view(np.uint16), orc[f]["history"].view(np.uint16))
     if yaw:
         assert len(np.unique(orc[1]["history"].view(np.uint16))) > 1          # some pixels were reset, some accumulated
+
+
+@pytest.mark.parametrize("W,rows,c0,crows,s", [(3840, 2160, 0, 2160, 2), (3840, 2160, 0, 2160, 8), (3840, 330, 30, 270, 8), (3840, 330, 6, 318, 2),
+                                               (3840, 300, 0, 298, 4), (1920, 420, 30, 360, 4), (640, 360, 0, 360, 8), (100, 77, 5, 60, 2)])
+def test_border_ctas_are_enumerated_exactly_once(host_denoiser, W, rows, c0, crows, s):
+    """A pass whose interior goes through the TMA tiles launches, ahead of the tiles, the CTAs of the clamped grid that reach outside the
+    tiles' rectangle (csrc/sgi_denoise.cuh: borderGeometry / borderCtaCount / borderCta — arithmetic, no device list).  For whole
+    frames, thin bands with and without halo rows above, and a plane smaller than any tile: the enumeration must be exactly the set of
+    CTAs that atrousCta's own early exit does NOT send home, each once.  The rectangle is the one k_atrous_tma.cu's planTiles would give
+    (whole lattice rows inside the computed rows, two lattice points from every plane edge)."""
+    L = host_denoiser
+    L.host_border_enumeration.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.host_border_enumeration.restype = C.c_int
+    LX, LY = W // s, rows // s
+    ix0, ix1 = 2, LX - 2
+    iy0, iy1 = max(2, -(-c0 // s)), min(LY - 2, (c0 + crows) // s)
+    rects = [(ix0 * s, max(ix0, ix1) * s, iy0 * s, max(iy0, iy1) * s), (0, 0, 0, 0), (0, W, c0, c0 + crows)]
+    for x0, x1, y0, y1 in rects:
+        cap = 1 << 16
+        lst = np.full((cap, 2), -1, np.int32); grid = np.zeros(2, np.int32); inside = np.zeros(1 << 16, np.uint8)
+        n = L.host_border_enumeration(W, rows, c0, crows, s, x0, x1, y0, y1, lst.ctypes.data, cap, grid.ctypes.data, inside.ctypes.data)
+        gx, gy = int(grid[0]), int(grid[1])
+        assert gx * gy <= inside.size and 0 <= n <= cap
+        inside2d = inside[:gx * gy].reshape(gy, gx).astype(bool)
+        want = {(bx, by) for by in range(gy) for bx in range(gx) if not inside2d[by, bx]}
+        got = [tuple(int(v) for v in lst[i]) for i in range(n)]
+        assert len(set(got)) == len(got) == n, "a border CTA is enumerated twice"
+        assert set(got) == want, (len(got), len(want))
