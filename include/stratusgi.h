@@ -245,12 +245,14 @@ typedef struct SgiHandle_* SgiHandle;
  *      reference is single-GPU) ------------------------------------------------------------------
  * A band handle HOLDS frame rows [y_offset, y_offset+rows) of every per-pixel plane but COMPUTES only
  * [compute_y0, compute_y0+compute_rows).  The held rows outside the computed range are halo: the caller
- * supplies the G-buffer there (it is an input), while the denoiser's reservoir / GI / history halo rows
- * are written by the neighbouring band's kernels directly into this handle's memory through NVLink peer
- * stores, followed by a release flag; the consumer pass waits on the flag in stream order.  The final
- * lit rows of every band end up in the root band's frame image (the "gather").
+ * supplies the G-buffer there (it is an input).  The denoiser's reservoir halo rows are either computed by
+ * the band itself (SGI_HALO_RECOMPUTE) or written by the neighbouring band's kernels directly into this
+ * handle's memory through NVLink peer stores, followed by a release flag the consumer pass waits on
+ * (SGI_HALO_EXCHANGE); the GI halo rows (next frame's reprojection) always arrive from the neighbours'
+ * final passes.  The final lit rows of every band end up in the root band's frame image (the "gather").
  * Handles may live in one process (peer access) or one process per GPU (CUDA IPC). */
-#define SGI_HALO_ROWS 20   /* >= 16 = reach of the widest reference à-trous pass (2*(multiplier+1), BE:1920), on the 5-row tile grid */
+#define SGI_HALO_ROWS 20   /* SGI_HALO_EXCHANGE: >= 16 = reach of the widest reference à-trous pass (2*(multiplier+1), BE:1920), on the 5-row tile grid */
+#define SGI_HALO_ROWS_RECOMPUTE 30   /* SGI_HALO_RECOMPUTE: >= 28 = summed reach of the reference's three à-trous passes (4 + 8 + 16) */
 enum { SGI_PEER_UP = 0 /* band rank-1 */, SGI_PEER_DOWN = 1 /* band rank+1 */, SGI_PEER_ROOT = 2 /* owner of the frame image */ };
 
 typedef struct SgiBandParams {

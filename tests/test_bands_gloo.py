@@ -116,3 +116,20 @@ def test_halo_rows_cover_the_reach_of_the_widest_pass():
         reach = 2 * (1 << (iters - 1)) if iters > 1 else 0          # 2 * (multiplier + 1), multiplier = 2^(iters-1) - 1 (BE:1920)
         h = halo_rows(iters)
         assert h >= reach and h % TILE == 0 and h - reach < TILE
+
+
+def test_recompute_rows_cover_the_summed_reach_of_all_passes():
+    """SGI_HALO_RECOMPUTE (include/stratusgi.h): pass p is recomputed on the band's rows +- sum_{j>p} 2^(j+1); pass 0 therefore on
+    2^(iters+1) - 4 rows, which the halo must hold (28 for the reference's four iterations, 30 on the tile grid), and every pass's
+    taps (2^(p+1) rows) stay inside what the pass before it computed."""
+    from stratusgfx_b200.bands import TILE, plan_bands, recompute_rows
+    for iters in range(1, 7):
+        h = recompute_rows(iters)
+        ext = [sum(2 << j for j in range(p + 1, iters)) for p in range(iters)]        # bandDimsForPass (csrc/sgi_abi.cu)
+        assert h % TILE == 0 and (ext[0] if iters > 1 else 0) <= h < (ext[0] if iters > 1 else 0) + TILE
+        assert ext[-1] == 0
+        for p in range(1, iters):
+            assert ext[p] + (2 << p) == ext[p - 1]          # rows pass p reads = rows pass p-1 wrote
+    assert [recompute_rows(i) for i in (1, 4, 5)] == [0, 30, 60]
+    bands = plan_bands(2160, 8, recompute_rows(4))
+    assert all(b.b0 - b.y0 in (0, 30) and (b.y0 + b.rows) - b.b1 in (0, 30) for b in bands)
