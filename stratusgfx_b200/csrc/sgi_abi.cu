@@ -216,6 +216,7 @@ int sgi_destroy(SgiHandle h) {
     if (h->evStage1) cudaEventDestroy(h->evStage1);
     if (h->cullTicket) cudaFree(h->cullTicket);
     if (h->gatherCounters) cudaFree(h->gatherCounters);
+    if (h->taaTables) cudaFree(h->taaTables);
     if (h->prepassKeys) cudaFree(h->prepassKeys);
     if (h->prepassInside) cudaFree(h->prepassInside);
     if (h->pinnedCount) cudaFreeHost(h->pinnedCount);
@@ -330,7 +331,8 @@ int sgi_taa(SgiHandle h, const SgiTaaParams* tp) {
     if (tp->historyOut && tp->historyOut == tp->prevScreen) return fail(h, SGI_ERR_INVALID_ARG, "sgi_taa: historyOut may not alias prevScreen (other pixels still read it)");
     if (h->banded || h->cp.rows != h->cp.full_height) return fail(h, SGI_ERR_UNSUPPORTED, "sgi_taa: whole-frame handles only");
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
-    return postLaunch(h, launchTaa(h->stream, bandDims(h), *tp));
+    if (h->taaTables == nullptr) SGI_CUDA(h, cudaMalloc((void**)&h->taaTables, sgi::kTaaTableFloats * sizeof(float)));
+    return postLaunch(h, launchTaa(h->stream, bandDims(h), *tp, h->taaTables));
 }
 
 int sgi_direct_lighting(SgiHandle h, const SgiFrameParams* fp, const SgiDirectParams* dp) {

@@ -248,6 +248,7 @@ struct SgiHandle_ {
     int prepassCap = 0;
     int* prepassInside = nullptr;   // lights inside the frustum (before the 10000 cap)
     int* gatherCounters = nullptr;  // two work counters of the persistent gather, used alternately (k_gather.cu)
+    float* taaTables = nullptr;     // [kTaaTableFloats] scratch of sgi_taa (k_taa.cu)
     float* coordU = nullptr;        // [width] (x + 0.5) / W, and [rows] ((y + 0.5) / fullH, hash(y + 0.5)): rebuilt with the planes
     float2* coordRow = nullptr;
     int64_t gatherLaunches = 0;
@@ -262,7 +263,8 @@ void fillFrameConsts(const SgiFrameParams* fp, FrameConsts* fc);
 bool preloadPrepassKernels(); int launchPrepass(cudaStream_t stream, const SgiPrepassParams& pp, unsigned long long* keys, int* inside);
 bool preloadDirectKernels();
 bool preloadCubemapKernels(); int launchCubemaps(cudaStream_t stream, const SgiCubeRenderParams& rp, const SgiVplData* lightData, const SgiAtlasEntry* atlasByVpl, int res, const AtlasTable& atlases);
-bool preloadTaaKernels(); int launchTaa(cudaStream_t stream, const BandDims& bd, const SgiTaaParams& tp);
+constexpr int kTaaTableFloats = 512;     // tonemap / inverse-tonemap tables of the 256 texel values (k_taa.cu)
+bool preloadTaaKernels(); int launchTaa(cudaStream_t stream, const BandDims& bd, const SgiTaaParams& tp, float* tables /* [kTaaTableFloats], device */);
 bool preloadSsaoKernels(); int launchSsao(cudaStream_t stream, const BandDims& bd, const SgiSsaoParams& sp);
 int launchDirectLighting(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const float* depth, const uint32_t* normal, const uint32_t* albedo,
                          const uint16_t* refl, const uint32_t* rma, const unsigned short* ssao, const float* csm, const AtlasTable& atlases,

@@ -49,7 +49,7 @@ def test_taa_kernel_on_the_host_equals_the_shader_text(host_taa, workload, yaw):
     out, hist = np.zeros((d.H, d.W, 4), np.float16), np.zeros((d.H, d.W, 4), np.uint8)
     tp = TaaParams()
     tp.screen, tp.prevScreen, tp.velocity, tp.colorOut, tp.historyOut = screen.ctypes.data, prev.ctypes.data, vel.ctypes.data, out.ctypes.data, hist.ctypes.data
-    assert L.host_taa(d.W, d.H, C.byref(tp)) == 1
+    assert L.host_taa(d.W, d.H, C.byref(tp)) == 2          # the table kernel + the resolve
     assert np.array_equal(out.view(np.uint16), want.view(np.uint16))
     assert (out[..., 3] == np.float16(0.0625)).all() and np.isfinite(out.astype(np.float32)).all()
     # the blit into the RGB8 history: clamp, scale, round to nearest
