@@ -69,8 +69,12 @@ SGI_DEV float calculateInfiniteShadowValue(const FrameConsts& fc, const float* _
     return fmul(mix(light2, light1, weight), fdiv(1.0f, samples));
 }
 
+// texture(samplerCubeArray, vec4(dir, layer)).r of a unorm16 depth map.  The texel is the exact one (cubeTexelDecided, sgi_math.cuh:
+// an estimate with a margin, the exact division chain of cubeTexel only for a coordinate next to a texel edge) and texel / 65535.0f
+// is unorm16's three instructions, bit for bit the division (tests/test_device_math_identities.py).
 SGI_DEV float cubeDepth(const AtlasTable& atlases, SgiAtlasEntry e, f3 dir, int res) {
-    return fdiv((float)__ldg(atlases.shadow[e.index] + (size_t)e.layer * 6 * res * res + cubeTexel(dir, res)), 65535.0f);
+    const float halfRes = 0.5f * (float)res, epsK = (float)res * (1.0f / 4194304.0f);
+    return unorm16(__ldg(atlases.shadow[e.index] + (size_t)e.layer * 6 * res * res + cubeTexelDecided(dir, res, halfRes, epsK)));
 }
 // pbr.glsl:116-136 and :79-112
 SGI_DEV float calculateShadowValue1Sample(const AtlasTable& atlases, SgiAtlasEntry e, int res, float farPlane, f3 fragPos, f3 lightPos, float lightNormalDot, float minBias) {
@@ -89,45 +93,59 @@ SGI_DEV float calculateShadowValue8Samples(const AtlasTable& atlases, SgiAtlasEn
         const float depth = fmul(cubeDepth(atlases, e, fragDir + mk3(offsets[x], offsets[y], offsets[z]), res), farPlane);
         if (fsub(currentDepth, bias) > depth) shadow = fadd(shadow, 1.0f);
     }
-    return fdiv(shadow, 8.0f);
+    return fmul(shadow, 0.125f);                  // shadow / 8.0: a power of two, the same rounding
 }
 
 struct Surface { f3 fragPos, baseColor, normal, viewDir, baseReflectance; float viewDist, roughness, metallic, ambient; };
 
-// calculateLighting_Burley (pbr2.glsl:454-476) with diffuseDivisor = specularMultiplier = vec3(1.0)
-SGI_DEV f3 calculateLightingBurley(const FrameConsts& fc, const Surface& s, f3 lightColor, f3 lightDir, float fogIntensity, float shadowFactor,
-                                   float attenuationFactor, float ambientIntensity) {
-    // BRDF_Base (:146-168)
+// What calculateLighting_Burley computes from the surface alone, once per pixel instead of once per light (each value by the same
+// operations in the same order, so nothing changes but the count): BRDF_Base (pbr2.glsl:146-168), the view half of
+// BRDF_DotProducts and of the Smith / Burley terms, the fog factor (fog.glsl:37-41).
+struct SurfaceTerms { f3 diffuseColor, f0; float remappedRoughness, r2, NdotV, ggxlRoot /* sqrt((NdotV - r2 NdotV) NdotV + r2) */, viewPow5, fog; };
+SGI_DEV SurfaceTerms surfaceTerms(const FrameConsts& fc, const Surface& s) {
+    SurfaceTerms t;
     float rr = s.roughness;
     if (fc.usePerceptualRoughness) rr = fmul(rr, rr);
-    const float remappedRoughness = vmax(vmax(0.0f, fc.minRoughness), rr);
+    t.remappedRoughness = vmax(vmax(0.0f, fc.minRoughness), rr);
     f3 diffuseColor = fsub(1.0f, s.metallic) * s.baseColor;
-    diffuseColor = diffuseColor / (mk3(1.0f) + PREVENT_DIV_BY_ZERO);
+    t.diffuseColor = diffuseColor / (mk3(1.0f) + PREVENT_DIV_BY_ZERO);
     f3 f0 = ((0.16f * s.baseReflectance) * s.baseReflectance) * fsub(1.0f, s.metallic) + s.baseColor * s.metallic;
-    f0 = f0 * mk3(1.0f);
+    t.f0 = f0 * mk3(1.0f);
+    t.NdotV = saturate(dot(s.normal, s.viewDir));
+    t.r2 = fmul(t.remappedRoughness, t.remappedRoughness);
+    t.ggxlRoot = fsqrt(fadd(fmul(fsub(t.NdotV, fmul(t.r2, t.NdotV)), t.NdotV), t.r2));
+    t.viewPow5 = powf(fsub(1.0f, t.NdotV), 5.0f);
+    t.fog = expf(fmul(-fc.fogDensity, s.viewDist));
+    return t;
+}
+
+// calculateLighting_Burley (pbr2.glsl:454-476) with diffuseDivisor = specularMultiplier = vec3(1.0)
+SGI_DEV f3 calculateLightingBurley(const FrameConsts& fc, const Surface& s, const SurfaceTerms& st, f3 lightColor, f3 lightDir, float fogIntensity, float shadowFactor,
+                                   float attenuationFactor, float ambientIntensity) {
+    const float remappedRoughness = st.remappedRoughness;
     // BRDF_DotProducts (:170-188)
     const f3 V = s.viewDir, L = normalize(lightDir), H = normalize(V + L), N = s.normal;
-    const float NdotV = saturate(dot(N, V)), NdotL = saturate(dot(N, L)), NdotH = saturate(dot(N, H)), LdotH = saturate(dot(L, H));
+    const float NdotV = st.NdotV, NdotL = saturate(dot(N, L)), NdotH = saturate(dot(N, H)), LdotH = saturate(dot(L, H));
     // singleScatteringBRDF_Specular (:102-115)
-    const float r2 = fmul(remappedRoughness, remappedRoughness);
+    const float r2 = st.r2;
     const float fN = fadd(fmul(fsub(fmul(NdotH, r2), NdotH), NdotH), 1.0f);
     const float NDF = fdiv(r2, vmax(fmul(fmul(PI_F, fN), fN), PREVENT_DIV_BY_ZERO));
     const float fF = powf(fsub(1.0f, LdotH), 5.0f);
-    const f3 Fresnel = fF + f0 * fsub(1.0f, fF);
-    const float ggxv = fmul(NdotL, fsqrt(fadd(fmul(fsub(NdotV, fmul(r2, NdotV)), NdotV), r2)));
+    const f3 Fresnel = fF + st.f0 * fsub(1.0f, fF);
+    const float ggxv = fmul(NdotL, st.ggxlRoot);
     const float ggxl = fmul(NdotV, fsqrt(fadd(fmul(fsub(NdotL, fmul(r2, NdotL)), NdotL), r2)));
     const float Visibility = fdiv(0.5f, vmax(fadd(ggxv, ggxl), PREVENT_DIV_BY_ZERO));
     const f3 Fr = fmul(NDF, Visibility) * Fresnel;
     // singleScatteringBRDF_Diffuse_Burley (:117-126) -> Fd_Burley (:91-96) -> Fd_Fresnel_Schlick (:85-88)
     const float f90 = fadd(0.5f, fmul(fmul(fmul(2.0f, remappedRoughness), LdotH), LdotH));
     const float lightScatter = fadd(1.0f, fmul(fsub(f90, 1.0f), powf(fsub(1.0f, NdotL), 5.0f)));
-    const float viewScatter = fadd(1.0f, fmul(fsub(f90, 1.0f), powf(fsub(1.0f, NdotV), 5.0f)));
-    const f3 Fd = diffuseColor * fmul(fmul(lightScatter, viewScatter), fdiv(1.0f, PI_F));
+    const float viewScatter = fadd(1.0f, fmul(fsub(f90, 1.0f), st.viewPow5));
+    const f3 Fd = st.diffuseColor * fmul(fmul(lightScatter, viewScatter), fdiv(1.0f, PI_F));
     const f3 brdf = (Fd + Fr) * NdotL;
     const f3 ambient = ((brdf * s.ambient) * lightColor) * ambientIntensity;
     const f3 finalBrightness = brdf * lightColor;
     // applyFog (fog.glsl:37-41)
-    const float f = expf(fmul(-fc.fogDensity, s.viewDist));
+    const float f = st.fog;
     const f3 fogC = mk3(fc.fogColor[0], fc.fogColor[1], fc.fogColor[2]) * fogIntensity;
     const f3 fogged = finalBrightness * f + fogC * fsub(1.0f, f);
     return attenuationFactor * (ambient + shadowFactor * fogged);
@@ -156,6 +174,7 @@ directKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
     s.baseReflectance = mk3(unorm8(refl & 0xffu));
     const f3 emissive = mk3(unorm8(alb >> 24), unorm8((refl >> 8) & 0xffu), unorm8((rma >> 16) & 0xffu));
 
+    const SurfaceTerms st = surfaceTerms(fc, s);
     f3 color = mk3(0.0f);
     for (int i = 0; i < da.numLights; ++i) {
         const float4 lp = __ldg(reinterpret_cast<const float4*>(da.nonShadowCasters + i)), lc = __ldg(reinterpret_cast<const float4*>(da.nonShadowCasters + i) + 1);
@@ -163,7 +182,7 @@ directKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
         const f3 lightPos = mk3(lp.x, lp.y, lp.z), lightColor = mk3(lc.x, lc.y, lc.z), lightDir = lightPos - s.fragPos;
         if (length(lightDir) < radius) {
             const float dist = length(lightDir);
-            color = color + calculateLightingBurley(fc, s, lightColor, lightDir, fdiv(length(lightColor), 12.0f), fsub(1.0f, 0.0f),
+            color = color + calculateLightingBurley(fc, s, st, lightColor, lightDir, fdiv(length(lightColor), 12.0f), fsub(1.0f, 0.0f),
                                                     fdiv(1.0f, fadd(1.0f, fmul(dist, dist))), da.pointLightAmbientIntensity);
         }
     }
@@ -177,7 +196,7 @@ directKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
             if (s.viewDist < 150.0f) shadowFactor = calculateShadowValue8Samples(atlases, e, bd.cubeRes, farPlane, s.fragPos, lightPos, dot(lightDir, s.normal), 0.03f);
             else if (s.viewDist < 750.0f) shadowFactor = calculateShadowValue1Sample(atlases, e, bd.cubeRes, farPlane, s.fragPos, lightPos, dot(lightDir, s.normal), 0.03f);
             const float dist = length(lightDir);
-            color = color + calculateLightingBurley(fc, s, lightColor, lightDir, fdiv(length(lightColor), 12.0f), fsub(1.0f, shadowFactor),
+            color = color + calculateLightingBurley(fc, s, st, lightColor, lightDir, fdiv(length(lightColor), 12.0f), fsub(1.0f, shadowFactor),
                                                     fdiv(1.0f, fadd(1.0f, fmul(dist, dist))), da.pointLightAmbientIntensity);
         }
     }
@@ -191,7 +210,7 @@ directKernel(const __grid_constant__ FrameConsts fc, BandDims bd, const float* _
         const float litFraction = calculateInfiniteShadowValue(fc, csm, bd.csmRes, s.fragPos, blends, s.normal, bias);
         // calculateDirectionalLighting(..., 1.0 - shadowFactor, ..., 0.0) passes 1.0 - (1.0 - shadowFactor) on to calculateLighting_Burley
         const f3 sunDir = mk3(fc.sunDir[0], fc.sunDir[1], fc.sunDir[2]), sunColor = mk3(fc.sunColor[0], fc.sunColor[1], fc.sunColor[2]);
-        color = color + calculateLightingBurley(fc, s, sunColor, sunDir, 0.0f, fsub(1.0f, fsub(1.0f, litFraction)), 1.0f, 0.0f);
+        color = color + calculateLightingBurley(fc, s, st, sunColor, sunDir, 0.0f, fsub(1.0f, fsub(1.0f, litFraction)), 1.0f, 0.0f);
     }
     const f3 result = vmin(color + emissive * da.emissionStrength, HALF_FLOAT_MAX);          // boundHDR (common.glsl:89-92)
     storeHalf4(out, p, result.x, result.y, result.z, 1.0f);

@@ -42,6 +42,7 @@ SGI_DEV f4 rectLinearHalf4(const uint2* __restrict__ plane, int W, int H, float 
 struct SsaoArgs {
     int W, H;
     float aspectRatio, projPlaneZDist, intensity;
+    float vectorScale;                 // 2 aspectRatio / (W projPlaneZDist) (ssao.fs:34): uniform, computed once on the host with the same IEEE operations
     const uint2* structure;            // half4 [H][W]
     const uint2* rotation;             // half4 [4][4]
     const unsigned short* occlusion;   // half [H][W] (blur pass input)
@@ -56,8 +57,8 @@ ssaoOccludeKernel(const __grid_constant__ SsaoArgs a) {
     const float w = (float)a.W, h = (float)a.H;
     // gl: fsTexCoords * vec2(windowWidth, windowHeight), fsTexCoords = (x + 0.5) / W (ssao.vs)
     const float pcx = fmul(fdiv(fadd((float)x, 0.5f), w), w), pcy = fmul(fdiv(fadd((float)y, 0.5f), h), h);
-    const float tau = fdiv(1.0f, 32.0f), dmax = 2.0f, r = 0.4f;
-    const float vectorScale = fdiv(fmul(2.0f, a.aspectRatio), fmul(w, a.projPlaneZDist));
+    const float tau = fdiv(1.0f, 32.0f), r = 0.4f;          // (dmax = 2.0: the division by it below is a multiplication by 0.5, the same rounding)
+    const float vectorScale = a.vectorScale;
     const float dx[4] = {fmul(0.25f, r), 0.0f, fmul(-0.75f, r), 0.0f};
     const float dy[4] = {0.0f, fmul(0.5f, r), 0.0f, -r};
 
@@ -85,7 +86,7 @@ ssaoOccludeKernel(const __grid_constant__ SsaoArgs a) {
         v.z = fsub(z, z0);
         const float c = vmax(fsub(dot(normal, normalize(v)), tau), 0.0f);
         const float fv = fsub(1.0f, fsqrt(fsub(1.0f, fmul(c, c))));
-        const float wv = saturate(fsub(1.0f, fdiv(dot(normal, v), dmax)));
+        const float wv = saturate(fsub(1.0f, fmul(dot(normal, v), 0.5f)));
         occlusion = fadd(occlusion, fmul(wv, fv));
         weight = fadd(weight, wv);
     }
@@ -136,6 +137,12 @@ int launchSsao(cudaStream_t stream, const BandDims& bd, const SgiSsaoParams& sp)
     SsaoArgs a;
     a.W = bd.W; a.H = bd.rows;
     a.aspectRatio = sp.aspectRatio; a.projPlaneZDist = sp.projPlaneZDist; a.intensity = sp.intensity;
+    {
+        // (volatile: every intermediate is rounded to binary32, whatever the host compiler would like to keep in a wider register)
+        volatile float num = 2.0f * sp.aspectRatio, den = (float)bd.W * sp.projPlaneZDist;
+        volatile float q = num / den;
+        a.vectorScale = q;
+    }
     a.structure = (const uint2*)sp.structureBuffer; a.rotation = (const uint2*)sp.rotationLookup;
     dim3 block(32, 8), grid((bd.W + 31) / 32, (bd.rows + 7) / 8);
     a.occlusion = nullptr; a.out = (unsigned short*)sp.occlusionScratch;

@@ -132,6 +132,42 @@ SGI_DEV int cubeTexel(f3 d, int res) {
     return (face * res + j) * res + i;
 }
 
+// ---- the same lookup as a two-tier decision (k_gather.cu, k_direct.cu) ------------------------------------------------------
+SGI_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SGI_DEV float rcpFast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+static __device__ __noinline__ int exactCubeTexel(f3 fragDir, int res) { return cubeTexel(fragDir, res); }      // (rarely executed)
+// Cube texel with exact semantics.  The face is chosen by exact comparisons of the inputs (GL 4.6 table 8.19: signs folded in with
+// bit operations, -0 as a major component only when the direction is all zeros, which the NaN of the estimate sends to the exact
+// chain).  The texel coordinates are estimated as se = fma(sc * rcp(ma), res/2, res/2) and only a coordinate within `eps` of a texel
+// edge needs the exact division chain of cubeTexel (sgi_math.cuh).  Bound: q = fl(sc/ma), qe = sc * rcp.approx(ma) differ by at most
+// |q| 2^-22 (1 ulp of the reciprocal, one product, one division); the exact chain fl(fl(fl(q + 1) / 2) res) is within
+// res (2^-25 + 2^-24) of (q + 1) res / 2 and the estimate within res 2^-24 of (qe + 1) res / 2, so |se - exact| <=
+// res (|q| 2^-23 + 2.5 * 2^-24) and eps = res 2^-22 (|qe| + 1) keeps a factor 1.6 to 2 over it.  (Round 1 used a flat 1e-4 texels,
+// round 2 first 3e-5: pixels that lie in the plane of a VPL — a floor pixel under a floor VPL — have |q| ~ 1e-6, that is se within
+// 1e-5 .. 1e-4 of the middle edge, and took the exact chain on 70 % of the warp iterations; profiles/r02k-q.)
+SGI_DEV int cubeTexelDecided(f3 d, int res, float halfRes, float epsK) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const bool xMajor = ax >= ay && ax >= az, yMajor = !xMajor && ay >= az;
+    const uint32_t bx = __float_as_uint(d.x), by = __float_as_uint(d.y), bz = __float_as_uint(d.z), kSign = 0x80000000u;
+    const float ma = xMajor ? ax : (yMajor ? ay : az);
+    const uint32_t major = xMajor ? bx : (yMajor ? by : bz);                                  // its sign bit: the negative face
+    const int face = (xMajor ? 0 : (yMajor ? 2 : 4)) + (int)(major >> 31);
+    // sc: +x: -z, -x: z | y: x | +z: x, -z: -x          tc: +y: z, -y: -z | others: -y
+    const float sc = __uint_as_float(xMajor ? (bz ^ (~bx & kSign)) : (yMajor ? bx : (bx ^ (bz & kSign))));
+    const float tc = __uint_as_float(yMajor ? (bz ^ (by & kSign)) : (by ^ kSign));
+    const float inv = rcpFast(ma);
+    const float qs = sc * inv, qt = tc * inv;
+    const float se = fma_(qs, halfRes, halfRes), te = fma_(qt, halfRes, halfRes);
+    const float sf = floorf(se), tf = floorf(te);
+    const float es = fma_(fabsf(qs), epsK, epsK), et = fma_(fabsf(qt), epsK, epsK);
+    // eps < frac < 1 - eps  <=>  |frac - 0.5| < 0.5 - eps   (false for a NaN estimate)
+    const bool sure = fabsf((se - sf) - 0.5f) < 0.5f - es && fabsf((te - tf) - 0.5f) < 0.5f - et;
+    if (!sure) return exactCubeTexel(d, res);
+    // a sure coordinate lies strictly inside [0, res): no clamp
+    return (face * res + (int)tf) * res + (int)sf;
+}
+
+
 // ---- binary16 planes --------------------------------------------------------------------------
 SGI_DEV float h2f(unsigned short h) { return __half2float(__ushort_as_half(h)); }
 SGI_DEV unsigned short f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }

@@ -16,6 +16,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __grid_constant__
 #define __launch_bounds__(...)
 
@@ -166,7 +167,6 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { sgiHostUnsupported("__sy
 #include <thread>
 #include <vector>
 #define __shared__ static
-#define __noinline__
 
 namespace sgihost {
 struct FlexBarrier {                  // the expected count is re-evaluated when a participant leaves
