@@ -309,7 +309,7 @@ int launchGather(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd,
 int launchCoordTables(cudaStream_t stream, const BandDims& bd, float* u /* [W] */, float2* row /* [rows] */);   // k_gather.cu: per-column / per-row texture coordinates
 int launchTemporal(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io);   // reads velocity / ids / normal / depth / prev* / prevGi / historyIn, writes historyOut + temporal
 bool planAtrousTma(const BandDims& bd, int s, int* x0, int* x1, int* y0, int* y1);                              // k_atrous_tma.cu: the rectangle its tiles would cover
-bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int nBorder);       // ... one launch: io.borderCtas, then the tiles
+bool launchAtrousTma(cudaStream_t stream, const BandDims& bd, const DenoiseIO& io, bool final_, int nBorder);       // ... one launch: the border CTAs of io (borderCta), then the tiles
 int launchPrepareGuide(cudaStream_t stream, const BandDims& bd, const uint32_t* normal, const float* depth, float4* guide);
 int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims& bd, const DenoiseIO& io, bool merge, bool final_,
                       bool* signalled /* out: the kernel releases the neighbours' flags itself */);
