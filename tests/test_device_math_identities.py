@@ -51,3 +51,61 @@ def test_plain_reciprocal_multiply_would_not_be_exact():
     # why the correction step exists
     b = np.arange(256, dtype=np.float32)
     assert np.any(b * (np.float32(1.0) / np.float32(255.0)) != b / np.float32(255.0))
+
+
+# ---- two-tier decisions of the gather (csrc/k_gather.cu, csrc/sgi_math.cuh): the cheap route may only answer when its answer is
+#      the exact route's.  Both properties are checked here against every estimate the stated error bound allows, in IEEE binary32
+#      arithmetic (numpy), so the claim does not depend on how a particular GPU rounds rcp.approx. -------------------------------
+
+def _ulp_step(x, k):
+    """x (float32 array, positive) moved by k units in the last place"""
+    return (x.view(np.int32) + np.int32(k)).view(np.float32)
+
+
+def test_pass0_epilogue_estimate_rounds_like_the_division_whenever_it_is_sure():
+    """mergedChannel (k_gather.cu): f2h(a / denom) for binary16 a, denom >= 1 is taken from q = a * rcp(denom) unless q is within
+    8 ulp of a binary16 rounding boundary or below binary16's normal range.  The stated bound: |q - fl(a / denom)| <= 4 ulp.  For
+    every binary16 a, a spread of denominators and every q within 4 ulp of the IEEE quotient: sure(q) implies f2h(q) == f2h(a / denom)."""
+    a = np.arange(1, 0x7c00, dtype=np.uint16).view(np.float16).astype(np.float32)                       # every positive finite binary16
+    rng = np.random.default_rng(3)
+    denoms = np.unique(np.concatenate([np.float16([1.0, 1.5, 2.0, 3.0, 5.999, 6.0, 65504.0]),
+                                       rng.uniform(1.0, 6.0, 60).astype(np.float16), rng.uniform(1.0, 60000.0, 20).astype(np.float16)])).astype(np.float32)
+    for d in denoms:
+        exact = a / d                                                                                      # IEEE binary32 division
+        want = exact.astype(np.float16).view(np.uint16)
+        for k in range(-4, 5):
+            q = _ulp_step(exact, k)
+            b = q.view(np.uint32)
+            sure = (((b + np.uint32(8) - np.uint32(0x1000)) & np.uint32(0x1fff)) > 16) & (q >= np.float32(6.2e-5))
+            got = q.astype(np.float16).view(np.uint16)
+            assert np.array_equal(got[sure], want[sure]), (float(d), k)
+        assert sure.mean() > 0.75 or d > 100         # (and the cheap route is the common one: the rest are quotients below binary16's normal range)
+
+
+def test_cube_texel_estimate_agrees_with_the_exact_chain_whenever_it_is_sure():
+    """cubeTexelDecided (sgi_math.cuh): texel coordinate floor(fl(fl(fl(sc / ma) + 1) * 0.5) * res) is taken from the estimate
+    se = fma(sc * r, res / 2, res / 2), r = rcp.approx(ma) (1 ulp), unless frac(se) is within eps = res 2^-22 (|q| + 1) of 0 or 1.
+    Random directions and the planes of the cube (sc / ma tiny), every reciprocal within 1 ulp: sure implies the same texel."""
+    rng = np.random.default_rng(11)
+    n = 400000
+    ma = rng.uniform(0.05, 400.0, n).astype(np.float32)
+    ratio = rng.uniform(-1.0, 1.0, n).astype(np.float32)
+    ratio[: n // 4] = (rng.uniform(-1.0, 1.0, n // 4) * 1e-5).astype(np.float32)                          # a pixel in the plane of its light
+    ratio[n // 4: n // 2] = (np.round(rng.uniform(-16, 16, n // 4)) / 16.0 + rng.uniform(-1, 1, n // 4) * 3e-6).astype(np.float32)   # next to texel edges
+    sc = (ratio * ma).astype(np.float32)
+    sc = np.clip(sc, -ma, ma)
+    for res in (32, 64, 17):
+        fres, half, epsk = np.float32(res), np.float32(0.5 * res), np.float32(res * 2.0 ** -22)
+        q = sc / ma
+        exact = np.floor((((q + np.float32(1.0)).astype(np.float32) * np.float32(0.5)).astype(np.float32) * fres).astype(np.float32))
+        exact = np.clip(exact, 0, res - 1)
+        r0 = (np.float32(1.0) / ma).astype(np.float32)
+        for k in (-1, 0, 1):
+            r = _ulp_step(r0, k)
+            qe = (sc * r).astype(np.float32)
+            se = (qe.astype(np.float64) * np.float64(half) + np.float64(half)).astype(np.float32)         # fma: one rounding
+            sf = np.floor(se)
+            eps = (np.abs(qe).astype(np.float64) * np.float64(epsk) + np.float64(epsk)).astype(np.float32)
+            sure = np.abs((se - sf) - np.float32(0.5)) < (np.float32(0.5) - eps)
+            assert np.array_equal(sf[sure], exact[sure]), (res, k, int((sf[sure] != exact[sure]).sum()))
+            assert sure.mean() > 0.7
