@@ -109,3 +109,50 @@ def test_cube_texel_estimate_agrees_with_the_exact_chain_whenever_it_is_sure():
             sure = np.abs((se - sf) - np.float32(0.5)) < (np.float32(0.5) - eps)
             assert np.array_equal(sf[sure], exact[sure]), (res, k, int((sf[sure] != exact[sure]).sum()))
             assert sure.mean() > 0.7
+
+
+def test_redraw_estimate_agrees_with_the_exact_chain_whenever_it_is_sure():
+    """behindOrOutOfRange (k_gather.cu): `dot(normal, normalize(l)) < 0 || length(l) > radius` (vpl_pbr_gi.fs:164-166) is answered from
+    s = n.l and |l|^2 (FMA) when s^2 > 1e-10 |l|^2 and |l|^2 is outside radius^2 (1 +- 4e-5).  Adversarial inputs — light directions
+    almost in the surface plane, distances within 1e-4 of the radius — and every estimate within 2 ulp of the FMA values: a sure
+    estimate gives the decision of the exact chain in glm's operation order."""
+    rng = np.random.default_rng(23)
+    n = 300000
+    f32 = np.float32
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = nrm.astype(f32)
+    l = rng.normal(size=(n, 3)) * rng.uniform(0.1, 80.0, (n, 1))
+    # a third of the directions nearly perpendicular to the normal
+    k = n // 3
+    perp = l[:k] - (l[:k] * nrm[:k]).sum(1, keepdims=True) * nrm[:k]
+    l[:k] = perp + nrm[:k] * (rng.uniform(-1, 1, (k, 1)) * 1e-5 * np.linalg.norm(perp, axis=1, keepdims=True))
+    l = l.astype(f32)
+    radius = np.linalg.norm(l.astype(np.float64), axis=1)
+    radius[k:2 * k] *= 1.0 + rng.uniform(-1, 1, k) * 1e-4                                                 # distance next to the radius
+    radius[2 * k:] *= rng.uniform(0.5, 2.0, n - 2 * k)
+    radius = radius.astype(f32)
+    lx, ly, lz = l[:, 0], l[:, 1], l[:, 2]
+    nx, ny, nz = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+    # exact chain, glm order: dot = (x + y) + z, length = sqrt(dot), normalize = v * (1 / sqrt(dot))
+    d = ((lx * lx + ly * ly).astype(f32) + lz * lz).astype(f32)
+    dist = np.sqrt(d).astype(f32)
+    inv = (f32(1.0) / dist).astype(f32)
+    side = (((nx * (lx * inv).astype(f32)).astype(f32) + (ny * (ly * inv).astype(f32)).astype(f32)).astype(f32) + (nz * (lz * inv).astype(f32)).astype(f32)).astype(f32)
+    exact = (side < 0) | (dist > radius)
+    # estimates: FMA chains (one rounding each), then every neighbour within 2 ulp
+    fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+    s0 = fma(nz, lz, fma(ny, ly, (nx * lx).astype(f32)))
+    d20 = fma(lz, lz, fma(ly, ly, (lx * lx).astype(f32)))
+    r2 = (radius * radius).astype(f32)
+    m = f32(1e-5)
+    for ks in (-2, 0, 2):
+        s = np.where(s0 != 0, (s0.view(np.int32) + np.int32(ks)).view(f32), s0)
+        for kd in (-2, 0, 2):
+            d2 = _ulp_step(d20, kd)
+            side_sure = (s * s).astype(f32) > ((m * m).astype(f32) * d2).astype(f32)
+            far = d2 > (r2 * (f32(1.0) + f32(4.0) * m)).astype(f32)
+            near = d2 < (r2 * (f32(1.0) - f32(4.0) * m)).astype(f32)
+            sure = side_sure & (far | near)
+            got = (s < 0) | far
+            assert np.array_equal(got[sure], exact[sure]), (ks, kd, int((got[sure] != exact[sure]).sum()))
+    assert sure.mean() > 0.5
