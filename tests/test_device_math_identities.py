@@ -156,3 +156,42 @@ def test_redraw_estimate_agrees_with_the_exact_chain_whenever_it_is_sure():
             got = (s < 0) | far
             assert np.array_equal(got[sure], exact[sure]), (ks, kd, int((got[sure] != exact[sure]).sum()))
     assert sure.mean() > 0.5
+
+
+def test_shadow_verdict_estimate_agrees_with_the_exact_chain_whenever_it_is_sure():
+    """shadeAcceptedLight (k_gather.cu): lit / shadowed is `currentDepth - currentDepth * bias > texelDepth * farPlane`
+    (calculateShadowValue1Sample, pbr.glsl:116-136).  The estimate uses |l| = d2 * rsqrt(d2) (<= 3 ulp), texel * (1 / 65535) (1 ulp)
+    and distance * (1 - bias), and answers only when the two sides differ by more than 8e-5 of the larger.  Texel depths placed
+    within 2e-4 of the decision, every estimate inside those bounds: a sure estimate gives the exact verdict."""
+    rng = np.random.default_rng(31)
+    f32 = np.float32
+    n = 300000
+    frag_dir = (rng.normal(size=(n, 3)) * rng.uniform(0.5, 200.0, (n, 1))).astype(f32)
+    lnd = (rng.uniform(-5.0, 40.0, n)).astype(f32)                       # dot(lightMinusFrag, normal): both sides of the 0.1 / 0.03 switch
+    far_plane = rng.uniform(50.0, 600.0, n).astype(f32)
+    x, y, z = frag_dir[:, 0], frag_dir[:, 1], frag_dir[:, 2]
+    d = ((x * x + y * y).astype(f32) + z * z).astype(f32)
+    cur = np.sqrt(d).astype(f32)                                          # length(fragDir), glm order
+    sat = np.clip(lnd, f32(0.0), f32(1.0))
+    bias_f = np.maximum(f32(0.1), (sat * f32(0.03)).astype(f32))
+    lhs_exact = (cur - (cur * bias_f).astype(f32)).astype(f32)
+    # a 16-bit texel whose depth * farPlane lands next to lhs (or anywhere, for a third of the samples)
+    target = lhs_exact.astype(np.float64) / far_plane * (1.0 + rng.uniform(-1, 1, n) * 2e-4)
+    target[: n // 3] = rng.uniform(0, 1, n // 3)
+    texel = np.clip(np.round(target * 65535.0), 0, 65535).astype(np.uint32)
+    depth_exact = (texel.astype(f32) / f32(65535.0)).astype(f32)
+    exact = lhs_exact > (depth_exact * far_plane).astype(f32)
+    d2 = (z.astype(np.float64) * z + (y.astype(np.float64) * y + (x * x).astype(f32))).astype(f32)       # FMA chain (one rounding each is finer than this)
+    dist0 = np.sqrt(d2.astype(np.float64)).astype(f32)
+    depth0 = (texel.astype(f32) * f32(1.0 / 65535.0)).astype(f32)
+    for kd in (-3, 0, 3):
+        dist = _ulp_step(dist0, kd)
+        for kt in (-1, 0, 1):
+            dep = np.where(texel > 0, _ulp_step(np.maximum(depth0, f32(1e-30)), kt), depth0)
+            lhs = (dist * (f32(1.0) - bias_f).astype(f32)).astype(f32)
+            rhs = (dep * far_plane).astype(f32)
+            gap = (lhs - rhs).astype(f32)
+            sure = np.abs(gap) > (f32(8.0) * f32(1e-5) * np.maximum(lhs, rhs)).astype(f32)
+            got = gap > 0
+            assert np.array_equal(got[sure], exact[sure]), (kd, kt, int((got[sure] != exact[sure]).sum()))
+    assert 0.3 < sure.mean() < 0.95                                       # (the adversarial two thirds really sit inside the margin)
