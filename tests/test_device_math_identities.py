@@ -195,3 +195,38 @@ def test_shadow_verdict_estimate_agrees_with_the_exact_chain_whenever_it_is_sure
             got = gap > 0
             assert np.array_equal(got[sure], exact[sure]), (kd, kt, int((got[sure] != exact[sure]).sum()))
     assert 0.3 < sure.mean() < 0.95                                       # (the adversarial two thirds really sit inside the margin)
+
+
+def test_stage2_pretests_only_drop_lights_the_exact_chain_drops():
+    """stage2Kernel (k_tiles.cu): before the exact chain of stage2.cs:86-94 a light is dropped when its FMA distance estimate says it is
+    surely beyond the tile's current threshold (d2e > radius^2 (1 + 4e-5) w^2 (1 + 1e-6)) or surely behind the tile
+    (n.l < 0 with (n.l)^2 > 1e-10 d2e).  Both must be conservative: a dropped light has exact ratio = length(l) / radius > w, or an
+    exact side check < 0.  Thresholds within 1e-4 of the true ratio and directions within 1e-5 of the tile plane."""
+    rng = np.random.default_rng(41)
+    f32 = np.float32
+    n = 300000
+    l = (rng.normal(size=(n, 3)) * rng.uniform(0.1, 60.0, (n, 1))).astype(f32)
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    k = n // 2
+    perp = l[:k].astype(np.float64) - (l[:k] * nrm[:k]).sum(1, keepdims=True) * nrm[:k]
+    l[:k] = (perp + nrm[:k] * (rng.uniform(-1, 1, (k, 1)) * 1e-5 * np.linalg.norm(perp, axis=1, keepdims=True))).astype(f32)
+    nrm = nrm.astype(f32)
+    lx, ly, lz = l[:, 0], l[:, 1], l[:, 2]
+    nx, ny, nz = nrm[:, 0], nrm[:, 1], nrm[:, 2]
+    d = ((lx * lx + ly * ly).astype(f32) + lz * lz).astype(f32)
+    radius = (np.sqrt(d.astype(np.float64)) * rng.uniform(0.8, 3.0, n)).astype(f32)
+    ratio = (np.sqrt(d).astype(f32) / radius).astype(f32)                                                  # fdiv(length(l), radius)
+    side = (((nx * lx).astype(f32) + (ny * ly).astype(f32)).astype(f32) + (nz * lz).astype(f32)).astype(f32)   # dot(normal, l), glm order
+    w = np.minimum(f32(1.0), (ratio.astype(np.float64) * (1.0 + rng.uniform(-1, 1, n) * 1e-4)).astype(f32))
+    w[::3] = rng.uniform(0.0, 1.0, len(w[::3])).astype(f32)
+    w2 = ((w * w).astype(f32) * (f32(1.0) + f32(1e-6))).astype(f32)
+    fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+    d2e0 = fma(lz, lz, fma(ly, ly, (lx * lx).astype(f32)))
+    se0 = fma(nz, lz, fma(ny, ly, (nx * lx).astype(f32)))
+    for kd in (-2, 0, 2):
+        d2e = _ulp_step(d2e0, kd)
+        far = d2e > (((radius * radius).astype(f32) * (f32(1.0) + f32(4e-5))).astype(f32) * w2).astype(f32)
+        assert (ratio[far] > w[far]).all(), kd
+        behind = (se0 < 0) & ((se0 * se0).astype(f32) > (f32(1e-10) * d2e).astype(f32))
+        assert (side[behind] < 0).all(), kd
+    assert far.mean() > 0.1 and behind.mean() > 0.1
