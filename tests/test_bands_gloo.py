@@ -85,13 +85,13 @@ def test_balanced_cuts_are_always_a_valid_partition():
     """Whatever the measured times, balance_cuts must return cuts on the 5-row tile grid that start at 0, end at the frame
     height, increase strictly and leave every band at least as tall as the halo — i.e. something bands_from_cuts accepts."""
     from hypothesis import given, settings, strategies as st
-    from stratusgfx_b200.bands import TILE, balance_cuts, bands_from_cuts, halo_rows, plan_bands
+    from stratusgfx_b200.bands import TILE, balance_cuts, bands_from_cuts, halo_rows, plan_bands, recompute_rows
 
     @settings(max_examples=200, deadline=None)
-    @given(world=st.sampled_from([2, 3, 4, 8]), tiles_per_band=st.integers(5, 120), iters=st.integers(1, 5),
+    @given(world=st.sampled_from([2, 3, 4, 8]), tiles_per_band=st.integers(5, 120), iters=st.integers(1, 5), recompute=st.booleans(),
            times=st.lists(st.floats(1e-3, 10.0, allow_nan=False, allow_infinity=False), min_size=8, max_size=8))
-    def check(world, tiles_per_band, iters, times):
-        halo = halo_rows(iters)
+    def check(world, tiles_per_band, iters, recompute, times):
+        halo = (recompute_rows if recompute else halo_rows)(iters)          # both halo modes of the band split (include/stratusgi.h)
         height = world * tiles_per_band * TILE
         if height // world < halo:
             return
