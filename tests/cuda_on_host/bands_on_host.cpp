@@ -22,6 +22,7 @@ struct State {
     std::vector<uint2> giColor, giReservoir;
     int gatherCounters[2] = {0, 0};
     bool kernelSignal = true;
+    bool recompute = false;          // SGI_HALO_RECOMPUTE (include/stratusgi.h)
 } *st = nullptr;
 
 // the slab layout of csrc/sgi_abi.cu allocPlanes for `rowsMax` held rows (the same in every band process of a test)
@@ -38,6 +39,18 @@ sgi::BandDims bandDims(const SgiHandle_& h) {
     bd.W = h.cp.width; bd.fullH = h.cp.full_height; bd.yOffset = h.cp.y_offset; bd.rows = h.cp.rows; bd.cubeRes = h.cp.cube_res; bd.csmRes = h.cp.csm_res;
     bd.c0 = h.banded ? h.band.compute_y0 - h.cp.y_offset : 0;
     bd.crows = h.banded ? h.band.compute_rows : h.cp.rows;
+    return bd;
+}
+// bandDimsForPass of csrc/sgi_abi.cu: the rows pass `pass` of a band that recomputes its halo covers
+sgi::BandDims bandDimsForPass(const SgiHandle_& h, int pass, bool recompute) {
+    sgi::BandDims bd = bandDims(h);
+    if (!h.banded || !recompute) return bd;
+    int ext = 0;
+    for (int j = pass + 1; j < h.cp.denoise_iters; ++j) ext += 2 << j;
+    const int up = ext < bd.c0 ? ext : bd.c0;
+    const int below = bd.rows - (bd.c0 + bd.crows);
+    const int down = ext < below ? ext : below;
+    bd.c0 -= up; bd.crows += up + down;
     return bd;
 }
 }  // namespace
@@ -57,6 +70,7 @@ extern "C" int host_band_init(int W, int fullH, int cubeRes, int csmRes, int ite
     h.offFlags = L.flags; h.flags = (int32_t*)(slab + L.flags); h.bandDone = h.flags + 4;
     h.banded = world > 1;
     h.band.compute_y0 = compute_y0; h.band.compute_rows = compute_rows; h.band.rank = rank; h.band.world = world; h.band.owns_frame_image = 0;
+    h.band.halo_mode = (kernelSignal & 2) ? SGI_HALO_RECOMPUTE : SGI_HALO_EXCHANGE;        // (bit 1 of the mode argument)
     const HostPeer* ps[2] = {up, down};
     for (int which = 0; which < 2; ++which) {
         if (!ps[which] || !ps[which]->present) continue;
@@ -71,7 +85,8 @@ extern "C" int host_band_init(int W, int fullH, int cubeRes, int csmRes, int ite
     st->guide.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
     st->temporal.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
     st->giColor.assign(n, make_uint2(0u, 0u)); st->giReservoir.assign(n, make_uint2(0u, 0u));
-    st->kernelSignal = kernelSignal != 0;
+    st->kernelSignal = (kernelSignal & 1) != 0;
+    st->recompute = (kernelSignal & 2) != 0;
     return 0;
 }
 
@@ -88,20 +103,23 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
     AtlasTable atl;
     for (int i = 0; i < SGI_MAX_TOTAL_SHADOW_ATLASES; ++i) { atl.shadow[i] = i < numAtlases ? (const unsigned short*)shadow[i] : nullptr; atl.diffuse[i] = nullptr; }
     // ---- sgi_gather ----
+    const bool recompute = h.banded && st->recompute;
     BandLinks links = noLinks();
     if (h.banded) {
         ++h.frameNo;
         const int prevDone = h.frameNo > 1 ? bandEpoch(h.frameNo - 1, iters) : 0;
-        links = bandLinks(&h, 0, false, prevDone);
-        if (st->kernelSignal) armInKernelSignal(&h, &links, bandEpoch(h.frameNo, 1));
+        if (!recompute) {          // (a band that recomputes its halo neither waits nor pushes here)
+            links = bandLinks(&h, 0, false, prevDone);
+            if (st->kernelSignal) armInKernelSignal(&h, &links, bandEpoch(h.frameNo, 1));
+        }
     }
     bool signalled = false;
     std::vector<float> coordU((size_t)bd.W);
     std::vector<float2> coordRow((size_t)bd.rows);
     launchCoordTables(nullptr, bd, coordU.data(), coordRow.data());
-    launchGather(nullptr, fc, bd, depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atl, st->giColor.data(), st->giReservoir.data(),
+    launchGather(nullptr, fc, bandDimsForPass(h, 0, recompute), depth, normal, albedo, refl, rma, ssao, updated, visible, entries, atl, st->giColor.data(), st->giReservoir.data(),
                  st->guide.data(), (uint2*)h.resA, links, nullptr, nullptr, st->gatherCounters, &h.gatherLaunches, &signalled, coordU.data(), coordRow.data());
-    if (h.banded && !signalled) signalNeighbours(&h, bandEpoch(h.frameNo, 1), false);
+    if (h.banded && !recompute && !signalled) signalNeighbours(&h, bandEpoch(h.frameNo, 1), false);
     // ---- sgi_denoise_pass 1 .. iters-1 (pass 0 was written by the gather) ----
     for (int pass = 1; pass < iters; ++pass) {
         const bool final_ = pass + 1 == iters;
@@ -117,7 +135,12 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
         io.combinedOut = (uint2*)combinedOutH4; io.giOut = (uint2*)h.giIllum[h.cur]; io.historyOut = (unsigned short*)h.history[h.cur];
         io.multiplier = (1 << pass) - 1;
         io.guide = st->guide.data();
-        if (h.banded) {
+        if (recompute) {           // only the final pass stores into the neighbours (GI rows) and releases their flags; it waits for nobody
+            if (final_) {
+                io.links = bandLinks(&h, pass % 2, true, 0);
+                if (st->kernelSignal) armInKernelSignal(&h, &io.links, bandEpoch(h.frameNo, pass + 1));
+            }
+        } else if (h.banded) {
             io.links = bandLinks(&h, pass % 2, final_, bandEpoch(h.frameNo, pass));
             if (st->kernelSignal) armInKernelSignal(&h, &io.links, bandEpoch(h.frameNo, pass + 1));
         }
@@ -136,9 +159,25 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
             launchTemporal(nullptr, fc, bd, tio);
         }
         signalled = false;
-        launchDenoisePass(nullptr, fc, bd, io, false, final_, &signalled);
-        if (h.banded && !signalled) signalNeighbours(&h, bandEpoch(h.frameNo, pass + 1), final_);
+        launchDenoisePass(nullptr, fc, bandDimsForPass(h, pass, recompute), io, false, final_, &signalled);
+        if (recompute && !final_) {}
+        else if (h.banded && !signalled) signalNeighbours(&h, bandEpoch(h.frameNo, pass + 1), final_);
         if (final_) h.cur ^= 1;
     }
     return h.flags[2];      // time-outs (none can occur here: clock64() is constant on the host, a dead-lock shows as a hang)
+}
+
+// Several frames in ONE call (tools/race_check_bands_on_host.py): between two frames the band thread does not return to the Python
+// interpreter, whose lock would otherwise order everything one band does in frame f before what another does in frame f + 1 and hide
+// a missing inter-frame wait from ThreadSanitizer.  ptrs: nFrames x 16 pointers in host_band_frame's order (depth .. entries, shadow).
+extern "C" int host_band_frames(int nFrames, const SgiFrameParams* fps, const void* const* ptrs, int numAtlases, void* const* combinedOut) {
+    int rc = 0;
+    for (int f = 0; f < nFrames; ++f) {
+        const void* const* p = ptrs + (size_t)f * 16;
+        rc |= host_band_frame(fps + f, (const float*)p[0], (const uint32_t*)p[1], (const uint32_t*)p[2], (const uint16_t*)p[3], (const uint32_t*)p[4],
+                              (const unsigned short*)p[5], (const uint32_t*)p[6], (const float*)p[7], p[8], (const uint32_t*)p[9], (const float*)p[10],
+                              (const float*)p[11], (const SgiVplData*)p[12], (const int32_t*)p[13], (const SgiAtlasEntry*)p[14],
+                              (const void* const*)p[15], numAtlases, combinedOut[f]);
+    }
+    return rc;
 }

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-W, H, FRAMES = 160, 240, 2
+W, H, FRAMES = 160, 240, 3      # (three frames: the GI ping-pong plane a final pass stores into is the one the neighbour's temporal pre-pass read two frames earlier)
 WORKLOAD = dict(workload="tiny", frames=FRAMES, yaw_deg_per_frame=1.5, height=H)
 
 
@@ -55,7 +55,7 @@ def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_si
     up, down = peer(rank - 1), peer(rank + 1)
     scene = Scene("tiny", height=H, yaw_deg_per_frame=1.5)
     L.host_band_init(W, H, scene.cube_res, scene.csm_res, scene.denoise_iters, rank, world, me.y0, me.rows, me.b0, me.b1 - me.b0,
-                     base[rank], rows_max, C.byref(up), C.byref(down), 1 if kernel_signal else 0)
+                     base[rank], rows_max, C.byref(up), C.byref(down), int(kernel_signal))          # bit 0: in-kernel signal, bit 1: SGI_HALO_RECOMPUTE
     sh, _ = scene.cubemaps()
     shp = _atlas_ptrs(sh)
     lit = np.ndarray((FRAMES, H, W, 4), np.float16, buffer=out.buf)
@@ -76,12 +76,12 @@ def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_si
         s.close()
 
 
-def _run(world, tables, kernel_signal, timeout=240):
+def _run(world, tables, kernel_signal, timeout=240, recompute=False):
     from multiprocessing import shared_memory
-    from stratusgfx_b200.bands import bands_from_cuts, halo_rows
+    from stratusgfx_b200.bands import bands_from_cuts, halo_rows, recompute_rows
     L = _load()
     cuts = {1: [0, H], 3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H], 8: list(range(0, H + 1, 30))}[world]      # (5: unequal bands, the balanced plan)
-    bands = bands_from_cuts(cuts, H, halo_rows(4))
+    bands = bands_from_cuts(cuts, H, (recompute_rows if recompute else halo_rows)(4))
     rows_max = max(b.rows for b in bands)
     slab_bytes = int(L.host_band_slab_bytes(W, rows_max))
     shms = [shared_memory.SharedMemory(create=True, size=slab_bytes) for _ in range(world)]
@@ -90,7 +90,7 @@ def _run(world, tables, kernel_signal, timeout=240):
         for s in shms:
             np.ndarray(slab_bytes, np.uint8, buffer=s.buf)[:] = 0
         ctx = mp.get_context("spawn")
-        procs = [ctx.Process(target=_band_worker, args=(r, bands, [s.name for s in shms], slab_bytes, rows_max, tables, kernel_signal, out.name))
+        procs = [ctx.Process(target=_band_worker, args=(r, bands, [s.name for s in shms], slab_bytes, rows_max, tables, (1 if kernel_signal else 0) | (2 if recompute else 0), out.name))
                  for r in range(world)]
         for p in procs:
             p.start()
@@ -131,5 +131,19 @@ def test_bands_with_middle_ranks_reproduce_the_whole_frame_bytes(whole_frame, wo
         pytest.skip("host-launched signals (the path the 4- and 8-GPU hardware runs used): set SGI_HOST_SUITE=full")
     tables, want = whole_frame
     got = _run(world, tables, kernel_signal)
+    for f in range(FRAMES):
+        assert np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)), f
+
+
+@pytest.mark.parametrize("world", [3, 4, 5])
+def test_bands_that_recompute_their_halo_reproduce_the_whole_frame_bytes(whole_frame, world):
+    """SGI_HALO_RECOMPUTE with middle bands, one process per band: the gather and the non-final passes run on the halo rows the later
+    passes read, nothing is exchanged inside the frame; the final pass stores its GI rows into the neighbours and releases their
+    flags, the temporal pre-pass waits for the neighbours' previous frame.  Three frames, so that a final pass stores into the GI
+    plane the neighbour's pre-pass read two frames before (the wait above is what orders the two)."""
+    if world == 5 and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("5 unequal bands of 40-60 rows with 30-row halos: set SGI_HOST_SUITE=full")
+    tables, want = whole_frame
+    got = _run(world, tables, True, recompute=True)
     for f in range(FRAMES):
         assert np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)), f

@@ -9,7 +9,16 @@ and csrc/sgi_internal.h (fence, producer count, last producer releases the flag;
 ThreadSanitizer reports any pair of accesses the protocol does not order — a missing wait, a flag released before the last producer's
 stores, a halo overwritten while the neighbour may still read it.
 
-    python tools/race_check_bands_on_host.py [bands=4] [kernel|host]      # re-executes itself under LD_PRELOAD=libtsan.so
+    python tools/race_check_bands_on_host.py [bands=4] [kernel|host] [exchange|recompute]      # re-executes itself under LD_PRELOAD=libtsan.so
+
+`recompute` = SGI_HALO_RECOMPUTE: the bands compute the non-final passes on their halo rows themselves; what is left to order is the
+final pass's GI rows (stored into the neighbours, read by their temporal pre-pass of the next frame, overwritten two frames later),
+which is why the check runs three frames, all of them inside ONE library call per band (the interpreter lock would otherwise order
+everything across frames).  Limit, observed: with the pre-pass's wait for the neighbours' previous frame REMOVED, ThreadSanitizer
+still reports nothing in this mode — every band executes sequentially consistent fences on its signal path (`__threadfence_system`),
+which ThreadSanitizer treats as synchronisation between all threads, so an access pair a whole frame apart is always "ordered" for
+it.  The intra-pass waits of the exchange mode are checked by this tool (a removed wait is reported); the inter-frame GI rows rest on
+the ordering argument of DESIGN.md section 6 and on the byte comparisons of tests/test_bands_lockstep_on_host.py and the GPU suite.
 """
 import ctypes as C
 import os
@@ -20,12 +29,13 @@ import threading
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-W, H, FRAMES = 160, 240, 2
+W, H, FRAMES = 160, 240, 3
 
 
 def main():
     world = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     kernel_signal = (sys.argv[2] if len(sys.argv) > 2 else "kernel") == "kernel"
+    recompute = (sys.argv[3] if len(sys.argv) > 3 else "exchange") == "recompute"
     from tests.cuda_on_host.host_tu import BUILD, compile_wrapper
     if os.environ.get("SGI_TSAN_CHILD") != "1":
         so = compile_wrapper(("vpl_on_host.cpp", "gather_on_host.cpp", "denoise_lockstep_on_host.cpp", "bands_on_host.cpp"),
@@ -41,7 +51,7 @@ def main():
     import numpy as np
     from oracle.oracle_py import _atlas_ptrs
     from stratusgfx_b200._abi import FrameParams
-    from stratusgfx_b200.bands import bands_from_cuts, halo_rows
+    from stratusgfx_b200.bands import bands_from_cuts, halo_rows, recompute_rows
     from stratusgfx_b200.scene import Scene
     from tests.parity_util import SceneData, run_oracle
     from tests.test_bands_lockstep_on_host import HostPeer
@@ -50,7 +60,7 @@ def main():
     orc = run_oracle(d, keep_passes=False)
     tables = [tuple(np.ascontiguousarray(o[k]) for k in ("updated", "visible", "entries")) for o in orc]
     cuts = {3: [0, 80, 160, H], 4: [0, 60, 120, 180, H], 5: [0, 40, 95, 140, 200, H], 8: list(range(0, H + 1, 30))}[world]
-    bands = bands_from_cuts(cuts, H, halo_rows(4))
+    bands = bands_from_cuts(cuts, H, (recompute_rows if recompute else halo_rows)(4))
     rows_max = max(b.rows for b in bands)
     libs = []
     for r in range(world):                                   # one DSO per band: its own runtime state and __shared__ statics
@@ -60,6 +70,7 @@ def main():
         L.host_band_slab_bytes.restype = C.c_int64
         L.host_band_init.argtypes = [C.c_int] * 11 + [C.c_void_p, C.c_int, C.POINTER(HostPeer), C.POINTER(HostPeer), C.c_int]
         L.host_band_frame.argtypes = [C.POINTER(FrameParams)] + [C.c_void_p] * 16 + [C.c_int, C.c_void_p]
+        L.host_band_frames.argtypes = [C.c_int, C.POINTER(FrameParams), C.c_void_p, C.c_int, C.c_void_p]
         libs.append(L)
     slab_bytes = int(libs[0].host_band_slab_bytes(W, rows_max))
     slabs = [np.zeros(slab_bytes, np.uint8) for _ in range(world)]
@@ -92,14 +103,22 @@ def main():
             b, L = bands[r], libs[r]
             up, down = peer(r - 1), peer(r + 1)
             L.host_band_init(W, H, scene.cube_res, scene.csm_res, scene.denoise_iters, r, world, b.y0, b.rows, b.b0, b.b1 - b.b0,
-                             slabs[r].ctypes.data, rows_max, C.byref(up), C.byref(down), 1 if kernel_signal else 0)
+                             slabs[r].ctypes.data, rows_max, C.byref(up), C.byref(down), (1 if kernel_signal else 0) | (2 if recompute else 0))
+            # all frames in ONE library call: the interpreter lock is not touched between two frames, so the only thing that orders
+            # a neighbour's stores of frame f against this band's reads of frame f + 1 (and its stores of frame f + 2) is the protocol
+            combined = [np.zeros((b.rows, W, 4), np.float16) for _ in range(FRAMES)]
+            ptrs = (C.c_void_p * (16 * FRAMES))()
             for f in range(FRAMES):
-                combined = np.zeros((b.rows, W, 4), np.float16)
                 updated, visible, entries = tables[f]
-                rc = L.host_band_frame(C.byref(fps[f]), *[a.ctypes.data for a in inputs[r][f]], updated.ctypes.data, visible.ctypes.data,
-                                       entries.ctypes.data, C.addressof(shp), sh.shape[0], combined.ctypes.data)
-                assert rc == 0
-                lit[f, b.b0:b.b1] = combined[b.owned]
+                vals = [a.ctypes.data for a in inputs[r][f]] + [updated.ctypes.data, visible.ctypes.data, entries.ctypes.data, C.addressof(shp)]
+                for k, v in enumerate(vals):
+                    ptrs[16 * f + k] = v
+            outs = (C.c_void_p * FRAMES)(*[c.ctypes.data for c in combined])
+            fp_arr = (FrameParams * FRAMES)(*fps)
+            rc = L.host_band_frames(FRAMES, fp_arr, ptrs, sh.shape[0], outs)
+            assert rc == 0
+            for f in range(FRAMES):
+                lit[f, b.b0:b.b1] = combined[f][b.owned]
         except Exception as e:          # noqa: BLE001
             errors.append((r, repr(e)))
 
@@ -114,7 +133,7 @@ def main():
     for f in range(FRAMES):
         rep = compare_radiance(lit[f], orc[f]["combined"], 3)
         assert rep["ok"] and rep["bit_exact"] > 0.99, (f, rep)
-    print(f"{world} bands as threads, {'in-kernel' if kernel_signal else 'host-launched'} signals, {FRAMES} frames: THREAD SANITIZER: NO REPORT")
+    print(f"{world} bands as threads, {'recomputed halos' if recompute else 'exchanged halos'}, {'in-kernel' if kernel_signal else 'host-launched'} signals, {FRAMES} frames: THREAD SANITIZER: NO REPORT")
     return 0
 
 
