@@ -15,9 +15,10 @@ stores, a halo overwritten while the neighbour may still read it.
 final pass's GI rows (stored into the neighbours, read by their temporal pre-pass of the next frame, overwritten two frames later),
 which is why the check runs three frames, all of them inside ONE library call per band (the interpreter lock would otherwise order
 everything across frames).  Limit, observed: with the pre-pass's wait for the neighbours' previous frame REMOVED, ThreadSanitizer
-still reports nothing in this mode — every band executes sequentially consistent fences on its signal path (`__threadfence_system`),
-which ThreadSanitizer treats as synchronisation between all threads, so an access pair a whole frame apart is always "ordered" for
-it.  The intra-pass waits of the exchange mode are checked by this tool (a removed wait is reported); the inter-frame GI rows rest on
+still reports nothing in this mode.  The cause was not established; the stores and the reads in question are a whole frame apart —
+hundreds of thousands of short-lived emulation threads (one OS thread per CUDA thread of every CTA) — which is probably more history
+than ThreadSanitizer keeps.  So this mode shows that nothing ELSE is shared between the bands, not that the inter-frame wait is needed.
+The intra-pass waits of the exchange mode are checked by this tool (a removed wait is reported); the inter-frame GI rows rest on
 the ordering argument of DESIGN.md section 6 and on the byte comparisons of tests/test_bands_lockstep_on_host.py and the GPU suite.
 """
 import ctypes as C
