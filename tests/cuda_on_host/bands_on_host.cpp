@@ -5,6 +5,7 @@
 // in-kernel waits and signals (producer counting, boundary-first order, epochs) neither dead-lock nor let a pass read a halo row
 // before its neighbour stored it — with MIDDLE bands, which a 2-GPU run does not have.
 #define SGI_HOST_LOCKSTEP
+#include <unistd.h>
 #include <vector>
 #include "cuda_host_shim.h"
 #include "sgi_band.cu"             // tests/cuda_on_host/_build/sgi_band.cu (namespace sgi part only)
@@ -24,6 +25,10 @@ struct State {
     bool kernelSignal = true;
     bool recompute = false;          // SGI_HALO_RECOMPUTE (include/stratusgi.h)
 } *st = nullptr;
+// test hooks (host_band_test_hooks): this band sleeps before every final pass; the temporal pre-pass skips its wait for the neighbours'
+// previous frame.  Together they show that the wait is what keeps a late neighbour's GI rows out of this band's reprojected reads.
+int gDelayFinalSeconds = 0;
+bool gDropInterFrameWait = false;
 
 // the slab layout of csrc/sgi_abi.cu allocPlanes for `rowsMax` held rows (the same in every band process of a test)
 struct Layout { int64_t res[2], gi[2], hist[2], flags, total; };
@@ -54,6 +59,8 @@ sgi::BandDims bandDimsForPass(const SgiHandle_& h, int pass, bool recompute) {
     return bd;
 }
 }  // namespace
+
+extern "C" void host_band_test_hooks(int delayFinalSeconds, int dropInterFrameWait) { gDelayFinalSeconds = delayFinalSeconds; gDropInterFrameWait = dropInterFrameWait != 0; }
 
 extern "C" int64_t host_band_slab_bytes(int W, int rowsMax) { return layoutOf(W, rowsMax).total; }
 
@@ -152,12 +159,13 @@ extern "C" int host_band_frame(const SgiFrameParams* fp, const float* depth, con
             tio.links = noLinks();
             if (h.banded) {
                 tio.links.reprojMisses = h.flags + 3;
-                if (h.frameNo > 1)
+                if (h.frameNo > 1 && !gDropInterFrameWait)
                     launchWaitFlags(nullptr, h.peer[SGI_PEER_UP].attached ? h.flags + 0 : nullptr, h.peer[SGI_PEER_DOWN].attached ? h.flags + 1 : nullptr,
                                     bandEpoch(h.frameNo - 1, iters), h.flags + 2);
             }
             launchTemporal(nullptr, fc, bd, tio);
         }
+        if (final_ && gDelayFinalSeconds > 0) sleep((unsigned)gDelayFinalSeconds);
         signalled = false;
         launchDenoisePass(nullptr, fc, bandDimsForPass(h, pass, recompute), io, false, final_, &signalled);
         if (recompute && !final_) {}

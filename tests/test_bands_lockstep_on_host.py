@@ -36,7 +36,7 @@ def _load():
     return L
 
 
-def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_signal, out_name):
+def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_signal, out_name, hooks=None):
     """One band process: attach every slab, run FRAMES frames, leave the lit owned rows in the output block."""
     from multiprocessing import shared_memory
     from oracle.oracle_py import _atlas_ptrs
@@ -56,6 +56,8 @@ def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_si
     scene = Scene("tiny", height=H, yaw_deg_per_frame=1.5)
     L.host_band_init(W, H, scene.cube_res, scene.csm_res, scene.denoise_iters, rank, world, me.y0, me.rows, me.b0, me.b1 - me.b0,
                      base[rank], rows_max, C.byref(up), C.byref(down), int(kernel_signal))          # bit 0: in-kernel signal, bit 1: SGI_HALO_RECOMPUTE
+    if hooks is not None:            # (delay of this rank's final passes in seconds, drop the inter-frame wait) per rank
+        L.host_band_test_hooks(int(hooks[rank][0]), int(hooks[rank][1]))
     sh, _ = scene.cubemaps()
     shp = _atlas_ptrs(sh)
     lit = np.ndarray((FRAMES, H, W, 4), np.float16, buffer=out.buf)
@@ -76,7 +78,7 @@ def _band_worker(rank, bands, shm_names, slab_bytes, rows_max, tables, kernel_si
         s.close()
 
 
-def _run(world, tables, kernel_signal, timeout=240, recompute=False):
+def _run(world, tables, kernel_signal, timeout=240, recompute=False, hooks=None):
     from multiprocessing import shared_memory
     from stratusgfx_b200.bands import bands_from_cuts, halo_rows, recompute_rows
     L = _load()
@@ -90,7 +92,7 @@ def _run(world, tables, kernel_signal, timeout=240, recompute=False):
         for s in shms:
             np.ndarray(slab_bytes, np.uint8, buffer=s.buf)[:] = 0
         ctx = mp.get_context("spawn")
-        procs = [ctx.Process(target=_band_worker, args=(r, bands, [s.name for s in shms], slab_bytes, rows_max, tables, (1 if kernel_signal else 0) | (2 if recompute else 0), out.name))
+        procs = [ctx.Process(target=_band_worker, args=(r, bands, [s.name for s in shms], slab_bytes, rows_max, tables, (1 if kernel_signal else 0) | (2 if recompute else 0), out.name, hooks))
                  for r in range(world)]
         for p in procs:
             p.start()
@@ -147,3 +149,18 @@ def test_bands_that_recompute_their_halo_reproduce_the_whole_frame_bytes(whole_f
     got = _run(world, tables, True, recompute=True)
     for f in range(FRAMES):
         assert np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)), f
+
+
+@pytest.mark.parametrize("drop_wait", [False, True], ids=["wait", "no-wait"])
+def test_the_inter_frame_wait_is_what_orders_a_late_neighbours_gi_rows(whole_frame, drop_wait):
+    """SGI_HALO_RECOMPUTE leaves ONE dependency between bands: the temporal pre-pass of frame f + 1 reads GI halo rows the neighbours'
+    final passes of frame f stored, and waits for their "frame complete" flag first.  Band 1 of 3 is made late (it sleeps before each
+    of its final passes).  With the wait the frames are still the one-handle bytes; with the wait dropped (test hook) bands 0 and 2
+    run ahead, read the rows before they are there, and the bytes differ — so the comparison above is sensitive to that wait."""
+    if os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("a minute per case (band 1 sleeps): set SGI_HOST_SUITE=full")
+    tables, want = whole_frame
+    hooks = [(0, drop_wait), (4, drop_wait), (0, drop_wait)]
+    got = _run(3, tables, True, recompute=True, hooks=hooks)
+    same = all(np.array_equal(got[f].view(np.uint16), want[f].view(np.uint16)) for f in range(FRAMES))
+    assert same != drop_wait
