@@ -95,6 +95,16 @@ def test_gpu_suite_edge_cases_on_the_host(built, name):
         getattr(G, name)(built)
 
 
+def test_tile_list_gather_with_full_lists_on_the_host(built):
+    """tests/test_parity_gpu.py::test_tile_list_gather_mode_with_full_lists, ten rows of its c3 band (every tile holds 12 VPLs)."""
+    if os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("27 s on the host: set SGI_HOST_SUITE=full")
+    from tests import test_parity_gpu as G
+    with gpu_tests_on_the_host():
+        rep, counts = G.check_tile_list_band("c3", 700, 10)
+    assert counts.min() == 12
+
+
 @pytest.mark.parametrize("iters", [1, 3])
 def test_denoise_iteration_count_on_the_host(tiny, iters):
     from tests import test_parity_gpu as G

@@ -88,6 +88,48 @@ def test_tile_list_gather_mode(built):
     gp.close()
 
 
+def check_tile_list_band(workload, y0, rows):
+    """One band of `workload` in SGI_GATHER_TILE_LIST mode, stage by stage against the oracle on the same band (the tile
+    lists are per tile and the gather per pixel, so a band is the whole frame's rows).  -> (report, stage-2 counts)"""
+    from oracle.oracle_py import OracleFrame
+    from stratusgfx_b200.gipass import VplGiPass
+    from stratusgfx_b200.scene import Scene
+    s = Scene(workload)
+    W, H = s.width, s.height
+    vd, at = s.vpls(); sh, df = s.cubemaps(); csm = s.csm(0); fp = s.frame_params(0)
+    fp.gatherMode = _abi.GATHER_TILE_LIST
+    gb, pgb = s.gbuffer(0, y0, rows), s.gbuffer(-1, y0, rows)
+    gp = VplGiPass(W, H, y0, rows, s.cube_res, s.csm_res, s.denoise_iters)
+    gp.set_vpls(vd, at); gp.set_atlases(sh, df); gp.set_csm(csm); gp.set_gbuffer(gb, pgb); gp.bind()
+    gp.cull(fp); V = gp.visible_count(); gp.color(fp); gp.tile_lists(fp); gp.gather(fp)
+    res = gp.plane(_abi.PLANE_GI_RESERVOIR)
+    gp.denoise(fp)
+    cu = dict(V=V, visible=gp.output("vplVisibleIndices"), updated=gp.output("vplUpdatedData"), entries=gp.output("shadowDiffuseIndices"),
+              stage1=gp.output("vplStage1Results"), stage2=gp.output("vplVisiblePerTile"), gi_color=gp.plane(_abi.PLANE_GI_COLOR),
+              gi_reservoir=res, combined=gp.output("lightingOut"), gi_illum=gp.plane(_abi.PLANE_GI_ILLUM),
+              history=gp.plane(_abi.PLANE_HISTORY), pass_reservoirs=[])
+    gp.close()
+    o = OracleFrame(W, rows, s.cube_res, s.csm_res, s.denoise_iters, y_offset=y0, full_height=H)
+    o.frame(fp, gb, pgb, vd, at, csm, sh, df)
+    orc = dict(visible=o.visible, updated=o.updated, entries=o.entries, stage1=o.stage1, stage2=o.stage2, gi_color=o.gi_color,
+               gi_reservoir=o.gi_reservoir, pass_reservoirs=[], combined=o.combined, gi_illum=o.gi_illum, history=o.history)
+    rep, bad = compare_frame(cu, orc)
+    assert not bad, bad
+    assert rep["stage2_lists_exact"]
+    w = res[..., 3].astype(np.float32)
+    assert w.min() >= 1.0 and w.max() <= 12.0
+    return rep, cu["stage2"][:, 0]
+
+
+def test_tile_list_gather_mode_with_full_lists(built):
+    """The tile-list mode where the lists are long: c3 (1920x1080, 1024 VPLs) and c4 (3840x2160, 2048 VPLs), a band of the
+    floor / column rows each.  Most tiles hold the full 12 entries there, so the shared-memory staging of the 5x5-tile
+    neighbourhood and the 12-light shading loop see the lengths that tiny and c1 never reach."""
+    for wl, y0, rows in (("c3", 700, 135), ("c4", 1400, 90)):
+        rep, counts = check_tile_list_band(wl, y0, rows)
+        assert counts.max() == 12 and np.mean(counts == 12) > 0.5, (wl, np.bincount(counts, minlength=13))
+
+
 def test_fused_frame_call_equals_staged_calls(tiny):
     staged = run_cuda_staged(tiny)
     gp = make_pass(tiny)
