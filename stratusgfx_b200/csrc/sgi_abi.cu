@@ -640,6 +640,11 @@ int sgi_frame(SgiHandle h, const SgiFrameParams* fp) {
         }
     }
     if (rc == SGI_OK) rc = sgi_denoise(h, fp);
+    if (rc != SGI_OK && h->temporalForked) {
+        // the final pass, which joins the pre-pass, was not reached: join it here, it reads the caller's G-buffer planes
+        cudaStreamWaitEvent(h->stream, h->evTemporal, 0);
+        h->temporalForked = false; h->temporalDone = false;
+    }
     if (fork) {
         const std::string keep = h->lastError;
         const cudaError_t e = cudaStreamWaitEvent(h->stream, h->evJoin, 0);
@@ -683,7 +688,7 @@ int sgi_download_plane(SgiHandle h, int32_t which, void* host_dst, int64_t bytes
     void* p = nullptr; int64_t n = 0;
     const int rc = sgi_get_plane(h, which, &p, &n);
     if (rc != SGI_OK) return rc;
-    if (bytes > n) return fail(h, SGI_ERR_INVALID_ARG, "sgi_download_plane: more bytes requested than the plane holds");
+    if (bytes < 0 || bytes > n) return fail(h, SGI_ERR_INVALID_ARG, "sgi_download_plane: negative size or more bytes requested than the plane holds");
     SGI_CUDA(h, cudaSetDevice(h->cp.device));
     SGI_CUDA(h, cudaMemcpyAsync(host_dst, p, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
     SGI_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -69,7 +69,8 @@ _FAST = ["test_reference_method_names_drive_the_same_path", "test_zero_lights_is
 # (45-50 s each on the host since the gather's per-pixel work grew tables and prefetches: sgi_frame against staged calls is also
 # covered by test_staged_calls_and_sgi_frame_through_the_host_built_abi, the early cull by the GPU suite)
 _SLOW = ["test_fused_frame_call_equals_staged_calls", "test_early_cull_gives_the_frames_of_the_serial_order",
-         "test_gather_modes_can_alternate_on_one_handle", "test_cuda_integer_outputs_match_the_glm_golden_fixture"]
+         "test_gather_modes_can_alternate_on_one_handle", "test_cuda_integer_outputs_match_the_glm_golden_fixture",
+         "test_frame_that_fails_in_its_last_pass_leaves_a_usable_handle"]
 _FAST_BUILT = ["test_no_visible_vpl", "test_resize_then_run"]
 _SLOW_BUILT = ["test_single_vpl_and_two_vpls", "test_more_visible_vpls_than_the_per_frame_cap", "test_tile_list_gather_mode",
                "test_row_bands_with_apron_reproduce_the_whole_frame"]

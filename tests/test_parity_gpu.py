@@ -379,6 +379,24 @@ def test_unbound_buffers_and_bad_passes_are_errors(tiny):
     gp.close(); gp2.close()
 
 
+def test_frame_that_fails_in_its_last_pass_leaves_a_usable_handle(tiny):
+    """sgi_frame without a `screen` plane fails in the final denoise pass, after the tile stages and the temporal pre-pass were
+    forked onto their side streams: the error comes back, the side streams are joined (they read the caller's planes), and the
+    handle gives the frame's bytes once the plane is bound."""
+    from stratusgfx_b200.gipass import StratusGiError
+    want = run_cuda_staged(tiny, frames=1)[0]
+    gp = make_pass(tiny)
+    gp.set_gbuffer(tiny.gb[0], tiny.gb[-1])
+    screen = gp.t.pop("screen"); gp.bind()
+    with pytest.raises(StratusGiError, match="screen"):
+        gp.frame(tiny.fp[0])
+    gp.t["screen"] = screen; gp.reset_history(); gp.bind()
+    gp.frame(tiny.fp[0])
+    assert np.array_equal(gp.output("lightingOut").view(np.uint16), want["combined"].view(np.uint16))
+    assert np.array_equal(gp.plane(_abi.PLANE_HISTORY).view(np.uint16), want["history"].view(np.uint16))
+    gp.close()
+
+
 def test_resize_then_run(built):
     d = SceneData("tiny", frames=1)
     gp = make_pass(d)
