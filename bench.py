@@ -800,7 +800,7 @@ def run_views(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 100 frames for the CUDA path, a timed region of about 0.1 s on c4; 20 bounded samples for --impl reference)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4", choices=["tiny", "c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -814,6 +814,9 @@ def main():
     ap.add_argument("--bands", default="recompute", choices=["recompute", "p2p", "apron", "isolated"],
                     help="multi-GPU halo strategy (N > 1). recompute (default): SGI_HALO_RECOMPUTE, the bands compute the non-final passes on their halo rows themselves; p2p: SGI_HALO_EXCHANGE, the neighbours' kernels store every pass's boundary rows; apron: plain handles, NCCL gather; isolated: band handles without neighbours, a timing diagnosis whose seams are wrong")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 100 if args.impl == "ours" else 20
+    args.steps = max(args.steps, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
