@@ -106,6 +106,15 @@ def test_tile_list_gather_with_full_lists_on_the_host(built):
     assert counts.min() == 12
 
 
+def test_ragged_frame_size_on_the_host(built):
+    """tests/test_parity_gpu.py::test_ragged_frame_sizes at 170 x 95 (no size is a multiple of a warp segment, a CTA or a spacing)."""
+    if os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("25 s on the host: set SGI_HOST_SUITE=full")
+    from tests import test_parity_gpu as G
+    with gpu_tests_on_the_host():
+        G.test_ragged_frame_sizes(built, 170, 95)
+
+
 @pytest.mark.parametrize("iters", [1, 3])
 def test_denoise_iteration_count_on_the_host(tiny, iters):
     from tests import test_parity_gpu as G

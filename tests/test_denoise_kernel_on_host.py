@@ -64,7 +64,8 @@ def test_denoiser_kernels_on_the_host_match_the_oracle(host_denoiser, yaw):
 
 
 @pytest.mark.parametrize("W,rows,c0,crows,s", [(3840, 2160, 0, 2160, 2), (3840, 2160, 0, 2160, 8), (3840, 330, 30, 270, 8), (3840, 330, 6, 318, 2),
-                                               (3840, 300, 0, 298, 4), (1920, 420, 30, 360, 4), (640, 360, 0, 360, 8), (100, 77, 5, 60, 2)])
+                                               (3840, 300, 0, 298, 4), (1920, 420, 30, 360, 4), (640, 360, 0, 360, 8), (100, 77, 5, 60, 2),
+                                               (170, 95, 0, 95, 2), (170, 95, 0, 95, 4), (1370, 770, 0, 770, 4), (1370, 770, 0, 770, 8), (1370, 330, 30, 270, 8)])
 def test_border_ctas_are_enumerated_exactly_once(host_denoiser, W, rows, c0, crows, s):
     """A pass whose interior goes through the TMA tiles launches, ahead of the tiles, the CTAs of the clamped grid that reach outside the
     tiles' rectangle (csrc/sgi_denoise.cuh: borderGeometry / borderCtaCount / borderCta — arithmetic, no device list).  For whole

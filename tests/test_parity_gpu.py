@@ -130,6 +130,16 @@ def test_tile_list_gather_mode_with_full_lists(built):
         assert counts.max() == 12 and np.mean(counts == 12) > 0.5, (wl, np.bincount(counts, minlength=13))
 
 
+@pytest.mark.parametrize("width,height", [(170, 95), (165, 95), (1370, 770)])
+def test_ragged_frame_sizes(built, width, height):
+    """Sizes that are multiples of the 5-pixel tile only: 170 and 1370 columns leave 2 columns beyond the last whole multiple of
+    the à-trous spacings 4 and 8 (they and the 2 leftover rows of 770 go to the border CTAs next to the TMA tiles), an odd width
+    has no 16-byte row pitch for a tensor map (every pass through the clamped global-memory kernel), and none of the sizes is a
+    multiple of the 32-pixel segments of the gather or of the 8-row CTAs of the temporal pre-pass.  Two frames of a turning camera."""
+    d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.0, width=width, height=height)
+    _assert_parity(run_cuda_staged(d), run_oracle(d))
+
+
 def test_fused_frame_call_equals_staged_calls(tiny):
     staged = run_cuda_staged(tiny)
     gp = make_pass(tiny)
