@@ -70,6 +70,13 @@ def test_header_declares_exactly_the_python_symbol_list():
     assert _declared_symbols() == sorted(_abi.ABI_SYMBOLS)
 
 
+def test_integration_notes_name_every_entry_point():
+    """INTEGRATION.md section 1 is the table a maintainer reads: every entry point of the header has a row there."""
+    text = open(os.path.join(os.path.dirname(HEADER), "..", "INTEGRATION.md")).read()
+    missing = [sym for sym in _declared_symbols() if sym not in text]
+    assert not missing, missing
+
+
 @pytest.fixture(scope="module")
 def native_lib():
     from stratusgfx_b200.build import build_native
