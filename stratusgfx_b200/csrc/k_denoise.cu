@@ -226,7 +226,7 @@ int launchDenoisePass(cudaStream_t stream, const FrameConsts& fc, const BandDims
         const int s = 1 + io.multiplier;
         const int threadRows = ((bd.crows + s * kLat - 1) / (s * kLat)) * s;
         dim3 grid((bd.W + kDnX - 1) / kDnX, (threadRows + kDnY - 1) / kDnY);
-#ifdef __CUDACC__                        // (the host-emulation builds of tests/cuda_on_host have no TMA: they run atrousKernel on everything)
+#ifdef __CUDACC__                        // (the per-kernel host-emulation builds of tests/cuda_on_host run atrousKernel on everything; host_tu.py rule 7)
         if (io.links.up.res == nullptr && io.links.down.res == nullptr && io.links.waitUp == nullptr && io.links.waitDown == nullptr) {
             // No reservoir rows leave this pass and it waits for nobody: whole-frame handles and row bands that recompute their halo
             // (SGI_HALO_RECOMPUTE; the final pass's GI and image rows are stored by the epilogue both kernels share).  The lattice

@@ -186,7 +186,7 @@ int sgi_create(const SgiCreateParams* params, SgiHandle* out) {
     if (!(preloadPrepassKernels() && preloadVplKernels() && preloadTileKernels() && preloadGatherKernels() && preloadDenoiseKernels() && preloadBandKernels() &&
           preloadDirectKernels() && preloadSsaoKernels() && preloadTaaKernels() && preloadCubemapKernels()
 #ifdef __CUDACC__
-          && preloadAtrousTmaKernels()            // (k_atrous_tma.cu is not part of the host-emulation builds)
+          && preloadAtrousTmaKernels()            // (the per-kernel host-emulation builds of tests/cuda_on_host leave k_atrous_tma.cu out)
 #endif
           )) return bail(SGI_ERR_CUDA);
     if (allocPlanes(h) != SGI_OK) return bail(SGI_ERR_CUDA);

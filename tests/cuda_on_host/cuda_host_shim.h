@@ -104,6 +104,7 @@ inline cudaError_t hostToken(void** p) { static char token; *p = &token; return 
 #define cudaFreeHost(p) sgihost::hostFree((void*)(p))
 #define cudaMemcpyAsync(dst, src, n, kind, stream) (std::memcpy((dst), (src), (n)), cudaSuccess)
 #define cudaMemcpy(dst, src, n, kind) (std::memcpy((dst), (src), (n)), cudaSuccess)
+#define cudaMemset(p, v, n) (std::memset((p), (v), (n)), cudaSuccess)
 #define cudaStreamCreateWithFlags(ps, flags) sgihost::hostToken((void**)(ps))
 #define cudaStreamCreateWithPriority(ps, flags, prio) sgihost::hostToken((void**)(ps))
 #define cudaDeviceGetStreamPriorityRange(lo, hi) (*(lo) = 0, *(hi) = 0, cudaSuccess)
@@ -117,6 +118,71 @@ inline cudaError_t hostToken(void** p) { static char token; *p = &token; return 
 #define cudaIpcOpenMemHandle(pp, h, f) cudaErrorNotSupported
 #define cudaDeviceCanAccessPeer(pc, a, b) (*(pc) = 0, cudaSuccess)
 #define cudaDeviceEnablePeerAccess(d, f) cudaErrorNotSupported
+#endif
+
+#ifdef SGI_HOST_TMA
+// ---- TMA as csrc/k_atrous_tma.cu uses it: a tiled tensor map of rank 4 over 32-bit elements, encoded through the driver entry
+// point the file looks up, and cp.async.bulk.tensor.4d into shared memory completing on an mbarrier.  Here the encode function is
+// a stand-in that keeps base / dimensions / strides / box in the 128 opaque bytes of the CUtensorMap and REJECTS what the driver
+// rejects (so the launcher's fall-back to the clamped kernel is taken for the same planes as on a GPU); the copy is synchronous,
+// done by the issuing thread before the CTA's barrier, coordinates outside the tensor read as zero; the mbarrier calls are no-ops.
+#include <cuda.h>
+namespace sgihost {
+struct HostTensorMap { uint64_t magic; const char* base; uint64_t elemBytes, rank, dims[4], strides[3], box[4]; };
+static_assert(sizeof(HostTensorMap) <= sizeof(CUtensorMap), "the stand-in lives inside the opaque bytes");
+constexpr uint64_t kTensorMapMagic = 0x5347495f544d4150ull;
+inline long long tmaLoads = 0, tmaRejected = 0;        // boxes copied / encode calls refused since the library was loaded (one CTA runs at a time)
+static inline CUresult encodeTiledOnHost(CUtensorMap* map, CUtensorMapDataType type, cuuint32_t rank, void* addr, const cuuint64_t* dims, const cuuint64_t* strides,
+                                         const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill fill) {
+    auto refuse = [] { ++tmaRejected; return CUDA_ERROR_INVALID_VALUE; };
+    if (!map || !addr || rank != 4 || il != CU_TENSOR_MAP_INTERLEAVE_NONE || sw != CU_TENSOR_MAP_SWIZZLE_NONE || fill != CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) return refuse();
+    if (type != CU_TENSOR_MAP_DATA_TYPE_FLOAT32 && type != CU_TENSOR_MAP_DATA_TYPE_UINT32) return refuse();
+    if (((uintptr_t)addr & 15u) != 0) return refuse();                                                   // globalAddress: 16-byte aligned
+    HostTensorMap m; std::memset(&m, 0, sizeof(m));
+    m.magic = kTensorMapMagic; m.base = (const char*)addr; m.elemBytes = 4; m.rank = rank;
+    for (cuuint32_t i = 0; i < rank; ++i) {
+        if (dims[i] == 0 || dims[i] > (1ull << 32)) return refuse();
+        if (box[i] == 0 || box[i] > 256 || estr[i] != 1) return refuse();                                 // boxDim <= 256 (element strides other than 1 are not emulated)
+        m.dims[i] = dims[i]; m.box[i] = box[i];
+    }
+    if ((box[0] * m.elemBytes) % 16 != 0) return refuse();                                               // inner box row: a multiple of 16 bytes
+    for (cuuint32_t i = 0; i + 1 < rank; ++i) {
+        if (strides[i] % 16 != 0 || strides[i] >= (1ull << 40)) return refuse();                          // globalStrides: multiples of 16 bytes
+        m.strides[i] = strides[i];
+    }
+    std::memset(map, 0, sizeof(*map));
+    std::memcpy(map, &m, sizeof(m));
+    return CUDA_SUCCESS;
+}
+static inline cudaError_t driverEntryPoint(const char* name, void** fn, cudaDriverEntryPointQueryResult* q) {
+    const bool known = std::strcmp(name, "cuTensorMapEncodeTiled") == 0;
+    *fn = known ? (void*)&encodeTiledOnHost : nullptr;
+    if (q) *q = known ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}
+}  // namespace sgihost
+extern "C" __attribute__((weak)) long long sgihost_tma_loads() { return sgihost::tmaLoads; }           // for the tests: was the TMA path taken?
+extern "C" __attribute__((weak)) long long sgihost_tma_rejected() { return sgihost::tmaRejected; }
+#define cudaGetDriverEntryPoint(name, pfn, flags, pq) sgihost::driverEntryPoint((name), (void**)(pfn), (pq))
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(uintptr_t)p; }
+static inline void mbarInit(uint64_t* bar, int) { *bar = 0; }
+static inline void mbarExpectTx(uint64_t*, uint32_t) {}
+static inline void mbarWait(uint64_t*, uint32_t) {}             // the copies below have completed before the CTA's barrier
+static inline void tmaLoad4d(void* dst, const CUtensorMap* map, uint64_t*, int c0, int c1, int c2, int c3) {
+    sgihost::HostTensorMap m; std::memcpy(&m, map, sizeof(m));
+    if (m.magic != sgihost::kTensorMapMagic) { std::fprintf(stderr, "cuda_host_shim: tmaLoad4d on a tensor map that was not encoded\n"); std::abort(); }
+    ++sgihost::tmaLoads;
+    uint32_t* out = (uint32_t*)dst;
+    const long long c[4] = {c0, c1, c2, c3};
+    for (uint64_t i3 = 0; i3 < m.box[3]; ++i3) for (uint64_t i2 = 0; i2 < m.box[2]; ++i2) for (uint64_t i1 = 0; i1 < m.box[1]; ++i1) for (uint64_t i0 = 0; i0 < m.box[0]; ++i0) {
+        const long long x0 = c[0] + (long long)i0, x1 = c[1] + (long long)i1, x2 = c[2] + (long long)i2, x3 = c[3] + (long long)i3;
+        const bool inside = x0 >= 0 && x0 < (long long)m.dims[0] && x1 >= 0 && x1 < (long long)m.dims[1] && x2 >= 0 && x2 < (long long)m.dims[2] && x3 >= 0 && x3 < (long long)m.dims[3];
+        uint32_t v = 0;
+        if (inside) std::memcpy(&v, m.base + (uint64_t)x0 * m.elemBytes + (uint64_t)x1 * m.strides[0] + (uint64_t)x2 * m.strides[1] + (uint64_t)x3 * m.strides[2], 4);
+        *out++ = v;
+    }
+}
 #endif
 
 // the host API calls a launch function of csrc/ makes around its kernels

@@ -15,6 +15,14 @@ compiles a small wrapper that includes the copy:
      they return before their barrier — in the thread-by-thread mode a barrier that IS reached aborts the process, see the shim)
   5. `extern __shared__ T name[];`                            ->  `T* name = (T*)sgihost::dynSmem();`
   6. sgi_band.cu                                             ->  its `namespace sgi` half only (the extern "C" half is CUDA IPC plumbing)
+  7. k_atrous_tma.cu (whole-library build only)              ->  the mbarrier / cp.async.bulk.tensor helpers are dropped like the helpers of
+     rule 2 and the two bare `asm volatile` statements of its kernel (`fence.mbarrier_init`, `prefetch.global.L2`) become empty
+     statements; cuda_host_shim.h supplies a tensor map (its own layout inside the 128 opaque bytes of a CUtensorMap, encoded by a
+     stand-in for cuTensorMapEncodeTiled that rejects what the driver rejects: a base or a stride that is not a multiple of 16 bytes,
+     a box row that is not a multiple of 16 bytes, a box dimension above 256) and a tmaLoad4d that copies the box synchronously,
+     zero-filling coordinates outside the tensor.  `#ifdef __CUDACC__` around the TMA path in k_denoise.cu and sgi_abi.cu becomes
+     `#ifdef SGI_HOST_TMA`, which only the whole-library build defines: the per-kernel host tests keep atrousKernel on everything,
+     the ABI-level host tests run the lattice tiles + border CTAs exactly as the GPU does.
 
 Everything else — the kernel body, its index arithmetic, its exact-arithmetic chains — is compiled as written, with
 -ffp-contract=off so that `a * b + c` is never fused behind the code's back.
@@ -30,7 +38,10 @@ BUILD = os.path.join(HERE, "_build")
 HEADERS = ("sgi_internal.h", "sgi_math.cuh", "sgi_merge.cuh", "sgi_denoise.cuh")
 
 # rule 2: helpers that the shim supplies (name -> only checked for presence, the definitions live in cuda_host_shim.h)
-PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "rcpFast", "rsqrtFast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys", "sqrtApprox", "sqrtFast")
+PTX_HELPERS = ("prefetchL2", "lg2Fast", "ex2Fast", "rcpFast", "rsqrtFast", "pack2", "unpack2", "fma2", "ldAcquireSys", "stReleaseSys", "sqrtApprox", "sqrtFast",
+               "mbarInit", "mbarExpectTx", "mbarWait", "tmaLoad4d")
+# rule 7: bare inline-PTX statements of k_atrous_tma.cu's kernel that have no host meaning
+_BARE_ASM = re.compile(r'asm volatile\("(fence\.mbarrier_init\.release\.cluster|prefetch\.global\.L2 \[%0\]);"\s*:[^\n]*?\);')
 
 _LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;]*>)?)\s*<<<((?:(?!<<<|>>>).)*)>>>\s*\(", re.S)
 
@@ -117,6 +128,10 @@ def translate(text, name, whole_band_file=False):
         text = text[:text.index("using namespace sgi;")]
     if name == "sgi_internal.h":
         text = text.replace("#ifdef __CUDACC__", "#if 1   // [host emulation] was: #ifdef __CUDACC__")
+    if name in ("k_denoise.cu", "sgi_abi.cu"):
+        text = text.replace("#ifdef __CUDACC__", "#ifdef SGI_HOST_TMA   // [host emulation] was: #ifdef __CUDACC__")
+    if name == "k_atrous_tma.cu":
+        text = _BARE_ASM.sub(lambda m: "/* [host emulation] " + m.group(1) + " */;", text)
     code = re.sub(r"//[^\n]*", "", text)
     if re.search(r"\basm\b", code):
         raise ValueError(f"{name}: inline PTX outside the known helpers — extend PTX_HELPERS and the shim")
@@ -163,7 +178,8 @@ def compile_wrapper(wrapper_cpps, kernel_files, out_name, defines=(), extra=()):
     return _gxx([os.path.join(HERE, w) for w in wrapper_cpps], so, build, defines, extra)
 
 
-ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_cubemaps.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu")
+ABI_FILES = ("sgi_abi.cu", "sgi_band.cu", "k_prepass.cu", "k_direct.cu", "k_ssao.cu", "k_taa.cu", "k_cubemaps.cu", "k_vpl.cu", "k_tiles.cu", "k_gather.cu", "k_denoise.cu",
+             "k_atrous_tma.cu")
 
 
 def compile_whole_library(sanitize=False):
@@ -180,7 +196,7 @@ def compile_whole_library(sanitize=False):
     wrappers = []
     for f in ABI_FILES:
         w = os.path.join(build, "tu_" + f.replace(".cu", ".cpp"))
-        text = f'// generated by host_tu.py\n#define SGI_HOST_LOCKSTEP\n#define SGI_HOST_RUNTIME\n#include "cuda_host_shim.h"\n#include "{f}"\n'
+        text = f'// generated by host_tu.py\n#define SGI_HOST_LOCKSTEP\n#define SGI_HOST_RUNTIME\n#define SGI_HOST_TMA\n#include "cuda_host_shim.h"\n#include "{f}"\n'
         if not os.path.exists(w) or open(w).read() != text:
             open(w, "w").write(text)
         wrappers.append(w)

@@ -1,5 +1,6 @@
-"""The C ABI itself without a GPU: every translation unit of libstratusgi.so compiled for the host (tests/cuda_on_host/host_tu.py
-compile_whole_library: lockstep kernels, CUDA-runtime stand-ins) behind the product's own Python host class (tests/host_gipass.py).
+"""The C ABI itself without a GPU: every translation unit of libstratusgi.so — the TMA-staged à-trous kernel included, over a stand-in
+for tensor maps and cp.async.bulk.tensor — compiled for the host (tests/cuda_on_host/host_tu.py compile_whole_library: lockstep kernels,
+CUDA-runtime stand-ins) behind the product's own Python host class (tests/host_gipass.py).
 What this adds to the per-kernel host tests is the host-side state machine of csrc/sgi_abi.cu — bind resets, the pass 0 the gather
 fuses, the guide plane, history ping-pong, sgi_frame's stage order — and a dry run of the GPU tests' own code, including the opt-in
 tests of kernels that have not met a GPU yet (direct lighting, SSAO, TAA)."""
@@ -18,12 +19,24 @@ def _need_cuda_headers(built):
         pytest.skip("CUDA headers not found")
 
 
+def _tma_counters():
+    """(boxes copied by the stand-in for cp.async.bulk.tensor, tensor-map encodes refused) of the host-built library so far"""
+    import ctypes
+    from tests.host_gipass import host_library
+    L = host_library()
+    L.sgihost_tma_loads.restype = L.sgihost_tma_rejected.restype = ctypes.c_longlong
+    return int(L.sgihost_tma_loads()), int(L.sgihost_tma_rejected())
+
+
 def test_staged_calls_and_sgi_frame_through_the_host_built_abi(tiny, tiny_oracle):
     """Two frames stage by stage against the oracle (the GPU suite's central test), then the same two frames through sgi_frame on a
-    second handle: same bytes."""
+    second handle: same bytes.  The à-trous passes with spacing 2 and 4 go through csrc/k_atrous_tma.cu as on a GPU — lattice tiles
+    from the emulated tensor maps next to the border CTAs in one launch (160 x 90 has too few lattice rows for spacing 8)."""
     from tests.parity_util import compare_frame, make_pass, run_cuda_staged
+    boxes0, _ = _tma_counters()
     with gpu_tests_on_the_host():
         cu = run_cuda_staged(tiny)
+        assert _tma_counters()[0] - boxes0 == 2 * 2 * (18 + 24), "the TMA-staged à-trous kernel did not run (2 frames x 2 planes x the tiles of spacing 2 and 4)"
         for f in range(2):
             rep, bad = compare_frame(cu[f], tiny_oracle[f])
             assert not bad, (f, bad)
@@ -106,13 +119,19 @@ def test_tile_list_gather_with_full_lists_on_the_host(built):
     assert counts.min() == 12
 
 
-def test_ragged_frame_size_on_the_host(built):
-    """tests/test_parity_gpu.py::test_ragged_frame_sizes at 170 x 95 (no size is a multiple of a warp segment, a CTA or a spacing)."""
+@pytest.mark.parametrize("width,tma", [(170, True), (165, False)])
+def test_ragged_frame_size_on_the_host(built, width, tma):
+    """tests/test_parity_gpu.py::test_ragged_frame_sizes at 170 x 95 (no size is a multiple of a warp segment, a CTA or a spacing:
+    lattice tiles with leftover columns and rows next to them) and 165 x 95 (an odd width: the reservoir plane's row pitch is no
+    multiple of 16 bytes, the tensor-map encode is refused as by the driver and every pass takes the clamped kernel)."""
     if os.environ.get("SGI_HOST_SUITE", "") != "full":
-        pytest.skip("25 s on the host: set SGI_HOST_SUITE=full")
+        pytest.skip("15 s each on the host: set SGI_HOST_SUITE=full")
     from tests import test_parity_gpu as G
+    boxes0, refused0 = _tma_counters()
     with gpu_tests_on_the_host():
-        G.test_ragged_frame_sizes(built, 170, 95)
+        G.test_ragged_frame_sizes(built, width, 95)
+    boxes, refused = _tma_counters()
+    assert (boxes > boxes0) == tma and (refused > refused0) == (not tma)
 
 
 @pytest.mark.parametrize("iters", [1, 3])

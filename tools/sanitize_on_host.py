@@ -4,6 +4,7 @@
     python tools/sanitize_on_host.py address      # re-executes itself under LD_PRELOAD=libasan.so   (9 minutes on 8 cores)
     python tools/sanitize_on_host.py thread       # ... libtsan.so
     python tools/sanitize_on_host.py undefined    # ... libubsan.so (misaligned vector accesses, signed overflow, bad shifts, float -> int overflow)
+    python tools/sanitize_on_host.py address tma  # the short run: two staged frames, sgi_frame and the ragged frame sizes (what reaches k_atrous_tma.cu)
 
 address: every "device" allocation is its own malloc block and the caller's buffers are ordinary heap tensors, so a kernel that
 reads or writes past the end of a plane — which a GPU forgives inside an allocation granule — is reported with the source line.
@@ -34,7 +35,7 @@ def main():
                    TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=2", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
         if kind == "thread":
             env["OMP_NUM_THREADS"] = "1"      # libgomp is not instrumented: its own barriers would look like races (oracle, scene generator)
-        rc = subprocess.call([sys.executable, os.path.abspath(__file__), kind], env=env)
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), kind] + sys.argv[2:], env=env)
         print("exit code", rc, "(a sanitizer report ends the run with a non-zero code)")
         return rc
     from tests import test_parity_gpu as G, test_zz_direct_lighting as D, test_zz_ssao as S, test_zz_taa as T
@@ -54,6 +55,15 @@ def main():
             gp.set_gbuffer(turning.gb[f], turning.gb[f - 1]); gp.set_csm(turning.csm[f]); gp.bind(); gp.frame(turning.fp[f])
         gp.close()
         print("staged frames, sgi_frame: clean", flush=True)
+        if "tma" in sys.argv[2:]:
+            # the short run: only what goes through the TMA-staged à-trous kernel (csrc/k_atrous_tma.cu over the shim's tensor maps:
+            # a tap read past a tile's shared-memory box is a global-buffer-overflow on the kernel's static arrays) — the frames
+            # above plus the ragged sizes (leftover columns and rows, a partial last tile row; an odd width without a tensor map)
+            G.test_ragged_frame_sizes(None, 170, 95)
+            G.test_ragged_frame_sizes(None, 165, 95)
+            print("ragged frame sizes: clean", flush=True)
+            print(kind.upper(), "SANITIZER: NO REPORT")
+            return 0
         for name, args in (("test_tile_list_gather_mode", (None,)), ("test_denoise_iteration_count_is_a_parameter", (tiny, 1)),
                            ("test_denoise_iteration_count_is_a_parameter", (tiny, 3)), ("test_cuda_integer_outputs_match_the_glm_golden_fixture", (tiny,)),
                            ("test_single_vpl_and_two_vpls", (None,)), ("test_no_visible_vpl", (None,)),
