@@ -90,3 +90,68 @@ def test_border_ctas_are_enumerated_exactly_once(host_denoiser, W, rows, c0, cro
         got = [tuple(int(v) for v in lst[i]) for i in range(n)]
         assert len(set(got)) == len(got) == n, "a border CTA is enumerated twice"
         assert set(got) == want, (len(got), len(want))
+
+
+# ---- the TMA-staged à-trous kernel against the clamped kernel, pass by pass, on the host ---------------------------------------
+_GEOMETRIES_FAST = [(200, 176, 0, 176), (170, 95, 0, 95), (256, 120, 28, 60), (164, 210, 30, 150)]
+_GEOMETRIES_FULL = [(160, 90, 0, 90), (165, 95, 0, 95), (136, 72, 0, 72), (134, 70, 0, 70), (272, 330, 30, 270), (272, 330, 6, 318), (200, 300, 0, 298),
+                    (320, 116, 28, 60), (320, 88, 0, 60), (320, 88, 28, 60), (1370, 64, 0, 64), (72, 400, 0, 400), (178, 181, 5, 171)]
+
+
+def _atrous_pass_libs():
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    from tests.cuda_on_host.host_tu import compile_wrapper
+    tma = C.CDLL(compile_wrapper(("atrous_pass_on_host.cpp", "atrous_tma_tu_on_host.cpp"), ("k_denoise.cu", "k_atrous_tma.cu"), "libatrous_tma_on_host.so", ("SGI_HOST_TMA",)))
+    plain = C.CDLL(compile_wrapper("atrous_pass_on_host.cpp", "k_denoise.cu", "libatrous_plain_on_host.so", ()))
+    for L in (tma, plain):
+        L.host_atrous_pass.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+        L.host_tma_boxes.restype = C.c_longlong
+    return tma, plain
+
+
+def _random_planes(W, rows, seed):
+    """A guide plane with structure (a few normal directions and depth steps, so that weights range from 0 to 1) and a random reservoir."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:rows, 0:W]
+    region = ((xx // 13) + 2 * (yy // 9)) % 5
+    normals = rng.normal(size=(5, 3)).astype(np.float32)
+    normals /= np.linalg.norm(normals, axis=1, keepdims=True)
+    n = normals[region] + rng.normal(scale=0.02, size=(rows, W, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=2, keepdims=True)
+    depth = (5.0 + 3.0 * region + rng.random((rows, W)) * 0.5).astype(np.float32)
+    guide = np.concatenate([n.astype(np.float32), depth[..., None]], axis=2).astype(np.float32)
+    res = rng.random((rows, W, 4)).astype(np.float16)
+    res[..., 3] = 1.0
+    return np.ascontiguousarray(guide), np.ascontiguousarray(res)
+
+
+@pytest.mark.parametrize("W,rows,c0,crows", _GEOMETRIES_FAST + _GEOMETRIES_FULL)
+def test_tma_tiles_and_border_ctas_write_the_clamped_kernels_bytes(built, W, rows, c0, crows):
+    """csrc/k_atrous_tma.cu (lattice tiles from the shim's tensor maps + the border CTAs at the head of the same launch) against
+    csrc/k_denoise.cu's atrousKernel on the whole plane, one pass per spacing on the same random planes: whole frames and row bands
+    (halo rows above / below the computed ones), leftover columns and rows beyond the last whole multiple of the spacing, a last tile
+    shifted back or left partial, planes that only just hold one tile, planes that hold none (then both runs are the clamped kernel),
+    an odd width (encode refused).  Same bytes in every computed pixel, and no pixel outside the computed rows touched by either."""
+    if (W, rows, c0, crows) in _GEOMETRIES_FULL and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("the long list of geometries: set SGI_HOST_SUITE=full")
+    tma, plain = _atrous_pass_libs()
+    guide, res = _random_planes(W, rows, seed=W * 1000 + rows)
+    took_tiles = []
+    for multiplier in (1, 3, 7):
+        outs = []
+        for L in (tma, plain):
+            out = np.full((rows, W, 4), np.float16(-7.0))                       # sentinel: no pass writes a negative value
+            before = L.host_tma_boxes()
+            assert L.host_atrous_pass(W, rows, c0, crows, multiplier, guide.ctypes.data, res.ctypes.data, out.ctypes.data) >= 1
+            if L is tma:
+                took_tiles.append(L.host_tma_boxes() > before)
+            outs.append(out)
+        a, b = (o.view(np.uint16) for o in outs)
+        assert np.array_equal(a, b), (multiplier, int((a != b).any(axis=2).sum()))
+        computed = np.zeros(rows, bool); computed[c0:c0 + crows] = True
+        assert np.all(outs[0][~computed] == np.float16(-7.0)) and np.all(outs[0][computed][..., 3] == np.float16(1.0))
+    expect = {(200, 176, 0, 176): [True, True, True], (170, 95, 0, 95): [True, True, False], (165, 95, 0, 95): [False, False, False]}
+    if (W, rows, c0, crows) in expect:
+        assert took_tiles == expect[(W, rows, c0, crows)], took_tiles
