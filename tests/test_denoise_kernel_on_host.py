@@ -106,7 +106,7 @@ def _atrous_pass_libs():
     tma = C.CDLL(compile_wrapper(("atrous_pass_on_host.cpp", "atrous_tma_tu_on_host.cpp"), ("k_denoise.cu", "k_atrous_tma.cu"), "libatrous_tma_on_host.so", ("SGI_HOST_TMA",)))
     plain = C.CDLL(compile_wrapper("atrous_pass_on_host.cpp", "k_denoise.cu", "libatrous_plain_on_host.so", ()))
     for L in (tma, plain):
-        L.host_atrous_pass.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
+        L.host_atrous_pass.argtypes = [C.c_int] * 5 + [C.c_void_p] * 8
         L.host_tma_boxes.restype = C.c_longlong
     return tma, plain
 
@@ -130,7 +130,8 @@ def _random_planes(W, rows, seed):
 @pytest.mark.parametrize("W,rows,c0,crows", _GEOMETRIES_FAST + _GEOMETRIES_FULL)
 def test_tma_tiles_and_border_ctas_write_the_clamped_kernels_bytes(built, W, rows, c0, crows):
     """csrc/k_atrous_tma.cu (lattice tiles from the shim's tensor maps + the border CTAs at the head of the same launch) against
-    csrc/k_denoise.cu's atrousKernel on the whole plane, one pass per spacing on the same random planes: whole frames and row bands
+    csrc/k_denoise.cu's atrousKernel on the whole plane, one pass per spacing — and the final pass with its blend epilogue at spacings
+    8 and 2 — on the same random planes: whole frames and row bands
     (halo rows above / below the computed ones), leftover columns and rows beyond the last whole multiple of the spacing, a last tile
     shifted back or left partial, planes that only just hold one tile, planes that hold none (then both runs are the clamped kernel),
     an odd width (encode refused).  Same bytes in every computed pixel, and no pixel outside the computed rows touched by either."""
@@ -138,20 +139,26 @@ def test_tma_tiles_and_border_ctas_write_the_clamped_kernels_bytes(built, W, row
         pytest.skip("the long list of geometries: set SGI_HOST_SUITE=full")
     tma, plain = _atrous_pass_libs()
     guide, res = _random_planes(W, rows, seed=W * 1000 + rows)
+    rng = np.random.default_rng(rows * 1000 + W)
+    temporal = np.ascontiguousarray(rng.random((rows, W, 4)).astype(np.float32))          # (reprojected GI, 1 / history in (0, 1])
+    screen, illum = (np.ascontiguousarray(rng.random((rows, W, 4)).astype(np.float16)) for _ in range(2))
+    computed = np.zeros(rows, bool); computed[c0:c0 + crows] = True
     took_tiles = []
-    for multiplier in (1, 3, 7):
+    for multiplier, final_ in ((1, False), (3, False), (7, False), (7, True), (1, True)):
         outs = []
         for L in (tma, plain):
-            out = np.full((rows, W, 4), np.float16(-7.0))                       # sentinel: no pass writes a negative value
+            planes = [np.full((rows, W, 4), np.float16(-7.0)) for _ in range(3)]        # sentinel: no pass writes a negative value
+            extra = [temporal.ctypes.data, screen.ctypes.data, illum.ctypes.data, planes[1].ctypes.data, planes[2].ctypes.data] if final_ else [None] * 5
             before = L.host_tma_boxes()
-            assert L.host_atrous_pass(W, rows, c0, crows, multiplier, guide.ctypes.data, res.ctypes.data, out.ctypes.data) >= 1
-            if L is tma:
+            assert L.host_atrous_pass(W, rows, c0, crows, multiplier, guide.ctypes.data, res.ctypes.data, planes[0].ctypes.data, *extra) >= 1
+            if L is tma and not final_:
                 took_tiles.append(L.host_tma_boxes() > before)
-            outs.append(out)
-        a, b = (o.view(np.uint16) for o in outs)
-        assert np.array_equal(a, b), (multiplier, int((a != b).any(axis=2).sum()))
-        computed = np.zeros(rows, bool); computed[c0:c0 + crows] = True
-        assert np.all(outs[0][~computed] == np.float16(-7.0)) and np.all(outs[0][computed][..., 3] == np.float16(1.0))
+            outs.append(planes)
+        for k, (pa, pb) in enumerate(zip(*outs)):                                           # reservoir; final pass: lit image, GI
+            a, b = pa.view(np.uint16), pb.view(np.uint16)
+            assert np.array_equal(a, b), (multiplier, final_, k, int((a != b).any(axis=2).sum()))
+            written = k == 0 or final_
+            assert np.all(pa[~computed] == np.float16(-7.0)) and np.all((pa[computed][..., 3] == np.float16(1.0)) == written)
     expect = {(200, 176, 0, 176): [True, True, True], (170, 95, 0, 95): [True, True, False], (165, 95, 0, 95): [False, False, False]}
     if (W, rows, c0, crows) in expect:
         assert took_tiles == expect[(W, rows, c0, crows)], took_tiles
