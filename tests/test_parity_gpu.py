@@ -137,7 +137,9 @@ def test_ragged_frame_sizes(built, width, height):
     has no 16-byte row pitch for a tensor map (every pass through the clamped global-memory kernel), and none of the sizes is a
     multiple of the 32-pixel segments of the gather or of the 8-row CTAs of the temporal pre-pass.  Two frames of a turning camera."""
     d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.0, width=width, height=height)
-    _assert_parity(run_cuda_staged(d), run_oracle(d))
+    for f, (cu, orc) in enumerate(zip(run_cuda_staged(d), run_oracle(d))):
+        rep, bad = compare_frame(cu, orc)                  # integer outputs and history bit-exact, radiance within the bar
+        assert not bad, f"frame {f}: {bad}"
 
 
 def test_fused_frame_call_equals_staged_calls(tiny):
