@@ -129,6 +129,8 @@ def whole_frame(built):
 def test_bands_with_middle_ranks_reproduce_the_whole_frame_bytes(whole_frame, world, kernel_signal):
     if world == 8 and os.environ.get("SGI_HOST_SUITE", "") != "full":
         pytest.skip("8 bands of 30 rows (halo 20): set SGI_HOST_SUITE=full")
+    if world == 5 and os.environ.get("SGI_HOST_SUITE", "") != "full":
+        pytest.skip("5 unequal bands (25 s; 3 and 4 bands run every time): set SGI_HOST_SUITE=full")
     if not kernel_signal and os.environ.get("SGI_HOST_SUITE", "") != "full":
         pytest.skip("host-launched signals (the path the 4- and 8-GPU hardware runs used): set SGI_HOST_SUITE=full")
     tables, want = whole_frame
