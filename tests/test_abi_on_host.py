@@ -2,8 +2,8 @@
 for tensor maps and cp.async.bulk.tensor — compiled for the host (tests/cuda_on_host/host_tu.py compile_whole_library: lockstep kernels,
 CUDA-runtime stand-ins) behind the product's own Python host class (tests/host_gipass.py).
 What this adds to the per-kernel host tests is the host-side state machine of csrc/sgi_abi.cu — bind resets, the pass 0 the gather
-fuses, the guide plane, history ping-pong, sgi_frame's stage order — and a dry run of the GPU tests' own code, including the opt-in
-tests of kernels that have not met a GPU yet (direct lighting, SSAO, TAA)."""
+fuses, the guide plane, history ping-pong, sgi_frame's stage order — and a dry run of the GPU tests' own code, including the
+tests of the widening kernels (direct lighting, SSAO, TAA)."""
 import os
 
 import numpy as np
@@ -56,7 +56,7 @@ def test_prepass_boundary_test_of_the_gpu_suite_runs_on_the_host(tiny):
         G.test_vpl_prepass_is_bit_exact(tiny, 257, 3)
 
 
-def test_opt_in_gpu_tests_of_the_unvalidated_kernels_run_on_the_host(built):
+def test_gpu_tests_of_the_widening_kernels_run_on_the_host(built):
     """tests/test_zz_direct_lighting.py, test_zz_ssao.py, test_zz_taa.py: the same code, the same bars."""
     from oracle import oracle_py
     if oracle_py.reference_glsl() is None:

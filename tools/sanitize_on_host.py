@@ -14,7 +14,7 @@ racecheck looks for).  CTAs run one after the other, so races between CTAs are n
 
 Covers: two staged frames of a turning camera against the oracle, sgi_frame, the tile-list gather mode, 1 and 3 denoise passes, the
 golden fixture, one / two / no visible VPL, more visible VPLs than the per-frame cap, resize, the pre-pass (0 .. 2048 lights and the
-frustum boundary cases) and the three kernels that have not met a GPU yet (direct lighting, SSAO, TAA)."""
+frustum boundary cases) and the widening kernels (direct lighting, SSAO, TAA)."""
 import os
 import subprocess
 import sys
