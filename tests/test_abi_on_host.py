@@ -119,8 +119,8 @@ def test_tile_list_gather_with_full_lists_on_the_host(built):
     assert counts.min() == 12
 
 
-@pytest.mark.parametrize("width,tma", [(170, True), (165, False)])
-def test_ragged_frame_size_on_the_host(built, width, tma):
+@pytest.mark.parametrize("width,tma,tile_list_mode", [(170, True, False), (165, False, False), (170, True, True)])
+def test_ragged_frame_size_on_the_host(built, width, tma, tile_list_mode):
     """tests/test_parity_gpu.py::test_ragged_frame_sizes at 170 x 95 (no size is a multiple of a warp segment, a CTA or a spacing:
     lattice tiles with leftover columns and rows next to them) and 165 x 95 (an odd width: the reservoir plane's row pitch is no
     multiple of 16 bytes, the tensor-map encode is refused as by the driver and every pass takes the clamped kernel)."""
@@ -129,7 +129,7 @@ def test_ragged_frame_size_on_the_host(built, width, tma):
     from tests import test_parity_gpu as G
     boxes0, refused0 = _tma_counters()
     with gpu_tests_on_the_host():
-        G.test_ragged_frame_sizes(built, width, 95)
+        G.test_ragged_frame_sizes(built, width, 95, tile_list_mode)
     boxes, refused = _tma_counters()
     assert (boxes > boxes0) == tma and (refused > refused0) == (not tma)
 

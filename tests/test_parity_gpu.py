@@ -123,20 +123,24 @@ def check_tile_list_band(workload, y0, rows):
 
 def test_tile_list_gather_mode_with_full_lists(built):
     """The tile-list mode where the lists are long: c3 (1920x1080, 1024 VPLs) and c4 (3840x2160, 2048 VPLs), a band of the
-    floor / column rows each.  Most tiles hold the full 12 entries there, so the shared-memory staging of the 5x5-tile
-    neighbourhood and the 12-light shading loop see the lengths that tiny and c1 never reach."""
+    floor / column rows each.  Every tile holds the full 12 entries there, so the shared-memory staging of a CTA's 8 x 2 tile
+    lists and the 12-light shading loop see the lengths that tiny and c1 never reach (27 tile rows of the c3 band: a partial CTA row)."""
     for wl, y0, rows in (("c3", 700, 135), ("c4", 1400, 90)):
         rep, counts = check_tile_list_band(wl, y0, rows)
         assert counts.max() == 12 and np.mean(counts == 12) > 0.5, (wl, np.bincount(counts, minlength=13))
 
 
-@pytest.mark.parametrize("width,height", [(170, 95), (165, 95), (1370, 770)])
-def test_ragged_frame_sizes(built, width, height):
+@pytest.mark.parametrize("width,height,tile_list_mode", [(170, 95, False), (165, 95, False), (1370, 770, False), (170, 95, True)])
+def test_ragged_frame_sizes(built, width, height, tile_list_mode):
     """Sizes that are multiples of the 5-pixel tile only: 170 and 1370 columns leave 2 columns beyond the last whole multiple of
     the à-trous spacings 4 and 8 (they and the 2 leftover rows of 770 go to the border CTAs next to the TMA tiles), an odd width
     has no 16-byte row pitch for a tensor map (every pass through the clamped global-memory kernel), and none of the sizes is a
-    multiple of the 32-pixel segments of the gather or of the 8-row CTAs of the temporal pre-pass.  Two frames of a turning camera."""
+    multiple of the 32-pixel segments of the gather or of the 8-row CTAs of the temporal pre-pass.  Two frames of a turning camera.
+    tile_list_mode: 34 x 19 tiles are 4.25 x 9.5 CTAs of the tile-list gather (8 x 2 tiles each): partial CTAs at both edges."""
     d = SceneData("tiny", frames=2, yaw_deg_per_frame=1.0, width=width, height=height)
+    if tile_list_mode:
+        for fp in d.fp:
+            fp.gatherMode = _abi.GATHER_TILE_LIST
     for f, (cu, orc) in enumerate(zip(run_cuda_staged(d), run_oracle(d))):
         rep, bad = compare_frame(cu, orc)                  # integer outputs and history bit-exact, radiance within the bar
         assert not bad, f"frame {f}: {bad}"

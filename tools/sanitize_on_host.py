@@ -59,8 +59,9 @@ def main():
             # the short run: only what goes through the TMA-staged à-trous kernel (csrc/k_atrous_tma.cu over the shim's tensor maps:
             # a tap read past a tile's shared-memory box is a global-buffer-overflow on the kernel's static arrays) — the frames
             # above plus the ragged sizes (leftover columns and rows, a partial last tile row; an odd width without a tensor map)
-            G.test_ragged_frame_sizes(None, 170, 95)
-            G.test_ragged_frame_sizes(None, 165, 95)
+            G.test_ragged_frame_sizes(None, 170, 95, False)
+            G.test_ragged_frame_sizes(None, 165, 95, False)
+            G.test_ragged_frame_sizes(None, 170, 95, True)       # tile-list gather: partial CTAs of 8 x 2 tiles at both edges
             print("ragged frame sizes: clean", flush=True)
             print(kind.upper(), "SANITIZER: NO REPORT")
             return 0
