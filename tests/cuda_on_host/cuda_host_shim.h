@@ -271,17 +271,34 @@ template <typename T, class F> static inline T exchange(unsigned mask, T v, F sr
 }
 static inline void* dynSmem() { return cta->dynSmem; }
 
+// The n OS threads of a launch are created once and walk through the CTAs together (a pool barrier before and after every CTA)
+// instead of being created and joined per CTA: thread creation was most of the system time of the host suite.
+struct PoolBarrier {
+    std::mutex m; std::condition_variable cv; int arrived = 0, n = 0; unsigned gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned g = gen;
+        if (++arrived == n) { arrived = 0; ++gen; cv.notify_all(); }
+        else cv.wait(l, [&] { return gen != g; });
+    }
+};
 template <class Body> static void runGrid(dim3 g, dim3 b, size_t smem, Body body) {
     const int n = (int)(b.x * b.y * b.z);
-    for (unsigned bz = 0; bz < g.z; ++bz) for (unsigned by = 0; by < g.y; ++by) for (unsigned bx = 0; bx < g.x; ++bx) {
-        Cta c(n);
-        std::vector<unsigned long long> mem((smem + 15) / 8 + 2);
-        c.dynSmem = (void*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15);
-        cta = &c;
-        std::vector<std::thread> th;
-        th.reserve(n);
-        for (int t = 0; t < n; ++t) th.emplace_back([&, t] {
-            gridDim = g; blockDim = b; blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+    const unsigned long long total = (unsigned long long)g.x * g.y * g.z;
+    if (n <= 0 || total == 0) return;
+    std::vector<unsigned long long> mem((smem + 15) / 8 + 2);
+    void* const dyn = (void*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15);
+    Cta* cur = nullptr;
+    PoolBarrier pool; pool.n = n;
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (int t = 0; t < n; ++t) th.emplace_back([&, t] {
+        for (unsigned long long i = 0; i < total; ++i) {
+            if (t == 0) { delete cur; cur = new Cta(n); cur->dynSmem = dyn; cta = cur; }      // CTAs of a launch run one after the other
+            pool.wait();                                                                   // the CTA's state is in place
+            Cta& c = *cur;
+            gridDim = g; blockDim = b;
+            blockIdx.x = (unsigned)(i % g.x); blockIdx.y = (unsigned)((i / g.x) % g.y); blockIdx.z = (unsigned)(i / ((unsigned long long)g.x * g.y));
             threadIdx.x = t % b.x; threadIdx.y = (t / b.x) % b.y; threadIdx.z = t / (b.x * b.y);
             lane = t % 32; warpId = t / 32; orPhase = 0;
             body();
@@ -290,10 +307,12 @@ template <class Body> static void runGrid(dim3 g, dim3 b, size_t smem, Body body
             w.bar.left([&] { return liveLanes(w, 0xffffffffu); });     // (a waiting partial-mask collective re-checks on its own arrival)
             c.live.fetch_sub(1);
             c.bar.left([&] { return c.live.load(); });
-        });
-        for (auto& x : th) x.join();
-        cta = nullptr;
-    }
+            pool.wait();                                                                   // every thread has left the CTA before thread 0 replaces it
+        }
+    });
+    for (auto& x : th) x.join();
+    delete cur;
+    cta = nullptr;
 }
 }  // namespace sgihost
 
