@@ -9,15 +9,16 @@ and csrc/sgi_internal.h (fence, producer count, last producer releases the flag;
 ThreadSanitizer reports any pair of accesses the protocol does not order — a missing wait, a flag released before the last producer's
 stores, a halo overwritten while the neighbour may still read it.
 
-    python tools/race_check_bands_on_host.py [bands=4] [kernel|host] [exchange|recompute]      # re-executes itself under LD_PRELOAD=libtsan.so
+    python tools/race_check_bands_on_host.py [bands=4] [kernel|host] [exchange|recompute] [nowait]      # re-executes itself under LD_PRELOAD=libtsan.so
 
 `recompute` = SGI_HALO_RECOMPUTE: the bands compute the non-final passes on their halo rows themselves; what is left to order is the
 final pass's GI rows (stored into the neighbours, read by their temporal pre-pass of the next frame, overwritten two frames later),
 which is why the check runs three frames, all of them inside ONE library call per band (the interpreter lock would otherwise order
-everything across frames).  Limit, observed: with the pre-pass's wait for the neighbours' previous frame REMOVED, ThreadSanitizer
-still reports nothing in this mode.  The cause was not established; the stores and the reads in question are a whole frame apart —
-hundreds of thousands of short-lived emulation threads (one OS thread per CUDA thread of every CTA) — which is probably more history
-than ThreadSanitizer keeps.  So this mode shows that nothing ELSE is shared between the bands, not that the inter-frame wait is needed.
+everything across frames).  Limit, observed: with the pre-pass's wait for the neighbours' previous frame REMOVED (`nowait` as a
+fourth argument), ThreadSanitizer still reports nothing in this mode.  The cause is not established.  It is not the number of emulation
+threads between the stores and the reads, a whole frame apart: the lockstep runtime used to create one OS thread per CUDA thread of
+every CTA (hundreds of thousands per frame) and now creates them once per launch (a few thousand), and the outcome is the same.
+So this mode shows that nothing ELSE is shared between the bands, not that the inter-frame wait is needed.
 The intra-pass waits of the exchange mode are checked by this tool (a removed wait is reported); the inter-frame GI rows rest on
 the ordering argument of DESIGN.md section 6 and on the byte comparisons of tests/test_bands_lockstep_on_host.py and the GPU suite.
 """
@@ -37,6 +38,7 @@ def main():
     world = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     kernel_signal = (sys.argv[2] if len(sys.argv) > 2 else "kernel") == "kernel"
     recompute = (sys.argv[3] if len(sys.argv) > 3 else "exchange") == "recompute"
+    drop_inter_frame_wait = "nowait" in sys.argv[4:]      # sensitivity check: the temporal pre-pass skips its wait for the neighbours' previous frame
     from tests.cuda_on_host.host_tu import BUILD, compile_wrapper
     if os.environ.get("SGI_TSAN_CHILD") != "1":
         so = compile_wrapper(("vpl_on_host.cpp", "gather_on_host.cpp", "denoise_lockstep_on_host.cpp", "bands_on_host.cpp"),
@@ -72,6 +74,8 @@ def main():
         L.host_band_init.argtypes = [C.c_int] * 11 + [C.c_void_p, C.c_int, C.POINTER(HostPeer), C.POINTER(HostPeer), C.c_int]
         L.host_band_frame.argtypes = [C.POINTER(FrameParams)] + [C.c_void_p] * 16 + [C.c_int, C.c_void_p]
         L.host_band_frames.argtypes = [C.c_int, C.POINTER(FrameParams), C.c_void_p, C.c_int, C.c_void_p]
+        if drop_inter_frame_wait:
+            L.host_band_test_hooks(0, 1)
         libs.append(L)
     slab_bytes = int(libs[0].host_band_slab_bytes(W, rows_max))
     slabs = [np.zeros(slab_bytes, np.uint8) for _ in range(world)]
