@@ -1,7 +1,7 @@
 """Memory check and race check of the kernels and the C ABI without a GPU: the whole library built for the host
 (tests/cuda_on_host/host_tu.py) with AddressSanitizer or ThreadSanitizer, driven by the GPU suite's own test bodies.
 
-    python tools/sanitize_on_host.py address      # re-executes itself under LD_PRELOAD=libasan.so   (9 minutes on 8 cores)
+    python tools/sanitize_on_host.py address      # re-executes itself under LD_PRELOAD=libasan.so   (4 minutes on 8 cores; thread: 6, undefined: 4)
     python tools/sanitize_on_host.py thread       # ... libtsan.so
     python tools/sanitize_on_host.py undefined    # ... libubsan.so (misaligned vector accesses, signed overflow, bad shifts, float -> int overflow)
     python tools/sanitize_on_host.py address tma  # the short run: two staged frames, sgi_frame and the ragged frame sizes (what reaches k_atrous_tma.cu)
