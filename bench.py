@@ -46,6 +46,41 @@ def workload_text(s):
     return f"{s.workload}: {s.width}x{s.height} {kind}, {s.num_vpls} VPLs, cube shadow maps 32^2x6, {s.denoise_iters} denoise passes, tile lists on"
 
 
+def bench_config(scene, world, args):
+    """The `config` object of the bench line: what is measured, as a function of the workload and the command line only — so that
+    `--impl reference`, launched with the same flags, prints the SAME object (the CPU arm times a bounded sample of this workload; what
+    the sample was is in its `cpu_baseline.sample`).  Everything a run measures or decides (visible VPLs, band rows after balancing,
+    wait time-outs, the image check) is in the line's `run` object instead."""
+    from stratusgfx_b200.bands import APRON, halo_rows, recompute_rows
+    iters = scene.denoise_iters
+    p2p = world > 1 and args.bands in ("p2p", "recompute")
+    recompute = world > 1 and args.bands == "recompute"
+    device_maps = args.maps == "device"
+    use_early = not args.no_early
+    prefetch = world > 1 and not args.no_prefetch
+    cfg = {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)", "storage": "f16/unorm8 planes"}
+    if world > 1 and args.split == "views":
+        cfg["parallelism"] = f"{world} independent camera views, one whole view per GPU, no exchange (the batch axis of configs[4]); a step = one frame of every view"
+        return cfg
+    if world == 1:
+        cfg["parallelism"] = "single GPU"
+    elif p2p:
+        halo = recompute_rows(iters) if recompute else halo_rows(iters)
+        cfg["parallelism"] = (
+            f"{world} row bands (cuts balanced by {args.balance} timed pre-pass round(s); rows in run.band_rows) + {halo}-row halos " +
+            ("on which the band recomputes the gather and the non-final passes itself (28/24/16 rows; only the final pass's GI rows travel, NVLink peer stores)" if recompute
+             else "filled by the neighbours' kernels through NVLink peer stores (CUDA IPC)") +
+            f", one NCCL broadcast of the VPL table{'' if device_maps else ' + 5 cube maps'} per frame ({'issued one frame ahead' if (prefetch or use_early) else 'at the start of the frame'}), "
+            "lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)")
+    else:
+        cfg["parallelism"] = f"{world} row bands + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"
+    cfg["look_ahead"] = (("cull + colouring" + (" + table broadcast" if world > 1 else "") + " + cube-map refresh of frame i+1 on a second stream under frame i's denoise passes "
+                          "(sgi_early_begin / sgi_cull_early; the reference culls at BE:1395, long before the GI pass at BE:2043)") if use_early else "off: everything on one stream")
+    cfg["refreshed_cube_maps"] = ("rendered on the device every frame (sgi_render_vpl_cubemaps, 5 maps)" if device_maps
+                                  else ("copied from the per-frame broadcast (5 maps)" if world > 1 else "resident (uploaded once)"))
+    return cfg
+
+
 # ---- clocks during the timed region (B200_PROFILING.md) -----------------------------------------------------
 class ClockSampler:
     """SM clock and throttle reasons while the timed region runs.  Two samplers run side by side: NVML (nvidia_ml_py) polled
@@ -311,7 +346,7 @@ def run_reference(args, rank):
     r = cpu_arm(scene, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_text(scene), "sample": r["sample"]},
+            "config": bench_config(scene, max(args.gpus, 1), args), "run": {"sample": r["sample"], "visible_vpls": r.get("V")},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "port_value") if k in r},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -686,16 +721,11 @@ def run_ours(args, rank, world, local_rank):
                     "note": "the dominant kernel is FP32-issue/L1 bound, not HBM bound (DESIGN.md section 3); frac is its algorithmic bytes against the measured HBM peak"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
-                           "parallelism": "single GPU" if world == 1 else (
-                               f"{world} row bands of {band} rows + {halo}-row halos " + ("on which the band recomputes the gather and the non-final passes itself (28/24/16 rows; only the final pass's GI rows travel, NVLink peer stores)" if recompute else "filled by the neighbours' kernels through NVLink peer stores (CUDA IPC)") + f", one NCCL broadcast of the VPL table{'' if device_maps else ' + 5 cube maps'} per frame ({'issued one frame ahead' if (prefetch or use_early) else 'at the start of the frame'}), lit rows copied into rank 0's frame image after the final pass (copy engine over NVLink, overlapping the next frame; the last frame's image is awaited inside the timed region)" if p2p else
-                               f"{world} row bands of {band} rows + {APRON}-row apron recomputed redundantly, one NCCL broadcast of VPL table + 5 cube maps, NCCL gather of lit bands"),
-                           "visible_vpls": V, "storage": "f16/unorm8 planes", "band_wait_timeouts": band_timeouts,
-                           "look_ahead": ("cull + colouring" + (" + table broadcast" if world > 1 else "") + " + cube-map refresh of frame i+1 on a second stream under frame i's denoise passes (sgi_early_begin / sgi_cull_early; the reference culls at BE:1395, long before the GI pass at BE:2043)") if use_early else "off: everything on one stream",
-                           "refreshed_cube_maps": ("rendered on the device every frame (sgi_render_vpl_cubemaps, 5 maps)" if device_maps else ("copied from the per-frame broadcast (5 maps)" if world > 1 else "resident (uploaded once)")),
-                           "image_equals_single_gpu": (image_equal or {}).get("equal"), "image_check": image_equal, "band_spin": band_spin,
-                           "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log,
-                           "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
+                "config": bench_config(scene, world, args),
+                "run": {"visible_vpls": V, "band_wait_timeouts": band_timeouts, "image_equals_single_gpu": (image_equal or {}).get("equal"),
+                        "image_check": image_equal, "band_spin": band_spin, "band_rows": [b.b1 - b.b0 for b in bands], "band_balancing": balance_log,
+                        "host_enqueue_ms_per_step": round(host_enqueue_ms, 4)},
+                "image_equals_single_gpu": (image_equal or {}).get("equal"),
                 "clocks": clocks,
                 "e2e": {"value": W * H * N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "how": "HostFramePipeline: pinned host -> device copy of the frame's G-buffer/VPL table/CSM/5 cube maps, sgi_frame, lit image -> pinned host, every step; 3 device slots overlap copies with the pass",
@@ -782,9 +812,7 @@ def run_views(args, rank, world, local_rank):
         ab = algorithmic_bytes(W * H, (W // 5) * (H // 5), N, V, iters)
         line = {"metric": METRIC, "value": world * W * H * N / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_text(scene), "l2": "inputs_exceed_l2 (per-frame working set > 126 MB)",
-                           "parallelism": f"{world} independent camera views, one whole view per GPU, no exchange (the batch axis of configs[4]); a step = one frame of every view",
-                           "visible_vpls_view0": V, "storage": "f16/unorm8 planes"},
+                "config": bench_config(scene, world, args), "run": {"visible_vpls_view0": V},
                 "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
                 "roofline": {"kernel": "frame", "bound": "hbm", "achieved": round(ab["frame"] / (ms_step * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                              "frac": round(ab["frame"] / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src,

@@ -133,3 +133,24 @@ def test_recompute_rows_cover_the_summed_reach_of_all_passes():
     assert [recompute_rows(i) for i in (1, 4, 5)] == [0, 30, 60]
     bands = plan_bands(2160, 8, recompute_rows(4))
     assert all(b.b0 - b.y0 in (0, 30) and (b.y0 + b.rows) - b.b1 in (0, 30) for b in bands)
+
+
+def test_both_bench_arms_print_the_same_config_object():
+    """bench.py: `config` is a function of the workload and the command line only, so `--impl reference` launched with the same flags
+    prints the same object as the CUDA arm (what a run measures or decides lives under `run`)."""
+    import argparse
+    import json
+    import bench
+    from stratusgfx_b200.scene import Scene
+    scene = Scene("c4")
+    for world in (1, 2, 8):
+        for bands in ("recompute", "p2p", "apron"):
+            for split in ("bands", "views"):
+                args = argparse.Namespace(gpus=world, bands=bands, split=split, maps="broadcast", no_early=False, no_prefetch=False, balance=2)
+                cfg = bench.bench_config(scene, world, args)
+                assert cfg == bench.bench_config(scene, max(args.gpus, 1), args)
+                assert cfg["workload"].startswith("c4: 3840x2160") and "parallelism" in cfg
+                json.dumps(cfg)
+                assert not any(k in cfg for k in ("visible_vpls", "band_rows", "sample", "image_check"))
+    assert bench.bench_config(scene, 1, args)["parallelism"] == "single GPU"
+    assert "28-row halos" not in bench.bench_config(scene, 8, argparse.Namespace(gpus=8, bands="p2p", split="bands", maps="device", no_early=True, no_prefetch=True, balance=0))["parallelism"]

@@ -19,7 +19,7 @@ for f,g in (("$out/bench_1.json",1),("$out/bench_${n}_recompute.json",$n),("$out
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         if base is None: base=d["ms_per_step"]
-        c=d["config"]
+        c=d.get("run", d["config"])      # (bench lines before the end of round 2 kept these under "config")
         print(f.split("/")[-1], "ms", round(d["ms_per_step"],4), "eff", round(base/d["ms_per_step"]/g,3), "e2e", round(d["e2e"]["ms_per_step"],3), "rows", c["band_rows"], "timeouts", c["band_wait_timeouts"], "equal", c["image_equals_single_gpu"])
         print("   stages", {k: v["ms"] for k,v in d["stages"].items()})
     except Exception as e:

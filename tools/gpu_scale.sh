@@ -26,7 +26,7 @@ for g in (1,2,4,8):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         if base is None: base=d["ms_per_step"]
-        print("n", d["n_gpus"], "ms", round(d["ms_per_step"],4), "speedup", round(base/d["ms_per_step"],2), "eff", round(base/d["ms_per_step"]/g,3), "e2e_ms", round(d["e2e"]["ms_per_step"],3), "rows", d["config"]["band_rows"], "timeouts", d["config"]["band_wait_timeouts"])
+        print("n", d["n_gpus"], "ms", round(d["ms_per_step"],4), "speedup", round(base/d["ms_per_step"],2), "eff", round(base/d["ms_per_step"]/g,3), "e2e_ms", round(d["e2e"]["ms_per_step"],3), "rows", d.get("run", d["config"])["band_rows"], "timeouts", d.get("run", d["config"])["band_wait_timeouts"])
         print("   stages", {k: v["ms"] for k,v in d["stages"].items()})
     except Exception as e:
         print(f, "unreadable", e)
