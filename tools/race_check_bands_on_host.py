@@ -10,6 +10,7 @@ ThreadSanitizer reports any pair of accesses the protocol does not order — a m
 stores, a halo overwritten while the neighbour may still read it.
 
     python tools/race_check_bands_on_host.py [bands=4] [kernel|host] [exchange|recompute] [nowait]      # re-executes itself under LD_PRELOAD=libtsan.so
+    (SGI_TSAN_EXTRA=":verbosity=2" is appended to the child's TSAN_OPTIONS)
 
 `recompute` = SGI_HALO_RECOMPUTE: the bands compute the non-final passes on their halo rows themselves; what is left to order is the
 final pass's GI rows (stored into the neighbours, read by their temporal pre-pass of the next frame, overwritten two frames later),
@@ -46,7 +47,7 @@ def main():
                              extra=("-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=thread", "-fno-gnu-unique"))
         rt = subprocess.check_output(["gcc", "-print-file-name=libtsan.so"], text=True).strip()
         env = dict(os.environ, SGI_TSAN_CHILD="1", LD_PRELOAD=rt, OMP_NUM_THREADS="1", SGI_BANDS_TSAN_LIB=so,
-                   TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=4")
+                   TSAN_OPTIONS="halt_on_error=1:report_signal_unsafe=0:history_size=4" + os.environ.get("SGI_TSAN_EXTRA", ""))
         rc = subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env)
         print("exit code", rc, "(a ThreadSanitizer report ends the run with a non-zero code)")
         return rc
